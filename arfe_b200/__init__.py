@@ -1,0 +1,17 @@
+"""arfe_b200 -- B200 (sm_100a) implementation of ARFE's region-aware feature
+path: AR-FPN aggregation (WFPNDualSpatial) and AR-RFF RoI fusion
+(SingleRoIExtractor x 3 regions + MultiRoIsBBoxHead gate), behind the
+reference's module/operator surface.  Compute lives in libarfe_b200.so
+(C ABI: include/arfe_b200.h); there is no CPU fallback.
+"""
+from ._compat import ConvModule, register_into_mmdet  # noqa: F401
+from .bbox_head import MultiBBoxHead, MultiRoIsBBoxHead  # noqa: F401
+from .functional import (fpn_apply, fpn_gather, rff_gate, roi_fuse,  # noqa: F401
+                         roi_fuse_debug, split3)
+from .neck import NonLocal2D, WFPNDualSpatial  # noqa: F401
+from .regions import get_adaptive_scale_rois  # noqa: F401
+from .roi_align import RoIAlign, RoIAlignFunction, roi_align  # noqa: F401
+from .roi_extractor import SingleRoIExtractor  # noqa: F401
+from .roi_head import CascadeRoIHead, StandardRoIHead  # noqa: F401
+
+__version__ = "0.1.0"

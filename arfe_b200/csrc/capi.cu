@@ -1,0 +1,290 @@
+// extern "C" surface of libarfe_b200.so (declared in include/arfe_b200.h):
+// argument validation, error strings, parameter packing.  No allocation, no
+// synchronisation, no global mutable state except the thread-local message.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/arfe_b200.h"
+#include "launch.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_result(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return ARFE_OK;
+  snprintf(g_err, sizeof(g_err), "%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+  return (int)e;
+}
+
+bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+size_t esize(int dtype) { return dtype == ARFE_F32 ? 4 : 2; }
+
+#define REQUIRE(cond, code, ...) \
+  do { if (!(cond)) return fail(code, __VA_ARGS__); } while (0)
+
+int check_common(const char* fn, int L, int B, int C, const int32_t* H, const int32_t* W,
+                 int dtype, int layout) {
+  REQUIRE(L >= 1 && L <= ARFE_MAX_LEVELS, ARFE_E_SHAPE, "%s: L=%d outside [1,%d]", fn, L, ARFE_MAX_LEVELS);
+  REQUIRE(B >= 0 && C >= 1, ARFE_E_SHAPE, "%s: bad B=%d / C=%d", fn, B, C);
+  REQUIRE(H && W, ARFE_E_NULL, "%s: H/W is NULL", fn);
+  for (int l = 0; l < L; ++l)
+    REQUIRE(H[l] >= 1 && W[l] >= 1, ARFE_E_SHAPE, "%s: level %d has size %dx%d", fn, l, H[l], W[l]);
+  REQUIRE(dtype == ARFE_F32 || dtype == ARFE_BF16, ARFE_E_ENUM, "%s: unknown dtype %d", fn, dtype);
+  REQUIRE(layout == ARFE_NCHW || layout == ARFE_NHWC, ARFE_E_ENUM, "%s: unknown layout %d", fn, layout);
+  return ARFE_OK;
+}
+
+int fill_roi_params(const char* fn, arfe::RoiFuseParams& p, const int32_t* H, const int32_t* W,
+                    const float* spatial_scale, int L, int B, int C, const float* rois, int K,
+                    int regions, float facs, int PH, int PW, int sampling_ratio,
+                    float finest_scale, int dtype, int layout) {
+  int rc = check_common(fn, L, B, C, H, W, dtype, layout);
+  if (rc) return rc;
+  REQUIRE(spatial_scale, ARFE_E_NULL, "%s: spatial_scale is NULL", fn);
+  REQUIRE(K >= 0, ARFE_E_SHAPE, "%s: K=%d", fn, K);
+  REQUIRE(K == 0 || rois, ARFE_E_NULL, "%s: rois is NULL", fn);
+  REQUIRE(regions == 1 || regions == 3, ARFE_E_ENUM, "%s: regions must be 1 or 3, got %d", fn, regions);
+  REQUIRE(PH >= 1 && PH <= ARFE_MAX_POOL && PW >= 1 && PW <= ARFE_MAX_POOL, ARFE_E_SHAPE,
+          "%s: pooled size %dx%d outside [1,%d]", fn, PH, PW, ARFE_MAX_POOL);
+  REQUIRE(sampling_ratio >= 0, ARFE_E_SHAPE, "%s: sampling_ratio=%d", fn, sampling_ratio);
+  REQUIRE(finest_scale > 0.f, ARFE_E_SHAPE, "%s: finest_scale must be > 0", fn);
+  REQUIRE((long long)K * regions < (1ll << 31), ARFE_E_SHAPE, "%s: K*regions too large", fn);
+  memset(&p, 0, sizeof(p));
+  for (int l = 0; l < L; ++l) { p.H[l] = H[l]; p.W[l] = W[l]; p.scale[l] = spatial_scale[l]; }
+  p.L = L; p.B = B; p.C = C; p.K = K; p.R = regions; p.PH = PH; p.PW = PW;
+  p.sampling_ratio = sampling_ratio; p.facs = facs; p.finest_scale = finest_scale;
+  p.rois = rois;
+  return ARFE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int arfe_version(void) { return ARFE_VERSION; }
+const char* arfe_last_error(void) { return g_err; }
+
+int arfe_roi_fuse_forward(const void* const* feats, const int32_t* H, const int32_t* W,
+                          const float* spatial_scale, int L, int B, int C, const float* rois,
+                          int K, int regions, float facs, int PH, int PW, int sampling_ratio,
+                          float finest_scale, int dtype, int layout, void* out,
+                          int32_t* lvl_out, float* boxes_out, void* stream) {
+  const char* fn = "arfe_roi_fuse_forward";
+  arfe::RoiFuseParams p;
+  int rc = fill_roi_params(fn, p, H, W, spatial_scale, L, B, C, rois, K, regions, facs, PH, PW,
+                           sampling_ratio, finest_scale, dtype, layout);
+  if (rc) return rc;
+  if (K == 0) return ARFE_OK;
+  REQUIRE(feats && out, ARFE_E_NULL, "%s: feats/out is NULL", fn);
+  REQUIRE(B >= 1, ARFE_E_SHAPE, "%s: B=0 with K>0", fn);
+  for (int l = 0; l < L; ++l) {
+    REQUIRE(feats[l], ARFE_E_NULL, "%s: feats[%d] is NULL", fn, l);
+    REQUIRE(aligned(feats[l], esize(dtype)), ARFE_E_ALIGN, "%s: feats[%d] misaligned", fn, l);
+    p.feats[l] = feats[l];
+  }
+  REQUIRE(aligned(out, esize(dtype)) && aligned(rois, 4), ARFE_E_ALIGN, "%s: out/rois misaligned", fn);
+  p.out = out; p.lvl_out = lvl_out; p.boxes_out = boxes_out;
+  return cuda_result(arfe::launch_roi_fuse_forward(p, dtype, layout, (cudaStream_t)stream), fn);
+}
+
+int arfe_roi_fuse_backward(const void* dout, const int32_t* H, const int32_t* W,
+                           const float* spatial_scale, int L, int B, int C, const float* rois,
+                           int K, int regions, float facs, int PH, int PW, int sampling_ratio,
+                           float finest_scale, int dtype, int layout, float* const* dfeats,
+                           void* stream) {
+  const char* fn = "arfe_roi_fuse_backward";
+  arfe::RoiFuseParams p;
+  int rc = fill_roi_params(fn, p, H, W, spatial_scale, L, B, C, rois, K, regions, facs, PH, PW,
+                           sampling_ratio, finest_scale, dtype, layout);
+  if (rc) return rc;
+  if (K == 0) return ARFE_OK;
+  REQUIRE(dout && dfeats, ARFE_E_NULL, "%s: dout/dfeats is NULL", fn);
+  REQUIRE(B >= 1, ARFE_E_SHAPE, "%s: B=0 with K>0", fn);
+  for (int l = 0; l < L; ++l) {
+    REQUIRE(dfeats[l], ARFE_E_NULL, "%s: dfeats[%d] is NULL", fn, l);
+    REQUIRE(aligned(dfeats[l], 4), ARFE_E_ALIGN, "%s: dfeats[%d] misaligned", fn, l);
+    p.dfeats[l] = dfeats[l];
+  }
+  p.dout = dout;
+  return cuda_result(arfe::launch_roi_fuse_backward(p, dtype, layout, (cudaStream_t)stream), fn);
+}
+
+int arfe_roi_align_forward(const void* input, const float* rois, float spatial_scale,
+                           int pooled_height, int pooled_width, int sampling_ratio, int aligned_,
+                           int B, int C, int H, int W, int K, int dtype, int layout,
+                           void* output, void* stream) {
+  REQUIRE(aligned_ == 1, ARFE_E_UNSUPPORTED,
+          "arfe_roi_align_forward: aligned=False (legacy v1 RoIAlign) is not implemented");
+  const void* feats[1] = {input};
+  const int32_t h[1] = {H}, w[1] = {W};
+  const float s[1] = {spatial_scale};
+  return arfe_roi_fuse_forward(feats, h, w, s, 1, B, C, rois, K, 1, 1.0f, pooled_height,
+                               pooled_width, sampling_ratio, 56.0f, dtype, layout, output,
+                               nullptr, nullptr, stream);
+}
+
+int arfe_roi_align_backward(const void* grad, const float* rois, float spatial_scale,
+                            int pooled_height, int pooled_width, int B, int C, int H, int W,
+                            int K, int sampling_ratio, int aligned_, int dtype, int layout,
+                            float* grad_input, void* stream) {
+  REQUIRE(aligned_ == 1, ARFE_E_UNSUPPORTED,
+          "arfe_roi_align_backward: aligned=False (legacy v1 RoIAlign) is not implemented");
+  float* dfeats[1] = {grad_input};
+  const int32_t h[1] = {H}, w[1] = {W};
+  const float s[1] = {spatial_scale};
+  return arfe_roi_fuse_backward(grad, h, w, s, 1, B, C, rois, K, 1, 1.0f, pooled_height,
+                                pooled_width, sampling_ratio, 56.0f, dtype, layout, dfeats, stream);
+}
+
+int arfe_roi_fuse_taps(const int32_t* H, const int32_t* W, const float* spatial_scale, int L,
+                       const float* rois, int K, int regions, float facs, int PH, int PW,
+                       int sampling_ratio, float finest_scale, int max_grid, int32_t* lvl,
+                       int32_t* grid, float* boxes, int32_t* ylo, int32_t* yhi, float* ywl,
+                       float* ywh, int32_t* xlo, int32_t* xhi, float* xwl, float* xwh,
+                       void* stream) {
+  const char* fn = "arfe_roi_fuse_taps";
+  arfe::RoiFuseParams p;
+  int rc = fill_roi_params(fn, p, H, W, spatial_scale, L, 1, 1, rois, K, regions, facs, PH, PW,
+                           sampling_ratio, finest_scale, ARFE_F32, ARFE_NCHW);
+  if (rc) return rc;
+  if (K == 0) return ARFE_OK;
+  REQUIRE(max_grid >= 1, ARFE_E_SHAPE, "%s: max_grid=%d", fn, max_grid);
+  REQUIRE((ylo == nullptr) == (yhi == nullptr) && (ylo == nullptr) == (ywl == nullptr) &&
+              (ylo == nullptr) == (ywh == nullptr) && (xlo == nullptr) == (xhi == nullptr) &&
+              (xlo == nullptr) == (xwl == nullptr) && (xlo == nullptr) == (xwh == nullptr),
+          ARFE_E_NULL, "%s: tap outputs must be given per axis as a complete set", fn);
+  return cuda_result(arfe::launch_roi_fuse_taps(p, max_grid, lvl, grid, boxes, ylo, yhi, ywl, ywh,
+                                                xlo, xhi, xwl, xwh, (cudaStream_t)stream), fn);
+}
+
+int arfe_rff_gate_forward(const void* ori, int64_t ori_roi_stride, const void* a, const void* b,
+                          void* out, int64_t K, int64_t n_per_roi, int dtype, void* stream) {
+  const char* fn = "arfe_rff_gate_forward";
+  REQUIRE(dtype == ARFE_F32 || dtype == ARFE_BF16, ARFE_E_ENUM, "%s: unknown dtype %d", fn, dtype);
+  REQUIRE(K >= 0 && n_per_roi >= 1 && ori_roi_stride >= n_per_roi, ARFE_E_SHAPE,
+          "%s: bad K=%lld n=%lld stride=%lld", fn, (long long)K, (long long)n_per_roi, (long long)ori_roi_stride);
+  if (K == 0) return ARFE_OK;
+  REQUIRE(ori && a && b && out, ARFE_E_NULL, "%s: NULL tensor", fn);
+  REQUIRE(n_per_roi < (1ll << 31), ARFE_E_SHAPE, "%s: n_per_roi too large", fn);
+  return cuda_result(arfe::launch_rff_gate_forward(ori, ori_roi_stride, a, b, out, K, n_per_roi,
+                                                   dtype, (cudaStream_t)stream), fn);
+}
+
+int arfe_rff_gate_backward(const void* g, const void* ori, int64_t ori_roi_stride, const void* a,
+                           const void* b, void* d_ori, void* d_ab, int64_t K, int64_t n_per_roi,
+                           int dtype, void* stream) {
+  const char* fn = "arfe_rff_gate_backward";
+  REQUIRE(dtype == ARFE_F32 || dtype == ARFE_BF16, ARFE_E_ENUM, "%s: unknown dtype %d", fn, dtype);
+  REQUIRE(K >= 0 && n_per_roi >= 1 && ori_roi_stride >= n_per_roi, ARFE_E_SHAPE,
+          "%s: bad K=%lld n=%lld stride=%lld", fn, (long long)K, (long long)n_per_roi, (long long)ori_roi_stride);
+  if (K == 0) return ARFE_OK;
+  REQUIRE(g && ori && a && b && d_ori && d_ab, ARFE_E_NULL, "%s: NULL tensor", fn);
+  REQUIRE(n_per_roi < (1ll << 31), ARFE_E_SHAPE, "%s: n_per_roi too large", fn);
+  return cuda_result(arfe::launch_rff_gate_backward(g, ori, ori_roi_stride, a, b, d_ori, d_ab, K,
+                                                    n_per_roi, dtype, (cudaStream_t)stream), fn);
+}
+
+static int fill_fpn(const char* fn, arfe::FpnParams& p, const int32_t* H, const int32_t* W, int L,
+                    int B, int C, int dtype, int layout) {
+  int rc = check_common(fn, L, B, C, H, W, dtype, layout);
+  if (rc) return rc;
+  memset(&p, 0, sizeof(p));
+  for (int l = 0; l < L; ++l) { p.H[l] = H[l]; p.W[l] = W[l]; }
+  p.L = L; p.B = B; p.C = C;
+  return ARFE_OK;
+}
+
+int arfe_fpn_gather_forward(const void* const* feats, const int32_t* H, const int32_t* W, int L,
+                            int B, int C, int refine_level, int dtype, int layout, void* out,
+                            uint8_t* argmax, void* stream) {
+  const char* fn = "arfe_fpn_gather_forward";
+  arfe::FpnParams p;
+  int rc = fill_fpn(fn, p, H, W, L, B, C, dtype, layout);
+  if (rc) return rc;
+  REQUIRE(refine_level >= 0 && refine_level < L, ARFE_E_SHAPE, "%s: refine_level=%d", fn, refine_level);
+  if (B == 0) return ARFE_OK;
+  REQUIRE(feats && out, ARFE_E_NULL, "%s: feats/out is NULL", fn);
+  p.refine_level = refine_level; p.Hr = H[refine_level]; p.Wr = W[refine_level];
+  for (int l = 0; l < L; ++l) {
+    REQUIRE(feats[l], ARFE_E_NULL, "%s: feats[%d] is NULL", fn, l);
+    p.feats[l] = feats[l];
+    if (l < refine_level) {
+      const long long kh = (H[l] + p.Hr - 1) / p.Hr + 1, kw = (W[l] + p.Wr - 1) / p.Wr + 1;
+      REQUIRE(argmax == nullptr || kh * kw <= 255, ARFE_E_UNSUPPORTED,
+              "%s: pooling window of level %d too large for uint8 argmax", fn, l);
+    }
+  }
+  p.gathered = out; p.argmax = argmax;
+  return cuda_result(arfe::launch_fpn_gather_forward(p, dtype, layout, (cudaStream_t)stream), fn);
+}
+
+int arfe_fpn_gather_backward(const void* dout, const uint8_t* argmax, const int32_t* H,
+                             const int32_t* W, int L, int B, int C, int refine_level, int dtype,
+                             int layout, void* const* dfeats, void* stream) {
+  const char* fn = "arfe_fpn_gather_backward";
+  arfe::FpnParams p;
+  int rc = fill_fpn(fn, p, H, W, L, B, C, dtype, layout);
+  if (rc) return rc;
+  REQUIRE(refine_level >= 0 && refine_level < L, ARFE_E_SHAPE, "%s: refine_level=%d", fn, refine_level);
+  if (B == 0) return ARFE_OK;
+  REQUIRE(dout && dfeats, ARFE_E_NULL, "%s: dout/dfeats is NULL", fn);
+  REQUIRE(refine_level == 0 || argmax, ARFE_E_NULL, "%s: argmax is NULL", fn);
+  p.refine_level = refine_level; p.Hr = H[refine_level]; p.Wr = W[refine_level];
+  for (int l = 0; l < L; ++l) {
+    REQUIRE(dfeats[l], ARFE_E_NULL, "%s: dfeats[%d] is NULL", fn, l);
+    p.outs[l] = dfeats[l];
+  }
+  p.gathered = const_cast<void*>(dout); p.argmax = const_cast<uint8_t*>(argmax);
+  return cuda_result(arfe::launch_fpn_gather_backward(p, dtype, layout, (cudaStream_t)stream), fn);
+}
+
+int arfe_fpn_apply_forward(const void* const* feats, const void* bsf, const void* const* g1,
+                           const void* const* g2, const int32_t* H, const int32_t* W, int L, int B,
+                           int C, int Hr, int Wr, int dtype, int layout, void* const* outs,
+                           void* stream) {
+  const char* fn = "arfe_fpn_apply_forward";
+  arfe::FpnParams p;
+  int rc = fill_fpn(fn, p, H, W, L, B, C, dtype, layout);
+  if (rc) return rc;
+  REQUIRE(Hr >= 1 && Wr >= 1, ARFE_E_SHAPE, "%s: bsf size %dx%d", fn, Hr, Wr);
+  if (B == 0) return ARFE_OK;
+  REQUIRE(feats && bsf && g1 && g2 && outs, ARFE_E_NULL, "%s: NULL argument", fn);
+  for (int l = 0; l < L; ++l) {
+    REQUIRE(feats[l] && g1[l] && g2[l] && outs[l], ARFE_E_NULL, "%s: NULL tensor at level %d", fn, l);
+    p.feats[l] = feats[l]; p.g1[l] = g1[l]; p.g2[l] = g2[l]; p.outs[l] = outs[l];
+  }
+  p.bsf = bsf; p.Hr = Hr; p.Wr = Wr;
+  return cuda_result(arfe::launch_fpn_apply_forward(p, dtype, layout, (cudaStream_t)stream), fn);
+}
+
+int arfe_fpn_apply_backward(const void* const* douts, const void* bsf, const void* const* g1,
+                            const void* const* g2, const int32_t* H, const int32_t* W, int L,
+                            int B, int C, int Hr, int Wr, int dtype, int layout, float* dbsf,
+                            float* const* dg1, float* const* dg2, void* stream) {
+  const char* fn = "arfe_fpn_apply_backward";
+  arfe::FpnParams p;
+  int rc = fill_fpn(fn, p, H, W, L, B, C, dtype, layout);
+  if (rc) return rc;
+  REQUIRE(Hr >= 1 && Wr >= 1, ARFE_E_SHAPE, "%s: bsf size %dx%d", fn, Hr, Wr);
+  if (B == 0) return ARFE_OK;
+  REQUIRE(douts && bsf && g1 && g2 && dbsf && dg1 && dg2, ARFE_E_NULL, "%s: NULL argument", fn);
+  for (int l = 0; l < L; ++l) {
+    REQUIRE(douts[l] && g1[l] && g2[l] && dg1[l] && dg2[l], ARFE_E_NULL, "%s: NULL tensor at level %d", fn, l);
+    p.feats[l] = douts[l]; p.g1[l] = g1[l]; p.g2[l] = g2[l]; p.dg1[l] = dg1[l]; p.dg2[l] = dg2[l];
+  }
+  p.bsf = bsf; p.Hr = Hr; p.Wr = Wr; p.dbsf = dbsf;
+  return cuda_result(arfe::launch_fpn_apply_backward(p, dtype, layout, (cudaStream_t)stream), fn);
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+// Internal launcher interface between capi.cu (argument validation, C ABI) and
+// the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace arfe {
+
+constexpr int kMaxLevels = 8;  // == ARFE_MAX_LEVELS
+constexpr int kMaxPool = 32;   // == ARFE_MAX_POOL
+
+struct RoiFuseParams {
+  const void* feats[kMaxLevels];  // forward: pyramid
+  float* dfeats[kMaxLevels];      // backward: gradient pyramid (accumulated)
+  int H[kMaxLevels], W[kMaxLevels];
+  float scale[kMaxLevels];
+  int L, B, C, K, R, PH, PW, sampling_ratio;
+  float facs, finest_scale;
+  const float* rois;
+  void* out;         // forward output
+  const void* dout;  // backward input
+  int32_t* lvl_out;
+  float* boxes_out;
+};
+
+cudaError_t launch_roi_fuse_forward(const RoiFuseParams& p, int dtype, int layout,
+                                    cudaStream_t stream);
+cudaError_t launch_roi_fuse_backward(const RoiFuseParams& p, int dtype, int layout,
+                                     cudaStream_t stream);
+cudaError_t launch_roi_fuse_taps(const RoiFuseParams& p, int max_grid, int32_t* lvl,
+                                 int32_t* grid, float* boxes, int32_t* ylo,
+                                 int32_t* yhi, float* ywl, float* ywh, int32_t* xlo,
+                                 int32_t* xhi, float* xwl, float* xwh,
+                                 cudaStream_t stream);
+
+cudaError_t launch_rff_gate_forward(const void* ori, int64_t ori_stride,
+                                    const void* a, const void* b, void* out,
+                                    int64_t K, int64_t n, int dtype,
+                                    cudaStream_t stream);
+cudaError_t launch_rff_gate_backward(const void* g, const void* ori,
+                                     int64_t ori_stride, const void* a,
+                                     const void* b, void* d_ori, void* d_ab,
+                                     int64_t K, int64_t n, int dtype,
+                                     cudaStream_t stream);
+
+struct FpnParams {
+  const void* feats[kMaxLevels];  // x_l (gather fwd / apply fwd) or dout_l (apply bwd)
+  void* outs[kMaxLevels];         // out_l (apply fwd) or dx_l (gather bwd)
+  const void* g1[kMaxLevels];
+  const void* g2[kMaxLevels];
+  float* dg1[kMaxLevels];
+  float* dg2[kMaxLevels];
+  int H[kMaxLevels], W[kMaxLevels];
+  int L, B, C, refine_level, Hr, Wr;
+  const void* bsf;        // apply: [B,C,Hr,Wr]
+  void* gathered;         // gather fwd out / gather bwd dout
+  uint8_t* argmax;        // gather
+  float* dbsf;            // apply bwd
+};
+
+cudaError_t launch_fpn_gather_forward(const FpnParams& p, int dtype, int layout,
+                                      cudaStream_t stream);
+cudaError_t launch_fpn_gather_backward(const FpnParams& p, int dtype, int layout,
+                                       cudaStream_t stream);
+cudaError_t launch_fpn_apply_forward(const FpnParams& p, int dtype, int layout,
+                                     cudaStream_t stream);
+cudaError_t launch_fpn_apply_backward(const FpnParams& p, int dtype, int layout,
+                                      cudaStream_t stream);
+
+}  // namespace arfe

@@ -1,0 +1,375 @@
+"""torch.autograd Functions over the C ABI (include/arfe_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the stream, the math runs
+in libarfe_b200.so.  Every op raises on non-CUDA tensors.
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+from torch.nn.modules.utils import _pair
+
+from . import _lib as L
+
+
+def _prep_feats(feats):
+    """Bring all levels to one dtype/layout (the first level's)."""
+    L.require_cuda(*feats)
+    layout = L.layout_of(feats[0])
+    return [L.as_layout(f, layout) for f in feats], layout, L.dtype_code(feats[0])
+
+
+def _zeros(shape, dtype, device, layout):
+    mf = torch.channels_last if layout == L.ARFE_NHWC else torch.contiguous_format
+    return torch.empty(shape, dtype=dtype, device=device, memory_format=mf).zero_()
+
+
+def _prep_rois(rois):
+    L.require_cuda(rois)
+    if rois.dim() != 2 or rois.size(1) != 5:
+        raise AssertionError("rois must be [K, 5] = (batch_idx, x1, y1, x2, y2)")
+    return rois.detach().float().contiguous()
+
+
+class _RoIFuseFunction(Function):
+    """Fused region generation + level map + multi-level RoIAlign (+ cat).
+
+    regions=1 reproduces SingleRoIExtractor.forward
+    (roi_extractors/single_level.py:109-152); regions=3 reproduces the AR-RFF
+    block of StandardRoIHead._bbox_forward (standard_roi_head.py:138-155).
+    """
+
+    @staticmethod
+    def forward(ctx, rois, out_size, spatial_scales, sample_num, regions, facs,
+                finest_scale, *feats):
+        oh, ow = _pair(out_size)
+        feats, layout, dt = _prep_feats(feats)
+        rois = _prep_rois(rois)
+        B, C = feats[0].shape[:2]
+        Hs = [f.shape[2] for f in feats]
+        Ws = [f.shape[3] for f in feats]
+        K = rois.size(0)
+        out = feats[0].new_empty((K, regions * C, oh, ow))
+        ctx.meta = (oh, ow, tuple(spatial_scales), sample_num, regions, facs,
+                    finest_scale, layout, dt, B, C, Hs, Ws, feats[0].dtype)
+        ctx.save_for_backward(rois)
+        if K > 0:
+            rc = L.lib().arfe_roi_fuse_forward(
+                L.ptr_array(feats), L.int_array(Hs), L.int_array(Ws),
+                L.float_array(spatial_scales), len(feats), B, C, rois.data_ptr(),
+                K, regions, float(facs), oh, ow, int(sample_num),
+                float(finest_scale), dt, layout, out.data_ptr(), None, None,
+                L.stream_ptr(out.device))
+            L.check(rc, "arfe_roi_fuse_forward")
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        (rois,) = ctx.saved_tensors
+        (oh, ow, scales, sample_num, regions, facs, finest_scale, layout, dt, B,
+         C, Hs, Ws, fdtype) = ctx.meta
+        nlev = len(Hs)
+        if not any(ctx.needs_input_grad[7:]):
+            return (None,) * (7 + nlev)
+        dfeats = [_zeros((B, C, Hs[l], Ws[l]), torch.float32, grad_out.device, layout)
+                  for l in range(nlev)]
+        K = rois.size(0)
+        if K > 0:
+            g = grad_out.contiguous()
+            if g.dtype != fdtype:
+                g = g.to(fdtype)
+            rc = L.lib().arfe_roi_fuse_backward(
+                g.data_ptr(), L.int_array(Hs), L.int_array(Ws),
+                L.float_array(scales), nlev, B, C, rois.data_ptr(), K, regions,
+                float(facs), oh, ow, int(sample_num), float(finest_scale), dt,
+                layout, L.ptr_array(dfeats), L.stream_ptr(g.device))
+            L.check(rc, "arfe_roi_fuse_backward")
+        grads = tuple(d if fdtype == torch.float32 else d.to(fdtype) for d in dfeats)
+        return (None,) * 7 + grads
+
+
+def roi_fuse(feats, rois, out_size, spatial_scales, sample_num=0, regions=3,
+             facs=1.0, finest_scale=56):
+    """[K, regions*C, oh, ow]; channel blocks (ori, lw, lh) when regions=3."""
+    return _RoIFuseFunction.apply(rois, out_size, tuple(spatial_scales),
+                                  sample_num, regions, facs, finest_scale,
+                                  *feats)
+
+
+def roi_fuse_debug(rois, Hs, Ws, spatial_scales, out_size=7, sample_num=0,
+                   regions=3, facs=1.0, finest_scale=56, max_grid=16):
+    """Boxes, levels, grids and bilinear taps exactly as the kernels compute
+    them (arfe_roi_fuse_taps) -- parity instrumentation."""
+    oh, ow = _pair(out_size)
+    rois = _prep_rois(rois)
+    dev = rois.device
+    K, R = rois.size(0), regions
+    i32 = dict(dtype=torch.int32, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    o = dict(
+        lvl=torch.zeros((R, K), **i32), grid=torch.zeros((R, K, 2), **i32),
+        boxes=torch.zeros((R, K, 5), **f32),
+        ylo=torch.zeros((R, K, oh, max_grid), **i32), yhi=torch.zeros((R, K, oh, max_grid), **i32),
+        ywl=torch.zeros((R, K, oh, max_grid), **f32), ywh=torch.zeros((R, K, oh, max_grid), **f32),
+        xlo=torch.zeros((R, K, ow, max_grid), **i32), xhi=torch.zeros((R, K, ow, max_grid), **i32),
+        xwl=torch.zeros((R, K, ow, max_grid), **f32), xwh=torch.zeros((R, K, ow, max_grid), **f32))
+    if K > 0:
+        rc = L.lib().arfe_roi_fuse_taps(
+            L.int_array(Hs), L.int_array(Ws), L.float_array(spatial_scales),
+            len(Hs), rois.data_ptr(), K, R, float(facs), oh, ow, int(sample_num),
+            float(finest_scale), max_grid, o["lvl"].data_ptr(), o["grid"].data_ptr(),
+            o["boxes"].data_ptr(), o["ylo"].data_ptr(), o["yhi"].data_ptr(),
+            o["ywl"].data_ptr(), o["ywh"].data_ptr(), o["xlo"].data_ptr(),
+            o["xhi"].data_ptr(), o["xwl"].data_ptr(), o["xwh"].data_ptr(),
+            L.stream_ptr(dev))
+        L.check(rc, "arfe_roi_fuse_taps")
+    return o
+
+
+class RoIAlignFunction(Function):
+    """mmdet/ops/roi_align/roi_align.py:9-73 over arfe_roi_align_forward /
+    arfe_roi_align_backward (the twins of roi_align_ext.forward_v2/backward_v2)."""
+
+    @staticmethod
+    def forward(ctx, features, rois, out_size, spatial_scale, sample_num=0,
+                aligned=True):
+        out_h, out_w = _pair(out_size)
+        assert isinstance(out_h, int) and isinstance(out_w, int)
+        if not aligned:
+            raise NotImplementedError(
+                "aligned=False is the legacy v1 RoIAlign, which does not build "
+                "on current toolchains (SURVEY.md section 2); only aligned=True "
+                "is provided")
+        (features,), layout, dt = _prep_feats([features])
+        rois = _prep_rois(rois)
+        B, C, H, W = features.shape
+        K = rois.size(0)
+        out = features.new_empty((K, C, out_h, out_w))
+        ctx.meta = (out_h, out_w, float(spatial_scale), int(sample_num), layout,
+                    dt, (B, C, H, W), features.dtype)
+        ctx.save_for_backward(rois)
+        if K > 0:
+            rc = L.lib().arfe_roi_align_forward(
+                features.data_ptr(), rois.data_ptr(), float(spatial_scale), out_h,
+                out_w, int(sample_num), 1, B, C, H, W, K, dt, layout,
+                out.data_ptr(), L.stream_ptr(out.device))
+            L.check(rc, "arfe_roi_align_forward")
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        (rois,) = ctx.saved_tensors
+        out_h, out_w, scale, sample_num, layout, dt, (B, C, H, W), fdtype = ctx.meta
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None, None, None
+        grad_input = _zeros((B, C, H, W), torch.float32, grad_output.device, layout)
+        K = rois.size(0)
+        if K > 0:
+            g = grad_output.contiguous()
+            if g.dtype != fdtype:
+                g = g.to(fdtype)
+            rc = L.lib().arfe_roi_align_backward(
+                g.data_ptr(), rois.data_ptr(), scale, out_h, out_w, B, C, H, W, K,
+                sample_num, 1, dt, layout, grad_input.data_ptr(),
+                L.stream_ptr(g.device))
+            L.check(rc, "arfe_roi_align_backward")
+        if fdtype != torch.float32:
+            grad_input = grad_input.to(fdtype)
+        return grad_input, None, None, None, None, None
+
+
+roi_align = RoIAlignFunction.apply
+
+
+class _Split3(Function):
+    """x[:, :C], x[:, C:2C], x[:, 2C:] (multirois_bbox_head.py:167-169) whose
+    backward is ONE concatenation instead of three zero-filled full-size
+    gradients plus two additions."""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        ctx.c = c
+        ctx.shape = x.shape
+        return x[:, :c], x[:, c:2 * c], x[:, 2 * c:]
+
+    @staticmethod
+    def backward(ctx, g0, g1, g2):
+        c, shape = ctx.c, ctx.shape
+        ref = next(g for g in (g0, g1, g2) if g is not None)
+        parts = []
+        for g, n in ((g0, c), (g1, c), (g2, shape[1] - 2 * c)):
+            parts.append(g if g is not None else
+                         ref.new_zeros((shape[0], n) + tuple(shape[2:])))
+        return torch.cat(parts, dim=1), None
+
+
+def split3(x, c):
+    return _Split3.apply(x, c)
+
+
+class _RFFGateFunction(Function):
+    """out = ori + ori*(a+b), multirois_bbox_head.py:175,182."""
+
+    @staticmethod
+    def forward(ctx, ori, a, b):
+        L.require_cuda(ori, a, b)
+        dt = L.dtype_code(ori)
+        K = ori.size(0)
+        n = 1
+        for d in ori.shape[1:]:
+            n *= int(d)
+        # ori may be a channel slice of the concatenated tensor: rows strided
+        if K > 1 and not ori[0].is_contiguous():
+            ori = ori.contiguous()
+        stride = ori.stride(0) if K > 1 else n
+        if stride < n:
+            ori = ori.contiguous()
+            stride = n
+        a = a.contiguous()
+        b = b.contiguous()
+        out = torch.empty(ori.shape, dtype=ori.dtype, device=ori.device)
+        if K > 0:
+            rc = L.lib().arfe_rff_gate_forward(
+                ori.data_ptr(), stride, a.data_ptr(), b.data_ptr(),
+                out.data_ptr(), K, n, dt, L.stream_ptr(ori.device))
+            L.check(rc, "arfe_rff_gate_forward")
+        ctx.save_for_backward(ori, a, b)
+        ctx.meta = (stride, n, dt)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        ori, a, b = ctx.saved_tensors
+        stride, n, dt = ctx.meta
+        K = ori.size(0)
+        g = g.contiguous()
+        d_ori = torch.empty(ori.shape, dtype=ori.dtype, device=ori.device)
+        d_ab = torch.empty(ori.shape, dtype=ori.dtype, device=ori.device)
+        if K > 0:
+            rc = L.lib().arfe_rff_gate_backward(
+                g.data_ptr(), ori.data_ptr(), stride, a.data_ptr(), b.data_ptr(),
+                d_ori.data_ptr(), d_ab.data_ptr(), K, n, dt,
+                L.stream_ptr(g.device))
+            L.check(rc, "arfe_rff_gate_backward")
+        return d_ori, d_ab, d_ab
+
+
+def rff_gate(ori, a, b):
+    return _RFFGateFunction.apply(ori, a, b)
+
+
+class _FPNGatherFunction(Function):
+    """wfpn_dual_spatial.py:102-113."""
+
+    @staticmethod
+    def forward(ctx, refine_level, *feats):
+        feats, layout, dt = _prep_feats(feats)
+        B, C = feats[0].shape[:2]
+        Hs = [f.shape[2] for f in feats]
+        Ws = [f.shape[3] for f in feats]
+        Hr, Wr = Hs[refine_level], Ws[refine_level]
+        mf = torch.channels_last if layout == L.ARFE_NHWC else torch.contiguous_format
+        out = torch.empty((B, C, Hr, Wr), dtype=feats[0].dtype,
+                          device=feats[0].device, memory_format=mf)
+        need_grad = any(f.requires_grad for f in feats)
+        argmax = None
+        if need_grad and refine_level > 0:
+            argmax = torch.empty((refine_level, B, C, Hr, Wr), dtype=torch.uint8,
+                                 device=out.device)
+        if B > 0:
+            rc = L.lib().arfe_fpn_gather_forward(
+                L.ptr_array(feats), L.int_array(Hs), L.int_array(Ws), len(feats),
+                B, C, refine_level, dt, layout, out.data_ptr(),
+                argmax.data_ptr() if argmax is not None else None,
+                L.stream_ptr(out.device))
+            L.check(rc, "arfe_fpn_gather_forward")
+        ctx.meta = (refine_level, layout, dt, B, C, Hs, Ws, feats[0].dtype)
+        if argmax is not None:
+            ctx.save_for_backward(argmax)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        refine_level, layout, dt, B, C, Hs, Ws, fdtype = ctx.meta
+        argmax = ctx.saved_tensors[0] if ctx.saved_tensors else None
+        mf = torch.channels_last if layout == L.ARFE_NHWC else torch.contiguous_format
+        g = L.as_layout(g.to(fdtype), layout)
+        dfeats = [torch.empty((B, C, Hs[l], Ws[l]), dtype=fdtype, device=g.device,
+                              memory_format=mf) for l in range(len(Hs))]
+        if B > 0:
+            rc = L.lib().arfe_fpn_gather_backward(
+                g.data_ptr(), argmax.data_ptr() if argmax is not None else None,
+                L.int_array(Hs), L.int_array(Ws), len(Hs), B, C, refine_level, dt,
+                layout, L.ptr_array(dfeats), L.stream_ptr(g.device))
+            L.check(rc, "arfe_fpn_gather_backward")
+        return (None,) + tuple(dfeats)
+
+
+def fpn_gather(feats, refine_level=2):
+    return _FPNGatherFunction.apply(refine_level, *feats)
+
+
+class _FPNApplyFunction(Function):
+    """wfpn_dual_spatial.py:118-135; args: bsf, then L feats, L g1, L g2."""
+
+    @staticmethod
+    def forward(ctx, nlev, bsf, *tensors):
+        feats, g1, g2 = tensors[:nlev], tensors[nlev:2 * nlev], tensors[2 * nlev:]
+        feats, layout, dt = _prep_feats(feats)
+        L.require_cuda(bsf, *g1, *g2)
+        bsf = L.as_layout(bsf.to(feats[0].dtype), layout)
+        g1 = [t.to(feats[0].dtype).contiguous() for t in g1]
+        g2 = [t.to(feats[0].dtype).contiguous() for t in g2]
+        B, C = feats[0].shape[:2]
+        Hs = [f.shape[2] for f in feats]
+        Ws = [f.shape[3] for f in feats]
+        Hr, Wr = bsf.shape[2:]
+        outs = [torch.empty_like(f) for f in feats]
+        if B > 0:
+            rc = L.lib().arfe_fpn_apply_forward(
+                L.ptr_array(feats), bsf.data_ptr(), L.ptr_array(g1), L.ptr_array(g2),
+                L.int_array(Hs), L.int_array(Ws), nlev, B, C, Hr, Wr, dt, layout,
+                L.ptr_array(outs), L.stream_ptr(bsf.device))
+            L.check(rc, "arfe_fpn_apply_forward")
+        ctx.meta = (nlev, layout, dt, B, C, Hs, Ws, Hr, Wr, feats[0].dtype)
+        ctx.save_for_backward(bsf, *g1, *g2)
+        return tuple(outs)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *douts):
+        nlev, layout, dt, B, C, Hs, Ws, Hr, Wr, fdtype = ctx.meta
+        saved = ctx.saved_tensors
+        bsf, g1, g2 = saved[0], saved[1:1 + nlev], saved[1 + nlev:]
+        dev = bsf.device
+        mf = torch.channels_last if layout == L.ARFE_NHWC else torch.contiguous_format
+        d = []
+        for l in range(nlev):
+            g = douts[l]
+            if g is None:
+                g = _zeros((B, C, Hs[l], Ws[l]), fdtype, dev, layout)
+            d.append(L.as_layout(g.to(fdtype), layout))
+        dbsf = torch.empty((B, C, Hr, Wr), dtype=torch.float32, device=dev,
+                           memory_format=mf)
+        dg1 = [torch.empty((B, 1, Hs[l], Ws[l]), dtype=torch.float32, device=dev)
+               for l in range(nlev)]
+        dg2 = [torch.empty_like(t) for t in dg1]
+        if B > 0:
+            rc = L.lib().arfe_fpn_apply_backward(
+                L.ptr_array(d), bsf.data_ptr(), L.ptr_array(list(g1)),
+                L.ptr_array(list(g2)), L.int_array(Hs), L.int_array(Ws), nlev, B,
+                C, Hr, Wr, dt, layout, dbsf.data_ptr(), L.ptr_array(dg1),
+                L.ptr_array(dg2), L.stream_ptr(dev))
+            L.check(rc, "arfe_fpn_apply_backward")
+        cast = (lambda t: t) if fdtype == torch.float32 else (lambda t: t.to(fdtype))
+        # d x_l = d out_l: the residual path is the identity, no copy is made
+        return (None, cast(dbsf)) + tuple(d) + tuple(cast(t) for t in dg1) + \
+            tuple(cast(t) for t in dg2)
+
+
+def fpn_apply(feats, bsf, g1, g2):
+    n = len(feats)
+    return _FPNApplyFunction.apply(n, bsf, *feats, *g1, *g2)

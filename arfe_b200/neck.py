@@ -1,0 +1,94 @@
+"""AR-FPN neck with the reference's surface and parameter names
+(mmdet/models/necks/wfpn_dual_spatial.py:10-137): reduce_convs.{i}.conv,
+reduce_convs2.{i}.conv, refine.{g,theta,phi,conv_out}.conv.
+
+The gather (all levels -> refine level, mean) and the gated residual
+``x + up(bsf) * (tanh(relu(c1)) + tanh(relu(c2)))`` run in libarfe_b200.so;
+the 256->1 3x3 gate convolutions and the NonLocal2D refine are dense
+contractions that stay on cuDNN/cuBLAS.
+"""
+import torch
+import torch.nn as nn
+
+from ._compat import ConvModule, xavier_init
+from .functional import fpn_apply, fpn_gather
+
+
+class NonLocal2D(nn.Module):
+    """mmdet/ops/non_local.py:6-105 (embedded gaussian / dot product).  Plain
+    PyTorch: out of the kernel scope of this tier ("next" row 1)."""
+
+    def __init__(self, in_channels, reduction=2, use_scale=True, conv_cfg=None,
+                 norm_cfg=None, mode='embedded_gaussian'):
+        super(NonLocal2D, self).__init__()
+        assert mode in ['embedded_gaussian', 'dot_product']
+        self.in_channels, self.reduction, self.use_scale = in_channels, reduction, use_scale
+        self.inter_channels = in_channels // reduction
+        self.mode = mode
+        self.g = ConvModule(in_channels, self.inter_channels, kernel_size=1, act_cfg=None)
+        self.theta = ConvModule(in_channels, self.inter_channels, kernel_size=1, act_cfg=None)
+        self.phi = ConvModule(in_channels, self.inter_channels, kernel_size=1, act_cfg=None)
+        self.conv_out = ConvModule(self.inter_channels, in_channels, kernel_size=1,
+                                   conv_cfg=conv_cfg, norm_cfg=norm_cfg, act_cfg=None)
+        self.init_weights()
+
+    def init_weights(self, std=0.01, zeros_init=True):
+        for m in [self.g, self.theta, self.phi]:
+            nn.init.normal_(m.conv.weight, 0, std)
+            nn.init.constant_(m.conv.bias, 0)
+        if zeros_init:
+            nn.init.constant_(self.conv_out.conv.weight, 0)
+        else:
+            nn.init.normal_(self.conv_out.conv.weight, 0, std)
+        nn.init.constant_(self.conv_out.conv.bias, 0)
+
+    def forward(self, x):
+        n, _, h, w = x.shape
+        g_x = self.g(x).reshape(n, self.inter_channels, -1).permute(0, 2, 1)
+        theta_x = self.theta(x).reshape(n, self.inter_channels, -1).permute(0, 2, 1)
+        phi_x = self.phi(x).reshape(n, self.inter_channels, -1)
+        pw = torch.matmul(theta_x, phi_x)
+        if self.mode == 'embedded_gaussian':
+            if self.use_scale:
+                pw = pw / theta_x.shape[-1] ** 0.5
+            pw = pw.softmax(dim=-1)
+        else:
+            pw = pw / pw.shape[-1]
+        y = torch.matmul(pw, g_x).permute(0, 2, 1).contiguous().reshape(
+            n, self.inter_channels, h, w)
+        return x + self.conv_out(y)
+
+
+class WFPNDualSpatial(nn.Module):
+
+    def __init__(self, in_channels, num_levels, refine_level=2, conv_cfg=None,
+                 norm_cfg=None):
+        super(WFPNDualSpatial, self).__init__()
+        self.in_channels = in_channels
+        self.num_levels = num_levels
+        self.conv_cfg = conv_cfg
+        self.norm_cfg = norm_cfg
+        self.refine_level = refine_level
+        self.reduce_convs = nn.ModuleList()
+        self.reduce_convs2 = nn.ModuleList()
+        for _ in range(num_levels):
+            for convs in (self.reduce_convs, self.reduce_convs2):
+                convs.append(ConvModule(in_channels, 1, 3, padding=1, conv_cfg=conv_cfg,
+                                        norm_cfg=norm_cfg, inplace=False))
+        self.refine = NonLocal2D(in_channels, reduction=1, use_scale=False,
+                                 conv_cfg=conv_cfg, norm_cfg=norm_cfg)
+
+    def init_weights(self):
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                xavier_init(m, distribution='uniform')
+
+    def forward(self, inputs):
+        assert len(inputs) == self.num_levels
+        ori_fe = fpn_gather(inputs, self.refine_level)
+        bsf = self.refine(ori_fe)
+        # pre-activation gate maps; relu (ConvModule's default act) + tanh + sum
+        # are fused into the apply kernel
+        g1 = [self.reduce_convs[i](inputs[i], activate=False) for i in range(self.num_levels)]
+        g2 = [self.reduce_convs2[i](inputs[i], activate=False) for i in range(self.num_levels)]
+        return tuple(fpn_apply(list(inputs), bsf, g1, g2))

@@ -1,0 +1,192 @@
+/*
+ * arfe_b200.h -- C ABI of libarfe_b200.so, the B200 (sm_100a) implementation of
+ * ARFE's region-aware feature path (AR-FPN aggregation + AR-RFF RoI fusion).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.
+ * Every entry point names the reference interface it replaces; paths are
+ * relative to the reference tree (Fanzhongjie/ARFE, an mmdetection 2.0 fork).
+ *
+ * Conventions:
+ *  - Every pointer marked "device" is a CUDA device pointer valid on the
+ *    current device.  The CALLER allocates every buffer; the library never
+ *    allocates, frees or retains a pointer.
+ *  - All work is enqueued on `stream` (a cudaStream_t passed as void*) and
+ *    the call returns immediately; nothing synchronises the host
+ *    (the reference blocks with cudaDeviceSynchronize() after every forward,
+ *    mmdet/ops/roi_align/src/cuda/roi_align_kernel_v2.cu:304).
+ *  - Return value: 0 = ok; negative = argument error (ARFE_E_*); positive =
+ *    the cudaError_t reported by the launch.  arfe_last_error() returns a
+ *    thread-local human-readable message for the last non-zero return.
+ *  - There is no CPU implementation behind these symbols.
+ *  - Tensors are dense and contiguous in the stated layout.
+ *      dtype : ARFE_F32 (float) or ARFE_BF16 (__nv_bfloat16); arithmetic and
+ *              accumulation are always fp32, box/level/index math is exact
+ *              fp32 in the reference's operation order.
+ *      layout: ARFE_NCHW (reference layout) or ARFE_NHWC (torch channels_last
+ *              memory format of the same logical NCHW tensor).
+ *  - RoIs are fp32 [K,5] = (batch_index, x1, y1, x2, y2) in image pixels
+ *    (mmdet/core/bbox/transforms.py:41-60).
+ */
+#ifndef ARFE_B200_H_
+#define ARFE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARFE_VERSION 100 /* 0.1.0 */
+#define ARFE_MAX_LEVELS 8
+#define ARFE_MAX_POOL 32 /* max pooled height / width */
+
+enum { ARFE_F32 = 0, ARFE_BF16 = 1 };
+enum { ARFE_NCHW = 0, ARFE_NHWC = 1 };
+
+enum {
+  ARFE_OK = 0,
+  ARFE_E_NULL = -1,   /* required pointer is NULL */
+  ARFE_E_SHAPE = -2,  /* negative / zero / too large dimension */
+  ARFE_E_ENUM = -3,   /* unknown dtype / layout / regions value */
+  ARFE_E_ALIGN = -4,  /* pointer not aligned for the element type */
+  ARFE_E_UNSUPPORTED = -5
+};
+
+int arfe_version(void);
+const char* arfe_last_error(void);
+
+/* ------------------------------------------------------------------------
+ * AR-RFF extraction: fused region generation + RoI->level map + multi-level
+ * RoIAlign, written straight into the concatenated tensor.
+ *
+ * Replaces, in one launch:
+ *   get_adaptive_scale_rois(rois, facs)        mmdet/models/utils/additional.py:38-71
+ *   SingleRoIExtractor.map_roi_levels          mmdet/models/roi_heads/roi_extractors/single_level.py:53-93
+ *   SingleRoIExtractor.forward  (x regions)    .../single_level.py:109-152
+ *   RoIAlign / roi_align_ext.forward_v2        mmdet/ops/roi_align/src/roi_align_ext.cpp:126-142
+ *   torch.cat([ori, lw, lh], dim=1)            mmdet/models/roi_heads/standard_roi_head.py:138-155
+ *
+ * regions = 1: out[K, C, PH, PW]      (plain SingleRoIExtractor.forward)
+ * regions = 3: out[K, 3*C, PH, PW]    channels [0,C) original box, [C,2C)
+ *              adaptive_w ("lw"), [2C,3C) adaptive_h ("lh").
+ * L = 1 skips the level map (single_level.py:120-123).
+ * feats[l]: device, [B, C, H[l], W[l]] in `layout`; out: device, NCHW dense.
+ * lvl_out  (optional, device int32 [regions, K]): level chosen per region box
+ *          (-1: box whose scale is NaN, matches no level -> zero output row).
+ * boxes_out(optional, device fp32 [regions, K, 5]): the region boxes used.
+ * ---------------------------------------------------------------------- */
+int arfe_roi_fuse_forward(const void* const* feats, const int32_t* H,
+                          const int32_t* W, const float* spatial_scale, int L,
+                          int B, int C, const float* rois, int K, int regions,
+                          float facs, int PH, int PW, int sampling_ratio,
+                          float finest_scale, int dtype, int layout, void* out,
+                          int32_t* lvl_out, float* boxes_out, void* stream);
+
+/* Backward of the above w.r.t. the pyramid (no gradient for rois, like
+ * RoIAlignFunction.backward, mmdet/ops/roi_align/roi_align.py:44-73, and
+ * roi_align_ext.backward_v2, roi_align_ext.cpp:144-161).
+ * dout: device [K, regions*C, PH, PW] dense NCHW, `dtype`.
+ * dfeats[l]: device fp32 [B, C, H[l], W[l]] in `layout`; the kernel ADDS into
+ * them (the caller zero-fills, as the reference's at::zeros does,
+ * roi_align_kernel_v2.cu:325-326; one buffer per level receives the sum over
+ * all regions, replacing the reference's 15 dense per-level/region grads). */
+int arfe_roi_fuse_backward(const void* dout, const int32_t* H, const int32_t* W,
+                           const float* spatial_scale, int L, int B, int C,
+                           const float* rois, int K, int regions, float facs,
+                           int PH, int PW, int sampling_ratio,
+                           float finest_scale, int dtype, int layout,
+                           float* const* dfeats, void* stream);
+
+/* Operator-level twins of roi_align_ext.forward_v2 / backward_v2
+ * (roi_align_ext.cpp:126-161; aligned=True only -- aligned=False is the legacy
+ * v1 path, which is not built).  input [B,C,H,W], rois [K,5],
+ * output [K,C,PH,PW]; grad_input is ADDED into (caller zero-fills). */
+int arfe_roi_align_forward(const void* input, const float* rois,
+                           float spatial_scale, int pooled_height,
+                           int pooled_width, int sampling_ratio, int aligned,
+                           int B, int C, int H, int W, int K, int dtype,
+                           int layout, void* output, void* stream);
+int arfe_roi_align_backward(const void* grad, const float* rois,
+                            float spatial_scale, int pooled_height,
+                            int pooled_width, int B, int C, int H, int W,
+                            int K, int sampling_ratio, int aligned, int dtype,
+                            int layout, float* grad_input, void* stream);
+
+/* Parity instrumentation: the region boxes, levels, sampling grids and the
+ * bilinear rows/columns/weights the kernels above use, computed by the same
+ * device functions.  Shapes (R = regions):
+ *   lvl [R,K] int32, grid [R,K,2] int32 (grid_h, grid_w), boxes [R,K,5] fp32,
+ *   ylo/yhi [R,K,PH,max_grid] int32, ywl/ywh same shape fp32,
+ *   xlo/xhi [R,K,PW,max_grid] int32, xwl/xwh same shape fp32.
+ * Slots i >= grid are -2; samples outside the map are -1 (weights 0). */
+int arfe_roi_fuse_taps(const int32_t* H, const int32_t* W,
+                       const float* spatial_scale, int L, const float* rois,
+                       int K, int regions, float facs, int PH, int PW,
+                       int sampling_ratio, float finest_scale, int max_grid,
+                       int32_t* lvl, int32_t* grid, float* boxes, int32_t* ylo,
+                       int32_t* yhi, float* ywl, float* ywh, int32_t* xlo,
+                       int32_t* xhi, float* xwl, float* xwh, void* stream);
+
+/* ------------------------------------------------------------------------
+ * AR-RFF fusion gate: out = ori + ori*(a + b) = ori*(1 + a + b)
+ *   MultiBBoxHead.forward, mmdet/models/roi_heads/bbox_heads/multirois_bbox_head.py:175,182
+ * ori is read in place from the concatenated tensor: roi k starts at
+ * ori + k*ori_roi_stride elements and holds n_per_roi (= C*PH*PW) elements.
+ * a, b, out: dense [K, n_per_roi].
+ * backward: d_ori = g*(1+a+b) (dense [K,n_per_roi]), da = db = g*ori (one
+ * buffer, d_ab). */
+int arfe_rff_gate_forward(const void* ori, int64_t ori_roi_stride, const void* a,
+                          const void* b, void* out, int64_t K,
+                          int64_t n_per_roi, int dtype, void* stream);
+int arfe_rff_gate_backward(const void* g, const void* ori,
+                           int64_t ori_roi_stride, const void* a, const void* b,
+                           void* d_ori, void* d_ab, int64_t K,
+                           int64_t n_per_roi, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------
+ * AR-FPN gather: every level resized to the refine level and averaged.
+ *   WFPNDualSpatial.forward, mmdet/models/necks/wfpn_dual_spatial.py:102-113
+ *   levels < refine_level: F.adaptive_max_pool2d; others: nearest interpolate;
+ *   out = ((((0+f0)+f1)+...)+f_{L-1}) / L
+ * out: device [B,C,H[refine],W[refine]] `dtype`, `layout`.
+ * argmax (optional, device uint8 [refine_level, B, C, Hr, Wr], NCHW order
+ * regardless of layout): position of the max inside the pooling window
+ * (dy*window_w+dx), saved for the backward. Window must have <= 255 cells.
+ * backward: dfeats[l] (device, `dtype`, `layout`) are fully WRITTEN. */
+int arfe_fpn_gather_forward(const void* const* feats, const int32_t* H,
+                            const int32_t* W, int L, int B, int C,
+                            int refine_level, int dtype, int layout, void* out,
+                            uint8_t* argmax, void* stream);
+int arfe_fpn_gather_backward(const void* dout, const uint8_t* argmax,
+                             const int32_t* H, const int32_t* W, int L, int B,
+                             int C, int refine_level, int dtype, int layout,
+                             void* const* dfeats, void* stream);
+
+/* ------------------------------------------------------------------------
+ * AR-FPN gated residual:
+ *   out_l = x_l + nearest(bsf -> H[l] x W[l]) * (tanh(relu(g1_l)) + tanh(relu(g2_l)))
+ *   WFPNDualSpatial.forward, mmdet/models/necks/wfpn_dual_spatial.py:118-135
+ *   (g1_l / g2_l are the raw outputs, bias included, of the Conv2d inside
+ *    reduce_convs[l] / reduce_convs2[l]; relu is mmcv ConvModule's default
+ *    activation, applied here together with the tanh.)
+ * feats[l], outs[l]: [B,C,H[l],W[l]]; bsf: [B,C,Hr,Wr]; g1[l], g2[l]:
+ * [B,1,H[l],W[l]]; all `dtype`, feats/outs/bsf in `layout`.
+ * backward (d x_l = d out_l is the identity and is left to the caller):
+ *   dbsf [B,C,Hr,Wr] fp32 (written), dg1[l], dg2[l] [B,1,H[l],W[l]] fp32
+ *   (written). */
+int arfe_fpn_apply_forward(const void* const* feats, const void* bsf,
+                           const void* const* g1, const void* const* g2,
+                           const int32_t* H, const int32_t* W, int L, int B,
+                           int C, int Hr, int Wr, int dtype, int layout,
+                           void* const* outs, void* stream);
+int arfe_fpn_apply_backward(const void* const* douts, const void* bsf,
+                            const void* const* g1, const void* const* g2,
+                            const int32_t* H, const int32_t* W, int L, int B,
+                            int C, int Hr, int Wr, int dtype, int layout,
+                            float* dbsf, float* const* dg1, float* const* dg2,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARFE_B200_H_ */

@@ -1,0 +1,179 @@
+"""Parity of the fused AR-RFF extraction (CUDA, through the C ABI) with the
+oracle: region boxes / levels / sampling indices bit-exact, fp32 values within
+1e-5 relative, bf16 within 1e-2 (BASELINE.json north_star)."""
+import pytest
+import torch
+
+from util import STRIDES, assert_close_bf16, assert_close_fp32, mixed_rois, small_pyramid
+
+pytestmark = pytest.mark.gpu
+
+
+def _scales(strides=STRIDES):
+    return [1.0 / s for s in strides]
+
+
+@pytest.mark.parametrize("regions", [3, 1])
+@pytest.mark.parametrize("channels", [16, 40])
+def test_forward_small_nchw(oracle, cuda, regions, channels):
+    import arfe_b200 as A
+    feats = small_pyramid(oracle, batch=2, channels=channels)
+    rois = mixed_rois(oracle, 96, 320, 192, 2)
+    if regions == 3:
+        ref = oracle.arrff_bbox_feats(feats, rois, list(STRIDES))
+    else:
+        ref = oracle.single_roi_extractor(feats, rois, list(STRIDES))
+    got = A.roi_fuse([f.to(cuda) for f in feats], rois.to(cuda), 7, _scales(),
+                     regions=regions)
+    assert_close_fp32(got, ref, f"roi_fuse regions={regions}")
+
+
+def test_indices_bit_exact(oracle, cuda):
+    """Boxes, levels, grid sizes, tap rows/cols and weights: exact equality."""
+    import arfe_b200 as A
+    rois = mixed_rois(oracle, 400, 1344, 800, 2, seed=3)
+    shapes = oracle.pyramid_shapes(800, 1344, STRIDES)
+    Hs, Ws = [s[0] for s in shapes], [s[1] for s in shapes]
+    MG = 64
+    dbg = A.roi_fuse_debug(rois.to(cuda), Hs, Ws, _scales(), 7, 0, 3, 1.0, 56, MG)
+    boxes, lvls = oracle.region_boxes_and_levels(rois, 5)
+    assert torch.equal(dbg["boxes"].cpu(), boxes), "region boxes differ"
+    assert torch.equal(dbg["lvl"].cpu().long(), lvls), "levels differ"
+    for r in range(3):
+        for l in range(5):
+            sel = (lvls[r] == l).nonzero().flatten()
+            if sel.numel() == 0:
+                continue
+            taps = oracle.roi_align_taps(boxes[r][sel], 7, 1.0 / STRIDES[l], Hs[l], Ws[l], 0, MG)
+            assert int(taps["grid"].max()) <= MG
+            assert torch.equal(dbg["grid"][r].cpu()[sel], taps["grid"])
+            for key in ("ylo", "yhi", "xlo", "xhi", "ywl", "ywh", "xwl", "xwh"):
+                assert torch.equal(dbg[key][r].cpu()[sel], taps[key]), (key, r, l)
+
+
+def test_level_thresholds_bit_exact(oracle, cuda):
+    """RoIs whose level-map argument lands within a few ulps of 2^k."""
+    import numpy as np
+    import arfe_b200 as A
+    rows = []
+    for k in range(1, 5):
+        side0 = np.float32(56.0 * 2.0 ** k)
+        # sweep square sides in 1-ulp steps around the threshold (the +1e-6 in
+        # the map shifts the crossing a few ulps below side0)
+        side = np.nextafter(side0, np.float32(0), dtype=np.float32)
+        for _ in range(40):
+            side = np.nextafter(side, np.float32(0), dtype=np.float32)
+        for _ in range(80):
+            rows.append([0.0, 0.0, 0.0, float(side), float(side)])
+            side = np.nextafter(side, np.float32(1e9), dtype=np.float32)
+    rois = torch.tensor(rows, dtype=torch.float32)
+    shapes = oracle.pyramid_shapes(800, 1344, STRIDES)
+    Hs, Ws = [s[0] for s in shapes], [s[1] for s in shapes]
+    dbg = A.roi_fuse_debug(rois.to(cuda), Hs, Ws, _scales(), 7, 0, 1, 1.0, 56, 4)
+    ref = oracle.map_roi_levels(rois, 5)
+    assert torch.equal(dbg["lvl"][0].cpu().long(), ref)
+    assert len(set(ref.tolist())) >= 4  # the sweep does cross thresholds
+
+
+@pytest.mark.parametrize("out_size,sample_num", [((14, 14), 0), ((7, 7), 2), ((3, 5), 0)])
+def test_forward_other_pool_sizes(oracle, cuda, out_size, sample_num):
+    import arfe_b200 as A
+    feats = small_pyramid(oracle, batch=2, channels=16)
+    rois = mixed_rois(oracle, 64, 320, 192, 2, seed=5)
+    ref = oracle.arrff_bbox_feats(feats, rois, list(STRIDES), out_size=out_size,
+                                  sample_num=sample_num)
+    got = A.roi_fuse([f.to(cuda) for f in feats], rois.to(cuda), out_size, _scales(),
+                     sample_num=sample_num, regions=3)
+    assert_close_fp32(got, ref, f"out_size={out_size} sample_num={sample_num}")
+
+
+def test_forward_config0_full_size(oracle, cuda):
+    """BASELINE config 0 shapes: one 800x1344 image, C=256, K=1000, 3 regions."""
+    import arfe_b200 as A
+    feats = oracle.synthetic_pyramid(1, 256, seed=0)
+    rois = oracle.synthetic_rois(1000, seed=0)
+    ref = oracle.arrff_bbox_feats(feats, rois, list(STRIDES))
+    got = A.roi_fuse([f.to(cuda) for f in feats], rois.to(cuda), 7, _scales(), regions=3)
+    assert got.shape == (1000, 768, 7, 7)
+    assert_close_fp32(got, ref, "config0")
+
+
+def test_forward_nhwc_and_bf16(oracle, cuda):
+    import arfe_b200 as A
+    feats = small_pyramid(oracle, batch=2, channels=32)
+    rois = mixed_rois(oracle, 64, 320, 192, 2, seed=7)
+    ref = oracle.arrff_bbox_feats(feats, rois, list(STRIDES))
+    cl = [f.to(cuda).contiguous(memory_format=torch.channels_last) for f in feats]
+    got = A.roi_fuse(cl, rois.to(cuda), 7, _scales(), regions=3)
+    assert got.is_contiguous()
+    assert_close_fp32(got, ref, "nhwc fp32")
+    # bf16 I/O: oracle = fp32 reference on the bf16-rounded inputs
+    fb = [f.bfloat16() for f in feats]
+    refb = oracle.arrff_bbox_feats([f.float() for f in fb], rois, list(STRIDES))
+    for name, inp in (("nchw", [f.to(cuda) for f in fb]),
+                      ("nhwc", [f.to(cuda).contiguous(memory_format=torch.channels_last) for f in fb])):
+        gb = A.roi_fuse(inp, rois.to(cuda), 7, _scales(), regions=3)
+        assert gb.dtype == torch.bfloat16
+        assert_close_bf16(gb, refb, f"bf16 {name}")
+
+
+def test_empty_and_degenerate(oracle, cuda):
+    import arfe_b200 as A
+    feats = [f.to(cuda) for f in small_pyramid(oracle, batch=1, channels=8)]
+    out = A.roi_fuse(feats, torch.zeros(0, 5, device=cuda), 7, _scales(), regions=3)
+    assert out.shape == (0, 24, 7, 7)
+    # negative-extent RoI: no level (NaN scale) -> zero row, like the reference
+    rois = torch.tensor([[0, 50.0, 50.0, 40.0, 60.0], [0, 8.0, 8.0, 40.0, 40.0]], device=cuda)
+    out = A.roi_fuse(feats, rois, 7, _scales(), regions=1)
+    assert float(out[0].abs().max()) == 0.0
+    assert float(out[1].abs().max()) > 0.0
+    # single-level extractor skips the level map (single_level.py:120-123)
+    ref = oracle.single_roi_extractor([feats[0].cpu()], rois[1:].cpu(), [4])
+    got = A.roi_fuse(feats[:1], rois[1:], 7, [0.25], regions=1)
+    assert_close_fp32(got, ref, "single level")
+
+
+def test_backward_small(oracle, cuda):
+    """d(pyramid) of the fused extraction vs autograd through the oracle
+    (reference backward_v2 per level/region, summed)."""
+    import arfe_b200 as A
+    feats = small_pyramid(oracle, batch=2, channels=16)
+    rois = mixed_rois(oracle, 80, 320, 192, 2, seed=11)
+    fo = [f.clone().requires_grad_(True) for f in feats]
+    ref = oracle.arrff_bbox_feats(fo, rois, list(STRIDES))
+    g = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1))
+    ref.backward(g)
+    fg = [f.to(cuda).requires_grad_(True) for f in feats]
+    got = A.roi_fuse(fg, rois.to(cuda), 7, _scales(), regions=3)
+    got.backward(g.to(cuda))
+    for l in range(5):
+        r = fo[l].grad
+        if r is None:  # no RoI region maps to this level
+            assert float(fg[l].grad.abs().max()) == 0.0
+            continue
+        d = (fg[l].grad.cpu() - r).abs()
+        scale = float(r.abs().max()) + 1e-12
+        assert float(d.max()) <= 2e-5 * scale + 1e-6, (l, float(d.max()), scale)
+
+
+def test_backward_nhwc_bf16_and_roialign_op(oracle, cuda):
+    import arfe_b200 as A
+    feats = small_pyramid(oracle, batch=2, channels=16)
+    rois = mixed_rois(oracle, 40, 320, 192, 2, seed=13)
+    # operator-level RoIAlign (reference gradcheck.py sizes: 3x3 out, scale 1/8)
+    x = feats[1]
+    xo = x.clone().requires_grad_(True)
+    ref = oracle.roi_align(xo, rois, 3, 1 / 8, 2)
+    g = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2))
+    ref.backward(g)
+    xg = x.to(cuda).requires_grad_(True)
+    got = A.RoIAlign(3, 1 / 8, sample_num=2)(xg, rois.to(cuda))
+    assert_close_fp32(got, ref, "RoIAlign op fwd")
+    got.backward(g.to(cuda))
+    d = (xg.grad.cpu() - xo.grad).abs().max()
+    assert float(d) <= 2e-5 * float(xo.grad.abs().max()) + 1e-6
+    # channels_last gradient
+    xc = x.to(cuda).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    A.RoIAlign(3, 1 / 8, sample_num=2)(xc, rois.to(cuda)).backward(g.to(cuda))
+    d = (xc.grad.cpu() - xo.grad).abs().max()
+    assert float(d) <= 2e-5 * float(xo.grad.abs().max()) + 1e-6
