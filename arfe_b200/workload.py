@@ -1,0 +1,221 @@
+"""The benchmark workload of BASELINE.json configs[1]: one training step
+(forward + backward) of the region-aware feature path for the images and RoIs
+one GPU holds -- Faster R-CNN R50 shapes, 2 images x 512 RoIs per GPU,
+800x1344 input, C=256, FPN strides 4..64 -- driven straight through the C ABI
+with every buffer pre-allocated (no allocation, no sync in the step).
+
+The convolutions / NonLocal2D / FCs between the kernels stay on PyTorch and are
+NOT part of the step (north_star); their outputs (bsf, gate pre-activations,
+relu(conv) of the context regions, incoming gradients) are synthetic inputs.
+
+Step (9 launches of our kernels):
+  fwd: gather -> apply -> roi_fuse (3 regions) -> gate
+  bwd: gate_bwd -> roi_fuse_bwd -> apply_bwd (2 launches) -> gather_bwd
+"""
+import math
+
+import torch
+
+from . import _lib as L
+
+STRIDES = (4, 8, 16, 32, 64)
+KERNELS = ("fpn_gather_fwd", "fpn_apply_fwd", "roi_fuse_fwd", "rff_gate_fwd",
+           "rff_gate_bwd", "roi_fuse_bwd", "fpn_apply_bwd", "fpn_gather_bwd")
+LAUNCHES_PER_STEP = 9
+
+
+def pyramid_shapes(img_h=800, img_w=1344, strides=STRIDES):
+    shapes, h, w, s = [], img_h, img_w, 1
+    for st in strides:
+        while s < st:
+            h, w, s = (h - 1) // 2 + 1, (w - 1) // 2 + 1, s * 2
+        shapes.append((h, w))
+    return shapes
+
+
+def synthetic_rois(K, img_w=1344, img_h=800, batch=1, seed=0, smin=16.0, smax=600.0):
+    """centre uniform, sqrt(area) log-uniform in
+    [16,600] px, aspect log-uniform in [0.5,2], clipped; RoI i belongs to
+    image i % batch (same generator as oracle.synthetic_rois)."""
+    g = torch.Generator().manual_seed(seed)
+    u = torch.rand(K, 4, generator=g)
+    cx, cy = u[:, 0] * img_w, u[:, 1] * img_h
+    s = torch.exp(math.log(smin) + u[:, 2] * (math.log(smax) - math.log(smin)))
+    ar = torch.exp(math.log(0.5) + u[:, 3] * (math.log(2.0) - math.log(0.5)))
+    w, h = s * torch.sqrt(ar), s / torch.sqrt(ar)
+    x1 = (cx - w / 2).clamp(0, img_w - 1)
+    y1 = (cy - h / 2).clamp(0, img_h - 1)
+    x2 = torch.max((cx + w / 2).clamp(0, img_w - 1), x1 + 1.0)
+    y2 = torch.max((cy + h / 2).clamp(0, img_h - 1), y1 + 1.0)
+    b = (torch.arange(K) % batch).float()
+    return torch.stack([b, x1, y1, x2, y2], dim=1).float().contiguous()
+
+
+def host_inputs(batch=2, rois_per_img=512, channels=256, img_h=800, img_w=1344,
+                dtype=torch.float32, seed=0, pin=False):
+    """Synthetic inputs of one step on the HOST (optionally pinned)."""
+    shapes = pyramid_shapes(img_h, img_w)
+    g = torch.Generator().manual_seed(seed)
+    K = batch * rois_per_img
+    hr, wr = shapes[2]
+    t = {}
+    t["x"] = [torch.randn(batch, channels, h, w, generator=g).to(dtype) for h, w in shapes]
+    t["bsf"] = torch.randn(batch, channels, hr, wr, generator=g).to(dtype)
+    t["g1"] = [torch.randn(batch, 1, h, w, generator=g).to(dtype) for h, w in shapes]
+    t["g2"] = [torch.randn(batch, 1, h, w, generator=g).to(dtype) for h, w in shapes]
+    t["rois"] = synthetic_rois(K, img_w, img_h, batch, seed)
+    t["a"] = torch.randn(K, channels, 7, 7, generator=g).relu().to(dtype)
+    t["b"] = torch.randn(K, channels, 7, 7, generator=g).relu().to(dtype)
+    t["gz"] = torch.randn(K, channels, 7, 7, generator=g).to(dtype)      # dL/d(gate out)
+    t["gbsf"] = torch.randn(batch, channels, hr, wr, generator=g).to(dtype)  # dL/d(gathered)
+    if pin:
+        def p(v):
+            return [p(e) for e in v] if isinstance(v, list) else v.pin_memory()
+        t = {k: p(v) for k, v in t.items()}
+    t["shapes"] = shapes
+    return t
+
+
+class TrainStep:
+    """Pre-allocated device state + the 9-launch step through the C ABI."""
+
+    def __init__(self, host, device, regions=3):
+        self.dev = device
+        self.lib = L.lib()
+        x = host["x"]
+        self.dtype = x[0].dtype
+        self.dt = L.dtype_code(x[0])
+        self.B, self.C = x[0].shape[:2]
+        self.shapes = host["shapes"]
+        self.nlev = len(x)
+        self.K = host["rois"].shape[0]
+        self.R = regions
+        d = lambda v: [e.to(device) for e in v] if isinstance(v, list) else v.to(device)
+        self.x, self.bsf, self.g1, self.g2 = d(host["x"]), d(host["bsf"]), d(host["g1"]), d(host["g2"])
+        self.rois, self.a, self.b, self.gz, self.gbsf = (d(host[k]) for k in ("rois", "a", "b", "gz", "gbsf"))
+        B, C, K, R = self.B, self.C, self.K, self.R
+        hr, wr = self.shapes[2]
+        e = lambda *s, dtype=self.dtype: torch.empty(*s, dtype=dtype, device=device)
+        self.gathered = e(B, C, hr, wr)
+        self.argmax = e(2, B, C, hr, wr, dtype=torch.uint8)
+        self.y = [e(B, C, h, w) for h, w in self.shapes]
+        self.F = e(K, R * C, 7, 7)
+        self.z = e(K, C, 7, 7)
+        self.dF = e(K, R * C, 7, 7)            # [d_ori | d_lw | d_lh]
+        self.d_ori = e(K, C, 7, 7)
+        self.d_ab = e(K, C, 7, 7)
+        self.dy = [e(B, C, h, w, dtype=torch.float32) for h, w in self.shapes]
+        self.dy_in = self.dy if self.dtype == torch.float32 else [e(B, C, h, w) for h, w in self.shapes]
+        self.dbsf = e(B, C, hr, wr, dtype=torch.float32)
+        self.dg1 = [e(B, 1, h, w, dtype=torch.float32) for h, w in self.shapes]
+        self.dg2 = [e(B, 1, h, w, dtype=torch.float32) for h, w in self.shapes]
+        self.dx = [e(B, C, h, w) for h, w in self.shapes]
+        # C arrays built once
+        self.H = L.int_array([s[0] for s in self.shapes])
+        self.W = L.int_array([s[1] for s in self.shapes])
+        self.scales = L.float_array([1.0 / s for s in STRIDES[:self.nlev]])
+        self.p_x, self.p_y = L.ptr_array(self.x), L.ptr_array(self.y)
+        self.p_g1, self.p_g2 = L.ptr_array(self.g1), L.ptr_array(self.g2)
+        self.p_dy, self.p_dy_in = L.ptr_array(self.dy), L.ptr_array(self.dy_in)
+        self.p_dg1, self.p_dg2 = L.ptr_array(self.dg1), L.ptr_array(self.dg2)
+        self.p_dx = L.ptr_array(self.dx)
+        self.n_per_roi = C * 49
+        self.stream = L.stream_ptr(device)
+
+    # -- the eight ops; each returns the C return code ----------------------
+    def fpn_gather_fwd(self):
+        return self.lib.arfe_fpn_gather_forward(
+            self.p_x, self.H, self.W, self.nlev, self.B, self.C, 2, self.dt, 0,
+            self.gathered.data_ptr(), self.argmax.data_ptr(), self.stream)
+
+    def fpn_apply_fwd(self):
+        hr, wr = self.shapes[2]
+        return self.lib.arfe_fpn_apply_forward(
+            self.p_x, self.bsf.data_ptr(), self.p_g1, self.p_g2, self.H, self.W, self.nlev,
+            self.B, self.C, hr, wr, self.dt, 0, self.p_y, self.stream)
+
+    def roi_fuse_fwd(self):
+        return self.lib.arfe_roi_fuse_forward(
+            self.p_y, self.H, self.W, self.scales, self.nlev, self.B, self.C,
+            self.rois.data_ptr(), self.K, self.R, 1.0, 7, 7, 0, 56.0, self.dt, 0,
+            self.F.data_ptr(), None, None, self.stream)
+
+    def rff_gate_fwd(self):
+        return self.lib.arfe_rff_gate_forward(
+            self.F.data_ptr(), self.R * self.n_per_roi, self.a.data_ptr(), self.b.data_ptr(),
+            self.z.data_ptr(), self.K, self.n_per_roi, self.dt, self.stream)
+
+    def rff_gate_bwd(self):
+        return self.lib.arfe_rff_gate_backward(
+            self.gz.data_ptr(), self.F.data_ptr(), self.R * self.n_per_roi, self.a.data_ptr(),
+            self.b.data_ptr(), self.d_ori.data_ptr(), self.d_ab.data_ptr(), self.K,
+            self.n_per_roi, self.dt, self.stream)
+
+    def roi_fuse_bwd(self):
+        return self.lib.arfe_roi_fuse_backward(
+            self.dF.data_ptr(), self.H, self.W, self.scales, self.nlev, self.B, self.C,
+            self.rois.data_ptr(), self.K, self.R, 1.0, 7, 7, 0, 56.0, self.dt, 0,
+            self.p_dy, self.stream)
+
+    def fpn_apply_bwd(self):
+        hr, wr = self.shapes[2]
+        return self.lib.arfe_fpn_apply_backward(
+            self.p_dy_in, self.bsf.data_ptr(), self.p_g1, self.p_g2, self.H, self.W, self.nlev,
+            self.B, self.C, hr, wr, self.dt, 0, self.dbsf.data_ptr(), self.p_dg1, self.p_dg2,
+            self.stream)
+
+    def fpn_gather_bwd(self):
+        return self.lib.arfe_fpn_gather_backward(
+            self.gbsf.data_ptr(), self.argmax.data_ptr(), self.H, self.W, self.nlev, self.B,
+            self.C, 2, self.dt, 0, self.p_dx, self.stream)
+
+    def glue_before_roi_bwd(self):
+        """torch plumbing between our kernels: assemble dF (stand-in for the
+        conv backward of the two context branches) and zero the accumulators
+        (the reference's at::zeros, roi_align_kernel_v2.cu:325-326)."""
+        C = self.C
+        self.dF[:, :C].copy_(self.d_ori)
+        self.dF[:, C:2 * C].copy_(self.d_ab)
+        self.dF[:, 2 * C:].copy_(self.d_ab)
+        for t in self.dy:
+            t.zero_()
+
+    def glue_before_apply_bwd(self):
+        if self.dy_in is not self.dy:
+            for a, b in zip(self.dy_in, self.dy):
+                a.copy_(b)
+
+    def step(self, timer=None):
+        """One training step. `timer(name, fn)` wraps each of our launches."""
+        run = timer or (lambda name, fn: L.check(fn(), name))
+        run("fpn_gather_fwd", self.fpn_gather_fwd)
+        run("fpn_apply_fwd", self.fpn_apply_fwd)
+        run("roi_fuse_fwd", self.roi_fuse_fwd)
+        run("rff_gate_fwd", self.rff_gate_fwd)
+        run("rff_gate_bwd", self.rff_gate_bwd)
+        self.glue_before_roi_bwd()
+        run("roi_fuse_bwd", self.roi_fuse_bwd)
+        self.glue_before_apply_bwd()
+        run("fpn_apply_bwd", self.fpn_apply_bwd)
+        run("fpn_gather_bwd", self.fpn_gather_bwd)
+
+    # -- algorithmic bytes per launch ------------------
+    def algorithmic_bytes(self):
+        e = 4 if self.dtype == torch.float32 else 2
+        B, C, K, R = self.B, self.C, self.K, self.R
+        P = sum(h * w for h, w in self.shapes)
+        hr, wr = self.shapes[2]
+        pyr = B * C * P * e
+        ref = B * C * hr * wr
+        out_roi = K * R * C * 49 * e
+        n_gate = K * C * 49 * e
+        return {
+            "fpn_gather_fwd": pyr + ref * e + 2 * ref,                       # + uint8 argmax (2 levels)
+            "fpn_apply_fwd": 2 * pyr + ref * e + 2 * B * P * e,
+            "roi_fuse_fwd": out_roi + pyr + 20 * K,
+            "rff_gate_fwd": 4 * n_gate,
+            "rff_gate_bwd": 6 * n_gate,
+            "roi_fuse_bwd": out_roi + B * C * P * 4 + 20 * K,                # fp32 accumulators
+            "fpn_apply_bwd": pyr + ref * e + 2 * B * P * e + ref * 4 + 2 * B * P * 4,
+            "fpn_gather_bwd": ref * e + 2 * ref + pyr,
+        }
