@@ -68,9 +68,36 @@ __device__ __forceinline__ int nearest_src(int d, int in, int out) {
 }
 
 // ---------------------------------------------------------------- gather fwd
+// Window maximum with the reference's tie/NaN rule, element order row-major.
+__device__ __forceinline__ void max_step(float t, int pos, float& best, int& arg) {
+  if (t > best || t != t) { best = t; arg = pos; }
+}
+
+// s x s window of an NCHW fp32 plane read with 128/64-bit loads (exact ratio).
+template <int S>
+__device__ __forceinline__ void window_max_vec(const float* __restrict__ row0, int W,
+                                               float& best, int& arg) {
+#pragma unroll
+  for (int r = 0; r < S; ++r) {
+    const float* q = row0 + (size_t)r * W;
+    if constexpr (S == 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(q));
+      max_step(v.x, r * 4 + 0, best, arg); max_step(v.y, r * 4 + 1, best, arg);
+      max_step(v.z, r * 4 + 2, best, arg); max_step(v.w, r * 4 + 3, best, arg);
+    } else {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(q));
+      max_step(v.x, r * 2 + 0, best, arg); max_step(v.y, r * 2 + 1, best, arg);
+    }
+  }
+}
+
+// `vec[l]` = pooling ratio (2 or 4) when level l < refine has an exact integer
+// ratio, an NCHW fp32 layout and 16-byte aligned rows; 0 selects generic loops.
+struct VecFlags { int s[kMaxLevels]; };
+
 template <typename T, bool kNHWC>
 __global__ void __launch_bounds__(kThreads)
-gather_fwd(const FpnParams p) {
+gather_fwd(const FpnParams p, const VecFlags vf) {
   const int Hr = p.Hr, Wr = p.Wr, C = p.C;
   const size_t total = (size_t)p.B * C * Hr * Wr;
   const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
@@ -83,15 +110,26 @@ gather_fwd(const FpnParams p) {
     const int H = p.H[l], W = p.W[l];
     float v;
     if (l < p.refine_level) {
-      const int y0 = pool_start(Y, H, Hr), y1 = pool_end(Y, H, Hr);
-      const int x0 = pool_start(X, W, Wr), x1 = pool_end(X, W, Wr);
       float best = -CUDART_INF_F;
       int arg = 0;
-      for (int y = y0; y < y1; ++y)
-        for (int x = x0; x < x1; ++x) {
-          const float t = ldf(f + at<kNHWC>(b, c, y, x, C, H, W));
-          if (t > best || t != t) { best = t; arg = (y - y0) * (x1 - x0) + (x - x0); }
+      bool done = false;
+      if constexpr (sizeof(T) == 4 && !kNHWC) {
+        const int s = vf.s[l];
+        if (s == 4) {
+          window_max_vec<4>(reinterpret_cast<const float*>(f) + (((size_t)b * C + c) * H + 4 * Y) * W + 4 * X, W, best, arg);
+          done = true;
+        } else if (s == 2) {
+          window_max_vec<2>(reinterpret_cast<const float*>(f) + (((size_t)b * C + c) * H + 2 * Y) * W + 2 * X, W, best, arg);
+          done = true;
         }
+      }
+      if (!done) {
+        const int y0 = pool_start(Y, H, Hr), y1 = pool_end(Y, H, Hr);
+        const int x0 = pool_start(X, W, Wr), x1 = pool_end(X, W, Wr);
+        for (int y = y0; y < y1; ++y)
+          for (int x = x0; x < x1; ++x)
+            max_step(ldf(f + at<kNHWC>(b, c, y, x, C, H, W)), (y - y0) * (x1 - x0) + (x - x0), best, arg);
+      }
       v = best;
       if (p.argmax)
         p.argmax[(((size_t)l * p.B + b) * C + c) * Hr * Wr + (size_t)Y * Wr + X] = (uint8_t)arg;
@@ -104,19 +142,25 @@ gather_fwd(const FpnParams p) {
 }
 
 // ---------------------------------------------------------------- gather bwd
-// One thread per element of every level's gradient (all fully written).
-struct LevelOffsets { size_t start[kMaxLevels + 1]; };
+// Generic: one thread per element of the gradient of each level listed in
+// `lo.level[]` (all fully written).
+struct LevelOffsets {
+  size_t start[kMaxLevels + 1];
+  int level[kMaxLevels];
+  int n;
+};
 
 template <typename T, bool kNHWC>
 __global__ void __launch_bounds__(kThreads)
 gather_bwd(const FpnParams p, const LevelOffsets lo) {
   const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
-  if (i >= lo.start[p.L]) return;
-  int l = 0;
-  while (l + 1 < p.L && i >= lo.start[l + 1]) ++l;
+  if (i >= lo.start[lo.n]) return;
+  int j = 0;
+  while (j + 1 < lo.n && i >= lo.start[j + 1]) ++j;
+  const int l = lo.level[j];
   const int H = p.H[l], W = p.W[l], C = p.C, Hr = p.Hr, Wr = p.Wr;
   int b, c, y, x;
-  decode<kNHWC>(i - lo.start[l], C, H, W, b, c, y, x);
+  decode<kNHWC>(i - lo.start[j], C, H, W, b, c, y, x);
   const T* __restrict__ d = static_cast<const T*>(p.gathered);  // dout [B,C,Hr,Wr]
   float g = 0.f;
   if (l < p.refine_level) {
@@ -149,7 +193,43 @@ gather_bwd(const FpnParams p, const LevelOffsets lo) {
         if (nearest_src(X, W, Wr) == x) g += ldf(d + at<kNHWC>(b, c, Y, X, C, Hr, Wr));
     }
   }
-  stf(static_cast<T*>(p.outs[l]) + (i - lo.start[l]), __fdiv_rn(g, (float)p.L));
+  stf(static_cast<T*>(p.outs[l]) + (i - lo.start[j]), __fdiv_rn(g, (float)p.L));
+}
+
+// Fast (NCHW fp32, exact integer ratios): one thread per refine element routes
+// g/L into the s x s block of every pooled level with 128/64-bit stores and
+// writes the refine level itself.
+__global__ void __launch_bounds__(kThreads)
+gather_bwd_fast(const FpnParams p, const VecFlags vf) {
+  const int Hr = p.Hr, Wr = p.Wr, C = p.C;
+  const size_t total = (size_t)p.B * C * Hr * Wr;
+  const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= total) return;
+  int b, c, Y, X;
+  decode<false>(i, C, Hr, Wr, b, c, Y, X);
+  const float g = __fdiv_rn(__ldg(static_cast<const float*>(p.gathered) + i), (float)p.L);
+  for (int l = 0; l < p.refine_level; ++l) {
+    const int s = vf.s[l];
+    if (s == 0) continue;
+    const int W = p.W[l], H = p.H[l];
+    const int arg = p.argmax[(((size_t)l * p.B + b) * C + c) * Hr * Wr + (size_t)Y * Wr + X];
+    float* __restrict__ o = static_cast<float*>(p.outs[l]) + (((size_t)b * C + c) * H + (size_t)s * Y) * W + (size_t)s * X;
+    if (s == 4) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int k = arg - 4 * r;
+        *reinterpret_cast<float4*>(o + (size_t)r * W) =
+            make_float4(k == 0 ? g : 0.f, k == 1 ? g : 0.f, k == 2 ? g : 0.f, k == 3 ? g : 0.f);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int k = arg - 2 * r;
+        *reinterpret_cast<float2*>(o + (size_t)r * W) = make_float2(k == 0 ? g : 0.f, k == 1 ? g : 0.f);
+      }
+    }
+  }
+  static_cast<float*>(p.outs[p.refine_level])[i] = g;
 }
 
 // ----------------------------------------------------------------- apply fwd
@@ -163,11 +243,12 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 apply_fwd_nchw(const FpnParams p, const LevelOffsets lo /* pixel offsets */, int cg) {
   const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
-  if (i >= lo.start[p.L]) return;
-  int l = 0;
-  while (l + 1 < p.L && i >= lo.start[l + 1]) ++l;
+  if (i >= lo.start[lo.n]) return;
+  int j = 0;
+  while (j + 1 < lo.n && i >= lo.start[j + 1]) ++j;
+  const int l = lo.level[j];
   const int H = p.H[l], W = p.W[l], C = p.C, Hr = p.Hr, Wr = p.Wr;
-  size_t r = i - lo.start[l];
+  size_t r = i - lo.start[j];
   const int x = (int)(r % W); r /= W;
   const int y = (int)(r % H);
   const int b = (int)(r / H);
@@ -190,18 +271,19 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 apply_fwd_nhwc(const FpnParams p, const LevelOffsets lo /* element offsets */) {
   const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
-  if (i >= lo.start[p.L]) return;
-  int l = 0;
-  while (l + 1 < p.L && i >= lo.start[l + 1]) ++l;
+  if (i >= lo.start[lo.n]) return;
+  int j = 0;
+  while (j + 1 < lo.n && i >= lo.start[j + 1]) ++j;
+  const int l = lo.level[j];
   const int H = p.H[l], W = p.W[l], C = p.C, Hr = p.Hr, Wr = p.Wr;
   int b, c, y, x;
-  decode<true>(i - lo.start[l], C, H, W, b, c, y, x);
+  decode<true>(i - lo.start[j], C, H, W, b, c, y, x);
   const size_t pix = ((size_t)b * H + y) * W + x;
   const float gate = gate_value(ldf(static_cast<const T*>(p.g1[l]) + pix),
                                 ldf(static_cast<const T*>(p.g2[l]) + pix));
   const int ny = nearest_src(y, Hr, H), nx = nearest_src(x, Wr, W);
   const float bv = ldf(static_cast<const T*>(p.bsf) + at<true>(b, c, ny, nx, C, Hr, Wr));
-  const size_t e = i - lo.start[l];
+  const size_t e = i - lo.start[j];
   stf(static_cast<T*>(p.outs[l]) + e, fmaf(bv, gate, ldf(static_cast<const T*>(p.feats[l]) + e)));
 }
 
@@ -214,11 +296,12 @@ template <typename T, bool kNHWC>
 __global__ void __launch_bounds__(kThreads)
 apply_bwd_gates(const FpnParams p, const LevelOffsets lo /* pixel offsets */) {
   const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
-  if (i >= lo.start[p.L]) return;
-  int l = 0;
-  while (l + 1 < p.L && i >= lo.start[l + 1]) ++l;
+  if (i >= lo.start[lo.n]) return;
+  int j = 0;
+  while (j + 1 < lo.n && i >= lo.start[j + 1]) ++j;
+  const int l = lo.level[j];
   const int H = p.H[l], W = p.W[l], C = p.C, Hr = p.Hr, Wr = p.Wr;
-  size_t r = i - lo.start[l];
+  size_t r = i - lo.start[j];
   const int x = (int)(r % W); r /= W;
   const int y = (int)(r % H);
   const int b = (int)(r / H);
@@ -272,15 +355,39 @@ apply_bwd_bsf(const FpnParams p) {
   p.dbsf[i] = acc;
 }
 
-inline LevelOffsets offsets(const FpnParams& p, bool per_pixel) {
+inline LevelOffsets offsets(const FpnParams& p, bool per_pixel, unsigned level_mask = 0xffffffffu) {
   LevelOffsets lo;
   size_t s = 0;
+  int n = 0;
   for (int l = 0; l < p.L; ++l) {
-    lo.start[l] = s;
+    if (!(level_mask & (1u << l))) continue;
+    lo.start[n] = s;
+    lo.level[n] = l;
     s += (size_t)p.B * (per_pixel ? 1 : p.C) * p.H[l] * p.W[l];
+    ++n;
   }
-  for (int l = p.L; l <= kMaxLevels; ++l) lo.start[l] = s;
+  lo.n = n;
+  for (int j = n; j <= kMaxLevels; ++j) lo.start[j] = s;
+  for (int j = n; j < kMaxLevels; ++j) lo.level[j] = 0;
   return lo;
+}
+
+// Levels below refine whose pooling ratio is an exact 2 or 4 with 16-byte
+// aligned rows (NCHW fp32 only) take the vector paths.
+inline VecFlags vec_flags(const FpnParams& p, int dtype, int layout, bool for_outs) {
+  VecFlags vf;
+  for (int l = 0; l < kMaxLevels; ++l) vf.s[l] = 0;
+  if (dtype != 0 || layout != 0) return vf;
+  for (int l = 0; l < p.refine_level; ++l) {
+    for (int s = 2; s <= 4; s *= 2) {
+      const void* base = for_outs ? p.outs[l] : p.feats[l];
+      const size_t align = s == 4 ? 16 : 8;
+      if (p.H[l] == s * p.Hr && p.W[l] == s * p.Wr &&
+          (reinterpret_cast<uintptr_t>(base) % align) == 0)
+        vf.s[l] = s;
+    }
+  }
+  return vf;
 }
 inline unsigned blocks_for(size_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
@@ -301,15 +408,28 @@ cudaError_t launch_fpn_gather_forward(const FpnParams& p, int dtype, int layout,
                                       cudaStream_t stream) {
   const size_t total = (size_t)p.B * p.C * p.Hr * p.Wr;
   if (total == 0) return cudaSuccess;
-  ARFE_DISPATCH(gather_fwd, blocks_for(total), p);
+  const VecFlags vf = vec_flags(p, dtype, layout, false);
+  ARFE_DISPATCH(gather_fwd, blocks_for(total), p, vf);
   return cudaGetLastError();
 }
 
 cudaError_t launch_fpn_gather_backward(const FpnParams& p, int dtype, int layout,
                                        cudaStream_t stream) {
-  const LevelOffsets lo = offsets(p, false);
-  if (lo.start[p.L] == 0) return cudaSuccess;
-  ARFE_DISPATCH(gather_bwd, blocks_for(lo.start[p.L]), p, lo);
+  const VecFlags vf = vec_flags(p, dtype, layout, true);
+  unsigned mask = (1u << p.L) - 1u;
+  bool any_fast = false;
+  for (int l = 0; l < p.refine_level; ++l)
+    if (vf.s[l]) { mask &= ~(1u << l); any_fast = true; }
+  if (any_fast) {
+    mask &= ~(1u << p.refine_level);
+    const size_t total = (size_t)p.B * p.C * p.Hr * p.Wr;
+    if (total) gather_bwd_fast<<<blocks_for(total), kThreads, 0, stream>>>(p, vf);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  const LevelOffsets lo = offsets(p, false, mask);
+  if (lo.start[lo.n] == 0) return cudaSuccess;
+  ARFE_DISPATCH(gather_bwd, blocks_for(lo.start[lo.n]), p, lo);
   return cudaGetLastError();
 }
 
@@ -317,16 +437,16 @@ cudaError_t launch_fpn_apply_forward(const FpnParams& p, int dtype, int layout,
                                      cudaStream_t stream) {
   if (layout == 0) {
     const LevelOffsets lo = offsets(p, true);
-    if (lo.start[p.L] == 0) return cudaSuccess;
+    if (lo.start[lo.n] == 0) return cudaSuccess;
     const int cg = p.C >= 32 ? 32 : p.C;
-    dim3 grid(blocks_for(lo.start[p.L]), (p.C + cg - 1) / cg);
+    dim3 grid(blocks_for(lo.start[lo.n]), (p.C + cg - 1) / cg);
     if (dtype == 0) apply_fwd_nchw<float><<<grid, kThreads, 0, stream>>>(p, lo, cg);
     else apply_fwd_nchw<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(p, lo, cg);
   } else {
     const LevelOffsets lo = offsets(p, false);
-    if (lo.start[p.L] == 0) return cudaSuccess;
-    if (dtype == 0) apply_fwd_nhwc<float><<<blocks_for(lo.start[p.L]), kThreads, 0, stream>>>(p, lo);
-    else apply_fwd_nhwc<__nv_bfloat16><<<blocks_for(lo.start[p.L]), kThreads, 0, stream>>>(p, lo);
+    if (lo.start[lo.n] == 0) return cudaSuccess;
+    if (dtype == 0) apply_fwd_nhwc<float><<<blocks_for(lo.start[lo.n]), kThreads, 0, stream>>>(p, lo);
+    else apply_fwd_nhwc<__nv_bfloat16><<<blocks_for(lo.start[lo.n]), kThreads, 0, stream>>>(p, lo);
   }
   return cudaGetLastError();
 }
@@ -334,8 +454,8 @@ cudaError_t launch_fpn_apply_forward(const FpnParams& p, int dtype, int layout,
 cudaError_t launch_fpn_apply_backward(const FpnParams& p, int dtype, int layout,
                                       cudaStream_t stream) {
   const LevelOffsets lo = offsets(p, true);
-  if (lo.start[p.L] == 0) return cudaSuccess;
-  ARFE_DISPATCH(apply_bwd_gates, blocks_for(lo.start[p.L]), p, lo);
+  if (lo.start[lo.n] == 0) return cudaSuccess;
+  ARFE_DISPATCH(apply_bwd_gates, blocks_for(lo.start[lo.n]), p, lo);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const size_t total = (size_t)p.B * p.C * p.Hr * p.Wr;

@@ -218,17 +218,76 @@ __device__ void zero_block(T* __restrict__ out_blk, int n) {
 
 // ---------------------------------------------------------------------------
 // Forward, NCHW features.
-// dynamic smem: [CtaHeader][AxisTable y][AxisTable x][win: cap_px*33][outs: 32*opitch]
+// dynamic smem: [CtaHeader][AxisTable y][AxisTable x][win: kCapPx*33][outs: 32*opitch]
+//
+// Per band (a run of bin rows whose feature rows fit the staged window, normally
+// the whole RoI) every lane precomputes the global offsets of "its" <= 15 window
+// pixels once; the staging loop over channels is then one address add + one
+// cp.async (LDGSTS, no register round trip) per element, with up to 60 copies
+// in flight per thread.  Compute runs lane == channel out of the [pixel][33]
+// window with the bin's column weights held in registers and the column loop
+// unrolled (template NC).
 // ---------------------------------------------------------------------------
+constexpr int kCapPx = 480;               // staged window pixels per band
+constexpr int kStageIters = kCapPx / 32;  // pixels per lane
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+template <int NC>
+__device__ __forceinline__ float bin_sum(const float* __restrict__ base, int rowpitch,
+                                         const float* __restrict__ wy, int nr,
+                                         const float* __restrict__ wx) {
+  float w[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) w[j] = wx[j];
+  float acc = 0.f;
+  for (int jr = 0; jr < nr; ++jr) {
+    const float* __restrict__ q = base + jr * rowpitch;
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) t = fmaf(w[j], q[j * kPitch], t);
+    acc = fmaf(wy[jr], t, acc);
+  }
+  return acc;
+}
+
+__device__ __forceinline__ float bin_sum_any(const float* __restrict__ base, int rowpitch,
+                                             const float* __restrict__ wy, int nr,
+                                             const float* __restrict__ wx, int nc) {
+  switch (nc) {
+    case 1: return bin_sum<1>(base, rowpitch, wy, nr, wx);
+    case 2: return bin_sum<2>(base, rowpitch, wy, nr, wx);
+    case 3: return bin_sum<3>(base, rowpitch, wy, nr, wx);
+    case 4: return bin_sum<4>(base, rowpitch, wy, nr, wx);
+    case 5: return bin_sum<5>(base, rowpitch, wy, nr, wx);
+    case 6: return bin_sum<6>(base, rowpitch, wy, nr, wx);
+    default: break;
+  }
+  float acc = 0.f;
+  for (int jr = 0; jr < nr; ++jr) {
+    const float* __restrict__ q = base + jr * rowpitch;
+    float t = 0.f;
+    for (int j = 0; j < nc; ++j) t = fmaf(wx[j], q[j * kPitch], t);
+    acc = fmaf(wy[jr], t, acc);
+  }
+  return acc;
+}
+
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
-roi_fuse_fwd_nchw(const RoiFuseParams p, int cap_px, int opitch) {
+__global__ void __launch_bounds__(kThreads, 3)
+roi_fuse_fwd_nchw(const RoiFuseParams p, int opitch) {
   extern __shared__ __align__(16) unsigned char smem[];
   CtaHeader& hd = *reinterpret_cast<CtaHeader*>(smem);
   AxisTable& ty = *reinterpret_cast<AxisTable*>(smem + 128);
   AxisTable& tx = *reinterpret_cast<AxisTable*>(smem + 128 + sizeof(AxisTable));
   float* win = reinterpret_cast<float*>(smem + 128 + 2 * sizeof(AxisTable));
-  float* outs = win + (size_t)cap_px * kPitch;
+  float* outs = win + (size_t)kCapPx * kPitch;
 
   const int k = blockIdx.x / p.R, r = blockIdx.x % p.R;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -241,86 +300,101 @@ roi_fuse_fwd_nchw(const RoiFuseParams p, int cap_px, int opitch) {
     return;
   }
   const int ww = hd.xmax - hd.xmin + 1;
-  if (hd.overflow || (long long)hd.max_rows * ww > cap_px) {
+  if (hd.overflow || (long long)hd.max_rows * ww > kCapPx) {
     forward_generic<T, false>(p, hd, out_blk);
     return;
   }
   const int H = hd.H, W = hd.W;
+  const size_t HW = (size_t)H * W;
   const float count = hd.g.count;
   const T* __restrict__ fimg =
-      static_cast<const T*>(p.feats[hd.lvl]) + (size_t)hd.g.batch * C * H * W;
+      static_cast<const T*>(p.feats[hd.lvl]) + (size_t)hd.g.batch * C * HW;
   const float inv_ww = 1.0f / (float)ww;
+  const int rowpitch = ww * kPitch;
 
-  for (int c0 = 0; c0 < C; c0 += kChunk) {
-    const int cc = min(kChunk, C - c0);
-    int ph0 = 0;
-    while (ph0 < PH) {
-      // Greedy band [ph0, ph1): as many bin rows as fit the staged window.
-      int r0 = 0x7fffffff, r1 = -1, ph1 = ph0;
-      while (ph1 < PH) {
-        int a = r0, b = r1;
-        if (ty.cnt[ph1] > 0) {
-          a = min(a, ty.first[ph1]);
-          b = max(b, ty.first[ph1] + ty.cnt[ph1] - 1);
-        }
-        if (b >= a && (long long)(b - a + 1) * ww > cap_px) break;
-        r0 = a; r1 = b; ++ph1;
+  int ph0 = 0;
+  while (ph0 < PH) {
+    // Greedy band [ph0, ph1): as many bin rows as fit the staged window.
+    int r0 = 0x7fffffff, r1 = -1, ph1 = ph0;
+    while (ph1 < PH) {
+      int a = r0, b = r1;
+      if (ty.cnt[ph1] > 0) {
+        a = min(a, ty.first[ph1]);
+        b = max(b, ty.first[ph1] + ty.cnt[ph1] - 1);
       }
-      if (r1 >= r0) {
-        // ---- stage rows r0..r1, cols xmin..xmax, channels c0..c0+cc ----
-        const int npx = (r1 - r0 + 1) * ww;
-        const T* __restrict__ src = fimg + (size_t)c0 * H * W + (size_t)r0 * W + hd.xmin;
-        for (int c = warp; c < cc; c += kWarps) {
-          const T* __restrict__ plane = src + (size_t)c * H * W;
-#pragma unroll 4
-          for (int px = lane; px < npx; px += 32) {
-            int row, col;
-            split_px(px, ww, inv_ww, row, col);
-            win[px * kPitch + c] = to_f(plane[(size_t)row * W + col]);
+      if (b >= a && (b - a + 1) * ww > kCapPx) break;
+      r0 = a; r1 = b; ++ph1;
+    }
+    const int npx = (r1 >= r0) ? (r1 - r0 + 1) * ww : 0;
+    const int nbins = (ph1 - ph0) * PW;
+    const int run = nbins;  // contiguous output floats per channel for this band
+
+    // global offsets (within a channel plane) of this lane's window pixels
+    int goff[kStageIters];
+#pragma unroll
+    for (int i = 0; i < kStageIters; ++i) {
+      const int px = lane + 32 * i;
+      int row, col;
+      split_px(px, ww, inv_ww, row, col);
+      goff[i] = (px < npx) ? (r0 + row) * W + hd.xmin + col : -1;
+    }
+
+    for (int c0 = 0; c0 < C; c0 += kChunk) {
+      const int cc = min(kChunk, C - c0);
+      // ---- stage the band's window for channels c0..c0+cc ----
+      for (int c = warp; c < cc; c += kWarps) {
+        const T* __restrict__ plane = fimg + (size_t)(c0 + c) * HW;
+        float* __restrict__ dst = win + lane * kPitch + c;
+#pragma unroll
+        for (int i = 0; i < kStageIters; ++i) {
+          if (goff[i] >= 0) {
+            if constexpr (sizeof(T) == 4)
+              cp_async4(dst + i * 32 * kPitch, reinterpret_cast<const float*>(plane) + goff[i]);
+            else
+              dst[i * 32 * kPitch] = to_f(plane[goff[i]]);
           }
         }
       }
+      if constexpr (sizeof(T) == 4) cp_async_wait_all();
       __syncthreads();
       // ---- compute: warp-strided over bins of the band, lane == channel ----
-      const int nbins = (ph1 - ph0) * PW;
       for (int bi = warp; bi < nbins; bi += kWarps) {
         const int ph = ph0 + bi / PW, pw = bi % PW;
         const int nr = ty.cnt[ph], nc = tx.cnt[pw];
-        float acc = 0.f;
-        if (nr > 0 && nc > 0 && lane < cc) {
-          const float* __restrict__ wy = ty.w + ty.off[ph];
-          const float* __restrict__ wx = tx.w + tx.off[pw];
-          const float* __restrict__ base =
-              win + ((size_t)(ty.first[ph] - r0) * ww + (tx.first[pw] - hd.xmin)) * kPitch + lane;
-          for (int jr = 0; jr < nr; ++jr) {
-            const float* __restrict__ wrow = base + (size_t)jr * ww * kPitch;
-            float t = 0.f;
-            for (int jc = 0; jc < nc; ++jc) t = fmaf(wx[jc], wrow[jc * kPitch], t);
-            acc = fmaf(wy[jr], t, acc);
-          }
-        }
         if (lane < cc) {
+          float acc = 0.f;
+          if (nr > 0 && nc > 0)
+            acc = bin_sum_any(win + ((ty.first[ph] - r0) * ww + (tx.first[pw] - hd.xmin)) * kPitch + lane,
+                              rowpitch, ty.w + ty.off[ph], nr, tx.w + tx.off[pw], nc);
           const float v = __fdiv_rn(acc, count);
           if (opitch > 0)
-            outs[lane * opitch + ph * PW + pw] = v;
+            outs[lane * opitch + bi] = v;
           else
-            out_blk[(size_t)(c0 + lane) * PHW + ph * PW + pw] = from_f<T>(v);
+            out_blk[(size_t)(c0 + lane) * PHW + ph0 * PW + bi] = from_f<T>(v);
         }
       }
       __syncthreads();
-      ph0 = ph1;
-    }
-    if (opitch > 0) {
-      // ---- coalesced write of the finished [cc][PHW] block ----
-      T* __restrict__ dst = out_blk + (size_t)c0 * PHW;
-      const int total = cc * PHW;
-      for (int e = tid; e < total; e += kThreads) {
-        const int c = e / PHW;
-        const int b = e - c * PHW;
-        dst[e] = from_f<T>(outs[c * opitch + b]);
+      if (opitch > 0) {
+        // ---- coalesced write: per channel a run of `run` floats at bin ph0*PW ----
+        T* __restrict__ dst = out_blk + (size_t)c0 * PHW + ph0 * PW;
+        const int total = cc * run;
+        if (run == PHW) {
+          for (int e = tid; e < total; e += kThreads) {
+            const int c = e / PHW;
+            dst[e] = from_f<T>(outs[c * opitch + (e - c * PHW)]);
+          }
+        } else {
+          for (int e = tid; e < total; e += kThreads) {
+            const int c = e / run;
+            const int b = e - c * run;
+            dst[(size_t)c * PHW + b] = from_f<T>(outs[c * opitch + b]);
+          }
+        }
+        // the next chunk's post-staging __syncthreads orders the reuse of outs
       }
-      // next chunk's first __syncthreads (after staging) orders outs reuse
     }
+    __syncthreads();
+    ph0 = ph1;
   }
 }
 
@@ -564,7 +638,6 @@ __global__ void roi_fuse_taps_kernel(const RoiFuseParams p, int max_grid,
 // ---------------------------------------------------------------------------
 constexpr int kHdrBytes = 128 + 2 * (int)sizeof(AxisTable);
 static_assert(sizeof(CtaHeader) <= 128, "header must fit its slot");
-constexpr int kFwdSmemNCHW = 110 * 1024;  // 2 CTAs / SM
 constexpr int kMaxSmem = 220 * 1024;
 
 template <typename K>
@@ -578,16 +651,14 @@ cudaError_t launch_roi_fuse_forward(const RoiFuseParams& p, int dtype, int layou
   const int grid = p.K * p.R;
   cudaError_t e;
   if (layout == 0) {
-    int opitch = (PHW <= 512) ? (PHW | 1) : 0;  // staged output block or direct stores
-    int smem = kFwdSmemNCHW;
-    int cap_px = (smem - kHdrBytes - kChunk * opitch * 4) / (kPitch * 4);
-    if (cap_px < 64) { opitch = 0; cap_px = (smem - kHdrBytes) / (kPitch * 4); }
+    int opitch = (PHW <= 256) ? (PHW | 1) : 0;  // staged output block or direct stores
+    const int smem = kHdrBytes + kCapPx * kPitch * 4 + kChunk * opitch * 4;
     if (dtype == 0) {
       if ((e = set_smem(roi_fuse_fwd_nchw<float>, smem)) != cudaSuccess) return e;
-      roi_fuse_fwd_nchw<float><<<grid, kThreads, smem, stream>>>(p, cap_px, opitch);
+      roi_fuse_fwd_nchw<float><<<grid, kThreads, smem, stream>>>(p, opitch);
     } else {
       if ((e = set_smem(roi_fuse_fwd_nchw<__nv_bfloat16>, smem)) != cudaSuccess) return e;
-      roi_fuse_fwd_nchw<__nv_bfloat16><<<grid, kThreads, smem, stream>>>(p, cap_px, opitch);
+      roi_fuse_fwd_nchw<__nv_bfloat16><<<grid, kThreads, smem, stream>>>(p, opitch);
     }
   } else {
     int opitch = PHW | 1;
