@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/arfe_b200.h"
@@ -95,6 +96,10 @@ int arfe_roi_fuse_forward(const void* const* feats, const int32_t* H, const int3
   }
   REQUIRE(aligned(out, esize(dtype)) && aligned(rois, 4), ARFE_E_ALIGN, "%s: out/rois misaligned", fn);
   p.out = out; p.lvl_out = lvl_out; p.boxes_out = boxes_out;
+  {
+    const char* ev = getenv("ARFE_FWD_SKIP");  // profiling aid, default off
+    p.debug_skip = ev ? atoi(ev) : 0;
+  }
   return cuda_result(arfe::launch_roi_fuse_forward(p, dtype, layout, (cudaStream_t)stream), fn);
 }
 
@@ -117,6 +122,10 @@ int arfe_roi_fuse_backward(const void* dout, const int32_t* H, const int32_t* W,
     p.dfeats[l] = dfeats[l];
   }
   p.dout = dout;
+  {
+    const char* ev = getenv("ARFE_BWD_VEC");  // tuning knob, default scalar
+    p.bwd_vec = ev ? atoi(ev) : 0;
+  }
   return cuda_result(arfe::launch_roi_fuse_backward(p, dtype, layout, (cudaStream_t)stream), fn);
 }
 

@@ -21,6 +21,8 @@ struct RoiFuseParams {
   const void* dout;  // backward input
   int32_t* lvl_out;
   float* boxes_out;
+  int bwd_vec;       // backward: 128-bit vector reductions (1) or scalar (0)
+  int debug_skip;    // profiling aid (ARFE_FWD_SKIP): 1 compute, 2 staging, 4 write-out, 8 all but setup
 };
 
 cudaError_t launch_roi_fuse_forward(const RoiFuseParams& p, int dtype, int layout,

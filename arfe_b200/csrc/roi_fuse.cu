@@ -169,7 +169,8 @@ __device__ void forward_generic(const RoiFuseParams& p, const CtaHeader& hd,
   const T* __restrict__ f = static_cast<const T*>(p.feats[hd.lvl]);
   const int H = hd.H, W = hd.W, C = p.C;
   const RoiGeom& g = hd.g;
-  for (int bin = warp; bin < PHW; bin += kWarps) {
+  const int nwarps = blockDim.x >> 5;
+  for (int bin = warp; bin < PHW; bin += nwarps) {
     const int ph = bin / p.PW, pw = bin % p.PW;
     for (int c = lane; c < C; c += 32) {
       float acc = 0.f;
@@ -200,6 +201,16 @@ __device__ void forward_generic(const RoiFuseParams& p, const CtaHeader& hd,
       out_blk[(size_t)c * PHW + bin] = from_f<T>(__fdiv_rn(acc, g.count));
     }
   }
+}
+
+// Vector float reductions to global memory (sm_90+): one L2 atomic transaction
+// for 4 (2) consecutive floats; the address must be 16 (8) byte aligned.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};\n" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 
 // px -> (row, col) of a window `ww` pixels wide without an integer division.
@@ -239,44 +250,67 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
+// Stage N*32 window pixels of one channel plane with N loads in flight, then N
+// conflict-free stores ([pixel][33] layout).  4-byte cp.async (LDGSTS) was
+// measured slower here: it occupies the LSU/MIO pipe ~8 cycles per warp-copy,
+// LDG + STS about half of that.  No predicates: offsets past the window are
+// clamped to a valid pixel and land in unused slots of the staging buffer.
+template <typename T, int N>
+__device__ __forceinline__ void stage_plane(const T* __restrict__ plane, float* __restrict__ dst,
+                                            const unsigned (&goff)[kStageIters]) {
+  float v[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = to_f(__ldg(plane + goff[i]));
+#pragma unroll
+  for (int i = 0; i < N; ++i) dst[i * 32 * kPitch] = v[i];
+}
+
+template <typename T>
+__device__ __forceinline__ void stage_plane_n(int n, const T* __restrict__ plane,
+                                              float* __restrict__ dst,
+                                              const unsigned (&goff)[kStageIters]) {
+  switch (n) {
+#define ARFE_CASE(N) case N: stage_plane<T, N>(plane, dst, goff); break;
+    ARFE_CASE(1) ARFE_CASE(2) ARFE_CASE(3) ARFE_CASE(4) ARFE_CASE(5) ARFE_CASE(6) ARFE_CASE(7)
+    ARFE_CASE(8) ARFE_CASE(9) ARFE_CASE(10) ARFE_CASE(11) ARFE_CASE(12) ARFE_CASE(13) ARFE_CASE(14)
+    ARFE_CASE(15)
+#undef ARFE_CASE
+    default: break;
+  }
+}
+
+// Per-band descriptors (built once per band, read by every chunk).
+struct BandDesc {
+  int4 ph[kMaxPool];  // x: window offset of the bin row's first feature row (floats), y: rows, z: offset of wy
+  int4 pw[kMaxPool];  // x: window offset of the bin column's first feature column, y: cols, z: offset of wx
+};
+
+// All bins of one bin column `pw` (weights in registers), rows ph0..ph1, for
+// the 32 channels of the staged chunk (lane == channel).
 template <int NC>
-__device__ __forceinline__ float bin_sum(const float* __restrict__ base, int rowpitch,
-                                         const float* __restrict__ wy, int nr,
-                                         const float* __restrict__ wx) {
+__device__ __forceinline__ void column_bins(const float* __restrict__ win, const BandDesc& bd,
+                                            const AxisTable& ty, const float* __restrict__ wx,
+                                            int coloff, int rowpitch, int nph, int lane,
+                                            float inv_count, float* __restrict__ outs_lane,
+                                            int PW, int pw) {
   float w[NC];
 #pragma unroll
   for (int j = 0; j < NC; ++j) w[j] = wx[j];
-  float acc = 0.f;
-  for (int jr = 0; jr < nr; ++jr) {
-    const float* __restrict__ q = base + jr * rowpitch;
-    float t = 0.f;
+  const float* __restrict__ colbase = win + coloff + lane;
+  for (int q = 0; q < nph; ++q) {
+    const int4 d = bd.ph[q];
+    const float* __restrict__ p = colbase + d.x;
+    const float* __restrict__ wy = ty.w + d.z;
+    float acc = 0.f;
+    for (int jr = 0; jr < d.y; ++jr) {
+      float t = 0.f;
 #pragma unroll
-    for (int j = 0; j < NC; ++j) t = fmaf(w[j], q[j * kPitch], t);
-    acc = fmaf(wy[jr], t, acc);
+      for (int j = 0; j < NC; ++j) t = fmaf(w[j], p[j * kPitch], t);
+      acc = fmaf(wy[jr], t, acc);
+      p += rowpitch;
+    }
+    outs_lane[q * PW + pw] = acc * inv_count;
   }
-  return acc;
-}
-
-__device__ __forceinline__ float bin_sum_any(const float* __restrict__ base, int rowpitch,
-                                             const float* __restrict__ wy, int nr,
-                                             const float* __restrict__ wx, int nc) {
-  switch (nc) {
-    case 1: return bin_sum<1>(base, rowpitch, wy, nr, wx);
-    case 2: return bin_sum<2>(base, rowpitch, wy, nr, wx);
-    case 3: return bin_sum<3>(base, rowpitch, wy, nr, wx);
-    case 4: return bin_sum<4>(base, rowpitch, wy, nr, wx);
-    case 5: return bin_sum<5>(base, rowpitch, wy, nr, wx);
-    case 6: return bin_sum<6>(base, rowpitch, wy, nr, wx);
-    default: break;
-  }
-  float acc = 0.f;
-  for (int jr = 0; jr < nr; ++jr) {
-    const float* __restrict__ q = base + jr * rowpitch;
-    float t = 0.f;
-    for (int j = 0; j < nc; ++j) t = fmaf(wx[j], q[j * kPitch], t);
-    acc = fmaf(wy[jr], t, acc);
-  }
-  return acc;
 }
 
 template <typename T>
@@ -286,17 +320,19 @@ roi_fuse_fwd_nchw(const RoiFuseParams p, int opitch) {
   CtaHeader& hd = *reinterpret_cast<CtaHeader*>(smem);
   AxisTable& ty = *reinterpret_cast<AxisTable*>(smem + 128);
   AxisTable& tx = *reinterpret_cast<AxisTable*>(smem + 128 + sizeof(AxisTable));
-  float* win = reinterpret_cast<float*>(smem + 128 + 2 * sizeof(AxisTable));
+  BandDesc& bd = *reinterpret_cast<BandDesc*>(smem + 128 + 2 * sizeof(AxisTable));
+  float* win = reinterpret_cast<float*>(smem + 128 + 2 * sizeof(AxisTable) + sizeof(BandDesc));
   float* outs = win + (size_t)kCapPx * kPitch;
 
   const int k = blockIdx.x / p.R, r = blockIdx.x % p.R;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nthr = blockDim.x, nw = nthr >> 5;
   const int PH = p.PH, PW = p.PW, PHW = PH * PW, C = p.C;
   T* __restrict__ out_blk =
       static_cast<T*>(p.out) + ((size_t)k * p.R + r) * C * PHW;
 
   if (!setup_cta(p, k, r, hd, ty, tx)) {
-    zero_block(out_blk, C * PHW);
+    for (int i = tid; i < C * PHW; i += nthr) out_blk[i] = from_f<T>(0.f);
     return;
   }
   const int ww = hd.xmax - hd.xmin + 1;
@@ -304,9 +340,10 @@ roi_fuse_fwd_nchw(const RoiFuseParams p, int opitch) {
     forward_generic<T, false>(p, hd, out_blk);
     return;
   }
+  if (p.debug_skip & 8) return;  // setup only
   const int H = hd.H, W = hd.W;
   const size_t HW = (size_t)H * W;
-  const float count = hd.g.count;
+  const float inv_count = 1.0f / hd.g.count;
   const T* __restrict__ fimg =
       static_cast<const T*>(p.feats[hd.lvl]) + (size_t)hd.g.batch * C * HW;
   const float inv_ww = 1.0f / (float)ww;
@@ -326,74 +363,86 @@ roi_fuse_fwd_nchw(const RoiFuseParams p, int opitch) {
       r0 = a; r1 = b; ++ph1;
     }
     const int npx = (r1 >= r0) ? (r1 - r0 + 1) * ww : 0;
-    const int nbins = (ph1 - ph0) * PW;
-    const int run = nbins;  // contiguous output floats per channel for this band
+    const int nph = ph1 - ph0;
+    const int run = nph * PW;  // contiguous output floats per channel for this band
 
-    // global offsets (within a channel plane) of this lane's window pixels
-    int goff[kStageIters];
+    __syncthreads();  // previous band's readers of bd/outs are done
+    if (tid < nph) {
+      const int q = ph0 + tid;
+      bd.ph[tid] = make_int4(ty.cnt[q] > 0 ? (ty.first[q] - r0) * rowpitch : 0, ty.cnt[q], ty.off[q], 0);
+    } else if (tid >= 32 && tid < 32 + PW) {
+      const int q = tid - 32;
+      bd.pw[q] = make_int4(tx.cnt[q] > 0 ? (tx.first[q] - hd.xmin) * kPitch : 0, tx.cnt[q], tx.off[q], 0);
+    }
+
+    // global offsets (within a channel plane) of this lane's window pixels;
+    // pixels past the window (last iteration only) re-read the first pixel
+    unsigned goff[kStageIters];
+    const int niter = (npx + 31) >> 5;
 #pragma unroll
     for (int i = 0; i < kStageIters; ++i) {
       const int px = lane + 32 * i;
-      int row, col;
-      split_px(px, ww, inv_ww, row, col);
-      goff[i] = (px < npx) ? (r0 + row) * W + hd.xmin + col : -1;
+      int row = 0, col = 0;
+      if (px < npx) split_px(px, ww, inv_ww, row, col);
+      goff[i] = (unsigned)((r0 + row) * W + hd.xmin + col);
+    }
+    if (npx == 0) {
+#pragma unroll
+      for (int i = 0; i < kStageIters; ++i) goff[i] = 0;
     }
 
     for (int c0 = 0; c0 < C; c0 += kChunk) {
       const int cc = min(kChunk, C - c0);
       // ---- stage the band's window for channels c0..c0+cc ----
-      for (int c = warp; c < cc; c += kWarps) {
+      for (int c = warp; c < cc; c += nw) {
         const T* __restrict__ plane = fimg + (size_t)(c0 + c) * HW;
         float* __restrict__ dst = win + lane * kPitch + c;
-#pragma unroll
-        for (int i = 0; i < kStageIters; ++i) {
-          if (goff[i] >= 0) {
-            if constexpr (sizeof(T) == 4)
-              cp_async4(dst + i * 32 * kPitch, reinterpret_cast<const float*>(plane) + goff[i]);
-            else
-              dst[i * 32 * kPitch] = to_f(plane[goff[i]]);
+        if (!(p.debug_skip & 2)) stage_plane_n<T>(niter, plane, dst, goff);
+      }
+      __syncthreads();
+      // ---- compute: one warp per bin column, lane == channel ----
+      if (lane < cc && !(p.debug_skip & 1)) {
+        float* __restrict__ outs_lane = opitch > 0 ? outs + lane * opitch : nullptr;
+        for (int pw = warp; pw < PW; pw += nw) {
+          const int4 d = bd.pw[pw];
+          const float* __restrict__ wx = tx.w + d.z;
+          if (opitch > 0 && d.y >= 1 && d.y <= 6) {
+            switch (d.y) {
+              case 1: column_bins<1>(win, bd, ty, wx, d.x, rowpitch, nph, lane, inv_count, outs_lane, PW, pw); break;
+              case 2: column_bins<2>(win, bd, ty, wx, d.x, rowpitch, nph, lane, inv_count, outs_lane, PW, pw); break;
+              case 3: column_bins<3>(win, bd, ty, wx, d.x, rowpitch, nph, lane, inv_count, outs_lane, PW, pw); break;
+              case 4: column_bins<4>(win, bd, ty, wx, d.x, rowpitch, nph, lane, inv_count, outs_lane, PW, pw); break;
+              case 5: column_bins<5>(win, bd, ty, wx, d.x, rowpitch, nph, lane, inv_count, outs_lane, PW, pw); break;
+              default: column_bins<6>(win, bd, ty, wx, d.x, rowpitch, nph, lane, inv_count, outs_lane, PW, pw); break;
+            }
+          } else {
+            for (int q = 0; q < nph; ++q) {
+              const int4 e = bd.ph[q];
+              const float* __restrict__ pp = win + d.x + e.x + lane;
+              float acc = 0.f;
+              for (int jr = 0; jr < e.y; ++jr) {
+                float t = 0.f;
+                for (int j = 0; j < d.y; ++j) t = fmaf(wx[j], pp[j * kPitch], t);
+                acc = fmaf(ty.w[e.z + jr], t, acc);
+                pp += rowpitch;
+              }
+              const float v = acc * inv_count;
+              if (opitch > 0) outs_lane[q * PW + pw] = v;
+              else out_blk[(size_t)(c0 + lane) * PHW + (ph0 + q) * PW + pw] = from_f<T>(v);
+            }
           }
         }
       }
-      if constexpr (sizeof(T) == 4) cp_async_wait_all();
       __syncthreads();
-      // ---- compute: warp-strided over bins of the band, lane == channel ----
-      for (int bi = warp; bi < nbins; bi += kWarps) {
-        const int ph = ph0 + bi / PW, pw = bi % PW;
-        const int nr = ty.cnt[ph], nc = tx.cnt[pw];
-        if (lane < cc) {
-          float acc = 0.f;
-          if (nr > 0 && nc > 0)
-            acc = bin_sum_any(win + ((ty.first[ph] - r0) * ww + (tx.first[pw] - hd.xmin)) * kPitch + lane,
-                              rowpitch, ty.w + ty.off[ph], nr, tx.w + tx.off[pw], nc);
-          const float v = __fdiv_rn(acc, count);
-          if (opitch > 0)
-            outs[lane * opitch + bi] = v;
-          else
-            out_blk[(size_t)(c0 + lane) * PHW + ph0 * PW + bi] = from_f<T>(v);
-        }
-      }
-      __syncthreads();
-      if (opitch > 0) {
+      if (opitch > 0 && !(p.debug_skip & 4)) {
         // ---- coalesced write: per channel a run of `run` floats at bin ph0*PW ----
         T* __restrict__ dst = out_blk + (size_t)c0 * PHW + ph0 * PW;
-        const int total = cc * run;
-        if (run == PHW) {
-          for (int e = tid; e < total; e += kThreads) {
-            const int c = e / PHW;
-            dst[e] = from_f<T>(outs[c * opitch + (e - c * PHW)]);
-          }
-        } else {
-          for (int e = tid; e < total; e += kThreads) {
-            const int c = e / run;
-            const int b = e - c * run;
+        for (int c = warp; c < cc; c += nw)
+          for (int b = lane; b < run; b += 32)
             dst[(size_t)c * PHW + b] = from_f<T>(outs[c * opitch + b]);
-          }
-        }
         // the next chunk's post-staging __syncthreads orders the reuse of outs
       }
     }
-    __syncthreads();
     ph0 = ph1;
   }
 }
@@ -458,6 +507,51 @@ roi_fuse_fwd_nhwc(const RoiFuseParams p, int opitch) {
   }
 }
 
+
+// Backward inner loops: one window pixel per lane, walk the channels.  PHW_T is
+// the compile-time bins-per-channel (0 = runtime) so the four taps of every
+// unrolled channel are LDS with immediate offsets; the destination pointer
+// advances by the channel stride.
+template <int PHW_T>
+__device__ __forceinline__ void bwd_px_scalar(const float* __restrict__ dsm, int PHW, int cc,
+                                              float w00, float w01, float w10, float w11,
+                                              int i00, int i01, int i10, int i11,
+                                              float* __restrict__ dst, size_t cstride) {
+  const int phw = PHW_T ? PHW_T : PHW;
+  const float* __restrict__ d0 = dsm + i00;
+  const float* __restrict__ d1 = dsm + i01;
+  const float* __restrict__ d2 = dsm + i10;
+  const float* __restrict__ d3 = dsm + i11;
+#pragma unroll 8
+  for (int c = 0; c < cc; ++c) {
+    const float v = w00 * d0[c * phw] + w01 * d1[c * phw] + w10 * d2[c * phw] + w11 * d3[c * phw];
+    atomicAdd(dst, v);
+    dst += cstride;
+  }
+}
+
+template <int PHW_T>
+__device__ __forceinline__ void bwd_px_vec4(const float* __restrict__ dsm, int PHW, int cc,
+                                            float w00, float w01, float w10, float w11,
+                                            int i00, int i01, int i10, int i11,
+                                            float* __restrict__ dst, size_t cstride, int lane) {
+  const int phw = PHW_T ? PHW_T : PHW;
+  const float* __restrict__ d0 = dsm + i00;
+  const float* __restrict__ d1 = dsm + i01;
+  const float* __restrict__ d2 = dsm + i10;
+  const float* __restrict__ d3 = dsm + i11;
+  const bool lead = (lane & 3) == 0;
+#pragma unroll 4
+  for (int c = 0; c < cc; ++c) {
+    const float v = w00 * d0[c * phw] + w01 * d1[c * phw] + w10 * d2[c * phw] + w11 * d3[c * phw];
+    const float v1 = __shfl_down_sync(0xffffffffu, v, 1);
+    const float v2 = __shfl_down_sync(0xffffffffu, v, 2);
+    const float v3 = __shfl_down_sync(0xffffffffu, v, 3);
+    if (lead) red_add_v4(dst, v, v1, v2, v3);
+    dst += cstride;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Backward.  Thread == one pixel of the RoI's feature window; it looks up the
 // (usually <= 2 x 2) bins that sample it once, keeps their weights in
@@ -468,7 +562,7 @@ roi_fuse_fwd_nhwc(const RoiFuseParams p, int opitch) {
 // dynamic smem: [CtaHeader][AxisTable y][AxisTable x][dsm: cb*PHW floats]
 // ---------------------------------------------------------------------------
 template <typename T, bool kNHWC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 roi_fuse_bwd(const RoiFuseParams p, int cb /* channels staged per pass */) {
   extern __shared__ __align__(16) unsigned char smem[];
   CtaHeader& hd = *reinterpret_cast<CtaHeader*>(smem);
@@ -518,10 +612,22 @@ roi_fuse_bwd(const RoiFuseParams p, int cb /* channels staged per pass */) {
     return;
   }
 
-  const int ww = hd.xmax - hd.xmin + 1, wh = hd.ymax - hd.ymin + 1;
+  // Window columns are widened to a multiple of VEC so that VEC consecutive
+  // lanes own one aligned pixel group and their sums leave in ONE vector
+  // reduction (red.global.add.v4.f32 / .v2.f32): global float atomics are the
+  // bottleneck of this kernel and this cuts them 4x.  NHWC vectorises over
+  // channels instead.
+  int vec = 1;
+  if (!kNHWC) {
+    if (p.bwd_vec && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(dimg) & 15) == 0) vec = 4;
+  }
+  const int xa = hd.xmin & ~(vec - 1);
+  const int ww = (hd.xmax | (vec - 1)) - xa + 1, wh = hd.ymax - hd.ymin + 1;
   const int npx = ww * wh;
   const float inv_ww = 1.0f / (float)ww;
   const float inv_count = 1.0f / g.count;
+  const int lane = tid & 31;
+  const size_t HW = (size_t)H * W;
 
   for (int c0 = 0; c0 < C; c0 += cb) {
     const int cc = min(cb, C - c0);
@@ -530,27 +636,29 @@ roi_fuse_bwd(const RoiFuseParams p, int cb /* channels staged per pass */) {
       dsm[e] = to_f(dout_blk[(size_t)c0 * PHW + e]);
     __syncthreads();
 
-    for (int px = tid; px < npx; px += kThreads) {
-      int wr, wc;
-      split_px(px, ww, inv_ww, wr, wc);
-      const int row = hd.ymin + wr, col = hd.xmin + wc;
+    for (int px0 = tid - lane; px0 < npx; px0 += kThreads) {  // warp-uniform bound
+      const int px = px0 + lane;
+      int wr = 0, wc = 0;
+      if (px < npx) split_px(px, ww, inv_ww, wr, wc);
+      const int row = hd.ymin + wr, col = xa + wc;
       // bins covering this row / column (contiguous ranges)
       int pa = -1, na = 0, pb = -1, nb = 0;
-      for (int q = 0; q < PH; ++q)
-        if (ty.cnt[q] > 0 && row >= ty.first[q] && row < ty.first[q] + ty.cnt[q]) {
-          if (pa < 0) pa = q;
-          na = q - pa + 1;
-        }
-      for (int q = 0; q < PW; ++q)
-        if (tx.cnt[q] > 0 && col >= tx.first[q] && col < tx.first[q] + tx.cnt[q]) {
-          if (pb < 0) pb = q;
-          nb = q - pb + 1;
-        }
-      if (na == 0 || nb == 0) continue;
+      if (px < npx) {
+        for (int q = 0; q < PH; ++q)
+          if (ty.cnt[q] > 0 && row >= ty.first[q] && row < ty.first[q] + ty.cnt[q]) {
+            if (pa < 0) pa = q;
+            na = q - pa + 1;
+          }
+        for (int q = 0; q < PW; ++q)
+          if (tx.cnt[q] > 0 && col >= tx.first[q] && col < tx.first[q] + tx.cnt[q]) {
+            if (pb < 0) pb = q;
+            nb = q - pb + 1;
+          }
+      }
+      const bool live = na > 0 && nb > 0;
       float* __restrict__ dst =
           kNHWC ? dimg + ((size_t)row * W + col) * C + c0
-                : dimg + (size_t)c0 * H * W + (size_t)row * W + col;
-      const size_t cstride = kNHWC ? 1 : (size_t)H * W;
+                : dimg + (size_t)c0 * HW + (size_t)row * W + col;
 
       auto wy_of = [&](int q) -> float {
         const int j = row - ty.first[q];
@@ -560,22 +668,59 @@ roi_fuse_bwd(const RoiFuseParams p, int cb /* channels staged per pass */) {
         const int j = col - tx.first[q];
         return (tx.cnt[q] > 0 && j >= 0 && j < tx.cnt[q]) ? tx.w[tx.off[q] + j] : 0.f;
       };
+      const bool simple = __all_sync(0xffffffffu, na <= 2 && nb <= 2);
 
-      if (na <= 2 && nb <= 2) {
-        const int pa1 = min(pa + 1, PH - 1), pb1 = min(pb + 1, PW - 1);
-        const float wa0 = wy_of(pa) * inv_count;
-        const float wa1 = (na > 1) ? wy_of(pa + 1) * inv_count : 0.f;
-        const float wb0 = wx_of(pb);
-        const float wb1 = (nb > 1) ? wx_of(pb + 1) : 0.f;
-        const float w00 = wa0 * wb0, w01 = wa0 * wb1, w10 = wa1 * wb0, w11 = wa1 * wb1;
-        const int i00 = pa * PW + pb, i01 = pa * PW + pb1, i10 = pa1 * PW + pb, i11 = pa1 * PW + pb1;
-#pragma unroll 4
-        for (int c = 0; c < cc; ++c) {
-          const float* __restrict__ d = dsm + c * PHW;
-          const float v = w00 * d[i00] + w01 * d[i01] + w10 * d[i10] + w11 * d[i11];
-          atomicAdd(dst + (size_t)c * cstride, v);
+      if (simple) {
+        float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
+        int i00 = 0, i01 = 0, i10 = 0, i11 = 0;
+        if (live) {
+          const int pa1 = min(pa + 1, PH - 1), pb1 = min(pb + 1, PW - 1);
+          const float wa0 = wy_of(pa) * inv_count;
+          const float wa1 = (na > 1) ? wy_of(pa + 1) * inv_count : 0.f;
+          const float wb0 = wx_of(pb);
+          const float wb1 = (nb > 1) ? wx_of(pb + 1) : 0.f;
+          w00 = wa0 * wb0; w01 = wa0 * wb1; w10 = wa1 * wb0; w11 = wa1 * wb1;
+          i00 = pa * PW + pb; i01 = pa * PW + pb1; i10 = pa1 * PW + pb; i11 = pa1 * PW + pb1;
         }
-      } else {
+        if (kNHWC) {
+          if (live) {
+            int c = 0;
+            if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+              for (; c + 3 < cc; c += 4) {
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float* __restrict__ d = dsm + (c + u) * PHW;
+                  v[u] = w00 * d[i00] + w01 * d[i01] + w10 * d[i10] + w11 * d[i11];
+                }
+                red_add_v4(dst + c, v[0], v[1], v[2], v[3]);
+              }
+            }
+            for (; c < cc; ++c) {
+              const float* __restrict__ d = dsm + c * PHW;
+              atomicAdd(dst + c, w00 * d[i00] + w01 * d[i01] + w10 * d[i10] + w11 * d[i11]);
+            }
+          }
+        } else if (vec == 4) {
+          // whole warp walks the channels together (shuffles); lanes outside
+          // every bin carry zero weights, a quad of four such lanes is skipped
+          const unsigned livemask = __ballot_sync(0xffffffffu, live);
+          if (livemask) {
+            const bool quad_live = ((livemask >> (lane & ~3)) & 0xfu) != 0;
+            const int lead_lane = quad_live ? lane : 1;  // (1 & 3) != 0: never issues
+            if (PHW == 49)
+              bwd_px_vec4<49>(dsm, PHW, cc, w00, w01, w10, w11, i00, i01, i10, i11, dst, HW, lead_lane);
+            else
+              bwd_px_vec4<0>(dsm, PHW, cc, w00, w01, w10, w11, i00, i01, i10, i11, dst, HW, lead_lane);
+          }
+        } else if (live) {
+          if (PHW == 49)
+            bwd_px_scalar<49>(dsm, PHW, cc, w00, w01, w10, w11, i00, i01, i10, i11, dst, HW);
+          else
+            bwd_px_scalar<0>(dsm, PHW, cc, w00, w01, w10, w11, i00, i01, i10, i11, dst, HW);
+        }
+      } else if (live) {
+        const size_t cstride = kNHWC ? 1 : HW;
         for (int c = 0; c < cc; ++c) {
           const float* __restrict__ d = dsm + c * PHW;
           float v = 0.f;
@@ -637,6 +782,7 @@ __global__ void roi_fuse_taps_kernel(const RoiFuseParams p, int max_grid,
 // Host launchers
 // ---------------------------------------------------------------------------
 constexpr int kHdrBytes = 128 + 2 * (int)sizeof(AxisTable);
+constexpr int kFwdHdrBytes = kHdrBytes + (int)sizeof(BandDesc);
 static_assert(sizeof(CtaHeader) <= 128, "header must fit its slot");
 constexpr int kMaxSmem = 220 * 1024;
 
@@ -652,13 +798,14 @@ cudaError_t launch_roi_fuse_forward(const RoiFuseParams& p, int dtype, int layou
   cudaError_t e;
   if (layout == 0) {
     int opitch = (PHW <= 256) ? (PHW | 1) : 0;  // staged output block or direct stores
-    const int smem = kHdrBytes + kCapPx * kPitch * 4 + kChunk * opitch * 4;
+    const int smem = kFwdHdrBytes + kCapPx * kPitch * 4 + kChunk * opitch * 4;
+    const int threads = (p.PW % 7 == 0) ? 224 : kThreads;  // one warp per bin column
     if (dtype == 0) {
       if ((e = set_smem(roi_fuse_fwd_nchw<float>, smem)) != cudaSuccess) return e;
-      roi_fuse_fwd_nchw<float><<<grid, kThreads, smem, stream>>>(p, opitch);
+      roi_fuse_fwd_nchw<float><<<grid, threads, smem, stream>>>(p, opitch);
     } else {
       if ((e = set_smem(roi_fuse_fwd_nchw<__nv_bfloat16>, smem)) != cudaSuccess) return e;
-      roi_fuse_fwd_nchw<__nv_bfloat16><<<grid, kThreads, smem, stream>>>(p, opitch);
+      roi_fuse_fwd_nchw<__nv_bfloat16><<<grid, threads, smem, stream>>>(p, opitch);
     }
   } else {
     int opitch = PHW | 1;
