@@ -79,7 +79,7 @@ const char* arfe_last_error(void) { return g_err; }
 int arfe_roi_fuse_forward(const void* const* feats, const int32_t* H, const int32_t* W,
                           const float* spatial_scale, int L, int B, int C, const float* rois,
                           int K, int regions, float facs, int PH, int PW, int sampling_ratio,
-                          float finest_scale, int dtype, int layout, void* out,
+                          float finest_scale, int dtype, int layout, int out_layout, void* out,
                           int32_t* lvl_out, float* boxes_out, void* stream) {
   const char* fn = "arfe_roi_fuse_forward";
   arfe::RoiFuseParams p;
@@ -95,7 +95,17 @@ int arfe_roi_fuse_forward(const void* const* feats, const int32_t* H, const int3
     p.feats[l] = feats[l];
   }
   REQUIRE(aligned(out, esize(dtype)) && aligned(rois, 4), ARFE_E_ALIGN, "%s: out/rois misaligned", fn);
-  p.out = out; p.lvl_out = lvl_out; p.boxes_out = boxes_out;
+  REQUIRE(out_layout == ARFE_NCHW || out_layout == ARFE_NHWC, ARFE_E_ENUM, "%s: unknown out_layout %d", fn, out_layout);
+  if (out_layout == ARFE_NHWC) {
+    REQUIRE(layout == ARFE_NHWC && C % (dtype == ARFE_F32 ? 4 : 8) == 0, ARFE_E_UNSUPPORTED,
+            "%s: channels-last output needs channels-last features and C %% %d == 0", fn, dtype == ARFE_F32 ? 4 : 8);
+  }
+  if (layout == ARFE_NHWC && C % (dtype == ARFE_F32 ? 4 : 8) == 0) {
+    for (int l = 0; l < L; ++l)
+      REQUIRE(aligned(feats[l], 16), ARFE_E_ALIGN, "%s: feats[%d] must be 16-byte aligned", fn, l);
+    REQUIRE(aligned(out, 16), ARFE_E_ALIGN, "%s: out must be 16-byte aligned", fn);
+  }
+  p.out = out; p.lvl_out = lvl_out; p.boxes_out = boxes_out; p.out_cl = out_layout == ARFE_NHWC;
   {
     const char* ev = getenv("ARFE_FWD_SKIP");  // profiling aid, default off
     p.debug_skip = ev ? atoi(ev) : 0;
@@ -103,7 +113,7 @@ int arfe_roi_fuse_forward(const void* const* feats, const int32_t* H, const int3
   return cuda_result(arfe::launch_roi_fuse_forward(p, dtype, layout, (cudaStream_t)stream), fn);
 }
 
-int arfe_roi_fuse_backward(const void* dout, const int32_t* H, const int32_t* W,
+int arfe_roi_fuse_backward(const void* dout, int dout_layout, const int32_t* H, const int32_t* W,
                            const float* spatial_scale, int L, int B, int C, const float* rois,
                            int K, int regions, float facs, int PH, int PW, int sampling_ratio,
                            float finest_scale, int dtype, int layout, float* const* dfeats,
@@ -121,12 +131,57 @@ int arfe_roi_fuse_backward(const void* dout, const int32_t* H, const int32_t* W,
     REQUIRE(aligned(dfeats[l], 4), ARFE_E_ALIGN, "%s: dfeats[%d] misaligned", fn, l);
     p.dfeats[l] = dfeats[l];
   }
-  p.dout = dout;
+  REQUIRE(dout_layout == ARFE_NCHW || dout_layout == ARFE_NHWC, ARFE_E_ENUM, "%s: unknown dout_layout %d", fn, dout_layout);
+  p.dout = dout; p.dout_cl = dout_layout == ARFE_NHWC;
   {
     const char* ev = getenv("ARFE_BWD_VEC");  // tuning knob, default scalar
     p.bwd_vec = ev ? atoi(ev) : 0;
   }
   return cuda_result(arfe::launch_roi_fuse_backward(p, dtype, layout, (cudaStream_t)stream), fn);
+}
+
+size_t arfe_roi_fuse_pull_workspace_bytes(int K, int regions, int L) {
+  if (K <= 0 || (regions != 1 && regions != 3) || L < 1 || L > ARFE_MAX_LEVELS) return 0;
+  return arfe::roi_pull_workspace_bytes(K, regions, L);
+}
+
+int arfe_roi_fuse_backward_pull(const void* dout, const int32_t* H, const int32_t* W,
+                                const float* spatial_scale, int L, int B, int C, const float* rois,
+                                int K, int regions, float facs, int PH, int PW, int sampling_ratio,
+                                float finest_scale, int dtype, float* const* dfeats,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  const char* fn = "arfe_roi_fuse_backward_pull";
+  arfe::RoiFuseParams p;
+  int rc = fill_roi_params(fn, p, H, W, spatial_scale, L, B, C, rois, K, regions, facs, PH, PW,
+                           sampling_ratio, finest_scale, dtype, ARFE_NHWC);
+  if (rc) return rc;
+  REQUIRE(dfeats, ARFE_E_NULL, "%s: dfeats is NULL", fn);
+  REQUIRE(B >= 1, ARFE_E_SHAPE, "%s: B=0", fn);
+  REQUIRE(C % (dtype == ARFE_F32 ? 4 : 8) == 0, ARFE_E_UNSUPPORTED, "%s: C must be a multiple of %d",
+          fn, dtype == ARFE_F32 ? 4 : 8);
+  for (int l = 0; l < L; ++l) {
+    REQUIRE(dfeats[l], ARFE_E_NULL, "%s: dfeats[%d] is NULL", fn, l);
+    REQUIRE(aligned(dfeats[l], 16), ARFE_E_ALIGN, "%s: dfeats[%d] must be 16-byte aligned", fn, l);
+    p.dfeats[l] = dfeats[l];
+  }
+  if (K == 0) {  // nothing is pooled: the gradient is all zeros, still fully written
+    for (int l = 0; l < L; ++l) {
+      cudaError_t e = cudaMemsetAsync(dfeats[l], 0, (size_t)B * C * H[l] * W[l] * 4, (cudaStream_t)stream);
+      if (e != cudaSuccess) return cuda_result(e, fn);
+    }
+    return ARFE_OK;
+  }
+  REQUIRE(dout && workspace, ARFE_E_NULL, "%s: dout/workspace is NULL", fn);
+  REQUIRE(aligned(dout, 16) && aligned(workspace, 256), ARFE_E_ALIGN, "%s: dout (16) / workspace (256) misaligned", fn);
+  REQUIRE(workspace_bytes >= arfe::roi_pull_workspace_bytes(K, regions, L), ARFE_E_SHAPE,
+          "%s: workspace too small (%zu < %zu)", fn, workspace_bytes, arfe::roi_pull_workspace_bytes(K, regions, L));
+  p.dout = dout; p.dout_cl = 1;
+  rc = cuda_result(arfe::launch_roi_fuse_backward_pull(p, dtype, workspace, workspace_bytes, (cudaStream_t)stream), fn);
+  if (rc) return rc;
+  // regions whose tap tables did not fit the workspace records: atomic kernel, adds on top
+  p.flag_hdr = arfe::roi_pull_headers(K, regions, L, workspace);
+  p.bwd_vec = 0;
+  return cuda_result(arfe::launch_roi_fuse_backward(p, dtype, ARFE_NHWC, (cudaStream_t)stream), fn);
 }
 
 int arfe_roi_align_forward(const void* input, const float* rois, float spatial_scale,
@@ -139,7 +194,7 @@ int arfe_roi_align_forward(const void* input, const float* rois, float spatial_s
   const int32_t h[1] = {H}, w[1] = {W};
   const float s[1] = {spatial_scale};
   return arfe_roi_fuse_forward(feats, h, w, s, 1, B, C, rois, K, 1, 1.0f, pooled_height,
-                               pooled_width, sampling_ratio, 56.0f, dtype, layout, output,
+                               pooled_width, sampling_ratio, 56.0f, dtype, layout, ARFE_NCHW, output,
                                nullptr, nullptr, stream);
 }
 
@@ -152,7 +207,7 @@ int arfe_roi_align_backward(const void* grad, const float* rois, float spatial_s
   float* dfeats[1] = {grad_input};
   const int32_t h[1] = {H}, w[1] = {W};
   const float s[1] = {spatial_scale};
-  return arfe_roi_fuse_backward(grad, h, w, s, 1, B, C, rois, K, 1, 1.0f, pooled_height,
+  return arfe_roi_fuse_backward(grad, ARFE_NCHW, h, w, s, 1, B, C, rois, K, 1, 1.0f, pooled_height,
                                 pooled_width, sampling_ratio, 56.0f, dtype, layout, dfeats, stream);
 }
 

@@ -11,60 +11,18 @@
 //   adaptive max pool window of output i: [floor(i*in/out), ceil((i+1)*in/out)),
 //     first maximum wins, NaN propagates;
 //   nearest source of destination d: min(floor(d * float(in)/float(out)), in-1).
-#include <cuda_bf16.h>
-#include <cuda_runtime.h>
-#include <math_constants.h>
-#include <stdint.h>
-
-#include "launch.h"
+#include "fpn_common.cuh"
 
 namespace arfe {
+using namespace fpn;
 namespace {
 
-constexpr int kThreads = 256;
-
-template <typename T> __device__ __forceinline__ float ldf(const T* p);
-template <> __device__ __forceinline__ float ldf<float>(const float* p) { return __ldg(p); }
-template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) {
-  return __bfloat162float(*p);
-}
-template <typename T> __device__ __forceinline__ void stf(T* p, float v);
-template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
-template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) {
-  *p = __float2bfloat16_rn(v);
-}
-
+// argmax buffer element of pooled level l: laid out like the tensors
+// (NCHW: [l][B][C][Hr][Wr], channels-last: [l][B][Hr][Wr][C]).
 template <bool kNHWC>
-__device__ __forceinline__ size_t at(int b, int c, int y, int x, int C, int H, int W) {
-  return kNHWC ? (((size_t)b * H + y) * W + x) * C + c
-               : (((size_t)b * C + c) * H + y) * W + x;
-}
-
-// Decode a flat index in memory order of a [B,C,H,W] tensor.
-template <bool kNHWC>
-__device__ __forceinline__ void decode(size_t i, int C, int H, int W, int& b, int& c,
-                                       int& y, int& x) {
-  if (kNHWC) {
-    c = (int)(i % C); i /= C;
-    x = (int)(i % W); i /= W;
-    y = (int)(i % H); b = (int)(i / H);
-  } else {
-    x = (int)(i % W); i /= W;
-    y = (int)(i % H); i /= H;
-    c = (int)(i % C); b = (int)(i / C);
-  }
-}
-
-__device__ __forceinline__ int pool_start(int i, int in, int out) {
-  return (int)(((long long)i * in) / out);
-}
-__device__ __forceinline__ int pool_end(int i, int in, int out) {
-  return (int)(((long long)(i + 1) * in + out - 1) / out);
-}
-__device__ __forceinline__ int nearest_src(int d, int in, int out) {
-  const float scale = __fdiv_rn((float)in, (float)out);
-  const int s = (int)floorf(__fmul_rn((float)d, scale));
-  return s < in - 1 ? s : in - 1;
+__device__ __forceinline__ size_t amax_at(int l, int B, int b, int c, int Y, int X, int C, int Hr, int Wr) {
+  return kNHWC ? ((((size_t)l * B + b) * Hr + Y) * Wr + X) * C + c
+               : (((size_t)l * B + b) * C + c) * Hr * Wr + (size_t)Y * Wr + X;
 }
 
 // ---------------------------------------------------------------- gather fwd
@@ -132,7 +90,7 @@ gather_fwd(const FpnParams p, const VecFlags vf) {
       }
       v = best;
       if (p.argmax)
-        p.argmax[(((size_t)l * p.B + b) * C + c) * Hr * Wr + (size_t)Y * Wr + X] = (uint8_t)arg;
+        p.argmax[amax_at<kNHWC>(l, p.B, b, c, Y, X, C, Hr, Wr)] = (uint8_t)arg;
     } else {
       v = ldf(f + at<kNHWC>(b, c, nearest_src(Y, H, Hr), nearest_src(X, W, Wr), C, H, W));
     }
@@ -175,7 +133,7 @@ gather_bwd(const FpnParams p, const LevelOffsets lo) {
       for (int X = X0; X < Wr && pool_start(X, W, Wr) <= x; ++X) {
         const int x0 = pool_start(X, W, Wr), x1 = pool_end(X, W, Wr);
         if (x1 <= x) continue;
-        const int arg = p.argmax[(((size_t)l * p.B + b) * C + c) * Hr * Wr + (size_t)Y * Wr + X];
+        const int arg = p.argmax[amax_at<kNHWC>(l, p.B, b, c, Y, X, C, Hr, Wr)];
         if (arg == (y - y0) * (x1 - x0) + (x - x0))
           g += ldf(d + at<kNHWC>(b, c, Y, X, C, Hr, Wr));
       }
@@ -233,9 +191,6 @@ gather_bwd_fast(const FpnParams p, const VecFlags vf) {
 }
 
 // ----------------------------------------------------------------- apply fwd
-__device__ __forceinline__ float gate_value(float a, float b) {
-  return tanhf(fmaxf(a, 0.f)) + tanhf(fmaxf(b, 0.f));
-}
 
 // NCHW: thread = one pixel of one level, loops over a group of channels so
 // the two tanh are amortised; consecutive threads = consecutive x (coalesced).
@@ -408,6 +363,10 @@ cudaError_t launch_fpn_gather_forward(const FpnParams& p, int dtype, int layout,
                                       cudaStream_t stream) {
   const size_t total = (size_t)p.B * p.C * p.Hr * p.Wr;
   if (total == 0) return cudaSuccess;
+  if (layout == 1 && fpn_cl_ok(p, dtype, true, false) &&
+      (reinterpret_cast<uintptr_t>(p.gathered) & 15u) == 0 &&
+      (p.argmax == nullptr || (reinterpret_cast<uintptr_t>(p.argmax) & 3u) == 0))
+    return launch_fpn_gather_forward_cl(p, dtype, stream);
   const VecFlags vf = vec_flags(p, dtype, layout, false);
   ARFE_DISPATCH(gather_fwd, blocks_for(total), p, vf);
   return cudaGetLastError();
@@ -415,6 +374,17 @@ cudaError_t launch_fpn_gather_forward(const FpnParams& p, int dtype, int layout,
 
 cudaError_t launch_fpn_gather_backward(const FpnParams& p, int dtype, int layout,
                                        cudaStream_t stream) {
+  if (layout == 1 && fpn_cl_ok(p, dtype, false, true) &&
+      (reinterpret_cast<uintptr_t>(p.gathered) & 15u) == 0 &&
+      (p.argmax == nullptr || (reinterpret_cast<uintptr_t>(p.argmax) & 3u) == 0)) {
+    unsigned rest = 0;
+    cudaError_t e = launch_fpn_gather_backward_cl(p, dtype, &rest, stream);
+    if (e != cudaSuccess) return e;
+    const LevelOffsets lo = offsets(p, false, rest);
+    if (lo.start[lo.n] == 0) return cudaSuccess;
+    ARFE_DISPATCH(gather_bwd, blocks_for(lo.start[lo.n]), p, lo);
+    return cudaGetLastError();
+  }
   const VecFlags vf = vec_flags(p, dtype, layout, true);
   unsigned mask = (1u << p.L) - 1u;
   bool any_fast = false;
@@ -433,8 +403,15 @@ cudaError_t launch_fpn_gather_backward(const FpnParams& p, int dtype, int layout
   return cudaGetLastError();
 }
 
+static bool apply_cl_ok(const FpnParams& p, int dtype) {
+  const int V = dtype == 0 ? 4 : 8;
+  return p.C <= 4 * 32 * V && (reinterpret_cast<uintptr_t>(p.bsf) & 15u) == 0;
+}
+
 cudaError_t launch_fpn_apply_forward(const FpnParams& p, int dtype, int layout,
                                      cudaStream_t stream) {
+  if (layout == 1 && fpn_cl_ok(p, dtype, true, true) && apply_cl_ok(p, dtype))
+    return launch_fpn_apply_forward_cl(p, dtype, stream);
   if (layout == 0) {
     const LevelOffsets lo = offsets(p, true);
     if (lo.start[lo.n] == 0) return cudaSuccess;
@@ -453,6 +430,9 @@ cudaError_t launch_fpn_apply_forward(const FpnParams& p, int dtype, int layout,
 
 cudaError_t launch_fpn_apply_backward(const FpnParams& p, int dtype, int layout,
                                       cudaStream_t stream) {
+  if (layout == 1 && fpn_cl_ok(p, dtype, true, false) && apply_cl_ok(p, dtype) &&
+      (reinterpret_cast<uintptr_t>(p.dbsf) & 15u) == 0)
+    return launch_fpn_apply_backward_cl(p, dtype, stream);
   const LevelOffsets lo = offsets(p, true);
   if (lo.start[lo.n] == 0) return cudaSuccess;
   ARFE_DISPATCH(apply_bwd_gates, blocks_for(lo.start[lo.n]), p, lo);

@@ -1,0 +1,323 @@
+// AR-FPN kernels, channels-last (NHWC) vector paths: lanes == channels, 128-bit
+// accesses, every access coalesced over the channel axis.
+//
+//   gather fwd : thread == (refine pixel, 4|8 channels): window max of the
+//                pooled levels + nearest taps of the others, summed in level
+//                order, / L.   (wfpn_dual_spatial.py:102-113)
+//   gather bwd : same thread shape routes g/L to the argmax cell of every
+//                exact-ratio pooling window and writes the refine level.
+//   apply fwd  : ONE WARP per refine pixel walks the level pixels that read it
+//                (4x4, 2x2, 1, ...): the gate (two tanh) is evaluated once per
+//                pixel, bsf is held in registers.   (wfpn_dual_spatial.py:118-135)
+//   apply bwd  : same walk, fused: d(gate sum) = sum_c dout*bsf by warp shuffle
+//                -> dg1, dg2; dbsf += dout*gate in registers.  dout is read
+//                exactly once, nothing is atomic, no scratch buffer.
+// Index rules as in fpn.cu.  Requires C % (4|8) == 0 and 16-byte aligned
+// tensors; anything else takes the generic kernels in fpn.cu.
+#include "fpn_common.cuh"
+
+namespace arfe {
+using namespace fpn;
+namespace {
+
+template <typename T> struct Vec;
+template <> struct Vec<float> { static constexpr int n = 4; };
+template <> struct Vec<__nv_bfloat16> { static constexpr int n = 8; };
+
+template <typename T>
+__device__ __forceinline__ void ldv(const T* __restrict__ p, float (&f)[Vec<T>::n]) {
+  if constexpr (sizeof(T) == 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  } else {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    }
+  }
+}
+template <typename T>
+__device__ __forceinline__ void stv(T* __restrict__ p, const float (&f)[Vec<T>::n]) {
+  if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  } else {
+    uint4 v;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = v;
+  }
+}
+
+struct Exact { int s[kMaxLevels]; };  // pooling ratio of level l (< refine) if exact, else 0
+
+// ---------------------------------------------------------------- gather fwd
+// argmax layout here: [l][B][Hr][Wr][C] (follows the channels-last layout).
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+gather_fwd_cl(const FpnParams p) {
+  constexpr int V = Vec<T>::n;
+  const int Hr = p.Hr, Wr = p.Wr, C = p.C, CV = C / V;
+  const size_t total = (size_t)p.B * Hr * Wr * CV;
+  const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= total) return;
+  const int cv = (int)(i % CV);
+  size_t r = i / CV;
+  const int X = (int)(r % Wr); r /= Wr;
+  const int Y = (int)(r % Hr);
+  const int b = (int)(r / Hr);
+  const int c = cv * V;
+  float acc[V];
+#pragma unroll
+  for (int u = 0; u < V; ++u) acc[u] = 0.f;
+  for (int l = 0; l < p.L; ++l) {
+    const T* __restrict__ f = static_cast<const T*>(p.feats[l]);
+    const int H = p.H[l], W = p.W[l];
+    float v[V];
+    if (l < p.refine_level) {
+      const int y0 = pool_start(Y, H, Hr), y1 = pool_end(Y, H, Hr);
+      const int x0 = pool_start(X, W, Wr), x1 = pool_end(X, W, Wr);
+      int arg[V];
+#pragma unroll
+      for (int u = 0; u < V; ++u) { v[u] = -CUDART_INF_F; arg[u] = 0; }
+      for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x) {
+          float t[V];
+          ldv<T>(f + (((size_t)b * H + y) * W + x) * C + c, t);
+          const int pos = (y - y0) * (x1 - x0) + (x - x0);
+#pragma unroll
+          for (int u = 0; u < V; ++u)
+            if (t[u] > v[u] || t[u] != t[u]) { v[u] = t[u]; arg[u] = pos; }
+        }
+      if (p.argmax) {
+        uint8_t* a = p.argmax + ((((size_t)l * p.B + b) * Hr + Y) * Wr + X) * C + c;
+#pragma unroll
+        for (int u = 0; u < V; u += 4)
+          *reinterpret_cast<uchar4*>(a + u) =
+              make_uchar4((uint8_t)arg[u], (uint8_t)arg[u + 1], (uint8_t)arg[u + 2], (uint8_t)arg[u + 3]);
+      }
+    } else {
+      ldv<T>(f + (((size_t)b * H + nearest_src(Y, H, Hr)) * W + nearest_src(X, W, Wr)) * C + c, v);
+    }
+#pragma unroll
+    for (int u = 0; u < V; ++u) acc[u] = __fadd_rn(acc[u], v[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < V; ++u) acc[u] = __fdiv_rn(acc[u], (float)p.L);
+  stv<T>(static_cast<T*>(p.gathered) + i * V, acc);
+}
+
+// ---------------------------------------------------------------- gather bwd
+// Exact-ratio pooled levels + the refine level, one thread per (refine px, vec).
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+gather_bwd_cl(const FpnParams p, const Exact ex) {
+  constexpr int V = Vec<T>::n;
+  const int Hr = p.Hr, Wr = p.Wr, C = p.C, CV = C / V;
+  const size_t total = (size_t)p.B * Hr * Wr * CV;
+  const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= total) return;
+  const int cv = (int)(i % CV);
+  size_t r = i / CV;
+  const int X = (int)(r % Wr); r /= Wr;
+  const int Y = (int)(r % Hr);
+  const int b = (int)(r / Hr);
+  const int c = cv * V;
+  float g[V];
+  ldv<T>(static_cast<const T*>(p.gathered) + i * V, g);
+#pragma unroll
+  for (int u = 0; u < V; ++u) g[u] = __fdiv_rn(g[u], (float)p.L);
+  for (int l = 0; l < p.refine_level; ++l) {
+    const int s = ex.s[l];
+    if (s == 0) continue;
+    const int H = p.H[l], W = p.W[l];
+    const uint8_t* a = p.argmax + ((((size_t)l * p.B + b) * Hr + Y) * Wr + X) * C + c;
+    int arg[V];
+#pragma unroll
+    for (int u = 0; u < V; u += 4) {
+      const uchar4 q = *reinterpret_cast<const uchar4*>(a + u);
+      arg[u] = q.x; arg[u + 1] = q.y; arg[u + 2] = q.z; arg[u + 3] = q.w;
+    }
+    T* __restrict__ o = static_cast<T*>(p.outs[l]);
+    for (int dy = 0; dy < s; ++dy)
+      for (int dx = 0; dx < s; ++dx) {
+        const int pos = dy * s + dx;
+        float v[V];
+#pragma unroll
+        for (int u = 0; u < V; ++u) v[u] = (arg[u] == pos) ? g[u] : 0.f;
+        stv<T>(o + (((size_t)b * H + (size_t)s * Y + dy) * W + (size_t)s * X + dx) * C + c, v);
+      }
+  }
+  stv<T>(static_cast<T*>(p.outs[p.refine_level]) + i * V, g);
+}
+
+// ------------------------------------------------------------ apply fwd/bwd
+// One warp per refine pixel (b, Y, X); NV vectors per lane cover C channels.
+template <typename T, int NV, bool kBackward>
+__global__ void __launch_bounds__(kThreads)
+apply_cl(const FpnParams p) {
+  constexpr int V = Vec<T>::n;
+  const int Hr = p.Hr, Wr = p.Wr, C = p.C;
+  const int lane = threadIdx.x & 31;
+  const size_t wid = (size_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (wid >= (size_t)p.B * Hr * Wr) return;
+  const int X = (int)(wid % Wr);
+  const int Y = (int)((wid / Wr) % Hr);
+  const int b = (int)(wid / ((size_t)Wr * Hr));
+  // this lane's channels: c = (v * 32 + lane) * V, v < NV
+  float bs[NV][V], db[NV][V];
+  bool on[NV];
+  const T* __restrict__ bsf = static_cast<const T*>(p.bsf) + (((size_t)b * Hr + Y) * Wr + X) * C;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = (v * 32 + lane) * V;
+    on[v] = c < C;
+    if (on[v]) ldv<T>(bsf + c, bs[v]);
+    else {
+#pragma unroll
+      for (int u = 0; u < V; ++u) bs[v][u] = 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < V; ++u) db[v][u] = 0.f;
+  }
+  for (int l = 0; l < p.L; ++l) {
+    const int H = p.H[l], W = p.W[l];
+    int ya, yb, xa, xb;
+    dst_range(Y, Hr, H, ya, yb);
+    dst_range(X, Wr, W, xa, xb);
+    const T* __restrict__ xin = static_cast<const T*>(p.feats[l]);  // x_l (fwd) / dout_l (bwd)
+    const T* __restrict__ q1 = static_cast<const T*>(p.g1[l]);
+    const T* __restrict__ q2 = static_cast<const T*>(p.g2[l]);
+    for (int y = ya; y < yb; ++y)
+      for (int x = xa; x < xb; ++x) {
+        const size_t pix = ((size_t)b * H + y) * W + x;
+        const float a1 = ldf(q1 + pix), a2 = ldf(q2 + pix);
+        const float t1 = tanhf(fmaxf(a1, 0.f)), t2 = tanhf(fmaxf(a2, 0.f));
+        const float gate = t1 + t2;
+        if (!kBackward) {
+          T* __restrict__ out = static_cast<T*>(p.outs[l]);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            if (!on[v]) continue;
+            const int c = (v * 32 + lane) * V;
+            float f[V];
+            ldv<T>(xin + pix * C + c, f);
+#pragma unroll
+            for (int u = 0; u < V; ++u) f[u] = fmaf(bs[v][u], gate, f[u]);
+            stv<T>(out + pix * C + c, f);
+          }
+        } else {
+          float s = 0.f;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            if (!on[v]) continue;
+            const int c = (v * 32 + lane) * V;
+            float f[V];
+            ldv<T>(xin + pix * C + c, f);
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+              s = fmaf(f[u], bs[v][u], s);
+              db[v][u] = fmaf(f[u], gate, db[v][u]);
+            }
+          }
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+          if (lane == 0) {
+            p.dg1[l][pix] = a1 > 0.f ? s * (1.f - t1 * t1) : 0.f;
+            p.dg2[l][pix] = a2 > 0.f ? s * (1.f - t2 * t2) : 0.f;
+          }
+        }
+      }
+  }
+  if (kBackward) {
+    float* __restrict__ o = p.dbsf + (((size_t)b * Hr + Y) * Wr + X) * C;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      if (!on[v]) continue;
+      const int c = (v * 32 + lane) * V;
+#pragma unroll
+      for (int u = 0; u < V; u += 4)
+        *reinterpret_cast<float4*>(o + c + u) = make_float4(db[v][u], db[v][u + 1], db[v][u + 2], db[v][u + 3]);
+    }
+  }
+}
+
+inline unsigned blocks_for(size_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
+inline bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+// True when the vector kernels can take this problem.
+bool fpn_cl_ok(const FpnParams& p, int dtype, bool need_feats, bool need_outs) {
+  const int V = dtype == 0 ? 4 : 8;
+  if (p.C % V) return false;
+  for (int l = 0; l < p.L; ++l) {
+    if (need_feats && !a16(p.feats[l])) return false;
+    if (need_outs && !a16(p.outs[l])) return false;
+  }
+  return true;
+}
+
+cudaError_t launch_fpn_gather_forward_cl(const FpnParams& p, int dtype, cudaStream_t stream) {
+  const int V = dtype == 0 ? 4 : 8;
+  const size_t total = (size_t)p.B * p.Hr * p.Wr * (p.C / V);
+  if (total == 0) return cudaSuccess;
+  if (dtype == 0) gather_fwd_cl<float><<<blocks_for(total, kThreads), kThreads, 0, stream>>>(p);
+  else gather_fwd_cl<__nv_bfloat16><<<blocks_for(total, kThreads), kThreads, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// Returns in *mask the levels NOT written here (generic kernel finishes them).
+cudaError_t launch_fpn_gather_backward_cl(const FpnParams& p, int dtype, unsigned* mask,
+                                          cudaStream_t stream) {
+  const int V = dtype == 0 ? 4 : 8;
+  Exact ex;
+  unsigned m = (1u << p.L) - 1u;
+  for (int l = 0; l < kMaxLevels; ++l) ex.s[l] = 0;
+  for (int l = 0; l < p.refine_level; ++l) {
+    if (p.H[l] % p.Hr == 0 && p.W[l] % p.Wr == 0 && p.H[l] / p.Hr == p.W[l] / p.Wr &&
+        p.H[l] / p.Hr <= 15) {
+      ex.s[l] = p.H[l] / p.Hr;
+      m &= ~(1u << l);
+    }
+  }
+  m &= ~(1u << p.refine_level);
+  *mask = m;
+  const size_t total = (size_t)p.B * p.Hr * p.Wr * (p.C / V);
+  if (total == 0) return cudaSuccess;
+  if (dtype == 0) gather_bwd_cl<float><<<blocks_for(total, kThreads), kThreads, 0, stream>>>(p, ex);
+  else gather_bwd_cl<__nv_bfloat16><<<blocks_for(total, kThreads), kThreads, 0, stream>>>(p, ex);
+  return cudaGetLastError();
+}
+
+template <bool kBackward>
+static cudaError_t launch_apply_cl(const FpnParams& p, int dtype, cudaStream_t stream) {
+  const int V = dtype == 0 ? 4 : 8;
+  const size_t warps = (size_t)p.B * p.Hr * p.Wr;
+  if (warps == 0) return cudaSuccess;
+  const unsigned grid = blocks_for(warps, kThreads / 32);
+  const int nv = (p.C + 32 * V - 1) / (32 * V);
+  if (nv > 4) return cudaErrorInvalidValue;
+#define ARFE_APPLY(TT, NV) apply_cl<TT, NV, kBackward><<<grid, kThreads, 0, stream>>>(p)
+  if (dtype == 0) {
+    switch (nv) { case 1: ARFE_APPLY(float, 1); break; case 2: ARFE_APPLY(float, 2); break;
+                  case 3: ARFE_APPLY(float, 3); break; default: ARFE_APPLY(float, 4); break; }
+  } else {
+    switch (nv) { case 1: ARFE_APPLY(__nv_bfloat16, 1); break; case 2: ARFE_APPLY(__nv_bfloat16, 2); break;
+                  case 3: ARFE_APPLY(__nv_bfloat16, 3); break; default: ARFE_APPLY(__nv_bfloat16, 4); break; }
+  }
+#undef ARFE_APPLY
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fpn_apply_forward_cl(const FpnParams& p, int dtype, cudaStream_t stream) {
+  return launch_apply_cl<false>(p, dtype, stream);
+}
+cudaError_t launch_fpn_apply_backward_cl(const FpnParams& p, int dtype, cudaStream_t stream) {
+  return launch_apply_cl<true>(p, dtype, stream);
+}
+
+}  // namespace arfe

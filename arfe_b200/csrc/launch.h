@@ -22,6 +22,9 @@ struct RoiFuseParams {
   int32_t* lvl_out;
   float* boxes_out;
   int bwd_vec;       // backward: 128-bit vector reductions (1) or scalar (0)
+  int out_cl;        // forward: output channels-last [K][PH*PW][R*C] (1) or NCHW (0)
+  int dout_cl;       // backward: dout channels-last (1) or NCHW (0)
+  const void* flag_hdr;  // backward (atomic kernel): RegionHdr array; only flagged regions run
   int debug_skip;    // profiling aid (ARFE_FWD_SKIP): 1 compute, 2 staging, 4 write-out, 8 all but setup
 };
 
@@ -29,6 +32,12 @@ cudaError_t launch_roi_fuse_forward(const RoiFuseParams& p, int dtype, int layou
                                     cudaStream_t stream);
 cudaError_t launch_roi_fuse_backward(const RoiFuseParams& p, int dtype, int layout,
                                      cudaStream_t stream);
+cudaError_t launch_roi_fuse_forward_cl(const RoiFuseParams& p, int dtype, int out_cl,
+                                       cudaStream_t stream);
+size_t roi_pull_workspace_bytes(int K, int R, int L);
+cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, void* workspace,
+                                          size_t workspace_bytes, cudaStream_t stream);
+const void* roi_pull_headers(int K, int R, int L, void* workspace);
 cudaError_t launch_roi_fuse_taps(const RoiFuseParams& p, int max_grid, int32_t* lvl,
                                  int32_t* grid, float* boxes, int32_t* ylo,
                                  int32_t* yhi, float* ywl, float* ywh, int32_t* xlo,
@@ -59,6 +68,13 @@ struct FpnParams {
   uint8_t* argmax;        // gather
   float* dbsf;            // apply bwd
 };
+
+bool fpn_cl_ok(const FpnParams& p, int dtype, bool need_feats, bool need_outs);
+cudaError_t launch_fpn_gather_forward_cl(const FpnParams& p, int dtype, cudaStream_t stream);
+cudaError_t launch_fpn_gather_backward_cl(const FpnParams& p, int dtype, unsigned* mask,
+                                          cudaStream_t stream);
+cudaError_t launch_fpn_apply_forward_cl(const FpnParams& p, int dtype, cudaStream_t stream);
+cudaError_t launch_fpn_apply_backward_cl(const FpnParams& p, int dtype, cudaStream_t stream);
 
 cudaError_t launch_fpn_gather_forward(const FpnParams& p, int dtype, int layout,
                                       cudaStream_t stream);

@@ -27,205 +27,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "geometry.cuh"
-#include "launch.h"
+#include "roi_common.cuh"
 
 namespace arfe {
-
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-constexpr int kAxisCap = 512;    // aggregated weights per axis
-constexpr int kPitch = 33;       // smem pitch of one staged pixel (32 ch + 1)
-constexpr int kChunk = 32;       // channels per staged chunk
-
-struct AxisTable {
-  int first[kMaxPool];  // first feature row (column) touched by bin p
-  int cnt[kMaxPool];    // number of consecutive rows touched (0: none)
-  int off[kMaxPool];    // offset of bin p's weights in w[]
-  float w[kAxisCap];
-};
-
-struct CtaHeader {
-  RoiGeom g;
-  int lvl;
-  int H, W;
-  int ymin, ymax, xmin, xmax;  // union window over all bins (inclusive)
-  int overflow;                // tables did not fit -> generic path
-  int max_rows;                // max over ph of cnt
-};
-
-template <typename T> __device__ __forceinline__ float to_f(T v);
-template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
-template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) {
-  return __bfloat162float(v);
-}
-template <typename T> __device__ __forceinline__ T from_f(float v);
-template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
-template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) {
-  return __float2bfloat16_rn(v);
-}
-
-// Build the aggregated per-axis table with one warp (lane p = bin p).
-__device__ void build_axis_table(AxisTable& t, int P, float start, float bin,
-                                 int grid, int extent, int* overflow,
-                                 int lane) {
-  int lo_min = 0x7fffffff, hi_max = -1;
-  if (lane < P) {
-    for (int i = 0; i < grid; ++i) {
-      AxisTap s = axis_sample(start, lane, bin, i, grid, extent);
-      if (s.lo >= 0) {
-        lo_min = min(lo_min, s.lo);
-        hi_max = max(hi_max, s.hi);
-      }
-    }
-  }
-  int n = (hi_max >= 0) ? (hi_max - lo_min + 1) : 0;
-  int incl = n;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += v;
-  }
-  const int total = __shfl_sync(0xffffffffu, incl, 31);
-  const int off = incl - n;
-  if (total > kAxisCap) {
-    if (lane == 0) *overflow = 1;
-    return;
-  }
-  if (lane < P) {
-    t.first[lane] = (n > 0) ? lo_min : 0;
-    t.cnt[lane] = n;
-    t.off[lane] = off;
-    for (int j = 0; j < n; ++j) t.w[off + j] = 0.f;
-    for (int i = 0; i < grid; ++i) {
-      AxisTap s = axis_sample(start, lane, bin, i, grid, extent);
-      if (s.lo >= 0) {
-        t.w[off + s.lo - lo_min] += s.wl;
-        t.w[off + s.hi - lo_min] += s.wh;
-      }
-    }
-  }
-}
-
-// Header + tables for CTA (k, r).  Returns false when the output row is all
-// zeros (no level, batch index out of range, or empty sampling window).
-__device__ bool setup_cta(const RoiFuseParams& p, int k, int r, CtaHeader& hd,
-                          AxisTable& ty, AxisTable& tx) {
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    RegionBox bx = region_box(p.rois + 5 * (size_t)k, r, p.facs);
-    int lvl = (p.L == 1) ? 0 : map_roi_level(bx, p.L, p.finest_scale);
-    hd.lvl = lvl;
-    hd.overflow = 0;
-    if (lvl >= 0) {
-      hd.g = roi_geometry(bx, p.scale[lvl], p.PH, p.PW, p.sampling_ratio);
-      hd.H = p.H[lvl];
-      hd.W = p.W[lvl];
-      if (hd.g.batch < 0 || hd.g.batch >= p.B) hd.lvl = -2;
-    }
-    if (p.lvl_out) p.lvl_out[(size_t)r * p.K + k] = lvl;
-    if (p.boxes_out) {
-      float* o = p.boxes_out + ((size_t)r * p.K + k) * 5;
-      o[0] = bx.b; o[1] = bx.x1; o[2] = bx.y1; o[3] = bx.x2; o[4] = bx.y2;
-    }
-  }
-  __syncthreads();
-  if (hd.lvl < 0) return false;
-  const int warp = tid >> 5, lane = tid & 31;
-  if (warp == 0)
-    build_axis_table(ty, p.PH, hd.g.start_h, hd.g.bin_h, hd.g.grid_h, hd.H,
-                     &hd.overflow, lane);
-  else if (warp == 1)
-    build_axis_table(tx, p.PW, hd.g.start_w, hd.g.bin_w, hd.g.grid_w, hd.W,
-                     &hd.overflow, lane);
-  __syncthreads();
-  if (hd.overflow) return true;
-  if (tid == 0) {
-    int ymin = 0x7fffffff, ymax = -1, xmin = 0x7fffffff, xmax = -1, mr = 0;
-    for (int q = 0; q < p.PH; ++q)
-      if (ty.cnt[q] > 0) {
-        ymin = min(ymin, ty.first[q]);
-        ymax = max(ymax, ty.first[q] + ty.cnt[q] - 1);
-        mr = max(mr, ty.cnt[q]);
-      }
-    for (int q = 0; q < p.PW; ++q)
-      if (tx.cnt[q] > 0) {
-        xmin = min(xmin, tx.first[q]);
-        xmax = max(xmax, tx.first[q] + tx.cnt[q] - 1);
-      }
-    hd.ymin = ymin; hd.ymax = ymax; hd.xmin = xmin; hd.xmax = xmax;
-    hd.max_rows = mr;
-  }
-  __syncthreads();
-  return hd.ymax >= 0 && hd.xmax >= 0;
-}
-
-// Generic path: reference loop order, direct global taps (any size, slow).
-template <typename T, bool kNHWC>
-__device__ void forward_generic(const RoiFuseParams& p, const CtaHeader& hd,
-                                T* __restrict__ out_blk) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int PHW = p.PH * p.PW;
-  const T* __restrict__ f = static_cast<const T*>(p.feats[hd.lvl]);
-  const int H = hd.H, W = hd.W, C = p.C;
-  const RoiGeom& g = hd.g;
-  const int nwarps = blockDim.x >> 5;
-  for (int bin = warp; bin < PHW; bin += nwarps) {
-    const int ph = bin / p.PW, pw = bin % p.PW;
-    for (int c = lane; c < C; c += 32) {
-      float acc = 0.f;
-      for (int iy = 0; iy < g.grid_h; ++iy) {
-        AxisTap a = axis_sample(g.start_h, ph, g.bin_h, iy, g.grid_h, H);
-        if (a.lo < 0) continue;
-        for (int ix = 0; ix < g.grid_w; ++ix) {
-          AxisTap b = axis_sample(g.start_w, pw, g.bin_w, ix, g.grid_w, W);
-          if (b.lo < 0) continue;
-          size_t i1, i2, i3, i4;
-          if (kNHWC) {
-            const size_t base = (size_t)g.batch * H * W;
-            i1 = (base + (size_t)a.lo * W + b.lo) * C + c;
-            i2 = (base + (size_t)a.lo * W + b.hi) * C + c;
-            i3 = (base + (size_t)a.hi * W + b.lo) * C + c;
-            i4 = (base + (size_t)a.hi * W + b.hi) * C + c;
-          } else {
-            const size_t base = ((size_t)g.batch * C + c) * H * W;
-            i1 = base + (size_t)a.lo * W + b.lo;
-            i2 = base + (size_t)a.lo * W + b.hi;
-            i3 = base + (size_t)a.hi * W + b.lo;
-            i4 = base + (size_t)a.hi * W + b.hi;
-          }
-          acc += a.wl * b.wl * to_f(f[i1]) + a.wl * b.wh * to_f(f[i2]) +
-                 a.wh * b.wl * to_f(f[i3]) + a.wh * b.wh * to_f(f[i4]);
-        }
-      }
-      out_blk[(size_t)c * PHW + bin] = from_f<T>(__fdiv_rn(acc, g.count));
-    }
-  }
-}
-
-// Vector float reductions to global memory (sm_90+): one L2 atomic transaction
-// for 4 (2) consecutive floats; the address must be 16 (8) byte aligned.
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
-               : "memory");
-}
-__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
-  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};\n" ::"l"(addr), "f"(a), "f"(b) : "memory");
-}
-
-// px -> (row, col) of a window `ww` pixels wide without an integer division.
-__device__ __forceinline__ void split_px(int px, int ww, float inv_ww, int& row,
-                                         int& col) {
-  row = (int)(((float)px + 0.5f) * inv_ww);
-  col = px - row * ww;
-  if (col < 0) { --row; col += ww; }
-  else if (col >= ww) { ++row; col -= ww; }
-}
-
-template <typename T>
-__device__ void zero_block(T* __restrict__ out_blk, int n) {
-  for (int i = threadIdx.x; i < n; i += kThreads) out_blk[i] = from_f<T>(0.f);
-}
 
 // ---------------------------------------------------------------------------
 // Forward, NCHW features.
@@ -575,6 +379,12 @@ roi_fuse_bwd(const RoiFuseParams p, int cb /* channels staged per pass */) {
   const int PH = p.PH, PW = p.PW, PHW = PH * PW, C = p.C;
   const T* __restrict__ dout_blk =
       static_cast<const T*>(p.dout) + ((size_t)k * p.R + r) * C * PHW;
+  if (p.flag_hdr && !static_cast<const RegionHdr*>(p.flag_hdr)[k * p.R + r].flags) return;
+  // element (c, bin) of this region's incoming gradient, NCHW or channels-last
+  auto dout_at = [&](int c, int bin) -> float {
+    return p.dout_cl ? to_f(static_cast<const T*>(p.dout)[((size_t)k * PHW + bin) * (p.R * C) + (size_t)r * C + c])
+                     : to_f(dout_blk[(size_t)c * PHW + bin]);
+  };
 
   if (!setup_cta(p, k, r, hd, ty, tx)) return;
   const int H = hd.H, W = hd.W;
@@ -586,7 +396,7 @@ roi_fuse_bwd(const RoiFuseParams p, int cb /* channels staged per pass */) {
     for (int e = tid; e < C * PHW; e += kThreads) {
       const int c = e / PHW, bin = e - c * PHW;
       const int ph = bin / PW, pw = bin % PW;
-      const float gv = to_f(dout_blk[e]);
+      const float gv = dout_at(c, bin);
       for (int iy = 0; iy < g.grid_h; ++iy) {
         AxisTap a = axis_sample(g.start_h, ph, g.bin_h, iy, g.grid_h, H);
         if (a.lo < 0) continue;
@@ -632,8 +442,15 @@ roi_fuse_bwd(const RoiFuseParams p, int cb /* channels staged per pass */) {
   for (int c0 = 0; c0 < C; c0 += cb) {
     const int cc = min(cb, C - c0);
     __syncthreads();
-    for (int e = tid; e < cc * PHW; e += kThreads)
-      dsm[e] = to_f(dout_blk[(size_t)c0 * PHW + e]);
+    if (p.dout_cl) {
+      for (int e = tid; e < cc * PHW; e += kThreads) {
+        const int bin = e / cc, c = e - bin * cc;
+        dsm[c * PHW + bin] = dout_at(c0 + c, bin);
+      }
+    } else {
+      for (int e = tid; e < cc * PHW; e += kThreads)
+        dsm[e] = to_f(dout_blk[(size_t)c0 * PHW + e]);
+    }
     __syncthreads();
 
     for (int px0 = tid - lane; px0 < npx; px0 += kThreads) {  // warp-uniform bound
@@ -781,15 +598,7 @@ __global__ void roi_fuse_taps_kernel(const RoiFuseParams p, int max_grid,
 // ---------------------------------------------------------------------------
 // Host launchers
 // ---------------------------------------------------------------------------
-constexpr int kHdrBytes = 128 + 2 * (int)sizeof(AxisTable);
 constexpr int kFwdHdrBytes = kHdrBytes + (int)sizeof(BandDesc);
-static_assert(sizeof(CtaHeader) <= 128, "header must fit its slot");
-constexpr int kMaxSmem = 220 * 1024;
-
-template <typename K>
-static cudaError_t set_smem(K kernel, int bytes) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-}
 
 cudaError_t launch_roi_fuse_forward(const RoiFuseParams& p, int dtype, int layout,
                                     cudaStream_t stream) {
@@ -807,7 +616,10 @@ cudaError_t launch_roi_fuse_forward(const RoiFuseParams& p, int dtype, int layou
       if ((e = set_smem(roi_fuse_fwd_nchw<__nv_bfloat16>, smem)) != cudaSuccess) return e;
       roi_fuse_fwd_nchw<__nv_bfloat16><<<grid, threads, smem, stream>>>(p, opitch);
     }
+  } else if (p.C % (dtype == 0 ? 4 : 8) == 0) {
+    return launch_roi_fuse_forward_cl(p, dtype, p.out_cl, stream);
   } else {
+    if (p.out_cl) return cudaErrorInvalidValue;
     int opitch = PHW | 1;
     long long need = (long long)kHdrBytes + (long long)p.C * opitch * 4;
     if (need > kMaxSmem) { opitch = 0; need = kHdrBytes; }

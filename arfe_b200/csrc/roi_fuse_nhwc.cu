@@ -1,0 +1,626 @@
+// Channels-last (NHWC) fast path of the AR-RFF extraction.
+//
+// With channels innermost every access of this gather/scatter workload is
+// lane == channel coalesced, so nothing has to be transposed through shared
+// memory and nothing needs an atomic:
+//
+//   forward  : one CTA per (RoI, region); a warp owns a bin, lanes own 4 (fp32)
+//              or 8 (bf16) consecutive channels; every tap is ONE 128-bit
+//              L1-cached load per lane (100 % sector efficiency; taps shared by
+//              neighbouring bins hit L1).  Output either channels-last
+//              (direct 128-bit stores) or NCHW (staged [bin][C] in smem).
+//   backward : PULL formulation.  roi_prep writes, per region, its window and
+//              for every window row/column the bins that sample it with their
+//              aggregated weights (the transpose of the forward tables) into a
+//              caller-provided workspace.  roi_bwd_pull then gives every 8x8
+//              pixel tile of every level to one CTA: warp == tile row,
+//              lanes == channels, accumulators in registers, the regions that
+//              intersect the tile are visited in index order -> every gradient
+//              element is written exactly once, deterministically, with no
+//              atomics and no zero-fill.  (The NCHW/atomic kernel is bound by
+//              the L2 atomic units at ~1 fp32 element per slice-clock; see
+//              DESIGN.md section 6.)
+#include "roi_common.cuh"
+
+namespace arfe {
+
+// ------------------------------------------------------------------ helpers
+template <typename T> struct VecOf;
+template <> struct VecOf<float> { static constexpr int n = 4; };
+template <> struct VecOf<__nv_bfloat16> { static constexpr int n = 8; };
+
+template <typename T>
+__device__ __forceinline__ void ldg_vec(const T* __restrict__ p, float (&f)[VecOf<T>::n]) {
+  if constexpr (sizeof(T) == 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  } else {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void st_vec(T* __restrict__ p, const float (&f)[VecOf<T>::n]) {
+  if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  } else {
+    uint4 v;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = v;
+  }
+}
+
+// ------------------------------------------------------------------ forward
+// One bin, VEC channels per lane: rows x NC taps, NC loads in flight per row.
+template <typename T, int NC>
+__device__ __forceinline__ void cl_bin(const T* __restrict__ base, size_t rowstride, int C,
+                                       const float* __restrict__ wy, int nr,
+                                       const float* __restrict__ wx,
+                                       float (&acc)[VecOf<T>::n]) {
+  constexpr int V = VecOf<T>::n;
+  float w[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) w[j] = wx[j];
+  for (int jr = 0; jr < nr; ++jr) {
+    float v[NC][V];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) ldg_vec<T>(base + (size_t)j * C, v[j]);
+    float t[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) t[u] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+#pragma unroll
+      for (int u = 0; u < V; ++u) t[u] = fmaf(w[j], v[j][u], t[u]);
+    const float a = wy[jr];
+#pragma unroll
+    for (int u = 0; u < V; ++u) acc[u] = fmaf(a, t[u], acc[u]);
+    base += rowstride;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void cl_bin_any(const T* __restrict__ base, size_t rowstride, int C,
+                                           const float* __restrict__ wy, int nr,
+                                           const float* __restrict__ wx, int nc,
+                                           float (&acc)[VecOf<T>::n]) {
+  constexpr int V = VecOf<T>::n;
+  switch (nc) {
+    case 1: cl_bin<T, 1>(base, rowstride, C, wy, nr, wx, acc); return;
+    case 2: cl_bin<T, 2>(base, rowstride, C, wy, nr, wx, acc); return;
+    case 3: cl_bin<T, 3>(base, rowstride, C, wy, nr, wx, acc); return;
+    case 4: cl_bin<T, 4>(base, rowstride, C, wy, nr, wx, acc); return;
+    case 5: cl_bin<T, 5>(base, rowstride, C, wy, nr, wx, acc); return;
+    case 6: cl_bin<T, 6>(base, rowstride, C, wy, nr, wx, acc); return;
+    default: break;
+  }
+  for (int jr = 0; jr < nr; ++jr) {
+    const float a = wy[jr];
+    for (int j = 0; j < nc; ++j) {
+      float v[V];
+      ldg_vec<T>(base + (size_t)j * C, v);
+      const float w = a * wx[j];
+#pragma unroll
+      for (int u = 0; u < V; ++u) acc[u] = fmaf(w, v[u], acc[u]);
+    }
+    base += rowstride;
+  }
+}
+
+// dynamic smem: [CtaHeader][AxisTable y][AxisTable x][outs: bins_per_pass * opitch] (NCHW out only)
+template <typename T, bool kOutCL>
+__global__ void __launch_bounds__(kThreads)
+roi_fuse_fwd_cl(const RoiFuseParams p, int opitch, int bins_per_pass) {
+  constexpr int V = VecOf<T>::n;
+  extern __shared__ __align__(16) unsigned char smem[];
+  CtaHeader& hd = *reinterpret_cast<CtaHeader*>(smem);
+  AxisTable& ty = *reinterpret_cast<AxisTable*>(smem + 128);
+  AxisTable& tx = *reinterpret_cast<AxisTable*>(smem + 128 + sizeof(AxisTable));
+  float* outs = reinterpret_cast<float*>(smem + kHdrBytes);
+
+  const int k = blockIdx.x / p.R, r = blockIdx.x % p.R;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int PH = p.PH, PW = p.PW, PHW = PH * PW, C = p.C, RC = p.R * C;
+  T* __restrict__ out = static_cast<T*>(p.out);
+  // element (bin, c) of this region's output block
+  auto out_index = [&](int bin, int c) -> size_t {
+    return kOutCL ? ((size_t)k * PHW + bin) * RC + (size_t)r * C + c
+                  : (((size_t)k * p.R + r) * C + c) * PHW + bin;
+  };
+
+  const bool live = setup_cta(p, k, r, hd, ty, tx);
+  if (!live || hd.overflow) {
+    if (live) {  // tables did not fit: reference loop order, direct taps
+      const T* __restrict__ f = static_cast<const T*>(p.feats[hd.lvl]);
+      const int H = hd.H, W = hd.W;
+      const RoiGeom g = hd.g;
+      for (int e = tid; e < C * PHW; e += kThreads) {
+        const int bin = e / C, c = e - bin * C;
+        const int ph = bin / PW, pw = bin % PW;
+        float acc = 0.f;
+        for (int iy = 0; iy < g.grid_h; ++iy) {
+          AxisTap a = axis_sample(g.start_h, ph, g.bin_h, iy, g.grid_h, H);
+          if (a.lo < 0) continue;
+          for (int ix = 0; ix < g.grid_w; ++ix) {
+            AxisTap b = axis_sample(g.start_w, pw, g.bin_w, ix, g.grid_w, W);
+            if (b.lo < 0) continue;
+            const size_t base = (size_t)g.batch * H * W;
+            acc += a.wl * b.wl * to_f(f[(base + (size_t)a.lo * W + b.lo) * C + c]) +
+                   a.wl * b.wh * to_f(f[(base + (size_t)a.lo * W + b.hi) * C + c]) +
+                   a.wh * b.wl * to_f(f[(base + (size_t)a.hi * W + b.lo) * C + c]) +
+                   a.wh * b.wh * to_f(f[(base + (size_t)a.hi * W + b.hi) * C + c]);
+          }
+        }
+        out[out_index(bin, c)] = from_f<T>(__fdiv_rn(acc, g.count));
+      }
+    } else {
+      for (int e = tid; e < C * PHW; e += kThreads) {
+        const int bin = e / C, c = e - bin * C;
+        out[out_index(bin, c)] = from_f<T>(0.f);
+      }
+    }
+    return;
+  }
+
+  const int H = hd.H, W = hd.W;
+  const float inv_count = 1.0f / hd.g.count;
+  const T* __restrict__ fimg =
+      static_cast<const T*>(p.feats[hd.lvl]) + (size_t)hd.g.batch * H * W * C;
+  const size_t rowstride = (size_t)W * C;
+  const int cw = 32 * V;  // channels per warp pass
+
+  for (int b0 = 0; b0 < PHW; b0 += bins_per_pass) {
+    const int b1 = min(PHW, b0 + bins_per_pass);
+    for (int bin = b0 + warp; bin < b1; bin += kWarps) {
+      const int ph = bin / PW, pw = bin - ph * PW;
+      const int nr = ty.cnt[ph], nc = tx.cnt[pw];
+      const float* __restrict__ wy = ty.w + ty.off[ph];
+      const float* __restrict__ wx = tx.w + tx.off[pw];
+      const T* __restrict__ base0 = fimg + ((size_t)ty.first[ph] * W + tx.first[pw]) * C + lane * V;
+      for (int c0 = 0; c0 < C; c0 += cw) {
+        if (c0 + lane * V >= C) continue;
+        float acc[V];
+#pragma unroll
+        for (int u = 0; u < V; ++u) acc[u] = 0.f;
+        if (nr > 0 && nc > 0) cl_bin_any<T>(base0 + c0, rowstride, C, wy, nr, wx, nc, acc);
+#pragma unroll
+        for (int u = 0; u < V; ++u) acc[u] *= inv_count;
+        if (kOutCL) {
+          st_vec<T>(out + out_index(bin, c0 + lane * V), acc);
+        } else {
+          float* o = outs + (size_t)(bin - b0) * opitch + c0 + lane * V;
+#pragma unroll
+          for (int u = 0; u < V; u += 4)
+            *reinterpret_cast<float4*>(o + u) = make_float4(acc[u], acc[u + 1], acc[u + 2], acc[u + 3]);
+        }
+      }
+    }
+    if (!kOutCL) {
+      __syncthreads();
+      // per channel a run of (b1 - b0) consecutive bins
+      const int run = b1 - b0;
+      for (int c = warp; c < C; c += kWarps)
+        for (int b = lane; b < run; b += 32)
+          out[out_index(b0 + b, c)] = from_f<T>(outs[(size_t)b * opitch + c]);
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------ region prep
+// Workspace layout (bytes):
+//   [0, 256)                      PrepCounts (per prep block, per level counts)   -- see below
+//   hdr     : N * 32
+//   rowtab  : N * kWinCap * 16     coltab : N * kWinCap * 16
+//   rowext  : N * kExtCap * 4      colext : N * kExtCap * 4
+//   seg_ids : nblk * L * kPrepBlock * 4   seg_cnt : nblk * L * 4
+constexpr int kWinCap = 64;     // window rows / columns described per region
+constexpr int kExtCap = 64;     // spill area for rows/columns sampled by > 2 bins
+constexpr int kPrepBlock = 256; // regions per header block
+
+struct __align__(16) TapEntry {
+  int p0n;        // first bin | (number of bins << 16)
+  float w0, w1;   // weights of the first two bins (row weights carry 1/count)
+  int ext;        // offset of the full weight list in the region's ext area (n > 2)
+};
+
+struct PullWs {
+  RegionHdr* hdr;
+  TapEntry* rowtab;
+  TapEntry* coltab;
+  float* rowext;
+  float* colext;
+  int* seg_ids;
+  int* seg_cnt;
+  int nblk;
+};
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+inline size_t pull_ws_layout(int N, int L, unsigned char* base, PullWs* ws) {
+  const int nblk = (N + kPrepBlock - 1) / kPrepBlock;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t o_hdr = take((size_t)N * sizeof(RegionHdr));
+  const size_t o_row = take((size_t)N * kWinCap * sizeof(TapEntry));
+  const size_t o_col = take((size_t)N * kWinCap * sizeof(TapEntry));
+  const size_t o_rext = take((size_t)N * kExtCap * 4);
+  const size_t o_cext = take((size_t)N * kExtCap * 4);
+  const size_t o_ids = take((size_t)nblk * L * kPrepBlock * 4);
+  const size_t o_cnt = take((size_t)nblk * L * 4);
+  if (ws) {
+    ws->hdr = reinterpret_cast<RegionHdr*>(base + o_hdr);
+    ws->rowtab = reinterpret_cast<TapEntry*>(base + o_row);
+    ws->coltab = reinterpret_cast<TapEntry*>(base + o_col);
+    ws->rowext = reinterpret_cast<float*>(base + o_rext);
+    ws->colext = reinterpret_cast<float*>(base + o_cext);
+    ws->seg_ids = reinterpret_cast<int*>(base + o_ids);
+    ws->seg_cnt = reinterpret_cast<int*>(base + o_cnt);
+    ws->nblk = nblk;
+  }
+  return off;
+}
+
+// Transpose one axis table: for every window row (column) the bins sampling it.
+// Executed by one warp; lane = window row.  Returns false if it does not fit.
+__device__ bool transpose_axis(const AxisTable& t, int P, int lo, int hi, float scale,
+                               TapEntry* __restrict__ tab, float* __restrict__ ext,
+                               int lane) {
+  const int n = hi - lo + 1;
+  if (n > kWinCap) return false;
+  bool ok = true;
+  int ext_used = 0;  // per-lane demand, prefix-summed below
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    int p0 = -1, cnt = 0;
+    float w0 = 0.f, w1 = 0.f;
+    if (i < n) {
+      const int row = lo + i;
+      for (int q = 0; q < P; ++q)
+        if (t.cnt[q] > 0 && row >= t.first[q] && row < t.first[q] + t.cnt[q]) {
+          if (p0 < 0) p0 = q;
+          cnt = q - p0 + 1;
+        }
+      auto w_of = [&](int q) -> float {
+        const int j = row - t.first[q];
+        return (t.cnt[q] > 0 && j >= 0 && j < t.cnt[q]) ? t.w[t.off[q] + j] * scale : 0.f;
+      };
+      if (cnt > 0) w0 = w_of(p0);
+      if (cnt > 1) w1 = w_of(p0 + 1);
+    }
+    // ordered allocation of ext space for entries with more than two bins
+    const int need = (cnt > 2) ? cnt : 0;
+    int incl = need;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int my = ext_used + incl - need;
+    if (ext_used + total > kExtCap) ok = false;
+    if (ok && i < n) {
+      if (need) {
+        const int row = lo + i;
+        for (int a = 0; a < cnt; ++a) {
+          const int q = p0 + a;
+          const int j = row - t.first[q];
+          ext[my + a] = (t.cnt[q] > 0 && j >= 0 && j < t.cnt[q]) ? t.w[t.off[q] + j] * scale : 0.f;
+        }
+      }
+      TapEntry e;
+      e.p0n = (p0 < 0 ? 0 : p0) | (cnt << 16);
+      e.w0 = w0; e.w1 = w1; e.ext = my;
+      tab[i] = e;
+    }
+    ext_used += total;
+  }
+  return __all_sync(0xffffffffu, ok);
+}
+
+// Blocks [0, nblk): headers of kPrepBlock regions each + per-level ordered id
+// segments.  Blocks [nblk, nblk + N): tap tables of one region each.
+__global__ void __launch_bounds__(kPrepBlock)
+roi_prep_kernel(const RoiFuseParams p, const PullWs ws) {
+  const int N = p.K * p.R;
+  const int tid = threadIdx.x;
+  if ((int)blockIdx.x < ws.nblk) {
+    // ---- headers (window bounds are filled by the table blocks) + segments ----
+    __shared__ int warp_cnt[kPrepBlock / 32][kMaxLevels];
+    const int i = blockIdx.x * kPrepBlock + tid;  // region id = r * K + k? no: k * R + r
+    int lvl = -1;
+    if (i < N) {
+      const int k = i / p.R, r = i - k * p.R;
+      RegionBox bx = region_box(p.rois + 5 * (size_t)k, r, p.facs);
+      lvl = (p.L == 1) ? 0 : map_roi_level(bx, p.L, p.finest_scale);
+      const int b = (int)bx.b;
+      if (lvl >= 0 && (b < 0 || b >= p.B)) lvl = -1;
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int l = 0; l < p.L; ++l) {
+      const unsigned m = __ballot_sync(0xffffffffu, lvl == l);
+      if (lane == 0) warp_cnt[warp][l] = __popc(m);
+    }
+    __syncthreads();
+    for (int l = 0; l < p.L; ++l) {
+      const unsigned m = __ballot_sync(0xffffffffu, lvl == l);
+      if (lvl == l) {
+        int off = __popc(m & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) off += warp_cnt[w][l];
+        ws.seg_ids[((size_t)blockIdx.x * p.L + l) * kPrepBlock + off] = i;
+      }
+    }
+    if (tid < p.L) {
+      int c = 0;
+      for (int w = 0; w < kPrepBlock / 32; ++w) c += warp_cnt[w][tid];
+      ws.seg_cnt[blockIdx.x * p.L + tid] = c;
+    }
+    return;
+  }
+  // ---- tap tables of region i ----
+  __shared__ CtaHeader hd;
+  __shared__ AxisTable ty, tx;
+  __shared__ int fit[2];
+  const int i = blockIdx.x - ws.nblk;
+  const int k = i / p.R, r = i - k * p.R;
+  const bool live = setup_cta(p, k, r, hd, ty, tx);
+  RegionHdr h;
+  h.lvl = live ? hd.lvl : -1;
+  h.batch = live ? hd.g.batch : 0;
+  h.ymin = h.ymax = h.xmin = h.xmax = 0;
+  h.src = i;
+  h.flags = 0;
+  if (live && hd.overflow) h.flags = 1;
+  if (live && !hd.overflow) {
+    h.ymin = hd.ymin; h.ymax = hd.ymax; h.xmin = hd.xmin; h.xmax = hd.xmax;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) {
+      const bool ok = transpose_axis(ty, p.PH, hd.ymin, hd.ymax, 1.0f / hd.g.count,
+                                     ws.rowtab + (size_t)i * kWinCap, ws.rowext + (size_t)i * kExtCap, lane);
+      if (lane == 0) fit[0] = ok;
+    } else if (warp == 1) {
+      const bool ok = transpose_axis(tx, p.PW, hd.xmin, hd.xmax, 1.0f,
+                                     ws.coltab + (size_t)i * kWinCap, ws.colext + (size_t)i * kExtCap, lane);
+      if (lane == 0) fit[1] = ok;
+    }
+    __syncthreads();
+    if (!fit[0] || !fit[1]) h.flags = 1;
+  }
+  if (tid == 0) ws.hdr[i] = h;
+}
+
+// ----------------------------------------------------------- pull backward
+constexpr int kTile = 8;        // 8 x 8 pixel tile, warp == tile row
+constexpr int kListCap = 1024;  // regions per list pass
+
+struct TileMap {
+  int start[kMaxLevels + 1];  // first tile index of each level (all images)
+  int tiles_x[kMaxLevels], tiles_y[kMaxLevels];
+};
+
+// NV = 128-bit vectors per lane (channels per pass = 32 * V * NV).
+template <typename T, int NV>
+__device__ __forceinline__ void pull_px(const T* __restrict__ dsrc, int RC, int PW,
+                                        const TapEntry re, const float* __restrict__ rext,
+                                        const TapEntry ce, const float* __restrict__ cext,
+                                        float (&acc)[NV][VecOf<T>::n]) {
+  constexpr int V = VecOf<T>::n;
+  const int pa = re.p0n & 0xffff, na = re.p0n >> 16;
+  const int pb = ce.p0n & 0xffff, nb = ce.p0n >> 16;
+  for (int a = 0; a < na; ++a) {
+    const float wa = (na <= 2) ? (a == 0 ? re.w0 : re.w1) : rext[re.ext + a];
+    const T* __restrict__ rowp = dsrc + (size_t)((pa + a) * PW + pb) * RC;
+    for (int b = 0; b < nb; ++b) {
+      const float w = wa * ((nb <= 2) ? (b == 0 ? ce.w0 : ce.w1) : cext[ce.ext + b]);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        float f[V];
+        ldg_vec<T>(rowp + (size_t)b * RC + v * 32 * V, f);
+#pragma unroll
+        for (int u = 0; u < V; ++u) acc[v][u] = fmaf(w, f[u], acc[v][u]);
+      }
+    }
+  }
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(kThreads)
+roi_bwd_pull(const RoiFuseParams p, const PullWs ws, const TileMap tm) {
+  constexpr int V = VecOf<T>::n;
+  __shared__ int list[kListCap];
+  __shared__ int list_n;
+  __shared__ int warp_tot[kThreads / 32];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int l = 0;
+  while (l + 1 < p.L && (int)blockIdx.x >= tm.start[l + 1]) ++l;
+  int t = blockIdx.x - tm.start[l];
+  const int per_img = tm.tiles_x[l] * tm.tiles_y[l];
+  const int b = t / per_img;
+  t -= b * per_img;
+  const int tyi = t / tm.tiles_x[l], txi = t - tyi * tm.tiles_x[l];
+  const int y0 = tyi * kTile, x0 = txi * kTile;
+  const int H = p.H[l], W = p.W[l], C = p.C, RC = p.R * C, PHW = p.PH * p.PW;
+  const int y = y0 + warp;  // this warp's row
+  const int y1 = min(y0 + kTile, H) - 1, x1 = min(x0 + kTile, W) - 1;
+  const T* __restrict__ dout = static_cast<const T*>(p.dout);
+  float* __restrict__ dimg = p.dfeats[l] + (size_t)b * H * W * C;
+  const int cpass = 32 * V * NV;
+
+  for (int c0 = 0; c0 < C; c0 += cpass) {
+    const int cl = c0 + lane * V;  // first channel of this lane's first vector
+    float acc[kTile][NV][V];
+#pragma unroll
+    for (int x = 0; x < kTile; ++x)
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int u = 0; u < V; ++u) acc[x][v][u] = 0.f;
+
+    // regions of this level in index order, kListCap candidates-hits per pass
+    int blk = 0, pos = 0;  // cursor into the per-block segments (uniform)
+    bool more = true;
+    while (more) {
+      __syncthreads();
+      if (tid == 0) list_n = 0;
+      __syncthreads();
+      // ---- ordered compaction of intersecting regions into list[] ----
+      while (blk < ws.nblk) {
+        const int cnt = ws.seg_cnt[blk * p.L + l];
+        const int* __restrict__ ids = ws.seg_ids + ((size_t)blk * p.L + l) * kPrepBlock;
+        bool full = false;
+        while (pos < cnt) {
+          const int j = pos + tid;
+          int id = -1;
+          bool hit = false;
+          if (j < cnt) {
+            id = ids[j];
+            const RegionHdr h = ws.hdr[id];
+            hit = h.lvl == l && h.batch == b && h.flags == 0 && h.ymax >= y0 && h.ymin <= y1 &&
+                  h.xmax >= x0 && h.xmin <= x1;
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, hit);
+          if (lane == 0) warp_tot[warp] = __popc(m);
+          __syncthreads();
+          int base = list_n, tot = 0;
+          for (int w = 0; w < kThreads / 32; ++w) {
+            if (w < warp) base += warp_tot[w];
+            tot += warp_tot[w];
+          }
+          if (list_n + tot > kListCap) { full = true; __syncthreads(); break; }
+          if (hit) list[base + __popc(m & ((1u << lane) - 1u))] = id;
+          __syncthreads();
+          if (tid == 0) list_n += tot;
+          __syncthreads();
+          pos += kThreads;
+        }
+        if (full) break;
+        ++blk; pos = 0;
+      }
+      more = blk < ws.nblk;
+      __syncthreads();
+      const int n = list_n;
+      // ---- accumulate: warp == row y, lanes == channels ----
+      if (y <= y1 && cl < C) {
+        for (int q = 0; q < n; ++q) {
+          const int id = list[q];
+          const RegionHdr h = ws.hdr[id];
+          if (y < h.ymin || y > h.ymax) continue;
+          const TapEntry re = ws.rowtab[(size_t)id * kWinCap + (y - h.ymin)];
+          if ((re.p0n >> 16) == 0) continue;
+          const T* __restrict__ dsrc = dout + (size_t)(h.src / p.R) * PHW * RC +
+                                       (size_t)(h.src % p.R) * C + cl;
+          const float* __restrict__ rext = ws.rowext + (size_t)id * kExtCap;
+          const float* __restrict__ cext = ws.colext + (size_t)id * kExtCap;
+          const TapEntry* __restrict__ ctab = ws.coltab + (size_t)id * kWinCap - h.xmin;
+#pragma unroll
+          for (int x = 0; x < kTile; ++x) {
+            const int xx = x0 + x;
+            if (xx < h.xmin || xx > h.xmax) continue;
+            const TapEntry ce = ctab[xx];
+            if ((ce.p0n >> 16) == 0) continue;
+            pull_px<T, NV>(dsrc, RC, p.PW, re, rext, ce, cext, acc[x]);
+          }
+        }
+      }
+    }
+    // ---- every element of the tile written exactly once ----
+    if (y <= y1) {
+#pragma unroll
+      for (int x = 0; x < kTile; ++x) {
+        if (x0 + x > x1) continue;
+        float* __restrict__ o = dimg + ((size_t)y * W + x0 + x) * C + cl;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          if (cl + v * 32 * V >= C) continue;
+#pragma unroll
+          for (int u = 0; u < V; u += 4)
+            *reinterpret_cast<float4*>(o + v * 32 * V + u) =
+                make_float4(acc[x][v][u], acc[x][v][u + 1], acc[x][v][u + 2], acc[x][v][u + 3]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ launchers
+cudaError_t launch_roi_fuse_forward_cl(const RoiFuseParams& p, int dtype, int out_cl,
+                                       cudaStream_t stream) {
+  const int PHW = p.PH * p.PW;
+  const int grid = p.K * p.R;
+  int opitch = 0, bpp = PHW, smem = kHdrBytes;
+  if (!out_cl) {
+    opitch = p.C + 4;
+    bpp = (96 * 1024) / (opitch * 4);
+    if (bpp < 1) return cudaErrorInvalidValue;
+    if (bpp > PHW) bpp = PHW;
+    smem += bpp * opitch * 4;
+  }
+  cudaError_t e;
+#define ARFE_FWD_CL(TT, OC)                                                        \
+  do {                                                                             \
+    if ((e = set_smem(roi_fuse_fwd_cl<TT, OC>, smem)) != cudaSuccess) return e;    \
+    roi_fuse_fwd_cl<TT, OC><<<grid, kThreads, smem, stream>>>(p, opitch, bpp);     \
+  } while (0)
+  if (dtype == 0) { if (out_cl) ARFE_FWD_CL(float, true); else ARFE_FWD_CL(float, false); }
+  else { if (out_cl) ARFE_FWD_CL(__nv_bfloat16, true); else ARFE_FWD_CL(__nv_bfloat16, false); }
+#undef ARFE_FWD_CL
+  return cudaGetLastError();
+}
+
+size_t roi_pull_workspace_bytes(int K, int R, int L) {
+  return pull_ws_layout(K * R, L, nullptr, nullptr);
+}
+
+// dout: channels-last [K][PH*PW][R*C]; dfeats: NHWC fp32, fully written.
+// `flags_out` (host side) is not needed: regions whose tables did not fit are
+// flagged in the workspace and added afterwards by the atomic kernel.
+cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, void* workspace,
+                                          size_t workspace_bytes, cudaStream_t stream) {
+  const int N = p.K * p.R;
+  PullWs ws;
+  const size_t need = pull_ws_layout(N, p.L, static_cast<unsigned char*>(workspace), &ws);
+  if (need > workspace_bytes) return cudaErrorInvalidValue;
+  roi_prep_kernel<<<ws.nblk + N, kPrepBlock, 0, stream>>>(p, ws);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  TileMap tm;
+  int total = 0;
+  for (int l = 0; l < p.L; ++l) {
+    tm.start[l] = total;
+    tm.tiles_x[l] = (p.W[l] + kTile - 1) / kTile;
+    tm.tiles_y[l] = (p.H[l] + kTile - 1) / kTile;
+    total += tm.tiles_x[l] * tm.tiles_y[l] * p.B;
+  }
+  for (int l = p.L; l <= kMaxLevels; ++l) tm.start[l] = total;
+  for (int l = p.L; l < kMaxLevels; ++l) tm.tiles_x[l] = tm.tiles_y[l] = 1;
+  if (total == 0) return cudaSuccess;
+  const int V = dtype == 0 ? 4 : 8;
+  const bool two = p.C > 32 * V;
+  if (dtype == 0) {
+    if (two) roi_bwd_pull<float, 2><<<total, kThreads, 0, stream>>>(p, ws, tm);
+    else roi_bwd_pull<float, 1><<<total, kThreads, 0, stream>>>(p, ws, tm);
+  } else {
+    if (two) roi_bwd_pull<__nv_bfloat16, 2><<<total, kThreads, 0, stream>>>(p, ws, tm);
+    else roi_bwd_pull<__nv_bfloat16, 1><<<total, kThreads, 0, stream>>>(p, ws, tm);
+  }
+  return cudaGetLastError();
+}
+
+// Device pointer to the per-region headers inside a laid-out workspace (the
+// atomic fallback kernel reads the `flags` field).
+const void* roi_pull_headers(int K, int R, int L, void* workspace) {
+  PullWs ws;
+  pull_ws_layout(K * R, L, static_cast<unsigned char*>(workspace), &ws);
+  return ws.hdr;
+}
+
+}  // namespace arfe

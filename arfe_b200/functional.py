@@ -30,17 +30,23 @@ def _prep_rois(rois):
     return rois.detach().float().contiguous()
 
 
+def _vec_ok(C, dtype):
+    return C % (4 if dtype == torch.float32 else 8) == 0
+
+
 class _RoIFuseFunction(Function):
     """Fused region generation + level map + multi-level RoIAlign (+ cat).
 
     regions=1 reproduces SingleRoIExtractor.forward
     (roi_extractors/single_level.py:109-152); regions=3 reproduces the AR-RFF
     block of StandardRoIHead._bbox_forward (standard_roi_head.py:138-155).
+    Channels-last features take the fast path: 128-bit gathers forward, the
+    atomic-free deterministic "pull" kernel backward.
     """
 
     @staticmethod
     def forward(ctx, rois, out_size, spatial_scales, sample_num, regions, facs,
-                finest_scale, *feats):
+                finest_scale, out_channels_last, *feats):
         oh, ow = _pair(out_size)
         feats, layout, dt = _prep_feats(feats)
         rois = _prep_rois(rois)
@@ -48,17 +54,20 @@ class _RoIFuseFunction(Function):
         Hs = [f.shape[2] for f in feats]
         Ws = [f.shape[3] for f in feats]
         K = rois.size(0)
-        out = feats[0].new_empty((K, regions * C, oh, ow))
+        fast = layout == L.ARFE_NHWC and _vec_ok(C, feats[0].dtype)
+        out_cl = bool(out_channels_last) and fast
+        out = torch.empty((K, regions * C, oh, ow), dtype=feats[0].dtype, device=feats[0].device,
+                          memory_format=torch.channels_last if out_cl else torch.contiguous_format)
         ctx.meta = (oh, ow, tuple(spatial_scales), sample_num, regions, facs,
-                    finest_scale, layout, dt, B, C, Hs, Ws, feats[0].dtype)
+                    finest_scale, layout, dt, B, C, Hs, Ws, feats[0].dtype, fast)
         ctx.save_for_backward(rois)
         if K > 0:
             rc = L.lib().arfe_roi_fuse_forward(
                 L.ptr_array(feats), L.int_array(Hs), L.int_array(Ws),
                 L.float_array(spatial_scales), len(feats), B, C, rois.data_ptr(),
                 K, regions, float(facs), oh, ow, int(sample_num),
-                float(finest_scale), dt, layout, out.data_ptr(), None, None,
-                L.stream_ptr(out.device))
+                float(finest_scale), dt, layout, L.ARFE_NHWC if out_cl else L.ARFE_NCHW,
+                out.data_ptr(), None, None, L.stream_ptr(out.device))
             L.check(rc, "arfe_roi_fuse_forward")
         return out
 
@@ -67,33 +76,53 @@ class _RoIFuseFunction(Function):
     def backward(ctx, grad_out):
         (rois,) = ctx.saved_tensors
         (oh, ow, scales, sample_num, regions, facs, finest_scale, layout, dt, B,
-         C, Hs, Ws, fdtype) = ctx.meta
+         C, Hs, Ws, fdtype, fast) = ctx.meta
         nlev = len(Hs)
-        if not any(ctx.needs_input_grad[7:]):
-            return (None,) * (7 + nlev)
-        dfeats = [_zeros((B, C, Hs[l], Ws[l]), torch.float32, grad_out.device, layout)
-                  for l in range(nlev)]
+        NP = 8  # non-tensor inputs of forward()
+        if not any(ctx.needs_input_grad[NP:]):
+            return (None,) * (NP + nlev)
         K = rois.size(0)
-        if K > 0:
-            g = grad_out.contiguous()
-            if g.dtype != fdtype:
-                g = g.to(fdtype)
-            rc = L.lib().arfe_roi_fuse_backward(
-                g.data_ptr(), L.int_array(Hs), L.int_array(Ws),
-                L.float_array(scales), nlev, B, C, rois.data_ptr(), K, regions,
-                float(facs), oh, ow, int(sample_num), float(finest_scale), dt,
-                layout, L.ptr_array(dfeats), L.stream_ptr(g.device))
-            L.check(rc, "arfe_roi_fuse_backward")
+        dev = grad_out.device
+        g = grad_out if grad_out.dtype == fdtype else grad_out.to(fdtype)
+        lib = L.lib()
+        if fast and K > 0:
+            # pull kernel: channels-last dout, every gradient element written once
+            g = g.contiguous(memory_format=torch.channels_last)
+            nbytes = lib.arfe_roi_fuse_pull_workspace_bytes(K, regions, nlev)
+            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+            ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+            dfeats = [torch.empty((B, C, Hs[l], Ws[l]), dtype=torch.float32, device=dev,
+                                  memory_format=torch.channels_last) for l in range(nlev)]
+            rc = lib.arfe_roi_fuse_backward_pull(
+                g.data_ptr(), L.int_array(Hs), L.int_array(Ws), L.float_array(scales), nlev, B,
+                C, rois.data_ptr(), K, regions, float(facs), oh, ow, int(sample_num),
+                float(finest_scale), dt, L.ptr_array(dfeats), ws_ptr, nbytes,
+                L.stream_ptr(dev))
+            L.check(rc, "arfe_roi_fuse_backward_pull")
+        else:
+            dfeats = [_zeros((B, C, Hs[l], Ws[l]), torch.float32, dev, layout)
+                      for l in range(nlev)]
+            if K > 0:
+                g_cl = L.layout_of(g) == L.ARFE_NHWC
+                g = g.contiguous(memory_format=torch.channels_last) if g_cl else g.contiguous()
+                rc = lib.arfe_roi_fuse_backward(
+                    g.data_ptr(), L.ARFE_NHWC if g_cl else L.ARFE_NCHW, L.int_array(Hs),
+                    L.int_array(Ws), L.float_array(scales), nlev, B, C, rois.data_ptr(), K,
+                    regions, float(facs), oh, ow, int(sample_num), float(finest_scale), dt,
+                    layout, L.ptr_array(dfeats), L.stream_ptr(dev))
+                L.check(rc, "arfe_roi_fuse_backward")
         grads = tuple(d if fdtype == torch.float32 else d.to(fdtype) for d in dfeats)
-        return (None,) * 7 + grads
+        return (None,) * NP + grads
 
 
 def roi_fuse(feats, rois, out_size, spatial_scales, sample_num=0, regions=3,
-             facs=1.0, finest_scale=56):
-    """[K, regions*C, oh, ow]; channel blocks (ori, lw, lh) when regions=3."""
+             facs=1.0, finest_scale=56, out_channels_last=False):
+    """[K, regions*C, oh, ow]; channel blocks (ori, lw, lh) when regions=3.
+    out_channels_last=True (channels-last features only) returns the tensor in
+    torch.channels_last memory format -- what cuDNN's 3x3 convs prefer."""
     return _RoIFuseFunction.apply(rois, out_size, tuple(spatial_scales),
                                   sample_num, regions, facs, finest_scale,
-                                  *feats)
+                                  out_channels_last, *feats)
 
 
 def roi_fuse_debug(rois, Hs, Ws, spatial_scales, out_size=7, sample_num=0,

@@ -23,6 +23,8 @@ class SingleRoIExtractor(nn.Module):
         self.featmap_strides = featmap_strides
         self.finest_scale = finest_scale
         self.fp16_enabled = False
+        # emit RoI features in torch.channels_last when the pyramid is channels-last
+        self.roi_feats_channels_last = False
 
     @property
     def num_inputs(self):
@@ -78,7 +80,8 @@ class SingleRoIExtractor(nn.Module):
             rois = self.roi_rescale(rois, roi_scale_factor)
         if lvl is None and replace_rois is None:
             out = roi_fuse(feats, rois, out_size, scales[:num_levels], sample_num,
-                           regions=1, finest_scale=self.finest_scale)
+                           regions=1, finest_scale=self.finest_scale,
+                           out_channels_last=self.roi_feats_channels_last)
         else:
             # hook path (unused by ARFE's configs): levels from torch ops, one
             # single-level launch of the same kernel per level
@@ -102,5 +105,6 @@ class SingleRoIExtractor(nn.Module):
         out_size, sample_num, scales = self._layer_args()
         feats, half = self._cast_in(feats)
         out = roi_fuse(feats, rois, out_size, scales[:len(feats)], sample_num,
-                       regions=regions, facs=facs, finest_scale=self.finest_scale)
+                       regions=regions, facs=facs, finest_scale=self.finest_scale,
+                       out_channels_last=self.roi_feats_channels_last)
         return out.half() if half else out

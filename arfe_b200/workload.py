@@ -21,7 +21,6 @@ from . import _lib as L
 STRIDES = (4, 8, 16, 32, 64)
 KERNELS = ("fpn_gather_fwd", "fpn_apply_fwd", "roi_fuse_fwd", "rff_gate_fwd",
            "rff_gate_bwd", "roi_fuse_bwd", "fpn_apply_bwd", "fpn_gather_bwd")
-LAUNCHES_PER_STEP = 9
 
 
 def pyramid_shapes(img_h=800, img_w=1344, strides=STRIDES):
@@ -52,8 +51,9 @@ def synthetic_rois(K, img_w=1344, img_h=800, batch=1, seed=0, smin=16.0, smax=60
 
 
 def host_inputs(batch=2, rois_per_img=512, channels=256, img_h=800, img_w=1344,
-                dtype=torch.float32, seed=0, pin=False):
-    """Synthetic inputs of one step on the HOST (optionally pinned)."""
+                dtype=torch.float32, seed=0, pin=False, channels_last=False):
+    """Synthetic inputs of one step on the HOST (optionally pinned; optionally
+    stored in torch.channels_last memory format -- same logical tensors)."""
     shapes = pyramid_shapes(img_h, img_w)
     g = torch.Generator().manual_seed(seed)
     K = batch * rois_per_img
@@ -68,6 +68,12 @@ def host_inputs(batch=2, rois_per_img=512, channels=256, img_h=800, img_w=1344,
     t["b"] = torch.randn(K, channels, 7, 7, generator=g).relu().to(dtype)
     t["gz"] = torch.randn(K, channels, 7, 7, generator=g).to(dtype)      # dL/d(gate out)
     t["gbsf"] = torch.randn(batch, channels, hr, wr, generator=g).to(dtype)  # dL/d(gathered)
+    if channels_last:
+        def cl(v):
+            if isinstance(v, list):
+                return [cl(e) for e in v]
+            return v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v
+        t = {k: cl(v) for k, v in t.items()}
     if pin:
         def p(v):
             return [p(e) for e in v] if isinstance(v, list) else v.pin_memory()
@@ -77,12 +83,20 @@ def host_inputs(batch=2, rois_per_img=512, channels=256, img_h=800, img_w=1344,
 
 
 class TrainStep:
-    """Pre-allocated device state + the 9-launch step through the C ABI."""
+    """Pre-allocated device state + the step through the C ABI.
 
-    def __init__(self, host, device, regions=3):
+    layout = channels-last (default): the fast path -- 128-bit gathers forward,
+    atomic-free pull backward, no zero-fill.  layout = NCHW: the reference's
+    memory layout through the compatibility kernels.
+    """
+
+    def __init__(self, host, device, regions=3, channels_last=True):
         self.dev = device
         self.lib = L.lib()
         x = host["x"]
+        self.cl = bool(channels_last)
+        self.layout = L.ARFE_NHWC if self.cl else L.ARFE_NCHW
+        mf = torch.channels_last if self.cl else torch.contiguous_format
         self.dtype = x[0].dtype
         self.dt = L.dtype_code(x[0])
         self.B, self.C = x[0].shape[:2]
@@ -90,14 +104,23 @@ class TrainStep:
         self.nlev = len(x)
         self.K = host["rois"].shape[0]
         self.R = regions
-        d = lambda v: [e.to(device) for e in v] if isinstance(v, list) else v.to(device)
+
+        def d(v):
+            if isinstance(v, list):
+                return [d(e) for e in v]
+            v = v.to(device)
+            return v.contiguous(memory_format=mf) if v.dim() == 4 else v
         self.x, self.bsf, self.g1, self.g2 = d(host["x"]), d(host["bsf"]), d(host["g1"]), d(host["g2"])
         self.rois, self.a, self.b, self.gz, self.gbsf = (d(host[k]) for k in ("rois", "a", "b", "gz", "gbsf"))
         B, C, K, R = self.B, self.C, self.K, self.R
         hr, wr = self.shapes[2]
-        e = lambda *s, dtype=self.dtype: torch.empty(*s, dtype=dtype, device=device)
+
+        def e(*s, dtype=self.dtype):
+            if len(s) == 4:
+                return torch.empty(s, dtype=dtype, device=device, memory_format=mf)
+            return torch.empty(s, dtype=dtype, device=device)
         self.gathered = e(B, C, hr, wr)
-        self.argmax = e(2, B, C, hr, wr, dtype=torch.uint8)
+        self.argmax = torch.empty((2, B, C, hr, wr), dtype=torch.uint8, device=device)
         self.y = [e(B, C, h, w) for h, w in self.shapes]
         self.F = e(K, R * C, 7, 7)
         self.z = e(K, C, 7, 7)
@@ -110,6 +133,9 @@ class TrainStep:
         self.dg1 = [e(B, 1, h, w, dtype=torch.float32) for h, w in self.shapes]
         self.dg2 = [e(B, 1, h, w, dtype=torch.float32) for h, w in self.shapes]
         self.dx = [e(B, C, h, w) for h, w in self.shapes]
+        self.ws_bytes = self.lib.arfe_roi_fuse_pull_workspace_bytes(K, R, self.nlev)
+        self.ws = torch.empty(self.ws_bytes + 256, dtype=torch.uint8, device=device)
+        self.ws_ptr = (self.ws.data_ptr() + 255) // 256 * 256
         # C arrays built once
         self.H = L.int_array([s[0] for s in self.shapes])
         self.W = L.int_array([s[1] for s in self.shapes])
@@ -119,66 +145,77 @@ class TrainStep:
         self.p_dy, self.p_dy_in = L.ptr_array(self.dy), L.ptr_array(self.dy_in)
         self.p_dg1, self.p_dg2 = L.ptr_array(self.dg1), L.ptr_array(self.dg2)
         self.p_dx = L.ptr_array(self.dx)
-        self.n_per_roi = C * 49
+        # the gate sees [rows][n] with `ori` strided inside the concatenated tensor
+        if self.cl:   # memory [K*49][R*C]: a row is one bin of one RoI
+            self.gate_rows, self.gate_n, self.gate_stride = K * 49, C, R * C
+        else:         # memory [K][R*C*49]: a row is one RoI
+            self.gate_rows, self.gate_n, self.gate_stride = K, C * 49, R * C * 49
         self.stream = L.stream_ptr(device)
 
     # -- the eight ops; each returns the C return code ----------------------
     def fpn_gather_fwd(self):
         return self.lib.arfe_fpn_gather_forward(
-            self.p_x, self.H, self.W, self.nlev, self.B, self.C, 2, self.dt, 0,
+            self.p_x, self.H, self.W, self.nlev, self.B, self.C, 2, self.dt, self.layout,
             self.gathered.data_ptr(), self.argmax.data_ptr(), self.stream)
 
     def fpn_apply_fwd(self):
         hr, wr = self.shapes[2]
         return self.lib.arfe_fpn_apply_forward(
             self.p_x, self.bsf.data_ptr(), self.p_g1, self.p_g2, self.H, self.W, self.nlev,
-            self.B, self.C, hr, wr, self.dt, 0, self.p_y, self.stream)
+            self.B, self.C, hr, wr, self.dt, self.layout, self.p_y, self.stream)
 
     def roi_fuse_fwd(self):
         return self.lib.arfe_roi_fuse_forward(
             self.p_y, self.H, self.W, self.scales, self.nlev, self.B, self.C,
-            self.rois.data_ptr(), self.K, self.R, 1.0, 7, 7, 0, 56.0, self.dt, 0,
-            self.F.data_ptr(), None, None, self.stream)
+            self.rois.data_ptr(), self.K, self.R, 1.0, 7, 7, 0, 56.0, self.dt, self.layout,
+            self.layout, self.F.data_ptr(), None, None, self.stream)
 
     def rff_gate_fwd(self):
         return self.lib.arfe_rff_gate_forward(
-            self.F.data_ptr(), self.R * self.n_per_roi, self.a.data_ptr(), self.b.data_ptr(),
-            self.z.data_ptr(), self.K, self.n_per_roi, self.dt, self.stream)
+            self.F.data_ptr(), self.gate_stride, self.a.data_ptr(), self.b.data_ptr(),
+            self.z.data_ptr(), self.gate_rows, self.gate_n, self.dt, self.stream)
 
     def rff_gate_bwd(self):
         return self.lib.arfe_rff_gate_backward(
-            self.gz.data_ptr(), self.F.data_ptr(), self.R * self.n_per_roi, self.a.data_ptr(),
-            self.b.data_ptr(), self.d_ori.data_ptr(), self.d_ab.data_ptr(), self.K,
-            self.n_per_roi, self.dt, self.stream)
+            self.gz.data_ptr(), self.F.data_ptr(), self.gate_stride, self.a.data_ptr(),
+            self.b.data_ptr(), self.d_ori.data_ptr(), self.d_ab.data_ptr(), self.gate_rows,
+            self.gate_n, self.dt, self.stream)
 
     def roi_fuse_bwd(self):
+        if self.cl:
+            return self.lib.arfe_roi_fuse_backward_pull(
+                self.dF.data_ptr(), self.H, self.W, self.scales, self.nlev, self.B, self.C,
+                self.rois.data_ptr(), self.K, self.R, 1.0, 7, 7, 0, 56.0, self.dt,
+                self.p_dy, self.ws_ptr, self.ws_bytes, self.stream)
         return self.lib.arfe_roi_fuse_backward(
-            self.dF.data_ptr(), self.H, self.W, self.scales, self.nlev, self.B, self.C,
-            self.rois.data_ptr(), self.K, self.R, 1.0, 7, 7, 0, 56.0, self.dt, 0,
-            self.p_dy, self.stream)
+            self.dF.data_ptr(), L.ARFE_NCHW, self.H, self.W, self.scales, self.nlev, self.B,
+            self.C, self.rois.data_ptr(), self.K, self.R, 1.0, 7, 7, 0, 56.0, self.dt,
+            self.layout, self.p_dy, self.stream)
 
     def fpn_apply_bwd(self):
         hr, wr = self.shapes[2]
         return self.lib.arfe_fpn_apply_backward(
             self.p_dy_in, self.bsf.data_ptr(), self.p_g1, self.p_g2, self.H, self.W, self.nlev,
-            self.B, self.C, hr, wr, self.dt, 0, self.dbsf.data_ptr(), self.p_dg1, self.p_dg2,
-            self.stream)
+            self.B, self.C, hr, wr, self.dt, self.layout, self.dbsf.data_ptr(), self.p_dg1,
+            self.p_dg2, self.stream)
 
     def fpn_gather_bwd(self):
         return self.lib.arfe_fpn_gather_backward(
             self.gbsf.data_ptr(), self.argmax.data_ptr(), self.H, self.W, self.nlev, self.B,
-            self.C, 2, self.dt, 0, self.p_dx, self.stream)
+            self.C, 2, self.dt, self.layout, self.p_dx, self.stream)
 
     def glue_before_roi_bwd(self):
         """torch plumbing between our kernels: assemble dF (stand-in for the
-        conv backward of the two context branches) and zero the accumulators
-        (the reference's at::zeros, roi_align_kernel_v2.cu:325-326)."""
+        conv backward of the two context branches, which stays on PyTorch) and,
+        on the NCHW path only, zero the accumulators (the reference's
+        at::zeros, roi_align_kernel_v2.cu:325-326; the pull kernel needs none)."""
         C = self.C
         self.dF[:, :C].copy_(self.d_ori)
         self.dF[:, C:2 * C].copy_(self.d_ab)
         self.dF[:, 2 * C:].copy_(self.d_ab)
-        for t in self.dy:
-            t.zero_()
+        if not self.cl:
+            for t in self.dy:
+                t.zero_()
 
     def glue_before_apply_bwd(self):
         if self.dy_in is not self.dy:
@@ -198,6 +235,12 @@ class TrainStep:
         self.glue_before_apply_bwd()
         run("fpn_apply_bwd", self.fpn_apply_bwd)
         run("fpn_gather_bwd", self.fpn_gather_bwd)
+
+    def launches_per_step(self):
+        """Kernels of libarfe_b200.so per step: gather 1, apply 1, roi fwd 1,
+        gate 2, roi bwd (prep + pull + flagged-region fallback = 3 | atomic 1),
+        apply bwd 2, gather bwd 2 (vector kernel + small levels) | 1."""
+        return (1 + 1 + 1 + 2 + 3 + 2 + 1) if self.cl else (1 + 1 + 1 + 2 + 1 + 2 + 2)
 
     # -- algorithmic bytes per launch (DESIGN.md section 5) ------------------
     def algorithmic_bytes(self):

@@ -205,8 +205,9 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    host = wl.host_inputs(BATCH, ROIS_PER_IMG, CHANNELS, seed=rank, pin=True)
-    step = wl.TrainStep(host, dev)
+    cl = not args.nchw
+    host = wl.host_inputs(BATCH, ROIS_PER_IMG, CHANNELS, seed=rank, pin=True, channels_last=cl)
+    step = wl.TrainStep(host, dev, channels_last=cl)
 
     def barrier():
         if world > 1:
@@ -241,7 +242,7 @@ def run_ours(args, rank, local_rank, world):
     per_kernel_ms = {n: sum(a.elapsed_time(b) for a, b in ev[n]) / len(ev[n]) for n in names}
 
     # ---- e2e: host buffers in, scalar out, public module-level API --------
-    e2e_ms, h2d, d2h = run_e2e(args, host, dev, barrier)
+    e2e_ms, h2d, d2h = run_e2e(args, host, dev, barrier, cl)
 
     t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -266,13 +267,14 @@ def run_ours(args, rank, local_rank, world):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "rois_per_gpu": BATCH * ROIS_PER_IMG,
                        "parallelism": f"dp{world} (images sharded, no data-path collective)",
+                       "memory_format": "torch.channels_last (fast path)" if cl else "NCHW (reference layout, compatibility kernels)",
                        "l2": "inputs+outputs per step (~1.5 GB) exceed the 126 MB L2; no explicit flush",
                        "timing": "CUDA events on the launch stream, max over ranks"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
                     "note": "pinned-host pyramid+RoIs+conv stand-ins copied H2D every step, loss scalar read back"},
-            "gpu_launches": wl.LAUNCHES_PER_STEP * args.steps,
+            "gpu_launches": step.launches_per_step() * args.steps,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src},
             "kernels": kern,
@@ -285,11 +287,11 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def run_e2e(args, host, dev, barrier):
+def run_e2e(args, host, dev, barrier, cl):
     """Same step, but every step starts from pinned host memory and ends with a
     device->host read of the result scalar."""
     from arfe_b200 import workload as wl
-    step = wl.TrainStep(host, dev)
+    step = wl.TrainStep(host, dev, channels_last=cl)
     pairs = []
     for key in ("x", "g1", "g2"):
         pairs += list(zip(getattr(step, key), host[key]))
@@ -324,6 +326,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nchw", action="store_true", help="reference memory layout through the compatibility kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))

@@ -30,6 +30,7 @@
 #ifndef ARFE_B200_H_
 #define ARFE_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -70,7 +71,10 @@ const char* arfe_last_error(void);
  * regions = 3: out[K, 3*C, PH, PW]    channels [0,C) original box, [C,2C)
  *              adaptive_w ("lw"), [2C,3C) adaptive_h ("lh").
  * L = 1 skips the level map (single_level.py:120-123).
- * feats[l]: device, [B, C, H[l], W[l]] in `layout`; out: device, NCHW dense.
+ * feats[l]: device, [B, C, H[l], W[l]] in `layout`; out: device, dense, in
+ * `out_layout`: ARFE_NCHW [K][regions*C][PH][PW] (the reference's) or ARFE_NHWC
+ * = torch channels_last of the same logical tensor, [K][PH][PW][regions*C]
+ * (needs layout == ARFE_NHWC and C a multiple of 4 (fp32) / 8 (bf16)).
  * lvl_out  (optional, device int32 [regions, K]): level chosen per region box
  *          (-1: box whose scale is NaN, matches no level -> zero output row).
  * boxes_out(optional, device fp32 [regions, K, 5]): the region boxes used.
@@ -79,23 +83,41 @@ int arfe_roi_fuse_forward(const void* const* feats, const int32_t* H,
                           const int32_t* W, const float* spatial_scale, int L,
                           int B, int C, const float* rois, int K, int regions,
                           float facs, int PH, int PW, int sampling_ratio,
-                          float finest_scale, int dtype, int layout, void* out,
-                          int32_t* lvl_out, float* boxes_out, void* stream);
+                          float finest_scale, int dtype, int layout,
+                          int out_layout, void* out, int32_t* lvl_out,
+                          float* boxes_out, void* stream);
 
 /* Backward of the above w.r.t. the pyramid (no gradient for rois, like
  * RoIAlignFunction.backward, mmdet/ops/roi_align/roi_align.py:44-73, and
  * roi_align_ext.backward_v2, roi_align_ext.cpp:144-161).
- * dout: device [K, regions*C, PH, PW] dense NCHW, `dtype`.
+ * dout: device [K, regions*C, PH, PW] dense in `dout_layout`, `dtype`.
  * dfeats[l]: device fp32 [B, C, H[l], W[l]] in `layout`; the kernel ADDS into
  * them (the caller zero-fills, as the reference's at::zeros does,
  * roi_align_kernel_v2.cu:325-326; one buffer per level receives the sum over
  * all regions, replacing the reference's 15 dense per-level/region grads). */
-int arfe_roi_fuse_backward(const void* dout, const int32_t* H, const int32_t* W,
-                           const float* spatial_scale, int L, int B, int C,
-                           const float* rois, int K, int regions, float facs,
-                           int PH, int PW, int sampling_ratio,
+int arfe_roi_fuse_backward(const void* dout, int dout_layout, const int32_t* H,
+                           const int32_t* W, const float* spatial_scale, int L,
+                           int B, int C, const float* rois, int K, int regions,
+                           float facs, int PH, int PW, int sampling_ratio,
                            float finest_scale, int dtype, int layout,
                            float* const* dfeats, void* stream);
+
+/* Atomic-free backward for channels-last tensors ("pull"): every element of
+ * every dfeats[l] (fp32, ARFE_NHWC) is WRITTEN exactly once, in a fixed
+ * summation order (deterministic, unlike the reference's atomicAdd,
+ * roi_align_kernel_v2.cu:251-258); no zero-fill by the caller.
+ * dout: [K][PH][PW][regions*C] (ARFE_NHWC), `dtype`; C a multiple of 4 / 8.
+ * workspace: device scratch of at least arfe_roi_fuse_pull_workspace_bytes()
+ * bytes, 256-byte aligned, owned by the caller, reusable after the stream
+ * passes this call. */
+size_t arfe_roi_fuse_pull_workspace_bytes(int K, int regions, int L);
+int arfe_roi_fuse_backward_pull(const void* dout, const int32_t* H, const int32_t* W,
+                                const float* spatial_scale, int L, int B, int C,
+                                const float* rois, int K, int regions, float facs,
+                                int PH, int PW, int sampling_ratio,
+                                float finest_scale, int dtype,
+                                float* const* dfeats, void* workspace,
+                                size_t workspace_bytes, void* stream);
 
 /* Operator-level twins of roi_align_ext.forward_v2 / backward_v2
  * (roi_align_ext.cpp:126-161; aligned=True only -- aligned=False is the legacy
@@ -149,9 +171,11 @@ int arfe_rff_gate_backward(const void* g, const void* ori,
  *   levels < refine_level: F.adaptive_max_pool2d; others: nearest interpolate;
  *   out = ((((0+f0)+f1)+...)+f_{L-1}) / L
  * out: device [B,C,H[refine],W[refine]] `dtype`, `layout`.
- * argmax (optional, device uint8 [refine_level, B, C, Hr, Wr], NCHW order
- * regardless of layout): position of the max inside the pooling window
- * (dy*window_w+dx), saved for the backward. Window must have <= 255 cells.
+ * argmax (optional, device uint8, refine_level*B*C*Hr*Wr bytes, 4-byte aligned;
+ * an opaque buffer between this call and the backward, element order
+ * [level][B][C][Hr][Wr] for ARFE_NCHW and [level][B][Hr][Wr][C] for ARFE_NHWC):
+ * position of the max inside the pooling window (dy*window_w+dx).  Window must
+ * have <= 255 cells.
  * backward: dfeats[l] (device, `dtype`, `layout`) are fully WRITTEN. */
 int arfe_fpn_gather_forward(const void* const* feats, const int32_t* H,
                             const int32_t* W, int L, int B, int C,
