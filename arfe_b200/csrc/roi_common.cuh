@@ -212,7 +212,7 @@ struct __align__(16) RegionHdr {
   int batch;
   int ymin, ymax, xmin, xmax;
   int src;        // k * R + r (row of dout)
-  int flags;      // 1: tables did not fit -> handled by the atomic fallback kernel
+  int flags;      // bit 0: tables did not fit -> atomic fallback kernel; bits 8-11 / 12-15: bin blocks per row / column
 };
 
 constexpr int kHdrBytes = 128 + 2 * (int)sizeof(AxisTable);

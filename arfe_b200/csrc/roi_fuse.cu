@@ -379,7 +379,7 @@ roi_fuse_bwd(const RoiFuseParams p, int cb /* channels staged per pass */) {
   const int PH = p.PH, PW = p.PW, PHW = PH * PW, C = p.C;
   const T* __restrict__ dout_blk =
       static_cast<const T*>(p.dout) + ((size_t)k * p.R + r) * C * PHW;
-  if (p.flag_hdr && !static_cast<const RegionHdr*>(p.flag_hdr)[k * p.R + r].flags) return;
+  if (p.flag_hdr && !(static_cast<const RegionHdr*>(p.flag_hdr)[k * p.R + r].flags & 1)) return;
   // element (c, bin) of this region's incoming gradient, NCHW or channels-last
   auto dout_at = [&](int c, int bin) -> float {
     return p.dout_cl ? to_f(static_cast<const T*>(p.dout)[((size_t)k * PHW + bin) * (p.R * C) + (size_t)r * C + c])

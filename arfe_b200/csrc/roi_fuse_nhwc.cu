@@ -216,28 +216,32 @@ roi_fuse_fwd_cl(const RoiFuseParams p, int opitch, int bins_per_pass) {
 }
 
 // ------------------------------------------------------------ region prep
-// Workspace layout (bytes):
-//   [0, 256)                      PrepCounts (per prep block, per level counts)   -- see below
-//   hdr     : N * 32
-//   rowtab  : N * kWinCap * 16     coltab : N * kWinCap * 16
-//   rowext  : N * kExtCap * 4      colext : N * kExtCap * 4
-//   seg_ids : nblk * L * kPrepBlock * 4   seg_cnt : nblk * L * 4
-constexpr int kWinCap = 64;     // window rows / columns described per region
-constexpr int kExtCap = 64;     // spill area for rows/columns sampled by > 2 bins
+// Workspace layout (bytes, each array 256-byte aligned):
+//   hdr     : N * 32                         RegionHdr
+//   rowtab  : N * kTabLen * 16               TapEntry per (bin block, window row)
+//   coltab  : N * kTabLen * 16               TapEntry per (bin block, window column)
+//   seg_ids : nblk * L * kPrepBlock * 4      region ids per (prep block, level), index order
+//   seg_cnt : nblk * L * 4
+constexpr int kWinCap = 64;     // window rows / columns described per region (bin block 0)
+constexpr int kWinCapX = 16;    // ... for bin blocks 1..3 (only sub-pixel bins need them: tiny windows)
+constexpr int kMaxBlk = 4;      // a row may be sampled by up to 2 * kMaxBlk bins
+constexpr int kTabLen = kWinCap + (kMaxBlk - 1) * kWinCapX;  // TapEntries per region per axis
 constexpr int kPrepBlock = 256; // regions per header block
 
+__host__ __device__ inline int tab_index(int blk, int i) {
+  return blk == 0 ? i : kWinCap + (blk - 1) * kWinCapX + i;
+}
+
 struct __align__(16) TapEntry {
-  int p0n;        // first bin | (number of bins << 16)
-  float w0, w1;   // weights of the first two bins (row weights carry 1/count)
-  int ext;        // offset of the full weight list in the region's ext area (n > 2)
+  int p0;         // first bin sampling this row / column
+  int n;          // number of bins sampling it: 0, 1 or 2
+  float w0, w1;   // their aggregated weights (row weights carry 1/count)
 };
 
 struct PullWs {
   RegionHdr* hdr;
   TapEntry* rowtab;
   TapEntry* coltab;
-  float* rowext;
-  float* colext;
   int* seg_ids;
   int* seg_cnt;
   int nblk;
@@ -250,18 +254,14 @@ inline size_t pull_ws_layout(int N, int L, unsigned char* base, PullWs* ws) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   const size_t o_hdr = take((size_t)N * sizeof(RegionHdr));
-  const size_t o_row = take((size_t)N * kWinCap * sizeof(TapEntry));
-  const size_t o_col = take((size_t)N * kWinCap * sizeof(TapEntry));
-  const size_t o_rext = take((size_t)N * kExtCap * 4);
-  const size_t o_cext = take((size_t)N * kExtCap * 4);
+  const size_t o_row = take((size_t)N * kTabLen * sizeof(TapEntry));
+  const size_t o_col = take((size_t)N * kTabLen * sizeof(TapEntry));
   const size_t o_ids = take((size_t)nblk * L * kPrepBlock * 4);
   const size_t o_cnt = take((size_t)nblk * L * 4);
   if (ws) {
     ws->hdr = reinterpret_cast<RegionHdr*>(base + o_hdr);
     ws->rowtab = reinterpret_cast<TapEntry*>(base + o_row);
     ws->coltab = reinterpret_cast<TapEntry*>(base + o_col);
-    ws->rowext = reinterpret_cast<float*>(base + o_rext);
-    ws->colext = reinterpret_cast<float*>(base + o_cext);
     ws->seg_ids = reinterpret_cast<int*>(base + o_ids);
     ws->seg_cnt = reinterpret_cast<int*>(base + o_cnt);
     ws->nblk = nblk;
@@ -269,61 +269,47 @@ inline size_t pull_ws_layout(int N, int L, unsigned char* base, PullWs* ws) {
   return off;
 }
 
-// Transpose one axis table: for every window row (column) the bins sampling it.
-// Executed by one warp; lane = window row.  Returns false if it does not fit.
-__device__ bool transpose_axis(const AxisTable& t, int P, int lo, int hi, float scale,
-                               TapEntry* __restrict__ tab, float* __restrict__ ext,
-                               int lane) {
+// Transpose one axis table: for every window row (column) the bins sampling
+// it, two per block (block k holds bins p0+2k, p0+2k+1).  One warp; lane =
+// window row.  Returns the number of blocks used (1..kMaxBlk), or 0 when the
+// window / bin count does not fit: such regions take the atomic fallback kernel.
+__device__ int transpose_axis(const AxisTable& t, int P, int lo, int hi, float scale,
+                              TapEntry* __restrict__ tab, int lane) {
   const int n = hi - lo + 1;
-  if (n > kWinCap) return false;
-  bool ok = true;
-  int ext_used = 0;  // per-lane demand, prefix-summed below
+  if (n > kWinCap) return 0;
+  int maxcnt = 0;
   for (int i0 = 0; i0 < n; i0 += 32) {
     const int i = i0 + lane;
+    if (i >= n) continue;
+    const int row = lo + i;
     int p0 = -1, cnt = 0;
-    float w0 = 0.f, w1 = 0.f;
-    if (i < n) {
-      const int row = lo + i;
-      for (int q = 0; q < P; ++q)
-        if (t.cnt[q] > 0 && row >= t.first[q] && row < t.first[q] + t.cnt[q]) {
-          if (p0 < 0) p0 = q;
-          cnt = q - p0 + 1;
-        }
-      auto w_of = [&](int q) -> float {
-        const int j = row - t.first[q];
-        return (t.cnt[q] > 0 && j >= 0 && j < t.cnt[q]) ? t.w[t.off[q] + j] * scale : 0.f;
-      };
-      if (cnt > 0) w0 = w_of(p0);
-      if (cnt > 1) w1 = w_of(p0 + 1);
-    }
-    // ordered allocation of ext space for entries with more than two bins
-    const int need = (cnt > 2) ? cnt : 0;
-    int incl = need;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += v;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    const int my = ext_used + incl - need;
-    if (ext_used + total > kExtCap) ok = false;
-    if (ok && i < n) {
-      if (need) {
-        const int row = lo + i;
-        for (int a = 0; a < cnt; ++a) {
-          const int q = p0 + a;
-          const int j = row - t.first[q];
-          ext[my + a] = (t.cnt[q] > 0 && j >= 0 && j < t.cnt[q]) ? t.w[t.off[q] + j] * scale : 0.f;
-        }
+    for (int q = 0; q < P; ++q)
+      if (t.cnt[q] > 0 && row >= t.first[q] && row < t.first[q] + t.cnt[q]) {
+        if (p0 < 0) p0 = q;
+        cnt = q - p0 + 1;
       }
+    maxcnt = max(maxcnt, cnt);
+    auto w_of = [&](int q) -> float {
+      const int j = row - t.first[q];
+      return (q < P && t.cnt[q] > 0 && j >= 0 && j < t.cnt[q]) ? t.w[t.off[q] + j] * scale : 0.f;
+    };
+    for (int blk = 0; blk < kMaxBlk; ++blk) {
+      if (blk > 0 && i >= kWinCapX) break;
+      const int rem = cnt - 2 * blk;
       TapEntry e;
-      e.p0n = (p0 < 0 ? 0 : p0) | (cnt << 16);
-      e.w0 = w0; e.w1 = w1; e.ext = my;
-      tab[i] = e;
+      e.p0 = (p0 < 0 ? 0 : p0) + 2 * blk;
+      e.n = rem <= 0 ? 0 : (rem > 2 ? 2 : rem);
+      e.w0 = e.n > 0 ? w_of(e.p0) : 0.f;
+      e.w1 = e.n > 1 ? w_of(e.p0 + 1) : 0.f;
+      tab[tab_index(blk, i)] = e;
     }
-    ext_used += total;
   }
-  return __all_sync(0xffffffffu, ok);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, d));
+  const int nblk = (maxcnt + 1) / 2;
+  if (nblk > kMaxBlk) return 0;
+  if (nblk > 1 && n > kWinCapX) return 0;
+  return nblk < 1 ? 1 : nblk;
 }
 
 // Blocks [0, nblk): headers of kPrepBlock regions each + per-level ordered id
@@ -383,169 +369,218 @@ roi_prep_kernel(const RoiFuseParams p, const PullWs ws) {
     h.ymin = hd.ymin; h.ymax = hd.ymax; h.xmin = hd.xmin; h.xmax = hd.xmax;
     const int warp = tid >> 5, lane = tid & 31;
     if (warp == 0) {
-      const bool ok = transpose_axis(ty, p.PH, hd.ymin, hd.ymax, 1.0f / hd.g.count,
-                                     ws.rowtab + (size_t)i * kWinCap, ws.rowext + (size_t)i * kExtCap, lane);
-      if (lane == 0) fit[0] = ok;
+      const int nb = transpose_axis(ty, p.PH, hd.ymin, hd.ymax, 1.0f / hd.g.count,
+                                    ws.rowtab + (size_t)i * kTabLen, lane);
+      if (lane == 0) fit[0] = nb;
     } else if (warp == 1) {
-      const bool ok = transpose_axis(tx, p.PW, hd.xmin, hd.xmax, 1.0f,
-                                     ws.coltab + (size_t)i * kWinCap, ws.colext + (size_t)i * kExtCap, lane);
-      if (lane == 0) fit[1] = ok;
+      const int nb = transpose_axis(tx, p.PW, hd.xmin, hd.xmax, 1.0f,
+                                    ws.coltab + (size_t)i * kTabLen, lane);
+      if (lane == 0) fit[1] = nb;
     }
     __syncthreads();
     if (!fit[0] || !fit[1]) h.flags = 1;
+    else h.flags = (fit[0] << 8) | (fit[1] << 12);  // bin blocks per axis
   }
   if (tid == 0) ws.hdr[i] = h;
 }
 
 // ----------------------------------------------------------- pull backward
-constexpr int kTile = 8;        // 8 x 8 pixel tile, warp == tile row
-constexpr int kListCap = 1024;  // regions per list pass
+constexpr int kTileH = 8;       // tile rows, warp == tile row
+constexpr int kListCap = 768;   // regions listed per pass
+constexpr int kChunkR = 16;     // regions whose taps are expanded per round
 
 struct TileMap {
-  int start[kMaxLevels + 1];  // first tile index of each level (all images)
+  int start[kMaxLevels + 1];  // first CTA of each scheduled slot
+  int level[kMaxLevels];      // level of slot j (heaviest first)
   int tiles_x[kMaxLevels], tiles_y[kMaxLevels];
+  int nslots;
+  int groups;                 // channel groups per tile (C / (32 * V * NV))
 };
 
-// NV = 128-bit vectors per lane (channels per pass = 32 * V * NV).
-template <typename T, int NV>
-__device__ __forceinline__ void pull_px(const T* __restrict__ dsrc, int RC, int PW,
-                                        const TapEntry re, const float* __restrict__ rext,
-                                        const TapEntry ce, const float* __restrict__ cext,
-                                        float (&acc)[NV][VecOf<T>::n]) {
-  constexpr int V = VecOf<T>::n;
-  const int pa = re.p0n & 0xffff, na = re.p0n >> 16;
-  const int pb = ce.p0n & 0xffff, nb = ce.p0n >> 16;
-  for (int a = 0; a < na; ++a) {
-    const float wa = (na <= 2) ? (a == 0 ? re.w0 : re.w1) : rext[re.ext + a];
-    const T* __restrict__ rowp = dsrc + (size_t)((pa + a) * PW + pb) * RC;
-    for (int b = 0; b < nb; ++b) {
-      const float w = wa * ((nb <= 2) ? (b == 0 ? ce.w0 : ce.w1) : cext[ce.ext + b]);
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        float f[V];
-        ldg_vec<T>(rowp + (size_t)b * RC + v * 32 * V, f);
-#pragma unroll
-        for (int u = 0; u < V; ++u) acc[v][u] = fmaf(w, f[u], acc[v][u]);
-      }
-    }
-  }
-}
+// Compact copy of a listed region kept in shared memory.
+struct __align__(16) ListEntry {
+  int id;      // region id | row block << 24 | column block << 28
+  short ymin, ymax, xmin, xmax;
+  int src;
+};
 
-template <typename T, int NV>
-__global__ void __launch_bounds__(kThreads)
+// NV = 128-bit vectors per lane, TW = tile width in pixels.
+//
+// Round structure (kChunkR listed regions at a time):
+//   expand : one THREAD per (region, tile pixel) turns the region's row/column
+//            records into an explicit tap descriptor -- four element offsets
+//            into dout and four weights (missing taps: weight 0, offset of
+//            tap 0) -- in shared memory.  All per-region control work happens
+//            here, thread-parallel.
+//   stream : warp == tile row, lanes == channels: for every descriptor of its
+//            row: 4 x NV 128-bit loads, 16 x NV FMAs into register accumulators.
+template <typename T, int NV, int TW>
+__global__ void __launch_bounds__(kThreads, 2)
 roi_bwd_pull(const RoiFuseParams p, const PullWs ws, const TileMap tm) {
   constexpr int V = VecOf<T>::n;
-  __shared__ int list[kListCap];
+  constexpr int kSlots = kChunkR * TW;          // descriptors per tile row per round
+  __shared__ ListEntry list[kListCap];
+  __shared__ int4 d_off[kTileH * kSlots];       // tap offsets, .x < 0: empty slot
+  __shared__ float4 d_w[kTileH * kSlots];
   __shared__ int list_n;
   __shared__ int warp_tot[kThreads / 32];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  int l = 0;
-  while (l + 1 < p.L && (int)blockIdx.x >= tm.start[l + 1]) ++l;
-  int t = blockIdx.x - tm.start[l];
-  const int per_img = tm.tiles_x[l] * tm.tiles_y[l];
+  int j = 0;
+  while (j + 1 < tm.nslots && (int)blockIdx.x >= tm.start[j + 1]) ++j;
+  const int l = tm.level[j];
+  int t = blockIdx.x - tm.start[j];
+  const int grp = t % tm.groups;
+  t /= tm.groups;
+  const int per_img = tm.tiles_x[j] * tm.tiles_y[j];
   const int b = t / per_img;
   t -= b * per_img;
-  const int tyi = t / tm.tiles_x[l], txi = t - tyi * tm.tiles_x[l];
-  const int y0 = tyi * kTile, x0 = txi * kTile;
-  const int H = p.H[l], W = p.W[l], C = p.C, RC = p.R * C, PHW = p.PH * p.PW;
+  const int tyi = t / tm.tiles_x[j], txi = t - tyi * tm.tiles_x[j];
+  const int y0 = tyi * kTileH, x0 = txi * TW;
+  const int H = p.H[l], W = p.W[l], C = p.C, RC = p.R * C, PHW = p.PH * p.PW, PW = p.PW;
   const int y = y0 + warp;  // this warp's row
-  const int y1 = min(y0 + kTile, H) - 1, x1 = min(x0 + kTile, W) - 1;
-  const T* __restrict__ dout = static_cast<const T*>(p.dout);
+  const int y1 = min(y0 + kTileH, H) - 1, x1 = min(x0 + TW, W) - 1;
+  const int cl = grp * (32 * V * NV) + lane * V;  // first channel of this lane's first vector
+  const T* __restrict__ dbase = static_cast<const T*>(p.dout) + cl;
   float* __restrict__ dimg = p.dfeats[l] + (size_t)b * H * W * C;
-  const int cpass = 32 * V * NV;
 
-  for (int c0 = 0; c0 < C; c0 += cpass) {
-    const int cl = c0 + lane * V;  // first channel of this lane's first vector
-    float acc[kTile][NV][V];
+  float acc[TW][NV][V];
 #pragma unroll
-    for (int x = 0; x < kTile; ++x)
+  for (int x = 0; x < TW; ++x)
 #pragma unroll
-      for (int v = 0; v < NV; ++v)
+    for (int v = 0; v < NV; ++v)
 #pragma unroll
-        for (int u = 0; u < V; ++u) acc[x][v][u] = 0.f;
+      for (int u = 0; u < V; ++u) acc[x][v][u] = 0.f;
 
-    // regions of this level in index order, kListCap candidates-hits per pass
-    int blk = 0, pos = 0;  // cursor into the per-block segments (uniform)
-    bool more = true;
-    while (more) {
-      __syncthreads();
-      if (tid == 0) list_n = 0;
-      __syncthreads();
-      // ---- ordered compaction of intersecting regions into list[] ----
-      while (blk < ws.nblk) {
-        const int cnt = ws.seg_cnt[blk * p.L + l];
-        const int* __restrict__ ids = ws.seg_ids + ((size_t)blk * p.L + l) * kPrepBlock;
-        bool full = false;
-        while (pos < cnt) {
-          const int j = pos + tid;
-          int id = -1;
-          bool hit = false;
-          if (j < cnt) {
-            id = ids[j];
-            const RegionHdr h = ws.hdr[id];
-            hit = h.lvl == l && h.batch == b && h.flags == 0 && h.ymax >= y0 && h.ymin <= y1 &&
-                  h.xmax >= x0 && h.xmin <= x1;
-          }
-          const unsigned m = __ballot_sync(0xffffffffu, hit);
-          if (lane == 0) warp_tot[warp] = __popc(m);
-          __syncthreads();
-          int base = list_n, tot = 0;
-          for (int w = 0; w < kThreads / 32; ++w) {
-            if (w < warp) base += warp_tot[w];
-            tot += warp_tot[w];
-          }
-          if (list_n + tot > kListCap) { full = true; __syncthreads(); break; }
-          if (hit) list[base + __popc(m & ((1u << lane) - 1u))] = id;
-          __syncthreads();
-          if (tid == 0) list_n += tot;
-          __syncthreads();
-          pos += kThreads;
+  // regions of this level in index order, at most kListCap listed per pass
+  int blk = 0, pos = 0;  // cursor into the per-block segments (uniform)
+  bool more = true;
+  while (more) {
+    __syncthreads();
+    if (tid == 0) list_n = 0;
+    __syncthreads();
+    // ---- ordered compaction of the intersecting regions into list[] ----
+    while (blk < ws.nblk) {
+      const int cnt = ws.seg_cnt[blk * p.L + l];
+      const int* __restrict__ ids = ws.seg_ids + ((size_t)blk * p.L + l) * kPrepBlock;
+      bool full = false;
+      while (pos < cnt) {
+        const int q = pos + tid;
+        int mine = 0, nbr = 0, nbc = 0;  // list entries this thread contributes
+        RegionHdr h;
+        if (q < cnt) {
+          h = ws.hdr[ids[q]];
+          const bool hit = h.lvl == l && h.batch == b && (h.flags & 1) == 0 && h.ymax >= y0 &&
+                           h.ymin <= y1 && h.xmax >= x0 && h.xmin <= x1;
+          if (hit) { nbr = (h.flags >> 8) & 15; nbc = (h.flags >> 12) & 15; mine = nbr * nbc; }
         }
-        if (full) break;
-        ++blk; pos = 0;
-      }
-      more = blk < ws.nblk;
-      __syncthreads();
-      const int n = list_n;
-      // ---- accumulate: warp == row y, lanes == channels ----
-      if (y <= y1 && cl < C) {
-        for (int q = 0; q < n; ++q) {
-          const int id = list[q];
-          const RegionHdr h = ws.hdr[id];
-          if (y < h.ymin || y > h.ymax) continue;
-          const TapEntry re = ws.rowtab[(size_t)id * kWinCap + (y - h.ymin)];
-          if ((re.p0n >> 16) == 0) continue;
-          const T* __restrict__ dsrc = dout + (size_t)(h.src / p.R) * PHW * RC +
-                                       (size_t)(h.src % p.R) * C + cl;
-          const float* __restrict__ rext = ws.rowext + (size_t)id * kExtCap;
-          const float* __restrict__ cext = ws.colext + (size_t)id * kExtCap;
-          const TapEntry* __restrict__ ctab = ws.coltab + (size_t)id * kWinCap - h.xmin;
+        int incl = mine;
 #pragma unroll
-          for (int x = 0; x < kTile; ++x) {
-            const int xx = x0 + x;
-            if (xx < h.xmin || xx > h.xmax) continue;
-            const TapEntry ce = ctab[xx];
-            if ((ce.p0n >> 16) == 0) continue;
-            pull_px<T, NV>(dsrc, RC, p.PW, re, rext, ce, cext, acc[x]);
-          }
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += v;
         }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        int base = list_n, tot = 0;
+        for (int w = 0; w < kThreads / 32; ++w) {
+          if (w < warp) base += warp_tot[w];
+          tot += warp_tot[w];
+        }
+        if (list_n + tot > kListCap) { full = true; __syncthreads(); break; }
+        if (mine) {
+          ListEntry e;
+          e.src = h.src;
+          e.ymin = (short)h.ymin; e.ymax = (short)h.ymax; e.xmin = (short)h.xmin; e.xmax = (short)h.xmax;
+          int o = base + incl - mine;
+          for (int rb = 0; rb < nbr; ++rb)
+            for (int cb = 0; cb < nbc; ++cb) {
+              e.id = ids[q] | (rb << 24) | (cb << 28);
+              list[o++] = e;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) list_n += tot;
+        __syncthreads();
+        pos += kThreads;
       }
+      if (full) break;
+      ++blk; pos = 0;
     }
-    // ---- every element of the tile written exactly once ----
-    if (y <= y1) {
-#pragma unroll
-      for (int x = 0; x < kTile; ++x) {
-        if (x0 + x > x1) continue;
-        float* __restrict__ o = dimg + ((size_t)y * W + x0 + x) * C + cl;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          if (cl + v * 32 * V >= C) continue;
-#pragma unroll
-          for (int u = 0; u < V; u += 4)
-            *reinterpret_cast<float4*>(o + v * 32 * V + u) =
-                make_float4(acc[x][v][u], acc[x][v][u + 1], acc[x][v][u + 2], acc[x][v][u + 3]);
+    more = blk < ws.nblk;
+    __syncthreads();
+    const int n = list_n;
+
+    for (int c0 = 0; c0 < n; c0 += kChunkR) {
+      const int nc = min(kChunkR, n - c0);
+      // ---- expand: thread == (tile row, region, tile column) ----
+      for (int s = tid; s < kTileH * nc * TW; s += kThreads) {
+        const int row = s / (nc * TW);
+        const int rem = s - row * (nc * TW);
+        const int q = rem / TW, x = rem - q * TW;
+        const ListEntry e = list[c0 + q];
+        const int yy = y0 + row, xx = x0 + x;
+        int4 o = make_int4(-1, 0, 0, 0);
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (yy >= e.ymin && yy <= e.ymax && xx >= e.xmin && xx <= e.xmax) {
+          const int id = e.id & 0xffffff, rb = (e.id >> 24) & 15, cb = (e.id >> 28) & 15;
+          const TapEntry re = ws.rowtab[(size_t)id * kTabLen + tab_index(rb, yy - e.ymin)];
+          const TapEntry ce = ws.coltab[(size_t)id * kTabLen + tab_index(cb, xx - e.xmin)];
+          if (re.n > 0 && ce.n > 0) {
+            const int k = e.src / p.R, r = e.src - k * p.R;
+            const int o00 = (k * PHW + re.p0 * PW + ce.p0) * RC + r * C;
+            const int dr = re.n > 1 ? PW * RC : 0, dc = ce.n > 1 ? RC : 0;
+            o = make_int4(o00, o00 + dc, o00 + dr, o00 + dr + dc);
+            w = make_float4(re.w0 * ce.w0, re.w0 * ce.w1, re.w1 * ce.w0, re.w1 * ce.w1);
+          }
         }
+        d_off[row * kSlots + q * TW + x] = o;
+        d_w[row * kSlots + q * TW + x] = w;
+      }
+      __syncthreads();
+      // ---- stream: warp == row y, lanes == channels ----
+      if (y <= y1 && cl < C) {
+        const int4* __restrict__ po = d_off + warp * kSlots;
+        const float4* __restrict__ pw = d_w + warp * kSlots;
+        for (int q = 0; q < nc; ++q) {
+#pragma unroll
+          for (int x = 0; x < TW; ++x) {
+            const int4 o = po[q * TW + x];
+            if (o.x < 0) continue;
+            const float4 w = pw[q * TW + x];
+            float f0[NV][V], f1[NV][V], f2[NV][V], f3[NV][V];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              ldg_vec<T>(dbase + o.x + v * 32 * V, f0[v]);
+              ldg_vec<T>(dbase + o.y + v * 32 * V, f1[v]);
+              ldg_vec<T>(dbase + o.z + v * 32 * V, f2[v]);
+              ldg_vec<T>(dbase + o.w + v * 32 * V, f3[v]);
+            }
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+#pragma unroll
+              for (int u = 0; u < V; ++u)
+                acc[x][v][u] = fmaf(w.w, f3[v][u], fmaf(w.z, f2[v][u], fmaf(w.y, f1[v][u],
+                                    fmaf(w.x, f0[v][u], acc[x][v][u]))));
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- every element of the tile written exactly once ----
+  if (y <= y1) {
+#pragma unroll
+    for (int x = 0; x < TW; ++x) {
+      if (x0 + x > x1) continue;
+      float* __restrict__ o = dimg + ((size_t)y * W + x0 + x) * C + cl;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if (cl + v * 32 * V >= C) continue;
+#pragma unroll
+        for (int u = 0; u < V; u += 4)
+          *reinterpret_cast<float4*>(o + v * 32 * V + u) =
+              make_float4(acc[x][v][u], acc[x][v][u + 1], acc[x][v][u + 2], acc[x][v][u + 3]);
       }
     }
   }
@@ -592,27 +627,44 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
   roi_prep_kernel<<<ws.nblk + N, kPrepBlock, 0, stream>>>(p, ws);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  TileMap tm;
-  int total = 0;
-  for (int l = 0; l < p.L; ++l) {
-    tm.start[l] = total;
-    tm.tiles_x[l] = (p.W[l] + kTile - 1) / kTile;
-    tm.tiles_y[l] = (p.H[l] + kTile - 1) / kTile;
-    total += tm.tiles_x[l] * tm.tiles_y[l] * p.B;
-  }
-  for (int l = p.L; l <= kMaxLevels; ++l) tm.start[l] = total;
-  for (int l = p.L; l < kMaxLevels; ++l) tm.tiles_x[l] = tm.tiles_y[l] = 1;
-  if (total == 0) return cudaSuccess;
+  // Two launches: the small upper-level maps carry ~40x more region-pixels per
+  // tile than level 0, so they get narrow tiles + a channel split and go first
+  // (heaviest level first inside each launch); the big maps follow with wide tiles.
   const int V = dtype == 0 ? 4 : 8;
-  const bool two = p.C > 32 * V;
-  if (dtype == 0) {
-    if (two) roi_bwd_pull<float, 2><<<total, kThreads, 0, stream>>>(p, ws, tm);
-    else roi_bwd_pull<float, 1><<<total, kThreads, 0, stream>>>(p, ws, tm);
-  } else {
-    if (two) roi_bwd_pull<__nv_bfloat16, 2><<<total, kThreads, 0, stream>>>(p, ws, tm);
-    else roi_bwd_pull<__nv_bfloat16, 1><<<total, kThreads, 0, stream>>>(p, ws, tm);
+  auto heavy = [&](int l) { return (long long)p.H[l] * p.W[l] <= 64 * 96; };
+  for (int pass = 0; pass < 2; ++pass) {
+    const int tw = pass == 0 ? 4 : 8;
+    const int nv = pass == 0 ? 1 : ((p.C > 32 * V) ? 2 : 1);
+    TileMap tm;
+    int total = 0, ns = 0;
+    tm.groups = (p.C + 32 * V * nv - 1) / (32 * V * nv);
+    for (int l = p.L - 1; l >= 0; --l) {
+      if (heavy(l) != (pass == 0)) continue;
+      tm.start[ns] = total;
+      tm.level[ns] = l;
+      tm.tiles_x[ns] = (p.W[l] + tw - 1) / tw;
+      tm.tiles_y[ns] = (p.H[l] + kTileH - 1) / kTileH;
+      total += tm.tiles_x[ns] * tm.tiles_y[ns] * p.B * tm.groups;
+      ++ns;
+    }
+    tm.nslots = ns;
+    for (int j2 = ns; j2 <= kMaxLevels; ++j2) tm.start[j2] = total;
+    for (int j2 = ns; j2 < kMaxLevels; ++j2) { tm.level[j2] = 0; tm.tiles_x[j2] = tm.tiles_y[j2] = 1; }
+    if (total == 0) continue;
+    if (pass == 0) {
+      if (dtype == 0) roi_bwd_pull<float, 1, 4><<<total, kThreads, 0, stream>>>(p, ws, tm);
+      else roi_bwd_pull<__nv_bfloat16, 1, 4><<<total, kThreads, 0, stream>>>(p, ws, tm);
+    } else if (nv == 2) {
+      if (dtype == 0) roi_bwd_pull<float, 2, 8><<<total, kThreads, 0, stream>>>(p, ws, tm);
+      else roi_bwd_pull<__nv_bfloat16, 2, 8><<<total, kThreads, 0, stream>>>(p, ws, tm);
+    } else {
+      if (dtype == 0) roi_bwd_pull<float, 1, 8><<<total, kThreads, 0, stream>>>(p, ws, tm);
+      else roi_bwd_pull<__nv_bfloat16, 1, 8><<<total, kThreads, 0, stream>>>(p, ws, tm);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
   }
-  return cudaGetLastError();
+  return cudaSuccess;
 }
 
 // Device pointer to the per-region headers inside a laid-out workspace (the
