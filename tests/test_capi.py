@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     from arfe_b200 import _lib, build
     build.build()
     names = _declared()
-    assert len(names) >= 13
+    assert len(names) >= 15
     handle = ctypes.CDLL(_lib.LIB_PATH)
     for n in names:
         assert hasattr(handle, n), f"{n} declared in include/arfe_b200.h but not exported"
@@ -36,21 +36,27 @@ def test_argument_errors_need_no_gpu():
     H, W, s = L.int_array([8]), L.int_array([8]), L.float_array([0.25])
     # regions must be 1 or 3
     rc = lib.arfe_roi_fuse_forward(None, H, W, s, 1, 1, 4, None, 0, 2, 1.0, 7, 7, 0, 56.0,
-                                   0, 0, None, None, None, None)
+                                   0, 0, 0, None, None, None, None)
     assert rc == -3 and b"regions" in lib.arfe_last_error()
     # pooled size out of range
     rc = lib.arfe_roi_fuse_forward(None, H, W, s, 1, 1, 4, None, 0, 3, 1.0, 64, 7, 0, 56.0,
-                                   0, 0, None, None, None, None)
+                                   0, 0, 0, None, None, None, None)
     assert rc == -2
     # K = 0 is a no-op success (reference returns early, roi_align_kernel_v2.cu:293-296)
     rc = lib.arfe_roi_fuse_forward(None, H, W, s, 1, 1, 4, None, 0, 3, 1.0, 7, 7, 0, 56.0,
-                                   0, 0, None, None, None, None)
+                                   0, 0, 0, None, None, None, None)
     assert rc == 0
     # NULL features with K > 0
     rois = torch.zeros(1, 5)
     rc = lib.arfe_roi_fuse_forward(None, H, W, s, 1, 1, 4, rois.data_ptr(), 1, 3, 1.0, 7, 7,
-                                   0, 56.0, 0, 0, None, None, None, None)
+                                   0, 56.0, 0, 0, 0, None, None, None, None)
     assert rc == -1
+    # channels-last output needs channels-last features
+    rc = lib.arfe_roi_fuse_forward(None, H, W, s, 1, 1, 4, rois.data_ptr(), 1, 3, 1.0, 7, 7,
+                                   0, 56.0, 0, 0, 1, None, None, None, None)
+    assert rc in (-1, -5)
+    assert lib.arfe_roi_fuse_pull_workspace_bytes(1024, 3, 5) > 0
+    assert lib.arfe_roi_fuse_pull_workspace_bytes(0, 3, 5) == 0
     # aligned=False is the legacy path
     rc = lib.arfe_roi_align_forward(None, None, 0.25, 7, 7, 0, 0, 1, 4, 8, 8, 0, 0, 0, None, None)
     assert rc == -5
