@@ -34,10 +34,10 @@ cudaError_t launch_roi_fuse_backward(const RoiFuseParams& p, int dtype, int layo
                                      cudaStream_t stream);
 cudaError_t launch_roi_fuse_forward_cl(const RoiFuseParams& p, int dtype, int out_cl,
                                        cudaStream_t stream);
-size_t roi_pull_workspace_bytes(int K, int R, int L);
+size_t roi_pull_workspace_bytes(int K, int R, int L, int B, const int* H);
 cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, void* workspace,
                                           size_t workspace_bytes, cudaStream_t stream);
-const void* roi_pull_headers(int K, int R, int L, void* workspace);
+const void* roi_pull_headers(int K, int R, int L, int B, const int* H, void* workspace);
 cudaError_t launch_roi_fuse_taps(const RoiFuseParams& p, int max_grid, int32_t* lvl,
                                  int32_t* grid, float* boxes, int32_t* ylo,
                                  int32_t* yhi, float* ywl, float* ywh, int32_t* xlo,

@@ -220,8 +220,8 @@ roi_fuse_fwd_cl(const RoiFuseParams p, int opitch, int bins_per_pass) {
 //   hdr     : N * 32                         RegionHdr
 //   rowtab  : N * kTabLen * 16               TapEntry per (bin block, window row)
 //   coltab  : N * kTabLen * 16               TapEntry per (bin block, window column)
-//   seg_ids : nblk * L * kPrepBlock * 4      region ids per (prep block, level), index order
-//   seg_cnt : nblk * L * 4
+//   seg_ids : nblk * NK * kPrepBlock * 4     region ids per (prep block, key), index order;
+//   seg_cnt : nblk * NK * 4                  key = (level, image, 8-row band of the level)
 constexpr int kWinCap = 64;     // window rows / columns described per region (bin block 0)
 constexpr int kWinCapX = 16;    // ... for bin blocks 1..3 (only sub-pixel bins need them: tiny windows)
 constexpr int kMaxBlk = 4;      // a row may be sampled by up to 2 * kMaxBlk bins
@@ -245,19 +245,30 @@ struct PullWs {
   int* seg_ids;
   int* seg_cnt;
   int nblk;
+  int nkeys;                  // sum over levels of B * bands(level)
+  int key_base[kMaxLevels];   // first key of level l
+  int nbands[kMaxLevels];     // ceil(H_l / 8)
 };
+
+constexpr int kBandH = 8;     // rows per band == rows per pull tile
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-inline size_t pull_ws_layout(int N, int L, unsigned char* base, PullWs* ws) {
+inline size_t pull_ws_layout(int N, int L, int B, const int* H, unsigned char* base, PullWs* ws) {
   const int nblk = (N + kPrepBlock - 1) / kPrepBlock;
+  int nkeys = 0, key_base[kMaxLevels], nbands[kMaxLevels];
+  for (int l = 0; l < kMaxLevels; ++l) {
+    key_base[l] = nkeys;
+    nbands[l] = l < L ? (H[l] + kBandH - 1) / kBandH : 0;
+    nkeys += nbands[l] * B;
+  }
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   const size_t o_hdr = take((size_t)N * sizeof(RegionHdr));
   const size_t o_row = take((size_t)N * kTabLen * sizeof(TapEntry));
   const size_t o_col = take((size_t)N * kTabLen * sizeof(TapEntry));
-  const size_t o_ids = take((size_t)nblk * L * kPrepBlock * 4);
-  const size_t o_cnt = take((size_t)nblk * L * 4);
+  const size_t o_ids = take((size_t)nblk * nkeys * kPrepBlock * 4);
+  const size_t o_cnt = take((size_t)nblk * nkeys * 4);
   if (ws) {
     ws->hdr = reinterpret_cast<RegionHdr*>(base + o_hdr);
     ws->rowtab = reinterpret_cast<TapEntry*>(base + o_row);
@@ -265,6 +276,8 @@ inline size_t pull_ws_layout(int N, int L, unsigned char* base, PullWs* ws) {
     ws->seg_ids = reinterpret_cast<int*>(base + o_ids);
     ws->seg_cnt = reinterpret_cast<int*>(base + o_cnt);
     ws->nblk = nblk;
+    ws->nkeys = nkeys;
+    for (int l = 0; l < kMaxLevels; ++l) { ws->key_base[l] = key_base[l]; ws->nbands[l] = nbands[l]; }
   }
   return off;
 }
@@ -319,35 +332,44 @@ roi_prep_kernel(const RoiFuseParams p, const PullWs ws) {
   const int N = p.K * p.R;
   const int tid = threadIdx.x;
   if ((int)blockIdx.x < ws.nblk) {
-    // ---- headers (window bounds are filled by the table blocks) + segments ----
-    __shared__ int warp_cnt[kPrepBlock / 32][kMaxLevels];
-    const int i = blockIdx.x * kPrepBlock + tid;  // region id = r * K + k? no: k * R + r
-    int lvl = -1;
+    // ---- per-(level, image, band) ordered id segments of kPrepBlock regions ----
+    // Each region marks the keys of the 8-row bands its window can touch in a
+    // per-key bitmask (order-independent), its slot is the popcount below it:
+    // lists come out in region-index order without a sort.
+    extern __shared__ unsigned mask[];  // [nkeys][kPrepBlock / 32]
+    constexpr int kW = kPrepBlock / 32;
+    for (int e = tid; e < ws.nkeys * kW; e += kPrepBlock) mask[e] = 0u;
+    __syncthreads();
+    const int i = blockIdx.x * kPrepBlock + tid;  // region id = k * R + r
+    int k0 = 0, k1 = -1;                           // key range of this region
     if (i < N) {
       const int k = i / p.R, r = i - k * p.R;
       RegionBox bx = region_box(p.rois + 5 * (size_t)k, r, p.facs);
-      lvl = (p.L == 1) ? 0 : map_roi_level(bx, p.L, p.finest_scale);
+      const int lvl = (p.L == 1) ? 0 : map_roi_level(bx, p.L, p.finest_scale);
       const int b = (int)bx.b;
-      if (lvl >= 0 && (b < 0 || b >= p.B)) lvl = -1;
-    }
-    const int lane = tid & 31, warp = tid >> 5;
-    for (int l = 0; l < p.L; ++l) {
-      const unsigned m = __ballot_sync(0xffffffffu, lvl == l);
-      if (lane == 0) warp_cnt[warp][l] = __popc(m);
-    }
-    __syncthreads();
-    for (int l = 0; l < p.L; ++l) {
-      const unsigned m = __ballot_sync(0xffffffffu, lvl == l);
-      if (lvl == l) {
-        int off = __popc(m & ((1u << lane) - 1u));
-        for (int w = 0; w < warp; ++w) off += warp_cnt[w][l];
-        ws.seg_ids[((size_t)blockIdx.x * p.L + l) * kPrepBlock + off] = i;
+      if (lvl >= 0 && b >= 0 && b < p.B) {
+        const RoiGeom g = roi_geometry(bx, p.scale[lvl], p.PH, p.PW, p.sampling_ratio);
+        // conservative row range of the sampling window (exact bounds are in hdr)
+        const float end_h = g.start_h + g.bin_h * (float)p.PH;
+        int r0 = (int)floorf(g.start_h) - 1, r1 = (int)ceilf(end_h) + 1;
+        r0 = max(r0, 0); r1 = min(r1, p.H[lvl] - 1);
+        if (r1 >= r0 && end_h == end_h) {
+          k0 = ws.key_base[lvl] + b * ws.nbands[lvl] + r0 / kBandH;
+          k1 = ws.key_base[lvl] + b * ws.nbands[lvl] + r1 / kBandH;
+        }
       }
     }
-    if (tid < p.L) {
+    for (int key = k0; key <= k1; ++key) atomicOr(&mask[key * kW + (tid >> 5)], 1u << (tid & 31));
+    __syncthreads();
+    for (int key = k0; key <= k1; ++key) {
+      int pos = __popc(mask[key * kW + (tid >> 5)] & ((1u << (tid & 31)) - 1u));
+      for (int w = 0; w < (tid >> 5); ++w) pos += __popc(mask[key * kW + w]);
+      ws.seg_ids[((size_t)blockIdx.x * ws.nkeys + key) * kPrepBlock + pos] = i;
+    }
+    for (int key = tid; key < ws.nkeys; key += kPrepBlock) {
       int c = 0;
-      for (int w = 0; w < kPrepBlock / 32; ++w) c += warp_cnt[w][tid];
-      ws.seg_cnt[blockIdx.x * p.L + tid] = c;
+      for (int w = 0; w < kW; ++w) c += __popc(mask[key * kW + w]);
+      ws.seg_cnt[(size_t)blockIdx.x * ws.nkeys + key] = c;
     }
     return;
   }
@@ -385,9 +407,10 @@ roi_prep_kernel(const RoiFuseParams p, const PullWs ws) {
 }
 
 // ----------------------------------------------------------- pull backward
-constexpr int kTileH = 8;       // tile rows, warp == tile row
-constexpr int kListCap = 768;   // regions listed per pass
+constexpr int kTileH = kBandH;  // tile rows, warp == tile row
+constexpr int kListCap = 512;   // list entries per pass
 constexpr int kChunkR = 16;     // regions whose taps are expanded per round
+constexpr int kMaxPrepBlocks = 511;   // K * regions <= 130 816 for the pull path
 
 struct TileMap {
   int start[kMaxLevels + 1];  // first CTA of each scheduled slot
@@ -424,6 +447,7 @@ roi_bwd_pull(const RoiFuseParams p, const PullWs ws, const TileMap tm) {
   __shared__ float4 d_w[kTileH * kSlots];
   __shared__ int list_n;
   __shared__ int warp_tot[kThreads / 32];
+  __shared__ int pre[kMaxPrepBlocks + 1];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int j = 0;
@@ -437,6 +461,7 @@ roi_bwd_pull(const RoiFuseParams p, const PullWs ws, const TileMap tm) {
   t -= b * per_img;
   const int tyi = t / tm.tiles_x[j], txi = t - tyi * tm.tiles_x[j];
   const int y0 = tyi * kTileH, x0 = txi * TW;
+  const int key = ws.key_base[l] + b * ws.nbands[l] + tyi;  // this tile's (level, image, band)
   const int H = p.H[l], W = p.W[l], C = p.C, RC = p.R * C, PHW = p.PH * p.PW, PW = p.PW;
   const int y = y0 + warp;  // this warp's row
   const int y1 = min(y0 + kTileH, H) - 1, x1 = min(x0 + TW, W) - 1;
@@ -452,62 +477,85 @@ roi_bwd_pull(const RoiFuseParams p, const PullWs ws, const TileMap tm) {
 #pragma unroll
       for (int u = 0; u < V; ++u) acc[x][v][u] = 0.f;
 
-  // regions of this level in index order, at most kListCap listed per pass
-  int blk = 0, pos = 0;  // cursor into the per-block segments (uniform)
+  // candidates = the ids of this tile's (level, image, band) key over all prep
+  // blocks, block-major == region-index order; pre[] = exclusive prefix of the
+  // per-block counts so that one 256-thread batch spans blocks
+  for (int i = tid; i <= ws.nblk; i += kThreads)
+    pre[i] = i < ws.nblk ? ws.seg_cnt[(size_t)i * ws.nkeys + key] : 0;
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of pre[0..nblk] by one warp
+    int carry = 0;
+    for (int i0 = 0; i0 <= ws.nblk; i0 += 32) {
+      const int i = i0 + lane;
+      const int v = i <= ws.nblk ? pre[i] : 0;
+      int incl = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t2 = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t2;
+      }
+      if (i <= ws.nblk) pre[i] = carry + incl - v;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+  __syncthreads();
+  const int total_cand = pre[ws.nblk];
+
+  int pos = 0;  // cursor into the flattened candidates (uniform)
   bool more = true;
   while (more) {
     __syncthreads();
     if (tid == 0) list_n = 0;
     __syncthreads();
     // ---- ordered compaction of the intersecting regions into list[] ----
-    while (blk < ws.nblk) {
-      const int cnt = ws.seg_cnt[blk * p.L + l];
-      const int* __restrict__ ids = ws.seg_ids + ((size_t)blk * p.L + l) * kPrepBlock;
-      bool full = false;
-      while (pos < cnt) {
-        const int q = pos + tid;
-        int mine = 0, nbr = 0, nbc = 0;  // list entries this thread contributes
-        RegionHdr h;
-        if (q < cnt) {
-          h = ws.hdr[ids[q]];
-          const bool hit = h.lvl == l && h.batch == b && (h.flags & 1) == 0 && h.ymax >= y0 &&
-                           h.ymin <= y1 && h.xmax >= x0 && h.xmin <= x1;
-          if (hit) { nbr = (h.flags >> 8) & 15; nbc = (h.flags >> 12) & 15; mine = nbr * nbc; }
+    bool full = false;
+    while (pos < total_cand && !full) {
+      const int q = pos + tid;
+      int mine = 0, nbr = 0, nbc = 0, id = 0;  // list entries this thread contributes
+      RegionHdr h;
+      if (q < total_cand) {
+        int lo = 0, hi = ws.nblk - 1;  // last block with pre[blk] <= q
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (pre[mid] <= q) lo = mid; else hi = mid - 1;
         }
-        int incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl += v;
-        }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        int base = list_n, tot = 0;
-        for (int w = 0; w < kThreads / 32; ++w) {
-          if (w < warp) base += warp_tot[w];
-          tot += warp_tot[w];
-        }
-        if (list_n + tot > kListCap) { full = true; __syncthreads(); break; }
-        if (mine) {
-          ListEntry e;
-          e.src = h.src;
-          e.ymin = (short)h.ymin; e.ymax = (short)h.ymax; e.xmin = (short)h.xmin; e.xmax = (short)h.xmax;
-          int o = base + incl - mine;
-          for (int rb = 0; rb < nbr; ++rb)
-            for (int cb = 0; cb < nbc; ++cb) {
-              e.id = ids[q] | (rb << 24) | (cb << 28);
-              list[o++] = e;
-            }
-        }
-        __syncthreads();
-        if (tid == 0) list_n += tot;
-        __syncthreads();
-        pos += kThreads;
+        id = ws.seg_ids[((size_t)lo * ws.nkeys + key) * kPrepBlock + (q - pre[lo])];
+        h = ws.hdr[id];
+        const bool hit = h.lvl == l && h.batch == b && (h.flags & 1) == 0 && h.ymax >= y0 &&
+                         h.ymin <= y1 && h.xmax >= x0 && h.xmin <= x1;
+        if (hit) { nbr = (h.flags >> 8) & 15; nbc = (h.flags >> 12) & 15; mine = nbr * nbc; }
       }
-      if (full) break;
-      ++blk; pos = 0;
+      int incl = mine;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      if (lane == 31) warp_tot[warp] = incl;
+      __syncthreads();
+      int base = list_n, tot = 0;
+      for (int w = 0; w < kThreads / 32; ++w) {
+        if (w < warp) base += warp_tot[w];
+        tot += warp_tot[w];
+      }
+      if (list_n + tot > kListCap) { full = true; __syncthreads(); break; }
+      if (mine) {
+        ListEntry e;
+        e.src = h.src;
+        e.ymin = (short)h.ymin; e.ymax = (short)h.ymax; e.xmin = (short)h.xmin; e.xmax = (short)h.xmax;
+        int o = base + incl - mine;
+        for (int rb = 0; rb < nbr; ++rb)
+          for (int cb = 0; cb < nbc; ++cb) {
+            e.id = id | (rb << 24) | (cb << 28);
+            list[o++] = e;
+          }
+      }
+      __syncthreads();
+      if (tid == 0) list_n += tot;
+      __syncthreads();
+      pos += kThreads;
     }
-    more = blk < ws.nblk;
+    more = pos < total_cand;
     __syncthreads();
     const int n = list_n;
 
@@ -611,8 +659,8 @@ cudaError_t launch_roi_fuse_forward_cl(const RoiFuseParams& p, int dtype, int ou
   return cudaGetLastError();
 }
 
-size_t roi_pull_workspace_bytes(int K, int R, int L) {
-  return pull_ws_layout(K * R, L, nullptr, nullptr);
+size_t roi_pull_workspace_bytes(int K, int R, int L, int B, const int* H) {
+  return pull_ws_layout(K * R, L, B, H, nullptr, nullptr);
 }
 
 // dout: channels-last [K][PH*PW][R*C]; dfeats: NHWC fp32, fully written.
@@ -622,10 +670,14 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
                                           size_t workspace_bytes, cudaStream_t stream) {
   const int N = p.K * p.R;
   PullWs ws;
-  const size_t need = pull_ws_layout(N, p.L, static_cast<unsigned char*>(workspace), &ws);
+  const size_t need = pull_ws_layout(N, p.L, p.B, p.H, static_cast<unsigned char*>(workspace), &ws);
   if (need > workspace_bytes) return cudaErrorInvalidValue;
-  roi_prep_kernel<<<ws.nblk + N, kPrepBlock, 0, stream>>>(p, ws);
-  cudaError_t e = cudaGetLastError();
+  const int prep_smem = ws.nkeys * (kPrepBlock / 32) * 4;
+  if (prep_smem > 160 * 1024 || ws.nblk > kMaxPrepBlocks) return cudaErrorInvalidValue;
+  cudaError_t e = set_smem(roi_prep_kernel, prep_smem);
+  if (e != cudaSuccess) return e;
+  roi_prep_kernel<<<ws.nblk + N, kPrepBlock, prep_smem, stream>>>(p, ws);
+  e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   // Two launches: the small upper-level maps carry ~40x more region-pixels per
   // tile than level 0, so they get narrow tiles + a channel split and go first
@@ -669,9 +721,9 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
 
 // Device pointer to the per-region headers inside a laid-out workspace (the
 // atomic fallback kernel reads the `flags` field).
-const void* roi_pull_headers(int K, int R, int L, void* workspace) {
+const void* roi_pull_headers(int K, int R, int L, int B, const int* H, void* workspace) {
   PullWs ws;
-  pull_ws_layout(K * R, L, static_cast<unsigned char*>(workspace), &ws);
+  pull_ws_layout(K * R, L, B, H, static_cast<unsigned char*>(workspace), &ws);
   return ws.hdr;
 }
 
