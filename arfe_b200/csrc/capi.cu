@@ -133,10 +133,6 @@ int arfe_roi_fuse_backward(const void* dout, int dout_layout, const int32_t* H, 
   }
   REQUIRE(dout_layout == ARFE_NCHW || dout_layout == ARFE_NHWC, ARFE_E_ENUM, "%s: unknown dout_layout %d", fn, dout_layout);
   p.dout = dout; p.dout_cl = dout_layout == ARFE_NHWC;
-  {
-    const char* ev = getenv("ARFE_BWD_VEC");  // tuning knob, default scalar
-    p.bwd_vec = ev ? atoi(ev) : 0;
-  }
   return cuda_result(arfe::launch_roi_fuse_backward(p, dtype, layout, (cudaStream_t)stream), fn);
 }
 

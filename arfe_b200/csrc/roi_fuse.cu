@@ -334,28 +334,6 @@ __device__ __forceinline__ void bwd_px_scalar(const float* __restrict__ dsm, int
   }
 }
 
-template <int PHW_T>
-__device__ __forceinline__ void bwd_px_vec4(const float* __restrict__ dsm, int PHW, int cc,
-                                            float w00, float w01, float w10, float w11,
-                                            int i00, int i01, int i10, int i11,
-                                            float* __restrict__ dst, size_t cstride, int lane) {
-  const int phw = PHW_T ? PHW_T : PHW;
-  const float* __restrict__ d0 = dsm + i00;
-  const float* __restrict__ d1 = dsm + i01;
-  const float* __restrict__ d2 = dsm + i10;
-  const float* __restrict__ d3 = dsm + i11;
-  const bool lead = (lane & 3) == 0;
-#pragma unroll 4
-  for (int c = 0; c < cc; ++c) {
-    const float v = w00 * d0[c * phw] + w01 * d1[c * phw] + w10 * d2[c * phw] + w11 * d3[c * phw];
-    const float v1 = __shfl_down_sync(0xffffffffu, v, 1);
-    const float v2 = __shfl_down_sync(0xffffffffu, v, 2);
-    const float v3 = __shfl_down_sync(0xffffffffu, v, 3);
-    if (lead) red_add_v4(dst, v, v1, v2, v3);
-    dst += cstride;
-  }
-}
-
 // ---------------------------------------------------------------------------
 // Backward.  Thread == one pixel of the RoI's feature window; it looks up the
 // (usually <= 2 x 2) bins that sample it once, keeps their weights in
@@ -422,17 +400,10 @@ roi_fuse_bwd(const RoiFuseParams p, int cb /* channels staged per pass */) {
     return;
   }
 
-  // Window columns are widened to a multiple of VEC so that VEC consecutive
-  // lanes own one aligned pixel group and their sums leave in ONE vector
-  // reduction (red.global.add.v4.f32 / .v2.f32): global float atomics are the
-  // bottleneck of this kernel and this cuts them 4x.  NHWC vectorises over
-  // channels instead.
-  int vec = 1;
-  if (!kNHWC) {
-    if (p.bwd_vec && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(dimg) & 15) == 0) vec = 4;
-  }
-  const int xa = hd.xmin & ~(vec - 1);
-  const int ww = (hd.xmax | (vec - 1)) - xa + 1, wh = hd.ymax - hd.ymin + 1;
+  // (128-bit vector reductions over x were measured: no gain -- the L2 atomic
+  // units retire ~1 fp32 element per slice-clock whatever the request width.)
+  const int xa = hd.xmin;
+  const int ww = hd.xmax - hd.xmin + 1, wh = hd.ymax - hd.ymin + 1;
   const int npx = ww * wh;
   const float inv_ww = 1.0f / (float)ww;
   const float inv_count = 1.0f / g.count;
@@ -453,6 +424,7 @@ roi_fuse_bwd(const RoiFuseParams p, int cb /* channels staged per pass */) {
     }
     __syncthreads();
 
+    int complex_px = 0;  // this thread saw a pixel sampled by more than 2 x 2 bins
     for (int px0 = tid - lane; px0 < npx; px0 += kThreads) {  // warp-uniform bound
       const int px = px0 + lane;
       int wr = 0, wc = 0;
@@ -485,71 +457,76 @@ roi_fuse_bwd(const RoiFuseParams p, int cb /* channels staged per pass */) {
         const int j = col - tx.first[q];
         return (tx.cnt[q] > 0 && j >= 0 && j < tx.cnt[q]) ? tx.w[tx.off[q] + j] : 0.f;
       };
-      const bool simple = __all_sync(0xffffffffu, na <= 2 && nb <= 2);
-
-      if (simple) {
-        float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
-        int i00 = 0, i01 = 0, i10 = 0, i11 = 0;
-        if (live) {
-          const int pa1 = min(pa + 1, PH - 1), pb1 = min(pb + 1, PW - 1);
-          const float wa0 = wy_of(pa) * inv_count;
-          const float wa1 = (na > 1) ? wy_of(pa + 1) * inv_count : 0.f;
-          const float wb0 = wx_of(pb);
-          const float wb1 = (nb > 1) ? wx_of(pb + 1) : 0.f;
-          w00 = wa0 * wb0; w01 = wa0 * wb1; w10 = wa1 * wb0; w11 = wa1 * wb1;
-          i00 = pa * PW + pb; i01 = pa * PW + pb1; i10 = pa1 * PW + pb; i11 = pa1 * PW + pb1;
-        }
+      if (live && (na > 2 || nb > 2)) complex_px = 1;
+      if (live && na <= 2 && nb <= 2) {
+        const int pa1 = min(pa + 1, PH - 1), pb1 = min(pb + 1, PW - 1);
+        const float wa0 = wy_of(pa) * inv_count;
+        const float wa1 = (na > 1) ? wy_of(pa + 1) * inv_count : 0.f;
+        const float wb0 = wx_of(pb);
+        const float wb1 = (nb > 1) ? wx_of(pb + 1) : 0.f;
+        const float w00 = wa0 * wb0, w01 = wa0 * wb1, w10 = wa1 * wb0, w11 = wa1 * wb1;
+        const int i00 = pa * PW + pb, i01 = pa * PW + pb1, i10 = pa1 * PW + pb, i11 = pa1 * PW + pb1;
         if (kNHWC) {
-          if (live) {
-            int c = 0;
-            if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-              for (; c + 3 < cc; c += 4) {
-                float v[4];
+          int c = 0;
+          if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            for (; c + 3 < cc; c += 4) {
+              float v[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const float* __restrict__ d = dsm + (c + u) * PHW;
-                  v[u] = w00 * d[i00] + w01 * d[i01] + w10 * d[i10] + w11 * d[i11];
-                }
-                red_add_v4(dst + c, v[0], v[1], v[2], v[3]);
+              for (int u = 0; u < 4; ++u) {
+                const float* __restrict__ d = dsm + (c + u) * PHW;
+                v[u] = w00 * d[i00] + w01 * d[i01] + w10 * d[i10] + w11 * d[i11];
               }
-            }
-            for (; c < cc; ++c) {
-              const float* __restrict__ d = dsm + c * PHW;
-              atomicAdd(dst + c, w00 * d[i00] + w01 * d[i01] + w10 * d[i10] + w11 * d[i11]);
+              red_add_v4(dst + c, v[0], v[1], v[2], v[3]);
             }
           }
-        } else if (vec == 4) {
-          // whole warp walks the channels together (shuffles); lanes outside
-          // every bin carry zero weights, a quad of four such lanes is skipped
-          const unsigned livemask = __ballot_sync(0xffffffffu, live);
-          if (livemask) {
-            const bool quad_live = ((livemask >> (lane & ~3)) & 0xfu) != 0;
-            const int lead_lane = quad_live ? lane : 1;  // (1 & 3) != 0: never issues
-            if (PHW == 49)
-              bwd_px_vec4<49>(dsm, PHW, cc, w00, w01, w10, w11, i00, i01, i10, i11, dst, HW, lead_lane);
-            else
-              bwd_px_vec4<0>(dsm, PHW, cc, w00, w01, w10, w11, i00, i01, i10, i11, dst, HW, lead_lane);
+          for (; c < cc; ++c) {
+            const float* __restrict__ d = dsm + c * PHW;
+            atomicAdd(dst + c, w00 * d[i00] + w01 * d[i01] + w10 * d[i10] + w11 * d[i11]);
           }
-        } else if (live) {
-          if (PHW == 49)
-            bwd_px_scalar<49>(dsm, PHW, cc, w00, w01, w10, w11, i00, i01, i10, i11, dst, HW);
-          else
-            bwd_px_scalar<0>(dsm, PHW, cc, w00, w01, w10, w11, i00, i01, i10, i11, dst, HW);
-        }
-      } else if (live) {
-        const size_t cstride = kNHWC ? 1 : HW;
-        for (int c = 0; c < cc; ++c) {
-          const float* __restrict__ d = dsm + c * PHW;
-          float v = 0.f;
-          for (int a = 0; a < na; ++a) {
-            const float wa = wy_of(pa + a);
-            float t = 0.f;
-            for (int b = 0; b < nb; ++b) t = fmaf(wx_of(pb + b), d[(pa + a) * PW + pb + b], t);
-            v = fmaf(wa, t, v);
-          }
-          atomicAdd(dst + (size_t)c * cstride, v * inv_count);
+        } else if (PHW == 49) {
+          bwd_px_scalar<49>(dsm, PHW, cc, w00, w01, w10, w11, i00, i01, i10, i11, dst, HW);
+        } else {
+          bwd_px_scalar<0>(dsm, PHW, cc, w00, w01, w10, w11, i00, i01, i10, i11, dst, HW);
         }
       }
+      // rows / columns sampled by more than two bins are finished below
+    }
+    // ---- generic pass: pixels sampled by more than 2 x 2 bins, one (pixel,
+    // channel) pair per thread so that tiny windows still use the whole CTA ----
+    if (!__syncthreads_or(complex_px)) continue;
+    for (int item = tid; item < npx * cc; item += kThreads) {
+      const int c = item / npx, px = item - c * npx;
+      int wr, wc;
+      split_px(px, ww, inv_ww, wr, wc);
+      const int row = hd.ymin + wr, col = xa + wc;
+      int pa = -1, na = 0, pb = -1, nb = 0;
+      for (int q = 0; q < PH; ++q)
+        if (ty.cnt[q] > 0 && row >= ty.first[q] && row < ty.first[q] + ty.cnt[q]) {
+          if (pa < 0) pa = q;
+          na = q - pa + 1;
+        }
+      for (int q = 0; q < PW; ++q)
+        if (tx.cnt[q] > 0 && col >= tx.first[q] && col < tx.first[q] + tx.cnt[q]) {
+          if (pb < 0) pb = q;
+          nb = q - pb + 1;
+        }
+      if (na == 0 || nb == 0 || (na <= 2 && nb <= 2)) continue;
+      const float* __restrict__ d = dsm + c * PHW;
+      float v = 0.f;
+      for (int a = 0; a < na; ++a) {
+        const int ja = row - ty.first[pa + a];
+        const float wa = (ty.cnt[pa + a] > 0 && ja >= 0 && ja < ty.cnt[pa + a]) ? ty.w[ty.off[pa + a] + ja] : 0.f;
+        float t = 0.f;
+        for (int b = 0; b < nb; ++b) {
+          const int jb = col - tx.first[pb + b];
+          const float wb = (tx.cnt[pb + b] > 0 && jb >= 0 && jb < tx.cnt[pb + b]) ? tx.w[tx.off[pb + b] + jb] : 0.f;
+          t = fmaf(wb, d[(pa + a) * PW + pb + b], t);
+        }
+        v = fmaf(wa, t, v);
+      }
+      float* __restrict__ dst = kNHWC ? dimg + ((size_t)row * W + col) * C + c0 + c
+                                      : dimg + (size_t)(c0 + c) * HW + (size_t)row * W + col;
+      atomicAdd(dst, v * inv_count);
     }
   }
 }

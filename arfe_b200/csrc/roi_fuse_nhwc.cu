@@ -222,15 +222,12 @@ roi_fuse_fwd_cl(const RoiFuseParams p, int opitch, int bins_per_pass) {
 //   coltab  : N * kTabLen * 16               TapEntry per (bin block, window column)
 //   seg_ids : nblk * NK * kPrepBlock * 4     region ids per (prep block, key), index order;
 //   seg_cnt : nblk * NK * 4                  key = (level, image, 8-row band of the level)
-constexpr int kWinCap = 64;     // window rows / columns described per region (bin block 0)
-constexpr int kWinCapX = 16;    // ... for bin blocks 1..3 (only sub-pixel bins need them: tiny windows)
-constexpr int kMaxBlk = 4;      // a row may be sampled by up to 2 * kMaxBlk bins
-constexpr int kTabLen = kWinCap + (kMaxBlk - 1) * kWinCapX;  // TapEntries per region per axis
+constexpr int kTabLen = 256;    // TapEntries per region per axis: (bin blocks) x (window length) <= kTabLen
+constexpr int kMaxBlk = 15;     // a row may be sampled by up to 2 * kMaxBlk bins (4-bit field)
 constexpr int kPrepBlock = 256; // regions per header block
 
-__host__ __device__ inline int tab_index(int blk, int i) {
-  return blk == 0 ? i : kWinCap + (blk - 1) * kWinCapX + i;
-}
+// Entry of window row i for bin block blk; `len` = window length of the region.
+__host__ __device__ inline int tab_index(int blk, int i, int len) { return blk * len + i; }
 
 struct __align__(16) TapEntry {
   int p0;         // first bin sampling this row / column
@@ -284,16 +281,16 @@ inline size_t pull_ws_layout(int N, int L, int B, const int* H, unsigned char* b
 
 // Transpose one axis table: for every window row (column) the bins sampling
 // it, two per block (block k holds bins p0+2k, p0+2k+1).  One warp; lane =
-// window row.  Returns the number of blocks used (1..kMaxBlk), or 0 when the
-// window / bin count does not fit: such regions take the atomic fallback kernel.
+// window row.  Returns the number of blocks used (>= 1), or 0 when
+// blocks x window length exceeds kTabLen: such regions take the atomic
+// fallback kernel.
 __device__ int transpose_axis(const AxisTable& t, int P, int lo, int hi, float scale,
                               TapEntry* __restrict__ tab, int lane) {
   const int n = hi - lo + 1;
-  if (n > kWinCap) return 0;
+  if (n > kTabLen) return 0;
+  // pass 1: the largest number of bins sampling one row
   int maxcnt = 0;
-  for (int i0 = 0; i0 < n; i0 += 32) {
-    const int i = i0 + lane;
-    if (i >= n) continue;
+  for (int i = lane; i < n; i += 32) {
     const int row = lo + i;
     int p0 = -1, cnt = 0;
     for (int q = 0; q < P; ++q)
@@ -302,27 +299,36 @@ __device__ int transpose_axis(const AxisTable& t, int P, int lo, int hi, float s
         cnt = q - p0 + 1;
       }
     maxcnt = max(maxcnt, cnt);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, d));
+  int nblk = (maxcnt + 1) / 2;
+  if (nblk < 1) nblk = 1;
+  if (nblk > kMaxBlk || nblk * n > kTabLen) return 0;
+  // pass 2: the entries
+  for (int i = lane; i < n; i += 32) {
+    const int row = lo + i;
+    int p0 = -1, cnt = 0;
+    for (int q = 0; q < P; ++q)
+      if (t.cnt[q] > 0 && row >= t.first[q] && row < t.first[q] + t.cnt[q]) {
+        if (p0 < 0) p0 = q;
+        cnt = q - p0 + 1;
+      }
     auto w_of = [&](int q) -> float {
       const int j = row - t.first[q];
       return (q < P && t.cnt[q] > 0 && j >= 0 && j < t.cnt[q]) ? t.w[t.off[q] + j] * scale : 0.f;
     };
-    for (int blk = 0; blk < kMaxBlk; ++blk) {
-      if (blk > 0 && i >= kWinCapX) break;
+    for (int blk = 0; blk < nblk; ++blk) {
       const int rem = cnt - 2 * blk;
       TapEntry e;
       e.p0 = (p0 < 0 ? 0 : p0) + 2 * blk;
       e.n = rem <= 0 ? 0 : (rem > 2 ? 2 : rem);
       e.w0 = e.n > 0 ? w_of(e.p0) : 0.f;
       e.w1 = e.n > 1 ? w_of(e.p0 + 1) : 0.f;
-      tab[tab_index(blk, i)] = e;
+      tab[tab_index(blk, i, n)] = e;
     }
   }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, d));
-  const int nblk = (maxcnt + 1) / 2;
-  if (nblk > kMaxBlk) return 0;
-  if (nblk > 1 && n > kWinCapX) return 0;
-  return nblk < 1 ? 1 : nblk;
+  return nblk;
 }
 
 // Blocks [0, nblk): headers of kPrepBlock regions each + per-level ordered id
@@ -572,8 +578,8 @@ roi_bwd_pull(const RoiFuseParams p, const PullWs ws, const TileMap tm) {
         float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
         if (yy >= e.ymin && yy <= e.ymax && xx >= e.xmin && xx <= e.xmax) {
           const int id = e.id & 0xffffff, rb = (e.id >> 24) & 15, cb = (e.id >> 28) & 15;
-          const TapEntry re = ws.rowtab[(size_t)id * kTabLen + tab_index(rb, yy - e.ymin)];
-          const TapEntry ce = ws.coltab[(size_t)id * kTabLen + tab_index(cb, xx - e.xmin)];
+          const TapEntry re = ws.rowtab[(size_t)id * kTabLen + tab_index(rb, yy - e.ymin, e.ymax - e.ymin + 1)];
+          const TapEntry ce = ws.coltab[(size_t)id * kTabLen + tab_index(cb, xx - e.xmin, e.xmax - e.xmin + 1)];
           if (re.n > 0 && ce.n > 0) {
             const int k = e.src / p.R, r = e.src - k * p.R;
             const int o00 = (k * PHW + re.p0 * PW + ce.p0) * RC + r * C;

@@ -51,10 +51,11 @@ def synthetic_rois(K, img_w=1344, img_h=800, batch=1, seed=0, smin=16.0, smax=60
 
 
 def host_inputs(batch=2, rois_per_img=512, channels=256, img_h=800, img_w=1344,
-                dtype=torch.float32, seed=0, pin=False, channels_last=False):
+                dtype=torch.float32, seed=0, pin=False, channels_last=False, strides=STRIDES,
+                out_size=7):
     """Synthetic inputs of one step on the HOST (optionally pinned; optionally
     stored in torch.channels_last memory format -- same logical tensors)."""
-    shapes = pyramid_shapes(img_h, img_w)
+    shapes = pyramid_shapes(img_h, img_w, strides)
     g = torch.Generator().manual_seed(seed)
     K = batch * rois_per_img
     hr, wr = shapes[2]
@@ -64,9 +65,10 @@ def host_inputs(batch=2, rois_per_img=512, channels=256, img_h=800, img_w=1344,
     t["g1"] = [torch.randn(batch, 1, h, w, generator=g).to(dtype) for h, w in shapes]
     t["g2"] = [torch.randn(batch, 1, h, w, generator=g).to(dtype) for h, w in shapes]
     t["rois"] = synthetic_rois(K, img_w, img_h, batch, seed)
-    t["a"] = torch.randn(K, channels, 7, 7, generator=g).relu().to(dtype)
-    t["b"] = torch.randn(K, channels, 7, 7, generator=g).relu().to(dtype)
-    t["gz"] = torch.randn(K, channels, 7, 7, generator=g).to(dtype)      # dL/d(gate out)
+    P = out_size
+    t["a"] = torch.randn(K, channels, P, P, generator=g).relu().to(dtype)
+    t["b"] = torch.randn(K, channels, P, P, generator=g).relu().to(dtype)
+    t["gz"] = torch.randn(K, channels, P, P, generator=g).to(dtype)      # dL/d(gate out)
     t["gbsf"] = torch.randn(batch, channels, hr, wr, generator=g).to(dtype)  # dL/d(gathered)
     if channels_last:
         def cl(v):
@@ -79,6 +81,8 @@ def host_inputs(batch=2, rois_per_img=512, channels=256, img_h=800, img_w=1344,
             return [p(e) for e in v] if isinstance(v, list) else v.pin_memory()
         t = {k: p(v) for k, v in t.items()}
     t["shapes"] = shapes
+    t["strides"] = tuple(strides)
+    t["out_size"] = out_size
     return t
 
 
@@ -104,6 +108,9 @@ class TrainStep:
         self.nlev = len(x)
         self.K = host["rois"].shape[0]
         self.R = regions
+        self.P = host.get("out_size", 7)
+        self.PP = self.P * self.P
+        self.strides = host.get("strides", STRIDES)
 
         def d(v):
             if isinstance(v, list):
@@ -122,11 +129,12 @@ class TrainStep:
         self.gathered = e(B, C, hr, wr)
         self.argmax = torch.empty((2, B, C, hr, wr), dtype=torch.uint8, device=device)
         self.y = [e(B, C, h, w) for h, w in self.shapes]
-        self.F = e(K, R * C, 7, 7)
-        self.z = e(K, C, 7, 7)
-        self.dF = e(K, R * C, 7, 7)            # [d_ori | d_lw | d_lh]
-        self.d_ori = e(K, C, 7, 7)
-        self.d_ab = e(K, C, 7, 7)
+        P = self.P
+        self.F = e(K, R * C, P, P)
+        self.z = e(K, C, P, P)
+        self.dF = e(K, R * C, P, P)            # [d_ori | d_lw | d_lh]
+        self.d_ori = e(K, C, P, P)
+        self.d_ab = e(K, C, P, P)
         self.dy = [e(B, C, h, w, dtype=torch.float32) for h, w in self.shapes]
         self.dy_in = self.dy if self.dtype == torch.float32 else [e(B, C, h, w) for h, w in self.shapes]
         self.dbsf = e(B, C, hr, wr, dtype=torch.float32)
@@ -140,7 +148,7 @@ class TrainStep:
         # C arrays built once
         self.H = L.int_array([s[0] for s in self.shapes])
         self.W = L.int_array([s[1] for s in self.shapes])
-        self.scales = L.float_array([1.0 / s for s in STRIDES[:self.nlev]])
+        self.scales = L.float_array([1.0 / s for s in self.strides[:self.nlev]])
         self.p_x, self.p_y = L.ptr_array(self.x), L.ptr_array(self.y)
         self.p_g1, self.p_g2 = L.ptr_array(self.g1), L.ptr_array(self.g2)
         self.p_dy, self.p_dy_in = L.ptr_array(self.dy), L.ptr_array(self.dy_in)
@@ -148,9 +156,9 @@ class TrainStep:
         self.p_dx = L.ptr_array(self.dx)
         # the gate sees [rows][n] with `ori` strided inside the concatenated tensor
         if self.cl:   # memory [K*49][R*C]: a row is one bin of one RoI
-            self.gate_rows, self.gate_n, self.gate_stride = K * 49, C, R * C
+            self.gate_rows, self.gate_n, self.gate_stride = K * self.PP, C, R * C
         else:         # memory [K][R*C*49]: a row is one RoI
-            self.gate_rows, self.gate_n, self.gate_stride = K, C * 49, R * C * 49
+            self.gate_rows, self.gate_n, self.gate_stride = K, C * self.PP, R * C * self.PP
         self.stream = L.stream_ptr(device)
 
     # -- the eight ops; each returns the C return code ----------------------
@@ -168,7 +176,7 @@ class TrainStep:
     def roi_fuse_fwd(self):
         return self.lib.arfe_roi_fuse_forward(
             self.p_y, self.H, self.W, self.scales, self.nlev, self.B, self.C,
-            self.rois.data_ptr(), self.K, self.R, 1.0, 7, 7, 0, 56.0, self.dt, self.layout,
+            self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt, self.layout,
             self.layout, self.F.data_ptr(), None, None, self.stream)
 
     def rff_gate_fwd(self):
@@ -186,11 +194,11 @@ class TrainStep:
         if self.cl:
             return self.lib.arfe_roi_fuse_backward_pull(
                 self.dF.data_ptr(), self.H, self.W, self.scales, self.nlev, self.B, self.C,
-                self.rois.data_ptr(), self.K, self.R, 1.0, 7, 7, 0, 56.0, self.dt,
+                self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt,
                 self.p_dy, self.ws_ptr, self.ws_bytes, self.stream)
         return self.lib.arfe_roi_fuse_backward(
             self.dF.data_ptr(), L.ARFE_NCHW, self.H, self.W, self.scales, self.nlev, self.B,
-            self.C, self.rois.data_ptr(), self.K, self.R, 1.0, 7, 7, 0, 56.0, self.dt,
+            self.C, self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt,
             self.layout, self.p_dy, self.stream)
 
     def fpn_apply_bwd(self):
@@ -212,8 +220,8 @@ class TrainStep:
         at::zeros, roi_align_kernel_v2.cu:325-326; the pull kernel needs none)."""
         C = self.C
         self.dF[:, :C].copy_(self.d_ori)
-        self.dF[:, C:2 * C].copy_(self.d_ab)
-        self.dF[:, 2 * C:].copy_(self.d_ab)
+        for r in range(1, self.R):
+            self.dF[:, r * C:(r + 1) * C].copy_(self.d_ab)
         if not self.cl:
             for t in self.dy:
                 t.zero_()
@@ -251,8 +259,8 @@ class TrainStep:
         hr, wr = self.shapes[2]
         pyr = B * C * P * e
         ref = B * C * hr * wr
-        out_roi = K * R * C * 49 * e
-        n_gate = K * C * 49 * e
+        out_roi = K * R * C * self.PP * e
+        n_gate = K * C * self.PP * e
         return {
             "fpn_gather_fwd": pyr + ref * e + 2 * ref,                       # + uint8 argmax (2 levels)
             "fpn_apply_fwd": 2 * pyr + ref * e + 2 * B * P * e,

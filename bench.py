@@ -131,6 +131,7 @@ def run_reference(args, rank, world):
     its Python modules call), all host threads torch will use."""
     if rank != 0:
         return
+    torch.set_num_threads(os.cpu_count() or 1)  # torchrun pins OMP_NUM_THREADS=1; use every host core
     from oracle import arfe_oracle as O
     from oracle import build_oracle
     build_oracle.build_c_oracle()
@@ -174,6 +175,7 @@ def cpu_baseline_leg():
         build_oracle.build_c_oracle()
     except Exception as ex:  # pragma: no cover
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
+    torch.set_num_threads(os.cpu_count() or 1)
     backend, kind = "c", "port"
     rpi = 128
     host = cpu_sample_inputs(rpi)
