@@ -243,3 +243,60 @@ def test_pull_backward_is_deterministic_and_handles_tiny_rois(oracle, cuda):
     # level must be bit-identical between runs
     same = [torch.equal(grads[0][l], grads[1][l]) for l in range(5)]
     assert sum(same) >= 3, same
+
+
+def test_full_size_properties(cuda):
+    """BASELINE configs[1] sizes (2 x 800x1344, C=256, K=1024, 3 regions): the
+    oracle is too slow here, so check size-independent properties --
+    adjoint identity <fwd(x), g> == <x, bwd(g)> (forward and backward are
+    transposes of the same linear map), linearity, and agreement of the NCHW
+    compatibility kernels with the channels-last fast path."""
+    import arfe_b200 as A
+    from arfe_b200 import workload as wl
+    host = wl.host_inputs(2, 512, 256, seed=5)
+    rois = host["rois"].to(cuda)
+    scales = [1.0 / s for s in STRIDES]
+    x_nchw = [t.to(cuda).requires_grad_(True) for t in host["x"]]
+    x_cl = [_cl(t.to(cuda)).requires_grad_(True) for t in host["x"]]
+    g = torch.randn(1024, 768, 7, 7, device=cuda, generator=torch.Generator(device=cuda).manual_seed(1))
+    f_nchw = A.roi_fuse(x_nchw, rois, 7, scales, regions=3)
+    f_cl = A.roi_fuse(x_cl, rois, 7, scales, regions=3, out_channels_last=True)
+    assert_close_fp32(f_cl, f_nchw.detach().cpu(), "CL vs NCHW forward")
+    f_nchw.backward(g)
+    f_cl.backward(_cl(g))
+    lhs = float((f_cl.detach().double() * g.double()).sum())
+    rhs_cl = sum(float((x.detach().double() * x.grad.double()).sum()) for x in x_cl)
+    rhs_nchw = sum(float((x.detach().double() * x.grad.double()).sum()) for x in x_nchw)
+    scale = float(f_cl.detach().abs().double().mul(g.abs().double()).sum())
+    assert abs(lhs - rhs_cl) <= 1e-6 * scale, (lhs, rhs_cl, scale)
+    assert abs(lhs - rhs_nchw) <= 1e-6 * scale, (lhs, rhs_nchw, scale)
+    for a, b in zip(x_cl, x_nchw):
+        d = (a.grad - b.grad).abs().max()
+        assert float(d) <= 2e-5 * float(b.grad.abs().max()) + 1e-6
+    # linearity in the features: fwd(2x + y) == 2 fwd(x) + fwd(y)
+    y = [torch.randn_like(t) for t in x_cl]
+    with torch.no_grad():
+        lin = A.roi_fuse([_cl(2 * a + b) for a, b in zip(x_cl, y)], rois, 7, scales, regions=3)
+        ref = 2 * A.roi_fuse([t.detach() for t in x_cl], rois, 7, scales, regions=3) + \
+            A.roi_fuse(y, rois, 7, scales, regions=3)
+    assert float((lin - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+
+
+def test_large_k_multi_pass_lists(oracle, cuda):
+    """K = 6000 RoIs on a small map: every tile lists far more than kListCap
+    regions, so the pull kernel runs several list passes."""
+    import arfe_b200 as A
+    feats = small_pyramid(oracle, batch=1, channels=8, img_h=128, img_w=192)
+    rois = oracle.synthetic_rois(6000, 192, 128, 1, seed=23, smin=8.0, smax=120.0)
+    fo = [f.clone().requires_grad_(True) for f in feats]
+    ref = oracle.arrff_bbox_feats(fo, rois, list(STRIDES))
+    g = torch.randn(ref.shape, generator=torch.Generator().manual_seed(6))
+    ref.backward(g)
+    fg = [_cl(f.to(cuda)).requires_grad_(True) for f in feats]
+    got = A.roi_fuse(fg, rois.to(cuda), 7, _scales(), regions=3, out_channels_last=True)
+    assert_close_fp32(got, ref, "K=6000 forward")
+    got.backward(_cl(g.to(cuda)))
+    for l in range(5):
+        r = fo[l].grad if fo[l].grad is not None else torch.zeros_like(feats[l])
+        d = (fg[l].grad.cpu() - r).abs().max()
+        assert float(d) <= 3e-5 * float(r.abs().max()) + 1e-5, (l, float(d), float(r.abs().max()))
