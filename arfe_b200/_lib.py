@@ -44,8 +44,8 @@ _SIGNATURES = {
                             c_int, c_float, c_int] + [c_void_p] * 11 + [c_void_p], c_int),
     "arfe_rff_gate_forward": ([c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_int,
                                c_void_p], c_int),
-    "arfe_rff_gate_backward": ([c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p,
-                                c_i64, c_i64, c_int, c_void_p], c_int),
+    "arfe_rff_gate_backward": ([c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64,
+                                c_void_p, c_i64, c_i64, c_int, c_void_p], c_int),
     "arfe_fpn_gather_forward": ([_pp, _ip, _ip, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                  c_void_p, c_void_p], c_int),
     "arfe_fpn_gather_backward": ([c_void_p, c_void_p, _ip, _ip, c_int, c_int, c_int, c_int, c_int,

@@ -244,8 +244,8 @@ int arfe_rff_gate_forward(const void* ori, int64_t ori_roi_stride, const void* a
 }
 
 int arfe_rff_gate_backward(const void* g, const void* ori, int64_t ori_roi_stride, const void* a,
-                           const void* b, void* d_ori, void* d_ab, int64_t K, int64_t n_per_roi,
-                           int dtype, void* stream) {
+                           const void* b, void* d_ori, int64_t d_ori_roi_stride, void* d_ab,
+                           int64_t K, int64_t n_per_roi, int dtype, void* stream) {
   const char* fn = "arfe_rff_gate_backward";
   REQUIRE(dtype == ARFE_F32 || dtype == ARFE_BF16, ARFE_E_ENUM, "%s: unknown dtype %d", fn, dtype);
   REQUIRE(K >= 0 && n_per_roi >= 1 && ori_roi_stride >= n_per_roi, ARFE_E_SHAPE,
@@ -253,7 +253,8 @@ int arfe_rff_gate_backward(const void* g, const void* ori, int64_t ori_roi_strid
   if (K == 0) return ARFE_OK;
   REQUIRE(g && ori && a && b && d_ori && d_ab, ARFE_E_NULL, "%s: NULL tensor", fn);
   REQUIRE(n_per_roi < (1ll << 31), ARFE_E_SHAPE, "%s: n_per_roi too large", fn);
-  return cuda_result(arfe::launch_rff_gate_backward(g, ori, ori_roi_stride, a, b, d_ori, d_ab, K,
+  REQUIRE(d_ori_roi_stride >= n_per_roi, ARFE_E_SHAPE, "%s: d_ori stride < n_per_roi", fn);
+  return cuda_result(arfe::launch_rff_gate_backward(g, ori, ori_roi_stride, a, b, d_ori, d_ori_roi_stride, d_ab, K,
                                                     n_per_roi, dtype, (cudaStream_t)stream), fn);
 }
 

@@ -50,8 +50,8 @@ cudaError_t launch_rff_gate_forward(const void* ori, int64_t ori_stride,
                                     cudaStream_t stream);
 cudaError_t launch_rff_gate_backward(const void* g, const void* ori,
                                      int64_t ori_stride, const void* a,
-                                     const void* b, void* d_ori, void* d_ab,
-                                     int64_t K, int64_t n, int dtype,
+                                     const void* b, void* d_ori, int64_t d_ori_stride,
+                                     void* d_ab, int64_t K, int64_t n, int dtype,
                                      cudaStream_t stream);
 
 struct FpnParams {

@@ -69,7 +69,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(kThreads)
 gate_bwd(const T* __restrict__ g, const T* __restrict__ ori, int64_t ori_stride,
          const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ d_ori,
-         T* __restrict__ d_ab, int64_t total, uint32_t nv, int64_t n) {
+         int64_t d_ori_stride, T* __restrict__ d_ab, int64_t total, uint32_t nv, int64_t n) {
   const int64_t step = (int64_t)gridDim.x * kThreads;
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += step) {
     const int64_t k = i / nv;
@@ -84,7 +84,7 @@ gate_bwd(const T* __restrict__ g, const T* __restrict__ ori, int64_t ori_stride,
       r0[q] = fg[q] * (1.0f + (fa[q] + fb[q]));
       r1[q] = fg[q] * fo[q];
     }
-    store_vec<T, V>(d_ori + k * n + j, r0);
+    store_vec<T, V>(d_ori + k * d_ori_stride + j, r0);
     store_vec<T, V>(d_ab + k * n + j, r1);
   }
 }
@@ -119,22 +119,22 @@ cudaError_t launch_rff_gate_forward(const void* ori, int64_t ori_stride, const v
 
 cudaError_t launch_rff_gate_backward(const void* g, const void* ori, int64_t ori_stride,
                                      const void* a, const void* b, void* d_ori,
-                                     void* d_ab, int64_t K, int64_t n, int dtype,
-                                     cudaStream_t stream) {
+                                     int64_t d_ori_stride, void* d_ab, int64_t K, int64_t n,
+                                     int dtype, cudaStream_t stream) {
   const int V = dtype == 0 ? 4 : 8;
-  const bool vec = (n % V == 0) && (ori_stride % V == 0) && aligned16(g) &&
-                   aligned16(ori) && aligned16(a) && aligned16(b) &&
+  const bool vec = (n % V == 0) && (ori_stride % V == 0) && (d_ori_stride % V == 0) &&
+                   aligned16(g) && aligned16(ori) && aligned16(a) && aligned16(b) &&
                    aligned16(d_ori) && aligned16(d_ab);
   if (dtype == 0) {
     auto pg = (const float*)g; auto o = (const float*)ori; auto pa = (const float*)a; auto pb = (const float*)b;
     auto d0 = (float*)d_ori; auto d1 = (float*)d_ab;
-    if (vec) gate_bwd<float, 4><<<grid_for(K * n / 4), kThreads, 0, stream>>>(pg, o, ori_stride, pa, pb, d0, d1, K * (n / 4), (uint32_t)(n / 4), n);
-    else gate_bwd<float, 1><<<grid_for(K * n), kThreads, 0, stream>>>(pg, o, ori_stride, pa, pb, d0, d1, K * n, (uint32_t)n, n);
+    if (vec) gate_bwd<float, 4><<<grid_for(K * n / 4), kThreads, 0, stream>>>(pg, o, ori_stride, pa, pb, d0, d_ori_stride, d1, K * (n / 4), (uint32_t)(n / 4), n);
+    else gate_bwd<float, 1><<<grid_for(K * n), kThreads, 0, stream>>>(pg, o, ori_stride, pa, pb, d0, d_ori_stride, d1, K * n, (uint32_t)n, n);
   } else {
     auto pg = (const __nv_bfloat16*)g; auto o = (const __nv_bfloat16*)ori; auto pa = (const __nv_bfloat16*)a; auto pb = (const __nv_bfloat16*)b;
     auto d0 = (__nv_bfloat16*)d_ori; auto d1 = (__nv_bfloat16*)d_ab;
-    if (vec) gate_bwd<__nv_bfloat16, 8><<<grid_for(K * n / 8), kThreads, 0, stream>>>(pg, o, ori_stride, pa, pb, d0, d1, K * (n / 8), (uint32_t)(n / 8), n);
-    else gate_bwd<__nv_bfloat16, 1><<<grid_for(K * n), kThreads, 0, stream>>>(pg, o, ori_stride, pa, pb, d0, d1, K * n, (uint32_t)n, n);
+    if (vec) gate_bwd<__nv_bfloat16, 8><<<grid_for(K * n / 8), kThreads, 0, stream>>>(pg, o, ori_stride, pa, pb, d0, d_ori_stride, d1, K * (n / 8), (uint32_t)(n / 8), n);
+    else gate_bwd<__nv_bfloat16, 1><<<grid_for(K * n), kThreads, 0, stream>>>(pg, o, ori_stride, pa, pb, d0, d_ori_stride, d1, K * n, (uint32_t)n, n);
   }
   return cudaGetLastError();
 }

@@ -117,7 +117,7 @@ __device__ __forceinline__ void cl_bin_any(const T* __restrict__ base, size_t ro
 
 // dynamic smem: [CtaHeader][AxisTable y][AxisTable x][outs: bins_per_pass * opitch] (NCHW out only)
 template <typename T, bool kOutCL>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 roi_fuse_fwd_cl(const RoiFuseParams p, int opitch, int bins_per_pass) {
   constexpr int V = VecOf<T>::n;
   extern __shared__ __align__(16) unsigned char smem[];

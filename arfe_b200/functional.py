@@ -279,7 +279,7 @@ class _RFFGateFunction(Function):
         if K > 0:
             rc = L.lib().arfe_rff_gate_backward(
                 g.data_ptr(), ori.data_ptr(), stride, a.data_ptr(), b.data_ptr(),
-                d_ori.data_ptr(), d_ab.data_ptr(), K, n, dt,
+                d_ori.data_ptr(), n, d_ab.data_ptr(), K, n, dt,
                 L.stream_ptr(g.device))
             L.check(rc, "arfe_rff_gate_backward")
         return d_ori, d_ab, d_ab

@@ -187,8 +187,8 @@ class TrainStep:
     def rff_gate_bwd(self):
         return self.lib.arfe_rff_gate_backward(
             self.gz.data_ptr(), self.F.data_ptr(), self.gate_stride, self.a.data_ptr(),
-            self.b.data_ptr(), self.d_ori.data_ptr(), self.d_ab.data_ptr(), self.gate_rows,
-            self.gate_n, self.dt, self.stream)
+            self.b.data_ptr(), self.dF.data_ptr(), self.gate_stride, self.d_ab.data_ptr(),
+            self.gate_rows, self.gate_n, self.dt, self.stream)
 
     def roi_fuse_bwd(self):
         if self.cl:
@@ -218,8 +218,7 @@ class TrainStep:
         conv backward of the two context branches, which stays on PyTorch) and,
         on the NCHW path only, zero the accumulators (the reference's
         at::zeros, roi_align_kernel_v2.cu:325-326; the pull kernel needs none)."""
-        C = self.C
-        self.dF[:, :C].copy_(self.d_ori)
+        C = self.C  # d_ori was written in place into dF[:, :C] by the gate backward
         for r in range(1, self.R):
             self.dF[:, r * C:(r + 1) * C].copy_(self.d_ab)
         if not self.cl:

@@ -37,6 +37,16 @@ WORKLOAD = ("configs[1]: Faster R-CNN R50 + AR-FPN + AR-RFF training step "
             "strides 4-64, 3 regions, 7x7")
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture
+    (profiles/r1_traffic.json); None when no capture exists for it."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        return float(t[kernel]["bytes"])
+    except Exception:
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -278,7 +288,9 @@ def run_ours(args, rank, local_rank, world):
                     "note": "pinned-host pyramid+RoIs+conv stand-ins copied H2D every step, loss scalar read back"},
             "gpu_launches": step.launches_per_step() * args.steps,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src},
+                         "frac": achieved / peak, "traffic": measured_traffic(top) if cl else None,
+                         "algorithmic_bytes": alg[top], "peak_source": peak_src,
+                         "traffic_source": "ncu --set full capture, profiles/r1_traffic.json"},
             "kernels": kern,
         }
         if world == 1 and not args.no_cpu_baseline:

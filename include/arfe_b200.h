@@ -156,15 +156,16 @@ int arfe_roi_fuse_taps(const int32_t* H, const int32_t* W,
  * ori is read in place from the concatenated tensor: roi k starts at
  * ori + k*ori_roi_stride elements and holds n_per_roi (= C*PH*PW) elements.
  * a, b, out: dense [K, n_per_roi].
- * backward: d_ori = g*(1+a+b) (dense [K,n_per_roi]), da = db = g*ori (one
- * buffer, d_ab). */
+ * backward: d_ori = g*(1+a+b), rows d_ori_roi_stride elements apart (so it can
+ * be written in place into the gradient of the concatenated tensor: no cat of
+ * the ori block), da = db = g*ori (one dense buffer, d_ab). */
 int arfe_rff_gate_forward(const void* ori, int64_t ori_roi_stride, const void* a,
                           const void* b, void* out, int64_t K,
                           int64_t n_per_roi, int dtype, void* stream);
 int arfe_rff_gate_backward(const void* g, const void* ori,
                            int64_t ori_roi_stride, const void* a, const void* b,
-                           void* d_ori, void* d_ab, int64_t K,
-                           int64_t n_per_roi, int dtype, void* stream);
+                           void* d_ori, int64_t d_ori_roi_stride, void* d_ab,
+                           int64_t K, int64_t n_per_roi, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------
  * AR-FPN gather: every level resized to the refine level and averaged.
