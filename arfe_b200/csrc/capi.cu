@@ -40,7 +40,8 @@ int check_common(const char* fn, int L, int B, int C, const int32_t* H, const in
   REQUIRE(B >= 0 && C >= 1, ARFE_E_SHAPE, "%s: bad B=%d / C=%d", fn, B, C);
   REQUIRE(H && W, ARFE_E_NULL, "%s: H/W is NULL", fn);
   for (int l = 0; l < L; ++l)
-    REQUIRE(H[l] >= 1 && W[l] >= 1, ARFE_E_SHAPE, "%s: level %d has size %dx%d", fn, l, H[l], W[l]);
+    REQUIRE(H[l] >= 1 && W[l] >= 1 && H[l] < 32768 && W[l] < 32768, ARFE_E_SHAPE,
+            "%s: level %d has size %dx%d (supported: 1..32767)", fn, l, H[l], W[l]);
   REQUIRE(dtype == ARFE_F32 || dtype == ARFE_BF16, ARFE_E_ENUM, "%s: unknown dtype %d", fn, dtype);
   REQUIRE(layout == ARFE_NCHW || layout == ARFE_NHWC, ARFE_E_ENUM, "%s: unknown layout %d", fn, layout);
   return ARFE_OK;

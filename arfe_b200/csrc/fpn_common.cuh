@@ -45,11 +45,12 @@ __device__ __forceinline__ void decode(size_t i, int C, int H, int W, int& b, in
   }
 }
 
+// Map sizes are validated < 32768 at the C ABI, so the products fit 32 bits.
 __device__ __forceinline__ int pool_start(int i, int in, int out) {
-  return (int)(((long long)i * in) / out);
+  return (int)(((unsigned)i * (unsigned)in) / (unsigned)out);
 }
 __device__ __forceinline__ int pool_end(int i, int in, int out) {
-  return (int)(((long long)(i + 1) * in + out - 1) / out);
+  return (int)(((unsigned)(i + 1) * (unsigned)in + (unsigned)out - 1u) / (unsigned)out);
 }
 __device__ __forceinline__ int nearest_src(int d, int in, int out) {
   const float scale = __fdiv_rn((float)in, (float)out);

@@ -58,7 +58,7 @@ struct Exact { int s[kMaxLevels]; };  // pooling ratio of level l (< refine) if 
 // argmax layout here: [l][B][Hr][Wr][C] (follows the channels-last layout).
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-gather_fwd_cl(const FpnParams p) {
+gather_fwd_cl(const FpnParams p, const Exact ex) {
   constexpr int V = Vec<T>::n;
   const int Hr = p.Hr, Wr = p.Wr, C = p.C, CV = C / V;
   const size_t total = (size_t)p.B * Hr * Wr * CV;
@@ -78,20 +78,48 @@ gather_fwd_cl(const FpnParams p) {
     const int H = p.H[l], W = p.W[l];
     float v[V];
     if (l < p.refine_level) {
-      const int y0 = pool_start(Y, H, Hr), y1 = pool_end(Y, H, Hr);
-      const int x0 = pool_start(X, W, Wr), x1 = pool_end(X, W, Wr);
       int arg[V];
 #pragma unroll
       for (int u = 0; u < V; ++u) { v[u] = -CUDART_INF_F; arg[u] = 0; }
-      for (int y = y0; y < y1; ++y)
-        for (int x = x0; x < x1; ++x) {
-          float t[V];
-          ldv<T>(f + (((size_t)b * H + y) * W + x) * C + c, t);
-          const int pos = (y - y0) * (x1 - x0) + (x - x0);
+      const int s = ex.s[l];
+      if (s == 4 || s == 2) {
+        // exact ratio: static window, a whole window row of loads in flight
+        const T* __restrict__ w0 = f + (((size_t)b * H + (size_t)s * Y) * W + (size_t)s * X) * C + c;
+        if (s == 4) {
 #pragma unroll
-          for (int u = 0; u < V; ++u)
-            if (t[u] > v[u] || t[u] != t[u]) { v[u] = t[u]; arg[u] = pos; }
+          for (int dy = 0; dy < 4; ++dy) {
+            float t[4][V];
+#pragma unroll
+            for (int dx = 0; dx < 4; ++dx) ldv<T>(w0 + ((size_t)dy * W + dx) * C, t[dx]);
+#pragma unroll
+            for (int dx = 0; dx < 4; ++dx)
+#pragma unroll
+              for (int u = 0; u < V; ++u)
+                if (t[dx][u] > v[u] || t[dx][u] != t[dx][u]) { v[u] = t[dx][u]; arg[u] = dy * 4 + dx; }
+          }
+        } else {
+          float t[4][V];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ldv<T>(w0 + ((size_t)(k >> 1) * W + (k & 1)) * C, t[k]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int u = 0; u < V; ++u)
+              if (t[k][u] > v[u] || t[k][u] != t[k][u]) { v[u] = t[k][u]; arg[u] = k; }
         }
+      } else {
+        const int y0 = pool_start(Y, H, Hr), y1 = pool_end(Y, H, Hr);
+        const int x0 = pool_start(X, W, Wr), x1 = pool_end(X, W, Wr);
+        for (int y = y0; y < y1; ++y)
+          for (int x = x0; x < x1; ++x) {
+            float t[V];
+            ldv<T>(f + (((size_t)b * H + y) * W + x) * C + c, t);
+            const int pos = (y - y0) * (x1 - x0) + (x - x0);
+#pragma unroll
+            for (int u = 0; u < V; ++u)
+              if (t[u] > v[u] || t[u] != t[u]) { v[u] = t[u]; arg[u] = pos; }
+          }
+      }
       if (p.argmax) {
         uint8_t* a = p.argmax + ((((size_t)l * p.B + b) * Hr + Y) * Wr + X) * C + c;
 #pragma unroll
@@ -152,6 +180,53 @@ gather_bwd_cl(const FpnParams p, const Exact ex) {
       }
   }
   stv<T>(static_cast<T*>(p.outs[p.refine_level]) + i * V, g);
+}
+
+// Levels above the refine level (smaller maps, nearest-upsampled in the forward):
+// thread == (level pixel, vector): sum of d(gathered) over the refine pixels whose
+// nearest source it is.
+struct UpLevels { size_t start[kMaxLevels + 1]; int level[kMaxLevels]; int n; };
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+gather_bwd_up_cl(const FpnParams p, const UpLevels ul) {
+  constexpr int V = Vec<T>::n;
+  const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= ul.start[ul.n]) return;
+  int j = 0;
+  while (j + 1 < ul.n && i >= ul.start[j + 1]) ++j;
+  const int l = ul.level[j];
+  const int H = p.H[l], W = p.W[l], C = p.C, CV = C / V, Hr = p.Hr, Wr = p.Wr;
+  size_t r = i - ul.start[j];
+  const int cv = (int)(r % CV); r /= CV;
+  const int x = (int)(r % W); r /= W;
+  const int y = (int)(r % H);
+  const int b = (int)(r / H);
+  const int c = cv * V;
+  // refine rows Y with nearest_src(Y: H <- Hr) == y
+  const float sy = (float)Hr / (float)H, sx = (float)Wr / (float)W;
+  int Ya = (int)floorf((float)y * sy) - 1; if (Ya < 0) Ya = 0;
+  int Yb = (int)ceilf((float)(y + 1) * sy) + 1; if (Yb > Hr) Yb = Hr;
+  int Xa = (int)floorf((float)x * sx) - 1; if (Xa < 0) Xa = 0;
+  int Xb = (int)ceilf((float)(x + 1) * sx) + 1; if (Xb > Wr) Xb = Wr;
+  while (Ya < Yb && nearest_src(Ya, H, Hr) != y) ++Ya;
+  while (Yb > Ya && nearest_src(Yb - 1, H, Hr) != y) --Yb;
+  while (Xa < Xb && nearest_src(Xa, W, Wr) != x) ++Xa;
+  while (Xb > Xa && nearest_src(Xb - 1, W, Wr) != x) --Xb;
+  float g[V];
+#pragma unroll
+  for (int u = 0; u < V; ++u) g[u] = 0.f;
+  const T* __restrict__ d = static_cast<const T*>(p.gathered);
+  for (int Y = Ya; Y < Yb; ++Y)
+    for (int X = Xa; X < Xb; ++X) {
+      float t[V];
+      ldv<T>(d + (((size_t)b * Hr + Y) * Wr + X) * C + c, t);
+#pragma unroll
+      for (int u = 0; u < V; ++u) g[u] += t[u];
+    }
+#pragma unroll
+  for (int u = 0; u < V; ++u) g[u] = __fdiv_rn(g[u], (float)p.L);
+  stv<T>(static_cast<T*>(p.outs[l]) + (i - ul.start[j]) * V, g);
 }
 
 // ------------------------------------------------------------ apply fwd/bwd
@@ -245,6 +320,16 @@ apply_cl(const FpnParams p) {
   }
 }
 
+// Pooling ratio of each level below the refine level when it is an exact integer.
+inline Exact exact_ratios(const FpnParams& p) {
+  Exact ex;
+  for (int l = 0; l < kMaxLevels; ++l) ex.s[l] = 0;
+  for (int l = 0; l < p.refine_level; ++l)
+    if (p.H[l] % p.Hr == 0 && p.W[l] % p.Wr == 0 && p.H[l] / p.Hr == p.W[l] / p.Wr && p.H[l] / p.Hr <= 15)
+      ex.s[l] = p.H[l] / p.Hr;
+  return ex;
+}
+
 inline unsigned blocks_for(size_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
 inline bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -265,8 +350,9 @@ cudaError_t launch_fpn_gather_forward_cl(const FpnParams& p, int dtype, cudaStre
   const int V = dtype == 0 ? 4 : 8;
   const size_t total = (size_t)p.B * p.Hr * p.Wr * (p.C / V);
   if (total == 0) return cudaSuccess;
-  if (dtype == 0) gather_fwd_cl<float><<<blocks_for(total, kThreads), kThreads, 0, stream>>>(p);
-  else gather_fwd_cl<__nv_bfloat16><<<blocks_for(total, kThreads), kThreads, 0, stream>>>(p);
+  const Exact ex = exact_ratios(p);
+  if (dtype == 0) gather_fwd_cl<float><<<blocks_for(total, kThreads), kThreads, 0, stream>>>(p, ex);
+  else gather_fwd_cl<__nv_bfloat16><<<blocks_for(total, kThreads), kThreads, 0, stream>>>(p, ex);
   return cudaGetLastError();
 }
 
@@ -274,22 +360,36 @@ cudaError_t launch_fpn_gather_forward_cl(const FpnParams& p, int dtype, cudaStre
 cudaError_t launch_fpn_gather_backward_cl(const FpnParams& p, int dtype, unsigned* mask,
                                           cudaStream_t stream) {
   const int V = dtype == 0 ? 4 : 8;
-  Exact ex;
+  const Exact ex = exact_ratios(p);
   unsigned m = (1u << p.L) - 1u;
-  for (int l = 0; l < kMaxLevels; ++l) ex.s[l] = 0;
-  for (int l = 0; l < p.refine_level; ++l) {
-    if (p.H[l] % p.Hr == 0 && p.W[l] % p.Wr == 0 && p.H[l] / p.Hr == p.W[l] / p.Wr &&
-        p.H[l] / p.Hr <= 15) {
-      ex.s[l] = p.H[l] / p.Hr;
-      m &= ~(1u << l);
-    }
-  }
+  for (int l = 0; l < p.refine_level; ++l)
+    if (ex.s[l]) m &= ~(1u << l);
   m &= ~(1u << p.refine_level);
-  *mask = m;
   const size_t total = (size_t)p.B * p.Hr * p.Wr * (p.C / V);
-  if (total == 0) return cudaSuccess;
+  if (total == 0) { *mask = 0; return cudaSuccess; }
   if (dtype == 0) gather_bwd_cl<float><<<blocks_for(total, kThreads), kThreads, 0, stream>>>(p, ex);
   else gather_bwd_cl<__nv_bfloat16><<<blocks_for(total, kThreads), kThreads, 0, stream>>>(p, ex);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  // levels above the refine level: vector kernel
+  UpLevels ul;
+  size_t st = 0;
+  int n = 0;
+  for (int l = p.refine_level + 1; l < p.L; ++l) {
+    ul.start[n] = st;
+    ul.level[n] = l;
+    st += (size_t)p.B * p.H[l] * p.W[l] * (p.C / V);
+    m &= ~(1u << l);
+    ++n;
+  }
+  ul.n = n;
+  for (int j = n; j <= kMaxLevels; ++j) ul.start[j] = st;
+  for (int j = n; j < kMaxLevels; ++j) ul.level[j] = 0;
+  *mask = m;
+  if (st) {
+    if (dtype == 0) gather_bwd_up_cl<float><<<blocks_for(st, kThreads), kThreads, 0, stream>>>(p, ul);
+    else gather_bwd_up_cl<__nv_bfloat16><<<blocks_for(st, kThreads), kThreads, 0, stream>>>(p, ul);
+  }
   return cudaGetLastError();
 }
 
