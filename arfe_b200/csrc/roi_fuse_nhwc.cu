@@ -20,6 +20,8 @@
 //              atomics and no zero-fill.  (The NCHW/atomic kernel is bound by
 //              the L2 atomic units at ~1 fp32 element per slice-clock; see
 //              DESIGN.md section 6.)
+#include <stdlib.h>
+
 #include "roi_common.cuh"
 
 namespace arfe {
@@ -58,66 +60,118 @@ __device__ __forceinline__ void st_vec(T* __restrict__ p, const float (&f)[VecOf
   }
 }
 
+// Packed fp32 pairs (FFMA2 / FMUL2: two IEEE fp32 operations per instruction).
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// VEC consecutive channels as packed pairs.
+template <typename T>
+__device__ __forceinline__ void ldg_pairs(const T* __restrict__ p, uint64_t (&f)[VecOf<T>::n / 2]) {
+  if constexpr (sizeof(T) == 4) {
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p));
+    f[0] = v.x; f[1] = v.y;
+  } else {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(h[i]);
+      f[i] = pack2(t.x, t.y);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ forward
 // One bin, VEC channels per lane: rows x NC taps, NC loads in flight per row.
+// `rstep` = +1 walks the bin's rows top-down, -1 bottom-up (base / wy then
+// point at the last row).
 template <typename T, int NC>
-__device__ __forceinline__ void cl_bin(const T* __restrict__ base, size_t rowstride, int C,
-                                       const float* __restrict__ wy, int nr,
+__device__ __forceinline__ void cl_bin(const T* __restrict__ base, ptrdiff_t rowstride, int C,
+                                       const float* __restrict__ wy, int nr, int rstep,
                                        const float* __restrict__ wx,
-                                       float (&acc)[VecOf<T>::n]) {
-  constexpr int V = VecOf<T>::n;
-  float w[NC];
+                                       uint64_t (&acc)[VecOf<T>::n / 2]) {
+  constexpr int V2 = VecOf<T>::n / 2;
+  uint64_t w[NC];
 #pragma unroll
-  for (int j = 0; j < NC; ++j) w[j] = wx[j];
+  for (int j = 0; j < NC; ++j) w[j] = pack2(wx[j], wx[j]);
+#pragma unroll 2
   for (int jr = 0; jr < nr; ++jr) {
-    float v[NC][V];
+    uint64_t v[NC][V2];
 #pragma unroll
-    for (int j = 0; j < NC; ++j) ldg_vec<T>(base + (size_t)j * C, v[j]);
-    float t[V];
+    for (int j = 0; j < NC; ++j) ldg_pairs<T>(base + (size_t)j * C, v[j]);
+    uint64_t t[V2];
 #pragma unroll
-    for (int u = 0; u < V; ++u) t[u] = 0.f;
+    for (int u = 0; u < V2; ++u) t[u] = mul2(v[0][u], w[0]);
 #pragma unroll
-    for (int j = 0; j < NC; ++j)
+    for (int j = 1; j < NC; ++j)
 #pragma unroll
-      for (int u = 0; u < V; ++u) t[u] = fmaf(w[j], v[j][u], t[u]);
-    const float a = wy[jr];
+      for (int u = 0; u < V2; ++u) t[u] = fma2(v[j][u], w[j], t[u]);
+    const float a = *wy;
+    const uint64_t ap = pack2(a, a);
 #pragma unroll
-    for (int u = 0; u < V; ++u) acc[u] = fmaf(a, t[u], acc[u]);
+    for (int u = 0; u < V2; ++u) acc[u] = fma2(t[u], ap, acc[u]);
     base += rowstride;
+    wy += rstep;
   }
 }
 
 template <typename T>
-__device__ __forceinline__ void cl_bin_any(const T* __restrict__ base, size_t rowstride, int C,
-                                           const float* __restrict__ wy, int nr,
+__device__ __forceinline__ void cl_bin_any(const T* __restrict__ base, size_t rowstride_, int C,
+                                           const float* __restrict__ wy, int nr, bool up,
                                            const float* __restrict__ wx, int nc,
-                                           float (&acc)[VecOf<T>::n]) {
-  constexpr int V = VecOf<T>::n;
+                                           uint64_t (&acc)[VecOf<T>::n / 2]) {
+  constexpr int V2 = VecOf<T>::n / 2;
+  ptrdiff_t rowstride = (ptrdiff_t)rowstride_;
+  int rstep = 1;
+  if (up) {  // start at the last row and walk up
+    base += (size_t)(nr - 1) * rowstride_;
+    wy += nr - 1;
+    rowstride = -rowstride;
+    rstep = -1;
+  }
   switch (nc) {
-    case 1: cl_bin<T, 1>(base, rowstride, C, wy, nr, wx, acc); return;
-    case 2: cl_bin<T, 2>(base, rowstride, C, wy, nr, wx, acc); return;
-    case 3: cl_bin<T, 3>(base, rowstride, C, wy, nr, wx, acc); return;
-    case 4: cl_bin<T, 4>(base, rowstride, C, wy, nr, wx, acc); return;
-    case 5: cl_bin<T, 5>(base, rowstride, C, wy, nr, wx, acc); return;
-    case 6: cl_bin<T, 6>(base, rowstride, C, wy, nr, wx, acc); return;
+    case 1: cl_bin<T, 1>(base, rowstride, C, wy, nr, rstep, wx, acc); return;
+    case 2: cl_bin<T, 2>(base, rowstride, C, wy, nr, rstep, wx, acc); return;
+    case 3: cl_bin<T, 3>(base, rowstride, C, wy, nr, rstep, wx, acc); return;
+    case 4: cl_bin<T, 4>(base, rowstride, C, wy, nr, rstep, wx, acc); return;
+    case 5: cl_bin<T, 5>(base, rowstride, C, wy, nr, rstep, wx, acc); return;
+    case 6: cl_bin<T, 6>(base, rowstride, C, wy, nr, rstep, wx, acc); return;
     default: break;
   }
   for (int jr = 0; jr < nr; ++jr) {
-    const float a = wy[jr];
+    const float a = *wy;
     for (int j = 0; j < nc; ++j) {
-      float v[V];
-      ldg_vec<T>(base + (size_t)j * C, v);
+      uint64_t v[V2];
+      ldg_pairs<T>(base + (size_t)j * C, v);
       const float w = a * wx[j];
+      const uint64_t wp = pack2(w, w);
 #pragma unroll
-      for (int u = 0; u < V; ++u) acc[u] = fmaf(w, v[u], acc[u]);
+      for (int u = 0; u < V2; ++u) acc[u] = fma2(v[u], wp, acc[u]);
     }
     base += rowstride;
+    wy += rstep;
   }
 }
 
 // dynamic smem: [CtaHeader][AxisTable y][AxisTable x][outs: bins_per_pass * opitch] (NCHW out only)
-template <typename T, bool kOutCL>
-__global__ void __launch_bounds__(kThreads, 4)
+template <typename T, bool kOutCL, int kOcc>
+__global__ void __launch_bounds__(kThreads, kOcc)
 roi_fuse_fwd_cl(const RoiFuseParams p, int opitch, int bins_per_pass) {
   constexpr int V = VecOf<T>::n;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -177,6 +231,39 @@ roi_fuse_fwd_cl(const RoiFuseParams p, int opitch, int bins_per_pass) {
   const size_t rowstride = (size_t)W * C;
   const int cw = 32 * V;  // channels per warp pass
 
+  constexpr int V2 = V / 2;
+  const float2 icp = make_float2(inv_count, inv_count);
+  const uint64_t inv2 = pack2(icp.x, icp.y);
+  if constexpr (kOutCL) {
+    // warp == (bin row ph, channel chunk): the warps of neighbouring bin rows run
+    // side by side and walk their rows in opposite directions (even ph top-down,
+    // odd ph bottom-up), so the feature row two bin rows share is touched by
+    // both at about the same time and the second touch hits L1.
+    const int nchunk = (C + cw - 1) / cw;
+    for (int item = warp; item < PH * nchunk; item += kWarps) {
+      const int chunk = item / PH, ph = item - chunk * PH;
+      const int c = chunk * cw + lane * V;
+      if (c >= C) continue;
+      const int nr = ty.cnt[ph];
+      const float* __restrict__ wy = ty.w + ty.off[ph];
+      const bool up = (ph & 1) != 0;
+      const T* __restrict__ rowbase = fimg + (size_t)ty.first[ph] * rowstride + c;
+      T* __restrict__ o = out + out_index(ph * PW, c);
+      for (int pw = 0; pw < PW; ++pw) {
+        const int nc = tx.cnt[pw];
+        uint64_t acc[V2];
+#pragma unroll
+        for (int u = 0; u < V2; ++u) acc[u] = 0ull;
+        if (nr > 0 && nc > 0)
+          cl_bin_any<T>(rowbase + (size_t)tx.first[pw] * C, rowstride, C, wy, nr, up,
+                        tx.w + tx.off[pw], nc, acc);
+        float f[V];
+#pragma unroll
+        for (int u = 0; u < V2; ++u) unpack2(mul2(acc[u], inv2), f[2 * u], f[2 * u + 1]);
+        st_vec<T>(o + (size_t)pw * RC, f);
+      }
+    }
+  } else {
   for (int b0 = 0; b0 < PHW; b0 += bins_per_pass) {
     const int b1 = min(PHW, b0 + bins_per_pass);
     for (int bin = b0 + warp; bin < b1; bin += kWarps) {
@@ -187,42 +274,38 @@ roi_fuse_fwd_cl(const RoiFuseParams p, int opitch, int bins_per_pass) {
       const T* __restrict__ base0 = fimg + ((size_t)ty.first[ph] * W + tx.first[pw]) * C + lane * V;
       for (int c0 = 0; c0 < C; c0 += cw) {
         if (c0 + lane * V >= C) continue;
-        float acc[V];
+        uint64_t acc[V2];
 #pragma unroll
-        for (int u = 0; u < V; ++u) acc[u] = 0.f;
-        if (nr > 0 && nc > 0) cl_bin_any<T>(base0 + c0, rowstride, C, wy, nr, wx, nc, acc);
+        for (int u = 0; u < V2; ++u) acc[u] = 0ull;
+        if (nr > 0 && nc > 0) cl_bin_any<T>(base0 + c0, rowstride, C, wy, nr, false, wx, nc, acc);
+        float* o = outs + (size_t)(bin - b0) * opitch + c0 + lane * V;
 #pragma unroll
-        for (int u = 0; u < V; ++u) acc[u] *= inv_count;
-        if (kOutCL) {
-          st_vec<T>(out + out_index(bin, c0 + lane * V), acc);
-        } else {
-          float* o = outs + (size_t)(bin - b0) * opitch + c0 + lane * V;
-#pragma unroll
-          for (int u = 0; u < V; u += 4)
-            *reinterpret_cast<float4*>(o + u) = make_float4(acc[u], acc[u + 1], acc[u + 2], acc[u + 3]);
+        for (int u = 0; u < V2; u += 2) {
+          const ulonglong2 r2 = make_ulonglong2(mul2(acc[u], inv2), mul2(acc[u + 1], inv2));
+          *reinterpret_cast<ulonglong2*>(o + 2 * u) = r2;
         }
       }
     }
-    if (!kOutCL) {
-      __syncthreads();
-      // per channel a run of (b1 - b0) consecutive bins
-      const int run = b1 - b0;
-      for (int c = warp; c < C; c += kWarps)
-        for (int b = lane; b < run; b += 32)
-          out[out_index(b0 + b, c)] = from_f<T>(outs[(size_t)b * opitch + c]);
-      __syncthreads();
-    }
+    __syncthreads();
+    // per channel a run of (b1 - b0) consecutive bins
+    const int run = b1 - b0;
+    for (int c = warp; c < C; c += kWarps)
+      for (int b = lane; b < run; b += 32)
+        out[out_index(b0 + b, c)] = from_f<T>(outs[(size_t)b * opitch + c]);
+    __syncthreads();
+  }
   }
 }
 
 // ------------------------------------------------------------ region prep
 // Workspace layout (bytes, each array 256-byte aligned):
 //   hdr     : N * 32                         RegionHdr
-//   rowtab  : N * kTabLen * 16               TapEntry per (bin block, window row)
-//   coltab  : N * kTabLen * 16               TapEntry per (bin block, window column)
+//   rowtab  : N * kTabLen * 16               TapEntry per (bin block, window row)   (transposed table)
+//   colbin  : N * kMaxPool * 8               ColBin per output column pw            (forward table)
+//   colw    : N * kTabLen * 4                aggregated column weights, bin-major
 //   seg_ids : nblk * NK * kPrepBlock * 4     region ids per (prep block, key), index order;
 //   seg_cnt : nblk * NK * 4                  key = (level, image, 8-row band of the level)
-constexpr int kTabLen = 256;    // TapEntries per region per axis: (bin blocks) x (window length) <= kTabLen
+constexpr int kTabLen = 256;    // per region: (row bin blocks) x (window rows) <= kTabLen, column weights <= kTabLen
 constexpr int kMaxBlk = 15;     // a row may be sampled by up to 2 * kMaxBlk bins (4-bit field)
 constexpr int kPrepBlock = 256; // regions per header block
 
@@ -230,15 +313,22 @@ constexpr int kPrepBlock = 256; // regions per header block
 __host__ __device__ inline int tab_index(int blk, int i, int len) { return blk * len + i; }
 
 struct __align__(16) TapEntry {
-  int p0;         // first bin sampling this row / column
+  int p0;         // first bin sampling this row
   int n;          // number of bins sampling it: 0, 1 or 2
-  float w0, w1;   // their aggregated weights (row weights carry 1/count)
+  float w0, w1;   // their aggregated weights (carry 1/count)
+};
+
+struct __align__(8) ColBin {
+  int first;      // first feature column touched by output column pw
+  short cnt;      // number of consecutive columns touched (0: none)
+  short off;      // offset of its weights in colw
 };
 
 struct PullWs {
   RegionHdr* hdr;
   TapEntry* rowtab;
-  TapEntry* coltab;
+  ColBin* colbin;
+  float* colw;
   int* seg_ids;
   int* seg_cnt;
   int nblk;
@@ -263,13 +353,15 @@ inline size_t pull_ws_layout(int N, int L, int B, const int* H, unsigned char* b
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   const size_t o_hdr = take((size_t)N * sizeof(RegionHdr));
   const size_t o_row = take((size_t)N * kTabLen * sizeof(TapEntry));
-  const size_t o_col = take((size_t)N * kTabLen * sizeof(TapEntry));
+  const size_t o_cbin = take((size_t)N * kMaxPool * sizeof(ColBin));
+  const size_t o_colw = take((size_t)N * kTabLen * sizeof(float));
   const size_t o_ids = take((size_t)nblk * nkeys * kPrepBlock * 4);
   const size_t o_cnt = take((size_t)nblk * nkeys * 4);
   if (ws) {
     ws->hdr = reinterpret_cast<RegionHdr*>(base + o_hdr);
     ws->rowtab = reinterpret_cast<TapEntry*>(base + o_row);
-    ws->coltab = reinterpret_cast<TapEntry*>(base + o_col);
+    ws->colbin = reinterpret_cast<ColBin*>(base + o_cbin);
+    ws->colw = reinterpret_cast<float*>(base + o_colw);
     ws->seg_ids = reinterpret_cast<int*>(base + o_ids);
     ws->seg_cnt = reinterpret_cast<int*>(base + o_cnt);
     ws->nblk = nblk;
@@ -279,11 +371,10 @@ inline size_t pull_ws_layout(int N, int L, int B, const int* H, unsigned char* b
   return off;
 }
 
-// Transpose one axis table: for every window row (column) the bins sampling
-// it, two per block (block k holds bins p0+2k, p0+2k+1).  One warp; lane =
-// window row.  Returns the number of blocks used (>= 1), or 0 when
-// blocks x window length exceeds kTabLen: such regions take the atomic
-// fallback kernel.
+// Transpose the row table: for every window row the bins sampling it, two
+// per block (block k holds bins p0+2k, p0+2k+1).  One warp; lane = window
+// row.  Returns the number of blocks used (>= 1), or 0 when blocks x window
+// length exceeds kTabLen: such regions take the atomic fallback kernel.
 __device__ int transpose_axis(const AxisTable& t, int P, int lo, int hi, float scale,
                               TapEntry* __restrict__ tab, int lane) {
   const int n = hi - lo + 1;
@@ -382,7 +473,7 @@ roi_prep_kernel(const RoiFuseParams p, const PullWs ws) {
   // ---- tap tables of region i ----
   __shared__ CtaHeader hd;
   __shared__ AxisTable ty, tx;
-  __shared__ int fit[2];
+  __shared__ int fit;
   const int i = blockIdx.x - ws.nblk;
   const int k = i / p.R, r = i - k * p.R;
   const bool live = setup_cta(p, k, r, hd, ty, tx);
@@ -396,18 +487,23 @@ roi_prep_kernel(const RoiFuseParams p, const PullWs ws) {
   if (live && !hd.overflow) {
     h.ymin = hd.ymin; h.ymax = hd.ymax; h.xmin = hd.xmin; h.xmax = hd.xmax;
     const int warp = tid >> 5, lane = tid & 31;
+    const int ctotal = tx.off[p.PW - 1] + tx.cnt[p.PW - 1];  // off[] is a running prefix
     if (warp == 0) {
       const int nb = transpose_axis(ty, p.PH, hd.ymin, hd.ymax, 1.0f / hd.g.count,
                                     ws.rowtab + (size_t)i * kTabLen, lane);
-      if (lane == 0) fit[0] = nb;
-    } else if (warp == 1) {
-      const int nb = transpose_axis(tx, p.PW, hd.xmin, hd.xmax, 1.0f,
-                                    ws.coltab + (size_t)i * kTabLen, lane);
-      if (lane == 0) fit[1] = nb;
+      if (lane == 0) fit = nb;
+    } else if (ctotal <= kTabLen) {
+      const int t2 = tid - 32;
+      if (t2 < p.PW) {
+        ColBin cb;
+        cb.first = tx.first[t2]; cb.cnt = (short)tx.cnt[t2]; cb.off = (short)tx.off[t2];
+        ws.colbin[(size_t)i * kMaxPool + t2] = cb;
+      }
+      for (int j = t2; j < ctotal; j += kPrepBlock - 32) ws.colw[(size_t)i * kTabLen + j] = tx.w[j];
     }
     __syncthreads();
-    if (!fit[0] || !fit[1]) h.flags = 1;
-    else h.flags = (fit[0] << 8) | (fit[1] << 12);  // bin blocks per axis
+    if (!fit || ctotal > kTabLen) h.flags = 1;
+    else h.flags = fit << 8;  // row bin blocks
   }
   if (tid == 0) ws.hdr[i] = h;
 }
@@ -415,8 +511,10 @@ roi_prep_kernel(const RoiFuseParams p, const PullWs ws) {
 // ----------------------------------------------------------- pull backward
 constexpr int kTileH = kBandH;  // tile rows, warp == tile row
 constexpr int kListCap = 512;   // list entries per pass
-constexpr int kChunkR = 16;     // regions whose taps are expanded per round
+constexpr int kChunkR = 32;     // list entries expanded per round
+constexpr int kJ = 8;           // output columns (pw) per list entry
 constexpr int kMaxPrepBlocks = 511;   // K * regions <= 130 816 for the pull path
+static_assert(kTileH * kChunkR == kThreads && kChunkR * kJ == kThreads, "expand: one item per thread");
 
 struct TileMap {
   int start[kMaxLevels + 1];  // first CTA of each scheduled slot
@@ -426,31 +524,37 @@ struct TileMap {
   int groups;                 // channel groups per tile (C / (32 * V * NV))
 };
 
-// Compact copy of a listed region kept in shared memory.
+// Compact copy of a listed (region, row bin block, pw block) in shared memory.
 struct __align__(16) ListEntry {
-  int id;      // region id | row block << 24 | column block << 28
-  short ymin, ymax, xmin, xmax;
-  int src;
+  int id;            // region id | row block << 24
+  int src;           // k * R + r
+  short ymin, ymax;  // window rows
+  short pw0, npw;    // output columns [pw0, pw0 + npw) reach this tile's columns
 };
 
 // NV = 128-bit vectors per lane, TW = tile width in pixels.
 //
-// Round structure (kChunkR listed regions at a time):
-//   expand : one THREAD per (region, tile pixel) turns the region's row/column
-//            records into an explicit tap descriptor -- four element offsets
-//            into dout and four weights (missing taps: weight 0, offset of
-//            tap 0) -- in shared memory.  All per-region control work happens
-//            here, thread-parallel.
-//   stream : warp == tile row, lanes == channels: for every descriptor of its
-//            row: 4 x NV 128-bit loads, 16 x NV FMAs into register accumulators.
+// The bilinear sum is separable: a gradient pixel (y, x) of a region receives
+//     sum_ph ry[ph][y] * sum_pw cx[pw][x] * dout[ph][pw]
+// with ry / cx the aggregated row / column weights.  A warp owns one tile row
+// y, lanes own channels.  For one listed region the warp walks the few output
+// columns pw whose samples reach the tile's columns; for each it loads
+// dout[ph][pw] of the (<= 2) bins ph sampling row y ONCE, combines them with the
+// row weights, and adds the result to its TW pixels with that pw's column
+// weights (zero where pw does not reach) -- 2 loads per pw instead of 4 per pixel.
+//
+// Round structure (kChunkR list entries at a time, one item per thread):
+//   expand : thread (tile row, entry): the row's TapEntry -> {dout offset, bins,
+//            row weights}; thread (entry, pw): that pw's TW column weights.
+//   stream : warp == tile row, lanes == channels, as above, FFMA2 arithmetic.
 template <typename T, int NV, int TW>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, (NV * TW * VecOf<T>::n <= 16 ? 4 : (NV * TW * VecOf<T>::n <= 32 ? 3 : 2)))
 roi_bwd_pull(const RoiFuseParams p, const PullWs ws, const TileMap tm) {
   constexpr int V = VecOf<T>::n;
-  constexpr int kSlots = kChunkR * TW;          // descriptors per tile row per round
+  constexpr int V2 = V / 2;
   __shared__ ListEntry list[kListCap];
-  __shared__ int4 d_off[kTileH * kSlots];       // tap offsets, .x < 0: empty slot
-  __shared__ float4 d_w[kTileH * kSlots];
+  __shared__ int4 rdesc[kTileH * kChunkR + 1];             // {dout offset (<0: none), npw | two << 8, w0, w1}
+  __shared__ __align__(16) float cwt[kChunkR * kJ * TW];   // [entry][pw - pw0][tile column]
   __shared__ int list_n;
   __shared__ int warp_tot[kThreads / 32];
   __shared__ int pre[kMaxPrepBlocks + 1];
@@ -474,20 +578,23 @@ roi_bwd_pull(const RoiFuseParams p, const PullWs ws, const TileMap tm) {
   const int cl = grp * (32 * V * NV) + lane * V;  // first channel of this lane's first vector
   const T* __restrict__ dbase = static_cast<const T*>(p.dout) + cl;
   float* __restrict__ dimg = p.dfeats[l] + (size_t)b * H * W * C;
+  const int rowstep = PW * RC;
+  const bool cok = cl < C;  // NV > 1 requires C % (32 * V * NV) == 0 (launcher)
 
-  float acc[TW][NV][V];
+  uint64_t acc[TW][NV][V2];
 #pragma unroll
   for (int x = 0; x < TW; ++x)
 #pragma unroll
     for (int v = 0; v < NV; ++v)
 #pragma unroll
-      for (int u = 0; u < V; ++u) acc[x][v][u] = 0.f;
+      for (int u = 0; u < V2; ++u) acc[x][v][u] = 0ull;
 
   // candidates = the ids of this tile's (level, image, band) key over all prep
   // blocks, block-major == region-index order; pre[] = exclusive prefix of the
   // per-block counts so that one 256-thread batch spans blocks
   for (int i = tid; i <= ws.nblk; i += kThreads)
     pre[i] = i < ws.nblk ? ws.seg_cnt[(size_t)i * ws.nkeys + key] : 0;
+  if (tid == 0) rdesc[kTileH * kChunkR] = make_int4(-1, 0, 0, 0);  // prefetch pad
   __syncthreads();
   if (warp == 0) {  // exclusive scan of pre[0..nblk] by one warp
     int carry = 0;
@@ -517,7 +624,7 @@ roi_bwd_pull(const RoiFuseParams p, const PullWs ws, const TileMap tm) {
     bool full = false;
     while (pos < total_cand && !full) {
       const int q = pos + tid;
-      int mine = 0, nbr = 0, nbc = 0, id = 0;  // list entries this thread contributes
+      int mine = 0, nbr = 0, ncb = 0, id = 0, plo = 0, phi = -1;
       RegionHdr h;
       if (q < total_cand) {
         int lo = 0, hi = ws.nblk - 1;  // last block with pre[blk] <= q
@@ -529,7 +636,23 @@ roi_bwd_pull(const RoiFuseParams p, const PullWs ws, const TileMap tm) {
         h = ws.hdr[id];
         const bool hit = h.lvl == l && h.batch == b && (h.flags & 1) == 0 && h.ymax >= y0 &&
                          h.ymin <= y1 && h.xmax >= x0 && h.xmin <= x1;
-        if (hit) { nbr = (h.flags >> 8) & 15; nbc = (h.flags >> 12) & 15; mine = nbr * nbc; }
+        if (hit) {
+          // output columns whose samples reach [x0, x1]
+          const ColBin* __restrict__ cbp = ws.colbin + (size_t)id * kMaxPool;
+          plo = PW;
+          for (int pw = 0; pw < PW; ++pw) {
+            const ColBin c = cbp[pw];
+            if (c.cnt > 0 && c.first <= x1 && c.first + c.cnt - 1 >= x0) {
+              plo = min(plo, pw);
+              phi = pw;
+            }
+          }
+          if (phi >= 0) {
+            nbr = (h.flags >> 8) & 15;
+            ncb = (phi - plo + kJ) / kJ;
+            mine = nbr * ncb;
+          }
+        }
       }
       int incl = mine;
 #pragma unroll
@@ -548,11 +671,13 @@ roi_bwd_pull(const RoiFuseParams p, const PullWs ws, const TileMap tm) {
       if (mine) {
         ListEntry e;
         e.src = h.src;
-        e.ymin = (short)h.ymin; e.ymax = (short)h.ymax; e.xmin = (short)h.xmin; e.xmax = (short)h.xmax;
+        e.ymin = (short)h.ymin; e.ymax = (short)h.ymax;
         int o = base + incl - mine;
         for (int rb = 0; rb < nbr; ++rb)
-          for (int cb = 0; cb < nbc; ++cb) {
-            e.id = id | (rb << 24) | (cb << 28);
+          for (int cb = 0; cb < ncb; ++cb) {
+            e.id = id | (rb << 24);
+            e.pw0 = (short)(plo + cb * kJ);
+            e.npw = (short)min(kJ, phi - (plo + cb * kJ) + 1);
             list[o++] = e;
           }
       }
@@ -567,55 +692,97 @@ roi_bwd_pull(const RoiFuseParams p, const PullWs ws, const TileMap tm) {
 
     for (int c0 = 0; c0 < n; c0 += kChunkR) {
       const int nc = min(kChunkR, n - c0);
-      // ---- expand: thread == (tile row, region, tile column) ----
-      for (int s = tid; s < kTileH * nc * TW; s += kThreads) {
-        const int row = s / (nc * TW);
-        const int rem = s - row * (nc * TW);
-        const int q = rem / TW, x = rem - q * TW;
-        const ListEntry e = list[c0 + q];
-        const int yy = y0 + row, xx = x0 + x;
-        int4 o = make_int4(-1, 0, 0, 0);
-        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (yy >= e.ymin && yy <= e.ymax && xx >= e.xmin && xx <= e.xmax) {
-          const int id = e.id & 0xffffff, rb = (e.id >> 24) & 15, cb = (e.id >> 28) & 15;
-          const TapEntry re = ws.rowtab[(size_t)id * kTabLen + tab_index(rb, yy - e.ymin, e.ymax - e.ymin + 1)];
-          const TapEntry ce = ws.coltab[(size_t)id * kTabLen + tab_index(cb, xx - e.xmin, e.xmax - e.xmin + 1)];
-          if (re.n > 0 && ce.n > 0) {
-            const int k = e.src / p.R, r = e.src - k * p.R;
-            const int o00 = (k * PHW + re.p0 * PW + ce.p0) * RC + r * C;
-            const int dr = re.n > 1 ? PW * RC : 0, dc = ce.n > 1 ? RC : 0;
-            o = make_int4(o00, o00 + dc, o00 + dr, o00 + dr + dc);
-            w = make_float4(re.w0 * ce.w0, re.w0 * ce.w1, re.w1 * ce.w0, re.w1 * ce.w1);
+      // ---- expand, one item per thread ----
+      {  // thread == (tile row, entry): row descriptor
+        const int row = tid / kChunkR, q = tid - row * kChunkR;
+        int4 d = make_int4(-1, 0, 0, 0);
+        if (q < nc) {
+          const ListEntry e = list[c0 + q];
+          const int yy = y0 + row;
+          if (yy >= e.ymin && yy <= e.ymax) {
+            const int id = e.id & 0xffffff, rb = e.id >> 24;
+            const TapEntry re = ws.rowtab[(size_t)id * kTabLen + tab_index(rb, yy - e.ymin, e.ymax - e.ymin + 1)];
+            if (re.n > 0) {
+              const int k = e.src / p.R, r = e.src - k * p.R;
+              d.x = (k * PHW + re.p0 * PW + e.pw0) * RC + r * C;
+              d.y = e.npw | (re.n > 1 ? 256 : 0);
+              d.z = __float_as_int(re.w0);
+              d.w = __float_as_int(re.w1);
+            }
           }
         }
-        d_off[row * kSlots + q * TW + x] = o;
-        d_w[row * kSlots + q * TW + x] = w;
+        rdesc[row * kChunkR + q] = d;
+      }
+      {  // thread == (entry, pw): the pw's column weights over the tile
+        const int q = tid / kJ, jj = tid - q * kJ;
+        if (q < nc) {
+          const ListEntry e = list[c0 + q];
+          if (jj < e.npw) {
+            const int id = e.id & 0xffffff;
+            const ColBin c = ws.colbin[(size_t)id * kMaxPool + e.pw0 + jj];
+            const float* __restrict__ cwp = ws.colw + (size_t)id * kTabLen + c.off;
+            float w[TW];
+#pragma unroll
+            for (int x = 0; x < TW; ++x) {
+              const int i = x0 + x - c.first;
+              w[x] = (i >= 0 && i < c.cnt) ? __ldg(cwp + i) : 0.f;
+            }
+#pragma unroll
+            for (int x = 0; x < TW; x += 4)
+              *reinterpret_cast<float4*>(cwt + tid * TW + x) = make_float4(w[x], w[x + 1], w[x + 2], w[x + 3]);
+          }
+        }
       }
       __syncthreads();
       // ---- stream: warp == row y, lanes == channels ----
-      if (y <= y1 && cl < C) {
-        const int4* __restrict__ po = d_off + warp * kSlots;
-        const float4* __restrict__ pw = d_w + warp * kSlots;
+      if (y <= y1 && cok) {
+        const int4* __restrict__ pr = rdesc + warp * kChunkR;
+        int4 rd = pr[0];
         for (int q = 0; q < nc; ++q) {
-#pragma unroll
-          for (int x = 0; x < TW; ++x) {
-            const int4 o = po[q * TW + x];
-            if (o.x < 0) continue;
-            const float4 w = pw[q * TW + x];
-            float f0[NV][V], f1[NV][V], f2[NV][V], f3[NV][V];
+          const int4 cur = rd;
+          rd = pr[q + 1];  // prefetch (the array is padded by one)
+          if (cur.x < 0) continue;
+          const int npw = cur.y & 255;
+          const bool two = (cur.y & 256) != 0;
+          const float a0 = __int_as_float(cur.z), a1 = __int_as_float(cur.w);
+          const uint64_t a0p = pack2(a0, a0), a1p = pack2(a1, a1);
+          const T* __restrict__ src = dbase + cur.x;
+          const float* __restrict__ cw = cwt + q * (kJ * TW);
+#pragma unroll 2
+          for (int jj = 0; jj < npw; ++jj) {
+            uint64_t e[NV][V2];
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
-              ldg_vec<T>(dbase + o.x + v * 32 * V, f0[v]);
-              ldg_vec<T>(dbase + o.y + v * 32 * V, f1[v]);
-              ldg_vec<T>(dbase + o.z + v * 32 * V, f2[v]);
-              ldg_vec<T>(dbase + o.w + v * 32 * V, f3[v]);
+              uint64_t d0[V2];
+              ldg_pairs<T>(src + v * 32 * V, d0);
+#pragma unroll
+              for (int u = 0; u < V2; ++u) e[v][u] = mul2(d0[u], a0p);
+            }
+            if (two) {
+#pragma unroll
+              for (int v = 0; v < NV; ++v) {
+                uint64_t d1[V2];
+                ldg_pairs<T>(src + rowstep + v * 32 * V, d1);
+#pragma unroll
+                for (int u = 0; u < V2; ++u) e[v][u] = fma2(d1[u], a1p, e[v][u]);
+              }
+            }
+            float w[TW];
+#pragma unroll
+            for (int x = 0; x < TW; x += 4) {
+              const float4 t4 = *reinterpret_cast<const float4*>(cw + x);
+              w[x] = t4.x; w[x + 1] = t4.y; w[x + 2] = t4.z; w[x + 3] = t4.w;
             }
 #pragma unroll
-            for (int v = 0; v < NV; ++v)
+            for (int x = 0; x < TW; ++x) {
+              const uint64_t wp = pack2(w[x], w[x]);
 #pragma unroll
-              for (int u = 0; u < V; ++u)
-                acc[x][v][u] = fmaf(w.w, f3[v][u], fmaf(w.z, f2[v][u], fmaf(w.y, f1[v][u],
-                                    fmaf(w.x, f0[v][u], acc[x][v][u]))));
+              for (int v = 0; v < NV; ++v)
+#pragma unroll
+                for (int u = 0; u < V2; ++u) acc[x][v][u] = fma2(e[v][u], wp, acc[x][v][u]);
+            }
+            src += RC;
+            cw += TW;
           }
         }
       }
@@ -623,18 +790,16 @@ roi_bwd_pull(const RoiFuseParams p, const PullWs ws, const TileMap tm) {
     }
   }
   // ---- every element of the tile written exactly once ----
-  if (y <= y1) {
+  if (y <= y1 && cok) {
 #pragma unroll
     for (int x = 0; x < TW; ++x) {
       if (x0 + x > x1) continue;
       float* __restrict__ o = dimg + ((size_t)y * W + x0 + x) * C + cl;
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        if (cl + v * 32 * V >= C) continue;
 #pragma unroll
-        for (int u = 0; u < V; u += 4)
-          *reinterpret_cast<float4*>(o + v * 32 * V + u) =
-              make_float4(acc[x][v][u], acc[x][v][u + 1], acc[x][v][u + 2], acc[x][v][u + 3]);
+        for (int u = 0; u < V2; u += 2)
+          *reinterpret_cast<ulonglong2*>(o + v * 32 * V + 2 * u) = make_ulonglong2(acc[x][v][u], acc[x][v][u + 1]);
       }
     }
   }
@@ -654,13 +819,19 @@ cudaError_t launch_roi_fuse_forward_cl(const RoiFuseParams& p, int dtype, int ou
     smem += bpp * opitch * 4;
   }
   cudaError_t e;
-#define ARFE_FWD_CL(TT, OC)                                                        \
-  do {                                                                             \
-    if ((e = set_smem(roi_fuse_fwd_cl<TT, OC>, smem)) != cudaSuccess) return e;    \
-    roi_fuse_fwd_cl<TT, OC><<<grid, kThreads, smem, stream>>>(p, opitch, bpp);     \
+  static const int occ = [] { const char* e = getenv("ARFE_FWD_OCC"); return e ? atoi(e) : 4; }();
+#define ARFE_FWD_CL1(TT, OC, OCC)                                                       \
+  do {                                                                                  \
+    if ((e = set_smem(roi_fuse_fwd_cl<TT, OC, OCC>, smem)) != cudaSuccess) return e;    \
+    roi_fuse_fwd_cl<TT, OC, OCC><<<grid, kThreads, smem, stream>>>(p, opitch, bpp);     \
+  } while (0)
+#define ARFE_FWD_CL(TT, OC)                                                             \
+  do {                                                                                  \
+    if (occ == 3) ARFE_FWD_CL1(TT, OC, 3); else ARFE_FWD_CL1(TT, OC, 4);                \
   } while (0)
   if (dtype == 0) { if (out_cl) ARFE_FWD_CL(float, true); else ARFE_FWD_CL(float, false); }
   else { if (out_cl) ARFE_FWD_CL(__nv_bfloat16, true); else ARFE_FWD_CL(__nv_bfloat16, false); }
+#undef ARFE_FWD_CL1
 #undef ARFE_FWD_CL
   return cudaGetLastError();
 }
@@ -689,10 +860,11 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
   // tile than level 0, so they get narrow tiles + a channel split and go first
   // (heaviest level first inside each launch); the big maps follow with wide tiles.
   const int V = dtype == 0 ? 4 : 8;
+  if ((long long)p.K * p.PH * p.PW * p.R * p.C > 0x7fffffffLL) return cudaErrorInvalidValue;  // 32-bit dout offsets
   auto heavy = [&](int l) { return (long long)p.H[l] * p.W[l] <= 64 * 96; };
   for (int pass = 0; pass < 2; ++pass) {
     const int tw = pass == 0 ? 4 : 8;
-    const int nv = pass == 0 ? 1 : ((p.C > 32 * V) ? 2 : 1);
+    const int nv = (pass == 0 || dtype != 0) ? 1 : ((p.C % (64 * V) == 0) ? 2 : 1);
     TileMap tm;
     int total = 0, ns = 0;
     tm.groups = (p.C + 32 * V * nv - 1) / (32 * V * nv);
@@ -713,8 +885,7 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
       if (dtype == 0) roi_bwd_pull<float, 1, 4><<<total, kThreads, 0, stream>>>(p, ws, tm);
       else roi_bwd_pull<__nv_bfloat16, 1, 4><<<total, kThreads, 0, stream>>>(p, ws, tm);
     } else if (nv == 2) {
-      if (dtype == 0) roi_bwd_pull<float, 2, 8><<<total, kThreads, 0, stream>>>(p, ws, tm);
-      else roi_bwd_pull<__nv_bfloat16, 2, 8><<<total, kThreads, 0, stream>>>(p, ws, tm);
+      roi_bwd_pull<float, 2, 8><<<total, kThreads, 0, stream>>>(p, ws, tm);
     } else {
       if (dtype == 0) roi_bwd_pull<float, 1, 8><<<total, kThreads, 0, stream>>>(p, ws, tm);
       else roi_bwd_pull<__nv_bfloat16, 1, 8><<<total, kThreads, 0, stream>>>(p, ws, tm);
