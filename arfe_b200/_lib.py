@@ -32,7 +32,7 @@ _SIGNATURES = {
     "arfe_roi_fuse_backward": ([c_void_p, c_int, _ip, _ip, _fp, c_int, c_int, c_int, c_void_p,
                                 c_int, c_int, c_float, c_int, c_int, c_int, c_float, c_int, c_int,
                                 _pp, c_void_p], c_int),
-    "arfe_roi_fuse_pull_workspace_bytes": ([c_int, c_int, c_int, c_int, _ip], ctypes.c_size_t),
+    "arfe_roi_fuse_pull_workspace_bytes": ([c_int, c_int, c_int, c_int, _ip, _ip], ctypes.c_size_t),
     "arfe_roi_fuse_backward_pull": ([c_void_p, _ip, _ip, _fp, c_int, c_int, c_int, c_void_p,
                                      c_int, c_int, c_float, c_int, c_int, c_int, c_float, c_int,
                                      _pp, c_void_p, ctypes.c_size_t, c_void_p], c_int),

@@ -137,11 +137,12 @@ int arfe_roi_fuse_backward(const void* dout, int dout_layout, const int32_t* H, 
   return cuda_result(arfe::launch_roi_fuse_backward(p, dtype, layout, (cudaStream_t)stream), fn);
 }
 
-size_t arfe_roi_fuse_pull_workspace_bytes(int K, int regions, int L, int B, const int32_t* H) {
-  if (K <= 0 || (regions != 1 && regions != 3) || L < 1 || L > ARFE_MAX_LEVELS || B < 1 || !H) return 0;
+size_t arfe_roi_fuse_pull_workspace_bytes(int K, int regions, int L, int B, const int32_t* H,
+                                          const int32_t* W) {
+  if (K <= 0 || (regions != 1 && regions != 3) || L < 1 || L > ARFE_MAX_LEVELS || B < 1 || !H || !W) return 0;
   for (int l = 0; l < L; ++l)
-    if (H[l] < 1) return 0;
-  return arfe::roi_pull_workspace_bytes(K, regions, L, B, H);
+    if (H[l] < 1 || W[l] < 1) return 0;
+  return arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W);
 }
 
 int arfe_roi_fuse_backward_pull(const void* dout, const int32_t* H, const int32_t* W,
@@ -172,13 +173,13 @@ int arfe_roi_fuse_backward_pull(const void* dout, const int32_t* H, const int32_
   }
   REQUIRE(dout && workspace, ARFE_E_NULL, "%s: dout/workspace is NULL", fn);
   REQUIRE(aligned(dout, 16) && aligned(workspace, 256), ARFE_E_ALIGN, "%s: dout (16) / workspace (256) misaligned", fn);
-  REQUIRE(workspace_bytes >= arfe::roi_pull_workspace_bytes(K, regions, L, B, H), ARFE_E_SHAPE,
-          "%s: workspace too small (%zu < %zu)", fn, workspace_bytes, arfe::roi_pull_workspace_bytes(K, regions, L, B, H));
+  REQUIRE(workspace_bytes >= arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W), ARFE_E_SHAPE,
+          "%s: workspace too small (%zu < %zu)", fn, workspace_bytes, arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W));
   p.dout = dout; p.dout_cl = 1;
   rc = cuda_result(arfe::launch_roi_fuse_backward_pull(p, dtype, workspace, workspace_bytes, (cudaStream_t)stream), fn);
   if (rc) return rc;
   // regions whose tap tables did not fit the workspace records: atomic kernel, adds on top
-  p.flag_hdr = arfe::roi_pull_headers(K, regions, L, B, H, workspace);
+  p.flag_list = arfe::roi_pull_flag_list(K, regions, L, B, H, W, workspace, &p.flag_count);
   p.bwd_vec = 0;
   return cuda_result(arfe::launch_roi_fuse_backward(p, dtype, ARFE_NHWC, (cudaStream_t)stream), fn);
 }

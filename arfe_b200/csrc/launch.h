@@ -24,7 +24,8 @@ struct RoiFuseParams {
   int bwd_vec;       // backward: 128-bit vector reductions (1) or scalar (0)
   int out_cl;        // forward: output channels-last [K][PH*PW][R*C] (1) or NCHW (0)
   int dout_cl;       // backward: dout channels-last (1) or NCHW (0)
-  const void* flag_hdr;  // backward (atomic kernel): RegionHdr array; only flagged regions run
+  const int* flag_list;   // backward (atomic kernel as the pull fallback): region ids to process ...
+  const int* flag_count;  // ... and how many (device memory)
   int debug_skip;    // profiling aid (ARFE_FWD_SKIP): 1 compute, 2 staging, 4 write-out, 8 all but setup
 };
 
@@ -34,10 +35,11 @@ cudaError_t launch_roi_fuse_backward(const RoiFuseParams& p, int dtype, int layo
                                      cudaStream_t stream);
 cudaError_t launch_roi_fuse_forward_cl(const RoiFuseParams& p, int dtype, int out_cl,
                                        cudaStream_t stream);
-size_t roi_pull_workspace_bytes(int K, int R, int L, int B, const int* H);
+size_t roi_pull_workspace_bytes(int K, int R, int L, int B, const int* H, const int* W);
 cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, void* workspace,
                                           size_t workspace_bytes, cudaStream_t stream);
-const void* roi_pull_headers(int K, int R, int L, int B, const int* H, void* workspace);
+const int* roi_pull_flag_list(int K, int R, int L, int B, const int* H, const int* W, void* workspace,
+                              const int** count);
 cudaError_t launch_roi_fuse_taps(const RoiFuseParams& p, int max_grid, int32_t* lvl,
                                  int32_t* grid, float* boxes, int32_t* ylo,
                                  int32_t* yhi, float* ywl, float* ywh, int32_t* xlo,

@@ -344,20 +344,18 @@ __device__ __forceinline__ void bwd_px_scalar(const float* __restrict__ dsm, int
 // dynamic smem: [CtaHeader][AxisTable y][AxisTable x][dsm: cb*PHW floats]
 // ---------------------------------------------------------------------------
 template <typename T, bool kNHWC>
-__global__ void __launch_bounds__(kThreads, 3)
-roi_fuse_bwd(const RoiFuseParams p, int cb /* channels staged per pass */) {
-  extern __shared__ __align__(16) unsigned char smem[];
+__device__ __forceinline__ void roi_fuse_bwd_region(const RoiFuseParams& p, int cb, int region,
+                                                    unsigned char* smem) {
   CtaHeader& hd = *reinterpret_cast<CtaHeader*>(smem);
   AxisTable& ty = *reinterpret_cast<AxisTable*>(smem + 128);
   AxisTable& tx = *reinterpret_cast<AxisTable*>(smem + 128 + sizeof(AxisTable));
   float* dsm = reinterpret_cast<float*>(smem + 128 + 2 * sizeof(AxisTable));
 
-  const int k = blockIdx.x / p.R, r = blockIdx.x % p.R;
+  const int k = region / p.R, r = region % p.R;
   const int tid = threadIdx.x;
   const int PH = p.PH, PW = p.PW, PHW = PH * PW, C = p.C;
   const T* __restrict__ dout_blk =
       static_cast<const T*>(p.dout) + ((size_t)k * p.R + r) * C * PHW;
-  if (p.flag_hdr && !(static_cast<const RegionHdr*>(p.flag_hdr)[k * p.R + r].flags & 1)) return;
   // element (c, bin) of this region's incoming gradient, NCHW or channels-last
   auto dout_at = [&](int c, int bin) -> float {
     return p.dout_cl ? to_f(static_cast<const T*>(p.dout)[((size_t)k * PHW + bin) * (p.R * C) + (size_t)r * C + c])
@@ -531,6 +529,24 @@ roi_fuse_bwd(const RoiFuseParams p, int cb /* channels staged per pass */) {
   }
 }
 
+// Grid = one CTA per (RoI, region); or, as the fallback behind the pull kernel
+// (p.flag_list / p.flag_count: region ids written by roi_prep_kernel), a
+// fixed small grid walking the regions whose tables did not fit.
+template <typename T, bool kNHWC>
+__global__ void __launch_bounds__(kThreads, 3)
+roi_fuse_bwd(const RoiFuseParams p, int cb /* channels staged per pass */) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  if (p.flag_list) {
+    const int n = *p.flag_count;
+    for (int j = blockIdx.x; j < n; j += gridDim.x) {
+      roi_fuse_bwd_region<T, kNHWC>(p, cb, p.flag_list[j], smem);
+      __syncthreads();
+    }
+  } else {
+    roi_fuse_bwd_region<T, kNHWC>(p, cb, blockIdx.x, smem);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Parity instrumentation: dump boxes / levels / grids / taps.
 // ---------------------------------------------------------------------------
@@ -615,7 +631,8 @@ cudaError_t launch_roi_fuse_forward(const RoiFuseParams& p, int dtype, int layou
 cudaError_t launch_roi_fuse_backward(const RoiFuseParams& p, int dtype, int layout,
                                      cudaStream_t stream) {
   const int PHW = p.PH * p.PW;
-  const int grid = p.K * p.R;
+  int grid = p.K * p.R;
+  if (p.flag_list && grid > 296) grid = 296;  // fallback mode: usually nothing to do
   // stage as many channels of dout as fit ~100 KB (2 CTAs / SM)
   int cb = (100 * 1024 - kHdrBytes) / (PHW * 4);
   if (cb > p.C) cb = p.C;

@@ -97,6 +97,23 @@ __device__ __forceinline__ void ldg_pairs(const T* __restrict__ p, uint64_t (&f)
   }
 }
 
+// VEC consecutive channels from shared memory as packed pairs.
+template <typename T>
+__device__ __forceinline__ void lds_pairs(const unsigned char* __restrict__ p, uint64_t (&f)[VecOf<T>::n / 2]) {
+  if constexpr (sizeof(T) == 4) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+    f[0] = v.x; f[1] = v.y;
+  } else {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(h[i]);
+      f[i] = pack2(t.x, t.y);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ forward
 // One bin, VEC channels per lane: rows x NC taps, NC loads in flight per row.
 // `rstep` = +1 walks the bin's rows top-down, -1 bottom-up (base / wy then
@@ -305,6 +322,7 @@ roi_fuse_fwd_cl(const RoiFuseParams p, int opitch, int bins_per_pass) {
 //   colw    : N * kTabLen * 4                aggregated column weights, bin-major
 //   seg_ids : nblk * NK * kPrepBlock * 4     region ids per (prep block, key), index order;
 //   seg_cnt : nblk * NK * 4                  key = (level, image, 8-row band of the level)
+constexpr int kBandH = 8;       // rows per band == rows per pull tile
 constexpr int kTabLen = 256;    // per region: (row bin blocks) x (window rows) <= kTabLen, column weights <= kTabLen
 constexpr int kMaxBlk = 15;     // a row may be sampled by up to 2 * kMaxBlk bins (4-bit field)
 constexpr int kPrepBlock = 256; // regions per header block
@@ -324,6 +342,21 @@ struct __align__(8) ColBin {
   short off;      // offset of its weights in colw
 };
 
+constexpr int kJ = 8;           // output columns (pw) per stage
+constexpr int kMaxPh = 8;       // output rows (ph) per stage
+constexpr int kMaxTW = 8;       // widest pull tile
+
+// One stage of the pull kernel = one listed region of one tile: the bins
+// [ph_lo, ph_lo + nph) x [pw0, pw0 + npw) of its dout block reach the tile.
+struct __align__(16) StageDesc {
+  int src_off;         // dout element offset of bin (ph_lo, pw0), channel 0 of the region's block
+  short nph, npw;
+  int pad[2];
+  int4 rows[kBandH];   // per tile row: {first bin row - ph_lo (< 0: row not sampled), two bins, w0, w1}
+  float cw[kJ][kMaxTW];  // per output column: its weights over the tile columns
+};
+static_assert(sizeof(StageDesc) == 400, "descriptor is copied as one 400-byte bulk");
+
 struct PullWs {
   RegionHdr* hdr;
   TapEntry* rowtab;
@@ -331,17 +364,34 @@ struct PullWs {
   float* colw;
   int* seg_ids;
   int* seg_cnt;
+  int2* tile_desc;            // per pull tile: {pool offset, stages} or {., -1}: the inline kernel serves it
+  int* counters;              // [0] next free pool entry, [1] flagged regions, [2] inline tiles (one memset)
+  int* flag_list;             // regions for the atomic fallback kernel
+  int* inline_list;           // tiles for the inline kernel
+  StageDesc* pool;            // [pool_cap] stage descriptors
+  int pool_cap;
   int nblk;
   int nkeys;                  // sum over levels of B * bands(level)
   int key_base[kMaxLevels];   // first key of level l
   int nbands[kMaxLevels];     // ceil(H_l / 8)
 };
 
-constexpr int kBandH = 8;     // rows per band == rows per pull tile
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-inline size_t pull_ws_layout(int N, int L, int B, const int* H, unsigned char* base, PullWs* ws) {
+// Tiles of the two pull passes (4- and 8-pixel-wide tiles, 8 rows).
+inline bool pull_heavy(int H, int W) { return (long long)H * W <= 64 * 96; }
+inline int pull_tiles(int L, int B, const int* H, const int* W) {
+  int n = 0;
+  for (int l = 0; l < L; ++l) {
+    const int tw = pull_heavy(H[l], W[l]) ? 4 : 8;
+    n += ((W[l] + tw - 1) / tw) * ((H[l] + kBandH - 1) / kBandH) * B;
+  }
+  return n;
+}
+inline int pull_pool_cap(int N) { return N * 24 > 4096 ? N * 24 : 4096; }
+
+inline size_t pull_ws_layout(int N, int L, int B, const int* H, const int* W, unsigned char* base, PullWs* ws) {
   const int nblk = (N + kPrepBlock - 1) / kPrepBlock;
   int nkeys = 0, key_base[kMaxLevels], nbands[kMaxLevels];
   for (int l = 0; l < kMaxLevels; ++l) {
@@ -357,7 +407,19 @@ inline size_t pull_ws_layout(int N, int L, int B, const int* H, unsigned char* b
   const size_t o_colw = take((size_t)N * kTabLen * sizeof(float));
   const size_t o_ids = take((size_t)nblk * nkeys * kPrepBlock * 4);
   const size_t o_cnt = take((size_t)nblk * nkeys * 4);
+  const int ntiles = pull_tiles(L, B, H, W), cap = pull_pool_cap(N);
+  const size_t o_td = take((size_t)ntiles * sizeof(int2));
+  const size_t o_cur = take(16);
+  const size_t o_fl = take((size_t)N * 4);
+  const size_t o_il = take((size_t)ntiles * 4);
+  const size_t o_pool = take((size_t)cap * sizeof(StageDesc));
   if (ws) {
+    ws->tile_desc = reinterpret_cast<int2*>(base + o_td);
+    ws->counters = reinterpret_cast<int*>(base + o_cur);
+    ws->flag_list = reinterpret_cast<int*>(base + o_fl);
+    ws->inline_list = reinterpret_cast<int*>(base + o_il);
+    ws->pool = reinterpret_cast<StageDesc*>(base + o_pool);
+    ws->pool_cap = cap;
     ws->hdr = reinterpret_cast<RegionHdr*>(base + o_hdr);
     ws->rowtab = reinterpret_cast<TapEntry*>(base + o_row);
     ws->colbin = reinterpret_cast<ColBin*>(base + o_cbin);
@@ -505,23 +567,26 @@ roi_prep_kernel(const RoiFuseParams p, const PullWs ws) {
     if (!fit || ctotal > kTabLen) h.flags = 1;
     else h.flags = fit << 8;  // row bin blocks
   }
-  if (tid == 0) ws.hdr[i] = h;
+  if (tid == 0) {
+    ws.hdr[i] = h;
+    if (h.flags & 1) ws.flag_list[atomicAdd(ws.counters + 1, 1)] = i;
+  }
 }
 
 // ----------------------------------------------------------- pull backward
 constexpr int kTileH = kBandH;  // tile rows, warp == tile row
 constexpr int kListCap = 512;   // list entries per pass
 constexpr int kChunkR = 32;     // list entries expanded per round
-constexpr int kJ = 8;           // output columns (pw) per list entry
 constexpr int kMaxPrepBlocks = 511;   // K * regions <= 130 816 for the pull path
 static_assert(kTileH * kChunkR == kThreads && kChunkR * kJ == kThreads, "expand: one item per thread");
 
 struct TileMap {
-  int start[kMaxLevels + 1];  // first CTA of each scheduled slot
-  int level[kMaxLevels];      // level of slot j (heaviest first)
+  int tstart[kMaxLevels + 1];  // first tile of each scheduled slot
+  int level[kMaxLevels];       // level of slot j (heaviest first)
   int tiles_x[kMaxLevels], tiles_y[kMaxLevels];
   int nslots;
-  int groups;                 // channel groups per tile (C / (32 * V * NV))
+  int groups;                  // channel groups per tile (C / (32 * V * NV))
+  int tile_base;               // first tile_desc slot of this pass
 };
 
 // Compact copy of a listed (region, row bin block, pw block) in shared memory.
@@ -532,276 +597,602 @@ struct __align__(16) ListEntry {
   short pw0, npw;    // output columns [pw0, pw0 + npw) reach this tile's columns
 };
 
-// NV = 128-bit vectors per lane, TW = tile width in pixels.
-//
-// The bilinear sum is separable: a gradient pixel (y, x) of a region receives
-//     sum_ph ry[ph][y] * sum_pw cx[pw][x] * dout[ph][pw]
-// with ry / cx the aggregated row / column weights.  A warp owns one tile row
-// y, lanes own channels.  For one listed region the warp walks the few output
-// columns pw whose samples reach the tile's columns; for each it loads
-// dout[ph][pw] of the (<= 2) bins ph sampling row y ONCE, combines them with the
-// row weights, and adds the result to its TW pixels with that pw's column
-// weights (zero where pw does not reach) -- 2 loads per pw instead of 4 per pixel.
-//
-// Round structure (kChunkR list entries at a time, one item per thread):
-//   expand : thread (tile row, entry): the row's TapEntry -> {dout offset, bins,
-//            row weights}; thread (entry, pw): that pw's TW column weights.
-//   stream : warp == tile row, lanes == channels, as above, FFMA2 arithmetic.
-template <typename T, int NV, int TW>
-__global__ void __launch_bounds__(kThreads, (NV * TW * VecOf<T>::n <= 16 ? 4 : (NV * TW * VecOf<T>::n <= 32 ? 3 : 2)))
-roi_bwd_pull(const RoiFuseParams p, const PullWs ws, const TileMap tm) {
-  constexpr int V = VecOf<T>::n;
-  constexpr int V2 = V / 2;
-  __shared__ ListEntry list[kListCap];
-  __shared__ int4 rdesc[kTileH * kChunkR + 1];             // {dout offset (<0: none), npw | two << 8, w0, w1}
-  __shared__ __align__(16) float cwt[kChunkR * kJ * TW];   // [entry][pw - pw0][tile column]
-  __shared__ int list_n;
-  __shared__ int warp_tot[kThreads / 32];
-  __shared__ int pre[kMaxPrepBlocks + 1];
+struct Tile {
+  int l, b, y0, x0, y1, x1, key, H, W;
+};
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+__device__ __forceinline__ Tile decode_tile(const RoiFuseParams& p, const PullWs& ws,
+                                            const TileMap& tm, int t, int TW) {
   int j = 0;
-  while (j + 1 < tm.nslots && (int)blockIdx.x >= tm.start[j + 1]) ++j;
-  const int l = tm.level[j];
-  int t = blockIdx.x - tm.start[j];
-  const int grp = t % tm.groups;
-  t /= tm.groups;
+  while (j + 1 < tm.nslots && t >= tm.tstart[j + 1]) ++j;
+  Tile T;
+  T.l = tm.level[j];
+  t -= tm.tstart[j];
   const int per_img = tm.tiles_x[j] * tm.tiles_y[j];
-  const int b = t / per_img;
-  t -= b * per_img;
+  T.b = t / per_img;
+  t -= T.b * per_img;
   const int tyi = t / tm.tiles_x[j], txi = t - tyi * tm.tiles_x[j];
-  const int y0 = tyi * kTileH, x0 = txi * TW;
-  const int key = ws.key_base[l] + b * ws.nbands[l] + tyi;  // this tile's (level, image, band)
-  const int H = p.H[l], W = p.W[l], C = p.C, RC = p.R * C, PHW = p.PH * p.PW, PW = p.PW;
-  const int y = y0 + warp;  // this warp's row
-  const int y1 = min(y0 + kTileH, H) - 1, x1 = min(x0 + TW, W) - 1;
-  const int cl = grp * (32 * V * NV) + lane * V;  // first channel of this lane's first vector
-  const T* __restrict__ dbase = static_cast<const T*>(p.dout) + cl;
-  float* __restrict__ dimg = p.dfeats[l] + (size_t)b * H * W * C;
-  const int rowstep = PW * RC;
-  const bool cok = cl < C;  // NV > 1 requires C % (32 * V * NV) == 0 (launcher)
+  T.y0 = tyi * kTileH;
+  T.x0 = txi * TW;
+  T.H = p.H[T.l];
+  T.W = p.W[T.l];
+  T.y1 = min(T.y0 + kTileH, T.H) - 1;
+  T.x1 = min(T.x0 + TW, T.W) - 1;
+  T.key = ws.key_base[T.l] + T.b * ws.nbands[T.l] + tyi;  // this tile's (level, image, band)
+  return T;
+}
 
-  uint64_t acc[TW][NV][V2];
-#pragma unroll
-  for (int x = 0; x < TW; ++x)
-#pragma unroll
-    for (int v = 0; v < NV; ++v)
-#pragma unroll
-      for (int u = 0; u < V2; ++u) acc[x][v][u] = 0ull;
+struct ListSmem {
+  ListEntry list[kListCap];
+  int pre[kMaxPrepBlocks + 1];
+  int warp_tot[kThreads / 32];
+  int list_n;
+};
 
-  // candidates = the ids of this tile's (level, image, band) key over all prep
-  // blocks, block-major == region-index order; pre[] = exclusive prefix of the
-  // per-block counts so that one 256-thread batch spans blocks
+// candidates = the ids of this tile's (level, image, band) key over all prep
+// blocks, block-major == region-index order; pre[] = exclusive prefix of the
+// per-block counts so that one 256-thread batch spans blocks.  CTA-wide.
+__device__ int init_candidates(ListSmem& sm, const PullWs& ws, int key) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i <= ws.nblk; i += kThreads)
-    pre[i] = i < ws.nblk ? ws.seg_cnt[(size_t)i * ws.nkeys + key] : 0;
-  if (tid == 0) rdesc[kTileH * kChunkR] = make_int4(-1, 0, 0, 0);  // prefetch pad
+    sm.pre[i] = i < ws.nblk ? ws.seg_cnt[(size_t)i * ws.nkeys + key] : 0;
   __syncthreads();
   if (warp == 0) {  // exclusive scan of pre[0..nblk] by one warp
     int carry = 0;
     for (int i0 = 0; i0 <= ws.nblk; i0 += 32) {
       const int i = i0 + lane;
-      const int v = i <= ws.nblk ? pre[i] : 0;
+      const int v = i <= ws.nblk ? sm.pre[i] : 0;
       int incl = v;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const int t2 = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += t2;
       }
-      if (i <= ws.nblk) pre[i] = carry + incl - v;
+      if (i <= ws.nblk) sm.pre[i] = carry + incl - v;
       carry += __shfl_sync(0xffffffffu, incl, 31);
     }
   }
   __syncthreads();
-  const int total_cand = pre[ws.nblk];
+  return sm.pre[ws.nblk];
+}
 
-  int pos = 0;  // cursor into the flattened candidates (uniform)
-  bool more = true;
-  while (more) {
-    __syncthreads();
-    if (tid == 0) list_n = 0;
-    __syncthreads();
-    // ---- ordered compaction of the intersecting regions into list[] ----
-    bool full = false;
-    while (pos < total_cand && !full) {
-      const int q = pos + tid;
-      int mine = 0, nbr = 0, ncb = 0, id = 0, plo = 0, phi = -1;
-      RegionHdr h;
-      if (q < total_cand) {
-        int lo = 0, hi = ws.nblk - 1;  // last block with pre[blk] <= q
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) >> 1;
-          if (pre[mid] <= q) lo = mid; else hi = mid - 1;
-        }
-        id = ws.seg_ids[((size_t)lo * ws.nkeys + key) * kPrepBlock + (q - pre[lo])];
-        h = ws.hdr[id];
-        const bool hit = h.lvl == l && h.batch == b && (h.flags & 1) == 0 && h.ymax >= y0 &&
-                         h.ymin <= y1 && h.xmax >= x0 && h.xmin <= x1;
-        if (hit) {
-          // output columns whose samples reach [x0, x1]
-          const ColBin* __restrict__ cbp = ws.colbin + (size_t)id * kMaxPool;
-          plo = PW;
-          for (int pw = 0; pw < PW; ++pw) {
-            const ColBin c = cbp[pw];
-            if (c.cnt > 0 && c.first <= x1 && c.first + c.cnt - 1 >= x0) {
-              plo = min(plo, pw);
-              phi = pw;
-            }
-          }
-          if (phi >= 0) {
-            nbr = (h.flags >> 8) & 15;
-            ncb = (phi - plo + kJ) / kJ;
-            mine = nbr * ncb;
+// Ordered compaction of the regions intersecting the tile into sm.list, from
+// candidate `pos` on, until the candidates or the list capacity run out.
+// Returns the new cursor.  CTA-wide (uniform control flow).
+__device__ int build_list(ListSmem& sm, const RoiFuseParams& p, const PullWs& ws, const Tile& T,
+                          int pos, int total_cand) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int PW = p.PW;
+  __syncthreads();
+  if (tid == 0) sm.list_n = 0;
+  __syncthreads();
+  while (pos < total_cand) {
+    const int q = pos + tid;
+    int mine = 0, nbr = 0, ncb = 0, id = 0, plo = 0, phi = -1;
+    RegionHdr h;
+    if (q < total_cand) {
+      int lo = 0, hi = ws.nblk - 1;  // last block with pre[blk] <= q
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (sm.pre[mid] <= q) lo = mid; else hi = mid - 1;
+      }
+      id = ws.seg_ids[((size_t)lo * ws.nkeys + T.key) * kPrepBlock + (q - sm.pre[lo])];
+      h = ws.hdr[id];
+      const bool hit = h.lvl == T.l && h.batch == T.b && (h.flags & 1) == 0 && h.ymax >= T.y0 &&
+                       h.ymin <= T.y1 && h.xmax >= T.x0 && h.xmin <= T.x1;
+      if (hit) {
+        // output columns whose samples reach [x0, x1]
+        const ColBin* __restrict__ cbp = ws.colbin + (size_t)id * kMaxPool;
+        plo = PW;
+        for (int pw = 0; pw < PW; ++pw) {
+          const ColBin c = cbp[pw];
+          if (c.cnt > 0 && c.first <= T.x1 && c.first + c.cnt - 1 >= T.x0) {
+            plo = min(plo, pw);
+            phi = pw;
           }
         }
+        if (phi >= 0) {
+          nbr = (h.flags >> 8) & 15;
+          ncb = (phi - plo + kJ) / kJ;
+          mine = nbr * ncb;
+        }
       }
-      int incl = mine;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
-      }
-      if (lane == 31) warp_tot[warp] = incl;
-      __syncthreads();
-      int base = list_n, tot = 0;
-      for (int w = 0; w < kThreads / 32; ++w) {
-        if (w < warp) base += warp_tot[w];
-        tot += warp_tot[w];
-      }
-      if (list_n + tot > kListCap) { full = true; __syncthreads(); break; }
-      if (mine) {
-        ListEntry e;
-        e.src = h.src;
-        e.ymin = (short)h.ymin; e.ymax = (short)h.ymax;
-        int o = base + incl - mine;
-        for (int rb = 0; rb < nbr; ++rb)
-          for (int cb = 0; cb < ncb; ++cb) {
-            e.id = id | (rb << 24);
-            e.pw0 = (short)(plo + cb * kJ);
-            e.npw = (short)min(kJ, phi - (plo + cb * kJ) + 1);
-            list[o++] = e;
-          }
-      }
-      __syncthreads();
-      if (tid == 0) list_n += tot;
-      __syncthreads();
-      pos += kThreads;
     }
-    more = pos < total_cand;
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) sm.warp_tot[warp] = incl;
     __syncthreads();
-    const int n = list_n;
+    int base = sm.list_n;
+    for (int w = 0; w < warp; ++w) base += sm.warp_tot[w];
+    // a candidate is accepted while its entries still fit the list: acceptance
+    // is monotone in candidate order, so the accepted ones form a prefix
+    const int end = base + incl;
+    const bool fits = end <= kListCap;
+    const int accepted = __syncthreads_count(q < total_cand && fits);  // also: everyone has read list_n
+    if (fits && mine) {
+      ListEntry e;
+      e.src = h.src;
+      e.ymin = (short)h.ymin; e.ymax = (short)h.ymax;
+      int o = end - mine;
+      for (int rb = 0; rb < nbr; ++rb)
+        for (int cb = 0; cb < ncb; ++cb) {
+          e.id = id | (rb << 24);
+          e.pw0 = (short)(plo + cb * kJ);
+          e.npw = (short)min(kJ, phi - (plo + cb * kJ) + 1);
+          sm.list[o++] = e;
+        }
+      atomicMax(&sm.list_n, end);
+    }
+    const int batch = min(kThreads, total_cand - pos);
+    pos += accepted;
+    __syncthreads();
+    if (accepted < batch) break;  // list full
+  }
+  __syncthreads();
+  return pos;
+}
 
-    for (int c0 = 0; c0 < n; c0 += kChunkR) {
-      const int nc = min(kChunkR, n - c0);
-      // ---- expand, one item per thread ----
-      {  // thread == (tile row, entry): row descriptor
-        const int row = tid / kChunkR, q = tid - row * kChunkR;
-        int4 d = make_int4(-1, 0, 0, 0);
-        if (q < nc) {
-          const ListEntry e = list[c0 + q];
-          const int yy = y0 + row;
-          if (yy >= e.ymin && yy <= e.ymax) {
-            const int id = e.id & 0xffffff, rb = e.id >> 24;
-            const TapEntry re = ws.rowtab[(size_t)id * kTabLen + tab_index(rb, yy - e.ymin, e.ymax - e.ymin + 1)];
-            if (re.n > 0) {
-              const int k = e.src / p.R, r = e.src - k * p.R;
-              d.x = (k * PHW + re.p0 * PW + e.pw0) * RC + r * C;
-              d.y = e.npw | (re.n > 1 ? 256 : 0);
-              d.z = __float_as_int(re.w0);
-              d.w = __float_as_int(re.w1);
-            }
-          }
-        }
-        rdesc[row * kChunkR + q] = d;
-      }
-      {  // thread == (entry, pw): the pw's column weights over the tile
-        const int q = tid / kJ, jj = tid - q * kJ;
-        if (q < nc) {
-          const ListEntry e = list[c0 + q];
-          if (jj < e.npw) {
-            const int id = e.id & 0xffffff;
-            const ColBin c = ws.colbin[(size_t)id * kMaxPool + e.pw0 + jj];
-            const float* __restrict__ cwp = ws.colw + (size_t)id * kTabLen + c.off;
-            float w[TW];
-#pragma unroll
-            for (int x = 0; x < TW; ++x) {
-              const int i = x0 + x - c.first;
-              w[x] = (i >= 0 && i < c.cnt) ? __ldg(cwp + i) : 0.f;
-            }
-#pragma unroll
-            for (int x = 0; x < TW; x += 4)
-              *reinterpret_cast<float4*>(cwt + tid * TW + x) = make_float4(w[x], w[x + 1], w[x + 2], w[x + 3]);
-          }
-        }
-      }
-      __syncthreads();
-      // ---- stream: warp == row y, lanes == channels ----
-      if (y <= y1 && cok) {
-        const int4* __restrict__ pr = rdesc + warp * kChunkR;
-        int4 rd = pr[0];
-        for (int q = 0; q < nc; ++q) {
-          const int4 cur = rd;
-          rd = pr[q + 1];  // prefetch (the array is padded by one)
-          if (cur.x < 0) continue;
-          const int npw = cur.y & 255;
-          const bool two = (cur.y & 256) != 0;
-          const float a0 = __int_as_float(cur.z), a1 = __int_as_float(cur.w);
-          const uint64_t a0p = pack2(a0, a0), a1p = pack2(a1, a1);
-          const T* __restrict__ src = dbase + cur.x;
-          const float* __restrict__ cw = cwt + q * (kJ * TW);
-#pragma unroll 2
-          for (int jj = 0; jj < npw; ++jj) {
-            uint64_t e[NV][V2];
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-              uint64_t d0[V2];
-              ldg_pairs<T>(src + v * 32 * V, d0);
-#pragma unroll
-              for (int u = 0; u < V2; ++u) e[v][u] = mul2(d0[u], a0p);
-            }
-            if (two) {
-#pragma unroll
-              for (int v = 0; v < NV; ++v) {
-                uint64_t d1[V2];
-                ldg_pairs<T>(src + rowstep + v * 32 * V, d1);
-#pragma unroll
-                for (int u = 0; u < V2; ++u) e[v][u] = fma2(d1[u], a1p, e[v][u]);
-              }
-            }
-            float w[TW];
-#pragma unroll
-            for (int x = 0; x < TW; x += 4) {
-              const float4 t4 = *reinterpret_cast<const float4*>(cw + x);
-              w[x] = t4.x; w[x + 1] = t4.y; w[x + 2] = t4.z; w[x + 3] = t4.w;
-            }
-#pragma unroll
-            for (int x = 0; x < TW; ++x) {
-              const uint64_t wp = pack2(w[x], w[x]);
-#pragma unroll
-              for (int v = 0; v < NV; ++v)
-#pragma unroll
-                for (int u = 0; u < V2; ++u) acc[x][v][u] = fma2(e[v][u], wp, acc[x][v][u]);
-            }
-            src += RC;
-            cw += TW;
-          }
-        }
-      }
-      __syncthreads();
+// Row record of list entry e for feature row yy: {first bin row p0 (< 0: row
+// not sampled), two bins, w0, w1}.
+__device__ __forceinline__ int4 expand_row(const PullWs& ws, const ListEntry& e, int yy) {
+  int4 d = make_int4(-1, 0, 0, 0);
+  if (yy >= e.ymin && yy <= e.ymax) {
+    const int id = e.id & 0xffffff, rb = e.id >> 24;
+    const TapEntry re = ws.rowtab[(size_t)id * kTabLen + tab_index(rb, yy - e.ymin, e.ymax - e.ymin + 1)];
+    if (re.n > 0) {
+      d.x = re.p0;
+      d.y = re.n > 1 ? 1 : 0;
+      d.z = __float_as_int(re.w0);
+      d.w = __float_as_int(re.w1);
     }
   }
-  // ---- every element of the tile written exactly once ----
-  if (y <= y1 && cok) {
+  return d;
+}
+
+// Column weights of output column e.pw0 + jj over the tile columns x0 .. x0 + TW - 1.
+template <int TW>
+__device__ __forceinline__ void expand_col(const PullWs& ws, const ListEntry& e, int jj, int x0,
+                                           float (&w)[TW]) {
+  const int id = e.id & 0xffffff;
+  const ColBin c = ws.colbin[(size_t)id * kMaxPool + e.pw0 + jj];
+  const float* __restrict__ cwp = ws.colw + (size_t)id * kTabLen + c.off;
 #pragma unroll
-    for (int x = 0; x < TW; ++x) {
-      if (x0 + x > x1) continue;
-      float* __restrict__ o = dimg + ((size_t)y * W + x0 + x) * C + cl;
+  for (int x = 0; x < TW; ++x) {
+    const int i = x0 + x - c.first;
+    w[x] = (i >= 0 && i < c.cnt) ? __ldg(cwp + i) : 0.f;
+  }
+}
+
+// The 8 tile rows of entry q live in 8 consecutive lanes: the bin-row range
+// [lo, hi] they reference.
+__device__ __forceinline__ void row_range(const int4 r, int& lo, int& hi) {
+  lo = r.x >= 0 ? r.x : (1 << 20);
+  hi = r.x >= 0 ? r.x + r.y : -1;
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
-#pragma unroll
-        for (int u = 0; u < V2; u += 2)
-          *reinterpret_cast<ulonglong2*>(o + v * 32 * V + 2 * u) = make_ulonglong2(acc[x][v][u], acc[x][v][u + 1]);
+  for (int d = 1; d < kTileH; d <<= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+  }
+}
+
+// Stage descriptor of list entry e for the tile, row part: thread == (entry,
+// row), [lo, hi] from row_range(); (entry, pw) threads add the column weights
+// separately.  Returns false when the entry references more
+// than kMaxPh bin rows (the tile then goes to the inline kernel).
+__device__ __forceinline__ bool write_stage_rows(const RoiFuseParams& p, StageDesc* sd,
+                                                 const ListEntry& e, int4 r, int row, int lo, int hi) {
+  const int nph = hi >= lo ? hi - lo + 1 : 0;
+  if (r.x >= 0) r.x -= lo;
+  sd->rows[row] = r;
+  if (row == 0) {
+    const int k = e.src / p.R, rr = e.src - k * p.R;
+    sd->src_off = nph > 0 ? (k * p.PH * p.PW + lo * p.PW + e.pw0) * (p.R * p.C) + rr * p.C : 0;
+    sd->nph = (short)nph;
+    sd->npw = e.npw;
+  }
+  return nph <= kMaxPh;
+}
+
+// ---- binning kernel: per tile, the ordered list of regions that reach it and
+// one stage descriptor per list entry, written to a pool in the workspace (one
+// atomic allocation per tile; the pool position varies from run to run, the
+// contents and their order do not).  Tiny register footprint -> the
+// latency-bound table walking runs at full occupancy, off the streaming
+// kernel's critical path.  Tiles whose list does not fit (kListCap entries, the
+// pool is exhausted, or an entry spans more than kMaxPh bin rows) are appended
+// to the inline list: roi_bwd_pull_inline builds their lists itself.
+template <int TW>
+__device__ void bin_tile(ListSmem& sm, const RoiFuseParams& p, const PullWs& ws,
+                         const TileMap& tm, int t) {
+  __shared__ int s_off;
+  const int tid = threadIdx.x;
+  const Tile T = decode_tile(p, ws, tm, t, TW);
+  const int total_cand = init_candidates(sm, ws, T.key);
+  const int pos = build_list(sm, p, ws, T, 0, total_cand);
+  const int n = sm.list_n;
+  if (tid == 0) {
+    int off = -1;
+    if (pos >= total_cand) {  // the whole list fits
+      off = 0;
+      if (n > 0) {
+        off = atomicAdd(ws.counters, n);
+        if (off + n > ws.pool_cap) off = -1;
       }
     }
+    s_off = off;
+  }
+  __syncthreads();
+  const int off = s_off;
+  bool ok = off >= 0;
+  if (ok) {
+    for (int c0 = 0; c0 < n; c0 += kChunkR) {
+      const int nc = min(kChunkR, n - c0);
+      {  // thread == (entry, tile row)
+        const int q = tid / kTileH, row = tid - q * kTileH;
+        const int qq = q < nc ? q : 0;  // idle lanes shadow entry 0 (no stores)
+        const ListEntry e = sm.list[c0 + qq];
+        const int4 r = expand_row(ws, e, T.y0 + row);
+        int lo, hi;
+        row_range(r, lo, hi);  // all lanes: the shuffles stay convergent
+        if (q < nc) ok = write_stage_rows(p, ws.pool + off + c0 + q, e, r, row, lo, hi) && ok;
+      }
+      {  // thread == (entry, pw)
+        const int q = tid / kJ, jj = tid - q * kJ;
+        if (q < nc) {
+          const ListEntry e = sm.list[c0 + q];
+          if (jj < e.npw) {
+            float w[TW];
+            expand_col<TW>(ws, e, jj, T.x0, w);
+            float* o = ws.pool[off + c0 + q].cw[jj];
+#pragma unroll
+            for (int x = 0; x < TW; x += 4)
+              *reinterpret_cast<float4*>(o + x) = make_float4(w[x], w[x + 1], w[x + 2], w[x + 3]);
+          }
+        }
+      }
+    }
+  }
+  ok = __syncthreads_and(ok);
+  if (tid == 0) {
+    ws.tile_desc[tm.tile_base + t] = make_int2(off, ok ? n : -1);
+    if (!ok) ws.inline_list[atomicAdd(ws.counters + 2, 1)] = tm.tile_base + t;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+roi_bin_kernel(const RoiFuseParams p, const PullWs ws, const TileMap tm4, const TileMap tm8, int nt4) {
+  __shared__ ListSmem sm;
+  if ((int)blockIdx.x < nt4) bin_tile<4>(sm, p, ws, tm4, blockIdx.x);
+  else bin_tile<8>(sm, p, ws, tm8, blockIdx.x - nt4);
+}
+
+// ------------------------------------------------------ mbarrier / bulk copy
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) {
+  return (uint32_t)__cvta_generic_to_shared(ptr);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// global -> shared bulk copy (TMA, no tensor map): 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ------------------------------------------------------------ pull kernel
+// CTA == (tile of 8 rows x TW columns, group of 32 * V channels); 8 consumer
+// warps (warp == tile row, lanes == channels) + 1 producer warp.
+//
+// The bilinear sum is separable: a gradient pixel (y, x) of a region receives
+//     sum_ph ry[ph][y] * sum_pw cx[pw][x] * dout[ph][pw]
+// with ry / cx the aggregated row / column weights.  For every listed region
+// (stage) the PRODUCER copies the bins [ph_lo, +nph) x [pw0, +npw) of the
+// region's dout block that reach the tile -- each bin's channel group is one
+// contiguous piece -- plus the 400-byte stage descriptor into a shared-memory
+// byte ring with bulk async copies (TMA) signalling the stage's mbarrier; it
+// runs up to kNSlot stages / kRing bytes ahead, so the loads of many regions
+// are in flight without holding registers.  Every bin is fetched once per tile
+// and shared by the 8 rows.  A CONSUMER warp combines, per output column, the
+// (<= 2) bins sampling its row with the row weights and adds the result to its
+// TW pixels with that column's weights (zero where it does not reach): FFMA2
+// arithmetic on shared-memory operands, accumulators in registers, every
+// gradient element written once -- no atomics, no zero-fill, deterministic.
+constexpr int kNSlot = 16;
+constexpr int kPullThreads = 288;
+constexpr int kDescBytes = (int)sizeof(StageDesc);
+constexpr int kPullCtl = 512;  // full[16] + empty[16] barriers, stage offsets
+
+template <typename T, int TW>
+__global__ void __launch_bounds__(kPullThreads, (TW * VecOf<T>::n <= 32 ? 3 : 2))
+roi_bwd_pull_tma(const RoiFuseParams p, const PullWs ws, const TileMap tm, int ring_bytes) {
+  constexpr int V = VecOf<T>::n;
+  constexpr int V2 = V / 2;
+  constexpr int CG = 32 * V;  // channels per group
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + kNSlot;
+  uint32_t* stage_off = reinterpret_cast<uint32_t*>(smem + 2 * kNSlot * 8);
+  StageDesc* desc = reinterpret_cast<StageDesc*>(smem + kPullCtl);
+  unsigned char* ring = smem + kPullCtl + kNSlot * kDescBytes;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int t = blockIdx.x / tm.groups, grp = blockIdx.x - t * tm.groups;
+  const int2 td = ws.tile_desc[tm.tile_base + t];
+  if (td.y < 0) return;  // served by roi_bwd_pull_inline
+  const int n = td.y;
+  const Tile tl = decode_tile(p, ws, tm, t, TW);
+  const int C = p.C, RC = p.R * C;
+  const int c0 = grp * CG;
+  const int cg = min(CG, C - c0);               // channels actually staged per bin
+  const uint32_t bin_bytes = (uint32_t)cg * sizeof(T);
+  const StageDesc* __restrict__ gdesc = ws.pool + td.x;
+
+  if (tid == 0) {
+    for (int i = 0; i < kNSlot; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, kTileH); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kTileH) {
+    // ------------------------------------------------------------ producer
+    uint32_t head = 0, tail = 0;  // live bytes of the ring: [tail, head) modulo wrap
+    uint32_t my_off = 0;          // lane j: ring offset of the stage in slot j
+    int released = 0;             // stages known to be consumed
+    const T* __restrict__ dsrc = static_cast<const T*>(p.dout) + c0;
+    int4 hdr = make_int4(0, 0, 0, 0);
+    for (int i = 0; i < n; ++i) {
+      if ((i & 31) == 0 && i + lane < n) hdr = __ldg(reinterpret_cast<const int4*>(gdesc + i + lane));
+      const int src_off = __shfl_sync(0xffffffffu, hdr.x, i & 31);
+      const int nn = __shfl_sync(0xffffffffu, hdr.y, i & 31);
+      const int nph = nn & 0xffff, npw = (nn >> 16) & 0xffff;
+      const int nbins = nph * npw;
+      const uint32_t bytes = (uint32_t)nbins * bin_bytes;
+      const int slot = i % kNSlot;
+      // the slot's previous stage and enough ring space must have been released
+      // (stages are released in order)
+      auto release_one = [&]() {
+        mbar_wait(empty + (released % kNSlot), (released / kNSlot) & 1);
+        ++released;
+        const uint32_t nxt = __shfl_sync(0xffffffffu, my_off, released % kNSlot);
+        tail = released < i ? nxt : head;
+      };
+      while (released < i - kNSlot + 1) release_one();
+      uint32_t off;
+      while (true) {
+        if (released == i) { head = tail = 0; off = 0; break; }           // ring empty
+        if (head >= tail) {
+          if (head + bytes <= (uint32_t)ring_bytes) { off = head; break; }
+          if (bytes < tail) { off = 0; break; }                            // wrap
+        } else if (head + bytes < tail) { off = head; break; }
+        release_one();
+      }
+      head = off + bytes;
+      if (lane == slot) my_off = off;
+      if (lane == 0) {
+        stage_off[slot] = off;
+        mbar_arrive_expect_tx(full + slot, bytes + kDescBytes);
+        bulk_g2s(desc + slot, gdesc + i, kDescBytes, full + slot);
+      }
+      for (int bi = lane; bi < nbins; bi += 32) {
+        const int ih = bi / npw, iw = bi - ih * npw;
+        bulk_g2s(ring + off + (uint32_t)bi * bin_bytes,
+                 dsrc + (size_t)src_off + (size_t)(ih * p.PW + iw) * RC, bin_bytes, full + slot);
+      }
+    }
+    return;
+  }
+
+  // ---------------------------------------------------------------- consumers
+  const int y = tl.y0 + warp;
+  const int cl = c0 + lane * V;
+  const bool act = y <= tl.y1 && cl < C;
+  uint64_t acc[TW][V2];
+#pragma unroll
+  for (int x = 0; x < TW; ++x)
+#pragma unroll
+    for (int u = 0; u < V2; ++u) acc[x][u] = 0ull;
+
+  for (int i = 0; i < n; ++i) {
+    const int slot = i % kNSlot;
+    mbar_wait(full + slot, (i / kNSlot) & 1);
+    const StageDesc& d = desc[slot];
+    const int4 rd = d.rows[warp];
+    if (act && rd.x >= 0) {
+      const int npw = d.npw;
+      const float a0 = __int_as_float(rd.z), a1 = __int_as_float(rd.w);
+      const uint64_t a0p = pack2(a0, a0), a1p = pack2(a1, a1);
+      const unsigned char* __restrict__ s0 =
+          ring + stage_off[slot] + (uint32_t)(rd.x * npw) * bin_bytes + (uint32_t)(lane * V) * sizeof(T);
+      const uint32_t two_step = rd.y ? (uint32_t)npw * bin_bytes : 0u;
+#pragma unroll 2
+      for (int jj = 0; jj < npw; ++jj) {
+        uint64_t e[V2], e1[V2];
+        lds_pairs<T>(s0, e);
+#pragma unroll
+        for (int u = 0; u < V2; ++u) e[u] = mul2(e[u], a0p);
+        if (rd.y) {
+          lds_pairs<T>(s0 + two_step, e1);
+#pragma unroll
+          for (int u = 0; u < V2; ++u) e[u] = fma2(e1[u], a1p, e[u]);
+        }
+        float w[TW];
+#pragma unroll
+        for (int x = 0; x < TW; x += 4) {
+          const float4 t4 = *reinterpret_cast<const float4*>(d.cw[jj] + x);
+          w[x] = t4.x; w[x + 1] = t4.y; w[x + 2] = t4.z; w[x + 3] = t4.w;
+        }
+#pragma unroll
+        for (int x = 0; x < TW; ++x) {
+          const uint64_t wp = pack2(w[x], w[x]);
+#pragma unroll
+          for (int u = 0; u < V2; ++u) acc[x][u] = fma2(e[u], wp, acc[x][u]);
+        }
+        s0 += bin_bytes;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + slot);
+  }
+  // ---- every element of the tile written exactly once ----
+  if (act) {
+    float* __restrict__ dimg = p.dfeats[tl.l] + (size_t)tl.b * tl.H * tl.W * C;
+#pragma unroll
+    for (int x = 0; x < TW; ++x) {
+      if (tl.x0 + x > tl.x1) continue;
+      float* __restrict__ o = dimg + ((size_t)y * tl.W + tl.x0 + x) * C + cl;
+#pragma unroll
+      for (int u = 0; u < V2; u += 2)
+        *reinterpret_cast<ulonglong2*>(o + 2 * u) = make_ulonglong2(acc[x][u], acc[x][u + 1]);
+    }
+  }
+}
+
+// ---- inline kernel: the tiles the binning kernel could not serve.  A small
+// fixed grid walks the inline list; per tile and channel group: rounds of list
+// building, expansion into shared memory and streaming from global memory.
+template <typename T, int TW>
+__device__ void pull_tile_inline(const RoiFuseParams& p, const PullWs& ws, const TileMap& tm, int t,
+                                 ListSmem& sm, int4* rdesc, float* cwt) {
+  constexpr int V = VecOf<T>::n;
+  constexpr int V2 = V / 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const Tile tl = decode_tile(p, ws, tm, t, TW);
+  const int C = p.C, RC = p.R * C, rowstep = p.PW * RC;
+  const int y = tl.y0 + warp;
+  for (int c0 = 0; c0 < C; c0 += 32 * V) {
+    const int cl = c0 + lane * V;
+    const bool act = y <= tl.y1 && cl < C;
+    const T* __restrict__ dbase = static_cast<const T*>(p.dout) + cl;
+    uint64_t acc[TW][V2];
+#pragma unroll
+    for (int x = 0; x < TW; ++x)
+#pragma unroll
+      for (int u = 0; u < V2; ++u) acc[x][u] = 0ull;
+    __syncthreads();
+    const int total_cand = init_candidates(sm, ws, tl.key);
+    int pos = 0;
+    while (pos < total_cand) {
+      pos = build_list(sm, p, ws, tl, pos, total_cand);
+      const int n = sm.list_n;
+      for (int q0 = 0; q0 < n; q0 += kChunkR) {
+        const int nc = min(kChunkR, n - q0);
+        {  // thread == (tile row, entry)
+          const int row = tid / kChunkR, q = tid - row * kChunkR;
+          int4 d = make_int4(-1, 0, 0, 0);
+          if (q < nc) {
+            const ListEntry e = sm.list[q0 + q];
+            d = expand_row(ws, e, tl.y0 + row);
+            if (d.x >= 0) {  // -> {dout offset of (p0, pw0), npw | two << 8, w0, w1}
+              const int k = e.src / p.R, r = e.src - k * p.R;
+              d.x = (k * p.PH * p.PW + d.x * p.PW + e.pw0) * RC + r * C;
+              d.y = e.npw | (d.y ? 256 : 0);
+            }
+          }
+          rdesc[row * kChunkR + q] = d;
+        }
+        {  // thread == (entry, pw)
+          const int q = tid / kJ, jj = tid - q * kJ;
+          if (q < nc) {
+            const ListEntry e = sm.list[q0 + q];
+            if (jj < e.npw) {
+              float w[TW];
+              expand_col<TW>(ws, e, jj, tl.x0, w);
+#pragma unroll
+              for (int x = 0; x < TW; x += 4)
+                *reinterpret_cast<float4*>(cwt + tid * TW + x) = make_float4(w[x], w[x + 1], w[x + 2], w[x + 3]);
+            }
+          }
+        }
+        __syncthreads();
+        if (act) {
+          const int4* __restrict__ pr = rdesc + warp * kChunkR;
+          for (int q = 0; q < nc; ++q) {
+            const int4 cur = pr[q];
+            if (cur.x < 0) continue;
+            const int npw = cur.y & 255;
+            const bool two = (cur.y & 256) != 0;
+            const float a0 = __int_as_float(cur.z), a1 = __int_as_float(cur.w);
+            const uint64_t a0p = pack2(a0, a0), a1p = pack2(a1, a1);
+            const T* __restrict__ src = dbase + cur.x;
+            const float* __restrict__ cw = cwt + q * (kJ * TW);
+            for (int jj = 0; jj < npw; ++jj) {
+              uint64_t e[V2], e1[V2];
+              ldg_pairs<T>(src, e);
+#pragma unroll
+              for (int u = 0; u < V2; ++u) e[u] = mul2(e[u], a0p);
+              if (two) {
+                ldg_pairs<T>(src + rowstep, e1);
+#pragma unroll
+                for (int u = 0; u < V2; ++u) e[u] = fma2(e1[u], a1p, e[u]);
+              }
+#pragma unroll
+              for (int x = 0; x < TW; ++x) {
+                const uint64_t wp = pack2(cw[x], cw[x]);
+#pragma unroll
+                for (int u = 0; u < V2; ++u) acc[x][u] = fma2(e[u], wp, acc[x][u]);
+              }
+              src += RC;
+              cw += TW;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (act) {
+      float* __restrict__ dimg = p.dfeats[tl.l] + (size_t)tl.b * tl.H * tl.W * C;
+#pragma unroll
+      for (int x = 0; x < TW; ++x) {
+        if (tl.x0 + x > tl.x1) continue;
+        float* __restrict__ o = dimg + ((size_t)y * tl.W + tl.x0 + x) * C + cl;
+#pragma unroll
+        for (int u = 0; u < V2; u += 2)
+          *reinterpret_cast<ulonglong2*>(o + 2 * u) = make_ulonglong2(acc[x][u], acc[x][u + 1]);
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+roi_bwd_pull_inline(const RoiFuseParams p, const PullWs ws, const TileMap tm4, const TileMap tm8, int nt4) {
+  __shared__ ListSmem sm;
+  __shared__ int4 rdesc[kTileH * kChunkR];
+  __shared__ __align__(16) float cwt[kChunkR * kJ * kMaxTW];
+  const int n = ws.counters[2];
+  for (int j = blockIdx.x; j < n; j += gridDim.x) {
+    const int t = ws.inline_list[j];
+    if (t < nt4) pull_tile_inline<T, 4>(p, ws, tm4, t, sm, rdesc, cwt);
+    else pull_tile_inline<T, 8>(p, ws, tm8, t - nt4, sm, rdesc, cwt);
+    __syncthreads();
   }
 }
 
@@ -836,72 +1227,85 @@ cudaError_t launch_roi_fuse_forward_cl(const RoiFuseParams& p, int dtype, int ou
   return cudaGetLastError();
 }
 
-size_t roi_pull_workspace_bytes(int K, int R, int L, int B, const int* H) {
-  return pull_ws_layout(K * R, L, B, H, nullptr, nullptr);
+size_t roi_pull_workspace_bytes(int K, int R, int L, int B, const int* H, const int* W) {
+  return pull_ws_layout(K * R, L, B, H, W, nullptr, nullptr);
 }
 
 // dout: channels-last [K][PH*PW][R*C]; dfeats: NHWC fp32, fully written.
-// `flags_out` (host side) is not needed: regions whose tables did not fit are
-// flagged in the workspace and added afterwards by the atomic kernel.
+// Regions whose tables did not fit are flagged in the workspace and added
+// afterwards by the atomic kernel.
 cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, void* workspace,
                                           size_t workspace_bytes, cudaStream_t stream) {
   const int N = p.K * p.R;
   PullWs ws;
-  const size_t need = pull_ws_layout(N, p.L, p.B, p.H, static_cast<unsigned char*>(workspace), &ws);
+  const size_t need = pull_ws_layout(N, p.L, p.B, p.H, p.W, static_cast<unsigned char*>(workspace), &ws);
   if (need > workspace_bytes) return cudaErrorInvalidValue;
   const int prep_smem = ws.nkeys * (kPrepBlock / 32) * 4;
   if (prep_smem > 160 * 1024 || ws.nblk > kMaxPrepBlocks) return cudaErrorInvalidValue;
+  if ((long long)p.K * p.PH * p.PW * p.R * p.C > 0x7fffffffLL) return cudaErrorInvalidValue;  // 32-bit dout offsets
   cudaError_t e = set_smem(roi_prep_kernel, prep_smem);
   if (e != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ws.counters, 0, 16, stream)) != cudaSuccess) return e;
   roi_prep_kernel<<<ws.nblk + N, kPrepBlock, prep_smem, stream>>>(p, ws);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  // Two launches: the small upper-level maps carry ~40x more region-pixels per
-  // tile than level 0, so they get narrow tiles + a channel split and go first
-  // (heaviest level first inside each launch); the big maps follow with wide tiles.
+  // Two tile shapes: the small upper-level maps carry ~40x more region-pixels per
+  // tile than level 0, so they get narrow tiles and go first (heaviest level
+  // first inside each launch); the big maps follow with wide tiles.
   const int V = dtype == 0 ? 4 : 8;
-  if ((long long)p.K * p.PH * p.PW * p.R * p.C > 0x7fffffffLL) return cudaErrorInvalidValue;  // 32-bit dout offsets
-  auto heavy = [&](int l) { return (long long)p.H[l] * p.W[l] <= 64 * 96; };
+  TileMap tm[2];
+  int ntiles[2];
+  int tile_base = 0;
   for (int pass = 0; pass < 2; ++pass) {
     const int tw = pass == 0 ? 4 : 8;
-    const int nv = (pass == 0 || dtype != 0) ? 1 : ((p.C % (64 * V) == 0) ? 2 : 1);
-    TileMap tm;
+    TileMap& m = tm[pass];
     int total = 0, ns = 0;
-    tm.groups = (p.C + 32 * V * nv - 1) / (32 * V * nv);
+    m.groups = (p.C + 32 * V - 1) / (32 * V);
     for (int l = p.L - 1; l >= 0; --l) {
-      if (heavy(l) != (pass == 0)) continue;
-      tm.start[ns] = total;
-      tm.level[ns] = l;
-      tm.tiles_x[ns] = (p.W[l] + tw - 1) / tw;
-      tm.tiles_y[ns] = (p.H[l] + kTileH - 1) / kTileH;
-      total += tm.tiles_x[ns] * tm.tiles_y[ns] * p.B * tm.groups;
+      if (pull_heavy(p.H[l], p.W[l]) != (pass == 0)) continue;
+      m.tstart[ns] = total;
+      m.level[ns] = l;
+      m.tiles_x[ns] = (p.W[l] + tw - 1) / tw;
+      m.tiles_y[ns] = (p.H[l] + kTileH - 1) / kTileH;
+      total += m.tiles_x[ns] * m.tiles_y[ns] * p.B;
       ++ns;
     }
-    tm.nslots = ns;
-    for (int j2 = ns; j2 <= kMaxLevels; ++j2) tm.start[j2] = total;
-    for (int j2 = ns; j2 < kMaxLevels; ++j2) { tm.level[j2] = 0; tm.tiles_x[j2] = tm.tiles_y[j2] = 1; }
-    if (total == 0) continue;
-    if (pass == 0) {
-      if (dtype == 0) roi_bwd_pull<float, 1, 4><<<total, kThreads, 0, stream>>>(p, ws, tm);
-      else roi_bwd_pull<__nv_bfloat16, 1, 4><<<total, kThreads, 0, stream>>>(p, ws, tm);
-    } else if (nv == 2) {
-      roi_bwd_pull<float, 2, 8><<<total, kThreads, 0, stream>>>(p, ws, tm);
-    } else {
-      if (dtype == 0) roi_bwd_pull<float, 1, 8><<<total, kThreads, 0, stream>>>(p, ws, tm);
-      else roi_bwd_pull<__nv_bfloat16, 1, 8><<<total, kThreads, 0, stream>>>(p, ws, tm);
-    }
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    m.nslots = ns;
+    for (int j2 = ns; j2 <= kMaxLevels; ++j2) m.tstart[j2] = total;
+    for (int j2 = ns; j2 < kMaxLevels; ++j2) { m.level[j2] = 0; m.tiles_x[j2] = m.tiles_y[j2] = 1; }
+    m.tile_base = tile_base;
+    tile_base += total;
+    ntiles[pass] = total;
   }
-  return cudaSuccess;
+  if (ntiles[0] + ntiles[1] == 0) return cudaSuccess;
+  roi_bin_kernel<<<ntiles[0] + ntiles[1], kThreads, 0, stream>>>(p, ws, tm[0], tm[1], ntiles[0]);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  const int ring = 64 * 1024;
+  const int smem = kPullCtl + kNSlot * kDescBytes + ring;
+#define ARFE_PULL(TT, TWW, PASS)                                                                   \
+  do {                                                                                             \
+    if ((e = set_smem(roi_bwd_pull_tma<TT, TWW>, smem)) != cudaSuccess) return e;                  \
+    roi_bwd_pull_tma<TT, TWW><<<ntiles[PASS] * tm[PASS].groups, kPullThreads, smem, stream>>>(     \
+        p, ws, tm[PASS], ring);                                                                    \
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;                                         \
+  } while (0)
+  if (ntiles[0] > 0) { if (dtype == 0) ARFE_PULL(float, 4, 0); else ARFE_PULL(__nv_bfloat16, 4, 0); }
+  if (ntiles[1] > 0) { if (dtype == 0) ARFE_PULL(float, 8, 1); else ARFE_PULL(__nv_bfloat16, 8, 1); }
+#undef ARFE_PULL
+  const int igrid = ntiles[0] + ntiles[1] < 148 ? ntiles[0] + ntiles[1] : 148;
+  if (dtype == 0) roi_bwd_pull_inline<float><<<igrid, kThreads, 0, stream>>>(p, ws, tm[0], tm[1], ntiles[0]);
+  else roi_bwd_pull_inline<__nv_bfloat16><<<igrid, kThreads, 0, stream>>>(p, ws, tm[0], tm[1], ntiles[0]);
+  return cudaGetLastError();
 }
 
-// Device pointer to the per-region headers inside a laid-out workspace (the
-// atomic fallback kernel reads the `flags` field).
-const void* roi_pull_headers(int K, int R, int L, int B, const int* H, void* workspace) {
+// Device pointer to the list of regions whose tables did not fit (the atomic
+// fallback kernel walks it).
+const int* roi_pull_flag_list(int K, int R, int L, int B, const int* H, const int* W, void* workspace,
+                              const int** count) {
   PullWs ws;
-  pull_ws_layout(K * R, L, B, H, static_cast<unsigned char*>(workspace), &ws);
-  return ws.hdr;
+  pull_ws_layout(K * R, L, B, H, W, static_cast<unsigned char*>(workspace), &ws);
+  *count = ws.counters + 1;
+  return ws.flag_list;
 }
 
 }  // namespace arfe

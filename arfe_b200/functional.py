@@ -88,7 +88,8 @@ class _RoIFuseFunction(Function):
         if fast and K > 0:
             # pull kernel: channels-last dout, every gradient element written once
             g = g.contiguous(memory_format=torch.channels_last)
-            nbytes = lib.arfe_roi_fuse_pull_workspace_bytes(K, regions, nlev, B, L.int_array(Hs))
+            nbytes = lib.arfe_roi_fuse_pull_workspace_bytes(K, regions, nlev, B, L.int_array(Hs),
+                                                            L.int_array(Ws))
             ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
             ws_ptr = (ws.data_ptr() + 255) // 256 * 256
             dfeats = [torch.empty((B, C, Hs[l], Ws[l]), dtype=torch.float32, device=dev,

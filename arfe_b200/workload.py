@@ -142,7 +142,8 @@ class TrainStep:
         self.dg2 = [e(B, 1, h, w, dtype=torch.float32) for h, w in self.shapes]
         self.dx = [e(B, C, h, w) for h, w in self.shapes]
         self.ws_bytes = self.lib.arfe_roi_fuse_pull_workspace_bytes(
-            K, R, self.nlev, B, L.int_array([s[0] for s in self.shapes]))
+            K, R, self.nlev, B, L.int_array([s[0] for s in self.shapes]),
+            L.int_array([s[1] for s in self.shapes]))
         self.ws = torch.empty(self.ws_bytes + 256, dtype=torch.uint8, device=device)
         self.ws_ptr = (self.ws.data_ptr() + 255) // 256 * 256
         # C arrays built once

@@ -111,7 +111,7 @@ int arfe_roi_fuse_backward(const void* dout, int dout_layout, const int32_t* H,
  * bytes, 256-byte aligned, owned by the caller, reusable after the stream
  * passes this call. */
 size_t arfe_roi_fuse_pull_workspace_bytes(int K, int regions, int L, int B,
-                                          const int32_t* H);
+                                          const int32_t* H, const int32_t* W);
 int arfe_roi_fuse_backward_pull(const void* dout, const int32_t* H, const int32_t* W,
                                 const float* spatial_scale, int L, int B, int C,
                                 const float* rois, int K, int regions, float facs,

@@ -56,8 +56,10 @@ def test_argument_errors_need_no_gpu():
                                    0, 56.0, 0, 0, 1, None, None, None, None)
     assert rc in (-1, -5)
     H5 = L.int_array([200, 100, 50, 25, 13])
-    assert lib.arfe_roi_fuse_pull_workspace_bytes(1024, 3, 5, 2, H5) > 0
-    assert lib.arfe_roi_fuse_pull_workspace_bytes(0, 3, 5, 2, H5) == 0
+    W5 = L.int_array([336, 168, 84, 42, 21])
+    assert lib.arfe_roi_fuse_pull_workspace_bytes(1024, 3, 5, 2, H5, W5) > 0
+    assert lib.arfe_roi_fuse_pull_workspace_bytes(0, 3, 5, 2, H5, W5) == 0
+    assert lib.arfe_roi_fuse_pull_workspace_bytes(1024, 3, 5, 2, H5, None) == 0
     # aligned=False is the legacy path
     rc = lib.arfe_roi_align_forward(None, None, 0.25, 7, 7, 0, 0, 1, 4, 8, 8, 0, 0, 0, None, None)
     assert rc == -5
