@@ -114,6 +114,43 @@ __device__ __forceinline__ void lds_pairs(const unsigned char* __restrict__ p, u
   }
 }
 
+// ------------------------------------------------------ mbarrier / bulk copy
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) {
+  return (uint32_t)__cvta_generic_to_shared(ptr);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// global -> shared bulk copy (TMA, no tensor map): 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ------------------------------------------------------------------ forward
 // One bin, VEC channels per lane: rows x NC taps, NC loads in flight per row.
 // `rstep` = +1 walks the bin's rows top-down, -1 bottom-up (base / wy then
@@ -186,6 +223,53 @@ __device__ __forceinline__ void cl_bin_any(const T* __restrict__ base, size_t ro
   }
 }
 
+// Direct (L1-cached loads) channels-last forward of one region:
+// warp == (bin row ph, channel chunk): the warps of neighbouring bin rows run
+// side by side and walk their rows in opposite directions (even ph top-down,
+// odd ph bottom-up), so the feature row two bin rows share is touched by
+// both at about the same time and the second touch hits L1.
+template <typename T>
+__device__ void fwd_direct_cl(const RoiFuseParams& p, const CtaHeader& hd, const AxisTable& ty,
+                              const AxisTable& tx, int k, int r, int nwarps) {
+  constexpr int V = VecOf<T>::n;
+  constexpr int V2 = V / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= nwarps) return;
+  const int PH = p.PH, PW = p.PW, C = p.C, RC = p.R * C;
+  const int H = hd.H, W = hd.W;
+  const float inv_count = 1.0f / hd.g.count;
+  const uint64_t inv2 = pack2(inv_count, inv_count);
+  const T* __restrict__ fimg =
+      static_cast<const T*>(p.feats[hd.lvl]) + (size_t)hd.g.batch * H * W * C;
+  const size_t rowstride = (size_t)W * C;
+  const int cw = 32 * V;  // channels per warp pass
+  T* __restrict__ out = static_cast<T*>(p.out);
+  const int nchunk = (C + cw - 1) / cw;
+  for (int item = warp; item < PH * nchunk; item += nwarps) {
+    const int chunk = item / PH, ph = item - chunk * PH;
+    const int c = chunk * cw + lane * V;
+    if (c >= C) continue;
+    const int nr = ty.cnt[ph];
+    const float* __restrict__ wy = ty.w + ty.off[ph];
+    const bool up = (ph & 1) != 0;
+    const T* __restrict__ rowbase = fimg + (size_t)ty.first[ph] * rowstride + c;
+    T* __restrict__ o = out + ((size_t)k * PH * PW + ph * PW) * RC + (size_t)r * C + c;
+    for (int pw = 0; pw < PW; ++pw) {
+      const int nc = tx.cnt[pw];
+      uint64_t acc[V2];
+#pragma unroll
+      for (int u = 0; u < V2; ++u) acc[u] = 0ull;
+      if (nr > 0 && nc > 0)
+        cl_bin_any<T>(rowbase + (size_t)tx.first[pw] * C, rowstride, C, wy, nr, up,
+                      tx.w + tx.off[pw], nc, acc);
+      float f[V];
+#pragma unroll
+      for (int u = 0; u < V2; ++u) unpack2(mul2(acc[u], inv2), f[2 * u], f[2 * u + 1]);
+      st_vec<T>(o + (size_t)pw * RC, f);
+    }
+  }
+}
+
 // dynamic smem: [CtaHeader][AxisTable y][AxisTable x][outs: bins_per_pass * opitch] (NCHW out only)
 template <typename T, bool kOutCL, int kOcc>
 __global__ void __launch_bounds__(kThreads, kOcc)
@@ -252,34 +336,7 @@ roi_fuse_fwd_cl(const RoiFuseParams p, int opitch, int bins_per_pass) {
   const float2 icp = make_float2(inv_count, inv_count);
   const uint64_t inv2 = pack2(icp.x, icp.y);
   if constexpr (kOutCL) {
-    // warp == (bin row ph, channel chunk): the warps of neighbouring bin rows run
-    // side by side and walk their rows in opposite directions (even ph top-down,
-    // odd ph bottom-up), so the feature row two bin rows share is touched by
-    // both at about the same time and the second touch hits L1.
-    const int nchunk = (C + cw - 1) / cw;
-    for (int item = warp; item < PH * nchunk; item += kWarps) {
-      const int chunk = item / PH, ph = item - chunk * PH;
-      const int c = chunk * cw + lane * V;
-      if (c >= C) continue;
-      const int nr = ty.cnt[ph];
-      const float* __restrict__ wy = ty.w + ty.off[ph];
-      const bool up = (ph & 1) != 0;
-      const T* __restrict__ rowbase = fimg + (size_t)ty.first[ph] * rowstride + c;
-      T* __restrict__ o = out + out_index(ph * PW, c);
-      for (int pw = 0; pw < PW; ++pw) {
-        const int nc = tx.cnt[pw];
-        uint64_t acc[V2];
-#pragma unroll
-        for (int u = 0; u < V2; ++u) acc[u] = 0ull;
-        if (nr > 0 && nc > 0)
-          cl_bin_any<T>(rowbase + (size_t)tx.first[pw] * C, rowstride, C, wy, nr, up,
-                        tx.w + tx.off[pw], nc, acc);
-        float f[V];
-#pragma unroll
-        for (int u = 0; u < V2; ++u) unpack2(mul2(acc[u], inv2), f[2 * u], f[2 * u + 1]);
-        st_vec<T>(o + (size_t)pw * RC, f);
-      }
-    }
+    fwd_direct_cl<T>(p, hd, ty, tx, k, r, kWarps);
   } else {
   for (int b0 = 0; b0 < PHW; b0 += bins_per_pass) {
     const int b1 = min(PHW, b0 + bins_per_pass);
@@ -314,6 +371,204 @@ roi_fuse_fwd_cl(const RoiFuseParams p, int opitch, int bins_per_pass) {
   }
 }
 
+// ---------------------------------------------------------- forward (TMA)
+// One CTA per (RoI, region), channels-last in and out.  In NHWC a row of the
+// region's sampling window (wlen pixels x C channels) is ONE contiguous piece of
+// memory, so a producer warp streams the window row by row into a shared-memory
+// ring with bulk async copies (TMA) signalling an mbarrier per row; several rows
+// are in flight without holding registers and every window byte crosses
+// L2 -> SM exactly once (the L1-cached kernel above re-fetches ~1.5x).
+// Consumer warp == (output column pw, channel chunk): per row it folds its
+// (<= 8) column taps into t = sum_j wx[j] * f[row][x0 + j] from shared memory
+// and adds wy[ph][row] * t to the (usually <= 2) bin rows ph that sample the
+// row (dense row-weight matrix, zero weights skipped); its PH accumulators
+// stay in registers and are written once at the end.
+// Regions the ring cannot serve (window wider than half the ring, more than
+// kFwdMaxRows rows, a column with more than 8 taps, overflowing tables) take
+// the direct path above inside the same kernel.
+constexpr int kFwdSlots = 8;
+constexpr int kFwdMaxRows = 64;
+constexpr int kFwdTaps = 8;
+constexpr int kFwdCopy = 8192;  // bytes per bulk copy
+
+// dynamic smem: [CtaHeader][AxisTable y][AxisTable x][roww: kFwdMaxRows x PHP][barriers][ring]
+template <typename T>
+__device__ __noinline__ void fwd_direct_cl_call(const RoiFuseParams& p, const CtaHeader& hd,
+                                                const AxisTable& ty, const AxisTable& tx, int k,
+                                                int r, int nwarps) {
+  fwd_direct_cl<T>(p, hd, ty, tx, k, r, nwarps);
+}
+
+template <typename T, int PH>
+__global__ void __launch_bounds__(512, (PH * VecOf<T>::n <= 32 ? 2 : 1))
+roi_fuse_fwd_tma(const RoiFuseParams p, int ncons, int ring_bytes) {
+  constexpr int V = VecOf<T>::n;
+  constexpr int V2 = V / 2;
+  constexpr int PHP = (PH + 3) / 4 * 4;
+  extern __shared__ __align__(16) unsigned char smem[];
+  CtaHeader& hd = *reinterpret_cast<CtaHeader*>(smem);
+  AxisTable& ty = *reinterpret_cast<AxisTable*>(smem + 128);
+  AxisTable& tx = *reinterpret_cast<AxisTable*>(smem + 128 + sizeof(AxisTable));
+  float* roww = reinterpret_cast<float*>(smem + kHdrBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kHdrBytes + kFwdMaxRows * PHP * 4);
+  uint64_t* empty = full + kFwdSlots;
+  unsigned char* ring = reinterpret_cast<unsigned char*>(empty + kFwdSlots);
+
+  const int k = blockIdx.x / p.R, r = blockIdx.x % p.R;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int PW = p.PW, PHW = PH * PW, C = p.C, RC = p.R * C;
+  T* __restrict__ out = static_cast<T*>(p.out);
+
+  const bool live = setup_cta(p, k, r, hd, ty, tx);
+  if (!live || hd.overflow) {
+    T* __restrict__ o = out + (size_t)k * PHW * RC + (size_t)r * C;
+    if (live) {  // tables did not fit: reference loop order, direct taps
+      const T* __restrict__ f = static_cast<const T*>(p.feats[hd.lvl]);
+      const int H = hd.H, W = hd.W;
+      const RoiGeom g = hd.g;
+      for (int e = tid; e < C * PHW; e += (int)blockDim.x) {
+        const int bin = e / C, c = e - bin * C;
+        const int ph = bin / PW, pw = bin % PW;
+        float acc = 0.f;
+        for (int iy = 0; iy < g.grid_h; ++iy) {
+          AxisTap a = axis_sample(g.start_h, ph, g.bin_h, iy, g.grid_h, H);
+          if (a.lo < 0) continue;
+          for (int ix = 0; ix < g.grid_w; ++ix) {
+            AxisTap b = axis_sample(g.start_w, pw, g.bin_w, ix, g.grid_w, W);
+            if (b.lo < 0) continue;
+            const size_t base = (size_t)g.batch * H * W;
+            acc += a.wl * b.wl * to_f(f[(base + (size_t)a.lo * W + b.lo) * C + c]) +
+                   a.wl * b.wh * to_f(f[(base + (size_t)a.lo * W + b.hi) * C + c]) +
+                   a.wh * b.wl * to_f(f[(base + (size_t)a.hi * W + b.lo) * C + c]) +
+                   a.wh * b.wh * to_f(f[(base + (size_t)a.hi * W + b.hi) * C + c]);
+          }
+        }
+        o[(size_t)bin * RC + c] = from_f<T>(__fdiv_rn(acc, g.count));
+      }
+    } else {
+      for (int e = tid; e < C * PHW; e += (int)blockDim.x) {
+        const int bin = e / C, c = e - bin * C;
+        o[(size_t)bin * RC + c] = from_f<T>(0.f);
+      }
+    }
+    return;
+  }
+
+  const int nrows = hd.ymax - hd.ymin + 1, wlen = hd.xmax - hd.xmin + 1;
+  const uint32_t row_bytes = (uint32_t)wlen * C * sizeof(T);
+  int maxc = 0;
+  for (int q = 0; q < PW; ++q) maxc = max(maxc, tx.cnt[q]);
+  const int ns = min(kFwdSlots, (int)(ring_bytes / row_bytes));
+  if (ns < 2 || nrows > kFwdMaxRows || maxc > kFwdTaps) {
+    fwd_direct_cl_call<T>(p, hd, ty, tx, k, r, ncons);
+    return;
+  }
+
+  // dense row weights (carry 1 / count), barriers
+  const float inv_count = 1.0f / hd.g.count;
+  for (int e = tid; e < nrows * PHP; e += (int)blockDim.x) {
+    const int i = e / PHP, ph = e - i * PHP;
+    float w = 0.f;
+    if (ph < PH) {
+      const int j = hd.ymin + i - ty.first[ph];
+      if (j >= 0 && j < ty.cnt[ph]) w = ty.w[ty.off[ph] + j] * inv_count;
+    }
+    roww[e] = w;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < kFwdSlots; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, ncons); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int H = hd.H, W = hd.W;
+  const T* __restrict__ fimg =
+      static_cast<const T*>(p.feats[hd.lvl]) + (size_t)hd.g.batch * H * W * C;
+
+  if (warp == ncons) {
+    // ------------------------------------------------------------ producer
+    const unsigned char* __restrict__ src =
+        reinterpret_cast<const unsigned char*>(fimg + ((size_t)hd.ymin * W + hd.xmin) * C);
+    const size_t src_step = (size_t)W * C * sizeof(T);
+    for (int i = 0; i < nrows; ++i) {
+      const int slot = i % ns;
+      if (i >= ns) mbar_wait(empty + slot, ((i / ns) - 1) & 1);
+      if (lane == 0) mbar_arrive_expect_tx(full + slot, row_bytes);
+      for (uint32_t o = (uint32_t)lane * kFwdCopy; o < row_bytes; o += 32u * kFwdCopy)
+        bulk_g2s(ring + (size_t)slot * row_bytes + o, src + o, min((uint32_t)kFwdCopy, row_bytes - o),
+                 full + slot);
+      src += src_step;
+    }
+    return;
+  }
+  if (warp > ncons) return;
+
+  // ---------------------------------------------------------------- consumers
+  const int cwid = 32 * V;
+  const int pw = warp % PW, chunk = warp / PW;
+  const int c = chunk * cwid + lane * V;
+  const bool act = c < C;
+  const int nc = tx.cnt[pw];
+  float wx[kFwdTaps];
+#pragma unroll
+  for (int j = 0; j < kFwdTaps; ++j) wx[j] = j < nc ? tx.w[tx.off[pw] + j] : 0.f;
+  const uint32_t tap0 = (uint32_t)((nc > 0 ? tx.first[pw] - hd.xmin : 0) * C + (act ? c : 0)) * sizeof(T);
+  const uint32_t tap_step = (uint32_t)C * sizeof(T);
+  uint64_t acc[PH][V2];
+#pragma unroll
+  for (int ph = 0; ph < PH; ++ph)
+#pragma unroll
+    for (int u = 0; u < V2; ++u) acc[ph][u] = 0ull;
+
+  for (int i = 0; i < nrows; ++i) {
+    const int slot = i % ns;
+    mbar_wait(full + slot, (i / ns) & 1);
+    if (nc > 0) {
+      const unsigned char* __restrict__ s0 = ring + (size_t)slot * row_bytes + tap0;
+      uint64_t t[V2];
+#pragma unroll
+      for (int u = 0; u < V2; ++u) t[u] = 0ull;
+#pragma unroll
+      for (int j = 0; j < kFwdTaps; ++j) {
+        if (j < nc) {
+          uint64_t v[V2];
+          lds_pairs<T>(s0 + j * tap_step, v);
+          const uint64_t wp = pack2(wx[j], wx[j]);
+#pragma unroll
+          for (int u = 0; u < V2; ++u) t[u] = fma2(v[u], wp, t[u]);
+        }
+      }
+      const float4* __restrict__ rw = reinterpret_cast<const float4*>(roww + i * PHP);
+#pragma unroll
+      for (int q4 = 0; q4 < PHP / 4; ++q4) {
+        const float4 w4 = rw[q4];
+        const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int ph = q4 * 4 + q;
+          if (ph < PH && ww[q] != 0.f) {
+            const uint64_t wp = pack2(ww[q], ww[q]);
+#pragma unroll
+            for (int u = 0; u < V2; ++u) acc[ph][u] = fma2(t[u], wp, acc[ph][u]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + slot);
+  }
+  if (act) {
+    T* __restrict__ o = out + ((size_t)k * PHW + pw) * RC + (size_t)r * C + c;
+#pragma unroll
+    for (int ph = 0; ph < PH; ++ph) {
+      float f[V];
+#pragma unroll
+      for (int u = 0; u < V2; ++u) unpack2(acc[ph][u], f[2 * u], f[2 * u + 1]);
+      st_vec<T>(o + (size_t)ph * PW * RC, f);
+    }
+  }
+}
+
 // ------------------------------------------------------------ region prep
 // Workspace layout (bytes, each array 256-byte aligned):
 //   hdr     : N * 32                         RegionHdr
@@ -325,7 +580,7 @@ roi_fuse_fwd_cl(const RoiFuseParams p, int opitch, int bins_per_pass) {
 constexpr int kBandH = 8;       // rows per band == rows per pull tile
 constexpr int kTabLen = 256;    // per region: (row bin blocks) x (window rows) <= kTabLen, column weights <= kTabLen
 constexpr int kMaxBlk = 15;     // a row may be sampled by up to 2 * kMaxBlk bins (4-bit field)
-constexpr int kPrepBlock = 256; // regions per header block
+constexpr int kPrepBlock = 64;  // regions per id-segment block (== threads of roi_prep_kernel)
 
 // Entry of window row i for bin block blk; `len` = window length of the region.
 __host__ __device__ inline int tab_index(int blk, int i, int len) { return blk * len + i; }
@@ -484,9 +739,11 @@ __device__ int transpose_axis(const AxisTable& t, int P, int lo, int hi, float s
   return nblk;
 }
 
-// Blocks [0, nblk): headers of kPrepBlock regions each + per-level ordered id
-// segments.  Blocks [nblk, nblk + N): tap tables of one region each.
-__global__ void __launch_bounds__(kPrepBlock)
+// Blocks [0, nblk): per-level ordered id segments of kPrepBlock regions each.
+// Blocks [nblk, nblk + N): tap tables of one region each.  64 threads: the table
+// construction is two warps wide, so small blocks keep the SMs full of them.
+constexpr int kPrepThreads = kPrepBlock;
+__global__ void __launch_bounds__(kPrepThreads)
 roi_prep_kernel(const RoiFuseParams p, const PullWs ws) {
   const int N = p.K * p.R;
   const int tid = threadIdx.x;
@@ -497,8 +754,9 @@ roi_prep_kernel(const RoiFuseParams p, const PullWs ws) {
     // lists come out in region-index order without a sort.
     extern __shared__ unsigned mask[];  // [nkeys][kPrepBlock / 32]
     constexpr int kW = kPrepBlock / 32;
-    for (int e = tid; e < ws.nkeys * kW; e += kPrepBlock) mask[e] = 0u;
+    for (int e = tid; e < ws.nkeys * kW; e += kPrepThreads) mask[e] = 0u;
     __syncthreads();
+    const int word = tid >> 5;
     const int i = blockIdx.x * kPrepBlock + tid;  // region id = k * R + r
     int k0 = 0, k1 = -1;                           // key range of this region
     if (i < N) {
@@ -518,14 +776,14 @@ roi_prep_kernel(const RoiFuseParams p, const PullWs ws) {
         }
       }
     }
-    for (int key = k0; key <= k1; ++key) atomicOr(&mask[key * kW + (tid >> 5)], 1u << (tid & 31));
+    for (int key = k0; key <= k1; ++key) atomicOr(&mask[key * kW + word], 1u << (tid & 31));
     __syncthreads();
     for (int key = k0; key <= k1; ++key) {
-      int pos = __popc(mask[key * kW + (tid >> 5)] & ((1u << (tid & 31)) - 1u));
-      for (int w = 0; w < (tid >> 5); ++w) pos += __popc(mask[key * kW + w]);
+      int pos = __popc(mask[key * kW + word] & ((1u << (tid & 31)) - 1u));
+      for (int w = 0; w < word; ++w) pos += __popc(mask[key * kW + w]);
       ws.seg_ids[((size_t)blockIdx.x * ws.nkeys + key) * kPrepBlock + pos] = i;
     }
-    for (int key = tid; key < ws.nkeys; key += kPrepBlock) {
+    for (int key = tid; key < ws.nkeys; key += kPrepThreads) {
       int c = 0;
       for (int w = 0; w < kW; ++w) c += __popc(mask[key * kW + w]);
       ws.seg_cnt[(size_t)blockIdx.x * ws.nkeys + key] = c;
@@ -561,7 +819,7 @@ roi_prep_kernel(const RoiFuseParams p, const PullWs ws) {
         cb.first = tx.first[t2]; cb.cnt = (short)tx.cnt[t2]; cb.off = (short)tx.off[t2];
         ws.colbin[(size_t)i * kMaxPool + t2] = cb;
       }
-      for (int j = t2; j < ctotal; j += kPrepBlock - 32) ws.colw[(size_t)i * kTabLen + j] = tx.w[j];
+      for (int j = t2; j < ctotal; j += kPrepThreads - 32) ws.colw[(size_t)i * kTabLen + j] = tx.w[j];
     }
     __syncthreads();
     if (!fit || ctotal > kTabLen) h.flags = 1;
@@ -577,7 +835,7 @@ roi_prep_kernel(const RoiFuseParams p, const PullWs ws) {
 constexpr int kTileH = kBandH;  // tile rows, warp == tile row
 constexpr int kListCap = 512;   // list entries per pass
 constexpr int kChunkR = 32;     // list entries expanded per round
-constexpr int kMaxPrepBlocks = 511;   // K * regions <= 130 816 for the pull path
+constexpr int kMaxPrepBlocks = 2047;  // K * regions <= 131 008 for the pull path
 static_assert(kTileH * kChunkR == kThreads && kChunkR * kJ == kThreads, "expand: one item per thread");
 
 struct TileMap {
@@ -634,7 +892,7 @@ struct ListSmem {
 // per-block counts so that one 256-thread batch spans blocks.  CTA-wide.
 __device__ int init_candidates(ListSmem& sm, const PullWs& ws, int key) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i <= ws.nblk; i += kThreads)
+  for (int i = tid; i <= ws.nblk; i += (int)blockDim.x)
     sm.pre[i] = i < ws.nblk ? ws.seg_cnt[(size_t)i * ws.nkeys + key] : 0;
   __syncthreads();
   if (warp == 0) {  // exclusive scan of pre[0..nblk] by one warp
@@ -727,7 +985,7 @@ __device__ int build_list(ListSmem& sm, const RoiFuseParams& p, const PullWs& ws
         }
       atomicMax(&sm.list_n, end);
     }
-    const int batch = min(kThreads, total_cand - pos);
+    const int batch = min((int)blockDim.x, total_cand - pos);
     pos += accepted;
     __syncthreads();
     if (accepted < batch) break;  // list full
@@ -829,8 +1087,9 @@ __device__ void bin_tile(ListSmem& sm, const RoiFuseParams& p, const PullWs& ws,
   const int off = s_off;
   bool ok = off >= 0;
   if (ok) {
-    for (int c0 = 0; c0 < n; c0 += kChunkR) {
-      const int nc = min(kChunkR, n - c0);
+    const int chunk = (int)blockDim.x / kTileH;
+    for (int c0 = 0; c0 < n; c0 += chunk) {
+      const int nc = min(chunk, n - c0);
       {  // thread == (entry, tile row)
         const int q = tid / kTileH, row = tid - q * kTileH;
         const int qq = q < nc ? q : 0;  // idle lanes shadow entry 0 (no stores)
@@ -863,48 +1122,13 @@ __device__ void bin_tile(ListSmem& sm, const RoiFuseParams& p, const PullWs& ws,
   }
 }
 
-__global__ void __launch_bounds__(kThreads)
+constexpr int kBinThreads = 128;
+static_assert(kJ == kTileH, "bin_tile: (entry, row) and (entry, pw) share the thread mapping");
+__global__ void __launch_bounds__(kBinThreads)
 roi_bin_kernel(const RoiFuseParams p, const PullWs ws, const TileMap tm4, const TileMap tm8, int nt4) {
   __shared__ ListSmem sm;
   if ((int)blockIdx.x < nt4) bin_tile<4>(sm, p, ws, tm4, blockIdx.x);
   else bin_tile<8>(sm, p, ws, tm8, blockIdx.x - nt4);
-}
-
-// ------------------------------------------------------ mbarrier / bulk copy
-__device__ __forceinline__ uint32_t smem_u32(const void* ptr) {
-  return (uint32_t)__cvta_generic_to_shared(ptr);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t a = smem_u32(bar);
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(a), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-// global -> shared bulk copy (TMA, no tensor map): 16-byte aligned, bytes % 16 == 0
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
 }
 
 // ------------------------------------------------------------ pull kernel
@@ -931,8 +1155,8 @@ constexpr int kDescBytes = (int)sizeof(StageDesc);
 constexpr int kPullCtl = 512;  // full[16] + empty[16] barriers, stage offsets
 
 template <typename T, int TW>
-__global__ void __launch_bounds__(kPullThreads, (TW * VecOf<T>::n <= 32 ? 3 : 2))
-roi_bwd_pull_tma(const RoiFuseParams p, const PullWs ws, const TileMap tm, int ring_bytes) {
+__device__ __forceinline__ void pull_tile_tma(const RoiFuseParams& p, const PullWs& ws, const TileMap& tm,
+                                              int ring_bytes, int block) {
   constexpr int V = VecOf<T>::n;
   constexpr int V2 = V / 2;
   constexpr int CG = 32 * V;  // channels per group
@@ -944,7 +1168,7 @@ roi_bwd_pull_tma(const RoiFuseParams p, const PullWs ws, const TileMap tm, int r
   unsigned char* ring = smem + kPullCtl + kNSlot * kDescBytes;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int t = blockIdx.x / tm.groups, grp = blockIdx.x - t * tm.groups;
+  const int t = block / tm.groups, grp = block - t * tm.groups;
   const int2 td = ws.tile_desc[tm.tile_base + t];
   if (td.y < 0) return;  // served by roi_bwd_pull_inline
   const int n = td.y;
@@ -1075,6 +1299,16 @@ roi_bwd_pull_tma(const RoiFuseParams p, const PullWs ws, const TileMap tm, int r
   }
 }
 
+// One launch for both tile shapes: the narrow (heavy) tiles come first, the wide
+// ones fill the machine behind them.
+template <typename T>
+__global__ void __launch_bounds__(kPullThreads, (VecOf<T>::n == 4 ? 3 : 2))
+roi_bwd_pull_tma(const RoiFuseParams p, const PullWs ws, const TileMap tm4, const TileMap tm8,
+                 int nb4, int ring_bytes) {
+  if ((int)blockIdx.x < nb4) pull_tile_tma<T, 4>(p, ws, tm4, ring_bytes, blockIdx.x);
+  else pull_tile_tma<T, 8>(p, ws, tm8, ring_bytes, blockIdx.x - nb4);
+}
+
 // ---- inline kernel: the tiles the binning kernel could not serve.  A small
 // fixed grid walks the inline list; per tile and channel group: rounds of list
 // building, expansion into shared memory and streaming from global memory.
@@ -1201,6 +1435,31 @@ cudaError_t launch_roi_fuse_forward_cl(const RoiFuseParams& p, int dtype, int ou
                                        cudaStream_t stream) {
   const int PHW = p.PH * p.PW;
   const int grid = p.K * p.R;
+  cudaError_t e;
+  {
+    // TMA row-ring kernel: channels-last output, 7x7 / 14x14 bins, one consumer
+    // warp per (output column, channel chunk)
+    static const int use_tma = [] { const char* ev = getenv("ARFE_FWD_TMA"); return ev ? atoi(ev) : 1; }();
+    const int V = dtype == 0 ? 4 : 8;
+    const int ncons = p.PW * ((p.C + 32 * V - 1) / (32 * V));
+    if (use_tma && out_cl && (p.PH == 7 || p.PH == 14) && ncons <= 15) {
+      const int php = (p.PH + 3) / 4 * 4;
+      const int fixed = kHdrBytes + kFwdMaxRows * php * 4 + 2 * kFwdSlots * 8;
+      // two CTAs per SM (7x7 fp32: 28 accumulator registers per thread), else one
+      const int ring = (p.PH * V <= 32 ? 108 * 1024 : 200 * 1024) - fixed;
+      const int smem = fixed + ring;
+      const int threads = (ncons + 1) * 32;
+#define ARFE_FWD_TMA(TT, PHH)                                                               \
+  do {                                                                                      \
+    if ((e = set_smem(roi_fuse_fwd_tma<TT, PHH>, smem)) != cudaSuccess) return e;           \
+    roi_fuse_fwd_tma<TT, PHH><<<grid, threads, smem, stream>>>(p, ncons, ring);             \
+  } while (0)
+      if (dtype == 0) { if (p.PH == 7) ARFE_FWD_TMA(float, 7); else ARFE_FWD_TMA(float, 14); }
+      else { if (p.PH == 7) ARFE_FWD_TMA(__nv_bfloat16, 7); else ARFE_FWD_TMA(__nv_bfloat16, 14); }
+#undef ARFE_FWD_TMA
+      return cudaGetLastError();
+    }
+  }
   int opitch = 0, bpp = PHW, smem = kHdrBytes;
   if (!out_cl) {
     opitch = p.C + 4;
@@ -1209,7 +1468,6 @@ cudaError_t launch_roi_fuse_forward_cl(const RoiFuseParams& p, int dtype, int ou
     if (bpp > PHW) bpp = PHW;
     smem += bpp * opitch * 4;
   }
-  cudaError_t e;
   static const int occ = [] { const char* e = getenv("ARFE_FWD_OCC"); return e ? atoi(e) : 4; }();
 #define ARFE_FWD_CL1(TT, OC, OCC)                                                       \
   do {                                                                                  \
@@ -1246,7 +1504,7 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
   cudaError_t e = set_smem(roi_prep_kernel, prep_smem);
   if (e != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(ws.counters, 0, 16, stream)) != cudaSuccess) return e;
-  roi_prep_kernel<<<ws.nblk + N, kPrepBlock, prep_smem, stream>>>(p, ws);
+  roi_prep_kernel<<<ws.nblk + N, kPrepThreads, prep_smem, stream>>>(p, ws);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   // Two tile shapes: the small upper-level maps carry ~40x more region-pixels per
@@ -1278,20 +1536,19 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
     ntiles[pass] = total;
   }
   if (ntiles[0] + ntiles[1] == 0) return cudaSuccess;
-  roi_bin_kernel<<<ntiles[0] + ntiles[1], kThreads, 0, stream>>>(p, ws, tm[0], tm[1], ntiles[0]);
+  roi_bin_kernel<<<ntiles[0] + ntiles[1], kBinThreads, 0, stream>>>(p, ws, tm[0], tm[1], ntiles[0]);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   const int ring = 64 * 1024;
   const int smem = kPullCtl + kNSlot * kDescBytes + ring;
-#define ARFE_PULL(TT, TWW, PASS)                                                                   \
-  do {                                                                                             \
-    if ((e = set_smem(roi_bwd_pull_tma<TT, TWW>, smem)) != cudaSuccess) return e;                  \
-    roi_bwd_pull_tma<TT, TWW><<<ntiles[PASS] * tm[PASS].groups, kPullThreads, smem, stream>>>(     \
-        p, ws, tm[PASS], ring);                                                                    \
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;                                         \
-  } while (0)
-  if (ntiles[0] > 0) { if (dtype == 0) ARFE_PULL(float, 4, 0); else ARFE_PULL(__nv_bfloat16, 4, 0); }
-  if (ntiles[1] > 0) { if (dtype == 0) ARFE_PULL(float, 8, 1); else ARFE_PULL(__nv_bfloat16, 8, 1); }
-#undef ARFE_PULL
+  const int nb4 = ntiles[0] * tm[0].groups, nb8 = ntiles[1] * tm[1].groups;
+  if (dtype == 0) {
+    if ((e = set_smem(roi_bwd_pull_tma<float>, smem)) != cudaSuccess) return e;
+    roi_bwd_pull_tma<float><<<nb4 + nb8, kPullThreads, smem, stream>>>(p, ws, tm[0], tm[1], nb4, ring);
+  } else {
+    if ((e = set_smem(roi_bwd_pull_tma<__nv_bfloat16>, smem)) != cudaSuccess) return e;
+    roi_bwd_pull_tma<__nv_bfloat16><<<nb4 + nb8, kPullThreads, smem, stream>>>(p, ws, tm[0], tm[1], nb4, ring);
+  }
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
   const int igrid = ntiles[0] + ntiles[1] < 148 ? ntiles[0] + ntiles[1] : 148;
   if (dtype == 0) roi_bwd_pull_inline<float><<<igrid, kThreads, 0, stream>>>(p, ws, tm[0], tm[1], ntiles[0]);
   else roi_bwd_pull_inline<__nv_bfloat16><<<igrid, kThreads, 0, stream>>>(p, ws, tm[0], tm[1], ntiles[0]);
