@@ -372,26 +372,199 @@ roi_fuse_fwd_cl(const RoiFuseParams p, int opitch, int bins_per_pass) {
 }
 
 // ---------------------------------------------------------- forward (TMA)
-// One CTA per (RoI, region), channels-last in and out.  In NHWC a row of the
-// region's sampling window (wlen pixels x C channels) is ONE contiguous piece of
-// memory, so a producer warp streams the window row by row into a shared-memory
-// ring with bulk async copies (TMA) signalling an mbarrier per row; several rows
-// are in flight without holding registers and every window byte crosses
-// L2 -> SM exactly once (the L1-cached kernel above re-fetches ~1.5x).
-// Consumer warp == (output column pw, channel chunk): per row it folds its
-// (<= 8) column taps into t = sum_j wx[j] * f[row][x0 + j] from shared memory
-// and adds wy[ph][row] * t to the (usually <= 2) bin rows ph that sample the
-// row (dense row-weight matrix, zero weights skipped); its PH accumulators
-// stay in registers and are written once at the end.
-// Regions the ring cannot serve (window wider than half the ring, more than
+// Persistent CTAs (one or two per SM) walk the (RoI, region) list; channels-last
+// in and out.  In NHWC a row of a region's sampling window (wlen pixels x C
+// channels) is ONE contiguous piece of memory, so a PRODUCER warp streams the
+// windows row by row into a shared-memory byte ring with bulk async copies (TMA)
+// signalling an mbarrier per row; it runs ahead across regions, so rows stay in
+// flight without holding registers and every window byte crosses L2 -> SM
+// exactly once (the L1-cached kernel above re-fetches ~1.5x).  A SETUP warp
+// builds the tables of the next region (geometry, aggregated axis tables, dense
+// row weights) into the other of two table buffers while the current region is
+// being consumed.  CONSUMER warp == (output column pw, channel chunk): per row
+// it folds its (<= 8) column taps into t = sum_j wx[j] * f[row][x0 + j] from
+// shared memory and adds wy[ph][row] * t to the (usually <= 2) bin rows ph that
+// sample the row (zero weights skipped); its PH accumulators stay in registers
+// and are written once per region.
+// Regions the ring cannot serve (window row wider than half the ring, more than
 // kFwdMaxRows rows, a column with more than 8 taps, overflowing tables) take
-// the direct path above inside the same kernel.
-constexpr int kFwdSlots = 8;
+// the direct / generic paths inside the same kernel.
+constexpr int kFwdSlots = 16;
 constexpr int kFwdMaxRows = 64;
 constexpr int kFwdTaps = 8;
 constexpr int kFwdCopy = 8192;  // bytes per bulk copy
 
-// dynamic smem: [CtaHeader][AxisTable y][AxisTable x][roww: kFwdMaxRows x PHP][barriers][ring]
+struct FwdTab {
+  CtaHeader hd;
+  int mode;      // 0: zeros, 1: generic (tables overflowed), 2: direct, 3: ring
+  int pad[3];
+  AxisTable ty, tx;
+  alignas(16) int4 rowrec[kFwdMaxRows];  // per window row: {first bin row p0, bins (0..2), w0 / count, w1 / count}
+};
+
+// Header + tables of region (k, r) by ONE warp (the CTA-wide twin is setup_cta).
+__device__ void setup_region_warp(const RoiFuseParams& p, int k, int r, FwdTab& tb,
+                                  int ring_bytes, int elt, int lane) {
+  CtaHeader& hd = tb.hd;
+  if (lane == 0) {
+    RegionBox bx = region_box(p.rois + 5 * (size_t)k, r, p.facs);
+    int lvl = (p.L == 1) ? 0 : map_roi_level(bx, p.L, p.finest_scale);
+    hd.lvl = lvl;
+    hd.overflow = 0;
+    if (lvl >= 0) {
+      hd.g = roi_geometry(bx, p.scale[lvl], p.PH, p.PW, p.sampling_ratio);
+      hd.H = p.H[lvl];
+      hd.W = p.W[lvl];
+      if (hd.g.batch < 0 || hd.g.batch >= p.B) hd.lvl = -2;
+    }
+    if (p.lvl_out) p.lvl_out[(size_t)r * p.K + k] = lvl;
+    if (p.boxes_out) {
+      float* o = p.boxes_out + ((size_t)r * p.K + k) * 5;
+      o[0] = bx.b; o[1] = bx.x1; o[2] = bx.y1; o[3] = bx.x2; o[4] = bx.y2;
+    }
+  }
+  __syncwarp();
+  int mode = 0;
+  if (hd.lvl >= 0) {
+    build_axis_table(tb.ty, p.PH, hd.g.start_h, hd.g.bin_h, hd.g.grid_h, hd.H, &hd.overflow, lane);
+    build_axis_table(tb.tx, p.PW, hd.g.start_w, hd.g.bin_w, hd.g.grid_w, hd.W, &hd.overflow, lane);
+    __syncwarp();
+    if (hd.overflow) {
+      mode = 1;
+    } else {
+      int ymin = 0x7fffffff, ymax = -1, xmin = 0x7fffffff, xmax = -1, mr = 0, mc = 0;
+      if (lane < p.PH && tb.ty.cnt[lane] > 0) {
+        ymin = tb.ty.first[lane]; ymax = ymin + tb.ty.cnt[lane] - 1; mr = tb.ty.cnt[lane];
+      }
+      if (lane < p.PW && tb.tx.cnt[lane] > 0) {
+        xmin = tb.tx.first[lane]; xmax = xmin + tb.tx.cnt[lane] - 1; mc = tb.tx.cnt[lane];
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, d));
+        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, d));
+        xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, d));
+        xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, d));
+        mr = max(mr, __shfl_xor_sync(0xffffffffu, mr, d));
+        mc = max(mc, __shfl_xor_sync(0xffffffffu, mc, d));
+      }
+      if (lane == 0) {
+        hd.ymin = ymin; hd.ymax = ymax; hd.xmin = xmin; hd.xmax = xmax;
+        hd.max_rows = mr;
+      }
+      if (ymax >= 0 && xmax >= 0) {
+        const int nrows = ymax - ymin + 1;
+        const long long row_bytes = (long long)(xmax - xmin + 1) * p.C * elt;
+        mode = (2 * row_bytes <= ring_bytes && nrows <= kFwdMaxRows && mc <= kFwdTaps) ? 3 : 2;
+        if (mode == 3) {
+          // transpose the row table: the (<= 2) bin rows sampling each window row
+          const float inv_count = 1.0f / hd.g.count;
+          bool wide = false;
+          for (int i = lane; i < nrows; i += 32) {
+            const int row = ymin + i;
+            int p0 = -1, cnt = 0;
+            for (int q = 0; q < p.PH; ++q)
+              if (tb.ty.cnt[q] > 0 && row >= tb.ty.first[q] && row < tb.ty.first[q] + tb.ty.cnt[q]) {
+                if (p0 < 0) p0 = q;
+                cnt = q - p0 + 1;
+              }
+            if (cnt > 2) wide = true;
+            int4 rec = make_int4(p0 < 0 ? 0 : p0, cnt, 0, 0);
+            if (cnt > 0) rec.z = __float_as_int(tb.ty.w[tb.ty.off[p0] + row - tb.ty.first[p0]] * inv_count);
+            if (cnt > 1) rec.w = __float_as_int(tb.ty.w[tb.ty.off[p0 + 1] + row - tb.ty.first[p0 + 1]] * inv_count);
+            tb.rowrec[i] = rec;
+          }
+          if (__any_sync(0xffffffffu, wide)) mode = 2;  // sub-pixel bins: direct path
+        }
+      }
+    }
+  }
+  if (lane == 0) tb.mode = mode;
+}
+
+struct FwdPipe {
+  uint64_t* full;
+  uint64_t* empty;
+  const uint32_t* stage_off;
+  const unsigned char* ring;
+};
+
+// acc[P0] += w0 * t, acc[P0 + 1] += w1 * t with P0 a run-time value: the
+// accumulators live in registers, so the bin row is resolved by a jump table.
+template <int PH, int V2>
+__device__ __forceinline__ void add_rows(uint64_t (&acc)[PH][V2], int p0, const uint64_t (&t)[V2],
+                                         float w0, float w1) {
+  const uint64_t w0p = pack2(w0, w0), w1p = pack2(w1, w1);
+#define ARFE_ROW_CASE(P)                                                         \
+  case P:                                                                        \
+    if constexpr (P < PH) {                                                      \
+      _Pragma("unroll") for (int u = 0; u < V2; ++u) {                           \
+        acc[P][u] = fma2(t[u], w0p, acc[P][u]);                                  \
+        if constexpr (P + 1 < PH) acc[P + 1][u] = fma2(t[u], w1p, acc[P + 1][u]); \
+      }                                                                          \
+    }                                                                            \
+    break;
+  switch (p0) {
+    ARFE_ROW_CASE(0) ARFE_ROW_CASE(1) ARFE_ROW_CASE(2) ARFE_ROW_CASE(3) ARFE_ROW_CASE(4)
+    ARFE_ROW_CASE(5) ARFE_ROW_CASE(6) ARFE_ROW_CASE(7) ARFE_ROW_CASE(8) ARFE_ROW_CASE(9)
+    ARFE_ROW_CASE(10) ARFE_ROW_CASE(11) ARFE_ROW_CASE(12) ARFE_ROW_CASE(13)
+    default: break;
+  }
+#undef ARFE_ROW_CASE
+}
+
+// One consumer warp, one region: NC column taps per row (compile-time), rows
+// streamed through the ring from stage `stage0` on.
+template <typename T, int PH, int NC>
+__device__ __forceinline__ void fwd_consume_rows(const FwdPipe& pp, int stage0, int nrows,
+                                                 const int4* __restrict__ rowrec,
+                                                 const float* __restrict__ wxp, uint32_t tap0, int C,
+                                                 T* __restrict__ o, size_t ostep) {
+  constexpr int V = VecOf<T>::n;
+  constexpr int V2 = V / 2;
+  const int lane = threadIdx.x & 31;
+  const uint32_t tap_step = (uint32_t)C * sizeof(T);
+  float wx[NC > 0 ? NC : 1];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) wx[j] = wxp[j];
+  uint64_t acc[PH][V2];
+#pragma unroll
+  for (int ph = 0; ph < PH; ++ph)
+#pragma unroll
+    for (int u = 0; u < V2; ++u) acc[ph][u] = 0ull;
+  for (int rr = 0; rr < nrows; ++rr) {
+    const int stage = stage0 + rr;
+    const int slot = stage % kFwdSlots;
+    const int4 rec = rowrec[rr];
+    mbar_wait(pp.full + slot, (stage / kFwdSlots) & 1);
+    if (NC > 0 && rec.y > 0) {
+      const unsigned char* __restrict__ s0 = pp.ring + pp.stage_off[slot] + tap0;
+      uint64_t v[NC > 0 ? NC : 1][V2];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) lds_pairs<T>(s0 + j * tap_step, v[j]);
+      uint64_t t[V2];
+#pragma unroll
+      for (int u = 0; u < V2; ++u) t[u] = mul2(v[0][u], pack2(wx[0], wx[0]));
+#pragma unroll
+      for (int j = 1; j < NC; ++j)
+#pragma unroll
+        for (int u = 0; u < V2; ++u) t[u] = fma2(v[j][u], pack2(wx[j], wx[j]), t[u]);
+      add_rows<PH, V2>(acc, rec.x, t, __int_as_float(rec.z), __int_as_float(rec.w));
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(pp.empty + slot);
+  }
+  if (o) {
+#pragma unroll
+    for (int ph = 0; ph < PH; ++ph) {
+      float f[V];
+#pragma unroll
+      for (int u = 0; u < V2; ++u) unpack2(acc[ph][u], f[2 * u], f[2 * u + 1]);
+      st_vec<T>(o + (size_t)ph * ostep, f);
+    }
+  }
+}
+
 template <typename T>
 __device__ __noinline__ void fwd_direct_cl_call(const RoiFuseParams& p, const CtaHeader& hd,
                                                 const AxisTable& ty, const AxisTable& tx, int k,
@@ -399,173 +572,175 @@ __device__ __noinline__ void fwd_direct_cl_call(const RoiFuseParams& p, const Ct
   fwd_direct_cl<T>(p, hd, ty, tx, k, r, nwarps);
 }
 
+// dynamic smem: [FwdTab x 2][barriers, stage offsets: 512 bytes][ring]
 template <typename T, int PH>
 __global__ void __launch_bounds__(512, (PH * VecOf<T>::n <= 32 ? 2 : 1))
 roi_fuse_fwd_tma(const RoiFuseParams p, int ncons, int ring_bytes) {
   constexpr int V = VecOf<T>::n;
   constexpr int V2 = V / 2;
-  constexpr int PHP = (PH + 3) / 4 * 4;
+  using Tab = FwdTab;
+  constexpr int kTabBytes = ((int)sizeof(Tab) + 127) / 128 * 128;
   extern __shared__ __align__(16) unsigned char smem[];
-  CtaHeader& hd = *reinterpret_cast<CtaHeader*>(smem);
-  AxisTable& ty = *reinterpret_cast<AxisTable*>(smem + 128);
-  AxisTable& tx = *reinterpret_cast<AxisTable*>(smem + 128 + sizeof(AxisTable));
-  float* roww = reinterpret_cast<float*>(smem + kHdrBytes);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kHdrBytes + kFwdMaxRows * PHP * 4);
+  unsigned char* ctl = smem + 2 * kTabBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ctl);
   uint64_t* empty = full + kFwdSlots;
-  unsigned char* ring = reinterpret_cast<unsigned char*>(empty + kFwdSlots);
+  uint64_t* tab_full = empty + kFwdSlots;
+  uint64_t* tab_empty = tab_full + 2;
+  uint32_t* stage_off = reinterpret_cast<uint32_t*>(tab_empty + 2);
+  unsigned char* ring = ctl + 512;
 
-  const int k = blockIdx.x / p.R, r = blockIdx.x % p.R;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int PW = p.PW, PHW = PH * PW, C = p.C, RC = p.R * C;
+  const int N = p.K * p.R;
+  const int n_my = ((int)blockIdx.x < N) ? (N - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   T* __restrict__ out = static_cast<T*>(p.out);
 
-  const bool live = setup_cta(p, k, r, hd, ty, tx);
-  if (!live || hd.overflow) {
-    T* __restrict__ o = out + (size_t)k * PHW * RC + (size_t)r * C;
-    if (live) {  // tables did not fit: reference loop order, direct taps
-      const T* __restrict__ f = static_cast<const T*>(p.feats[hd.lvl]);
-      const int H = hd.H, W = hd.W;
-      const RoiGeom g = hd.g;
-      for (int e = tid; e < C * PHW; e += (int)blockDim.x) {
-        const int bin = e / C, c = e - bin * C;
-        const int ph = bin / PW, pw = bin % PW;
-        float acc = 0.f;
-        for (int iy = 0; iy < g.grid_h; ++iy) {
-          AxisTap a = axis_sample(g.start_h, ph, g.bin_h, iy, g.grid_h, H);
-          if (a.lo < 0) continue;
-          for (int ix = 0; ix < g.grid_w; ++ix) {
-            AxisTap b = axis_sample(g.start_w, pw, g.bin_w, ix, g.grid_w, W);
-            if (b.lo < 0) continue;
-            const size_t base = (size_t)g.batch * H * W;
-            acc += a.wl * b.wl * to_f(f[(base + (size_t)a.lo * W + b.lo) * C + c]) +
-                   a.wl * b.wh * to_f(f[(base + (size_t)a.lo * W + b.hi) * C + c]) +
-                   a.wh * b.wl * to_f(f[(base + (size_t)a.hi * W + b.lo) * C + c]) +
-                   a.wh * b.wh * to_f(f[(base + (size_t)a.hi * W + b.hi) * C + c]);
-          }
-        }
-        o[(size_t)bin * RC + c] = from_f<T>(__fdiv_rn(acc, g.count));
-      }
-    } else {
-      for (int e = tid; e < C * PHW; e += (int)blockDim.x) {
-        const int bin = e / C, c = e - bin * C;
-        o[(size_t)bin * RC + c] = from_f<T>(0.f);
-      }
-    }
-    return;
-  }
-
-  const int nrows = hd.ymax - hd.ymin + 1, wlen = hd.xmax - hd.xmin + 1;
-  const uint32_t row_bytes = (uint32_t)wlen * C * sizeof(T);
-  int maxc = 0;
-  for (int q = 0; q < PW; ++q) maxc = max(maxc, tx.cnt[q]);
-  const int ns = min(kFwdSlots, (int)(ring_bytes / row_bytes));
-  if (ns < 2 || nrows > kFwdMaxRows || maxc > kFwdTaps) {
-    fwd_direct_cl_call<T>(p, hd, ty, tx, k, r, ncons);
-    return;
-  }
-
-  // dense row weights (carry 1 / count), barriers
-  const float inv_count = 1.0f / hd.g.count;
-  for (int e = tid; e < nrows * PHP; e += (int)blockDim.x) {
-    const int i = e / PHP, ph = e - i * PHP;
-    float w = 0.f;
-    if (ph < PH) {
-      const int j = hd.ymin + i - ty.first[ph];
-      if (j >= 0 && j < ty.cnt[ph]) w = ty.w[ty.off[ph] + j] * inv_count;
-    }
-    roww[e] = w;
-  }
   if (tid == 0) {
     for (int i = 0; i < kFwdSlots; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, ncons); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tab_full + i, 1); mbar_init(tab_empty + i, ncons + 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  const int H = hd.H, W = hd.W;
-  const T* __restrict__ fimg =
-      static_cast<const T*>(p.feats[hd.lvl]) + (size_t)hd.g.batch * H * W * C;
-
-  if (warp == ncons) {
-    // ------------------------------------------------------------ producer
-    const unsigned char* __restrict__ src =
-        reinterpret_cast<const unsigned char*>(fimg + ((size_t)hd.ymin * W + hd.xmin) * C);
-    const size_t src_step = (size_t)W * C * sizeof(T);
-    for (int i = 0; i < nrows; ++i) {
-      const int slot = i % ns;
-      if (i >= ns) mbar_wait(empty + slot, ((i / ns) - 1) & 1);
-      if (lane == 0) mbar_arrive_expect_tx(full + slot, row_bytes);
-      for (uint32_t o = (uint32_t)lane * kFwdCopy; o < row_bytes; o += 32u * kFwdCopy)
-        bulk_g2s(ring + (size_t)slot * row_bytes + o, src + o, min((uint32_t)kFwdCopy, row_bytes - o),
-                 full + slot);
-      src += src_step;
+  if (warp == ncons + 1) {
+    // --------------------------------------------------------------- setup
+    for (int i = 0; i < n_my; ++i) {
+      const int buf = i & 1;
+      if (i >= 2) mbar_wait(tab_empty + buf, ((i >> 1) - 1) & 1);
+      const int reg = blockIdx.x + i * gridDim.x;
+      Tab& tb = *reinterpret_cast<Tab*>(smem + buf * kTabBytes);
+      setup_region_warp(p, reg / p.R, reg % p.R, tb, ring_bytes, (int)sizeof(T), lane);
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tab_full + buf);
     }
     return;
   }
-  if (warp > ncons) return;
+
+  if (warp == ncons) {
+    // ------------------------------------------------------------ producer
+    uint32_t head = 0, tail = 0;  // live bytes of the ring: [tail, head) modulo wrap
+    uint32_t my_off = 0;          // lane j: ring offset of the stage in slot j
+    int issued = 0, released = 0; // stages (rows) issued / known to be consumed
+    for (int i = 0; i < n_my; ++i) {
+      const int buf = i & 1;
+      mbar_wait(tab_full + buf, (i >> 1) & 1);
+      const Tab& tb = *reinterpret_cast<const Tab*>(smem + buf * kTabBytes);
+      const int mode = tb.mode;
+      const int ymin = tb.hd.ymin, xmin = tb.hd.xmin;
+      const int nrows = tb.hd.ymax - ymin + 1, wlen = tb.hd.xmax - xmin + 1;
+      const int H = tb.hd.H, W = tb.hd.W, lvl = tb.hd.lvl, batch = tb.hd.g.batch;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tab_empty + buf);  // header copied to registers
+      if (mode != 3) continue;
+      const uint32_t bytes = (uint32_t)wlen * C * sizeof(T);
+      const unsigned char* __restrict__ src = reinterpret_cast<const unsigned char*>(
+          static_cast<const T*>(p.feats[lvl]) + (((size_t)batch * H + ymin) * W + xmin) * C);
+      const size_t src_step = (size_t)W * C * sizeof(T);
+      for (int rr = 0; rr < nrows; ++rr) {
+        const int slot = issued % kFwdSlots;
+        auto release_one = [&]() {
+          mbar_wait(empty + (released % kFwdSlots), (released / kFwdSlots) & 1);
+          ++released;
+          const uint32_t nxt = __shfl_sync(0xffffffffu, my_off, released % kFwdSlots);
+          tail = released < issued ? nxt : head;
+        };
+        while (released < issued - kFwdSlots + 1) release_one();
+        uint32_t off;
+        while (true) {
+          if (released == issued) { head = tail = 0; off = 0; break; }   // ring empty
+          if (head >= tail) {
+            if (head + bytes <= (uint32_t)ring_bytes) { off = head; break; }
+            if (bytes < tail) { off = 0; break; }                          // wrap
+          } else if (head + bytes < tail) { off = head; break; }
+          release_one();
+        }
+        head = off + bytes;
+        if (lane == slot) my_off = off;
+        if (lane == 0) {
+          stage_off[slot] = off;
+          mbar_arrive_expect_tx(full + slot, bytes);
+        }
+        for (uint32_t o = (uint32_t)lane * kFwdCopy; o < bytes; o += 32u * kFwdCopy)
+          bulk_g2s(ring + off + o, src + o, min((uint32_t)kFwdCopy, bytes - o), full + slot);
+        src += src_step;
+        ++issued;
+      }
+    }
+    return;
+  }
+  if (warp > ncons + 1) return;
 
   // ---------------------------------------------------------------- consumers
   const int cwid = 32 * V;
   const int pw = warp % PW, chunk = warp / PW;
   const int c = chunk * cwid + lane * V;
   const bool act = c < C;
-  const int nc = tx.cnt[pw];
-  float wx[kFwdTaps];
-#pragma unroll
-  for (int j = 0; j < kFwdTaps; ++j) wx[j] = j < nc ? tx.w[tx.off[pw] + j] : 0.f;
-  const uint32_t tap0 = (uint32_t)((nc > 0 ? tx.first[pw] - hd.xmin : 0) * C + (act ? c : 0)) * sizeof(T);
-  const uint32_t tap_step = (uint32_t)C * sizeof(T);
-  uint64_t acc[PH][V2];
-#pragma unroll
-  for (int ph = 0; ph < PH; ++ph)
-#pragma unroll
-    for (int u = 0; u < V2; ++u) acc[ph][u] = 0ull;
-
-  for (int i = 0; i < nrows; ++i) {
-    const int slot = i % ns;
-    mbar_wait(full + slot, (i / ns) & 1);
-    if (nc > 0) {
-      const unsigned char* __restrict__ s0 = ring + (size_t)slot * row_bytes + tap0;
-      uint64_t t[V2];
-#pragma unroll
-      for (int u = 0; u < V2; ++u) t[u] = 0ull;
-#pragma unroll
-      for (int j = 0; j < kFwdTaps; ++j) {
-        if (j < nc) {
-          uint64_t v[V2];
-          lds_pairs<T>(s0 + j * tap_step, v);
-          const uint64_t wp = pack2(wx[j], wx[j]);
-#pragma unroll
-          for (int u = 0; u < V2; ++u) t[u] = fma2(v[u], wp, t[u]);
-        }
+  const int ctid = tid, cthreads = ncons * 32;  // consumer threads: [0, ncons * 32)
+  int stage = 0;
+  for (int i = 0; i < n_my; ++i) {
+    const int buf = i & 1;
+    mbar_wait(tab_full + buf, (i >> 1) & 1);
+    const Tab& tb = *reinterpret_cast<const Tab*>(smem + buf * kTabBytes);
+    const CtaHeader& hd = tb.hd;
+    const int reg = blockIdx.x + i * gridDim.x;
+    const int k = reg / p.R, r = reg - k * p.R;
+    const int mode = tb.mode;
+    if (mode == 3) {
+      const int nrows = hd.ymax - hd.ymin + 1;
+      const int nc = tb.tx.cnt[pw];
+      const float* __restrict__ wxp = tb.tx.w + tb.tx.off[pw];
+      const uint32_t tap0 = (uint32_t)((nc > 0 ? tb.tx.first[pw] - hd.xmin : 0) * C + (act ? c : 0)) * sizeof(T);
+      T* __restrict__ o = act ? out + ((size_t)k * PHW + pw) * RC + (size_t)r * C + c : nullptr;
+      FwdPipe pipe{full, empty, stage_off, ring};
+      switch (nc) {
+        case 0: fwd_consume_rows<T, PH, 0>(pipe, stage, nrows, tb.rowrec, wxp, tap0, C, o, (size_t)PW * RC); break;
+        case 1: fwd_consume_rows<T, PH, 1>(pipe, stage, nrows, tb.rowrec, wxp, tap0, C, o, (size_t)PW * RC); break;
+        case 2: fwd_consume_rows<T, PH, 2>(pipe, stage, nrows, tb.rowrec, wxp, tap0, C, o, (size_t)PW * RC); break;
+        case 3: fwd_consume_rows<T, PH, 3>(pipe, stage, nrows, tb.rowrec, wxp, tap0, C, o, (size_t)PW * RC); break;
+        case 4: fwd_consume_rows<T, PH, 4>(pipe, stage, nrows, tb.rowrec, wxp, tap0, C, o, (size_t)PW * RC); break;
+        case 5: fwd_consume_rows<T, PH, 5>(pipe, stage, nrows, tb.rowrec, wxp, tap0, C, o, (size_t)PW * RC); break;
+        case 6: fwd_consume_rows<T, PH, 6>(pipe, stage, nrows, tb.rowrec, wxp, tap0, C, o, (size_t)PW * RC); break;
+        case 7: fwd_consume_rows<T, PH, 7>(pipe, stage, nrows, tb.rowrec, wxp, tap0, C, o, (size_t)PW * RC); break;
+        default: fwd_consume_rows<T, PH, 8>(pipe, stage, nrows, tb.rowrec, wxp, tap0, C, o, (size_t)PW * RC); break;
       }
-      const float4* __restrict__ rw = reinterpret_cast<const float4*>(roww + i * PHP);
-#pragma unroll
-      for (int q4 = 0; q4 < PHP / 4; ++q4) {
-        const float4 w4 = rw[q4];
-        const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int ph = q4 * 4 + q;
-          if (ph < PH && ww[q] != 0.f) {
-            const uint64_t wp = pack2(ww[q], ww[q]);
-#pragma unroll
-            for (int u = 0; u < V2; ++u) acc[ph][u] = fma2(t[u], wp, acc[ph][u]);
+      stage += nrows;
+    } else if (mode == 2) {
+      fwd_direct_cl_call<T>(p, hd, tb.ty, tb.tx, k, r, ncons);
+    } else {
+      T* __restrict__ o = out + (size_t)k * PHW * RC + (size_t)r * C;
+      if (mode == 1) {  // tables did not fit: reference loop order, direct taps
+        const T* __restrict__ f = static_cast<const T*>(p.feats[hd.lvl]);
+        const int H = hd.H, W = hd.W;
+        const RoiGeom g = hd.g;
+        for (int e = ctid; e < C * PHW; e += cthreads) {
+          const int bin = e / C, cc = e - bin * C;
+          const int ph = bin / PW, pq = bin % PW;
+          float a0 = 0.f;
+          for (int iy = 0; iy < g.grid_h; ++iy) {
+            AxisTap a = axis_sample(g.start_h, ph, g.bin_h, iy, g.grid_h, H);
+            if (a.lo < 0) continue;
+            for (int ix = 0; ix < g.grid_w; ++ix) {
+              AxisTap b = axis_sample(g.start_w, pq, g.bin_w, ix, g.grid_w, W);
+              if (b.lo < 0) continue;
+              const size_t base = (size_t)g.batch * H * W;
+              a0 += a.wl * b.wl * to_f(f[(base + (size_t)a.lo * W + b.lo) * C + cc]) +
+                    a.wl * b.wh * to_f(f[(base + (size_t)a.lo * W + b.hi) * C + cc]) +
+                    a.wh * b.wl * to_f(f[(base + (size_t)a.hi * W + b.lo) * C + cc]) +
+                    a.wh * b.wh * to_f(f[(base + (size_t)a.hi * W + b.hi) * C + cc]);
+            }
           }
+          o[(size_t)bin * RC + cc] = from_f<T>(__fdiv_rn(a0, g.count));
+        }
+      } else {
+        for (int e = ctid; e < C * PHW; e += cthreads) {
+          const int bin = e / C, cc = e - bin * C;
+          o[(size_t)bin * RC + cc] = from_f<T>(0.f);
         }
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(empty + slot);
-  }
-  if (act) {
-    T* __restrict__ o = out + ((size_t)k * PHW + pw) * RC + (size_t)r * C + c;
-#pragma unroll
-    for (int ph = 0; ph < PH; ++ph) {
-      float f[V];
-#pragma unroll
-      for (int u = 0; u < V2; ++u) unpack2(acc[ph][u], f[2 * u], f[2 * u + 1]);
-      st_vec<T>(o + (size_t)ph * PW * RC, f);
-    }
+    if (lane == 0) mbar_arrive(tab_empty + buf);
   }
 }
 
@@ -1442,20 +1617,28 @@ cudaError_t launch_roi_fuse_forward_cl(const RoiFuseParams& p, int dtype, int ou
     static const int use_tma = [] { const char* ev = getenv("ARFE_FWD_TMA"); return ev ? atoi(ev) : 1; }();
     const int V = dtype == 0 ? 4 : 8;
     const int ncons = p.PW * ((p.C + 32 * V - 1) / (32 * V));
-    if (use_tma && out_cl && (p.PH == 7 || p.PH == 14) && ncons <= 15) {
-      const int php = (p.PH + 3) / 4 * 4;
-      const int fixed = kHdrBytes + kFwdMaxRows * php * 4 + 2 * kFwdSlots * 8;
+    if (use_tma && out_cl && (p.PH == 7 || p.PH == 14) && p.PH * V <= 64 && ncons <= 14) {
+      const int tab = ((int)sizeof(FwdTab) + 127) / 128 * 128;
+      const int fixed = 2 * tab + 512;
       // two CTAs per SM (7x7 fp32: 28 accumulator registers per thread), else one
-      const int ring = (p.PH * V <= 32 ? 108 * 1024 : 200 * 1024) - fixed;
+      const int per_sm = p.PH * V <= 32 ? 2 : 1;
+      const int ring = (per_sm == 2 ? 108 * 1024 : 200 * 1024) - fixed;
       const int smem = fixed + ring;
-      const int threads = (ncons + 1) * 32;
+      const int threads = (ncons + 2) * 32;
+      static const int sms = [] {
+        int dev = 0, n = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n;
+      }();
+      const int pgrid = grid < per_sm * sms ? grid : per_sm * sms;
 #define ARFE_FWD_TMA(TT, PHH)                                                               \
   do {                                                                                      \
     if ((e = set_smem(roi_fuse_fwd_tma<TT, PHH>, smem)) != cudaSuccess) return e;           \
-    roi_fuse_fwd_tma<TT, PHH><<<grid, threads, smem, stream>>>(p, ncons, ring);             \
+    roi_fuse_fwd_tma<TT, PHH><<<pgrid, threads, smem, stream>>>(p, ncons, ring);             \
   } while (0)
       if (dtype == 0) { if (p.PH == 7) ARFE_FWD_TMA(float, 7); else ARFE_FWD_TMA(float, 14); }
-      else { if (p.PH == 7) ARFE_FWD_TMA(__nv_bfloat16, 7); else ARFE_FWD_TMA(__nv_bfloat16, 14); }
+      else ARFE_FWD_TMA(__nv_bfloat16, 7);
 #undef ARFE_FWD_TMA
       return cudaGetLastError();
     }
