@@ -393,13 +393,15 @@ constexpr int kFwdSlots = 16;
 constexpr int kFwdMaxRows = 64;
 constexpr int kFwdTaps = 8;
 constexpr int kFwdCopy = 8192;  // bytes per bulk copy
+constexpr int kFwdRowPitch = 16;  // >= PH
 
 struct FwdTab {
   CtaHeader hd;
   int mode;      // 0: zeros, 1: generic (tables overflowed), 2: direct, 3: ring
   int pad[3];
   AxisTable ty, tx;
-  alignas(16) int4 rowrec[kFwdMaxRows];  // per window row: {first bin row p0, bins (0..2), w0 / count, w1 / count}
+  alignas(16) int4 rowrec[kFwdMaxRows];  // per window row: {first bin row p0, bins n, w0 / count, w1 / count}
+  alignas(16) float roww[kFwdMaxRows * kFwdRowPitch];  // rows sampled by n > 2 bins (sub-pixel bins): dense weights / count
 };
 
 // Header + tables of region (k, r) by ONE warp (the CTA-wide twin is setup_cta).
@@ -459,7 +461,6 @@ __device__ void setup_region_warp(const RoiFuseParams& p, int k, int r, FwdTab& 
         if (mode == 3) {
           // transpose the row table: the (<= 2) bin rows sampling each window row
           const float inv_count = 1.0f / hd.g.count;
-          bool wide = false;
           for (int i = lane; i < nrows; i += 32) {
             const int row = ymin + i;
             int p0 = -1, cnt = 0;
@@ -468,13 +469,21 @@ __device__ void setup_region_warp(const RoiFuseParams& p, int k, int r, FwdTab& 
                 if (p0 < 0) p0 = q;
                 cnt = q - p0 + 1;
               }
-            if (cnt > 2) wide = true;
             int4 rec = make_int4(p0 < 0 ? 0 : p0, cnt, 0, 0);
             if (cnt > 0) rec.z = __float_as_int(tb.ty.w[tb.ty.off[p0] + row - tb.ty.first[p0]] * inv_count);
             if (cnt > 1) rec.w = __float_as_int(tb.ty.w[tb.ty.off[p0 + 1] + row - tb.ty.first[p0 + 1]] * inv_count);
             tb.rowrec[i] = rec;
+            if (cnt > 2) {  // sub-pixel bins: dense weights of this row
+              for (int q = 0; q < kFwdRowPitch; ++q) {
+                float w = 0.f;
+                if (q < p.PH) {
+                  const int j = row - tb.ty.first[q];
+                  if (j >= 0 && j < tb.ty.cnt[q]) w = tb.ty.w[tb.ty.off[q] + j] * inv_count;
+                }
+                tb.roww[i * kFwdRowPitch + q] = w;
+              }
+            }
           }
-          if (__any_sync(0xffffffffu, wide)) mode = 2;  // sub-pixel bins: direct path
         }
       }
     }
@@ -518,6 +527,7 @@ __device__ __forceinline__ void add_rows(uint64_t (&acc)[PH][V2], int p0, const 
 template <typename T, int PH, int NC>
 __device__ __forceinline__ void fwd_consume_rows(const FwdPipe& pp, int stage0, int nrows,
                                                  const int4* __restrict__ rowrec,
+                                                 const float* __restrict__ roww,
                                                  const float* __restrict__ wxp, uint32_t tap0, int C,
                                                  T* __restrict__ o, size_t ostep) {
   constexpr int V = VecOf<T>::n;
@@ -549,7 +559,20 @@ __device__ __forceinline__ void fwd_consume_rows(const FwdPipe& pp, int stage0, 
       for (int j = 1; j < NC; ++j)
 #pragma unroll
         for (int u = 0; u < V2; ++u) t[u] = fma2(v[j][u], pack2(wx[j], wx[j]), t[u]);
-      add_rows<PH, V2>(acc, rec.x, t, __int_as_float(rec.z), __int_as_float(rec.w));
+      if (rec.y <= 2) {
+        add_rows<PH, V2>(acc, rec.x, t, __int_as_float(rec.z), __int_as_float(rec.w));
+      } else {
+        const float* __restrict__ rw = roww + rr * kFwdRowPitch;
+#pragma unroll
+        for (int ph = 0; ph < PH; ++ph) {
+          const float w = rw[ph];
+          if (w != 0.f) {
+            const uint64_t wp = pack2(w, w);
+#pragma unroll
+            for (int u = 0; u < V2; ++u) acc[ph][u] = fma2(t[u], wp, acc[ph][u]);
+          }
+        }
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(pp.empty + slot);
@@ -572,6 +595,69 @@ __device__ __noinline__ void fwd_direct_cl_call(const RoiFuseParams& p, const Ct
   fwd_direct_cl<T>(p, hd, ty, tx, k, r, nwarps);
 }
 
+// Work estimate of region i: the pixels of its sampling window (+ a constant for
+// the per-region setup).  Cheap geometry only -- no tables.
+__device__ __forceinline__ float region_cost(const RoiFuseParams& p, int i) {
+  const int k = i / p.R, r = i - k * p.R;
+  const RegionBox bx = region_box(p.rois + 5 * (size_t)k, r, p.facs);
+  const int lvl = (p.L == 1) ? 0 : map_roi_level(bx, p.L, p.finest_scale);
+  if (lvl < 0) return 8.f;
+  const float s = p.scale[lvl];
+  float w = (bx.x2 - bx.x1) * s + 2.f, h = (bx.y2 - bx.y1) * s + 2.f;
+  w = fminf(fmaxf(w, 1.f), (float)p.W[lvl]);
+  h = fminf(fmaxf(h, 1.f), (float)p.H[lvl]);
+  return (w == w && h == h) ? w * h + 8.f : 8.f;
+}
+
+// Contiguous, cost-balanced partition of the N regions over the grid: CTA b owns
+// the regions whose cumulative cost (exclusive) falls into the b-th of gridDim.x
+// equal shares.  Every CTA evaluates the same arithmetic in the same order, so
+// the partition is consistent and deterministic without any global state.
+__device__ void balanced_range(const RoiFuseParams& p, int N, int* s_range, float* s_warp,
+                               int& begin, int& end) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int chunk = (N + nt - 1) / nt;
+  const int i0 = min(N, tid * chunk), i1 = min(N, i0 + chunk);
+  constexpr int kCache = 8;  // costs kept in registers (independent loads, evaluated once)
+  float cc[kCache];
+#pragma unroll
+  for (int j = 0; j < kCache; ++j) cc[j] = (i0 + j < i1) ? region_cost(p, i0 + j) : 0.f;
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kCache; ++j) sum += cc[j];
+  for (int i = i0 + kCache; i < i1; ++i) sum += region_cost(p, i);
+  float incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  if (tid == 0) { s_range[0] = N; s_range[1] = N; }
+  __syncthreads();
+  float base = 0.f, total = 0.f;
+  for (int w = 0; w < nw; ++w) {
+    if (w < warp) base += s_warp[w];
+    total += s_warp[w];
+  }
+  float cum = base + incl - sum;  // cost before region i0
+  const float scale = (float)gridDim.x / total;
+  const int b = blockIdx.x;
+  auto visit = [&](int i, float c) {
+    const int owner = min((int)gridDim.x - 1, (int)(cum * scale));
+    if (owner >= b) atomicMin(&s_range[0], i);
+    if (owner >= b + 1) atomicMin(&s_range[1], i);
+    cum += c;
+  };
+#pragma unroll
+  for (int j = 0; j < kCache; ++j)
+    if (i0 + j < i1) visit(i0 + j, cc[j]);
+  for (int i = i0 + kCache; i < i1; ++i) visit(i, region_cost(p, i));
+  __syncthreads();
+  begin = s_range[0];
+  end = s_range[1];
+}
+
 // dynamic smem: [FwdTab x 2][barriers, stage offsets: 512 bytes][ring]
 template <typename T, int PH>
 __global__ void __launch_bounds__(512, (PH * VecOf<T>::n <= 32 ? 2 : 1))
@@ -592,8 +678,17 @@ roi_fuse_fwd_tma(const RoiFuseParams p, int ncons, int ring_bytes) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int PW = p.PW, PHW = PH * PW, C = p.C, RC = p.R * C;
   const int N = p.K * p.R;
-  const int n_my = ((int)blockIdx.x < N) ? (N - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   T* __restrict__ out = static_cast<T*>(p.out);
+  __shared__ int s_range[2];
+  __shared__ float s_warp[16];
+  int reg0, reg1, rstep = 1;
+  if (p.debug_skip & 16) {  // profiling aid: static striding
+    reg0 = blockIdx.x; rstep = gridDim.x;
+    reg1 = ((int)blockIdx.x < N) ? reg0 + ((N - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) : reg0;
+  } else {
+    balanced_range(p, N, s_range, s_warp, reg0, reg1);
+  }
+  const int n_my = reg1 - reg0;
 
   if (tid == 0) {
     for (int i = 0; i < kFwdSlots; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, ncons); }
@@ -607,9 +702,10 @@ roi_fuse_fwd_tma(const RoiFuseParams p, int ncons, int ring_bytes) {
     for (int i = 0; i < n_my; ++i) {
       const int buf = i & 1;
       if (i >= 2) mbar_wait(tab_empty + buf, ((i >> 1) - 1) & 1);
-      const int reg = blockIdx.x + i * gridDim.x;
+      const int reg = reg0 + i * rstep;
       Tab& tb = *reinterpret_cast<Tab*>(smem + buf * kTabBytes);
-      setup_region_warp(p, reg / p.R, reg % p.R, tb, ring_bytes, (int)sizeof(T), lane);
+      if (!((p.debug_skip & 32) && i >= 2))  // profiling aid: stale tables
+        setup_region_warp(p, reg / p.R, reg % p.R, tb, ring_bytes, (int)sizeof(T), lane);
       __threadfence_block();
       __syncwarp();
       if (lane == 0) mbar_arrive(tab_full + buf);
@@ -628,7 +724,7 @@ roi_fuse_fwd_tma(const RoiFuseParams p, int ncons, int ring_bytes) {
       const Tab& tb = *reinterpret_cast<const Tab*>(smem + buf * kTabBytes);
       const int mode = tb.mode;
       const int ymin = tb.hd.ymin, xmin = tb.hd.xmin;
-      const int nrows = tb.hd.ymax - ymin + 1, wlen = tb.hd.xmax - xmin + 1;
+      const int nrows = (p.debug_skip & 64) ? 0 : tb.hd.ymax - ymin + 1, wlen = tb.hd.xmax - xmin + 1;
       const int H = tb.hd.H, W = tb.hd.W, lvl = tb.hd.lvl, batch = tb.hd.g.batch;
       __syncwarp();
       if (lane == 0) mbar_arrive(tab_empty + buf);  // header copied to registers
@@ -657,12 +753,16 @@ roi_fuse_fwd_tma(const RoiFuseParams p, int ncons, int ring_bytes) {
         }
         head = off + bytes;
         if (lane == slot) my_off = off;
-        if (lane == 0) {
-          stage_off[slot] = off;
-          mbar_arrive_expect_tx(full + slot, bytes);
+        if (p.debug_skip & 2) {  // profiling aid: no copies
+          if (lane == 0) { stage_off[slot] = off; mbar_arrive(full + slot); }
+        } else {
+          if (lane == 0) {
+            stage_off[slot] = off;
+            mbar_arrive_expect_tx(full + slot, bytes);
+          }
+          for (uint32_t o = (uint32_t)lane * kFwdCopy; o < bytes; o += 32u * kFwdCopy)
+            bulk_g2s(ring + off + o, src + o, min((uint32_t)kFwdCopy, bytes - o), full + slot);
         }
-        for (uint32_t o = (uint32_t)lane * kFwdCopy; o < bytes; o += 32u * kFwdCopy)
-          bulk_g2s(ring + off + o, src + o, min((uint32_t)kFwdCopy, bytes - o), full + slot);
         src += src_step;
         ++issued;
       }
@@ -683,26 +783,26 @@ roi_fuse_fwd_tma(const RoiFuseParams p, int ncons, int ring_bytes) {
     mbar_wait(tab_full + buf, (i >> 1) & 1);
     const Tab& tb = *reinterpret_cast<const Tab*>(smem + buf * kTabBytes);
     const CtaHeader& hd = tb.hd;
-    const int reg = blockIdx.x + i * gridDim.x;
+    const int reg = reg0 + i * rstep;
     const int k = reg / p.R, r = reg - k * p.R;
     const int mode = tb.mode;
     if (mode == 3) {
-      const int nrows = hd.ymax - hd.ymin + 1;
+      const int nrows = (p.debug_skip & 64) ? 0 : hd.ymax - hd.ymin + 1;  // profiling aid: no rows
       const int nc = tb.tx.cnt[pw];
       const float* __restrict__ wxp = tb.tx.w + tb.tx.off[pw];
       const uint32_t tap0 = (uint32_t)((nc > 0 ? tb.tx.first[pw] - hd.xmin : 0) * C + (act ? c : 0)) * sizeof(T);
       T* __restrict__ o = act ? out + ((size_t)k * PHW + pw) * RC + (size_t)r * C + c : nullptr;
       FwdPipe pipe{full, empty, stage_off, ring};
-      switch (nc) {
-        case 0: fwd_consume_rows<T, PH, 0>(pipe, stage, nrows, tb.rowrec, wxp, tap0, C, o, (size_t)PW * RC); break;
-        case 1: fwd_consume_rows<T, PH, 1>(pipe, stage, nrows, tb.rowrec, wxp, tap0, C, o, (size_t)PW * RC); break;
-        case 2: fwd_consume_rows<T, PH, 2>(pipe, stage, nrows, tb.rowrec, wxp, tap0, C, o, (size_t)PW * RC); break;
-        case 3: fwd_consume_rows<T, PH, 3>(pipe, stage, nrows, tb.rowrec, wxp, tap0, C, o, (size_t)PW * RC); break;
-        case 4: fwd_consume_rows<T, PH, 4>(pipe, stage, nrows, tb.rowrec, wxp, tap0, C, o, (size_t)PW * RC); break;
-        case 5: fwd_consume_rows<T, PH, 5>(pipe, stage, nrows, tb.rowrec, wxp, tap0, C, o, (size_t)PW * RC); break;
-        case 6: fwd_consume_rows<T, PH, 6>(pipe, stage, nrows, tb.rowrec, wxp, tap0, C, o, (size_t)PW * RC); break;
-        case 7: fwd_consume_rows<T, PH, 7>(pipe, stage, nrows, tb.rowrec, wxp, tap0, C, o, (size_t)PW * RC); break;
-        default: fwd_consume_rows<T, PH, 8>(pipe, stage, nrows, tb.rowrec, wxp, tap0, C, o, (size_t)PW * RC); break;
+      switch ((p.debug_skip & 1) ? 0 : nc) {  // profiling aid: 0 taps == no math
+        case 0: fwd_consume_rows<T, PH, 0>(pipe, stage, nrows, tb.rowrec, tb.roww, wxp, tap0, C, o, (size_t)PW * RC); break;
+        case 1: fwd_consume_rows<T, PH, 1>(pipe, stage, nrows, tb.rowrec, tb.roww, wxp, tap0, C, o, (size_t)PW * RC); break;
+        case 2: fwd_consume_rows<T, PH, 2>(pipe, stage, nrows, tb.rowrec, tb.roww, wxp, tap0, C, o, (size_t)PW * RC); break;
+        case 3: fwd_consume_rows<T, PH, 3>(pipe, stage, nrows, tb.rowrec, tb.roww, wxp, tap0, C, o, (size_t)PW * RC); break;
+        case 4: fwd_consume_rows<T, PH, 4>(pipe, stage, nrows, tb.rowrec, tb.roww, wxp, tap0, C, o, (size_t)PW * RC); break;
+        case 5: fwd_consume_rows<T, PH, 5>(pipe, stage, nrows, tb.rowrec, tb.roww, wxp, tap0, C, o, (size_t)PW * RC); break;
+        case 6: fwd_consume_rows<T, PH, 6>(pipe, stage, nrows, tb.rowrec, tb.roww, wxp, tap0, C, o, (size_t)PW * RC); break;
+        case 7: fwd_consume_rows<T, PH, 7>(pipe, stage, nrows, tb.rowrec, tb.roww, wxp, tap0, C, o, (size_t)PW * RC); break;
+        default: fwd_consume_rows<T, PH, 8>(pipe, stage, nrows, tb.rowrec, tb.roww, wxp, tap0, C, o, (size_t)PW * RC); break;
       }
       stage += nrows;
     } else if (mode == 2) {
