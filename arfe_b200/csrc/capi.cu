@@ -114,6 +114,35 @@ int arfe_roi_fuse_forward(const void* const* feats, const int32_t* H, const int3
   return cuda_result(arfe::launch_roi_fuse_forward(p, dtype, layout, (cudaStream_t)stream), fn);
 }
 
+int arfe_roi_fuse_forward_plan(const void* const* feats, const int32_t* H, const int32_t* W,
+                               const float* spatial_scale, int L, int B, int C, const float* rois,
+                               int K, int regions, float facs, int PH, int PW, int sampling_ratio,
+                               float finest_scale, int dtype, void* out, int32_t* lvl_out,
+                               float* boxes_out, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  const char* fn = "arfe_roi_fuse_forward_plan";
+  arfe::RoiFuseParams p;
+  int rc = fill_roi_params(fn, p, H, W, spatial_scale, L, B, C, rois, K, regions, facs, PH, PW,
+                           sampling_ratio, finest_scale, dtype, ARFE_NHWC);
+  if (rc) return rc;
+  if (K == 0) return ARFE_OK;
+  REQUIRE(feats && out && workspace, ARFE_E_NULL, "%s: feats/out/workspace is NULL", fn);
+  REQUIRE(B >= 1, ARFE_E_SHAPE, "%s: B=0 with K>0", fn);
+  REQUIRE(C % (dtype == ARFE_F32 ? 4 : 8) == 0, ARFE_E_UNSUPPORTED, "%s: C must be a multiple of %d",
+          fn, dtype == ARFE_F32 ? 4 : 8);
+  for (int l = 0; l < L; ++l) {
+    REQUIRE(feats[l], ARFE_E_NULL, "%s: feats[%d] is NULL", fn, l);
+    REQUIRE(aligned(feats[l], 16), ARFE_E_ALIGN, "%s: feats[%d] must be 16-byte aligned", fn, l);
+    p.feats[l] = feats[l];
+  }
+  REQUIRE(aligned(out, 16) && aligned(rois, 4) && aligned(workspace, 256), ARFE_E_ALIGN,
+          "%s: out (16) / rois (4) / workspace (256) misaligned", fn);
+  REQUIRE(workspace_bytes >= arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W), ARFE_E_SHAPE,
+          "%s: workspace too small (%zu < %zu)", fn, workspace_bytes, arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W));
+  p.out = out; p.lvl_out = lvl_out; p.boxes_out = boxes_out; p.out_cl = 1;
+  return cuda_result(arfe::launch_roi_fuse_forward_plan(p, dtype, workspace, workspace_bytes, (cudaStream_t)stream), fn);
+}
+
 int arfe_roi_fuse_backward(const void* dout, int dout_layout, const int32_t* H, const int32_t* W,
                            const float* spatial_scale, int L, int B, int C, const float* rois,
                            int K, int regions, float facs, int PH, int PW, int sampling_ratio,
@@ -137,6 +166,10 @@ int arfe_roi_fuse_backward(const void* dout, int dout_layout, const int32_t* H, 
   return cuda_result(arfe::launch_roi_fuse_backward(p, dtype, layout, (cudaStream_t)stream), fn);
 }
 
+size_t arfe_roi_plan_bytes(int K, int regions, int L, int B, const int32_t* H, const int32_t* W) {
+  return arfe_roi_fuse_pull_workspace_bytes(K, regions, L, B, H, W);
+}
+
 size_t arfe_roi_fuse_pull_workspace_bytes(int K, int regions, int L, int B, const int32_t* H,
                                           const int32_t* W) {
   if (K <= 0 || (regions != 1 && regions != 3) || L < 1 || L > ARFE_MAX_LEVELS || B < 1 || !H || !W) return 0;
@@ -149,7 +182,7 @@ int arfe_roi_fuse_backward_pull(const void* dout, const int32_t* H, const int32_
                                 const float* spatial_scale, int L, int B, int C, const float* rois,
                                 int K, int regions, float facs, int PH, int PW, int sampling_ratio,
                                 float finest_scale, int dtype, float* const* dfeats,
-                                void* workspace, size_t workspace_bytes, void* stream) {
+                                void* workspace, size_t workspace_bytes, int plan_ready, void* stream) {
   const char* fn = "arfe_roi_fuse_backward_pull";
   arfe::RoiFuseParams p;
   int rc = fill_roi_params(fn, p, H, W, spatial_scale, L, B, C, rois, K, regions, facs, PH, PW,
@@ -176,7 +209,7 @@ int arfe_roi_fuse_backward_pull(const void* dout, const int32_t* H, const int32_
   REQUIRE(workspace_bytes >= arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W), ARFE_E_SHAPE,
           "%s: workspace too small (%zu < %zu)", fn, workspace_bytes, arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W));
   p.dout = dout; p.dout_cl = 1;
-  rc = cuda_result(arfe::launch_roi_fuse_backward_pull(p, dtype, workspace, workspace_bytes, (cudaStream_t)stream), fn);
+  rc = cuda_result(arfe::launch_roi_fuse_backward_pull(p, dtype, workspace, workspace_bytes, plan_ready, (cudaStream_t)stream), fn);
   if (rc) return rc;
   // regions whose tap tables did not fit the workspace records: atomic kernel, adds on top
   p.flag_list = arfe::roi_pull_flag_list(K, regions, L, B, H, W, workspace, &p.flag_count);

@@ -271,17 +271,16 @@ __device__ void fwd_direct_cl(const RoiFuseParams& p, const CtaHeader& hd, const
 }
 
 // dynamic smem: [CtaHeader][AxisTable y][AxisTable x][outs: bins_per_pass * opitch] (NCHW out only)
-template <typename T, bool kOutCL, int kOcc>
-__global__ void __launch_bounds__(kThreads, kOcc)
-roi_fuse_fwd_cl(const RoiFuseParams p, int opitch, int bins_per_pass) {
+template <typename T, bool kOutCL>
+__device__ __forceinline__ void fwd_region_cl(const RoiFuseParams& p, int opitch, int bins_per_pass,
+                                              int region, unsigned char* smem) {
   constexpr int V = VecOf<T>::n;
-  extern __shared__ __align__(16) unsigned char smem[];
   CtaHeader& hd = *reinterpret_cast<CtaHeader*>(smem);
   AxisTable& ty = *reinterpret_cast<AxisTable*>(smem + 128);
   AxisTable& tx = *reinterpret_cast<AxisTable*>(smem + 128 + sizeof(AxisTable));
   float* outs = reinterpret_cast<float*>(smem + kHdrBytes);
 
-  const int k = blockIdx.x / p.R, r = blockIdx.x % p.R;
+  const int k = region / p.R, r = region % p.R;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int PH = p.PH, PW = p.PW, PHW = PH * PW, C = p.C, RC = p.R * C;
   T* __restrict__ out = static_cast<T*>(p.out);
@@ -371,476 +370,21 @@ roi_fuse_fwd_cl(const RoiFuseParams p, int opitch, int bins_per_pass) {
   }
 }
 
-// ---------------------------------------------------------- forward (TMA)
-// Persistent CTAs (one or two per SM) walk the (RoI, region) list; channels-last
-// in and out.  In NHWC a row of a region's sampling window (wlen pixels x C
-// channels) is ONE contiguous piece of memory, so a PRODUCER warp streams the
-// windows row by row into a shared-memory byte ring with bulk async copies (TMA)
-// signalling an mbarrier per row; it runs ahead across regions, so rows stay in
-// flight without holding registers and every window byte crosses L2 -> SM
-// exactly once (the L1-cached kernel above re-fetches ~1.5x).  A SETUP warp
-// builds the tables of the next region (geometry, aggregated axis tables, dense
-// row weights) into the other of two table buffers while the current region is
-// being consumed.  CONSUMER warp == (output column pw, channel chunk): per row
-// it folds its (<= 8) column taps into t = sum_j wx[j] * f[row][x0 + j] from
-// shared memory and adds wy[ph][row] * t to the (usually <= 2) bin rows ph that
-// sample the row (zero weights skipped); its PH accumulators stay in registers
-// and are written once per region.
-// Regions the ring cannot serve (window row wider than half the ring, more than
-// kFwdMaxRows rows, a column with more than 8 taps, overflowing tables) take
-// the direct / generic paths inside the same kernel.
-constexpr int kFwdSlots = 16;
-constexpr int kFwdMaxRows = 64;
-constexpr int kFwdTaps = 8;
-constexpr int kFwdCopy = 8192;  // bytes per bulk copy
-constexpr int kFwdRowPitch = 16;  // >= PH
-
-struct FwdTab {
-  CtaHeader hd;
-  int mode;      // 0: zeros, 1: generic (tables overflowed), 2: direct, 3: ring
-  int pad[3];
-  AxisTable ty, tx;
-  alignas(16) int4 rowrec[kFwdMaxRows];  // per window row: {first bin row p0, bins n, w0 / count, w1 / count}
-  alignas(16) float roww[kFwdMaxRows * kFwdRowPitch];  // rows sampled by n > 2 bins (sub-pixel bins): dense weights / count
-};
-
-// Header + tables of region (k, r) by ONE warp (the CTA-wide twin is setup_cta).
-__device__ void setup_region_warp(const RoiFuseParams& p, int k, int r, FwdTab& tb,
-                                  int ring_bytes, int elt, int lane) {
-  CtaHeader& hd = tb.hd;
-  if (lane == 0) {
-    RegionBox bx = region_box(p.rois + 5 * (size_t)k, r, p.facs);
-    int lvl = (p.L == 1) ? 0 : map_roi_level(bx, p.L, p.finest_scale);
-    hd.lvl = lvl;
-    hd.overflow = 0;
-    if (lvl >= 0) {
-      hd.g = roi_geometry(bx, p.scale[lvl], p.PH, p.PW, p.sampling_ratio);
-      hd.H = p.H[lvl];
-      hd.W = p.W[lvl];
-      if (hd.g.batch < 0 || hd.g.batch >= p.B) hd.lvl = -2;
-    }
-    if (p.lvl_out) p.lvl_out[(size_t)r * p.K + k] = lvl;
-    if (p.boxes_out) {
-      float* o = p.boxes_out + ((size_t)r * p.K + k) * 5;
-      o[0] = bx.b; o[1] = bx.x1; o[2] = bx.y1; o[3] = bx.x2; o[4] = bx.y2;
-    }
-  }
-  __syncwarp();
-  int mode = 0;
-  if (hd.lvl >= 0) {
-    build_axis_table(tb.ty, p.PH, hd.g.start_h, hd.g.bin_h, hd.g.grid_h, hd.H, &hd.overflow, lane);
-    build_axis_table(tb.tx, p.PW, hd.g.start_w, hd.g.bin_w, hd.g.grid_w, hd.W, &hd.overflow, lane);
-    __syncwarp();
-    if (hd.overflow) {
-      mode = 1;
-    } else {
-      int ymin = 0x7fffffff, ymax = -1, xmin = 0x7fffffff, xmax = -1, mr = 0, mc = 0;
-      if (lane < p.PH && tb.ty.cnt[lane] > 0) {
-        ymin = tb.ty.first[lane]; ymax = ymin + tb.ty.cnt[lane] - 1; mr = tb.ty.cnt[lane];
-      }
-      if (lane < p.PW && tb.tx.cnt[lane] > 0) {
-        xmin = tb.tx.first[lane]; xmax = xmin + tb.tx.cnt[lane] - 1; mc = tb.tx.cnt[lane];
-      }
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, d));
-        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, d));
-        xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, d));
-        xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, d));
-        mr = max(mr, __shfl_xor_sync(0xffffffffu, mr, d));
-        mc = max(mc, __shfl_xor_sync(0xffffffffu, mc, d));
-      }
-      if (lane == 0) {
-        hd.ymin = ymin; hd.ymax = ymax; hd.xmin = xmin; hd.xmax = xmax;
-        hd.max_rows = mr;
-      }
-      if (ymax >= 0 && xmax >= 0) {
-        const int nrows = ymax - ymin + 1;
-        const long long row_bytes = (long long)(xmax - xmin + 1) * p.C * elt;
-        mode = (2 * row_bytes <= ring_bytes && nrows <= kFwdMaxRows && mc <= kFwdTaps) ? 3 : 2;
-        if (mode == 3) {
-          // transpose the row table: the (<= 2) bin rows sampling each window row
-          const float inv_count = 1.0f / hd.g.count;
-          for (int i = lane; i < nrows; i += 32) {
-            const int row = ymin + i;
-            int p0 = -1, cnt = 0;
-            for (int q = 0; q < p.PH; ++q)
-              if (tb.ty.cnt[q] > 0 && row >= tb.ty.first[q] && row < tb.ty.first[q] + tb.ty.cnt[q]) {
-                if (p0 < 0) p0 = q;
-                cnt = q - p0 + 1;
-              }
-            int4 rec = make_int4(p0 < 0 ? 0 : p0, cnt, 0, 0);
-            if (cnt > 0) rec.z = __float_as_int(tb.ty.w[tb.ty.off[p0] + row - tb.ty.first[p0]] * inv_count);
-            if (cnt > 1) rec.w = __float_as_int(tb.ty.w[tb.ty.off[p0 + 1] + row - tb.ty.first[p0 + 1]] * inv_count);
-            tb.rowrec[i] = rec;
-            if (cnt > 2) {  // sub-pixel bins: dense weights of this row
-              for (int q = 0; q < kFwdRowPitch; ++q) {
-                float w = 0.f;
-                if (q < p.PH) {
-                  const int j = row - tb.ty.first[q];
-                  if (j >= 0 && j < tb.ty.cnt[q]) w = tb.ty.w[tb.ty.off[q] + j] * inv_count;
-                }
-                tb.roww[i * kFwdRowPitch + q] = w;
-              }
-            }
-          }
-        }
-      }
-    }
-  }
-  if (lane == 0) tb.mode = mode;
-}
-
-struct FwdPipe {
-  uint64_t* full;
-  uint64_t* empty;
-  const uint32_t* stage_off;
-  const unsigned char* ring;
-};
-
-// acc[P0] += w0 * t, acc[P0 + 1] += w1 * t with P0 a run-time value: the
-// accumulators live in registers, so the bin row is resolved by a jump table.
-template <int PH, int V2>
-__device__ __forceinline__ void add_rows(uint64_t (&acc)[PH][V2], int p0, const uint64_t (&t)[V2],
-                                         float w0, float w1) {
-  const uint64_t w0p = pack2(w0, w0), w1p = pack2(w1, w1);
-#define ARFE_ROW_CASE(P)                                                         \
-  case P:                                                                        \
-    if constexpr (P < PH) {                                                      \
-      _Pragma("unroll") for (int u = 0; u < V2; ++u) {                           \
-        acc[P][u] = fma2(t[u], w0p, acc[P][u]);                                  \
-        if constexpr (P + 1 < PH) acc[P + 1][u] = fma2(t[u], w1p, acc[P + 1][u]); \
-      }                                                                          \
-    }                                                                            \
-    break;
-  switch (p0) {
-    ARFE_ROW_CASE(0) ARFE_ROW_CASE(1) ARFE_ROW_CASE(2) ARFE_ROW_CASE(3) ARFE_ROW_CASE(4)
-    ARFE_ROW_CASE(5) ARFE_ROW_CASE(6) ARFE_ROW_CASE(7) ARFE_ROW_CASE(8) ARFE_ROW_CASE(9)
-    ARFE_ROW_CASE(10) ARFE_ROW_CASE(11) ARFE_ROW_CASE(12) ARFE_ROW_CASE(13)
-    default: break;
-  }
-#undef ARFE_ROW_CASE
-}
-
-// One consumer warp, one region: NC column taps per row (compile-time), rows
-// streamed through the ring from stage `stage0` on.
-template <typename T, int PH, int NC>
-__device__ __forceinline__ void fwd_consume_rows(const FwdPipe& pp, int stage0, int nrows,
-                                                 const int4* __restrict__ rowrec,
-                                                 const float* __restrict__ roww,
-                                                 const float* __restrict__ wxp, uint32_t tap0, int C,
-                                                 T* __restrict__ o, size_t ostep) {
-  constexpr int V = VecOf<T>::n;
-  constexpr int V2 = V / 2;
-  const int lane = threadIdx.x & 31;
-  const uint32_t tap_step = (uint32_t)C * sizeof(T);
-  float wx[NC > 0 ? NC : 1];
-#pragma unroll
-  for (int j = 0; j < NC; ++j) wx[j] = wxp[j];
-  uint64_t acc[PH][V2];
-#pragma unroll
-  for (int ph = 0; ph < PH; ++ph)
-#pragma unroll
-    for (int u = 0; u < V2; ++u) acc[ph][u] = 0ull;
-  for (int rr = 0; rr < nrows; ++rr) {
-    const int stage = stage0 + rr;
-    const int slot = stage % kFwdSlots;
-    const int4 rec = rowrec[rr];
-    mbar_wait(pp.full + slot, (stage / kFwdSlots) & 1);
-    if (NC > 0 && rec.y > 0) {
-      const unsigned char* __restrict__ s0 = pp.ring + pp.stage_off[slot] + tap0;
-      uint64_t v[NC > 0 ? NC : 1][V2];
-#pragma unroll
-      for (int j = 0; j < NC; ++j) lds_pairs<T>(s0 + j * tap_step, v[j]);
-      uint64_t t[V2];
-#pragma unroll
-      for (int u = 0; u < V2; ++u) t[u] = mul2(v[0][u], pack2(wx[0], wx[0]));
-#pragma unroll
-      for (int j = 1; j < NC; ++j)
-#pragma unroll
-        for (int u = 0; u < V2; ++u) t[u] = fma2(v[j][u], pack2(wx[j], wx[j]), t[u]);
-      if (rec.y <= 2) {
-        add_rows<PH, V2>(acc, rec.x, t, __int_as_float(rec.z), __int_as_float(rec.w));
-      } else {
-        const float* __restrict__ rw = roww + rr * kFwdRowPitch;
-#pragma unroll
-        for (int ph = 0; ph < PH; ++ph) {
-          const float w = rw[ph];
-          if (w != 0.f) {
-            const uint64_t wp = pack2(w, w);
-#pragma unroll
-            for (int u = 0; u < V2; ++u) acc[ph][u] = fma2(t[u], wp, acc[ph][u]);
-          }
-        }
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(pp.empty + slot);
-  }
-  if (o) {
-#pragma unroll
-    for (int ph = 0; ph < PH; ++ph) {
-      float f[V];
-#pragma unroll
-      for (int u = 0; u < V2; ++u) unpack2(acc[ph][u], f[2 * u], f[2 * u + 1]);
-      st_vec<T>(o + (size_t)ph * ostep, f);
-    }
-  }
-}
-
-template <typename T>
-__device__ __noinline__ void fwd_direct_cl_call(const RoiFuseParams& p, const CtaHeader& hd,
-                                                const AxisTable& ty, const AxisTable& tx, int k,
-                                                int r, int nwarps) {
-  fwd_direct_cl<T>(p, hd, ty, tx, k, r, nwarps);
-}
-
-// Work estimate of region i: the pixels of its sampling window (+ a constant for
-// the per-region setup).  Cheap geometry only -- no tables.
-__device__ __forceinline__ float region_cost(const RoiFuseParams& p, int i) {
-  const int k = i / p.R, r = i - k * p.R;
-  const RegionBox bx = region_box(p.rois + 5 * (size_t)k, r, p.facs);
-  const int lvl = (p.L == 1) ? 0 : map_roi_level(bx, p.L, p.finest_scale);
-  if (lvl < 0) return 8.f;
-  const float s = p.scale[lvl];
-  float w = (bx.x2 - bx.x1) * s + 2.f, h = (bx.y2 - bx.y1) * s + 2.f;
-  w = fminf(fmaxf(w, 1.f), (float)p.W[lvl]);
-  h = fminf(fmaxf(h, 1.f), (float)p.H[lvl]);
-  return (w == w && h == h) ? w * h + 8.f : 8.f;
-}
-
-// Contiguous, cost-balanced partition of the N regions over the grid: CTA b owns
-// the regions whose cumulative cost (exclusive) falls into the b-th of gridDim.x
-// equal shares.  Every CTA evaluates the same arithmetic in the same order, so
-// the partition is consistent and deterministic without any global state.
-__device__ void balanced_range(const RoiFuseParams& p, int N, int* s_range, float* s_warp,
-                               int& begin, int& end) {
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-  const int chunk = (N + nt - 1) / nt;
-  const int i0 = min(N, tid * chunk), i1 = min(N, i0 + chunk);
-  constexpr int kCache = 8;  // costs kept in registers (independent loads, evaluated once)
-  float cc[kCache];
-#pragma unroll
-  for (int j = 0; j < kCache; ++j) cc[j] = (i0 + j < i1) ? region_cost(p, i0 + j) : 0.f;
-  float sum = 0.f;
-#pragma unroll
-  for (int j = 0; j < kCache; ++j) sum += cc[j];
-  for (int i = i0 + kCache; i < i1; ++i) sum += region_cost(p, i);
-  float incl = sum;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const float v = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += v;
-  }
-  if (lane == 31) s_warp[warp] = incl;
-  if (tid == 0) { s_range[0] = N; s_range[1] = N; }
-  __syncthreads();
-  float base = 0.f, total = 0.f;
-  for (int w = 0; w < nw; ++w) {
-    if (w < warp) base += s_warp[w];
-    total += s_warp[w];
-  }
-  float cum = base + incl - sum;  // cost before region i0
-  const float scale = (float)gridDim.x / total;
-  const int b = blockIdx.x;
-  auto visit = [&](int i, float c) {
-    const int owner = min((int)gridDim.x - 1, (int)(cum * scale));
-    if (owner >= b) atomicMin(&s_range[0], i);
-    if (owner >= b + 1) atomicMin(&s_range[1], i);
-    cum += c;
-  };
-#pragma unroll
-  for (int j = 0; j < kCache; ++j)
-    if (i0 + j < i1) visit(i0 + j, cc[j]);
-  for (int i = i0 + kCache; i < i1; ++i) visit(i, region_cost(p, i));
-  __syncthreads();
-  begin = s_range[0];
-  end = s_range[1];
-}
-
-// dynamic smem: [FwdTab x 2][barriers, stage offsets: 512 bytes][ring]
-template <typename T, int PH>
-__global__ void __launch_bounds__(512, (PH * VecOf<T>::n <= 32 ? 2 : 1))
-roi_fuse_fwd_tma(const RoiFuseParams p, int ncons, int ring_bytes) {
-  constexpr int V = VecOf<T>::n;
-  constexpr int V2 = V / 2;
-  using Tab = FwdTab;
-  constexpr int kTabBytes = ((int)sizeof(Tab) + 127) / 128 * 128;
+// Grid = one CTA per (RoI, region); or, behind the ring kernel (p.flag_list /
+// p.flag_count: the plan's fwd_list), a fixed small grid walking the regions the
+// ring kernel left out.
+template <typename T, bool kOutCL, int kOcc>
+__global__ void __launch_bounds__(kThreads, kOcc)
+roi_fuse_fwd_cl(const RoiFuseParams p, int opitch, int bins_per_pass) {
   extern __shared__ __align__(16) unsigned char smem[];
-  unsigned char* ctl = smem + 2 * kTabBytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ctl);
-  uint64_t* empty = full + kFwdSlots;
-  uint64_t* tab_full = empty + kFwdSlots;
-  uint64_t* tab_empty = tab_full + 2;
-  uint32_t* stage_off = reinterpret_cast<uint32_t*>(tab_empty + 2);
-  unsigned char* ring = ctl + 512;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int PW = p.PW, PHW = PH * PW, C = p.C, RC = p.R * C;
-  const int N = p.K * p.R;
-  T* __restrict__ out = static_cast<T*>(p.out);
-  __shared__ int s_range[2];
-  __shared__ float s_warp[16];
-  int reg0, reg1, rstep = 1;
-  if (p.debug_skip & 16) {  // profiling aid: static striding
-    reg0 = blockIdx.x; rstep = gridDim.x;
-    reg1 = ((int)blockIdx.x < N) ? reg0 + ((N - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) : reg0;
+  if (p.flag_list) {
+    const int n = *p.flag_count;
+    for (int j = blockIdx.x; j < n; j += gridDim.x) {
+      fwd_region_cl<T, kOutCL>(p, opitch, bins_per_pass, p.flag_list[j], smem);
+      __syncthreads();
+    }
   } else {
-    balanced_range(p, N, s_range, s_warp, reg0, reg1);
-  }
-  const int n_my = reg1 - reg0;
-
-  if (tid == 0) {
-    for (int i = 0; i < kFwdSlots; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, ncons); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tab_full + i, 1); mbar_init(tab_empty + i, ncons + 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (warp == ncons + 1) {
-    // --------------------------------------------------------------- setup
-    for (int i = 0; i < n_my; ++i) {
-      const int buf = i & 1;
-      if (i >= 2) mbar_wait(tab_empty + buf, ((i >> 1) - 1) & 1);
-      const int reg = reg0 + i * rstep;
-      Tab& tb = *reinterpret_cast<Tab*>(smem + buf * kTabBytes);
-      if (!((p.debug_skip & 32) && i >= 2))  // profiling aid: stale tables
-        setup_region_warp(p, reg / p.R, reg % p.R, tb, ring_bytes, (int)sizeof(T), lane);
-      __threadfence_block();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tab_full + buf);
-    }
-    return;
-  }
-
-  if (warp == ncons) {
-    // ------------------------------------------------------------ producer
-    uint32_t head = 0, tail = 0;  // live bytes of the ring: [tail, head) modulo wrap
-    uint32_t my_off = 0;          // lane j: ring offset of the stage in slot j
-    int issued = 0, released = 0; // stages (rows) issued / known to be consumed
-    for (int i = 0; i < n_my; ++i) {
-      const int buf = i & 1;
-      mbar_wait(tab_full + buf, (i >> 1) & 1);
-      const Tab& tb = *reinterpret_cast<const Tab*>(smem + buf * kTabBytes);
-      const int mode = tb.mode;
-      const int ymin = tb.hd.ymin, xmin = tb.hd.xmin;
-      const int nrows = (p.debug_skip & 64) ? 0 : tb.hd.ymax - ymin + 1, wlen = tb.hd.xmax - xmin + 1;
-      const int H = tb.hd.H, W = tb.hd.W, lvl = tb.hd.lvl, batch = tb.hd.g.batch;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tab_empty + buf);  // header copied to registers
-      if (mode != 3) continue;
-      const uint32_t bytes = (uint32_t)wlen * C * sizeof(T);
-      const unsigned char* __restrict__ src = reinterpret_cast<const unsigned char*>(
-          static_cast<const T*>(p.feats[lvl]) + (((size_t)batch * H + ymin) * W + xmin) * C);
-      const size_t src_step = (size_t)W * C * sizeof(T);
-      for (int rr = 0; rr < nrows; ++rr) {
-        const int slot = issued % kFwdSlots;
-        auto release_one = [&]() {
-          mbar_wait(empty + (released % kFwdSlots), (released / kFwdSlots) & 1);
-          ++released;
-          const uint32_t nxt = __shfl_sync(0xffffffffu, my_off, released % kFwdSlots);
-          tail = released < issued ? nxt : head;
-        };
-        while (released < issued - kFwdSlots + 1) release_one();
-        uint32_t off;
-        while (true) {
-          if (released == issued) { head = tail = 0; off = 0; break; }   // ring empty
-          if (head >= tail) {
-            if (head + bytes <= (uint32_t)ring_bytes) { off = head; break; }
-            if (bytes < tail) { off = 0; break; }                          // wrap
-          } else if (head + bytes < tail) { off = head; break; }
-          release_one();
-        }
-        head = off + bytes;
-        if (lane == slot) my_off = off;
-        if (p.debug_skip & 2) {  // profiling aid: no copies
-          if (lane == 0) { stage_off[slot] = off; mbar_arrive(full + slot); }
-        } else {
-          if (lane == 0) {
-            stage_off[slot] = off;
-            mbar_arrive_expect_tx(full + slot, bytes);
-          }
-          for (uint32_t o = (uint32_t)lane * kFwdCopy; o < bytes; o += 32u * kFwdCopy)
-            bulk_g2s(ring + off + o, src + o, min((uint32_t)kFwdCopy, bytes - o), full + slot);
-        }
-        src += src_step;
-        ++issued;
-      }
-    }
-    return;
-  }
-  if (warp > ncons + 1) return;
-
-  // ---------------------------------------------------------------- consumers
-  const int cwid = 32 * V;
-  const int pw = warp % PW, chunk = warp / PW;
-  const int c = chunk * cwid + lane * V;
-  const bool act = c < C;
-  const int ctid = tid, cthreads = ncons * 32;  // consumer threads: [0, ncons * 32)
-  int stage = 0;
-  for (int i = 0; i < n_my; ++i) {
-    const int buf = i & 1;
-    mbar_wait(tab_full + buf, (i >> 1) & 1);
-    const Tab& tb = *reinterpret_cast<const Tab*>(smem + buf * kTabBytes);
-    const CtaHeader& hd = tb.hd;
-    const int reg = reg0 + i * rstep;
-    const int k = reg / p.R, r = reg - k * p.R;
-    const int mode = tb.mode;
-    if (mode == 3) {
-      const int nrows = (p.debug_skip & 64) ? 0 : hd.ymax - hd.ymin + 1;  // profiling aid: no rows
-      const int nc = tb.tx.cnt[pw];
-      const float* __restrict__ wxp = tb.tx.w + tb.tx.off[pw];
-      const uint32_t tap0 = (uint32_t)((nc > 0 ? tb.tx.first[pw] - hd.xmin : 0) * C + (act ? c : 0)) * sizeof(T);
-      T* __restrict__ o = act ? out + ((size_t)k * PHW + pw) * RC + (size_t)r * C + c : nullptr;
-      FwdPipe pipe{full, empty, stage_off, ring};
-      switch ((p.debug_skip & 1) ? 0 : nc) {  // profiling aid: 0 taps == no math
-        case 0: fwd_consume_rows<T, PH, 0>(pipe, stage, nrows, tb.rowrec, tb.roww, wxp, tap0, C, o, (size_t)PW * RC); break;
-        case 1: fwd_consume_rows<T, PH, 1>(pipe, stage, nrows, tb.rowrec, tb.roww, wxp, tap0, C, o, (size_t)PW * RC); break;
-        case 2: fwd_consume_rows<T, PH, 2>(pipe, stage, nrows, tb.rowrec, tb.roww, wxp, tap0, C, o, (size_t)PW * RC); break;
-        case 3: fwd_consume_rows<T, PH, 3>(pipe, stage, nrows, tb.rowrec, tb.roww, wxp, tap0, C, o, (size_t)PW * RC); break;
-        case 4: fwd_consume_rows<T, PH, 4>(pipe, stage, nrows, tb.rowrec, tb.roww, wxp, tap0, C, o, (size_t)PW * RC); break;
-        case 5: fwd_consume_rows<T, PH, 5>(pipe, stage, nrows, tb.rowrec, tb.roww, wxp, tap0, C, o, (size_t)PW * RC); break;
-        case 6: fwd_consume_rows<T, PH, 6>(pipe, stage, nrows, tb.rowrec, tb.roww, wxp, tap0, C, o, (size_t)PW * RC); break;
-        case 7: fwd_consume_rows<T, PH, 7>(pipe, stage, nrows, tb.rowrec, tb.roww, wxp, tap0, C, o, (size_t)PW * RC); break;
-        default: fwd_consume_rows<T, PH, 8>(pipe, stage, nrows, tb.rowrec, tb.roww, wxp, tap0, C, o, (size_t)PW * RC); break;
-      }
-      stage += nrows;
-    } else if (mode == 2) {
-      fwd_direct_cl_call<T>(p, hd, tb.ty, tb.tx, k, r, ncons);
-    } else {
-      T* __restrict__ o = out + (size_t)k * PHW * RC + (size_t)r * C;
-      if (mode == 1) {  // tables did not fit: reference loop order, direct taps
-        const T* __restrict__ f = static_cast<const T*>(p.feats[hd.lvl]);
-        const int H = hd.H, W = hd.W;
-        const RoiGeom g = hd.g;
-        for (int e = ctid; e < C * PHW; e += cthreads) {
-          const int bin = e / C, cc = e - bin * C;
-          const int ph = bin / PW, pq = bin % PW;
-          float a0 = 0.f;
-          for (int iy = 0; iy < g.grid_h; ++iy) {
-            AxisTap a = axis_sample(g.start_h, ph, g.bin_h, iy, g.grid_h, H);
-            if (a.lo < 0) continue;
-            for (int ix = 0; ix < g.grid_w; ++ix) {
-              AxisTap b = axis_sample(g.start_w, pq, g.bin_w, ix, g.grid_w, W);
-              if (b.lo < 0) continue;
-              const size_t base = (size_t)g.batch * H * W;
-              a0 += a.wl * b.wl * to_f(f[(base + (size_t)a.lo * W + b.lo) * C + cc]) +
-                    a.wl * b.wh * to_f(f[(base + (size_t)a.lo * W + b.hi) * C + cc]) +
-                    a.wh * b.wl * to_f(f[(base + (size_t)a.hi * W + b.lo) * C + cc]) +
-                    a.wh * b.wh * to_f(f[(base + (size_t)a.hi * W + b.hi) * C + cc]);
-            }
-          }
-          o[(size_t)bin * RC + cc] = from_f<T>(__fdiv_rn(a0, g.count));
-        }
-      } else {
-        for (int e = ctid; e < C * PHW; e += cthreads) {
-          const int bin = e / C, cc = e - bin * C;
-          o[(size_t)bin * RC + cc] = from_f<T>(0.f);
-        }
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(tab_empty + buf);
+    fwd_region_cl<T, kOutCL>(p, opitch, bins_per_pass, blockIdx.x, smem);
   }
 }
 
@@ -853,6 +397,7 @@ roi_fuse_fwd_tma(const RoiFuseParams p, int ncons, int ring_bytes) {
 //   seg_ids : nblk * NK * kPrepBlock * 4     region ids per (prep block, key), index order;
 //   seg_cnt : nblk * NK * 4                  key = (level, image, 8-row band of the level)
 constexpr int kBandH = 8;       // rows per band == rows per pull tile
+constexpr int kFwdTaps = 8;     // column taps per bin the forward ring kernel takes
 constexpr int kTabLen = 256;    // per region: (row bin blocks) x (window rows) <= kTabLen, column weights <= kTabLen
 constexpr int kMaxBlk = 15;     // a row may be sampled by up to 2 * kMaxBlk bins (4-bit field)
 constexpr int kPrepBlock = 64;  // regions per id-segment block (== threads of roi_prep_kernel)
@@ -895,9 +440,13 @@ struct PullWs {
   int* seg_ids;
   int* seg_cnt;
   int2* tile_desc;            // per pull tile: {pool offset, stages} or {., -1}: the inline kernel serves it
-  int* counters;              // [0] next free pool entry, [1] flagged regions, [2] inline tiles (one memset)
+  int* counters;              // [0] next free pool entry, [1] inline tiles (backward); [2] regions for the
+                              // atomic fallback kernel, [3] regions for the forward fallback kernel (prep)
   int* flag_list;             // regions for the atomic fallback kernel
+  int* fwd_list;              // regions the forward ring kernel cannot serve
+  int* wsize;                 // per region: window rows << 16 | window columns (0: not served by the ring kernel)
   int* inline_list;           // tiles for the inline kernel
+  int fwd_wlen_cap;           // widest window the forward ring kernel takes (0: no forward planned)
   StageDesc* pool;            // [pool_cap] stage descriptors
   int pool_cap;
   int nblk;
@@ -941,12 +490,17 @@ inline size_t pull_ws_layout(int N, int L, int B, const int* H, const int* W, un
   const size_t o_td = take((size_t)ntiles * sizeof(int2));
   const size_t o_cur = take(16);
   const size_t o_fl = take((size_t)N * 4);
+  const size_t o_fwl = take((size_t)N * 4);
+  const size_t o_wsz = take((size_t)N * 4);
   const size_t o_il = take((size_t)ntiles * 4);
   const size_t o_pool = take((size_t)cap * sizeof(StageDesc));
   if (ws) {
     ws->tile_desc = reinterpret_cast<int2*>(base + o_td);
     ws->counters = reinterpret_cast<int*>(base + o_cur);
     ws->flag_list = reinterpret_cast<int*>(base + o_fl);
+    ws->fwd_list = reinterpret_cast<int*>(base + o_fwl);
+    ws->wsize = reinterpret_cast<int*>(base + o_wsz);
+    ws->fwd_wlen_cap = 0;
     ws->inline_list = reinterpret_cast<int*>(base + o_il);
     ws->pool = reinterpret_cast<StageDesc*>(base + o_pool);
     ws->pool_cap = cap;
@@ -1101,8 +655,337 @@ roi_prep_kernel(const RoiFuseParams p, const PullWs ws) {
     else h.flags = fit << 8;  // row bin blocks
   }
   if (tid == 0) {
+    int wsz = 0;
+    if (live) {  // can the forward ring kernel take it?
+      int maxc = 0;
+      for (int q = 0; q < p.PW; ++q) maxc = max(maxc, tx.cnt[q]);
+      const int wlen = h.xmax - h.xmin + 1;
+      if ((h.flags & 1) || hd.overflow || maxc > kFwdTaps || wlen > ws.fwd_wlen_cap) h.flags |= 2;
+      else wsz = ((h.ymax - h.ymin + 1) << 16) | wlen;
+    }
     ws.hdr[i] = h;
-    if (h.flags & 1) ws.flag_list[atomicAdd(ws.counters + 1, 1)] = i;
+    ws.wsize[i] = wsz;
+    if (h.flags & 1) ws.flag_list[atomicAdd(ws.counters + 2, 1)] = i;
+    if ((h.flags & 2) && ws.fwd_wlen_cap > 0) ws.fwd_list[atomicAdd(ws.counters + 3, 1)] = i;
+  }
+}
+
+// ------------------------------------------------------- forward (TMA ring)
+// Persistent CTAs (one or two per SM) walk a cost-balanced, contiguous range of
+// the (RoI, region) list; channels-last in and out; the region tables come from
+// the plan written by roi_prep_kernel (the same plan the backward uses).
+// In NHWC a row of a region's sampling window (wlen pixels x C channels) is ONE
+// contiguous piece of memory, so the PRODUCER warp streams the windows row by
+// row into a shared-memory byte ring with bulk async copies (TMA) signalling an
+// mbarrier per row, and the small tables of the next regions into one of
+// kFwdTabs table buffers; it runs ahead across regions, so rows stay in flight
+// without holding registers and every window byte crosses L2 -> SM exactly once
+// (the L1-cached kernel above re-fetches ~1.5x).  CONSUMER warp == (output
+// column pw, channel chunk): per row it folds its (<= 8) column taps into
+// t = sum_j wx[j] * f[row][x0 + j] from shared memory and adds wy[ph][row] * t
+// to the bin rows ph that sample the row (two per table block); its PH
+// accumulators stay in registers and are written once per region.
+// Regions the ring cannot serve (flag bit 1 in the plan: window row wider than
+// half the ring, a column with more than 8 taps, tables that did not fit) are
+// left to the L1-cached kernel, launched over the plan's fwd_list.
+constexpr int kFwdSlots = 16;
+constexpr int kFwdTabs = 3;
+constexpr int kFwdCopy = 8192;  // bytes per bulk copy
+
+struct __align__(128) FwdTab {
+  RegionHdr hdr;
+  int pad[8];
+  TapEntry rowtab[kTabLen];
+  ColBin colbin[kMaxPool];
+  float colw[kTabLen];
+};
+
+struct FwdPipe {
+  uint64_t* full;
+  uint64_t* empty;
+  const uint32_t* stage_off;
+  const unsigned char* ring;
+};
+
+// acc[P0] += w0 * t, acc[P0 + 1] += w1 * t with P0 a run-time value: the
+// accumulators live in registers, so the bin row is resolved by a jump table.
+template <int PH, int V2>
+__device__ __forceinline__ void add_rows(uint64_t (&acc)[PH][V2], int p0, const uint64_t (&t)[V2],
+                                         float w0, float w1) {
+  const uint64_t w0p = pack2(w0, w0), w1p = pack2(w1, w1);
+#define ARFE_ROW_CASE(P)                                                         \
+  case P:                                                                        \
+    if constexpr (P < PH) {                                                      \
+      _Pragma("unroll") for (int u = 0; u < V2; ++u) {                           \
+        acc[P][u] = fma2(t[u], w0p, acc[P][u]);                                  \
+        if constexpr (P + 1 < PH) acc[P + 1][u] = fma2(t[u], w1p, acc[P + 1][u]); \
+      }                                                                          \
+    }                                                                            \
+    break;
+  switch (p0) {
+    ARFE_ROW_CASE(0) ARFE_ROW_CASE(1) ARFE_ROW_CASE(2) ARFE_ROW_CASE(3) ARFE_ROW_CASE(4)
+    ARFE_ROW_CASE(5) ARFE_ROW_CASE(6) ARFE_ROW_CASE(7) ARFE_ROW_CASE(8) ARFE_ROW_CASE(9)
+    ARFE_ROW_CASE(10) ARFE_ROW_CASE(11) ARFE_ROW_CASE(12) ARFE_ROW_CASE(13)
+    default: break;
+  }
+#undef ARFE_ROW_CASE
+}
+
+// One consumer warp, one region: NC column taps per row (compile-time), rows
+// streamed through the ring from stage `stage0` on.
+template <typename T, int PH, int NC>
+__device__ __forceinline__ void fwd_consume_rows(const FwdPipe& pp, int stage0, int nrows, int nblk,
+                                                 const TapEntry* __restrict__ rowtab,
+                                                 const float* __restrict__ wxp, uint32_t tap0, int C,
+                                                 T* __restrict__ o, size_t ostep) {
+  constexpr int V = VecOf<T>::n;
+  constexpr int V2 = V / 2;
+  const int lane = threadIdx.x & 31;
+  const uint32_t tap_step = (uint32_t)C * sizeof(T);
+  float wx[NC > 0 ? NC : 1];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) wx[j] = wxp[j];
+  uint64_t acc[PH][V2];
+#pragma unroll
+  for (int ph = 0; ph < PH; ++ph)
+#pragma unroll
+    for (int u = 0; u < V2; ++u) acc[ph][u] = 0ull;
+  for (int rr = 0; rr < nrows; ++rr) {
+    const int stage = stage0 + rr;
+    const int slot = stage % kFwdSlots;
+    const int4 rec = *reinterpret_cast<const int4*>(rowtab + rr);
+    mbar_wait(pp.full + slot, (stage / kFwdSlots) & 1);
+    if (NC > 0 && rec.y > 0) {
+      const unsigned char* __restrict__ s0 = pp.ring + pp.stage_off[slot] + tap0;
+      uint64_t v[NC > 0 ? NC : 1][V2];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) lds_pairs<T>(s0 + j * tap_step, v[j]);
+      uint64_t t[V2];
+#pragma unroll
+      for (int u = 0; u < V2; ++u) t[u] = mul2(v[0][u], pack2(wx[0], wx[0]));
+#pragma unroll
+      for (int j = 1; j < NC; ++j)
+#pragma unroll
+        for (int u = 0; u < V2; ++u) t[u] = fma2(v[j][u], pack2(wx[j], wx[j]), t[u]);
+      add_rows<PH, V2>(acc, rec.x, t, __int_as_float(rec.z), __int_as_float(rec.w));
+      for (int rb = 1; rb < nblk; ++rb) {  // sub-pixel bins: more than two bin rows sample this row
+        const int4 r2 = *reinterpret_cast<const int4*>(rowtab + tab_index(rb, rr, nrows));
+        if (r2.y > 0) add_rows<PH, V2>(acc, r2.x, t, __int_as_float(r2.z), __int_as_float(r2.w));
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(pp.empty + slot);
+  }
+  if (o) {
+#pragma unroll
+    for (int ph = 0; ph < PH; ++ph) {
+      float f[V];
+#pragma unroll
+      for (int u = 0; u < V2; ++u) unpack2(acc[ph][u], f[2 * u], f[2 * u + 1]);
+      st_vec<T>(o + (size_t)ph * ostep, f);
+    }
+  }
+}
+
+// Contiguous, cost-balanced partition of the N regions over the grid: CTA b owns
+// the regions whose cumulative cost (exclusive) falls into the b-th of gridDim.x
+// equal shares; cost = window pixels (from the plan) + a constant.  Every CTA
+// evaluates the same arithmetic in the same order, so the partition is
+// consistent and deterministic without any global state.
+__device__ void balanced_range(const int* __restrict__ wsize, int N, int* s_range, float* s_warp,
+                               int& begin, int& end) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = (nt + 31) >> 5;
+  const int chunk = (N + nt - 1) / nt;
+  const int i0 = min(N, tid * chunk), i1 = min(N, i0 + chunk);
+  auto cost = [&](int i) -> float {
+    const int w = __ldg(wsize + i);
+    return (float)((w >> 16) * (w & 0xffff)) + 16.f;
+  };
+  float sum = 0.f;
+  for (int i = i0; i < i1; ++i) sum += cost(i);
+  float incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  if (tid == 0) { s_range[0] = N; s_range[1] = N; }
+  __syncthreads();
+  float base = 0.f, total = 0.f;
+  for (int w = 0; w < nw; ++w) {
+    if (w < warp) base += s_warp[w];
+    total += s_warp[w];
+  }
+  float cum = base + incl - sum;  // cost before region i0
+  const float scale = (float)gridDim.x / total;
+  const int b = blockIdx.x;
+  for (int i = i0; i < i1; ++i) {
+    const int owner = min((int)gridDim.x - 1, (int)(cum * scale));
+    if (owner >= b) atomicMin(&s_range[0], i);
+    if (owner >= b + 1) atomicMin(&s_range[1], i);
+    cum += cost(i);
+  }
+  __syncthreads();
+  begin = s_range[0];
+  end = s_range[1];
+}
+
+// dynamic smem: [FwdTab x kFwdTabs][barriers, stage offsets: 512 bytes][ring]
+template <typename T, int PH>
+__global__ void __launch_bounds__(480, (PH * VecOf<T>::n <= 32 ? 2 : 1))
+roi_fuse_fwd_ring(const RoiFuseParams p, const PullWs ws, int ncons, int ring_bytes) {
+  constexpr int V = VecOf<T>::n;
+  extern __shared__ __align__(16) unsigned char smem[];
+  FwdTab* tabs = reinterpret_cast<FwdTab*>(smem);
+  unsigned char* ctl = smem + kFwdTabs * sizeof(FwdTab);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ctl);
+  uint64_t* empty = full + kFwdSlots;
+  uint64_t* tab_full = empty + kFwdSlots;
+  uint64_t* tab_empty = tab_full + kFwdTabs;
+  uint32_t* stage_off = reinterpret_cast<uint32_t*>(tab_empty + kFwdTabs);
+  unsigned char* ring = ctl + 512;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int PW = p.PW, PHW = PH * PW, C = p.C, RC = p.R * C;
+  const int N = p.K * p.R;
+  T* __restrict__ out = static_cast<T*>(p.out);
+  __shared__ int s_range[2];
+  __shared__ float s_warp[16];
+  int reg0, reg1;
+  balanced_range(ws.wsize, N, s_range, s_warp, reg0, reg1);
+  const int n_my = reg1 - reg0;
+
+  if (tid == 0) {
+    for (int i = 0; i < kFwdSlots; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, ncons); }
+    for (int i = 0; i < kFwdTabs; ++i) { mbar_init(tab_full + i, 1); mbar_init(tab_empty + i, ncons); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == ncons) {
+    // ------------------------------------------------------------ producer
+    uint32_t head = 0, tail = 0;  // live bytes of the ring: [tail, head) modulo wrap
+    uint32_t my_off = 0;          // lane j: ring offset of the stage in slot j
+    int issued = 0, released = 0; // stages (rows) issued / known to be consumed
+    RegionHdr hq;                 // lane j: header of region (i & ~31) + j
+    hq.lvl = -1; hq.flags = 0; hq.batch = hq.ymin = hq.ymax = hq.xmin = hq.xmax = hq.src = 0;
+    for (int i = 0; i < n_my; ++i) {
+      if ((i & 31) == 0 && i + lane < n_my) hq = ws.hdr[reg0 + i + lane];
+      const int reg = reg0 + i;
+      RegionHdr h;
+      h.lvl = __shfl_sync(0xffffffffu, hq.lvl, i & 31);
+      h.batch = __shfl_sync(0xffffffffu, hq.batch, i & 31);
+      h.ymin = __shfl_sync(0xffffffffu, hq.ymin, i & 31);
+      h.ymax = __shfl_sync(0xffffffffu, hq.ymax, i & 31);
+      h.xmin = __shfl_sync(0xffffffffu, hq.xmin, i & 31);
+      h.xmax = __shfl_sync(0xffffffffu, hq.xmax, i & 31);
+      h.src = reg;
+      h.flags = __shfl_sync(0xffffffffu, hq.flags, i & 31);
+      const bool ringed = h.lvl >= 0 && (h.flags & 3) == 0;
+      const int nrows = h.ymax - h.ymin + 1, wlen = h.xmax - h.xmin + 1;
+      const int nblk = (h.flags >> 8) & 15;
+      const int buf = i % kFwdTabs;
+      if (i >= kFwdTabs) mbar_wait(tab_empty + buf, ((i / kFwdTabs) - 1) & 1);
+      FwdTab& tb = tabs[buf];
+      if (lane == 0) {
+        tb.hdr = h;
+        if (ringed) {
+          const uint32_t rb = (uint32_t)(nblk * nrows) * sizeof(TapEntry);
+          mbar_arrive_expect_tx(tab_full + buf, rb + sizeof(tb.colbin) + sizeof(tb.colw));
+          bulk_g2s(tb.rowtab, ws.rowtab + (size_t)reg * kTabLen, rb, tab_full + buf);
+          bulk_g2s(tb.colbin, ws.colbin + (size_t)reg * kMaxPool, sizeof(tb.colbin), tab_full + buf);
+          bulk_g2s(tb.colw, ws.colw + (size_t)reg * kTabLen, sizeof(tb.colw), tab_full + buf);
+        } else {
+          mbar_arrive(tab_full + buf);
+        }
+      }
+      if (!ringed) continue;
+      const uint32_t bytes = (uint32_t)wlen * C * sizeof(T);
+      const unsigned char* __restrict__ src = reinterpret_cast<const unsigned char*>(
+          static_cast<const T*>(p.feats[h.lvl]) +
+          (((size_t)h.batch * p.H[h.lvl] + h.ymin) * p.W[h.lvl] + h.xmin) * C);
+      const size_t src_step = (size_t)p.W[h.lvl] * C * sizeof(T);
+      for (int rr = 0; rr < nrows; ++rr) {
+        const int slot = issued % kFwdSlots;
+        auto release_one = [&]() {
+          mbar_wait(empty + (released % kFwdSlots), (released / kFwdSlots) & 1);
+          ++released;
+          const uint32_t nxt = __shfl_sync(0xffffffffu, my_off, released % kFwdSlots);
+          tail = released < issued ? nxt : head;
+        };
+        while (released < issued - kFwdSlots + 1) release_one();
+        uint32_t off;
+        while (true) {
+          if (released == issued) { head = tail = 0; off = 0; break; }   // ring empty
+          if (head >= tail) {
+            if (head + bytes <= (uint32_t)ring_bytes) { off = head; break; }
+            if (bytes < tail) { off = 0; break; }                          // wrap
+          } else if (head + bytes < tail) { off = head; break; }
+          release_one();
+        }
+        head = off + bytes;
+        if (lane == slot) my_off = off;
+        if (lane == 0) {
+          stage_off[slot] = off;
+          mbar_arrive_expect_tx(full + slot, bytes);
+        }
+        for (uint32_t o = (uint32_t)lane * kFwdCopy; o < bytes; o += 32u * kFwdCopy)
+          bulk_g2s(ring + off + o, src + o, min((uint32_t)kFwdCopy, bytes - o), full + slot);
+        src += src_step;
+        ++issued;
+      }
+    }
+    return;
+  }
+  if (warp > ncons) return;
+
+  // ---------------------------------------------------------------- consumers
+  const int cwid = 32 * V;
+  const int pw = warp % PW, chunk = warp / PW;
+  const int c = chunk * cwid + lane * V;
+  const bool act = c < C;
+  int stage = 0;
+  for (int i = 0; i < n_my; ++i) {
+    const int buf = i % kFwdTabs;
+    mbar_wait(tab_full + buf, (i / kFwdTabs) & 1);
+    const FwdTab& tb = tabs[buf];
+    const int reg = reg0 + i;
+    const int k = reg / p.R, r = reg - k * p.R;
+    const int lvl = tb.hdr.lvl, flags = tb.hdr.flags;
+    if (lvl >= 0 && (flags & 3) == 0) {
+      const int nrows = tb.hdr.ymax - tb.hdr.ymin + 1;
+      const ColBin cb = tb.colbin[pw];
+      const int nc = cb.cnt;
+      const float* __restrict__ wxp = tb.colw + cb.off;
+      const uint32_t tap0 = (uint32_t)((nc > 0 ? cb.first - tb.hdr.xmin : 0) * C + (act ? c : 0)) * sizeof(T);
+      T* __restrict__ o = act ? out + ((size_t)k * PHW + pw) * RC + (size_t)r * C + c : nullptr;
+      const int nblk = (flags >> 8) & 15;
+      FwdPipe pipe{full, empty, stage_off, ring};
+#define ARFE_CONSUME(NCC) \
+  fwd_consume_rows<T, PH, NCC>(pipe, stage, nrows, nblk, tb.rowtab, wxp, tap0, C, o, (size_t)PW * RC)
+      switch (nc) {
+        case 0: ARFE_CONSUME(0); break;
+        case 1: ARFE_CONSUME(1); break;
+        case 2: ARFE_CONSUME(2); break;
+        case 3: ARFE_CONSUME(3); break;
+        case 4: ARFE_CONSUME(4); break;
+        case 5: ARFE_CONSUME(5); break;
+        case 6: ARFE_CONSUME(6); break;
+        case 7: ARFE_CONSUME(7); break;
+        default: ARFE_CONSUME(8); break;
+      }
+#undef ARFE_CONSUME
+      stage += nrows;
+    } else if (lvl < 0) {  // nothing is pooled: zeros
+      T* __restrict__ o = out + (size_t)k * PHW * RC + (size_t)r * C;
+      for (int e = tid; e < C * PHW; e += ncons * 32) {
+        const int bin = e / C, cc = e - bin * C;
+        o[(size_t)bin * RC + cc] = from_f<T>(0.f);
+      }
+    }  // else: served by the L1-cached kernel over ws.fwd_list
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tab_empty + buf);
   }
 }
 
@@ -1393,7 +1276,7 @@ __device__ void bin_tile(ListSmem& sm, const RoiFuseParams& p, const PullWs& ws,
   ok = __syncthreads_and(ok);
   if (tid == 0) {
     ws.tile_desc[tm.tile_base + t] = make_int2(off, ok ? n : -1);
-    if (!ok) ws.inline_list[atomicAdd(ws.counters + 2, 1)] = tm.tile_base + t;
+    if (!ok) ws.inline_list[atomicAdd(ws.counters + 1, 1)] = tm.tile_base + t;
   }
 }
 
@@ -1696,7 +1579,7 @@ roi_bwd_pull_inline(const RoiFuseParams p, const PullWs ws, const TileMap tm4, c
   __shared__ ListSmem sm;
   __shared__ int4 rdesc[kTileH * kChunkR];
   __shared__ __align__(16) float cwt[kChunkR * kJ * kMaxTW];
-  const int n = ws.counters[2];
+  const int n = ws.counters[1];
   for (int j = blockIdx.x; j < n; j += gridDim.x) {
     const int t = ws.inline_list[j];
     if (t < nt4) pull_tile_inline<T, 4>(p, ws, tm4, t, sm, rdesc, cwt);
@@ -1709,40 +1592,9 @@ roi_bwd_pull_inline(const RoiFuseParams p, const PullWs ws, const TileMap tm4, c
 cudaError_t launch_roi_fuse_forward_cl(const RoiFuseParams& p, int dtype, int out_cl,
                                        cudaStream_t stream) {
   const int PHW = p.PH * p.PW;
-  const int grid = p.K * p.R;
+  int grid = p.K * p.R;
+  if (p.flag_list && grid > 296) grid = 296;  // behind the ring kernel: usually nothing to do
   cudaError_t e;
-  {
-    // TMA row-ring kernel: channels-last output, 7x7 / 14x14 bins, one consumer
-    // warp per (output column, channel chunk)
-    static const int use_tma = [] { const char* ev = getenv("ARFE_FWD_TMA"); return ev ? atoi(ev) : 1; }();
-    const int V = dtype == 0 ? 4 : 8;
-    const int ncons = p.PW * ((p.C + 32 * V - 1) / (32 * V));
-    if (use_tma && out_cl && (p.PH == 7 || p.PH == 14) && p.PH * V <= 64 && ncons <= 14) {
-      const int tab = ((int)sizeof(FwdTab) + 127) / 128 * 128;
-      const int fixed = 2 * tab + 512;
-      // two CTAs per SM (7x7 fp32: 28 accumulator registers per thread), else one
-      const int per_sm = p.PH * V <= 32 ? 2 : 1;
-      const int ring = (per_sm == 2 ? 108 * 1024 : 200 * 1024) - fixed;
-      const int smem = fixed + ring;
-      const int threads = (ncons + 2) * 32;
-      static const int sms = [] {
-        int dev = 0, n = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        return n;
-      }();
-      const int pgrid = grid < per_sm * sms ? grid : per_sm * sms;
-#define ARFE_FWD_TMA(TT, PHH)                                                               \
-  do {                                                                                      \
-    if ((e = set_smem(roi_fuse_fwd_tma<TT, PHH>, smem)) != cudaSuccess) return e;           \
-    roi_fuse_fwd_tma<TT, PHH><<<pgrid, threads, smem, stream>>>(p, ncons, ring);             \
-  } while (0)
-      if (dtype == 0) { if (p.PH == 7) ARFE_FWD_TMA(float, 7); else ARFE_FWD_TMA(float, 14); }
-      else ARFE_FWD_TMA(__nv_bfloat16, 7);
-#undef ARFE_FWD_TMA
-      return cudaGetLastError();
-    }
-  }
   int opitch = 0, bpp = PHW, smem = kHdrBytes;
   if (!out_cl) {
     opitch = p.C + 4;
@@ -1751,7 +1603,7 @@ cudaError_t launch_roi_fuse_forward_cl(const RoiFuseParams& p, int dtype, int ou
     if (bpp > PHW) bpp = PHW;
     smem += bpp * opitch * 4;
   }
-  static const int occ = [] { const char* e = getenv("ARFE_FWD_OCC"); return e ? atoi(e) : 4; }();
+  static const int occ = [] { const char* e = getenv("ARFE_FWD_OCC"); return e ? atoi(e) : 3; }();
 #define ARFE_FWD_CL1(TT, OC, OCC)                                                       \
   do {                                                                                  \
     if ((e = set_smem(roi_fuse_fwd_cl<TT, OC, OCC>, smem)) != cudaSuccess) return e;    \
@@ -1768,6 +1620,61 @@ cudaError_t launch_roi_fuse_forward_cl(const RoiFuseParams& p, int dtype, int ou
   return cudaGetLastError();
 }
 
+static cudaError_t launch_prep(const RoiFuseParams& p, const PullWs& ws, cudaStream_t stream) {
+  const int N = p.K * p.R;
+  const int prep_smem = ws.nkeys * (kPrepBlock / 32) * 4;
+  if (prep_smem > 160 * 1024 || ws.nblk > kMaxPrepBlocks) return cudaErrorInvalidValue;
+  cudaError_t e = set_smem(roi_prep_kernel, prep_smem);
+  if (e != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ws.counters + 2, 0, 8, stream)) != cudaSuccess) return e;
+  roi_prep_kernel<<<ws.nblk + N, kPrepThreads, prep_smem, stream>>>(p, ws);
+  return cudaGetLastError();
+}
+
+// Forward with a plan: roi_prep_kernel writes the region tables into the
+// workspace (the backward can reuse them: plan_ready), the ring kernel consumes
+// them, the L1-cached kernel serves the regions the ring kernel left out.
+// Channels-last features and output.
+cudaError_t launch_roi_fuse_forward_plan(const RoiFuseParams& p0, int dtype, void* workspace,
+                                         size_t workspace_bytes, cudaStream_t stream) {
+  RoiFuseParams p = p0;
+  const int N = p.K * p.R;
+  PullWs ws;
+  const size_t need = pull_ws_layout(N, p.L, p.B, p.H, p.W, static_cast<unsigned char*>(workspace), &ws);
+  if (need > workspace_bytes) return cudaErrorInvalidValue;
+  const int V = dtype == 0 ? 4 : 8, elt = dtype == 0 ? 4 : 2;
+  const int ncons = p.PW * ((p.C + 32 * V - 1) / (32 * V));
+  const bool ring_ok = (p.PH == 7 || p.PH == 14) && p.PH * V <= 64 && ncons <= 14;
+  // two CTAs per SM (7x7 fp32: 28 accumulator registers per thread), else one
+  const int per_sm = p.PH * V <= 32 ? 2 : 1;
+  const int fixed = kFwdTabs * (int)sizeof(FwdTab) + 512;
+  const int ring = (per_sm == 2 ? 108 * 1024 : 200 * 1024) - fixed;
+  ws.fwd_wlen_cap = ring_ok ? ring / (2 * p.C * elt) : 0;
+  cudaError_t e = launch_prep(p, ws, stream);
+  if (e != cudaSuccess) return e;
+  if (!ring_ok) return launch_roi_fuse_forward_cl(p, dtype, 1, stream);
+  static const int sms = [] {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  const int pgrid = N < per_sm * sms ? N : per_sm * sms;
+  const int smem = fixed + ring, threads = (ncons + 1) * 32;
+#define ARFE_FWD_RING(TT, PHH)                                                             \
+  do {                                                                                     \
+    if ((e = set_smem(roi_fuse_fwd_ring<TT, PHH>, smem)) != cudaSuccess) return e;         \
+    roi_fuse_fwd_ring<TT, PHH><<<pgrid, threads, smem, stream>>>(p, ws, ncons, ring);      \
+  } while (0)
+  if (dtype == 0) { if (p.PH == 7) ARFE_FWD_RING(float, 7); else ARFE_FWD_RING(float, 14); }
+  else ARFE_FWD_RING(__nv_bfloat16, 7);
+#undef ARFE_FWD_RING
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  p.flag_list = ws.fwd_list;
+  p.flag_count = ws.counters + 3;
+  return launch_roi_fuse_forward_cl(p, dtype, 1, stream);
+}
+
 size_t roi_pull_workspace_bytes(int K, int R, int L, int B, const int* H, const int* W) {
   return pull_ws_layout(K * R, L, B, H, W, nullptr, nullptr);
 }
@@ -1776,20 +1683,16 @@ size_t roi_pull_workspace_bytes(int K, int R, int L, int B, const int* H, const 
 // Regions whose tables did not fit are flagged in the workspace and added
 // afterwards by the atomic kernel.
 cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, void* workspace,
-                                          size_t workspace_bytes, cudaStream_t stream) {
+                                          size_t workspace_bytes, int plan_ready, cudaStream_t stream) {
   const int N = p.K * p.R;
   PullWs ws;
   const size_t need = pull_ws_layout(N, p.L, p.B, p.H, p.W, static_cast<unsigned char*>(workspace), &ws);
   if (need > workspace_bytes) return cudaErrorInvalidValue;
-  const int prep_smem = ws.nkeys * (kPrepBlock / 32) * 4;
-  if (prep_smem > 160 * 1024 || ws.nblk > kMaxPrepBlocks) return cudaErrorInvalidValue;
+  if (ws.nblk > kMaxPrepBlocks) return cudaErrorInvalidValue;
   if ((long long)p.K * p.PH * p.PW * p.R * p.C > 0x7fffffffLL) return cudaErrorInvalidValue;  // 32-bit dout offsets
-  cudaError_t e = set_smem(roi_prep_kernel, prep_smem);
-  if (e != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(ws.counters, 0, 16, stream)) != cudaSuccess) return e;
-  roi_prep_kernel<<<ws.nblk + N, kPrepThreads, prep_smem, stream>>>(p, ws);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(ws.counters, 0, 8, stream)) != cudaSuccess) return e;
+  if (!plan_ready && (e = launch_prep(p, ws, stream)) != cudaSuccess) return e;
   // Two tile shapes: the small upper-level maps carry ~40x more region-pixels per
   // tile than level 0, so they get narrow tiles and go first (heaviest level
   // first inside each launch); the big maps follow with wide tiles.
@@ -1844,7 +1747,7 @@ const int* roi_pull_flag_list(int K, int R, int L, int B, const int* H, const in
                               const int** count) {
   PullWs ws;
   pull_ws_layout(K * R, L, B, H, W, static_cast<unsigned char*>(workspace), &ws);
-  *count = ws.counters + 1;
+  *count = ws.counters + 2;
   return ws.flag_list;
 }
 

@@ -61,7 +61,23 @@ class _RoIFuseFunction(Function):
         ctx.meta = (oh, ow, tuple(spatial_scales), sample_num, regions, facs,
                     finest_scale, layout, dt, B, C, Hs, Ws, feats[0].dtype, fast)
         ctx.save_for_backward(rois)
-        if K > 0:
+        ctx.plan = None
+        if K > 0 and out_cl:
+            # channels-last in and out: plan + ring kernel; the plan (region tables in
+            # a device workspace) is kept for the backward
+            nbytes = L.lib().arfe_roi_plan_bytes(K, regions, len(feats), B, L.int_array(Hs),
+                                                 L.int_array(Ws))
+            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=out.device)
+            ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+            rc = L.lib().arfe_roi_fuse_forward_plan(
+                L.ptr_array(feats), L.int_array(Hs), L.int_array(Ws),
+                L.float_array(spatial_scales), len(feats), B, C, rois.data_ptr(),
+                K, regions, float(facs), oh, ow, int(sample_num), float(finest_scale), dt,
+                out.data_ptr(), None, None, ws_ptr, nbytes, L.stream_ptr(out.device))
+            L.check(rc, "arfe_roi_fuse_forward_plan")
+            if any(f.requires_grad for f in feats):
+                ctx.plan = (ws, ws_ptr, nbytes)
+        elif K > 0:
             rc = L.lib().arfe_roi_fuse_forward(
                 L.ptr_array(feats), L.int_array(Hs), L.int_array(Ws),
                 L.float_array(spatial_scales), len(feats), B, C, rois.data_ptr(),
@@ -88,16 +104,20 @@ class _RoIFuseFunction(Function):
         if fast and K > 0:
             # pull kernel: channels-last dout, every gradient element written once
             g = g.contiguous(memory_format=torch.channels_last)
-            nbytes = lib.arfe_roi_fuse_pull_workspace_bytes(K, regions, nlev, B, L.int_array(Hs),
-                                                            L.int_array(Ws))
-            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
-            ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+            if ctx.plan is not None:
+                ws, ws_ptr, nbytes = ctx.plan
+                ready = 1
+            else:
+                nbytes = lib.arfe_roi_plan_bytes(K, regions, nlev, B, L.int_array(Hs), L.int_array(Ws))
+                ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+                ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+                ready = 0
             dfeats = [torch.empty((B, C, Hs[l], Ws[l]), dtype=torch.float32, device=dev,
                                   memory_format=torch.channels_last) for l in range(nlev)]
             rc = lib.arfe_roi_fuse_backward_pull(
                 g.data_ptr(), L.int_array(Hs), L.int_array(Ws), L.float_array(scales), nlev, B,
                 C, rois.data_ptr(), K, regions, float(facs), oh, ow, int(sample_num),
-                float(finest_scale), dt, L.ptr_array(dfeats), ws_ptr, nbytes,
+                float(finest_scale), dt, L.ptr_array(dfeats), ws_ptr, nbytes, ready,
                 L.stream_ptr(dev))
             L.check(rc, "arfe_roi_fuse_backward_pull")
         else:

@@ -8,9 +8,10 @@ The convolutions / NonLocal2D / FCs between the kernels stay on PyTorch and are
 NOT part of the step (north_star); their outputs (bsf, gate pre-activations,
 relu(conv) of the context regions, incoming gradients) are synthetic inputs.
 
-Step (9 launches of our kernels):
-  fwd: gather -> apply -> roi_fuse (3 regions) -> gate
-  bwd: gate_bwd -> roi_fuse_bwd -> apply_bwd (2 launches) -> gather_bwd
+Step (channels-last: 14 launches of our kernels):
+  fwd: gather -> apply -> roi_fuse (3 regions: plan, ring kernel, left-out regions) -> gate
+  bwd: gate_bwd -> roi_fuse_bwd (bin, pull, inline tiles, flagged regions; reuses the
+       forward's plan) -> apply_bwd (2 launches) -> gather_bwd
 """
 import math
 
@@ -141,7 +142,7 @@ class TrainStep:
         self.dg1 = [e(B, 1, h, w, dtype=torch.float32) for h, w in self.shapes]
         self.dg2 = [e(B, 1, h, w, dtype=torch.float32) for h, w in self.shapes]
         self.dx = [e(B, C, h, w) for h, w in self.shapes]
-        self.ws_bytes = self.lib.arfe_roi_fuse_pull_workspace_bytes(
+        self.ws_bytes = self.lib.arfe_roi_plan_bytes(
             K, R, self.nlev, B, L.int_array([s[0] for s in self.shapes]),
             L.int_array([s[1] for s in self.shapes]))
         self.ws = torch.empty(self.ws_bytes + 256, dtype=torch.uint8, device=device)
@@ -175,6 +176,13 @@ class TrainStep:
             self.B, self.C, hr, wr, self.dt, self.layout, self.p_y, self.stream)
 
     def roi_fuse_fwd(self):
+        if self.cl:
+            # channels-last: plan + ring kernel; the plan stays in the workspace for the backward
+            self.planned = 1
+            return self.lib.arfe_roi_fuse_forward_plan(
+                self.p_y, self.H, self.W, self.scales, self.nlev, self.B, self.C,
+                self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt,
+                self.F.data_ptr(), None, None, self.ws_ptr, self.ws_bytes, self.stream)
         return self.lib.arfe_roi_fuse_forward(
             self.p_y, self.H, self.W, self.scales, self.nlev, self.B, self.C,
             self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt, self.layout,
@@ -196,7 +204,7 @@ class TrainStep:
             return self.lib.arfe_roi_fuse_backward_pull(
                 self.dF.data_ptr(), self.H, self.W, self.scales, self.nlev, self.B, self.C,
                 self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt,
-                self.p_dy, self.ws_ptr, self.ws_bytes, self.stream)
+                self.p_dy, self.ws_ptr, self.ws_bytes, getattr(self, "planned", 0), self.stream)
         return self.lib.arfe_roi_fuse_backward(
             self.dF.data_ptr(), L.ARFE_NCHW, self.H, self.W, self.scales, self.nlev, self.B,
             self.C, self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt,
@@ -246,10 +254,11 @@ class TrainStep:
         run("fpn_gather_bwd", self.fpn_gather_bwd)
 
     def launches_per_step(self):
-        """Kernels of libarfe_b200.so per step: gather 1, apply 1, roi fwd 1,
-        gate 2, roi bwd (prep + pull + flagged-region fallback = 3 | atomic 1),
+        """Kernels of libarfe_b200.so per step: gather 1, apply 1, roi fwd (plan +
+        ring + left-out regions = 3 | 1), gate 2, roi bwd (bin + pull + inline tiles +
+        flagged-region fallback = 4, the plan is the forward's | atomic 1),
         apply bwd 2, gather bwd 2 (vector kernel + small levels) | 1."""
-        return (1 + 1 + 1 + 2 + 3 + 2 + 1) if self.cl else (1 + 1 + 1 + 2 + 1 + 2 + 2)
+        return (1 + 1 + 3 + 2 + 4 + 2 + 1) if self.cl else (1 + 1 + 1 + 2 + 1 + 2 + 2)
 
     # -- algorithmic bytes per launch (DESIGN.md section 5) ------------------
     def algorithmic_bytes(self):

@@ -102,23 +102,43 @@ int arfe_roi_fuse_backward(const void* dout, int dout_layout, const int32_t* H,
                            float finest_scale, int dtype, int layout,
                            float* const* dfeats, void* stream);
 
+/* The RoI plan.  arfe_roi_fuse_forward_plan and arfe_roi_fuse_backward_pull share
+ * a caller-provided device workspace of arfe_roi_plan_bytes() bytes (256-byte
+ * aligned, owned by the caller, reusable after the stream passes the last call
+ * that reads it).  The forward writes the per-region tables (boxes, levels,
+ * sampling windows, aggregated bilinear weights) into it and consumes them; a
+ * backward for the SAME rois / shapes / pool size may reuse them
+ * (plan_ready = 1) instead of rebuilding them (plan_ready = 0).
+ * arfe_roi_fuse_pull_workspace_bytes is the same number (older name). */
+size_t arfe_roi_plan_bytes(int K, int regions, int L, int B, const int32_t* H, const int32_t* W);
+size_t arfe_roi_fuse_pull_workspace_bytes(int K, int regions, int L, int B,
+                                          const int32_t* H, const int32_t* W);
+
+/* Forward for channels-last tensors (feats ARFE_NHWC, out [K][PH][PW][regions*C]),
+ * same result as arfe_roi_fuse_forward; C a multiple of 4 (fp32) / 8 (bf16).
+ * One launch builds the plan, a persistent kernel streams every region's
+ * sampling window through shared memory with bulk async copies (each window
+ * byte is fetched once), a third serves the few regions that do not fit. */
+int arfe_roi_fuse_forward_plan(const void* const* feats, const int32_t* H, const int32_t* W,
+                               const float* spatial_scale, int L, int B, int C,
+                               const float* rois, int K, int regions, float facs,
+                               int PH, int PW, int sampling_ratio, float finest_scale,
+                               int dtype, void* out, int32_t* lvl_out, float* boxes_out,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* Atomic-free backward for channels-last tensors ("pull"): every element of
  * every dfeats[l] (fp32, ARFE_NHWC) is WRITTEN exactly once, in a fixed
  * summation order (deterministic, unlike the reference's atomicAdd,
  * roi_align_kernel_v2.cu:251-258); no zero-fill by the caller.
  * dout: [K][PH][PW][regions*C] (ARFE_NHWC), `dtype`; C a multiple of 4 / 8.
- * workspace: device scratch of at least arfe_roi_fuse_pull_workspace_bytes()
- * bytes, 256-byte aligned, owned by the caller, reusable after the stream
- * passes this call. */
-size_t arfe_roi_fuse_pull_workspace_bytes(int K, int regions, int L, int B,
-                                          const int32_t* H, const int32_t* W);
+ * workspace: see "The RoI plan" above. */
 int arfe_roi_fuse_backward_pull(const void* dout, const int32_t* H, const int32_t* W,
                                 const float* spatial_scale, int L, int B, int C,
                                 const float* rois, int K, int regions, float facs,
                                 int PH, int PW, int sampling_ratio,
                                 float finest_scale, int dtype,
                                 float* const* dfeats, void* workspace,
-                                size_t workspace_bytes, void* stream);
+                                size_t workspace_bytes, int plan_ready, void* stream);
 
 /* Operator-level twins of roi_align_ext.forward_v2 / backward_v2
  * (roi_align_ext.cpp:126-161; aligned=True only -- aligned=False is the legacy
