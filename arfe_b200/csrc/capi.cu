@@ -140,6 +140,10 @@ int arfe_roi_fuse_forward_plan(const void* const* feats, const int32_t* H, const
   REQUIRE(workspace_bytes >= arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W), ARFE_E_SHAPE,
           "%s: workspace too small (%zu < %zu)", fn, workspace_bytes, arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W));
   p.out = out; p.lvl_out = lvl_out; p.boxes_out = boxes_out; p.out_cl = 1;
+  {
+    const char* ev = getenv("ARFE_FWD_SKIP");  // profiling aid, default off
+    p.debug_skip = ev ? atoi(ev) : 0;
+  }
   return cuda_result(arfe::launch_roi_fuse_forward_plan(p, dtype, workspace, workspace_bytes, (cudaStream_t)stream), fn);
 }
 

@@ -143,6 +143,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// (Polling with one lane per warp + __syncwarp instead of all 32 lanes was
+// measured 2x slower: the divergent wait costs more than the extra polls.)
 // global -> shared bulk copy (TMA, no tensor map): 16-byte aligned, bytes % 16 == 0
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -441,7 +443,8 @@ struct PullWs {
   int* seg_cnt;
   int2* tile_desc;            // per pull tile: {pool offset, stages} or {., -1}: the inline kernel serves it
   int* counters;              // [0] next free pool entry, [1] inline tiles (backward); [2] regions for the
-                              // atomic fallback kernel, [3] regions for the forward fallback kernel (prep)
+                              // atomic fallback kernel, [3] regions for the forward fallback kernel,
+                              // [4] next region of the forward ring kernel (prep zeroes 2..4)
   int* flag_list;             // regions for the atomic fallback kernel
   int* fwd_list;              // regions the forward ring kernel cannot serve
   int* wsize;                 // per region: window rows << 16 | window columns (0: not served by the ring kernel)
@@ -488,7 +491,7 @@ inline size_t pull_ws_layout(int N, int L, int B, const int* H, const int* W, un
   const size_t o_cnt = take((size_t)nblk * nkeys * 4);
   const int ntiles = pull_tiles(L, B, H, W), cap = pull_pool_cap(N);
   const size_t o_td = take((size_t)ntiles * sizeof(int2));
-  const size_t o_cur = take(16);
+  const size_t o_cur = take(32);
   const size_t o_fl = take((size_t)N * 4);
   const size_t o_fwl = take((size_t)N * 4);
   const size_t o_wsz = take((size_t)N * 4);
@@ -657,10 +660,8 @@ roi_prep_kernel(const RoiFuseParams p, const PullWs ws) {
   if (tid == 0) {
     int wsz = 0;
     if (live) {  // can the forward ring kernel take it?
-      int maxc = 0;
-      for (int q = 0; q < p.PW; ++q) maxc = max(maxc, tx.cnt[q]);
       const int wlen = h.xmax - h.xmin + 1;
-      if ((h.flags & 1) || hd.overflow || maxc > kFwdTaps || wlen > ws.fwd_wlen_cap) h.flags |= 2;
+      if ((h.flags & 1) || hd.overflow || wlen > ws.fwd_wlen_cap) h.flags |= 2;
       else wsz = ((h.ymax - h.ymin + 1) << 16) | wlen;
     }
     ws.hdr[i] = h;
@@ -671,9 +672,9 @@ roi_prep_kernel(const RoiFuseParams p, const PullWs ws) {
 }
 
 // ------------------------------------------------------- forward (TMA ring)
-// Persistent CTAs (one or two per SM) walk a cost-balanced, contiguous range of
-// the (RoI, region) list; channels-last in and out; the region tables come from
-// the plan written by roi_prep_kernel (the same plan the backward uses).
+// Persistent CTAs (one or two per SM) take (RoI, region)s from a work counter in
+// the plan; channels-last in and out; the region tables come from the plan
+// written by roi_prep_kernel (the same plan the backward uses).
 // In NHWC a row of a region's sampling window (wlen pixels x C channels) is ONE
 // contiguous piece of memory, so the PRODUCER warp streams the windows row by
 // row into a shared-memory byte ring with bulk async copies (TMA) signalling an
@@ -731,25 +732,29 @@ __device__ __forceinline__ void add_rows(uint64_t (&acc)[PH][V2], int p0, const 
 #undef ARFE_ROW_CASE
 }
 
-// One consumer warp, one region: NC column taps per row (compile-time), rows
-// streamed through the ring from stage `stage0` on.
-template <typename T, int PH, int NC>
+// One consumer warp, one region: NC column taps per row (compile-time), NCH
+// channel chunks of 32 * V channels per lane set, rows streamed through the
+// ring from stage `stage0` on.
+template <typename T, int PH, int NC, int NCH>
 __device__ __forceinline__ void fwd_consume_rows(const FwdPipe& pp, int stage0, int nrows, int nblk,
                                                  const TapEntry* __restrict__ rowtab,
                                                  const float* __restrict__ wxp, uint32_t tap0, int C,
-                                                 T* __restrict__ o, size_t ostep) {
+                                                 T* __restrict__ o, size_t ostep, int nc_dyn = 0) {
   constexpr int V = VecOf<T>::n;
   constexpr int V2 = V / 2;
+  constexpr uint32_t kChunkBytes = 32 * V * sizeof(T);
   const int lane = threadIdx.x & 31;
   const uint32_t tap_step = (uint32_t)C * sizeof(T);
   float wx[NC > 0 ? NC : 1];
 #pragma unroll
   for (int j = 0; j < NC; ++j) wx[j] = wxp[j];
-  uint64_t acc[PH][V2];
+  uint64_t acc[NCH][PH][V2];
 #pragma unroll
-  for (int ph = 0; ph < PH; ++ph)
+  for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
-    for (int u = 0; u < V2; ++u) acc[ph][u] = 0ull;
+    for (int ph = 0; ph < PH; ++ph)
+#pragma unroll
+      for (int u = 0; u < V2; ++u) acc[ch][ph][u] = 0ull;
   for (int rr = 0; rr < nrows; ++rr) {
     const int stage = stage0 + rr;
     const int slot = stage % kFwdSlots;
@@ -757,20 +762,31 @@ __device__ __forceinline__ void fwd_consume_rows(const FwdPipe& pp, int stage0, 
     mbar_wait(pp.full + slot, (stage / kFwdSlots) & 1);
     if (NC > 0 && rec.y > 0) {
       const unsigned char* __restrict__ s0 = pp.ring + pp.stage_off[slot] + tap0;
-      uint64_t v[NC > 0 ? NC : 1][V2];
 #pragma unroll
-      for (int j = 0; j < NC; ++j) lds_pairs<T>(s0 + j * tap_step, v[j]);
-      uint64_t t[V2];
+      for (int ch = 0; ch < NCH; ++ch) {
+        const unsigned char* __restrict__ sc = s0 + ch * kChunkBytes;
+        uint64_t v[NC > 0 ? NC : 1][V2];
 #pragma unroll
-      for (int u = 0; u < V2; ++u) t[u] = mul2(v[0][u], pack2(wx[0], wx[0]));
+        for (int j = 0; j < NC; ++j) lds_pairs<T>(sc + j * tap_step, v[j]);
+        uint64_t t[V2];
 #pragma unroll
-      for (int j = 1; j < NC; ++j)
+        for (int u = 0; u < V2; ++u) t[u] = mul2(v[0][u], pack2(wx[0], wx[0]));
 #pragma unroll
-        for (int u = 0; u < V2; ++u) t[u] = fma2(v[j][u], pack2(wx[j], wx[j]), t[u]);
-      add_rows<PH, V2>(acc, rec.x, t, __int_as_float(rec.z), __int_as_float(rec.w));
-      for (int rb = 1; rb < nblk; ++rb) {  // sub-pixel bins: more than two bin rows sample this row
-        const int4 r2 = *reinterpret_cast<const int4*>(rowtab + tab_index(rb, rr, nrows));
-        if (r2.y > 0) add_rows<PH, V2>(acc, r2.x, t, __int_as_float(r2.z), __int_as_float(r2.w));
+        for (int j = 1; j < NC; ++j)
+#pragma unroll
+          for (int u = 0; u < V2; ++u) t[u] = fma2(v[j][u], pack2(wx[j], wx[j]), t[u]);
+        for (int j = NC; j < nc_dyn; ++j) {  // more than kFwdTaps taps: weights from shared memory
+          uint64_t vv[V2];
+          lds_pairs<T>(sc + j * tap_step, vv);
+          const float w = wxp[j];
+#pragma unroll
+          for (int u = 0; u < V2; ++u) t[u] = fma2(vv[u], pack2(w, w), t[u]);
+        }
+        add_rows<PH, V2>(acc[ch], rec.x, t, __int_as_float(rec.z), __int_as_float(rec.w));
+        for (int rb = 1; rb < nblk; ++rb) {  // sub-pixel bins: more than two bin rows sample this row
+          const int4 r2 = *reinterpret_cast<const int4*>(rowtab + tab_index(rb, rr, nrows));
+          if (r2.y > 0) add_rows<PH, V2>(acc[ch], r2.x, t, __int_as_float(r2.z), __int_as_float(r2.w));
+        }
       }
     }
     __syncwarp();
@@ -778,62 +794,22 @@ __device__ __forceinline__ void fwd_consume_rows(const FwdPipe& pp, int stage0, 
   }
   if (o) {
 #pragma unroll
-    for (int ph = 0; ph < PH; ++ph) {
-      float f[V];
+    for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
-      for (int u = 0; u < V2; ++u) unpack2(acc[ph][u], f[2 * u], f[2 * u + 1]);
-      st_vec<T>(o + (size_t)ph * ostep, f);
-    }
-  }
-}
-
-// Contiguous, cost-balanced partition of the N regions over the grid: CTA b owns
-// the regions whose cumulative cost (exclusive) falls into the b-th of gridDim.x
-// equal shares; cost = window pixels (from the plan) + a constant.  Every CTA
-// evaluates the same arithmetic in the same order, so the partition is
-// consistent and deterministic without any global state.
-__device__ void balanced_range(const int* __restrict__ wsize, int N, int* s_range, float* s_warp,
-                               int& begin, int& end) {
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = (nt + 31) >> 5;
-  const int chunk = (N + nt - 1) / nt;
-  const int i0 = min(N, tid * chunk), i1 = min(N, i0 + chunk);
-  auto cost = [&](int i) -> float {
-    const int w = __ldg(wsize + i);
-    return (float)((w >> 16) * (w & 0xffff)) + 16.f;
-  };
-  float sum = 0.f;
-  for (int i = i0; i < i1; ++i) sum += cost(i);
-  float incl = sum;
+      for (int ph = 0; ph < PH; ++ph) {
+        float f[V];
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const float v = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += v;
+        for (int u = 0; u < V2; ++u) unpack2(acc[ch][ph][u], f[2 * u], f[2 * u + 1]);
+        st_vec<T>(o + (size_t)ph * ostep + ch * (32 * V), f);
+      }
   }
-  if (lane == 31) s_warp[warp] = incl;
-  if (tid == 0) { s_range[0] = N; s_range[1] = N; }
-  __syncthreads();
-  float base = 0.f, total = 0.f;
-  for (int w = 0; w < nw; ++w) {
-    if (w < warp) base += s_warp[w];
-    total += s_warp[w];
-  }
-  float cum = base + incl - sum;  // cost before region i0
-  const float scale = (float)gridDim.x / total;
-  const int b = blockIdx.x;
-  for (int i = i0; i < i1; ++i) {
-    const int owner = min((int)gridDim.x - 1, (int)(cum * scale));
-    if (owner >= b) atomicMin(&s_range[0], i);
-    if (owner >= b + 1) atomicMin(&s_range[1], i);
-    cum += cost(i);
-  }
-  __syncthreads();
-  begin = s_range[0];
-  end = s_range[1];
 }
 
 // dynamic smem: [FwdTab x kFwdTabs][barriers, stage offsets: 512 bytes][ring]
-template <typename T, int PH>
-__global__ void __launch_bounds__(480, (PH * VecOf<T>::n <= 32 ? 2 : 1))
+// NCH = channel chunks per consumer warp: 2 halves the barrier operations per
+// byte (the per-row wait / arrive round trip, not bandwidth, bounds the pipeline).
+template <typename T, int PH, int NCH>
+__global__ void __launch_bounds__((NCH == 2 ? 256 : 480), ((PH * VecOf<T>::n * NCH <= 32 || NCH == 2) ? 2 : 1))
 roi_fuse_fwd_ring(const RoiFuseParams p, const PullWs ws, int ncons, int ring_bytes) {
   constexpr int V = VecOf<T>::n;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -850,11 +826,6 @@ roi_fuse_fwd_ring(const RoiFuseParams p, const PullWs ws, int ncons, int ring_by
   const int PW = p.PW, PHW = PH * PW, C = p.C, RC = p.R * C;
   const int N = p.K * p.R;
   T* __restrict__ out = static_cast<T*>(p.out);
-  __shared__ int s_range[2];
-  __shared__ float s_warp[16];
-  int reg0, reg1;
-  balanced_range(ws.wsize, N, s_range, s_warp, reg0, reg1);
-  const int n_my = reg1 - reg0;
 
   if (tid == 0) {
     for (int i = 0; i < kFwdSlots; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, ncons); }
@@ -868,26 +839,22 @@ roi_fuse_fwd_ring(const RoiFuseParams p, const PullWs ws, int ncons, int ring_by
     uint32_t head = 0, tail = 0;  // live bytes of the ring: [tail, head) modulo wrap
     uint32_t my_off = 0;          // lane j: ring offset of the stage in slot j
     int issued = 0, released = 0; // stages (rows) issued / known to be consumed
-    RegionHdr hq;                 // lane j: header of region (i & ~31) + j
-    hq.lvl = -1; hq.flags = 0; hq.batch = hq.ymin = hq.ymax = hq.xmin = hq.xmax = hq.src = 0;
-    for (int i = 0; i < n_my; ++i) {
-      if ((i & 31) == 0 && i + lane < n_my) hq = ws.hdr[reg0 + i + lane];
-      const int reg = reg0 + i;
-      RegionHdr h;
-      h.lvl = __shfl_sync(0xffffffffu, hq.lvl, i & 31);
-      h.batch = __shfl_sync(0xffffffffu, hq.batch, i & 31);
-      h.ymin = __shfl_sync(0xffffffffu, hq.ymin, i & 31);
-      h.ymax = __shfl_sync(0xffffffffu, hq.ymax, i & 31);
-      h.xmin = __shfl_sync(0xffffffffu, hq.xmin, i & 31);
-      h.xmax = __shfl_sync(0xffffffffu, hq.xmax, i & 31);
-      h.src = reg;
-      h.flags = __shfl_sync(0xffffffffu, hq.flags, i & 31);
-      const bool ringed = h.lvl >= 0 && (h.flags & 3) == 0;
-      const int nrows = h.ymax - h.ymin + 1, wlen = h.xmax - h.xmin + 1;
-      const int nblk = (h.flags >> 8) & 15;
+    for (int i = 0;; ++i) {
+      // regions are handed out dynamically: the next one of the plan's counter
+      int reg = 0;
+      if (lane == 0) reg = atomicAdd(ws.counters + 4, 1);
+      reg = __shfl_sync(0xffffffffu, reg, 0);
       const int buf = i % kFwdTabs;
       if (i >= kFwdTabs) mbar_wait(tab_empty + buf, ((i / kFwdTabs) - 1) & 1);
       FwdTab& tb = tabs[buf];
+      if (reg >= N) {  // no more work: tell the consumers
+        if (lane == 0) { tb.hdr.lvl = -9; mbar_arrive(tab_full + buf); }
+        break;
+      }
+      const RegionHdr h = ws.hdr[reg];
+      const bool ringed = h.lvl >= 0 && (h.flags & 3) == 0;
+      const int nrows = h.ymax - h.ymin + 1, wlen = h.xmax - h.xmin + 1;
+      const int nblk = (h.flags >> 8) & 15;
       if (lane == 0) {
         tb.hdr = h;
         if (ringed) {
@@ -926,12 +893,16 @@ roi_fuse_fwd_ring(const RoiFuseParams p, const PullWs ws, int ncons, int ring_by
         }
         head = off + bytes;
         if (lane == slot) my_off = off;
-        if (lane == 0) {
-          stage_off[slot] = off;
-          mbar_arrive_expect_tx(full + slot, bytes);
+        if (p.debug_skip & 2) {  // profiling aid: no copies
+          if (lane == 0) { stage_off[slot] = off; mbar_arrive(full + slot); }
+        } else {
+          if (lane == 0) {
+            stage_off[slot] = off;
+            mbar_arrive_expect_tx(full + slot, bytes);
+          }
+          for (uint32_t o = (uint32_t)lane * kFwdCopy; o < bytes; o += 32u * kFwdCopy)
+            bulk_g2s(ring + off + o, src + o, min((uint32_t)kFwdCopy, bytes - o), full + slot);
         }
-        for (uint32_t o = (uint32_t)lane * kFwdCopy; o < bytes; o += 32u * kFwdCopy)
-          bulk_g2s(ring + off + o, src + o, min((uint32_t)kFwdCopy, bytes - o), full + slot);
         src += src_step;
         ++issued;
       }
@@ -941,18 +912,19 @@ roi_fuse_fwd_ring(const RoiFuseParams p, const PullWs ws, int ncons, int ring_by
   if (warp > ncons) return;
 
   // ---------------------------------------------------------------- consumers
-  const int cwid = 32 * V;
+  const int cwid = 32 * V * NCH;
   const int pw = warp % PW, chunk = warp / PW;
   const int c = chunk * cwid + lane * V;
-  const bool act = c < C;
+  const bool act = c < C;  // NCH == 2 requires C % (64 * V) == 0 (launcher)
   int stage = 0;
-  for (int i = 0; i < n_my; ++i) {
+  for (int i = 0;; ++i) {
     const int buf = i % kFwdTabs;
     mbar_wait(tab_full + buf, (i / kFwdTabs) & 1);
     const FwdTab& tb = tabs[buf];
-    const int reg = reg0 + i;
-    const int k = reg / p.R, r = reg - k * p.R;
     const int lvl = tb.hdr.lvl, flags = tb.hdr.flags;
+    if (lvl == -9) break;  // no more work
+    const int reg = tb.hdr.src;
+    const int k = reg / p.R, r = reg - k * p.R;
     if (lvl >= 0 && (flags & 3) == 0) {
       const int nrows = tb.hdr.ymax - tb.hdr.ymin + 1;
       const ColBin cb = tb.colbin[pw];
@@ -963,8 +935,8 @@ roi_fuse_fwd_ring(const RoiFuseParams p, const PullWs ws, int ncons, int ring_by
       const int nblk = (flags >> 8) & 15;
       FwdPipe pipe{full, empty, stage_off, ring};
 #define ARFE_CONSUME(NCC) \
-  fwd_consume_rows<T, PH, NCC>(pipe, stage, nrows, nblk, tb.rowtab, wxp, tap0, C, o, (size_t)PW * RC)
-      switch (nc) {
+  fwd_consume_rows<T, PH, NCC, NCH>(pipe, stage, nrows, nblk, tb.rowtab, wxp, tap0, C, o, (size_t)PW * RC)
+      switch ((p.debug_skip & 1) ? 0 : nc) {  // profiling aid: 0 taps == no math
         case 0: ARFE_CONSUME(0); break;
         case 1: ARFE_CONSUME(1); break;
         case 2: ARFE_CONSUME(2); break;
@@ -973,7 +945,10 @@ roi_fuse_fwd_ring(const RoiFuseParams p, const PullWs ws, int ncons, int ring_by
         case 5: ARFE_CONSUME(5); break;
         case 6: ARFE_CONSUME(6); break;
         case 7: ARFE_CONSUME(7); break;
-        default: ARFE_CONSUME(8); break;
+        case 8: ARFE_CONSUME(8); break;
+        default:
+          fwd_consume_rows<T, PH, 8, NCH>(pipe, stage, nrows, nblk, tb.rowtab, wxp, tap0, C, o, (size_t)PW * RC, nc);
+          break;
       }
 #undef ARFE_CONSUME
       stage += nrows;
@@ -1626,7 +1601,7 @@ static cudaError_t launch_prep(const RoiFuseParams& p, const PullWs& ws, cudaStr
   if (prep_smem > 160 * 1024 || ws.nblk > kMaxPrepBlocks) return cudaErrorInvalidValue;
   cudaError_t e = set_smem(roi_prep_kernel, prep_smem);
   if (e != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(ws.counters + 2, 0, 8, stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ws.counters + 2, 0, 12, stream)) != cudaSuccess) return e;
   roi_prep_kernel<<<ws.nblk + N, kPrepThreads, prep_smem, stream>>>(p, ws);
   return cudaGetLastError();
 }
@@ -1643,13 +1618,15 @@ cudaError_t launch_roi_fuse_forward_plan(const RoiFuseParams& p0, int dtype, voi
   const size_t need = pull_ws_layout(N, p.L, p.B, p.H, p.W, static_cast<unsigned char*>(workspace), &ws);
   if (need > workspace_bytes) return cudaErrorInvalidValue;
   const int V = dtype == 0 ? 4 : 8, elt = dtype == 0 ? 4 : 2;
-  const int ncons = p.PW * ((p.C + 32 * V - 1) / (32 * V));
-  const bool ring_ok = (p.PH == 7 || p.PH == 14) && p.PH * V <= 64 && ncons <= 14;
-  // two CTAs per SM (7x7 fp32: 28 accumulator registers per thread), else one
-  const int per_sm = p.PH * V <= 32 ? 2 : 1;
+  // consumer warp == (output column, channel chunk pair | chunk)
+  const int nch = (p.C % (64 * V) == 0 && p.PH * V * 2 <= 64) ? 2 : 1;
+  const int ncons = p.PW * ((p.C + 32 * V * nch - 1) / (32 * V * nch));
+  const bool ring_ok = (p.PH == 7 || p.PH == 14) && p.PH * V <= 64 && ncons <= (nch == 2 ? 7 : 14);
+  // two CTAs per SM when the accumulators leave room (7x7 fp32), else one
+  const int per_sm = (p.PH * V * nch <= 32 || nch == 2) ? 2 : 1;
   const int fixed = kFwdTabs * (int)sizeof(FwdTab) + 512;
   const int ring = (per_sm == 2 ? 108 * 1024 : 200 * 1024) - fixed;
-  ws.fwd_wlen_cap = ring_ok ? ring / (2 * p.C * elt) : 0;
+  ws.fwd_wlen_cap = ring_ok ? ring / (p.C * elt) : 0;  // a window row must fit the ring
   cudaError_t e = launch_prep(p, ws, stream);
   if (e != cudaSuccess) return e;
   if (!ring_ok) return launch_roi_fuse_forward_cl(p, dtype, 1, stream);
@@ -1661,13 +1638,17 @@ cudaError_t launch_roi_fuse_forward_plan(const RoiFuseParams& p0, int dtype, voi
   }();
   const int pgrid = N < per_sm * sms ? N : per_sm * sms;
   const int smem = fixed + ring, threads = (ncons + 1) * 32;
-#define ARFE_FWD_RING(TT, PHH)                                                             \
-  do {                                                                                     \
-    if ((e = set_smem(roi_fuse_fwd_ring<TT, PHH>, smem)) != cudaSuccess) return e;         \
-    roi_fuse_fwd_ring<TT, PHH><<<pgrid, threads, smem, stream>>>(p, ws, ncons, ring);      \
+#define ARFE_FWD_RING(TT, PHH, NCHH)                                                             \
+  do {                                                                                           \
+    if ((e = set_smem(roi_fuse_fwd_ring<TT, PHH, NCHH>, smem)) != cudaSuccess) return e;         \
+    roi_fuse_fwd_ring<TT, PHH, NCHH><<<pgrid, threads, smem, stream>>>(p, ws, ncons, ring);      \
   } while (0)
-  if (dtype == 0) { if (p.PH == 7) ARFE_FWD_RING(float, 7); else ARFE_FWD_RING(float, 14); }
-  else ARFE_FWD_RING(__nv_bfloat16, 7);
+  if (dtype == 0) {
+    if (p.PH == 7) { if (nch == 2) ARFE_FWD_RING(float, 7, 2); else ARFE_FWD_RING(float, 7, 1); }
+    else ARFE_FWD_RING(float, 14, 1);
+  } else {
+    ARFE_FWD_RING(__nv_bfloat16, 7, 1);
+  }
 #undef ARFE_FWD_RING
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   p.flag_list = ws.fwd_list;
