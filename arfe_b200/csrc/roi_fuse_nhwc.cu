@@ -131,6 +131,19 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   uint32_t done;
+#ifdef ARFE_MBAR_TEST_WAIT
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+#else
   do {
     asm volatile(
         "{\n"
@@ -142,6 +155,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(a), "r"(parity)
         : "memory");
   } while (!done);
+#endif
 }
 // (Polling with one lane per warp + __syncwarp instead of all 32 lanes was
 // measured 2x slower: the divergent wait costs more than the extra polls.)
@@ -839,34 +853,42 @@ roi_fuse_fwd_ring(const RoiFuseParams p, const PullWs ws, int ncons, int ring_by
     uint32_t head = 0, tail = 0;  // live bytes of the ring: [tail, head) modulo wrap
     uint32_t my_off = 0;          // lane j: ring offset of the stage in slot j
     int issued = 0, released = 0; // stages (rows) issued / known to be consumed
-    for (int i = 0;; ++i) {
-      // regions are handed out dynamically: the next one of the plan's counter
-      int reg = 0;
-      if (lane == 0) reg = atomicAdd(ws.counters + 4, 1);
-      reg = __shfl_sync(0xffffffffu, reg, 0);
-      const int buf = i % kFwdTabs;
-      if (i >= kFwdTabs) mbar_wait(tab_empty + buf, ((i / kFwdTabs) - 1) & 1);
+    // Regions are handed out dynamically from the plan's counter.  The claim of
+    // region i + 2 and the table copies of region i + 1 (header, row table,
+    // column table: fixed 5.4 KB straight from the plan) are issued before the
+    // rows of region i, so neither the atomic nor the header fetch sits on the
+    // row stream's critical path.
+    auto claim = [&]() -> int { return lane == 0 ? atomicAdd(ws.counters + 4, 1) : 0; };
+    auto issue_tables = [&](int reg, int j) {  // tables of the j-th region of this CTA
+      const int buf = j % kFwdTabs;
+      if (j >= kFwdTabs) mbar_wait(tab_empty + buf, ((j / kFwdTabs) - 1) & 1);
       FwdTab& tb = tabs[buf];
-      if (reg >= N) {  // no more work: tell the consumers
-        if (lane == 0) { tb.hdr.lvl = -9; mbar_arrive(tab_full + buf); }
-        break;
-      }
-      const RegionHdr h = ws.hdr[reg];
-      const bool ringed = h.lvl >= 0 && (h.flags & 3) == 0;
-      const int nrows = h.ymax - h.ymin + 1, wlen = h.xmax - h.xmin + 1;
-      const int nblk = (h.flags >> 8) & 15;
       if (lane == 0) {
-        tb.hdr = h;
-        if (ringed) {
-          const uint32_t rb = (uint32_t)(nblk * nrows) * sizeof(TapEntry);
-          mbar_arrive_expect_tx(tab_full + buf, rb + sizeof(tb.colbin) + sizeof(tb.colw));
-          bulk_g2s(tb.rowtab, ws.rowtab + (size_t)reg * kTabLen, rb, tab_full + buf);
+        if (reg >= N) {  // no more work: tell the consumers (and ourselves)
+          tb.hdr.lvl = -9;
+          mbar_arrive(tab_full + buf);
+        } else {
+          mbar_arrive_expect_tx(tab_full + buf, sizeof(RegionHdr) + sizeof(tb.rowtab) + sizeof(tb.colbin) + sizeof(tb.colw));
+          bulk_g2s(&tb.hdr, ws.hdr + reg, sizeof(RegionHdr), tab_full + buf);
+          bulk_g2s(tb.rowtab, ws.rowtab + (size_t)reg * kTabLen, sizeof(tb.rowtab), tab_full + buf);
           bulk_g2s(tb.colbin, ws.colbin + (size_t)reg * kMaxPool, sizeof(tb.colbin), tab_full + buf);
           bulk_g2s(tb.colw, ws.colw + (size_t)reg * kTabLen, sizeof(tb.colw), tab_full + buf);
-        } else {
-          mbar_arrive(tab_full + buf);
         }
       }
+    };
+    int c_next = claim();
+    issue_tables(__shfl_sync(0xffffffffu, c_next, 0), 0);
+    c_next = claim();
+    for (int i = 0;; ++i) {
+      const int reg_next = __shfl_sync(0xffffffffu, c_next, 0);
+      c_next = claim();
+      issue_tables(reg_next, i + 1);
+      const int buf = i % kFwdTabs;
+      mbar_wait(tab_full + buf, (i / kFwdTabs) & 1);
+      const RegionHdr h = tabs[buf].hdr;
+      if (h.lvl == -9) break;
+      const bool ringed = h.lvl >= 0 && (h.flags & 3) == 0;
+      const int nrows = h.ymax - h.ymin + 1, wlen = h.xmax - h.xmin + 1;
       if (!ringed) continue;
       const uint32_t bytes = (uint32_t)wlen * C * sizeof(T);
       const unsigned char* __restrict__ src = reinterpret_cast<const unsigned char*>(
