@@ -822,8 +822,10 @@ __device__ __forceinline__ void fwd_consume_rows(const FwdPipe& pp, int stage0, 
 // dynamic smem: [FwdTab x kFwdTabs][barriers, stage offsets: 512 bytes][ring]
 // NCH = channel chunks per consumer warp: 2 halves the barrier operations per
 // byte (the per-row wait / arrive round trip, not bandwidth, bounds the pipeline).
-template <typename T, int PH, int NCH>
-__global__ void __launch_bounds__((NCH == 2 ? 256 : 480), ((PH * VecOf<T>::n * NCH <= 32 || NCH == 2) ? 2 : 1))
+// NT = threads per CTA (256: up to 7 consumer warps, two CTAs per SM at 128
+// registers; 480: up to 14, two CTAs per SM only for 7x7 fp32 single chunks).
+template <typename T, int PH, int NCH, int NT>
+__global__ void __launch_bounds__(NT, ((NT == 256 || PH * VecOf<T>::n * NCH <= 32) ? 2 : 1))
 roi_fuse_fwd_ring(const RoiFuseParams p, const PullWs ws, int ncons, int ring_bytes) {
   constexpr int V = VecOf<T>::n;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -1215,9 +1217,9 @@ __device__ __forceinline__ bool write_stage_rows(const RoiFuseParams& p, StageDe
 // atomic allocation per tile; the pool position varies from run to run, the
 // contents and their order do not).  Tiny register footprint -> the
 // latency-bound table walking runs at full occupancy, off the streaming
-// kernel's critical path.  Tiles whose list does not fit (kListCap entries, the
-// pool is exhausted, or an entry spans more than kMaxPh bin rows) are appended
-// to the inline list: roi_bwd_pull_inline builds their lists itself.
+// kernel's critical path.  Tiles the pool cannot take (it is exhausted, or an
+// entry spans more than kMaxPh bin rows) are appended to the inline list:
+// roi_bwd_pull_inline builds their lists itself.
 template <int TW>
 __device__ void bin_tile(ListSmem& sm, const RoiFuseParams& p, const PullWs& ws,
                          const TileMap& tm, int t) {
@@ -1225,50 +1227,62 @@ __device__ void bin_tile(ListSmem& sm, const RoiFuseParams& p, const PullWs& ws,
   const int tid = threadIdx.x;
   const Tile T = decode_tile(p, ws, tm, t, TW);
   const int total_cand = init_candidates(sm, ws, T.key);
-  const int pos = build_list(sm, p, ws, T, 0, total_cand);
-  const int n = sm.list_n;
+  // How many list entries in all?  Usually one pass of the list builder holds
+  // them; long lists (upper levels, thousands of RoIs) are counted pass by pass
+  // first, so that the tile still gets ONE contiguous run of the pool.
+  int pos = build_list(sm, p, ws, T, 0, total_cand);
+  int n = sm.list_n;
+  const bool single = pos >= total_cand;
+  while (pos < total_cand) {
+    pos = build_list(sm, p, ws, T, pos, total_cand);
+    n += sm.list_n;
+  }
   if (tid == 0) {
-    int off = -1;
-    if (pos >= total_cand) {  // the whole list fits
-      off = 0;
-      if (n > 0) {
-        off = atomicAdd(ws.counters, n);
-        if (off + n > ws.pool_cap) off = -1;
-      }
+    int off = 0;
+    if (n > 0) {
+      off = atomicAdd(ws.counters, n);
+      if (off + n > ws.pool_cap) off = -1;  // pool exhausted: inline kernel
     }
     s_off = off;
   }
   __syncthreads();
   const int off = s_off;
   bool ok = off >= 0;
-  if (ok) {
+  if (ok && n > 0) {
     const int chunk = (int)blockDim.x / kTileH;
-    for (int c0 = 0; c0 < n; c0 += chunk) {
-      const int nc = min(chunk, n - c0);
-      {  // thread == (entry, tile row)
-        const int q = tid / kTileH, row = tid - q * kTileH;
-        const int qq = q < nc ? q : 0;  // idle lanes shadow entry 0 (no stores)
-        const ListEntry e = sm.list[c0 + qq];
-        const int4 r = expand_row(ws, e, T.y0 + row);
-        int lo, hi;
-        row_range(r, lo, hi);  // all lanes: the shuffles stay convergent
-        if (q < nc) ok = write_stage_rows(p, ws.pool + off + c0 + q, e, r, row, lo, hi) && ok;
-      }
-      {  // thread == (entry, pw)
-        const int q = tid / kJ, jj = tid - q * kJ;
-        if (q < nc) {
-          const ListEntry e = sm.list[c0 + q];
-          if (jj < e.npw) {
-            float w[TW];
-            expand_col<TW>(ws, e, jj, T.x0, w);
-            float* o = ws.pool[off + c0 + q].cw[jj];
+    int done = 0;  // entries written so far
+    pos = 0;
+    do {
+      if (!single) pos = build_list(sm, p, ws, T, pos, total_cand);  // else: the list is still in place
+      const int m = sm.list_n;
+      for (int c0 = 0; c0 < m; c0 += chunk) {
+        const int nc = min(chunk, m - c0);
+        {  // thread == (entry, tile row)
+          const int q = tid / kTileH, row = tid - q * kTileH;
+          const int qq = q < nc ? q : 0;  // idle lanes shadow entry 0 (no stores)
+          const ListEntry e = sm.list[c0 + qq];
+          const int4 r = expand_row(ws, e, T.y0 + row);
+          int lo, hi;
+          row_range(r, lo, hi);  // all lanes: the shuffles stay convergent
+          if (q < nc) ok = write_stage_rows(p, ws.pool + off + done + c0 + q, e, r, row, lo, hi) && ok;
+        }
+        {  // thread == (entry, pw)
+          const int q = tid / kJ, jj = tid - q * kJ;
+          if (q < nc) {
+            const ListEntry e = sm.list[c0 + q];
+            if (jj < e.npw) {
+              float w[TW];
+              expand_col<TW>(ws, e, jj, T.x0, w);
+              float* o = ws.pool[off + done + c0 + q].cw[jj];
 #pragma unroll
-            for (int x = 0; x < TW; x += 4)
-              *reinterpret_cast<float4*>(o + x) = make_float4(w[x], w[x + 1], w[x + 2], w[x + 3]);
+              for (int x = 0; x < TW; x += 4)
+                *reinterpret_cast<float4*>(o + x) = make_float4(w[x], w[x + 1], w[x + 2], w[x + 3]);
+            }
           }
         }
       }
-    }
+      done += m;
+    } while (!single && pos < total_cand);
   }
   ok = __syncthreads_and(ok);
   if (tid == 0) {
@@ -1644,8 +1658,10 @@ cudaError_t launch_roi_fuse_forward_plan(const RoiFuseParams& p0, int dtype, voi
   const int nch = (p.C % (64 * V) == 0 && p.PH * V * 2 <= 64) ? 2 : 1;
   const int ncons = p.PW * ((p.C + 32 * V * nch - 1) / (32 * V * nch));
   const bool ring_ok = (p.PH == 7 || p.PH == 14) && p.PH * V <= 64 && ncons <= (nch == 2 ? 7 : 14);
-  // two CTAs per SM when the accumulators leave room (7x7 fp32), else one
-  const int per_sm = (p.PH * V * nch <= 32 || nch == 2) ? 2 : 1;
+  const int threads = (ncons + 1) * 32;
+  // two CTAs per SM when the block is small (<= 256 threads at 128 registers) or
+  // the accumulators are few (7x7 fp32 single chunk at 64 registers), else one
+  const int per_sm = (threads <= 256 || p.PH * V * nch <= 32) ? 2 : 1;
   const int fixed = kFwdTabs * (int)sizeof(FwdTab) + 512;
   const int ring = (per_sm == 2 ? 108 * 1024 : 200 * 1024) - fixed;
   ws.fwd_wlen_cap = ring_ok ? ring / (p.C * elt) : 0;  // a window row must fit the ring
@@ -1659,17 +1675,22 @@ cudaError_t launch_roi_fuse_forward_plan(const RoiFuseParams& p0, int dtype, voi
     return n;
   }();
   const int pgrid = N < per_sm * sms ? N : per_sm * sms;
-  const int smem = fixed + ring, threads = (ncons + 1) * 32;
-#define ARFE_FWD_RING(TT, PHH, NCHH)                                                             \
-  do {                                                                                           \
-    if ((e = set_smem(roi_fuse_fwd_ring<TT, PHH, NCHH>, smem)) != cudaSuccess) return e;         \
-    roi_fuse_fwd_ring<TT, PHH, NCHH><<<pgrid, threads, smem, stream>>>(p, ws, ncons, ring);      \
+  const int smem = fixed + ring;
+#define ARFE_FWD_RING(TT, PHH, NCHH, NTT)                                                             \
+  do {                                                                                                \
+    if ((e = set_smem(roi_fuse_fwd_ring<TT, PHH, NCHH, NTT>, smem)) != cudaSuccess) return e;         \
+    roi_fuse_fwd_ring<TT, PHH, NCHH, NTT><<<pgrid, threads, smem, stream>>>(p, ws, ncons, ring);      \
   } while (0)
   if (dtype == 0) {
-    if (p.PH == 7) { if (nch == 2) ARFE_FWD_RING(float, 7, 2); else ARFE_FWD_RING(float, 7, 1); }
-    else ARFE_FWD_RING(float, 14, 1);
+    if (p.PH == 7) {
+      if (nch == 2) ARFE_FWD_RING(float, 7, 2, 256);
+      else if (threads <= 256) ARFE_FWD_RING(float, 7, 1, 256);
+      else ARFE_FWD_RING(float, 7, 1, 480);
+    } else {
+      if (threads <= 256) ARFE_FWD_RING(float, 14, 1, 256); else ARFE_FWD_RING(float, 14, 1, 480);
+    }
   } else {
-    ARFE_FWD_RING(__nv_bfloat16, 7, 1);
+    if (threads <= 256) ARFE_FWD_RING(__nv_bfloat16, 7, 1, 256); else ARFE_FWD_RING(__nv_bfloat16, 7, 1, 480);
   }
 #undef ARFE_FWD_RING
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -1738,7 +1759,7 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
     roi_bwd_pull_tma<__nv_bfloat16><<<nb4 + nb8, kPullThreads, smem, stream>>>(p, ws, tm[0], tm[1], nb4, ring);
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  const int igrid = ntiles[0] + ntiles[1] < 148 ? ntiles[0] + ntiles[1] : 148;
+  const int igrid = ntiles[0] + ntiles[1] < 592 ? ntiles[0] + ntiles[1] : 592;
   if (dtype == 0) roi_bwd_pull_inline<float><<<igrid, kThreads, 0, stream>>>(p, ws, tm[0], tm[1], ntiles[0]);
   else roi_bwd_pull_inline<__nv_bfloat16><<<igrid, kThreads, 0, stream>>>(p, ws, tm[0], tm[1], ntiles[0]);
   return cudaGetLastError();
