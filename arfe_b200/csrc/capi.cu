@@ -213,9 +213,14 @@ int arfe_roi_fuse_backward_pull(const void* dout, const int32_t* H, const int32_
   REQUIRE(workspace_bytes >= arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W), ARFE_E_SHAPE,
           "%s: workspace too small (%zu < %zu)", fn, workspace_bytes, arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W));
   p.dout = dout; p.dout_cl = 1;
+  {
+    const char* ev = getenv("ARFE_BWD_SKIP");  // profiling aid, default off
+    p.debug_skip = ev ? atoi(ev) : 0;
+  }
   rc = cuda_result(arfe::launch_roi_fuse_backward_pull(p, dtype, workspace, workspace_bytes, plan_ready, (cudaStream_t)stream), fn);
   if (rc) return rc;
   // regions whose tap tables did not fit the workspace records: atomic kernel, adds on top
+  p.debug_skip = 0;
   p.flag_list = arfe::roi_pull_flag_list(K, regions, L, B, H, W, workspace, &p.flag_count);
   p.bwd_vec = 0;
   return cuda_result(arfe::launch_roi_fuse_backward(p, dtype, ARFE_NHWC, (cudaStream_t)stream), fn);

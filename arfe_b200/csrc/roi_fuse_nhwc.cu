@@ -456,9 +456,10 @@ struct PullWs {
   int* seg_ids;
   int* seg_cnt;
   int2* tile_desc;            // per pull tile: {pool offset, stages} or {., -1}: the inline kernel serves it
-  int* counters;              // [0] next free pool entry, [1] inline tiles (backward); [2] regions for the
-                              // atomic fallback kernel, [3] regions for the forward fallback kernel,
-                              // [4] next region of the forward ring kernel (prep zeroes 2..4)
+  int* counters;              // backward (zeroed per call): [0] next free pool entry, [1] inline tiles,
+                              // [2] next tile of the pull kernel; plan (zeroed by prep): [3] regions for
+                              // the atomic fallback kernel, [4] regions for the forward fallback kernel,
+                              // [5] next region of the forward ring kernel
   int* flag_list;             // regions for the atomic fallback kernel
   int* fwd_list;              // regions the forward ring kernel cannot serve
   int* wsize;                 // per region: window rows << 16 | window columns (0: not served by the ring kernel)
@@ -680,8 +681,8 @@ roi_prep_kernel(const RoiFuseParams p, const PullWs ws) {
     }
     ws.hdr[i] = h;
     ws.wsize[i] = wsz;
-    if (h.flags & 1) ws.flag_list[atomicAdd(ws.counters + 2, 1)] = i;
-    if ((h.flags & 2) && ws.fwd_wlen_cap > 0) ws.fwd_list[atomicAdd(ws.counters + 3, 1)] = i;
+    if (h.flags & 1) ws.flag_list[atomicAdd(ws.counters + 3, 1)] = i;
+    if ((h.flags & 2) && ws.fwd_wlen_cap > 0) ws.fwd_list[atomicAdd(ws.counters + 4, 1)] = i;
   }
 }
 
@@ -860,7 +861,7 @@ roi_fuse_fwd_ring(const RoiFuseParams p, const PullWs ws, int ncons, int ring_by
     // column table: fixed 5.4 KB straight from the plan) are issued before the
     // rows of region i, so neither the atomic nor the header fetch sits on the
     // row stream's critical path.
-    auto claim = [&]() -> int { return lane == 0 ? atomicAdd(ws.counters + 4, 1) : 0; };
+    auto claim = [&]() -> int { return lane == 0 ? atomicAdd(ws.counters + 5, 1) : 0; };
     auto issue_tables = [&](int reg, int j) {  // tables of the j-th region of this CTA
       const int buf = j % kFwdTabs;
       if (j >= kFwdTabs) mbar_wait(tab_empty + buf, ((j / kFwdTabs) - 1) & 1);
@@ -1321,89 +1322,38 @@ roi_bin_kernel(const RoiFuseParams p, const PullWs ws, const TileMap tm4, const 
 constexpr int kNSlot = 16;
 constexpr int kPullThreads = 288;
 constexpr int kDescBytes = (int)sizeof(StageDesc);
-constexpr int kPullCtl = 512;  // full[16] + empty[16] barriers, stage offsets
+constexpr int kTileQ = 4;      // tiles announced ahead of the consumers
+constexpr int kPullCtl = 1024; // barriers, stage offsets, tile queue
 
+// The kernel is PERSISTENT: CTAs (three per SM) claim (tile, channel group)s from
+// a work counter, heavy tiles first; the producer announces each tile to the
+// consumers through a small queue and keeps issuing the next tile's stages
+// while the consumers finish the current one, so a tile's start-up latency
+// (claim -> tile descriptor -> stage headers -> first bins) is hidden behind
+// the previous tile instead of being paid 14 times per SM slot.
+struct PullCtl {
+  uint64_t full[kNSlot], empty[kNSlot];
+  uint64_t tq_full[kTileQ], tq_empty[kTileQ];
+  uint32_t stage_off[kNSlot];
+  int4 tq[kTileQ];  // {work item g (< 0: no more work), pool offset, stages, 0}
+};
+static_assert(sizeof(PullCtl) <= kPullCtl, "control block");
+
+// Consumer side of one tile: stages [stage0, stage0 + n).
 template <typename T, int TW>
-__device__ __forceinline__ void pull_tile_tma(const RoiFuseParams& p, const PullWs& ws, const TileMap& tm,
-                                              int ring_bytes, int block) {
+__device__ __forceinline__ void pull_consume_tile(const RoiFuseParams& p, const PullWs& ws,
+                                                  const TileMap& tm, PullCtl& ctl,
+                                                  const StageDesc* desc, const unsigned char* ring,
+                                                  int block, int n, int stage0) {
   constexpr int V = VecOf<T>::n;
   constexpr int V2 = V / 2;
-  constexpr int CG = 32 * V;  // channels per group
-  extern __shared__ __align__(16) unsigned char smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* empty = full + kNSlot;
-  uint32_t* stage_off = reinterpret_cast<uint32_t*>(smem + 2 * kNSlot * 8);
-  StageDesc* desc = reinterpret_cast<StageDesc*>(smem + kPullCtl);
-  unsigned char* ring = smem + kPullCtl + kNSlot * kDescBytes;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int CG = 32 * V;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = block / tm.groups, grp = block - t * tm.groups;
-  const int2 td = ws.tile_desc[tm.tile_base + t];
-  if (td.y < 0) return;  // served by roi_bwd_pull_inline
-  const int n = td.y;
   const Tile tl = decode_tile(p, ws, tm, t, TW);
-  const int C = p.C, RC = p.R * C;
+  const int C = p.C;
   const int c0 = grp * CG;
-  const int cg = min(CG, C - c0);               // channels actually staged per bin
-  const uint32_t bin_bytes = (uint32_t)cg * sizeof(T);
-  const StageDesc* __restrict__ gdesc = ws.pool + td.x;
-
-  if (tid == 0) {
-    for (int i = 0; i < kNSlot; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, kTileH); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (warp == kTileH) {
-    // ------------------------------------------------------------ producer
-    uint32_t head = 0, tail = 0;  // live bytes of the ring: [tail, head) modulo wrap
-    uint32_t my_off = 0;          // lane j: ring offset of the stage in slot j
-    int released = 0;             // stages known to be consumed
-    const T* __restrict__ dsrc = static_cast<const T*>(p.dout) + c0;
-    int4 hdr = make_int4(0, 0, 0, 0);
-    for (int i = 0; i < n; ++i) {
-      if ((i & 31) == 0 && i + lane < n) hdr = __ldg(reinterpret_cast<const int4*>(gdesc + i + lane));
-      const int src_off = __shfl_sync(0xffffffffu, hdr.x, i & 31);
-      const int nn = __shfl_sync(0xffffffffu, hdr.y, i & 31);
-      const int nph = nn & 0xffff, npw = (nn >> 16) & 0xffff;
-      const int nbins = nph * npw;
-      const uint32_t bytes = (uint32_t)nbins * bin_bytes;
-      const int slot = i % kNSlot;
-      // the slot's previous stage and enough ring space must have been released
-      // (stages are released in order)
-      auto release_one = [&]() {
-        mbar_wait(empty + (released % kNSlot), (released / kNSlot) & 1);
-        ++released;
-        const uint32_t nxt = __shfl_sync(0xffffffffu, my_off, released % kNSlot);
-        tail = released < i ? nxt : head;
-      };
-      while (released < i - kNSlot + 1) release_one();
-      uint32_t off;
-      while (true) {
-        if (released == i) { head = tail = 0; off = 0; break; }           // ring empty
-        if (head >= tail) {
-          if (head + bytes <= (uint32_t)ring_bytes) { off = head; break; }
-          if (bytes < tail) { off = 0; break; }                            // wrap
-        } else if (head + bytes < tail) { off = head; break; }
-        release_one();
-      }
-      head = off + bytes;
-      if (lane == slot) my_off = off;
-      if (lane == 0) {
-        stage_off[slot] = off;
-        mbar_arrive_expect_tx(full + slot, bytes + kDescBytes);
-        bulk_g2s(desc + slot, gdesc + i, kDescBytes, full + slot);
-      }
-      for (int bi = lane; bi < nbins; bi += 32) {
-        const int ih = bi / npw, iw = bi - ih * npw;
-        bulk_g2s(ring + off + (uint32_t)bi * bin_bytes,
-                 dsrc + (size_t)src_off + (size_t)(ih * p.PW + iw) * RC, bin_bytes, full + slot);
-      }
-    }
-    return;
-  }
-
-  // ---------------------------------------------------------------- consumers
+  const uint32_t bin_bytes = (uint32_t)min(CG, C - c0) * sizeof(T);
   const int y = tl.y0 + warp;
   const int cl = c0 + lane * V;
   const bool act = y <= tl.y1 && cl < C;
@@ -1414,16 +1364,17 @@ __device__ __forceinline__ void pull_tile_tma(const RoiFuseParams& p, const Pull
     for (int u = 0; u < V2; ++u) acc[x][u] = 0ull;
 
   for (int i = 0; i < n; ++i) {
-    const int slot = i % kNSlot;
-    mbar_wait(full + slot, (i / kNSlot) & 1);
+    const int stage = stage0 + i;
+    const int slot = stage % kNSlot;
+    mbar_wait(ctl.full + slot, (stage / kNSlot) & 1);
     const StageDesc& d = desc[slot];
     const int4 rd = d.rows[warp];
-    if (act && rd.x >= 0) {
+    if (act && rd.x >= 0 && !(p.debug_skip & 1)) {  // (profiling aid: no math)
       const int npw = d.npw;
       const float a0 = __int_as_float(rd.z), a1 = __int_as_float(rd.w);
       const uint64_t a0p = pack2(a0, a0), a1p = pack2(a1, a1);
       const unsigned char* __restrict__ s0 =
-          ring + stage_off[slot] + (uint32_t)(rd.x * npw) * bin_bytes + (uint32_t)(lane * V) * sizeof(T);
+          ring + ctl.stage_off[slot] + (uint32_t)(rd.x * npw) * bin_bytes + (uint32_t)(lane * V) * sizeof(T);
       const uint32_t two_step = rd.y ? (uint32_t)npw * bin_bytes : 0u;
 #pragma unroll 2
       for (int jj = 0; jj < npw; ++jj) {
@@ -1452,7 +1403,7 @@ __device__ __forceinline__ void pull_tile_tma(const RoiFuseParams& p, const Pull
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(empty + slot);
+    if (lane == 0) mbar_arrive(ctl.empty + slot);
   }
   // ---- every element of the tile written exactly once ----
   if (act) {
@@ -1468,14 +1419,133 @@ __device__ __forceinline__ void pull_tile_tma(const RoiFuseParams& p, const Pull
   }
 }
 
-// One launch for both tile shapes: the narrow (heavy) tiles come first, the wide
-// ones fill the machine behind them.
+// Work item g in [0, nb4 + nb8): (tile, channel group) of the narrow-tile pass,
+// then of the wide-tile pass.
 template <typename T>
 __global__ void __launch_bounds__(kPullThreads, (VecOf<T>::n == 4 ? 3 : 2))
 roi_bwd_pull_tma(const RoiFuseParams p, const PullWs ws, const TileMap tm4, const TileMap tm8,
-                 int nb4, int ring_bytes) {
-  if ((int)blockIdx.x < nb4) pull_tile_tma<T, 4>(p, ws, tm4, ring_bytes, blockIdx.x);
-  else pull_tile_tma<T, 8>(p, ws, tm8, ring_bytes, blockIdx.x - nb4);
+                 int nb4, int nb8, int ring_bytes) {
+  constexpr int V = VecOf<T>::n;
+  constexpr int CG = 32 * V;
+  extern __shared__ __align__(16) unsigned char smem[];
+  PullCtl& ctl = *reinterpret_cast<PullCtl*>(smem);
+  StageDesc* desc = reinterpret_cast<StageDesc*>(smem + kPullCtl);
+  unsigned char* ring = smem + kPullCtl + kNSlot * kDescBytes;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int total = nb4 + nb8;
+
+  if (tid == 0) {
+    for (int i = 0; i < kNSlot; ++i) { mbar_init(ctl.full + i, 1); mbar_init(ctl.empty + i, kTileH); }
+    for (int i = 0; i < kTileQ; ++i) { mbar_init(ctl.tq_full + i, 1); mbar_init(ctl.tq_empty + i, kTileH); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kTileH) {
+    // ------------------------------------------------------------ producer
+    uint32_t head = 0, tail = 0;  // live bytes of the ring: [tail, head) modulo wrap
+    uint32_t my_off = 0;          // lane j: ring offset of the stage in slot j
+    int issued = 0, released = 0; // stages issued / known to be consumed
+    const int C = p.C, RC = p.R * C;
+    auto claim = [&]() -> int { return lane == 0 ? atomicAdd(ws.counters + 2, 1) : 0; };
+    auto tile_desc_of = [&](int g) -> int2 {
+      if (g >= total) return make_int2(0, -1);
+      return g < nb4 ? ws.tile_desc[tm4.tile_base + g / tm4.groups]
+                     : ws.tile_desc[tm8.tile_base + (g - nb4) / tm8.groups];
+    };
+    // software pipeline: claim two items ahead, tile descriptor and the first 32
+    // stage headers one item ahead
+    int g = __shfl_sync(0xffffffffu, claim(), 0);
+    int c_next = claim();
+    int2 td = tile_desc_of(g);
+    int4 hdr = make_int4(0, 0, 0, 0);
+    if (td.y > 0 && lane < td.y) hdr = __ldg(reinterpret_cast<const int4*>(ws.pool + td.x + lane));
+    for (int it = 0;; ++it) {
+      const int g_next = __shfl_sync(0xffffffffu, c_next, 0);
+      c_next = claim();
+      const int2 td_next = tile_desc_of(g_next);
+      // announce the current item
+      const int qs = it % kTileQ;
+      if (it >= kTileQ) mbar_wait(ctl.tq_empty + qs, ((it / kTileQ) - 1) & 1);
+      if (lane == 0) {
+        ctl.tq[qs] = make_int4(g < total ? g : -1, td.x, td.y, 0);
+        mbar_arrive(ctl.tq_full + qs);
+      }
+      if (g >= total) break;
+      const int n = td.y;  // < 0: inline tile, nothing to stream
+      if (n > 0) {
+        const bool narrow = g < nb4;
+        const int grp = narrow ? g % tm4.groups : (g - nb4) % tm8.groups;
+        const int c0 = grp * CG;
+        const uint32_t bin_bytes = (uint32_t)min(CG, C - c0) * sizeof(T);
+        const T* __restrict__ dsrc = static_cast<const T*>(p.dout) + c0;
+        const StageDesc* __restrict__ gdesc = ws.pool + td.x;
+        for (int i = 0; i < n; ++i) {
+          if ((i & 31) == 0 && i > 0 && i + lane < n) hdr = __ldg(reinterpret_cast<const int4*>(gdesc + i + lane));
+          const int src_off = __shfl_sync(0xffffffffu, hdr.x, i & 31);
+          const int nn = __shfl_sync(0xffffffffu, hdr.y, i & 31);
+          const int nph = nn & 0xffff, npw = (nn >> 16) & 0xffff;
+          const int nbins = nph * npw;
+          const uint32_t bytes = (uint32_t)nbins * bin_bytes;
+          const int slot = issued % kNSlot;
+          // the slot's previous stage and enough ring space must have been released
+          // (stages are released in order)
+          auto release_one = [&]() {
+            mbar_wait(ctl.empty + (released % kNSlot), (released / kNSlot) & 1);
+            ++released;
+            const uint32_t nxt = __shfl_sync(0xffffffffu, my_off, released % kNSlot);
+            tail = released < issued ? nxt : head;
+          };
+          while (released < issued - kNSlot + 1) release_one();
+          uint32_t off;
+          while (true) {
+            if (released == issued) { head = tail = 0; off = 0; break; }           // ring empty
+            if (head >= tail) {
+              if (head + bytes <= (uint32_t)ring_bytes) { off = head; break; }
+              if (bytes < tail) { off = 0; break; }                                  // wrap
+            } else if (head + bytes < tail) { off = head; break; }
+            release_one();
+          }
+          head = off + bytes;
+          if (lane == slot) my_off = off;
+          if (lane == 0) {
+            ctl.stage_off[slot] = off;
+            mbar_arrive_expect_tx(ctl.full + slot, ((p.debug_skip & 2) ? 0u : bytes) + kDescBytes);
+            bulk_g2s(desc + slot, gdesc + i, kDescBytes, ctl.full + slot);
+          }
+          if (!(p.debug_skip & 2))  // profiling aid: no bin copies
+          for (int bi = lane; bi < nbins; bi += 32) {
+            const int ih = bi / npw, iw = bi - ih * npw;
+            bulk_g2s(ring + off + (uint32_t)bi * bin_bytes,
+                     dsrc + (size_t)src_off + (size_t)(ih * p.PW + iw) * RC, bin_bytes, ctl.full + slot);
+          }
+          ++issued;
+        }
+      }
+      // rotate: the next item's descriptor has been in flight since the top
+      g = g_next;
+      td = td_next;
+      hdr = make_int4(0, 0, 0, 0);
+      if (td.y > 0 && lane < td.y) hdr = __ldg(reinterpret_cast<const int4*>(ws.pool + td.x + lane));
+    }
+    return;
+  }
+
+  // ---------------------------------------------------------------- consumers
+  int stage = 0;
+  for (int it = 0;; ++it) {
+    const int qs = it % kTileQ;
+    mbar_wait(ctl.tq_full + qs, (it / kTileQ) & 1);
+    const int4 q = ctl.tq[qs];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(ctl.tq_empty + qs);  // copied to registers
+    if (q.x < 0) break;
+    const int n = q.z;
+    if (n < 0) continue;  // served by roi_bwd_pull_inline
+    if (q.x < nb4) pull_consume_tile<T, 4>(p, ws, tm4, ctl, desc, ring, q.x, n, stage);
+    else pull_consume_tile<T, 8>(p, ws, tm8, ctl, desc, ring, q.x - nb4, n, stage);
+    stage += n;
+  }
 }
 
 // ---- inline kernel: the tiles the binning kernel could not serve.  A small
@@ -1637,7 +1707,7 @@ static cudaError_t launch_prep(const RoiFuseParams& p, const PullWs& ws, cudaStr
   if (prep_smem > 160 * 1024 || ws.nblk > kMaxPrepBlocks) return cudaErrorInvalidValue;
   cudaError_t e = set_smem(roi_prep_kernel, prep_smem);
   if (e != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(ws.counters + 2, 0, 12, stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ws.counters + 3, 0, 12, stream)) != cudaSuccess) return e;
   roi_prep_kernel<<<ws.nblk + N, kPrepThreads, prep_smem, stream>>>(p, ws);
   return cudaGetLastError();
 }
@@ -1695,7 +1765,7 @@ cudaError_t launch_roi_fuse_forward_plan(const RoiFuseParams& p0, int dtype, voi
 #undef ARFE_FWD_RING
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   p.flag_list = ws.fwd_list;
-  p.flag_count = ws.counters + 3;
+  p.flag_count = ws.counters + 4;
   return launch_roi_fuse_forward_cl(p, dtype, 1, stream);
 }
 
@@ -1715,7 +1785,7 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
   if (ws.nblk > kMaxPrepBlocks) return cudaErrorInvalidValue;
   if ((long long)p.K * p.PH * p.PW * p.R * p.C > 0x7fffffffLL) return cudaErrorInvalidValue;  // 32-bit dout offsets
   cudaError_t e;
-  if ((e = cudaMemsetAsync(ws.counters, 0, 8, stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ws.counters, 0, 12, stream)) != cudaSuccess) return e;
   if (!plan_ready && (e = launch_prep(p, ws, stream)) != cudaSuccess) return e;
   // Two tile shapes: the small upper-level maps carry ~40x more region-pixels per
   // tile than level 0, so they get narrow tiles and go first (heaviest level
@@ -1751,12 +1821,20 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
   const int ring = 64 * 1024;
   const int smem = kPullCtl + kNSlot * kDescBytes + ring;
   const int nb4 = ntiles[0] * tm[0].groups, nb8 = ntiles[1] * tm[1].groups;
+  static const int sms = [] {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  const int per_sm = dtype == 0 ? 3 : 2;
+  const int pgrid = nb4 + nb8 < per_sm * sms ? nb4 + nb8 : per_sm * sms;
   if (dtype == 0) {
     if ((e = set_smem(roi_bwd_pull_tma<float>, smem)) != cudaSuccess) return e;
-    roi_bwd_pull_tma<float><<<nb4 + nb8, kPullThreads, smem, stream>>>(p, ws, tm[0], tm[1], nb4, ring);
+    roi_bwd_pull_tma<float><<<pgrid, kPullThreads, smem, stream>>>(p, ws, tm[0], tm[1], nb4, nb8, ring);
   } else {
     if ((e = set_smem(roi_bwd_pull_tma<__nv_bfloat16>, smem)) != cudaSuccess) return e;
-    roi_bwd_pull_tma<__nv_bfloat16><<<nb4 + nb8, kPullThreads, smem, stream>>>(p, ws, tm[0], tm[1], nb4, ring);
+    roi_bwd_pull_tma<__nv_bfloat16><<<pgrid, kPullThreads, smem, stream>>>(p, ws, tm[0], tm[1], nb4, nb8, ring);
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   const int igrid = ntiles[0] + ntiles[1] < 592 ? ntiles[0] + ntiles[1] : 592;
@@ -1771,7 +1849,7 @@ const int* roi_pull_flag_list(int K, int R, int L, int B, const int* H, const in
                               const int** count) {
   PullWs ws;
   pull_ws_layout(K * R, L, B, H, W, static_cast<unsigned char*>(workspace), &ws);
-  *count = ws.counters + 2;
+  *count = ws.counters + 3;
   return ws.flag_list;
 }
 
