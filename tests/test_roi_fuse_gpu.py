@@ -300,3 +300,118 @@ def test_large_k_multi_pass_lists(oracle, cuda):
         r = fo[l].grad if fo[l].grad is not None else torch.zeros_like(feats[l])
         d = (fg[l].grad.cpu() - r).abs().max()
         assert float(d) <= 3e-5 * float(r.abs().max()) + 1e-5, (l, float(d), float(r.abs().max()))
+
+
+def _plan_calls(cuda, feats_cl, rois, regions=3, P=7):
+    """Direct C-ABI calls: (forward via the L1 kernel, forward via plan + ring
+    kernel, workspace pointer/size, helper for the pull backward)."""
+    from arfe_b200 import _lib as L
+    lib = L.lib()
+    B, C = feats_cl[0].shape[:2]
+    Hs = [f.shape[2] for f in feats_cl]
+    Ws = [f.shape[3] for f in feats_cl]
+    K = rois.size(0)
+    nlev = len(feats_cl)
+    scales = _scales()[:nlev]
+    H, W, S = L.int_array(Hs), L.int_array(Ws), L.float_array(scales)
+    stream = L.stream_ptr(cuda)
+
+    def new_ws():
+        n = lib.arfe_roi_plan_bytes(K, regions, nlev, B, H, W)
+        t = torch.empty(n + 256, dtype=torch.uint8, device=cuda)
+        return t, (t.data_ptr() + 255) // 256 * 256, n
+
+    def fwd_l1():
+        out = torch.empty((K, regions * C, P, P), device=cuda, memory_format=torch.channels_last)
+        L.check(lib.arfe_roi_fuse_forward(L.ptr_array(feats_cl), H, W, S, nlev, B, C, rois.data_ptr(), K,
+                                          regions, 1.0, P, P, 0, 56.0, L.ARFE_F32, L.ARFE_NHWC, L.ARFE_NHWC,
+                                          out.data_ptr(), None, None, stream), "fwd")
+        return out
+
+    def fwd_plan(ws):
+        out = torch.empty((K, regions * C, P, P), device=cuda, memory_format=torch.channels_last)
+        L.check(lib.arfe_roi_fuse_forward_plan(L.ptr_array(feats_cl), H, W, S, nlev, B, C, rois.data_ptr(), K,
+                                               regions, 1.0, P, P, 0, 56.0, L.ARFE_F32, out.data_ptr(), None,
+                                               None, ws[1], ws[2], stream), "fwd_plan")
+        return out
+
+    def bwd(g_cl, ws, ready):
+        d = [torch.empty((B, C, Hs[l], Ws[l]), device=cuda, memory_format=torch.channels_last)
+             for l in range(nlev)]
+        L.check(lib.arfe_roi_fuse_backward_pull(g_cl.data_ptr(), H, W, S, nlev, B, C, rois.data_ptr(), K,
+                                                regions, 1.0, P, P, 0, 56.0, L.ARFE_F32, L.ptr_array(d),
+                                                ws[1], ws[2], ready, stream), "bwd")
+        return d
+    return new_ws, fwd_l1, fwd_plan, bwd
+
+
+def test_plan_forward_and_plan_reuse(oracle, cuda):
+    """The ring kernel (forward with a plan) against the oracle and against the
+    L1-cached kernel; a backward that reuses the forward's plan is bit-identical
+    to one that rebuilds it, and to itself run twice."""
+    feats = small_pyramid(oracle, batch=2, channels=64, img_h=256, img_w=384)
+    rois = mixed_rois(oracle, 200, 384, 256, 2, seed=29)
+    ref = oracle.arrff_bbox_feats(feats, rois, list(STRIDES))
+    f_cl = [_cl(f.to(cuda)) for f in feats]
+    r = rois.to(cuda)
+    new_ws, fwd_l1, fwd_plan, bwd = _plan_calls(cuda, f_cl, r)
+    ws = new_ws()
+    a, b = fwd_l1(), fwd_plan(ws)
+    assert_close_fp32(b, ref, "ring forward vs oracle")
+    assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max())
+    g = _cl(torch.randn(ref.shape, device=cuda, generator=torch.Generator(device=cuda).manual_seed(2)))
+    d_reuse = bwd(g, ws, 1)
+    d_again = bwd(g, ws, 1)
+    ws2 = new_ws()
+    d_fresh = bwd(g, ws2, 0)
+    torch.cuda.synchronize()
+    for x, y, z in zip(d_reuse, d_fresh, d_again):
+        assert torch.equal(x, y), "plan reuse changes the gradient"
+        assert torch.equal(x, z), "backward is not reproducible"
+
+
+def test_ring_forward_wide_windows_and_many_taps(oracle, cuda):
+    """C = 256 (1 KB per pixel): windows wider than the ring's row capacity go to
+    the L1-cached kernel over the plan's fwd_list, bins wider than 8 feature
+    pixels take the run-time tap loop; thin slivers, border boxes and sub-pixel
+    RoIs mixed in."""
+    import arfe_b200 as A
+    feats = small_pyramid(oracle, batch=1, channels=256, img_h=384, img_w=640)
+    extra = torch.tensor([[0, 2.0, 100.0, 636.0, 118.0],     # 158 px wide at level 0 (sliver): left out of the ring
+                          [0, 10.0, 10.0, 400.0, 40.0],      # ~98 px wide window at level 0
+                          [0, 20.0, 30.0, 380.0, 75.0],      # 13-pixel bins at level 0: > 8 taps
+                          [0, 0.0, 0.0, 639.0, 383.0],       # whole image
+                          [0, 300.0, 200.0, 300.5, 200.4],   # sub-pixel
+                          [0, 600.0, 350.0, 700.0, 420.0]])  # partly outside
+    rois = torch.cat([mixed_rois(oracle, 24, 640, 384, 1, seed=31), extra])
+    fo = [f.clone().requires_grad_(True) for f in feats]
+    ref = oracle.arrff_bbox_feats(fo, rois, list(STRIDES))
+    g = torch.randn(ref.shape, generator=torch.Generator().manual_seed(8))
+    ref.backward(g)
+    fg = [_cl(f.to(cuda)).requires_grad_(True) for f in feats]
+    got = A.roi_fuse(fg, rois.to(cuda), 7, _scales(), regions=3, out_channels_last=True)
+    assert_close_fp32(got, ref, "ring forward, wide windows / many taps")
+    got.backward(_cl(g.to(cuda)))
+    for l in range(5):
+        r = fo[l].grad if fo[l].grad is not None else torch.zeros_like(feats[l])
+        d = (fg[l].grad.cpu() - r).abs().max()
+        assert float(d) <= 3e-5 * float(r.abs().max()) + 1e-5, (l, float(d), float(r.abs().max()))
+
+
+def test_pull_pool_exhaustion_takes_inline_tiles(oracle, cuda):
+    """Few huge RoIs on one big level (plain RoIAlign, L = 1): every RoI reaches
+    hundreds of tiles, the stage pool (sized for ~24 tiles per region) runs out
+    and the remaining tiles are served by the inline kernel."""
+    import arfe_b200 as A
+    x = torch.randn(1, 8, 128, 200, generator=torch.Generator().manual_seed(3))
+    rois = torch.tensor([[0, 4.0 * i, 3.0 * i, 780.0 - 5 * i, 500.0 - 2 * i] for i in range(16)])
+    xo = x.clone().requires_grad_(True)
+    ref = oracle.single_roi_extractor([xo], rois, [4])
+    g = torch.randn(ref.shape, generator=torch.Generator().manual_seed(4))
+    ref.backward(g)
+    xg = _cl(x.to(cuda)).requires_grad_(True)
+    got = A.roi_fuse([xg], rois.to(cuda), 7, [0.25], regions=1, out_channels_last=True)
+    assert_close_fp32(got, ref, "L=1 huge RoIs forward")
+    got.backward(_cl(g.to(cuda)))
+    d = (xg.grad.cpu() - xo.grad).abs().max()
+    assert float(d) <= 3e-5 * float(xo.grad.abs().max()) + 1e-5, float(d)
