@@ -1340,14 +1340,15 @@ struct PullCtl {
 static_assert(sizeof(PullCtl) <= kPullCtl, "control block");
 
 // Consumer side of one tile: stages [stage0, stage0 + n).
-template <typename T, int TW>
+template <typename T, int TW, int NV>
 __device__ __forceinline__ void pull_consume_tile(const RoiFuseParams& p, const PullWs& ws,
                                                   const TileMap& tm, PullCtl& ctl,
                                                   const StageDesc* desc, const unsigned char* ring,
                                                   int block, int n, int stage0) {
   constexpr int V = VecOf<T>::n;
   constexpr int V2 = V / 2;
-  constexpr int CG = 32 * V;
+  constexpr int CG = 32 * V * NV;  // channels per group; NV > 1 requires C % CG == 0 (launcher)
+  constexpr uint32_t kVecBytes = 32 * V * sizeof(T);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = block / tm.groups, grp = block - t * tm.groups;
   const Tile tl = decode_tile(p, ws, tm, t, TW);
@@ -1357,11 +1358,13 @@ __device__ __forceinline__ void pull_consume_tile(const RoiFuseParams& p, const 
   const int y = tl.y0 + warp;
   const int cl = c0 + lane * V;
   const bool act = y <= tl.y1 && cl < C;
-  uint64_t acc[TW][V2];
+  uint64_t acc[TW][NV][V2];
 #pragma unroll
   for (int x = 0; x < TW; ++x)
 #pragma unroll
-    for (int u = 0; u < V2; ++u) acc[x][u] = 0ull;
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int u = 0; u < V2; ++u) acc[x][v][u] = 0ull;
 
   for (int i = 0; i < n; ++i) {
     const int stage = stage0 + i;
@@ -1378,14 +1381,21 @@ __device__ __forceinline__ void pull_consume_tile(const RoiFuseParams& p, const 
       const uint32_t two_step = rd.y ? (uint32_t)npw * bin_bytes : 0u;
 #pragma unroll 2
       for (int jj = 0; jj < npw; ++jj) {
-        uint64_t e[V2], e1[V2];
-        lds_pairs<T>(s0, e);
+        uint64_t e[NV][V2];
 #pragma unroll
-        for (int u = 0; u < V2; ++u) e[u] = mul2(e[u], a0p);
+        for (int v = 0; v < NV; ++v) {
+          lds_pairs<T>(s0 + v * kVecBytes, e[v]);
+#pragma unroll
+          for (int u = 0; u < V2; ++u) e[v][u] = mul2(e[v][u], a0p);
+        }
         if (rd.y) {
-          lds_pairs<T>(s0 + two_step, e1);
 #pragma unroll
-          for (int u = 0; u < V2; ++u) e[u] = fma2(e1[u], a1p, e[u]);
+          for (int v = 0; v < NV; ++v) {
+            uint64_t e1[V2];
+            lds_pairs<T>(s0 + two_step + v * kVecBytes, e1);
+#pragma unroll
+            for (int u = 0; u < V2; ++u) e[v][u] = fma2(e1[u], a1p, e[v][u]);
+          }
         }
         float w[TW];
 #pragma unroll
@@ -1397,7 +1407,9 @@ __device__ __forceinline__ void pull_consume_tile(const RoiFuseParams& p, const 
         for (int x = 0; x < TW; ++x) {
           const uint64_t wp = pack2(w[x], w[x]);
 #pragma unroll
-          for (int u = 0; u < V2; ++u) acc[x][u] = fma2(e[u], wp, acc[x][u]);
+          for (int v = 0; v < NV; ++v)
+#pragma unroll
+            for (int u = 0; u < V2; ++u) acc[x][v][u] = fma2(e[v][u], wp, acc[x][v][u]);
         }
         s0 += bin_bytes;
       }
@@ -1413,20 +1425,22 @@ __device__ __forceinline__ void pull_consume_tile(const RoiFuseParams& p, const 
       if (tl.x0 + x > tl.x1) continue;
       float* __restrict__ o = dimg + ((size_t)y * tl.W + tl.x0 + x) * C + cl;
 #pragma unroll
-      for (int u = 0; u < V2; u += 2)
-        *reinterpret_cast<ulonglong2*>(o + 2 * u) = make_ulonglong2(acc[x][u], acc[x][u + 1]);
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int u = 0; u < V2; u += 2)
+          *reinterpret_cast<ulonglong2*>(o + v * 32 * V + 2 * u) = make_ulonglong2(acc[x][v][u], acc[x][v][u + 1]);
     }
   }
 }
 
 // Work item g in [0, nb4 + nb8): (tile, channel group) of the narrow-tile pass,
 // then of the wide-tile pass.
-template <typename T>
-__global__ void __launch_bounds__(kPullThreads, (VecOf<T>::n == 4 ? 3 : 2))
+template <typename T, int NV>
+__global__ void __launch_bounds__(kPullThreads, (VecOf<T>::n * NV == 4 ? 3 : 2))
 roi_bwd_pull_tma(const RoiFuseParams p, const PullWs ws, const TileMap tm4, const TileMap tm8,
                  int nb4, int nb8, int ring_bytes) {
   constexpr int V = VecOf<T>::n;
-  constexpr int CG = 32 * V;
+  constexpr int CG = 32 * V * NV;
   extern __shared__ __align__(16) unsigned char smem[];
   PullCtl& ctl = *reinterpret_cast<PullCtl*>(smem);
   StageDesc* desc = reinterpret_cast<StageDesc*>(smem + kPullCtl);
@@ -1542,8 +1556,8 @@ roi_bwd_pull_tma(const RoiFuseParams p, const PullWs ws, const TileMap tm4, cons
     if (q.x < 0) break;
     const int n = q.z;
     if (n < 0) continue;  // served by roi_bwd_pull_inline
-    if (q.x < nb4) pull_consume_tile<T, 4>(p, ws, tm4, ctl, desc, ring, q.x, n, stage);
-    else pull_consume_tile<T, 8>(p, ws, tm8, ctl, desc, ring, q.x - nb4, n, stage);
+    if (q.x < nb4) pull_consume_tile<T, 4, NV>(p, ws, tm4, ctl, desc, ring, q.x, n, stage);
+    else pull_consume_tile<T, 8, NV>(p, ws, tm8, ctl, desc, ring, q.x - nb4, n, stage);
     stage += n;
   }
 }
@@ -1791,6 +1805,10 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
   // tile than level 0, so they get narrow tiles and go first (heaviest level
   // first inside each launch); the big maps follow with wide tiles.
   const int V = dtype == 0 ? 4 : 8;
+  // fp32: a CTA takes 2 x 128 channels when C allows (1 KB bin pieces: half the bulk
+  // copies and stages of the 128-channel variant)
+  static const int nv_env = [] { const char* ev = getenv("ARFE_PULL_NV"); return ev ? atoi(ev) : 0; }();
+  const int nv = (dtype == 0 && p.C % (64 * V) == 0 && nv_env != 1) ? 2 : 1;
   TileMap tm[2];
   int ntiles[2];
   int tile_base = 0;
@@ -1798,7 +1816,7 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
     const int tw = pass == 0 ? 4 : 8;
     TileMap& m = tm[pass];
     int total = 0, ns = 0;
-    m.groups = (p.C + 32 * V - 1) / (32 * V);
+    m.groups = (p.C + 32 * V * nv - 1) / (32 * V * nv);
     for (int l = p.L - 1; l >= 0; --l) {
       if (pull_heavy(p.H[l], p.W[l]) != (pass == 0)) continue;
       m.tstart[ns] = total;
@@ -1818,7 +1836,8 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
   if (ntiles[0] + ntiles[1] == 0) return cudaSuccess;
   roi_bin_kernel<<<ntiles[0] + ntiles[1], kBinThreads, 0, stream>>>(p, ws, tm[0], tm[1], ntiles[0]);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  const int ring = 64 * 1024;
+  const int per_sm = (dtype == 0 && nv == 1) ? 3 : 2;
+  const int ring = (per_sm == 3 ? 64 : 96) * 1024;
   const int smem = kPullCtl + kNSlot * kDescBytes + ring;
   const int nb4 = ntiles[0] * tm[0].groups, nb8 = ntiles[1] * tm[1].groups;
   static const int sms = [] {
@@ -1827,15 +1846,15 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     return n;
   }();
-  const int per_sm = dtype == 0 ? 3 : 2;
   const int pgrid = nb4 + nb8 < per_sm * sms ? nb4 + nb8 : per_sm * sms;
-  if (dtype == 0) {
-    if ((e = set_smem(roi_bwd_pull_tma<float>, smem)) != cudaSuccess) return e;
-    roi_bwd_pull_tma<float><<<pgrid, kPullThreads, smem, stream>>>(p, ws, tm[0], tm[1], nb4, nb8, ring);
-  } else {
-    if ((e = set_smem(roi_bwd_pull_tma<__nv_bfloat16>, smem)) != cudaSuccess) return e;
-    roi_bwd_pull_tma<__nv_bfloat16><<<pgrid, kPullThreads, smem, stream>>>(p, ws, tm[0], tm[1], nb4, nb8, ring);
-  }
+#define ARFE_PULL(TT, NVV)                                                                          \
+  do {                                                                                              \
+    if ((e = set_smem(roi_bwd_pull_tma<TT, NVV>, smem)) != cudaSuccess) return e;                   \
+    roi_bwd_pull_tma<TT, NVV><<<pgrid, kPullThreads, smem, stream>>>(p, ws, tm[0], tm[1], nb4, nb8, ring); \
+  } while (0)
+  if (dtype == 0) { if (nv == 2) ARFE_PULL(float, 2); else ARFE_PULL(float, 1); }
+  else ARFE_PULL(__nv_bfloat16, 1);
+#undef ARFE_PULL
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   const int igrid = ntiles[0] + ntiles[1] < 592 ? ntiles[0] + ntiles[1] : 592;
   if (dtype == 0) roi_bwd_pull_inline<float><<<igrid, kThreads, 0, stream>>>(p, ws, tm[0], tm[1], ntiles[0]);
