@@ -1,25 +1,29 @@
 // Channels-last (NHWC) fast path of the AR-RFF extraction.
 //
 // With channels innermost every access of this gather/scatter workload is
-// lane == channel coalesced, so nothing has to be transposed through shared
-// memory and nothing needs an atomic:
+// lane == channel coalesced, a window row of a region is one contiguous piece
+// of memory, and nothing needs an atomic:
 //
-//   forward  : one CTA per (RoI, region); a warp owns a bin, lanes own 4 (fp32)
-//              or 8 (bf16) consecutive channels; every tap is ONE 128-bit
-//              L1-cached load per lane (100 % sector efficiency; taps shared by
-//              neighbouring bins hit L1).  Output either channels-last
-//              (direct 128-bit stores) or NCHW (staged [bin][C] in smem).
-//   backward : PULL formulation.  roi_prep writes, per region, its window and
-//              for every window row/column the bins that sample it with their
-//              aggregated weights (the transpose of the forward tables) into a
-//              caller-provided workspace.  roi_bwd_pull then gives every 8x8
-//              pixel tile of every level to one CTA: warp == tile row,
-//              lanes == channels, accumulators in registers, the regions that
-//              intersect the tile are visited in index order -> every gradient
-//              element is written exactly once, deterministically, with no
-//              atomics and no zero-fill.  (The NCHW/atomic kernel is bound by
-//              the L2 atomic units at ~1 fp32 element per slice-clock; see
-//              DESIGN.md section 6.)
+//   plan     : roi_prep_kernel writes, per (RoI, region), its level, window and
+//              the aggregated bilinear tables (rows transposed, columns in
+//              forward form) plus per-band id segments into a caller-provided
+//              workspace; forward and backward share it.
+//   forward  : roi_fuse_fwd_ring -- persistent CTAs, a producer warp streams
+//              window rows through a shared-memory byte ring with bulk async
+//              copies (TMA) + mbarriers, consumer warps (one per output column)
+//              fold taps from shared memory; every window byte crosses L2 -> SM
+//              once.  roi_fuse_fwd_cl (L1-cached 128-bit gathers, one CTA per
+//              region) is the plan-free kernel and serves the regions the ring
+//              cannot take, and NCHW output.
+//   backward : PULL formulation.  roi_bin_kernel lists, per 8x8 / 8x4 tile, the
+//              regions that reach it (index order) and writes one stage
+//              descriptor per entry; roi_bwd_pull_tma (persistent, TMA ring)
+//              streams the dout bins of each stage once per tile, warp == tile
+//              row, lanes == channels, accumulators in registers -> every
+//              gradient element is written exactly once, deterministically,
+//              with no atomics and no zero-fill.  (The NCHW/atomic kernel is
+//              bound by the L2 atomic units at ~1 fp32 element per slice-clock;
+//              see DESIGN.md section 6.)
 #include <stdlib.h>
 
 #include "roi_common.cuh"
