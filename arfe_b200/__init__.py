@@ -7,7 +7,7 @@ reference's module/operator surface.  Compute lives in libarfe_b200.so
 from ._compat import ConvModule, register_into_mmdet  # noqa: F401
 from .bbox_head import MultiBBoxHead, MultiRoIsBBoxHead  # noqa: F401
 from .functional import (fpn_apply, fpn_gather, rff_gate, roi_fuse,  # noqa: F401
-                         roi_fuse_debug, split3)
+                         roi_fuse_debug, roi_fuse_split, split3)
 from .neck import NonLocal2D, WFPNDualSpatial  # noqa: F401
 from .regions import get_adaptive_scale_rois  # noqa: F401
 from .roi_align import RoIAlign, RoIAlignFunction, roi_align  # noqa: F401

@@ -67,6 +67,25 @@ int fill_roi_params(const char* fn, arfe::RoiFuseParams& p, const int32_t* H, co
   p.L = L; p.B = B; p.C = C; p.K = K; p.R = regions; p.PH = PH; p.PW = PW;
   p.sampling_ratio = sampling_ratio; p.facs = facs; p.finest_scale = finest_scale;
   p.rois = rois;
+  // channels-last RoI tensors: the concatenated layout [K][PH*PW][regions*C]
+  for (int r = 0; r < 3; ++r) p.reg_off[r] = (long long)r * C;
+  p.bin_stride = regions * C;
+  return ARFE_OK;
+}
+
+// Split layout: one tensor [K][PH*PW][C] per region, anywhere in memory.
+template <typename P>
+int set_split_regions(const char* fn, arfe::RoiFuseParams& p, P const* reg, int regions,
+                      int C, int dtype, const void** base) {
+  REQUIRE(reg, ARFE_E_NULL, "%s: region pointer array is NULL", fn);
+  for (int r = 0; r < regions; ++r) {
+    REQUIRE(reg[r], ARFE_E_NULL, "%s: region %d is NULL", fn, r);
+    REQUIRE(aligned(reg[r], 16), ARFE_E_ALIGN, "%s: region %d must be 16-byte aligned", fn, r);
+    const long long d = static_cast<const char*>(reg[r]) - static_cast<const char*>(reg[0]);
+    p.reg_off[r] = d / (long long)esize(dtype);
+  }
+  p.bin_stride = C;
+  *base = reg[0];
   return ARFE_OK;
 }
 
@@ -114,19 +133,18 @@ int arfe_roi_fuse_forward(const void* const* feats, const int32_t* H, const int3
   return cuda_result(arfe::launch_roi_fuse_forward(p, dtype, layout, (cudaStream_t)stream), fn);
 }
 
-int arfe_roi_fuse_forward_plan(const void* const* feats, const int32_t* H, const int32_t* W,
-                               const float* spatial_scale, int L, int B, int C, const float* rois,
-                               int K, int regions, float facs, int PH, int PW, int sampling_ratio,
-                               float finest_scale, int dtype, void* out, int32_t* lvl_out,
-                               float* boxes_out, void* workspace, size_t workspace_bytes,
-                               void* stream) {
-  const char* fn = "arfe_roi_fuse_forward_plan";
+static int forward_plan_impl(const char* fn, const void* const* feats, const int32_t* H, const int32_t* W,
+                             const float* spatial_scale, int L, int B, int C, const float* rois,
+                             int K, int regions, float facs, int PH, int PW, int sampling_ratio,
+                             float finest_scale, int dtype, void* out, void* const* out_regions,
+                             int32_t* lvl_out, float* boxes_out, void* workspace,
+                             size_t workspace_bytes, void* stream) {
   arfe::RoiFuseParams p;
   int rc = fill_roi_params(fn, p, H, W, spatial_scale, L, B, C, rois, K, regions, facs, PH, PW,
                            sampling_ratio, finest_scale, dtype, ARFE_NHWC);
   if (rc) return rc;
   if (K == 0) return ARFE_OK;
-  REQUIRE(feats && out && workspace, ARFE_E_NULL, "%s: feats/out/workspace is NULL", fn);
+  REQUIRE(feats && (out || out_regions) && workspace, ARFE_E_NULL, "%s: feats/out/workspace is NULL", fn);
   REQUIRE(B >= 1, ARFE_E_SHAPE, "%s: B=0 with K>0", fn);
   REQUIRE(C % (dtype == ARFE_F32 ? 4 : 8) == 0, ARFE_E_UNSUPPORTED, "%s: C must be a multiple of %d",
           fn, dtype == ARFE_F32 ? 4 : 8);
@@ -134,6 +152,12 @@ int arfe_roi_fuse_forward_plan(const void* const* feats, const int32_t* H, const
     REQUIRE(feats[l], ARFE_E_NULL, "%s: feats[%d] is NULL", fn, l);
     REQUIRE(aligned(feats[l], 16), ARFE_E_ALIGN, "%s: feats[%d] must be 16-byte aligned", fn, l);
     p.feats[l] = feats[l];
+  }
+  if (out_regions) {
+    const void* base = nullptr;
+    rc = set_split_regions(fn, p, out_regions, regions, C, dtype, &base);
+    if (rc) return rc;
+    out = const_cast<void*>(base);
   }
   REQUIRE(aligned(out, 16) && aligned(rois, 4) && aligned(workspace, 256), ARFE_E_ALIGN,
           "%s: out (16) / rois (4) / workspace (256) misaligned", fn);
@@ -145,6 +169,29 @@ int arfe_roi_fuse_forward_plan(const void* const* feats, const int32_t* H, const
     p.debug_skip = ev ? atoi(ev) : 0;
   }
   return cuda_result(arfe::launch_roi_fuse_forward_plan(p, dtype, workspace, workspace_bytes, (cudaStream_t)stream), fn);
+}
+
+int arfe_roi_fuse_forward_plan(const void* const* feats, const int32_t* H, const int32_t* W,
+                               const float* spatial_scale, int L, int B, int C, const float* rois,
+                               int K, int regions, float facs, int PH, int PW, int sampling_ratio,
+                               float finest_scale, int dtype, void* out, int32_t* lvl_out,
+                               float* boxes_out, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  return forward_plan_impl("arfe_roi_fuse_forward_plan", feats, H, W, spatial_scale, L, B, C, rois, K,
+                           regions, facs, PH, PW, sampling_ratio, finest_scale, dtype, out, nullptr,
+                           lvl_out, boxes_out, workspace, workspace_bytes, stream);
+}
+
+int arfe_roi_fuse_forward_plan_split(const void* const* feats, const int32_t* H, const int32_t* W,
+                                     const float* spatial_scale, int L, int B, int C,
+                                     const float* rois, int K, int regions, float facs, int PH,
+                                     int PW, int sampling_ratio, float finest_scale, int dtype,
+                                     void* const* out_regions, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  if (!out_regions) return fail(ARFE_E_NULL, "arfe_roi_fuse_forward_plan_split: out_regions is NULL");
+  return forward_plan_impl("arfe_roi_fuse_forward_plan_split", feats, H, W, spatial_scale, L, B, C, rois,
+                           K, regions, facs, PH, PW, sampling_ratio, finest_scale, dtype, nullptr,
+                           out_regions, nullptr, nullptr, workspace, workspace_bytes, stream);
 }
 
 int arfe_roi_fuse_backward(const void* dout, int dout_layout, const int32_t* H, const int32_t* W,
@@ -182,12 +229,12 @@ size_t arfe_roi_fuse_pull_workspace_bytes(int K, int regions, int L, int B, cons
   return arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W);
 }
 
-int arfe_roi_fuse_backward_pull(const void* dout, const int32_t* H, const int32_t* W,
+static int backward_pull_impl(const char* fn, const void* dout, const void* const* dout_regions,
+                              const int32_t* H, const int32_t* W,
                                 const float* spatial_scale, int L, int B, int C, const float* rois,
                                 int K, int regions, float facs, int PH, int PW, int sampling_ratio,
                                 float finest_scale, int dtype, float* const* dfeats,
                                 void* workspace, size_t workspace_bytes, int plan_ready, void* stream) {
-  const char* fn = "arfe_roi_fuse_backward_pull";
   arfe::RoiFuseParams p;
   int rc = fill_roi_params(fn, p, H, W, spatial_scale, L, B, C, rois, K, regions, facs, PH, PW,
                            sampling_ratio, finest_scale, dtype, ARFE_NHWC);
@@ -208,6 +255,10 @@ int arfe_roi_fuse_backward_pull(const void* dout, const int32_t* H, const int32_
     }
     return ARFE_OK;
   }
+  if (dout_regions) {
+    rc = set_split_regions(fn, p, dout_regions, regions, C, dtype, &dout);
+    if (rc) return rc;
+  }
   REQUIRE(dout && workspace, ARFE_E_NULL, "%s: dout/workspace is NULL", fn);
   REQUIRE(aligned(dout, 16) && aligned(workspace, 256), ARFE_E_ALIGN, "%s: dout (16) / workspace (256) misaligned", fn);
   REQUIRE(workspace_bytes >= arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W), ARFE_E_SHAPE,
@@ -224,6 +275,28 @@ int arfe_roi_fuse_backward_pull(const void* dout, const int32_t* H, const int32_
   p.flag_list = arfe::roi_pull_flag_list(K, regions, L, B, H, W, workspace, &p.flag_count);
   p.bwd_vec = 0;
   return cuda_result(arfe::launch_roi_fuse_backward(p, dtype, ARFE_NHWC, (cudaStream_t)stream), fn);
+}
+
+int arfe_roi_fuse_backward_pull(const void* dout, const int32_t* H, const int32_t* W,
+                                const float* spatial_scale, int L, int B, int C, const float* rois,
+                                int K, int regions, float facs, int PH, int PW, int sampling_ratio,
+                                float finest_scale, int dtype, float* const* dfeats,
+                                void* workspace, size_t workspace_bytes, int plan_ready, void* stream) {
+  return backward_pull_impl("arfe_roi_fuse_backward_pull", dout, nullptr, H, W, spatial_scale, L, B, C,
+                            rois, K, regions, facs, PH, PW, sampling_ratio, finest_scale, dtype, dfeats,
+                            workspace, workspace_bytes, plan_ready, stream);
+}
+
+int arfe_roi_fuse_backward_pull_split(const void* const* dout_regions, const int32_t* H, const int32_t* W,
+                                      const float* spatial_scale, int L, int B, int C,
+                                      const float* rois, int K, int regions, float facs, int PH,
+                                      int PW, int sampling_ratio, float finest_scale, int dtype,
+                                      float* const* dfeats, void* workspace, size_t workspace_bytes,
+                                      int plan_ready, void* stream) {
+  if (!dout_regions && K > 0) return fail(ARFE_E_NULL, "arfe_roi_fuse_backward_pull_split: dout_regions is NULL");
+  return backward_pull_impl("arfe_roi_fuse_backward_pull_split", nullptr, dout_regions, H, W, spatial_scale,
+                            L, B, C, rois, K, regions, facs, PH, PW, sampling_ratio, finest_scale, dtype,
+                            dfeats, workspace, workspace_bytes, plan_ready, stream);
 }
 
 int arfe_roi_align_forward(const void* input, const float* rois, float spatial_scale,

@@ -26,6 +26,8 @@ struct RoiFuseParams {
   int dout_cl;       // backward: dout channels-last (1) or NCHW (0)
   const int* flag_list;   // backward (atomic kernel as the pull fallback): region ids to process ...
   const int* flag_count;  // ... and how many (device memory)
+  long long reg_off[3];  // channels-last out / dout: element offset of region r's block from the base pointer ...
+  int bin_stride;        // ... and elements between consecutive bins (concatenated: r * C, R * C)
   int debug_skip;    // profiling aid (ARFE_FWD_SKIP): 1 compute, 2 staging, 4 write-out, 8 all but setup
 };
 

@@ -358,7 +358,7 @@ __device__ __forceinline__ void roi_fuse_bwd_region(const RoiFuseParams& p, int 
       static_cast<const T*>(p.dout) + ((size_t)k * p.R + r) * C * PHW;
   // element (c, bin) of this region's incoming gradient, NCHW or channels-last
   auto dout_at = [&](int c, int bin) -> float {
-    return p.dout_cl ? to_f(static_cast<const T*>(p.dout)[((size_t)k * PHW + bin) * (p.R * C) + (size_t)r * C + c])
+    return p.dout_cl ? to_f(static_cast<const T*>(p.dout)[((size_t)k * PHW + bin) * p.bin_stride + p.reg_off[r] + c])
                      : to_f(dout_blk[(size_t)c * PHW + bin]);
   };
 

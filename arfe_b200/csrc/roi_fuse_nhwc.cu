@@ -255,7 +255,7 @@ __device__ void fwd_direct_cl(const RoiFuseParams& p, const CtaHeader& hd, const
   constexpr int V2 = V / 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp >= nwarps) return;
-  const int PH = p.PH, PW = p.PW, C = p.C, RC = p.R * C;
+  const int PH = p.PH, PW = p.PW, C = p.C, BS = p.bin_stride;
   const int H = hd.H, W = hd.W;
   const float inv_count = 1.0f / hd.g.count;
   const uint64_t inv2 = pack2(inv_count, inv_count);
@@ -273,7 +273,7 @@ __device__ void fwd_direct_cl(const RoiFuseParams& p, const CtaHeader& hd, const
     const float* __restrict__ wy = ty.w + ty.off[ph];
     const bool up = (ph & 1) != 0;
     const T* __restrict__ rowbase = fimg + (size_t)ty.first[ph] * rowstride + c;
-    T* __restrict__ o = out + ((size_t)k * PH * PW + ph * PW) * RC + (size_t)r * C + c;
+    T* __restrict__ o = out + ((size_t)k * PH * PW + ph * PW) * BS + p.reg_off[r] + c;
     for (int pw = 0; pw < PW; ++pw) {
       const int nc = tx.cnt[pw];
       uint64_t acc[V2];
@@ -285,7 +285,7 @@ __device__ void fwd_direct_cl(const RoiFuseParams& p, const CtaHeader& hd, const
       float f[V];
 #pragma unroll
       for (int u = 0; u < V2; ++u) unpack2(mul2(acc[u], inv2), f[2 * u], f[2 * u + 1]);
-      st_vec<T>(o + (size_t)pw * RC, f);
+      st_vec<T>(o + (size_t)pw * BS, f);
     }
   }
 }
@@ -302,11 +302,11 @@ __device__ __forceinline__ void fwd_region_cl(const RoiFuseParams& p, int opitch
 
   const int k = region / p.R, r = region % p.R;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int PH = p.PH, PW = p.PW, PHW = PH * PW, C = p.C, RC = p.R * C;
+  const int PH = p.PH, PW = p.PW, PHW = PH * PW, C = p.C;
   T* __restrict__ out = static_cast<T*>(p.out);
   // element (bin, c) of this region's output block
   auto out_index = [&](int bin, int c) -> size_t {
-    return kOutCL ? ((size_t)k * PHW + bin) * RC + (size_t)r * C + c
+    return kOutCL ? ((size_t)k * PHW + bin) * p.bin_stride + p.reg_off[r] + c
                   : (((size_t)k * p.R + r) * C + c) * PHW + bin;
   };
 
@@ -444,9 +444,10 @@ constexpr int kMaxTW = 8;       // widest pull tile
 // One stage of the pull kernel = one listed region of one tile: the bins
 // [ph_lo, ph_lo + nph) x [pw0, pw0 + npw) of its dout block reach the tile.
 struct __align__(16) StageDesc {
-  int src_off;         // dout element offset of bin (ph_lo, pw0), channel 0 of the region's block
+  int src_off;         // dout element offset of bin (ph_lo, pw0) inside the region's block
   short nph, npw;
-  int pad[2];
+  int region;          // which dout block (p.reg_off[region])
+  int pad;
   int4 rows[kBandH];   // per tile row: {first bin row - ph_lo (< 0: row not sampled), two bins, w0, w1}
   float cw[kJ][kMaxTW];  // per output column: its weights over the tile columns
 };
@@ -844,7 +845,7 @@ roi_fuse_fwd_ring(const RoiFuseParams p, const PullWs ws, int ncons, int ring_by
   unsigned char* ring = ctl + 512;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int PW = p.PW, PHW = PH * PW, C = p.C, RC = p.R * C;
+  const int PW = p.PW, PHW = PH * PW, C = p.C, BS = p.bin_stride;
   const int N = p.K * p.R;
   T* __restrict__ out = static_cast<T*>(p.out);
 
@@ -960,11 +961,11 @@ roi_fuse_fwd_ring(const RoiFuseParams p, const PullWs ws, int ncons, int ring_by
       const int nc = cb.cnt;
       const float* __restrict__ wxp = tb.colw + cb.off;
       const uint32_t tap0 = (uint32_t)((nc > 0 ? cb.first - tb.hdr.xmin : 0) * C + (act ? c : 0)) * sizeof(T);
-      T* __restrict__ o = act ? out + ((size_t)k * PHW + pw) * RC + (size_t)r * C + c : nullptr;
+      T* __restrict__ o = act ? out + ((size_t)k * PHW + pw) * BS + p.reg_off[r] + c : nullptr;
       const int nblk = (flags >> 8) & 15;
       FwdPipe pipe{full, empty, stage_off, ring};
 #define ARFE_CONSUME(NCC) \
-  fwd_consume_rows<T, PH, NCC, NCH>(pipe, stage, nrows, nblk, tb.rowtab, wxp, tap0, C, o, (size_t)PW * RC)
+  fwd_consume_rows<T, PH, NCC, NCH>(pipe, stage, nrows, nblk, tb.rowtab, wxp, tap0, C, o, (size_t)PW * BS)
       switch ((p.debug_skip & 1) ? 0 : nc) {  // profiling aid: 0 taps == no math
         case 0: ARFE_CONSUME(0); break;
         case 1: ARFE_CONSUME(1); break;
@@ -976,16 +977,16 @@ roi_fuse_fwd_ring(const RoiFuseParams p, const PullWs ws, int ncons, int ring_by
         case 7: ARFE_CONSUME(7); break;
         case 8: ARFE_CONSUME(8); break;
         default:
-          fwd_consume_rows<T, PH, 8, NCH>(pipe, stage, nrows, nblk, tb.rowtab, wxp, tap0, C, o, (size_t)PW * RC, nc);
+          fwd_consume_rows<T, PH, 8, NCH>(pipe, stage, nrows, nblk, tb.rowtab, wxp, tap0, C, o, (size_t)PW * BS, nc);
           break;
       }
 #undef ARFE_CONSUME
       stage += nrows;
     } else if (lvl < 0) {  // nothing is pooled: zeros
-      T* __restrict__ o = out + (size_t)k * PHW * RC + (size_t)r * C;
+      T* __restrict__ o = out + (size_t)k * PHW * BS + p.reg_off[r];
       for (int e = tid; e < C * PHW; e += ncons * 32) {
         const int bin = e / C, cc = e - bin * C;
-        o[(size_t)bin * RC + cc] = from_f<T>(0.f);
+        o[(size_t)bin * BS + cc] = from_f<T>(0.f);
       }
     }  // else: served by the L1-cached kernel over ws.fwd_list
     __syncwarp();
@@ -1210,9 +1211,10 @@ __device__ __forceinline__ bool write_stage_rows(const RoiFuseParams& p, StageDe
   sd->rows[row] = r;
   if (row == 0) {
     const int k = e.src / p.R, rr = e.src - k * p.R;
-    sd->src_off = nph > 0 ? (k * p.PH * p.PW + lo * p.PW + e.pw0) * (p.R * p.C) + rr * p.C : 0;
+    sd->src_off = nph > 0 ? (k * p.PH * p.PW + lo * p.PW + e.pw0) * p.bin_stride : 0;
     sd->nph = (short)nph;
     sd->npw = e.npw;
+    sd->region = rr;
   }
   return nph <= kMaxPh;
 }
@@ -1464,7 +1466,7 @@ roi_bwd_pull_tma(const RoiFuseParams p, const PullWs ws, const TileMap tm4, cons
     uint32_t head = 0, tail = 0;  // live bytes of the ring: [tail, head) modulo wrap
     uint32_t my_off = 0;          // lane j: ring offset of the stage in slot j
     int issued = 0, released = 0; // stages issued / known to be consumed
-    const int C = p.C, RC = p.R * C;
+    const int C = p.C, BS = p.bin_stride;
     auto claim = [&]() -> int { return lane == 0 ? atomicAdd(ws.counters + 2, 1) : 0; };
     auto tile_desc_of = [&](int g) -> int2 {
       if (g >= total) return make_int2(0, -1);
@@ -1502,6 +1504,7 @@ roi_bwd_pull_tma(const RoiFuseParams p, const PullWs ws, const TileMap tm4, cons
           if ((i & 31) == 0 && i > 0 && i + lane < n) hdr = __ldg(reinterpret_cast<const int4*>(gdesc + i + lane));
           const int src_off = __shfl_sync(0xffffffffu, hdr.x, i & 31);
           const int nn = __shfl_sync(0xffffffffu, hdr.y, i & 31);
+          const int rg = __shfl_sync(0xffffffffu, hdr.z, i & 31);
           const int nph = nn & 0xffff, npw = (nn >> 16) & 0xffff;
           const int nbins = nph * npw;
           const uint32_t bytes = (uint32_t)nbins * bin_bytes;
@@ -1535,7 +1538,7 @@ roi_bwd_pull_tma(const RoiFuseParams p, const PullWs ws, const TileMap tm4, cons
           for (int bi = lane; bi < nbins; bi += 32) {
             const int ih = bi / npw, iw = bi - ih * npw;
             bulk_g2s(ring + off + (uint32_t)bi * bin_bytes,
-                     dsrc + (size_t)src_off + (size_t)(ih * p.PW + iw) * RC, bin_bytes, ctl.full + slot);
+                     dsrc + p.reg_off[rg] + (size_t)src_off + (size_t)(ih * p.PW + iw) * BS, bin_bytes, ctl.full + slot);
           }
           ++issued;
         }
@@ -1576,7 +1579,7 @@ __device__ void pull_tile_inline(const RoiFuseParams& p, const PullWs& ws, const
   constexpr int V2 = V / 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Tile tl = decode_tile(p, ws, tm, t, TW);
-  const int C = p.C, RC = p.R * C, rowstep = p.PW * RC;
+  const int C = p.C, BS = p.bin_stride, rowstep = p.PW * BS;
   const int y = tl.y0 + warp;
   for (int c0 = 0; c0 < C; c0 += 32 * V) {
     const int cl = c0 + lane * V;
@@ -1603,8 +1606,8 @@ __device__ void pull_tile_inline(const RoiFuseParams& p, const PullWs& ws, const
             d = expand_row(ws, e, tl.y0 + row);
             if (d.x >= 0) {  // -> {dout offset of (p0, pw0), npw | two << 8, w0, w1}
               const int k = e.src / p.R, r = e.src - k * p.R;
-              d.x = (k * p.PH * p.PW + d.x * p.PW + e.pw0) * RC + r * C;
-              d.y = e.npw | (d.y ? 256 : 0);
+              d.x = (k * p.PH * p.PW + d.x * p.PW + e.pw0) * BS;
+              d.y = e.npw | (d.y ? 256 : 0) | (r << 16);
             }
           }
           rdesc[row * kChunkR + q] = d;
@@ -1632,7 +1635,7 @@ __device__ void pull_tile_inline(const RoiFuseParams& p, const PullWs& ws, const
             const bool two = (cur.y & 256) != 0;
             const float a0 = __int_as_float(cur.z), a1 = __int_as_float(cur.w);
             const uint64_t a0p = pack2(a0, a0), a1p = pack2(a1, a1);
-            const T* __restrict__ src = dbase + cur.x;
+            const T* __restrict__ src = dbase + p.reg_off[(cur.y >> 16) & 3] + cur.x;
             const float* __restrict__ cw = cwt + q * (kJ * TW);
             for (int jj = 0; jj < npw; ++jj) {
               uint64_t e[V2], e1[V2];
@@ -1650,7 +1653,7 @@ __device__ void pull_tile_inline(const RoiFuseParams& p, const PullWs& ws, const
 #pragma unroll
                 for (int u = 0; u < V2; ++u) acc[x][u] = fma2(e[u], wp, acc[x][u]);
               }
-              src += RC;
+              src += BS;
               cw += TW;
             }
           }

@@ -146,6 +146,98 @@ def roi_fuse(feats, rois, out_size, spatial_scales, sample_num=0, regions=3,
                                   out_channels_last, *feats)
 
 
+class _RoIFuseSplitFunction(Function):
+    """Same extraction as _RoIFuseFunction for channels-last features, with the
+    regions as SEPARATE channels-last tensors (ori, lw, lh) instead of
+    torch.cat([ori, lw, lh], 1) (standard_roi_head.py:155): the head convolves
+    each region on its own (multirois_bbox_head.py:167-173), so the cat and the
+    slices (and, backward, the zero-fill + slice-assign autograd inserts for
+    them) are pure copies.  Forward: plan + ring kernel; backward: pull kernel
+    reading the three incoming gradients in place, reusing the plan."""
+
+    @staticmethod
+    def forward(ctx, rois, out_size, spatial_scales, sample_num, regions, facs,
+                finest_scale, *feats):
+        oh, ow = _pair(out_size)
+        feats, layout, dt = _prep_feats(feats)
+        rois = _prep_rois(rois)
+        B, C = feats[0].shape[:2]
+        if layout != L.ARFE_NHWC or not _vec_ok(C, feats[0].dtype):
+            raise RuntimeError("roi_fuse_split needs channels-last features with C % 4 (fp32) / 8 (bf16) == 0")
+        Hs = [f.shape[2] for f in feats]
+        Ws = [f.shape[3] for f in feats]
+        K = rois.size(0)
+        dev = feats[0].device
+        outs = [torch.empty((K, C, oh, ow), dtype=feats[0].dtype, device=dev,
+                            memory_format=torch.channels_last) for _ in range(regions)]
+        ctx.meta = (oh, ow, tuple(spatial_scales), sample_num, regions, facs, finest_scale, dt,
+                    B, C, Hs, Ws, feats[0].dtype)
+        ctx.save_for_backward(rois)
+        ctx.plan = None
+        if K > 0:
+            lib = L.lib()
+            nbytes = lib.arfe_roi_plan_bytes(K, regions, len(feats), B, L.int_array(Hs), L.int_array(Ws))
+            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+            ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+            rc = lib.arfe_roi_fuse_forward_plan_split(
+                L.ptr_array(feats), L.int_array(Hs), L.int_array(Ws), L.float_array(spatial_scales),
+                len(feats), B, C, rois.data_ptr(), K, regions, float(facs), oh, ow, int(sample_num),
+                float(finest_scale), dt, L.ptr_array(outs), ws_ptr, nbytes, L.stream_ptr(dev))
+            L.check(rc, "arfe_roi_fuse_forward_plan_split")
+            if any(f.requires_grad for f in feats):
+                ctx.plan = (ws, ws_ptr, nbytes)
+        return tuple(outs)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *grad_outs):
+        (rois,) = ctx.saved_tensors
+        (oh, ow, scales, sample_num, regions, facs, finest_scale, dt, B, C, Hs, Ws, fdtype) = ctx.meta
+        nlev = len(Hs)
+        NP = 7  # non-tensor inputs of forward()
+        if not any(ctx.needs_input_grad[NP:]):
+            return (None,) * (NP + nlev)
+        K = rois.size(0)
+        dev = rois.device
+        lib = L.lib()
+        gs = []
+        for g in grad_outs:
+            if g is None:
+                g = torch.zeros((K, C, oh, ow), dtype=fdtype, device=dev)
+            g = g if g.dtype == fdtype else g.to(fdtype)
+            gs.append(g.contiguous(memory_format=torch.channels_last))
+        dfeats = [torch.empty((B, C, Hs[l], Ws[l]), dtype=torch.float32, device=dev,
+                              memory_format=torch.channels_last) for l in range(nlev)]
+        if K > 0:
+            if ctx.plan is not None:
+                ws, ws_ptr, nbytes = ctx.plan
+                ready = 1
+            else:
+                nbytes = lib.arfe_roi_plan_bytes(K, regions, nlev, B, L.int_array(Hs), L.int_array(Ws))
+                ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+                ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+                ready = 0
+            rc = lib.arfe_roi_fuse_backward_pull_split(
+                L.ptr_array(gs), L.int_array(Hs), L.int_array(Ws), L.float_array(scales), nlev, B, C,
+                rois.data_ptr(), K, regions, float(facs), oh, ow, int(sample_num), float(finest_scale),
+                dt, L.ptr_array(dfeats), ws_ptr, nbytes, ready, L.stream_ptr(dev))
+            L.check(rc, "arfe_roi_fuse_backward_pull_split")
+        else:
+            for d in dfeats:
+                d.zero_()
+        grads = tuple(d if fdtype == torch.float32 else d.to(fdtype) for d in dfeats)
+        return (None,) * NP + grads
+
+
+def roi_fuse_split(feats, rois, out_size, spatial_scales, sample_num=0, regions=3,
+                   facs=1.0, finest_scale=56):
+    """The `regions` region tensors (ori, lw, lh), each [K, C, oh, ow] in
+    torch.channels_last -- torch.cat(roi_fuse_split(...), 1) == roi_fuse(...).
+    Channels-last features only."""
+    return _RoIFuseSplitFunction.apply(rois, out_size, tuple(spatial_scales), sample_num,
+                                       regions, facs, finest_scale, *feats)
+
+
 def roi_fuse_debug(rois, Hs, Ws, spatial_scales, out_size=7, sample_num=0,
                    regions=3, facs=1.0, finest_scale=56, max_grid=16):
     """Boxes, levels, grids and bilinear taps exactly as the kernels compute

@@ -95,11 +95,16 @@ class TrainStep:
     memory layout through the compatibility kernels.
     """
 
-    def __init__(self, host, device, regions=3, channels_last=True):
+    def __init__(self, host, device, regions=3, channels_last=True, split=None):
+        """split (channels-last only, default on): the region features and their
+        gradients are separate tensors (ori | lw | lh) instead of one concatenated
+        tensor -- what the head's convolutions produce / consume -- so the step
+        needs no torch copies between our kernels."""
         self.dev = device
         self.lib = L.lib()
         x = host["x"]
         self.cl = bool(channels_last)
+        self.split = self.cl if split is None else (bool(split) and self.cl)
         self.layout = L.ARFE_NHWC if self.cl else L.ARFE_NCHW
         mf = torch.channels_last if self.cl else torch.contiguous_format
         self.dtype = x[0].dtype
@@ -136,6 +141,11 @@ class TrainStep:
         self.dF = e(K, R * C, P, P)            # [d_ori | d_lw | d_lh]
         self.d_ori = e(K, C, P, P)
         self.d_ab = e(K, C, P, P)
+        if self.split:
+            self.Fr = [e(K, C, P, P) for _ in range(R)]
+            self.p_Fr = L.ptr_array(self.Fr)
+            # stand-ins for the conv backward of the two context branches: d_ab for both
+            self.p_dFr = L.ptr_array([self.d_ori] + [self.d_ab] * (R - 1))
         self.dy = [e(B, C, h, w, dtype=torch.float32) for h, w in self.shapes]
         self.dy_in = self.dy if self.dtype == torch.float32 else [e(B, C, h, w) for h, w in self.shapes]
         self.dbsf = e(B, C, hr, wr, dtype=torch.float32)
@@ -157,7 +167,11 @@ class TrainStep:
         self.p_dg1, self.p_dg2 = L.ptr_array(self.dg1), L.ptr_array(self.dg2)
         self.p_dx = L.ptr_array(self.dx)
         # the gate sees [rows][n] with `ori` strided inside the concatenated tensor
-        if self.cl:   # memory [K*49][R*C]: a row is one bin of one RoI
+        self.gate_in, self.gate_dout = self.F, self.dF
+        if self.split:  # memory [K*49][C]: `ori` and d_ori are tensors of their own
+            self.gate_rows, self.gate_n, self.gate_stride = K * self.PP, C, C
+            self.gate_in, self.gate_dout = self.Fr[0], self.d_ori
+        elif self.cl:   # memory [K*49][R*C]: a row is one bin of one RoI
             self.gate_rows, self.gate_n, self.gate_stride = K * self.PP, C, R * C
         else:         # memory [K][R*C*49]: a row is one RoI
             self.gate_rows, self.gate_n, self.gate_stride = K, C * self.PP, R * C * self.PP
@@ -176,6 +190,12 @@ class TrainStep:
             self.B, self.C, hr, wr, self.dt, self.layout, self.p_y, self.stream)
 
     def roi_fuse_fwd(self):
+        if self.split:
+            self.planned = 1
+            return self.lib.arfe_roi_fuse_forward_plan_split(
+                self.p_y, self.H, self.W, self.scales, self.nlev, self.B, self.C,
+                self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt,
+                self.p_Fr, self.ws_ptr, self.ws_bytes, self.stream)
         if self.cl:
             # channels-last: plan + ring kernel; the plan stays in the workspace for the backward
             self.planned = 1
@@ -190,16 +210,21 @@ class TrainStep:
 
     def rff_gate_fwd(self):
         return self.lib.arfe_rff_gate_forward(
-            self.F.data_ptr(), self.gate_stride, self.a.data_ptr(), self.b.data_ptr(),
+            self.gate_in.data_ptr(), self.gate_stride, self.a.data_ptr(), self.b.data_ptr(),
             self.z.data_ptr(), self.gate_rows, self.gate_n, self.dt, self.stream)
 
     def rff_gate_bwd(self):
         return self.lib.arfe_rff_gate_backward(
-            self.gz.data_ptr(), self.F.data_ptr(), self.gate_stride, self.a.data_ptr(),
-            self.b.data_ptr(), self.dF.data_ptr(), self.gate_stride, self.d_ab.data_ptr(),
+            self.gz.data_ptr(), self.gate_in.data_ptr(), self.gate_stride, self.a.data_ptr(),
+            self.b.data_ptr(), self.gate_dout.data_ptr(), self.gate_stride, self.d_ab.data_ptr(),
             self.gate_rows, self.gate_n, self.dt, self.stream)
 
     def roi_fuse_bwd(self):
+        if self.split:
+            return self.lib.arfe_roi_fuse_backward_pull_split(
+                self.p_dFr, self.H, self.W, self.scales, self.nlev, self.B, self.C,
+                self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt,
+                self.p_dy, self.ws_ptr, self.ws_bytes, getattr(self, "planned", 0), self.stream)
         if self.cl:
             return self.lib.arfe_roi_fuse_backward_pull(
                 self.dF.data_ptr(), self.H, self.W, self.scales, self.nlev, self.B, self.C,
@@ -227,6 +252,8 @@ class TrainStep:
         conv backward of the two context branches, which stays on PyTorch) and,
         on the NCHW path only, zero the accumulators (the reference's
         at::zeros, roi_align_kernel_v2.cu:325-326; the pull kernel needs none)."""
+        if self.split:
+            return  # the pull kernel reads d_ori / d_ab where they are
         C = self.C  # d_ori was written in place into dF[:, :C] by the gate backward
         for r in range(1, self.R):
             self.dF[:, r * C:(r + 1) * C].copy_(self.d_ab)

@@ -280,6 +280,8 @@ def run_ours(args, rank, local_rank, world):
             "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "rois_per_gpu": BATCH * ROIS_PER_IMG,
                        "parallelism": f"dp{world} (images sharded, no data-path collective)",
                        "memory_format": "torch.channels_last (fast path)" if cl else "NCHW (reference layout, compatibility kernels)",
+                       "roi_tensors": ("regions as separate tensors (ori | lw | lh), read/written in place: no cat / slice copies in the step"
+                                       if step.split else "concatenated [K, 3C, 7, 7]; torch slice copies between the kernels are inside the step"),
                        "l2": "inputs+outputs per step (~1.5 GB) exceed the 126 MB L2; no explicit flush",
                        "timing": "CUDA events on the launch stream, max over ranks"},
             "clocks": clocks,

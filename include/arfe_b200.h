@@ -126,6 +126,25 @@ int arfe_roi_fuse_forward_plan(const void* const* feats, const int32_t* H, const
                                int dtype, void* out, int32_t* lvl_out, float* boxes_out,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/* Split layout: the regions as separate tensors [K][PH][PW][C] (channels-last of
+ * [K, C, PH, PW]) instead of one concatenated [K][PH][PW][regions*C] -- what the
+ * head's convolutions and their backward produce / consume, so no torch.cat /
+ * slice copies are needed around the kernels.  out_regions / dout_regions:
+ * `regions` device pointers, 16-byte aligned, anywhere in memory.  Everything
+ * else as in arfe_roi_fuse_forward_plan / arfe_roi_fuse_backward_pull. */
+int arfe_roi_fuse_forward_plan_split(const void* const* feats, const int32_t* H, const int32_t* W,
+                                     const float* spatial_scale, int L, int B, int C,
+                                     const float* rois, int K, int regions, float facs,
+                                     int PH, int PW, int sampling_ratio, float finest_scale,
+                                     int dtype, void* const* out_regions, void* workspace,
+                                     size_t workspace_bytes, void* stream);
+int arfe_roi_fuse_backward_pull_split(const void* const* dout_regions, const int32_t* H,
+                                      const int32_t* W, const float* spatial_scale, int L, int B,
+                                      int C, const float* rois, int K, int regions, float facs,
+                                      int PH, int PW, int sampling_ratio, float finest_scale,
+                                      int dtype, float* const* dfeats, void* workspace,
+                                      size_t workspace_bytes, int plan_ready, void* stream);
+
 /* Atomic-free backward for channels-last tensors ("pull"): every element of
  * every dfeats[l] (fp32, ARFE_NHWC) is WRITTEN exactly once, in a fixed
  * summation order (deterministic, unlike the reference's atomicAdd,

@@ -415,3 +415,36 @@ def test_pull_pool_exhaustion_takes_inline_tiles(oracle, cuda):
     got.backward(_cl(g.to(cuda)))
     d = (xg.grad.cpu() - xo.grad).abs().max()
     assert float(d) <= 3e-5 * float(xo.grad.abs().max()) + 1e-5, float(d)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_split_regions_match_concatenated(oracle, cuda, dtype):
+    """roi_fuse_split: the regions as separate tensors, forward and backward,
+    against the oracle's cat([ori, lw, lh]) and against roi_fuse."""
+    import arfe_b200 as A
+    C = 64
+    feats = small_pyramid(oracle, batch=2, channels=C, img_h=256, img_w=384)
+    feats = [f.to(dtype).float() for f in feats]
+    rois = mixed_rois(oracle, 150, 384, 256, 2, seed=37)
+    fo = [f.clone().requires_grad_(True) for f in feats]
+    ref = oracle.arrff_bbox_feats(fo, rois, list(STRIDES))
+    g = torch.randn(ref.shape, generator=torch.Generator().manual_seed(9)).to(dtype).float()
+    ref.backward(g)
+    fg = [_cl(f.to(cuda).to(dtype)).requires_grad_(True) for f in feats]
+    parts = A.roi_fuse_split(fg, rois.to(cuda), 7, _scales(), regions=3)
+    assert len(parts) == 3 and all(p.shape == (rois.size(0), C, 7, 7) for p in parts)
+    check = assert_close_fp32 if dtype == torch.float32 else assert_close_bf16
+    check(torch.cat(parts, 1), ref, "split forward")
+    gs = [_cl(g[:, r * C:(r + 1) * C].to(cuda).to(dtype)) for r in range(3)]
+    torch.autograd.backward(parts, gs)
+    fc = [_cl(f.to(cuda).to(dtype)).requires_grad_(True) for f in feats]
+    cat = A.roi_fuse(fc, rois.to(cuda), 7, _scales(), regions=3, out_channels_last=True)
+    cat.backward(_cl(g.to(cuda).to(dtype)))
+    for l in range(5):
+        r = fo[l].grad if fo[l].grad is not None else torch.zeros_like(feats[l])
+        if dtype == torch.float32:
+            assert torch.equal(fg[l].grad, fc[l].grad), f"split vs concatenated backward differ at level {l}"
+            d = (fg[l].grad.cpu() - r).abs().max()
+            assert float(d) <= 2e-5 * float(r.abs().max()) + 1e-6, (l, float(d))
+        else:
+            assert_close_bf16(fg[l].grad, r, f"split backward level {l}")
