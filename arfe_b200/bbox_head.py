@@ -101,8 +101,9 @@ class MultiBBoxHead(nn.Module):
                 xavier_init(m, distribution='uniform')
 
     def fuse(self, x):
-        """[K, 3C, h, w] -> gated [K, C, h, w] (multirois_bbox_head.py:167-182)."""
-        ori, lwh, lhh = split3(x, self.conv_out_channels)
+        """[K, 3C, h, w] (or the three region tensors (ori, lw, lh) of the
+        extractor's split mode) -> gated [K, C, h, w] (multirois_bbox_head.py:167-182)."""
+        ori, lwh, lhh = x if isinstance(x, (tuple, list)) else split3(x, self.conv_out_channels)
         a = F.relu(self.wh_conv(lwh))
         b = F.relu(self.hh_conv(lhh))
         return rff_gate(ori, a, b)

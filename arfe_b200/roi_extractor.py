@@ -6,7 +6,7 @@ extraction (3 region boxes x level map x RoIAlign x cat) in one launch.
 import torch
 import torch.nn as nn
 
-from .functional import roi_fuse
+from .functional import roi_fuse, roi_fuse_split
 from .roi_align import RoIAlign
 
 _ROI_LAYERS = {'RoIAlign': RoIAlign}
@@ -25,6 +25,9 @@ class SingleRoIExtractor(nn.Module):
         self.fp16_enabled = False
         # emit RoI features in torch.channels_last when the pyramid is channels-last
         self.roi_feats_channels_last = False
+        # forward_regions returns (ori, lw, lh) instead of their cat for channels-last pyramids
+        # (opt-in: the reference interface is the concatenated tensor)
+        self.roi_feats_split = False
 
     @property
     def num_inputs(self):
@@ -104,6 +107,12 @@ class SingleRoIExtractor(nn.Module):
         boxes' features (standard_roi_head.py:138-155), one kernel launch."""
         out_size, sample_num, scales = self._layer_args()
         feats, half = self._cast_in(feats)
+        if self.roi_feats_split and all(f.is_contiguous(memory_format=torch.channels_last) for f in feats):
+            # the regions as separate tensors: the head convolves each on its own, so the
+            # cat (forward) and the slice gradients (backward) would be pure copies
+            outs = roi_fuse_split(feats, rois, out_size, scales[:len(feats)], sample_num,
+                                  regions=regions, facs=facs, finest_scale=self.finest_scale)
+            return tuple(o.half() for o in outs) if half else outs
         out = roi_fuse(feats, rois, out_size, scales[:len(feats)], sample_num,
                        regions=regions, facs=facs, finest_scale=self.finest_scale,
                        out_channels_last=self.roi_feats_channels_last)

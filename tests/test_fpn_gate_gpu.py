@@ -177,3 +177,39 @@ def test_head_and_roi_head_match_oracle(oracle, cuda):
     for got, ref in ((res["cls_score"], cls_ref), (res["bbox_pred"], reg_ref)):
         err = (got.cpu() - ref).abs().max()
         assert float(err) <= 1e-3 * float(ref.abs().max()) + 1e-5
+
+
+def test_roi_head_split_regions_forward_backward(oracle, cuda):
+    """StandardRoIHead with the extractor's opt-in split mode (channels-last
+    pyramid, regions as separate tensors straight into the head): scores and
+    pyramid gradients against the oracle modules."""
+    import arfe_b200 as A
+    from util import STRIDES, mixed_rois, small_pyramid
+    torch.manual_seed(2)
+    C = 16
+    ref_h = oracle.MultiRoIsBBoxHead(in_channels=C, fc_out_channels=32, num_classes=3)
+    ref_h.conv_out_channels = C
+    rh = A.StandardRoIHead(
+        bbox_roi_extractor=dict(type='SingleRoIExtractor',
+                                roi_layer=dict(type='RoIAlign', out_size=7, sample_num=0),
+                                out_channels=C, featmap_strides=list(STRIDES)),
+        bbox_head=dict(type='MultiRoIsBBoxHead', in_channels=C, conv_out_channels=C,
+                       fc_out_channels=32, roi_feat_size=7, num_classes=3))
+    rh.bbox_head.load_state_dict(ref_h.state_dict())
+    rh.bbox_roi_extractor.roi_feats_split = True
+    feats = small_pyramid(oracle, batch=2, channels=C)
+    rois = mixed_rois(oracle, 40, 320, 192, 2, seed=5)
+    fo = [f.clone().requires_grad_(True) for f in feats]
+    cls_ref, reg_ref = ref_h(oracle.arrff_bbox_feats(fo, rois, list(STRIDES)))
+    (cls_ref.sum() + reg_ref.square().sum()).backward()
+    fg = [f.to(cuda).contiguous(memory_format=torch.channels_last).requires_grad_(True) for f in feats]
+    res = rh.to(cuda)._bbox_forward(fg, rois.to(cuda))
+    assert isinstance(res["bbox_feats"], tuple) and len(res["bbox_feats"]) == 3
+    for got, ref in ((res["cls_score"], cls_ref), (res["bbox_pred"], reg_ref)):
+        err = (got.detach().cpu() - ref.detach()).abs().max()
+        assert float(err) <= 1e-3 * float(ref.abs().max()) + 1e-5
+    (res["cls_score"].sum() + res["bbox_pred"].square().sum()).backward()
+    for l in range(5):
+        r = fo[l].grad if fo[l].grad is not None else torch.zeros_like(feats[l])
+        err = (fg[l].grad.cpu() - r).abs().max()
+        assert float(err) <= 1e-3 * float(r.abs().max()) + 1e-6, (l, float(err))
