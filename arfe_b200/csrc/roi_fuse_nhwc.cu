@@ -1534,11 +1534,22 @@ roi_bwd_pull_tma(const RoiFuseParams p, const PullWs ws, const TileMap tm4, cons
             mbar_arrive_expect_tx(ctl.full + slot, ((p.debug_skip & 2) ? 0u : bytes) + kDescBytes);
             bulk_g2s(desc + slot, gdesc + i, kDescBytes, ctl.full + slot);
           }
-          if (!(p.debug_skip & 2))  // profiling aid: no bin copies
-          for (int bi = lane; bi < nbins; bi += 32) {
-            const int ih = bi / npw, iw = bi - ih * npw;
-            bulk_g2s(ring + off + (uint32_t)bi * bin_bytes,
-                     dsrc + p.reg_off[rg] + (size_t)src_off + (size_t)(ih * p.PW + iw) * BS, bin_bytes, ctl.full + slot);
+          if (p.debug_skip & 2) {
+            // profiling aid: no bin copies
+          } else if ((uint32_t)BS * sizeof(T) == bin_bytes) {
+            // split layout, all channels in this group: the npw bins of a bin row are
+            // contiguous -> one bulk copy per bin row (the per-SM rate of small bulk
+            // copies, not bandwidth, bounds this kernel)
+            for (int ih = lane; ih < nph; ih += 32)
+              bulk_g2s(ring + off + (uint32_t)(ih * npw) * bin_bytes,
+                       dsrc + p.reg_off[rg] + (size_t)src_off + (size_t)(ih * p.PW) * BS,
+                       (uint32_t)npw * bin_bytes, ctl.full + slot);
+          } else {
+            for (int bi = lane; bi < nbins; bi += 32) {
+              const int ih = bi / npw, iw = bi - ih * npw;
+              bulk_g2s(ring + off + (uint32_t)bi * bin_bytes,
+                       dsrc + p.reg_off[rg] + (size_t)src_off + (size_t)(ih * p.PW + iw) * BS, bin_bytes, ctl.full + slot);
+            }
           }
           ++issued;
         }
