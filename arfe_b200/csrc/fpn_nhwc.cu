@@ -14,6 +14,7 @@
 //                exactly once, nothing is atomic, no scratch buffer.
 // Index rules as in fpn.cu.  Requires C % (4|8) == 0 and 16-byte aligned
 // tensors; anything else takes the generic kernels in fpn.cu.
+#include <stdlib.h>
 #include <type_traits>
 
 #include "fpn_common.cuh"
@@ -233,8 +234,8 @@ gather_bwd_up_cl(const FpnParams p, const UpLevels ul) {
 
 // ------------------------------------------------------------ apply fwd/bwd
 // One warp per refine pixel (b, Y, X); NV vectors per lane cover C channels.
-template <typename T, int NV, bool kBackward>
-__global__ void __launch_bounds__(kThreads, (kBackward ? 1 : (NV * Vec<T>::n <= 8 ? 4 : 2)))
+template <typename T, int NV, bool kBackward, int kOcc>
+__global__ void __launch_bounds__(kThreads, kOcc)
 apply_cl(const FpnParams p) {
   constexpr int V = Vec<T>::n;
   const int Hr = p.Hr, Wr = p.Wr, C = p.C;
@@ -454,7 +455,17 @@ static cudaError_t launch_apply_cl(const FpnParams& p, int dtype, cudaStream_t s
   const unsigned grid = blocks_for(warps, kThreads / 32);
   const int nv = (p.C + 32 * V - 1) / (32 * V);
   if (nv > 4) return cudaErrorInvalidValue;
-#define ARFE_APPLY(TT, NV) apply_cl<TT, NV, kBackward><<<grid, kThreads, 0, stream>>>(p)
+  // resident CTAs per SM the compiler must allow: the backward is latency-bound, its
+  // speed follows occupancy (80 registers: 76 us, 64: 62 us); forward 4 / 2
+  static const int occ_env = [] { const char* ev = getenv("ARFE_APPLY_OCC"); return ev ? atoi(ev) : 0; }();
+  const int occ = kBackward ? (occ_env ? occ_env : 4) : 0;
+#define ARFE_APPLY(TT, NV)                                                                         \
+  do {                                                                                             \
+    if (!kBackward) apply_cl<TT, NV, kBackward, (NV * Vec<TT>::n <= 8 ? 4 : 2)><<<grid, kThreads, 0, stream>>>(p); \
+    else if (occ == 5) apply_cl<TT, NV, kBackward, 5><<<grid, kThreads, 0, stream>>>(p);           \
+    else if (occ == 6) apply_cl<TT, NV, kBackward, 6><<<grid, kThreads, 0, stream>>>(p);           \
+    else apply_cl<TT, NV, kBackward, 4><<<grid, kThreads, 0, stream>>>(p);                         \
+  } while (0)
   if (dtype == 0) {
     switch (nv) { case 1: ARFE_APPLY(float, 1); break; case 2: ARFE_APPLY(float, 2); break;
                   case 3: ARFE_APPLY(float, 3); break; default: ARFE_APPLY(float, 4); break; }
