@@ -17,7 +17,7 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
-    "--expt-relaxed-constexpr",] + (["-DARFE_MBAR_TEST_WAIT"] if os.environ.get("ARFE_MBAR_TEST_WAIT") else []) + [
+    "--expt-relaxed-constexpr",
     "-shared",
 ]
 
