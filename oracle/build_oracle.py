@@ -66,11 +66,42 @@ def build_reference_ext(force=False):
     return ref_ext_path()
 
 
+REF_CUDA_SRC = "mmdet/ops/roi_align/src/cuda/roi_align_kernel_v2.cu"
+REF_CUDA_DIR = os.path.join(REF_DIR, "cuda")
+
+
+def ref_cuda_ext_path():
+    hits = sorted(glob.glob(os.path.join(REF_CUDA_DIR, "roi_align_ref_cuda*.so")))
+    return hits[0] if hits else None
+
+
+def build_reference_cuda_ext(force=False):
+    """The reference's own CUDA RoIAlign v2 kernel, compiled unmodified and in
+    place for sm_100a, bound by oracle/ref_cuda_glue.cpp: the GPU baseline of
+    scripts/ref_gpu_baseline.py (BASELINE.md: 'GPU baseline to beat')."""
+    src = os.path.join(REF_ROOT, REF_CUDA_SRC)
+    glue = os.path.join(HERE, "ref_cuda_glue.cpp")
+    if not os.path.exists(src):
+        return ref_cuda_ext_path()  # GPU box: use the prebuilt .so if it travelled
+    have = ref_cuda_ext_path()
+    if have and not force and _newer(have, [src, glue]):
+        return have
+    os.makedirs(REF_CUDA_DIR, exist_ok=True)
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    from torch.utils.cpp_extension import load
+    load(name="roi_align_ref_cuda", sources=[glue, src], build_directory=REF_CUDA_DIR,
+         extra_cflags=["-O2"], extra_cuda_cflags=["-O3", "-gencode", "arch=compute_100a,code=sm_100a"],
+         verbose=False, is_python_module=True)
+    return ref_cuda_ext_path()
+
+
 def main():
     force = "--force" in sys.argv
     print("C oracle      :", build_c_oracle(force))
     print("reference ext :", build_reference_ext(force) or
           "unavailable (no /root/reference and no prebuilt oracle/_ref)")
+    if "--cuda" in sys.argv:
+        print("reference CUDA:", build_reference_cuda_ext(force) or "unavailable")
 
 
 if __name__ == "__main__":
