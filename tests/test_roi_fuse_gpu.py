@@ -448,3 +448,30 @@ def test_split_regions_match_concatenated(oracle, cuda, dtype):
             assert float(d) <= 2e-5 * float(r.abs().max()) + 1e-6, (l, float(d))
         else:
             assert_close_bf16(fg[l].grad, r, f"split backward level {l}")
+
+
+def test_mask_pool_14x14_tiny_rois_backward(oracle, cuda):
+    """14x14 bins on RoIs only a few feature pixels wide: feature rows are sampled
+    by up to 14 bin rows, more than a pull stage holds (8) -> those tiles go to
+    the inline kernel; 1 region (the Mask R-CNN extractor) and 3 regions."""
+    import arfe_b200 as A
+    feats = small_pyramid(oracle, batch=1, channels=16, img_h=192, img_w=320)
+    tiny = torch.tensor([[0, 20.0, 20.0, 26.0, 25.0], [0, 100.3, 50.2, 104.9, 53.7],
+                         [0, 200.0, 100.0, 212.0, 140.0], [0, 5.0, 5.0, 9.0, 60.0]])
+    rois = torch.cat([mixed_rois(oracle, 40, 320, 192, 1, seed=41), tiny])
+    for regions in (1, 3):
+        fo = [f.clone().requires_grad_(True) for f in feats]
+        if regions == 1:
+            ref = oracle.single_roi_extractor(fo, rois, list(STRIDES), out_size=14)
+        else:
+            ref = oracle.arrff_bbox_feats(fo, rois, list(STRIDES), out_size=14)
+        g = torch.randn(ref.shape, generator=torch.Generator().manual_seed(12))
+        ref.backward(g)
+        fg = [_cl(f.to(cuda)).requires_grad_(True) for f in feats]
+        got = A.roi_fuse(fg, rois.to(cuda), 14, _scales(), regions=regions, out_channels_last=True)
+        assert_close_fp32(got, ref, f"14x14 forward regions={regions}")
+        got.backward(_cl(g.to(cuda)))
+        for l in range(5):
+            r = fo[l].grad if fo[l].grad is not None else torch.zeros_like(feats[l])
+            d = (fg[l].grad.cpu() - r).abs().max()
+            assert float(d) <= 3e-5 * float(r.abs().max()) + 1e-5, (regions, l, float(d))
