@@ -147,6 +147,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // non-blocking
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 // (Polling with one lane per warp + __syncwarp instead of all 32 lanes was
 // measured 2x slower: the divergent wait costs more than the extra polls.)
 // global -> shared bulk copy (TMA, no tensor map): 16-byte aligned, bytes % 16 == 0
@@ -697,7 +710,7 @@ roi_prep_kernel(const RoiFuseParams p, const PullWs ws) {
 // left to the L1-cached kernel, launched over the plan's fwd_list.
 constexpr int kFwdSlots = 16;
 constexpr int kFwdTabs = 3;
-constexpr int kFwdCopy = 8192;  // bytes per bulk copy
+constexpr int kFwdCopy = 65536;  // bytes per bulk copy (a typical 22 KB window row is one copy)
 
 struct __align__(128) FwdTab {
   RegionHdr hdr;
@@ -889,38 +902,49 @@ roi_fuse_fwd_ring(const RoiFuseParams p, const PullWs ws, int ncons, int ring_by
           static_cast<const T*>(p.feats[h.lvl]) +
           (((size_t)h.batch * p.H[h.lvl] + h.ymin) * p.W[h.lvl] + h.xmin) * C);
       const size_t src_step = (size_t)p.W[h.lvl] * C * sizeof(T);
-      for (int rr = 0; rr < nrows; ++rr) {
-        const int slot = issued % kFwdSlots;
-        auto release_one = [&]() {
-          mbar_wait(empty + (released % kFwdSlots), (released / kFwdSlots) & 1);
-          ++released;
-          const uint32_t nxt = __shfl_sync(0xffffffffu, my_off, released % kFwdSlots);
-          tail = released < issued ? nxt : head;
-        };
-        while (released < issued - kFwdSlots + 1) release_one();
-        uint32_t off;
+      // Rows of one region are equally long, so the producer hands out ring space
+      // to as many rows as fit at once: lane j issues row rr + j (its barrier arm and
+      // its bulk copies).  When the producer has fallen behind, several rows are
+      // free and one pass of this loop catches up -- its ~60-instruction dependent
+      // path per pass, not bandwidth, was what the consumers waited for.
+      auto retire = [&]() {  // `released` was consumed: its space is free
+        ++released;
+        const uint32_t nxt = __shfl_sync(0xffffffffu, my_off, released % kFwdSlots);
+        tail = released < issued ? nxt : head;
+      };
+      for (int rr = 0; rr < nrows;) {
+        while (released < issued && mbar_test(empty + (released % kFwdSlots), (released / kFwdSlots) & 1)) retire();
+        int m = 0;
         while (true) {
-          if (released == issued) { head = tail = 0; off = 0; break; }   // ring empty
-          if (head >= tail) {
-            if (head + bytes <= (uint32_t)ring_bytes) { off = head; break; }
-            if (bytes < tail) { off = 0; break; }                          // wrap
-          } else if (head + bytes < tail) { off = head; break; }
-          release_one();
+          if (released == issued) head = tail = 0;                                   // ring empty
+          uint32_t room = head >= tail ? (uint32_t)ring_bytes - head : tail - head - 1u;
+          if (head >= tail && room < bytes && bytes < tail) { head = 0; room = tail - 1u; }  // wrap
+          m = min(min((int)(room / bytes), nrows - rr), kFwdSlots - (issued - released));
+          if (m > 0) break;
+          mbar_wait(empty + (released % kFwdSlots), (released / kFwdSlots) & 1);     // wait for the oldest row
+          retire();
         }
-        head = off + bytes;
-        if (lane == slot) my_off = off;
-        if (p.debug_skip & 2) {  // profiling aid: no copies
-          if (lane == 0) { stage_off[slot] = off; mbar_arrive(full + slot); }
-        } else {
-          if (lane == 0) {
-            stage_off[slot] = off;
+        {  // lane s < kFwdSlots keeps the ring offset of the stage in slot s
+          const int j = (lane - issued % kFwdSlots + kFwdSlots) % kFwdSlots;
+          if (lane < kFwdSlots && j < m) my_off = head + (uint32_t)j * bytes;
+        }
+        if (lane < m) {
+          const int slot = (issued + lane) % kFwdSlots;
+          const uint32_t off = head + (uint32_t)lane * bytes;
+          const unsigned char* __restrict__ rsrc = src + (size_t)(rr + lane) * src_step;
+          stage_off[slot] = off;
+          if (p.debug_skip & 2) {  // profiling aid: no copies
+            mbar_arrive(full + slot);
+          } else {
             mbar_arrive_expect_tx(full + slot, bytes);
+            for (uint32_t o = 0; o < bytes; o += kFwdCopy)
+              bulk_g2s(ring + off + o, rsrc + o, min((uint32_t)kFwdCopy, bytes - o), full + slot);
           }
-          for (uint32_t o = (uint32_t)lane * kFwdCopy; o < bytes; o += 32u * kFwdCopy)
-            bulk_g2s(ring + off + o, src + o, min((uint32_t)kFwdCopy, bytes - o), full + slot);
         }
-        src += src_step;
-        ++issued;
+        __syncwarp();
+        head += (uint32_t)m * bytes;
+        issued += m;
+        rr += m;
       }
     }
     return;
