@@ -36,10 +36,14 @@ _SIGNATURES = {
     "arfe_roi_plan_bytes": ([c_int, c_int, c_int, c_int, _ip, _ip], ctypes.c_size_t),
     "arfe_roi_fuse_forward_plan": ([_pp, _ip, _ip, _fp, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                     c_float, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
-                                    c_void_p, c_void_p, ctypes.c_size_t, c_void_p], c_int),
+                                    c_void_p, c_void_p, ctypes.c_size_t, c_int, c_void_p], c_int),
+    "arfe_roi_plan_build": ([_ip, _ip, _fp, c_int, c_int, c_int, c_void_p, c_int, c_int, c_float, c_int,
+                             c_int, c_int, c_float, c_int, c_void_p, ctypes.c_size_t, c_void_p], c_int),
+    "arfe_roi_pull_bin": ([_ip, _ip, _fp, c_int, c_int, c_int, c_void_p, c_int, c_int, c_float, c_int,
+                           c_int, c_int, c_float, c_int, c_int, c_void_p, ctypes.c_size_t, c_void_p], c_int),
     "arfe_roi_fuse_forward_plan_split": ([_pp, _ip, _ip, _fp, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                           c_float, c_int, c_int, c_int, c_float, c_int, _pp,
-                                          c_void_p, ctypes.c_size_t, c_void_p], c_int),
+                                          c_void_p, ctypes.c_size_t, c_int, c_void_p], c_int),
     "arfe_roi_fuse_backward_pull_split": ([_pp, _ip, _ip, _fp, c_int, c_int, c_int, c_void_p,
                                            c_int, c_int, c_float, c_int, c_int, c_int, c_float, c_int,
                                            _pp, c_void_p, ctypes.c_size_t, c_int, c_void_p], c_int),

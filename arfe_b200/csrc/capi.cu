@@ -138,13 +138,20 @@ static int forward_plan_impl(const char* fn, const void* const* feats, const int
                              int K, int regions, float facs, int PH, int PW, int sampling_ratio,
                              float finest_scale, int dtype, void* out, void* const* out_regions,
                              int32_t* lvl_out, float* boxes_out, void* workspace,
-                             size_t workspace_bytes, void* stream) {
+                             size_t workspace_bytes, int stages, void* stream) {
   arfe::RoiFuseParams p;
   int rc = fill_roi_params(fn, p, H, W, spatial_scale, L, B, C, rois, K, regions, facs, PH, PW,
                            sampling_ratio, finest_scale, dtype, ARFE_NHWC);
   if (rc) return rc;
   if (K == 0) return ARFE_OK;
-  REQUIRE(feats && (out || out_regions) && workspace, ARFE_E_NULL, "%s: feats/out/workspace is NULL", fn);
+  REQUIRE(workspace, ARFE_E_NULL, "%s: workspace is NULL", fn);
+  if (stages == 1) {  // plan only: no tensors involved
+    REQUIRE(B >= 1 && aligned(rois, 4) && aligned(workspace, 256), ARFE_E_ALIGN, "%s: rois / workspace misaligned", fn);
+    REQUIRE(workspace_bytes >= arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W), ARFE_E_SHAPE,
+            "%s: workspace too small", fn);
+    return cuda_result(arfe::launch_roi_fuse_forward_plan(p, dtype, workspace, workspace_bytes, 1, (cudaStream_t)stream), fn);
+  }
+  REQUIRE(feats && (out || out_regions), ARFE_E_NULL, "%s: feats/out is NULL", fn);
   REQUIRE(B >= 1, ARFE_E_SHAPE, "%s: B=0 with K>0", fn);
   REQUIRE(C % (dtype == ARFE_F32 ? 4 : 8) == 0, ARFE_E_UNSUPPORTED, "%s: C must be a multiple of %d",
           fn, dtype == ARFE_F32 ? 4 : 8);
@@ -168,7 +175,16 @@ static int forward_plan_impl(const char* fn, const void* const* feats, const int
     const char* ev = getenv("ARFE_FWD_SKIP");  // profiling aid, default off
     p.debug_skip = ev ? atoi(ev) : 0;
   }
-  return cuda_result(arfe::launch_roi_fuse_forward_plan(p, dtype, workspace, workspace_bytes, (cudaStream_t)stream), fn);
+  return cuda_result(arfe::launch_roi_fuse_forward_plan(p, dtype, workspace, workspace_bytes, stages, (cudaStream_t)stream), fn);
+}
+
+int arfe_roi_plan_build(const int32_t* H, const int32_t* W, const float* spatial_scale, int L, int B, int C,
+                        const float* rois, int K, int regions, float facs, int PH, int PW,
+                        int sampling_ratio, float finest_scale, int dtype, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  return forward_plan_impl("arfe_roi_plan_build", nullptr, H, W, spatial_scale, L, B, C, rois, K, regions,
+                           facs, PH, PW, sampling_ratio, finest_scale, dtype, nullptr, nullptr, nullptr,
+                           nullptr, workspace, workspace_bytes, 1, stream);
 }
 
 int arfe_roi_fuse_forward_plan(const void* const* feats, const int32_t* H, const int32_t* W,
@@ -176,10 +192,10 @@ int arfe_roi_fuse_forward_plan(const void* const* feats, const int32_t* H, const
                                int K, int regions, float facs, int PH, int PW, int sampling_ratio,
                                float finest_scale, int dtype, void* out, int32_t* lvl_out,
                                float* boxes_out, void* workspace, size_t workspace_bytes,
-                               void* stream) {
+                               int plan_ready, void* stream) {
   return forward_plan_impl("arfe_roi_fuse_forward_plan", feats, H, W, spatial_scale, L, B, C, rois, K,
                            regions, facs, PH, PW, sampling_ratio, finest_scale, dtype, out, nullptr,
-                           lvl_out, boxes_out, workspace, workspace_bytes, stream);
+                           lvl_out, boxes_out, workspace, workspace_bytes, plan_ready ? 2 : 3, stream);
 }
 
 int arfe_roi_fuse_forward_plan_split(const void* const* feats, const int32_t* H, const int32_t* W,
@@ -187,11 +203,11 @@ int arfe_roi_fuse_forward_plan_split(const void* const* feats, const int32_t* H,
                                      const float* rois, int K, int regions, float facs, int PH,
                                      int PW, int sampling_ratio, float finest_scale, int dtype,
                                      void* const* out_regions, void* workspace,
-                                     size_t workspace_bytes, void* stream) {
+                                     size_t workspace_bytes, int plan_ready, void* stream) {
   if (!out_regions) return fail(ARFE_E_NULL, "arfe_roi_fuse_forward_plan_split: out_regions is NULL");
   return forward_plan_impl("arfe_roi_fuse_forward_plan_split", feats, H, W, spatial_scale, L, B, C, rois,
                            K, regions, facs, PH, PW, sampling_ratio, finest_scale, dtype, nullptr,
-                           out_regions, nullptr, nullptr, workspace, workspace_bytes, stream);
+                           out_regions, nullptr, nullptr, workspace, workspace_bytes, plan_ready ? 2 : 3, stream);
 }
 
 int arfe_roi_fuse_backward(const void* dout, int dout_layout, const int32_t* H, const int32_t* W,
@@ -229,21 +245,26 @@ size_t arfe_roi_fuse_pull_workspace_bytes(int K, int regions, int L, int B, cons
   return arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W);
 }
 
+constexpr int kBinOnly = -77, kBinOnlySplit = -78;  // internal: arfe_roi_pull_bin (concatenated / split dout)
+
 static int backward_pull_impl(const char* fn, const void* dout, const void* const* dout_regions,
                               const int32_t* H, const int32_t* W,
                                 const float* spatial_scale, int L, int B, int C, const float* rois,
                                 int K, int regions, float facs, int PH, int PW, int sampling_ratio,
                                 float finest_scale, int dtype, float* const* dfeats,
                                 void* workspace, size_t workspace_bytes, int plan_ready, void* stream) {
+  const bool bin_split = plan_ready == kBinOnlySplit;
+  if (bin_split) plan_ready = kBinOnly;
   arfe::RoiFuseParams p;
   int rc = fill_roi_params(fn, p, H, W, spatial_scale, L, B, C, rois, K, regions, facs, PH, PW,
                            sampling_ratio, finest_scale, dtype, ARFE_NHWC);
   if (rc) return rc;
-  REQUIRE(dfeats, ARFE_E_NULL, "%s: dfeats is NULL", fn);
+  REQUIRE(dfeats || plan_ready == kBinOnly, ARFE_E_NULL, "%s: dfeats is NULL", fn);
   REQUIRE(B >= 1, ARFE_E_SHAPE, "%s: B=0", fn);
   REQUIRE(C % (dtype == ARFE_F32 ? 4 : 8) == 0, ARFE_E_UNSUPPORTED, "%s: C must be a multiple of %d",
           fn, dtype == ARFE_F32 ? 4 : 8);
-  for (int l = 0; l < L; ++l) {
+  if (plan_ready == kBinOnly && K == 0) return ARFE_OK;
+  for (int l = 0; l < L && dfeats; ++l) {
     REQUIRE(dfeats[l], ARFE_E_NULL, "%s: dfeats[%d] is NULL", fn, l);
     REQUIRE(aligned(dfeats[l], 16), ARFE_E_ALIGN, "%s: dfeats[%d] must be 16-byte aligned", fn, l);
     p.dfeats[l] = dfeats[l];
@@ -255,6 +276,15 @@ static int backward_pull_impl(const char* fn, const void* dout, const void* cons
     }
     return ARFE_OK;
   }
+  const int stages = plan_ready == kBinOnly ? 2 : (plan_ready == 0 ? 7 : (plan_ready == 1 ? 6 : 4));
+  if (stages == 2) {  // bin only: no tensors involved, but the stage offsets follow dout's layout
+    if (bin_split) p.bin_stride = C;
+    REQUIRE(workspace && aligned(workspace, 256), ARFE_E_ALIGN, "%s: workspace NULL or misaligned", fn);
+    REQUIRE(workspace_bytes >= arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W), ARFE_E_SHAPE,
+            "%s: workspace too small", fn);
+    return cuda_result(arfe::launch_roi_fuse_backward_pull(p, dtype, workspace, workspace_bytes, 2, (cudaStream_t)stream), fn);
+  }
+  REQUIRE(plan_ready >= 0 && plan_ready <= 2, ARFE_E_ENUM, "%s: plan_ready must be 0, 1 or 2", fn);
   if (dout_regions) {
     rc = set_split_regions(fn, p, dout_regions, regions, C, dtype, &dout);
     if (rc) return rc;
@@ -268,7 +298,7 @@ static int backward_pull_impl(const char* fn, const void* dout, const void* cons
     const char* ev = getenv("ARFE_BWD_SKIP");  // profiling aid, default off
     p.debug_skip = ev ? atoi(ev) : 0;
   }
-  rc = cuda_result(arfe::launch_roi_fuse_backward_pull(p, dtype, workspace, workspace_bytes, plan_ready, (cudaStream_t)stream), fn);
+  rc = cuda_result(arfe::launch_roi_fuse_backward_pull(p, dtype, workspace, workspace_bytes, stages, (cudaStream_t)stream), fn);
   if (rc) return rc;
   // regions whose tap tables did not fit the workspace records: atomic kernel, adds on top
   p.debug_skip = 0;
@@ -285,6 +315,15 @@ int arfe_roi_fuse_backward_pull(const void* dout, const int32_t* H, const int32_
   return backward_pull_impl("arfe_roi_fuse_backward_pull", dout, nullptr, H, W, spatial_scale, L, B, C,
                             rois, K, regions, facs, PH, PW, sampling_ratio, finest_scale, dtype, dfeats,
                             workspace, workspace_bytes, plan_ready, stream);
+}
+
+int arfe_roi_pull_bin(const int32_t* H, const int32_t* W, const float* spatial_scale, int L, int B, int C,
+                      const float* rois, int K, int regions, float facs, int PH, int PW,
+                      int sampling_ratio, float finest_scale, int dtype, int split_regions,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  return backward_pull_impl("arfe_roi_pull_bin", nullptr, nullptr, H, W, spatial_scale, L, B, C, rois, K,
+                            regions, facs, PH, PW, sampling_ratio, finest_scale, dtype, nullptr, workspace,
+                            workspace_bytes, split_regions ? kBinOnlySplit : kBinOnly, stream);
 }
 
 int arfe_roi_fuse_backward_pull_split(const void* const* dout_regions, const int32_t* H, const int32_t* W,

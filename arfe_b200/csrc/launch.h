@@ -39,9 +39,9 @@ cudaError_t launch_roi_fuse_forward_cl(const RoiFuseParams& p, int dtype, int ou
                                        cudaStream_t stream);
 size_t roi_pull_workspace_bytes(int K, int R, int L, int B, const int* H, const int* W);
 cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, void* workspace,
-                                          size_t workspace_bytes, int plan_ready, cudaStream_t stream);
+                                          size_t workspace_bytes, int stages, cudaStream_t stream);
 cudaError_t launch_roi_fuse_forward_plan(const RoiFuseParams& p, int dtype, void* workspace,
-                                         size_t workspace_bytes, cudaStream_t stream);
+                                         size_t workspace_bytes, int stages, cudaStream_t stream);
 const int* roi_pull_flag_list(int K, int R, int L, int B, const int* H, const int* W, void* workspace,
                               const int** count);
 cudaError_t launch_roi_fuse_taps(const RoiFuseParams& p, int max_grid, int32_t* lvl,

@@ -1758,8 +1758,9 @@ static cudaError_t launch_prep(const RoiFuseParams& p, const PullWs& ws, cudaStr
 // workspace (the backward can reuse them: plan_ready), the ring kernel consumes
 // them, the L1-cached kernel serves the regions the ring kernel left out.
 // Channels-last features and output.
+// stages: 1 = build the plan (roi_prep_kernel), 2 = run the forward on it.
 cudaError_t launch_roi_fuse_forward_plan(const RoiFuseParams& p0, int dtype, void* workspace,
-                                         size_t workspace_bytes, cudaStream_t stream) {
+                                         size_t workspace_bytes, int stages, cudaStream_t stream) {
   RoiFuseParams p = p0;
   const int N = p.K * p.R;
   PullWs ws;
@@ -1777,8 +1778,9 @@ cudaError_t launch_roi_fuse_forward_plan(const RoiFuseParams& p0, int dtype, voi
   const int fixed = kFwdTabs * (int)sizeof(FwdTab) + 512;
   const int ring = (per_sm == 2 ? 108 * 1024 : 200 * 1024) - fixed;
   ws.fwd_wlen_cap = ring_ok ? ring / (p.C * elt) : 0;  // a window row must fit the ring
-  cudaError_t e = launch_prep(p, ws, stream);
-  if (e != cudaSuccess) return e;
+  cudaError_t e = cudaSuccess;
+  if ((stages & 1) && (e = launch_prep(p, ws, stream)) != cudaSuccess) return e;
+  if (!(stages & 2)) return cudaSuccess;
   if (!ring_ok) return launch_roi_fuse_forward_cl(p, dtype, 1, stream);
   static const int sms = [] {
     int dev = 0, n = 148;
@@ -1818,8 +1820,9 @@ size_t roi_pull_workspace_bytes(int K, int R, int L, int B, const int* H, const 
 // dout: channels-last [K][PH*PW][R*C]; dfeats: NHWC fp32, fully written.
 // Regions whose tables did not fit are flagged in the workspace and added
 // afterwards by the atomic kernel.
+// stages: 1 = build the plan, 2 = bin the tiles (stage descriptors), 4 = pull.
 cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, void* workspace,
-                                          size_t workspace_bytes, int plan_ready, cudaStream_t stream) {
+                                          size_t workspace_bytes, int stages, cudaStream_t stream) {
   const int N = p.K * p.R;
   PullWs ws;
   const size_t need = pull_ws_layout(N, p.L, p.B, p.H, p.W, static_cast<unsigned char*>(workspace), &ws);
@@ -1827,8 +1830,8 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
   if (ws.nblk > kMaxPrepBlocks) return cudaErrorInvalidValue;
   if ((long long)p.K * p.PH * p.PW * p.R * p.C > 0x7fffffffLL) return cudaErrorInvalidValue;  // 32-bit dout offsets
   cudaError_t e;
-  if ((e = cudaMemsetAsync(ws.counters, 0, 12, stream)) != cudaSuccess) return e;
-  if (!plan_ready && (e = launch_prep(p, ws, stream)) != cudaSuccess) return e;
+  if ((stages & 1) && (e = launch_prep(p, ws, stream)) != cudaSuccess) return e;
+  if ((stages & 2) && (e = cudaMemsetAsync(ws.counters, 0, 12, stream)) != cudaSuccess) return e;
   // Two tile shapes: the small upper-level maps carry ~40x more region-pixels per
   // tile than level 0, so they get narrow tiles and go first (heaviest level
   // first inside each launch); the big maps follow with wide tiles.
@@ -1862,8 +1865,11 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
     ntiles[pass] = total;
   }
   if (ntiles[0] + ntiles[1] == 0) return cudaSuccess;
-  roi_bin_kernel<<<ntiles[0] + ntiles[1], kBinThreads, 0, stream>>>(p, ws, tm[0], tm[1], ntiles[0]);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (stages & 2) {
+    roi_bin_kernel<<<ntiles[0] + ntiles[1], kBinThreads, 0, stream>>>(p, ws, tm[0], tm[1], ntiles[0]);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  if (!(stages & 4)) return cudaSuccess;
   const int per_sm = (dtype == 0 && nv == 1) ? 3 : 2;
   const int ring = (per_sm == 3 ? 64 : 96) * 1024;
   const int smem = kPullCtl + kNSlot * kDescBytes + ring;

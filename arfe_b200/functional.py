@@ -73,7 +73,7 @@ class _RoIFuseFunction(Function):
                 L.ptr_array(feats), L.int_array(Hs), L.int_array(Ws),
                 L.float_array(spatial_scales), len(feats), B, C, rois.data_ptr(),
                 K, regions, float(facs), oh, ow, int(sample_num), float(finest_scale), dt,
-                out.data_ptr(), None, None, ws_ptr, nbytes, L.stream_ptr(out.device))
+                out.data_ptr(), None, None, ws_ptr, nbytes, 0, L.stream_ptr(out.device))
             L.check(rc, "arfe_roi_fuse_forward_plan")
             if any(f.requires_grad for f in feats):
                 ctx.plan = (ws, ws_ptr, nbytes)
@@ -182,7 +182,7 @@ class _RoIFuseSplitFunction(Function):
             rc = lib.arfe_roi_fuse_forward_plan_split(
                 L.ptr_array(feats), L.int_array(Hs), L.int_array(Ws), L.float_array(spatial_scales),
                 len(feats), B, C, rois.data_ptr(), K, regions, float(facs), oh, ow, int(sample_num),
-                float(finest_scale), dt, L.ptr_array(outs), ws_ptr, nbytes, L.stream_ptr(dev))
+                float(finest_scale), dt, L.ptr_array(outs), ws_ptr, nbytes, 0, L.stream_ptr(dev))
             L.check(rc, "arfe_roi_fuse_forward_plan_split")
             if any(f.requires_grad for f in feats):
                 ctx.plan = (ws, ws_ptr, nbytes)

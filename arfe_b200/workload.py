@@ -105,6 +105,7 @@ class TrainStep:
         x = host["x"]
         self.cl = bool(channels_last)
         self.split = self.cl if split is None else (bool(split) and self.cl)
+        self.overlap_plan = self.cl  # step(): plan + tile bins on a second stream (plan_async)
         self.layout = L.ARFE_NHWC if self.cl else L.ARFE_NCHW
         mf = torch.channels_last if self.cl else torch.contiguous_format
         self.dtype = x[0].dtype
@@ -189,20 +190,42 @@ class TrainStep:
             self.p_x, self.bsf.data_ptr(), self.p_g1, self.p_g2, self.H, self.W, self.nlev,
             self.B, self.C, hr, wr, self.dt, self.layout, self.p_y, self.stream)
 
+    def plan_async(self):
+        """The RoI plan depends only on the RoIs, the backward's tile bins only on
+        the plan: build both on a second stream, under the AR-FPN kernels of the
+        forward (latency-bound table walking next to bandwidth-bound streaming)."""
+        if getattr(self, "side", None) is None:
+            self.side = torch.cuda.Stream(self.dev)
+            self.ev_free, self.ev_plan, self.ev_bin = (torch.cuda.Event() for _ in range(3))
+            self.ev_free.record(torch.cuda.current_stream(self.dev))
+        self.side.wait_event(self.ev_free)  # the previous step's backward still reads the workspace
+        geo = (self.H, self.W, self.scales, self.nlev, self.B, self.C, self.rois.data_ptr(), self.K,
+               self.R, 1.0, self.P, self.P, 0, 56.0, self.dt)
+        tail = (self.ws_ptr, self.ws_bytes, self.side.cuda_stream)
+        L.check(self.lib.arfe_roi_plan_build(*geo, *tail), "arfe_roi_plan_build")
+        self.ev_plan.record(self.side)
+        L.check(self.lib.arfe_roi_pull_bin(*geo, int(self.split), *tail), "arfe_roi_pull_bin")
+        self.ev_bin.record(self.side)
+        self.async_plan, self.async_bins = 1, 1
+
     def roi_fuse_fwd(self):
+        ready = 0
+        if self.cl and getattr(self, "async_plan", 0):
+            torch.cuda.current_stream(self.dev).wait_event(self.ev_plan)
+            ready, self.async_plan = 1, 0
         if self.split:
             self.planned = 1
             return self.lib.arfe_roi_fuse_forward_plan_split(
                 self.p_y, self.H, self.W, self.scales, self.nlev, self.B, self.C,
                 self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt,
-                self.p_Fr, self.ws_ptr, self.ws_bytes, self.stream)
+                self.p_Fr, self.ws_ptr, self.ws_bytes, ready, self.stream)
         if self.cl:
             # channels-last: plan + ring kernel; the plan stays in the workspace for the backward
             self.planned = 1
             return self.lib.arfe_roi_fuse_forward_plan(
                 self.p_y, self.H, self.W, self.scales, self.nlev, self.B, self.C,
                 self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt,
-                self.F.data_ptr(), None, None, self.ws_ptr, self.ws_bytes, self.stream)
+                self.F.data_ptr(), None, None, self.ws_ptr, self.ws_bytes, ready, self.stream)
         return self.lib.arfe_roi_fuse_forward(
             self.p_y, self.H, self.W, self.scales, self.nlev, self.B, self.C,
             self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt, self.layout,
@@ -220,16 +243,24 @@ class TrainStep:
             self.gate_rows, self.gate_n, self.dt, self.stream)
 
     def roi_fuse_bwd(self):
+        ready = getattr(self, "planned", 0)
+        if self.cl and getattr(self, "async_bins", 0):
+            torch.cuda.current_stream(self.dev).wait_event(self.ev_bin)
+            ready, self.async_bins = 2, 0
         if self.split:
-            return self.lib.arfe_roi_fuse_backward_pull_split(
+            rc = self.lib.arfe_roi_fuse_backward_pull_split(
                 self.p_dFr, self.H, self.W, self.scales, self.nlev, self.B, self.C,
                 self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt,
-                self.p_dy, self.ws_ptr, self.ws_bytes, getattr(self, "planned", 0), self.stream)
-        if self.cl:
-            return self.lib.arfe_roi_fuse_backward_pull(
+                self.p_dy, self.ws_ptr, self.ws_bytes, ready, self.stream)
+        elif self.cl:
+            rc = self.lib.arfe_roi_fuse_backward_pull(
                 self.dF.data_ptr(), self.H, self.W, self.scales, self.nlev, self.B, self.C,
                 self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt,
-                self.p_dy, self.ws_ptr, self.ws_bytes, getattr(self, "planned", 0), self.stream)
+                self.p_dy, self.ws_ptr, self.ws_bytes, ready, self.stream)
+        if self.cl:
+            if getattr(self, "side", None) is not None:
+                self.ev_free.record(torch.cuda.current_stream(self.dev))
+            return rc
         return self.lib.arfe_roi_fuse_backward(
             self.dF.data_ptr(), L.ARFE_NCHW, self.H, self.W, self.scales, self.nlev, self.B,
             self.C, self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt,
@@ -269,6 +300,8 @@ class TrainStep:
     def step(self, timer=None):
         """One training step. `timer(name, fn)` wraps each of our launches."""
         run = timer or (lambda name, fn: L.check(fn(), name))
+        if self.cl and self.overlap_plan:
+            self.plan_async()
         run("fpn_gather_fwd", self.fpn_gather_fwd)
         run("fpn_apply_fwd", self.fpn_apply_fwd)
         run("roi_fuse_fwd", self.roi_fuse_fwd)
@@ -284,7 +317,8 @@ class TrainStep:
         """Kernels of libarfe_b200.so per step: gather 1, apply 1, roi fwd (plan +
         ring + left-out regions = 3 | 1), gate 2, roi bwd (bin + pull + inline tiles +
         flagged-region fallback = 4, the plan is the forward's | atomic 1),
-        apply bwd 2, gather bwd 2 (vector kernel + small levels) | 1."""
+        apply bwd 2, gather bwd 2 (vector kernel + small levels) | 1.  (Channels-last:
+        plan and bin run on the second stream of plan_async; same count.)"""
         return (1 + 1 + 3 + 2 + 4 + 2 + 1) if self.cl else (1 + 1 + 1 + 2 + 1 + 2 + 2)
 
     # -- algorithmic bytes per launch (DESIGN.md section 5) ------------------

@@ -282,6 +282,9 @@ def run_ours(args, rank, local_rank, world):
                        "memory_format": "torch.channels_last (fast path)" if cl else "NCHW (reference layout, compatibility kernels)",
                        "roi_tensors": ("regions as separate tensors (ori | lw | lh), read/written in place: no cat / slice copies in the step"
                                        if step.split else "concatenated [K, 3C, 7, 7]; torch slice copies between the kernels are inside the step"),
+                       "streams": ("RoI plan and tile binning (2 kernels, ~40 us) run on a second stream under the AR-FPN forward kernels; "
+                                   "the per-op times of roi_fuse_fwd / roi_fuse_bwd exclude them, the step time includes them"
+                                   if getattr(step, "overlap_plan", False) else "one stream"),
                        "l2": "inputs+outputs per step (~1.5 GB) exceed the 126 MB L2; no explicit flush",
                        "timing": "CUDA events on the launch stream, max over ranks"},
             "clocks": clocks,

@@ -108,9 +108,29 @@ int arfe_roi_fuse_backward(const void* dout, int dout_layout, const int32_t* H,
  * that reads it).  The forward writes the per-region tables (boxes, levels,
  * sampling windows, aggregated bilinear weights) into it and consumes them; a
  * backward for the SAME rois / shapes / pool size may reuse them
- * (plan_ready = 1) instead of rebuilding them (plan_ready = 0).
+ * (plan_ready = 1) instead of rebuilding them (plan_ready = 0); plan_ready = 2:
+ * the backward's tile bins are ready too (arfe_roi_pull_bin).
  * arfe_roi_fuse_pull_workspace_bytes is the same number (older name). */
 size_t arfe_roi_plan_bytes(int K, int regions, int L, int B, const int32_t* H, const int32_t* W);
+
+/* The plan depends only on the RoIs and the shapes, the tile binning of the
+ * backward only on the plan: both may be issued early, on another stream, to
+ * overlap unrelated work (the neck's kernels, the head's backward).
+ *   arfe_roi_plan_build : writes the plan; afterwards the forward may be called with
+ *                         plan_ready = 1 and the backward with plan_ready = 1.
+ *   arfe_roi_pull_bin   : needs the plan; afterwards arfe_roi_fuse_backward_pull(_split)
+ *                         may be called with plan_ready = 2 (plan and bins ready).
+ * `dtype` must be the dtype of the tensors the plan will be used with (it bounds
+ * the window width the forward's ring takes).  The caller orders the streams. */
+int arfe_roi_plan_build(const int32_t* H, const int32_t* W, const float* spatial_scale, int L,
+                        int B, int C, const float* rois, int K, int regions, float facs,
+                        int PH, int PW, int sampling_ratio, float finest_scale, int dtype,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int arfe_roi_pull_bin(const int32_t* H, const int32_t* W, const float* spatial_scale, int L,
+                      int B, int C, const float* rois, int K, int regions, float facs,
+                      int PH, int PW, int sampling_ratio, float finest_scale, int dtype,
+                      int split_regions /* the backward will be the _split entry point */,
+                      void* workspace, size_t workspace_bytes, void* stream);
 size_t arfe_roi_fuse_pull_workspace_bytes(int K, int regions, int L, int B,
                                           const int32_t* H, const int32_t* W);
 
@@ -124,7 +144,8 @@ int arfe_roi_fuse_forward_plan(const void* const* feats, const int32_t* H, const
                                const float* rois, int K, int regions, float facs,
                                int PH, int PW, int sampling_ratio, float finest_scale,
                                int dtype, void* out, int32_t* lvl_out, float* boxes_out,
-                               void* workspace, size_t workspace_bytes, void* stream);
+                               void* workspace, size_t workspace_bytes, int plan_ready,
+                               void* stream);
 
 /* Split layout: the regions as separate tensors [K][PH][PW][C] (channels-last of
  * [K, C, PH, PW]) instead of one concatenated [K][PH][PW][regions*C] -- what the
@@ -137,7 +158,7 @@ int arfe_roi_fuse_forward_plan_split(const void* const* feats, const int32_t* H,
                                      const float* rois, int K, int regions, float facs,
                                      int PH, int PW, int sampling_ratio, float finest_scale,
                                      int dtype, void* const* out_regions, void* workspace,
-                                     size_t workspace_bytes, void* stream);
+                                     size_t workspace_bytes, int plan_ready, void* stream);
 int arfe_roi_fuse_backward_pull_split(const void* const* dout_regions, const int32_t* H,
                                       const int32_t* W, const float* spatial_scale, int L, int B,
                                       int C, const float* rois, int K, int regions, float facs,

@@ -64,7 +64,7 @@ def test_argument_errors_need_no_gpu():
         lib.arfe_roi_fuse_pull_workspace_bytes(1024, 3, 5, 2, H5, W5)
     # the planned forward validates its arguments before touching the device
     rc = lib.arfe_roi_fuse_forward_plan(None, H, W, s, 1, 1, 4, rois.data_ptr(), 1, 3, 1.0, 7, 7,
-                                        0, 56.0, 0, None, None, None, None, 0, None)
+                                        0, 56.0, 0, None, None, None, None, 0, 0, None)
     assert rc == -1
     # aligned=False is the legacy path
     rc = lib.arfe_roi_align_forward(None, None, 0.25, 7, 7, 0, 0, 1, 4, 8, 8, 0, 0, 0, None, None)

@@ -328,12 +328,20 @@ def _plan_calls(cuda, feats_cl, rois, regions=3, P=7):
                                           out.data_ptr(), None, None, stream), "fwd")
         return out
 
-    def fwd_plan(ws):
+    def fwd_plan(ws, ready=0):
         out = torch.empty((K, regions * C, P, P), device=cuda, memory_format=torch.channels_last)
         L.check(lib.arfe_roi_fuse_forward_plan(L.ptr_array(feats_cl), H, W, S, nlev, B, C, rois.data_ptr(), K,
                                                regions, 1.0, P, P, 0, 56.0, L.ARFE_F32, out.data_ptr(), None,
-                                               None, ws[1], ws[2], stream), "fwd_plan")
+                                               None, ws[1], ws[2], ready, stream), "fwd_plan")
         return out
+
+    def staged(ws, what):
+        geo = (H, W, S, nlev, B, C, rois.data_ptr(), K, regions, 1.0, P, P, 0, 56.0, L.ARFE_F32)
+        if what == "plan":
+            L.check(lib.arfe_roi_plan_build(*geo, ws[1], ws[2], stream), "plan_build")
+        else:
+            L.check(lib.arfe_roi_pull_bin(*geo, 0, ws[1], ws[2], stream), "pull_bin")
+    fwd_plan.staged = staged
 
     def bwd(g_cl, ws, ready):
         d = [torch.empty((B, C, Hs[l], Ws[l]), device=cuda, memory_format=torch.channels_last)
@@ -365,9 +373,19 @@ def test_plan_forward_and_plan_reuse(oracle, cuda):
     ws2 = new_ws()
     d_fresh = bwd(g, ws2, 0)
     torch.cuda.synchronize()
-    for x, y, z in zip(d_reuse, d_fresh, d_again):
+    # staged entry points: plan built ahead, forward with plan_ready = 1, tiles binned
+    # ahead, backward with plan_ready = 2
+    ws3 = new_ws()
+    fwd_plan.staged(ws3, "plan")
+    c = fwd_plan(ws3, ready=1)
+    fwd_plan.staged(ws3, "bin")
+    d_staged = bwd(g, ws3, 2)
+    torch.cuda.synchronize()
+    assert torch.equal(b, c), "forward on a pre-built plan differs"
+    for x, y, z, s in zip(d_reuse, d_fresh, d_again, d_staged):
         assert torch.equal(x, y), "plan reuse changes the gradient"
         assert torch.equal(x, z), "backward is not reproducible"
+        assert torch.equal(x, s), "backward on pre-built bins differs"
 
 
 def test_ring_forward_wide_windows_and_many_taps(oracle, cuda):
