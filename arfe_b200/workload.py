@@ -258,8 +258,6 @@ class TrainStep:
                 self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt,
                 self.p_dy, self.ws_ptr, self.ws_bytes, ready, self.stream)
         if self.cl:
-            if getattr(self, "side", None) is not None:
-                self.ev_free.record(torch.cuda.current_stream(self.dev))
             return rc
         return self.lib.arfe_roi_fuse_backward(
             self.dF.data_ptr(), L.ARFE_NCHW, self.H, self.W, self.scales, self.nlev, self.B,
@@ -312,6 +310,10 @@ class TrainStep:
         self.glue_before_apply_bwd()
         run("fpn_apply_bwd", self.fpn_apply_bwd)
         run("fpn_gather_bwd", self.fpn_gather_bwd)
+        if getattr(self, "side", None) is not None:
+            # the next step's plan may be rebuilt (second stream) once this step is over, i.e.
+            # under the next step's AR-FPN forward kernels, not under this step's tail
+            self.ev_free.record(torch.cuda.current_stream(self.dev))
 
     def launches_per_step(self):
         """Kernels of libarfe_b200.so per step: gather 1, apply 1, roi fwd (plan +
