@@ -1832,6 +1832,9 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
   cudaError_t e;
   if ((stages & 1) && (e = launch_prep(p, ws, stream)) != cudaSuccess) return e;
   if ((stages & 2) && (e = cudaMemsetAsync(ws.counters, 0, 12, stream)) != cudaSuccess) return e;
+  // bins built earlier (arfe_roi_pull_bin): only the pull kernel's work counter is reset, so the
+  // same bins serve any number of backward calls
+  if (stages == 4 && (e = cudaMemsetAsync(ws.counters + 2, 0, 4, stream)) != cudaSuccess) return e;
   // Two tile shapes: the small upper-level maps carry ~40x more region-pixels per
   // tile than level 0, so they get narrow tiles and go first (heaviest level
   // first inside each launch); the big maps follow with wide tiles.

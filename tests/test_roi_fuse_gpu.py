@@ -380,7 +380,10 @@ def test_plan_forward_and_plan_reuse(oracle, cuda):
     c = fwd_plan(ws3, ready=1)
     fwd_plan.staged(ws3, "bin")
     d_staged = bwd(g, ws3, 2)
+    d_staged2 = bwd(g, ws3, 2)   # the bins are not consumed
     torch.cuda.synchronize()
+    for x, y in zip(d_staged, d_staged2):
+        assert torch.equal(x, y), "second backward on the same bins differs"
     assert torch.equal(b, c), "forward on a pre-built plan differs"
     for x, y, z, s in zip(d_reuse, d_fresh, d_again, d_staged):
         assert torch.equal(x, y), "plan reuse changes the gradient"
