@@ -496,3 +496,30 @@ def test_mask_pool_14x14_tiny_rois_backward(oracle, cuda):
             r = fo[l].grad if fo[l].grad is not None else torch.zeros_like(feats[l])
             d = (fg[l].grad.cpu() - r).abs().max()
             assert float(d) <= 3e-5 * float(r.abs().max()) + 1e-5, (regions, l, float(d))
+
+
+@pytest.mark.parametrize("dtype,C", [(torch.float32, 192), (torch.bfloat16, 320), (torch.float32, 512)])
+def test_ring_kernel_variants_by_channel_count(oracle, cuda, dtype, C):
+    """Channel counts that select the other instantiations of the ring forward
+    (14 consumer warps of one 128-bit vector per lane: 480-thread CTAs) or leave
+    it for the L1-cached kernel (C = 512 fp32), and the one-vector pull kernel."""
+    import arfe_b200 as A
+    feats = small_pyramid(oracle, batch=1, channels=C, img_h=128, img_w=192)
+    feats = [f.to(dtype).float() for f in feats]
+    rois = mixed_rois(oracle, 30, 192, 128, 1, seed=43)
+    fo = [f.clone().requires_grad_(True) for f in feats]
+    ref = oracle.arrff_bbox_feats(fo, rois, list(STRIDES))
+    g = torch.randn(ref.shape, generator=torch.Generator().manual_seed(13)).to(dtype).float()
+    ref.backward(g)
+    fg = [_cl(f.to(cuda).to(dtype)).requires_grad_(True) for f in feats]
+    got = A.roi_fuse(fg, rois.to(cuda), 7, _scales(), regions=3, out_channels_last=True)
+    check = assert_close_fp32 if dtype == torch.float32 else assert_close_bf16
+    check(got, ref, f"forward C={C}")
+    got.backward(_cl(g.to(cuda).to(dtype)))
+    for l in range(5):
+        r = fo[l].grad if fo[l].grad is not None else torch.zeros_like(feats[l])
+        if dtype == torch.float32:
+            d = (fg[l].grad.cpu() - r).abs().max()
+            assert float(d) <= 3e-5 * float(r.abs().max()) + 1e-5, (l, float(d))
+        else:
+            assert_close_bf16(fg[l].grad, r, f"backward level {l} C={C}")
