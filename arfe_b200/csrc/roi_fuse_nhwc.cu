@@ -1336,7 +1336,6 @@ roi_bin_kernel(const RoiFuseParams p, const PullWs ws, const TileMap tm4, const 
 // arithmetic on shared-memory operands, accumulators in registers, every
 // gradient element written once -- no atomics, no zero-fill, deterministic.
 constexpr int kNSlot = 16;
-constexpr int kPullThreads = 288;
 constexpr int kDescBytes = (int)sizeof(StageDesc);
 constexpr int kTileQ = 4;      // tiles announced ahead of the consumers
 constexpr int kPullCtl = 1024; // barriers, stage offsets, tile queue
@@ -1451,12 +1450,22 @@ __device__ __forceinline__ void pull_consume_tile(const RoiFuseParams& p, const 
 
 // Work item g in [0, nb4 + nb8): (tile, channel group) of the narrow-tile pass,
 // then of the wide-tile pass.
-template <typename T, int NV>
-__global__ void __launch_bounds__(kPullThreads, (VecOf<T>::n * NV == 4 ? 3 : 2))
+//
+// NP producer warps.  One thread needs ~250 ns per (barrier wait, expect_tx, bulk
+// copy) sequence however small the copy (scripts/micro/l2_tma_bw.cu), and that, not
+// bandwidth, bounds a stream of 10-50 KB stages; the rate scales with the number of
+// issuing warps.  Producer w owns the stages s with s % NP == w (s counts the CTA's
+// stages), the slots s % kNSlot of those stages and the w-th part of the byte ring.
+// Producer 0 also claims the work items and announces them in the tile queue;
+// the others follow the queue like the consumers do.
+template <typename T, int NV, int NP>
+__global__ void __launch_bounds__((kTileH + NP) * 32, (VecOf<T>::n * NV == 4 ? 3 : 2))
 roi_bwd_pull_tma(const RoiFuseParams p, const PullWs ws, const TileMap tm4, const TileMap tm8,
                  int nb4, int nb8, int ring_bytes) {
   constexpr int V = VecOf<T>::n;
   constexpr int CG = 32 * V * NV;
+  constexpr int kOwnSlots = kNSlot / NP;
+  static_assert(kNSlot % NP == 0, "slots are dealt round-robin to the producers");
   extern __shared__ __align__(16) unsigned char smem[];
   PullCtl& ctl = *reinterpret_cast<PullCtl*>(smem);
   StageDesc* desc = reinterpret_cast<StageDesc*>(smem + kPullCtl);
@@ -1466,109 +1475,156 @@ roi_bwd_pull_tma(const RoiFuseParams p, const PullWs ws, const TileMap tm4, cons
 
   if (tid == 0) {
     for (int i = 0; i < kNSlot; ++i) { mbar_init(ctl.full + i, 1); mbar_init(ctl.empty + i, kTileH); }
-    for (int i = 0; i < kTileQ; ++i) { mbar_init(ctl.tq_full + i, 1); mbar_init(ctl.tq_empty + i, kTileH); }
+    for (int i = 0; i < kTileQ; ++i) { mbar_init(ctl.tq_full + i, 1); mbar_init(ctl.tq_empty + i, kTileH + NP - 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  if (warp == kTileH) {
-    // ------------------------------------------------------------ producer
-    uint32_t head = 0, tail = 0;  // live bytes of the ring: [tail, head) modulo wrap
-    uint32_t my_off = 0;          // lane j: ring offset of the stage in slot j
-    int issued = 0, released = 0; // stages issued / known to be consumed
+  if (warp >= kTileH) {
+    // ------------------------------------------------------------ producers
+    const int w = warp - kTileH;
+    const uint32_t sub_bytes = ((uint32_t)ring_bytes / NP) & ~127u;
+    unsigned char* const sub = ring + (uint32_t)w * sub_bytes;
+    uint32_t head = 0, tail = 0;  // live bytes of this producer's ring part: [tail, head) modulo wrap
+    uint32_t my_off = 0;          // lane j: offset of the stage in this producer's j-th slot
+    int issued = 0, released = 0; // own stages issued / known to be consumed
     const int C = p.C, BS = p.bin_stride;
+    // slot and barrier phase of this producer's o-th stage
+    auto slot_of = [&](int o) -> int { return (o * NP + w) % kNSlot; };
+    auto phase_of = [&](int o) -> uint32_t { return (uint32_t)((o * NP + w) / kNSlot) & 1u; };
+    auto load_hdr = [&](int pool_off, int n, int first) -> int4 {
+      return (n > 0 && first + lane < n) ? __ldg(reinterpret_cast<const int4*>(ws.pool + pool_off + first + lane))
+                                         : make_int4(0, 0, 0, 0);
+    };
+    // stages [0, n) of work item g (pool entries from pool_off) whose CTA-wide index
+    // stage0 + i belongs to this producer; hdr = headers of the first 32 entries
+    auto produce = [&](int g, int pool_off, int n, int stage0, int4 hdr) {
+      const bool narrow = g < nb4;
+      const int grp = narrow ? g % tm4.groups : (g - nb4) % tm8.groups;
+      const int c0 = grp * CG;
+      const uint32_t bin_bytes = (uint32_t)min(CG, C - c0) * sizeof(T);
+      const T* __restrict__ dsrc = static_cast<const T*>(p.dout) + c0;
+      const StageDesc* __restrict__ gdesc = ws.pool + pool_off;
+      for (int i = 0; i < n; ++i) {
+        if ((i & 31) == 0 && i > 0) hdr = load_hdr(pool_off, n, i);
+        if (NP > 1 && (stage0 + i) % NP != w) continue;
+        const int src_off = __shfl_sync(0xffffffffu, hdr.x, i & 31);
+        const int nn = __shfl_sync(0xffffffffu, hdr.y, i & 31);
+        const int rg = __shfl_sync(0xffffffffu, hdr.z, i & 31);
+        const int nph = nn & 0xffff, npw = (nn >> 16) & 0xffff;
+        const int nbins = nph * npw;
+        const uint32_t bytes = (uint32_t)nbins * bin_bytes;
+        const int slot = slot_of(issued);
+        // the slot's previous stage and enough ring space must have been released
+        // (a producer's stages are released in order)
+        auto release_one = [&]() {
+          mbar_wait(ctl.empty + slot_of(released), phase_of(released));
+          ++released;
+          const uint32_t nxt = __shfl_sync(0xffffffffu, my_off, released % kOwnSlots);
+          tail = released < issued ? nxt : head;
+        };
+        while (released < issued - kOwnSlots + 1) release_one();
+        uint32_t off;
+        while (true) {
+          if (released == issued) { head = tail = 0; off = 0; break; }           // ring empty
+          if (head >= tail) {
+            if (head + bytes <= sub_bytes) { off = head; break; }
+            if (bytes < tail) { off = 0; break; }                                  // wrap
+          } else if (head + bytes < tail) { off = head; break; }
+          release_one();
+        }
+        head = off + bytes;
+        if (lane == issued % kOwnSlots) my_off = off;
+        unsigned char* const dst = sub + off;
+        if (lane == 0) {
+          ctl.stage_off[slot] = (uint32_t)(dst - ring);
+          mbar_arrive_expect_tx(ctl.full + slot, ((p.debug_skip & 2) ? 0u : bytes) + kDescBytes);
+          bulk_g2s(desc + slot, gdesc + i, kDescBytes, ctl.full + slot);
+        }
+        if (p.debug_skip & 2) {
+          // profiling aid: no bin copies
+        } else if ((uint32_t)BS * sizeof(T) == bin_bytes) {
+          // split layout, all channels in this group: the npw bins of a bin row are
+          // contiguous -> one bulk copy per bin row
+          for (int ih = lane; ih < nph; ih += 32)
+            bulk_g2s(dst + (uint32_t)(ih * npw) * bin_bytes,
+                     dsrc + p.reg_off[rg] + (size_t)src_off + (size_t)(ih * p.PW) * BS,
+                     (uint32_t)npw * bin_bytes, ctl.full + slot);
+        } else {
+          for (int bi = lane; bi < nbins; bi += 32) {
+            const int ih = bi / npw, iw = bi - ih * npw;
+            bulk_g2s(dst + (uint32_t)bi * bin_bytes,
+                     dsrc + p.reg_off[rg] + (size_t)src_off + (size_t)(ih * p.PW + iw) * BS, bin_bytes, ctl.full + slot);
+          }
+        }
+        ++issued;
+      }
+    };
+    int stage0 = 0;
     auto claim = [&]() -> int { return lane == 0 ? atomicAdd(ws.counters + 2, 1) : 0; };
     auto tile_desc_of = [&](int g) -> int2 {
       if (g >= total) return make_int2(0, -1);
       return g < nb4 ? ws.tile_desc[tm4.tile_base + g / tm4.groups]
                      : ws.tile_desc[tm8.tile_base + (g - nb4) / tm8.groups];
     };
-    // software pipeline: claim two items ahead, tile descriptor and the first 32
-    // stage headers one item ahead
-    int g = __shfl_sync(0xffffffffu, claim(), 0);
-    int c_next = claim();
-    int2 td = tile_desc_of(g);
-    int4 hdr = make_int4(0, 0, 0, 0);
-    if (td.y > 0 && lane < td.y) hdr = __ldg(reinterpret_cast<const int4*>(ws.pool + td.x + lane));
-    for (int it = 0;; ++it) {
-      const int g_next = __shfl_sync(0xffffffffu, c_next, 0);
+    // current item {g (< 0: no more work), pool offset, stages} and its first 32 headers
+    int4 q = make_int4(0, 0, 0, 0), hdr = make_int4(0, 0, 0, 0);
+    // producer 0: software pipeline -- claim two items ahead, tile descriptor and the
+    // first 32 stage headers one item ahead
+    int c_next = 0;
+    // followers: the next item, when it had been announced already
+    bool have = false;
+    if (w == 0) {
+      const int g = __shfl_sync(0xffffffffu, claim(), 0);
       c_next = claim();
-      const int2 td_next = tile_desc_of(g_next);
-      // announce the current item
-      const int qs = it % kTileQ;
-      if (it >= kTileQ) mbar_wait(ctl.tq_empty + qs, ((it / kTileQ) - 1) & 1);
-      if (lane == 0) {
-        ctl.tq[qs] = make_int4(g < total ? g : -1, td.x, td.y, 0);
-        mbar_arrive(ctl.tq_full + qs);
-      }
-      if (g >= total) break;
-      const int n = td.y;  // < 0: inline tile, nothing to stream
-      if (n > 0) {
-        const bool narrow = g < nb4;
-        const int grp = narrow ? g % tm4.groups : (g - nb4) % tm8.groups;
-        const int c0 = grp * CG;
-        const uint32_t bin_bytes = (uint32_t)min(CG, C - c0) * sizeof(T);
-        const T* __restrict__ dsrc = static_cast<const T*>(p.dout) + c0;
-        const StageDesc* __restrict__ gdesc = ws.pool + td.x;
-        for (int i = 0; i < n; ++i) {
-          if ((i & 31) == 0 && i > 0 && i + lane < n) hdr = __ldg(reinterpret_cast<const int4*>(gdesc + i + lane));
-          const int src_off = __shfl_sync(0xffffffffu, hdr.x, i & 31);
-          const int nn = __shfl_sync(0xffffffffu, hdr.y, i & 31);
-          const int rg = __shfl_sync(0xffffffffu, hdr.z, i & 31);
-          const int nph = nn & 0xffff, npw = (nn >> 16) & 0xffff;
-          const int nbins = nph * npw;
-          const uint32_t bytes = (uint32_t)nbins * bin_bytes;
-          const int slot = issued % kNSlot;
-          // the slot's previous stage and enough ring space must have been released
-          // (stages are released in order)
-          auto release_one = [&]() {
-            mbar_wait(ctl.empty + (released % kNSlot), (released / kNSlot) & 1);
-            ++released;
-            const uint32_t nxt = __shfl_sync(0xffffffffu, my_off, released % kNSlot);
-            tail = released < issued ? nxt : head;
-          };
-          while (released < issued - kNSlot + 1) release_one();
-          uint32_t off;
-          while (true) {
-            if (released == issued) { head = tail = 0; off = 0; break; }           // ring empty
-            if (head >= tail) {
-              if (head + bytes <= (uint32_t)ring_bytes) { off = head; break; }
-              if (bytes < tail) { off = 0; break; }                                  // wrap
-            } else if (head + bytes < tail) { off = head; break; }
-            release_one();
+      const int2 td = tile_desc_of(g);
+      q = make_int4(g < total ? g : -1, td.x, td.y, 0);
+      hdr = load_hdr(q.y, q.z, 0);
+    }
+    for (int it = 0;; ++it) {
+      int4 q_next = make_int4(0, 0, 0, 0), hdr_next = make_int4(0, 0, 0, 0);
+      if (w == 0) {
+        const int g_next = __shfl_sync(0xffffffffu, c_next, 0);
+        c_next = claim();
+        const int2 td_next = tile_desc_of(g_next);
+        q_next = make_int4(g_next < total ? g_next : -1, td_next.x, td_next.y, 0);
+        // announce the current item
+        const int qs = it % kTileQ;
+        if (it >= kTileQ) mbar_wait(ctl.tq_empty + qs, ((it / kTileQ) - 1) & 1);
+        if (lane == 0) {
+          ctl.tq[qs] = q;
+          mbar_arrive(ctl.tq_full + qs);
+        }
+      } else {
+        if (!have) {
+          const int qs = it % kTileQ;
+          mbar_wait(ctl.tq_full + qs, (it / kTileQ) & 1);
+          q = ctl.tq[qs];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ctl.tq_empty + qs);
+          hdr = load_hdr(q.y, q.z, 0);
+        }
+        have = false;
+        if (q.x >= 0) {
+          const int qn = (it + 1) % kTileQ;
+          const int ready = __shfl_sync(0xffffffffu, (int)mbar_test(ctl.tq_full + qn, ((it + 1) / kTileQ) & 1), 0);
+          if (ready) {
+            q_next = ctl.tq[qn];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ctl.tq_empty + qn);
+            hdr_next = load_hdr(q_next.y, q_next.z, 0);
+            have = true;
           }
-          head = off + bytes;
-          if (lane == slot) my_off = off;
-          if (lane == 0) {
-            ctl.stage_off[slot] = off;
-            mbar_arrive_expect_tx(ctl.full + slot, ((p.debug_skip & 2) ? 0u : bytes) + kDescBytes);
-            bulk_g2s(desc + slot, gdesc + i, kDescBytes, ctl.full + slot);
-          }
-          if (p.debug_skip & 2) {
-            // profiling aid: no bin copies
-          } else if ((uint32_t)BS * sizeof(T) == bin_bytes) {
-            // split layout, all channels in this group: the npw bins of a bin row are
-            // contiguous -> one bulk copy per bin row (the per-SM rate of small bulk
-            // copies, not bandwidth, bounds this kernel)
-            for (int ih = lane; ih < nph; ih += 32)
-              bulk_g2s(ring + off + (uint32_t)(ih * npw) * bin_bytes,
-                       dsrc + p.reg_off[rg] + (size_t)src_off + (size_t)(ih * p.PW) * BS,
-                       (uint32_t)npw * bin_bytes, ctl.full + slot);
-          } else {
-            for (int bi = lane; bi < nbins; bi += 32) {
-              const int ih = bi / npw, iw = bi - ih * npw;
-              bulk_g2s(ring + off + (uint32_t)bi * bin_bytes,
-                       dsrc + p.reg_off[rg] + (size_t)src_off + (size_t)(ih * p.PW + iw) * BS, bin_bytes, ctl.full + slot);
-            }
-          }
-          ++issued;
         }
       }
-      // rotate: the next item's descriptor has been in flight since the top
-      g = g_next;
-      td = td_next;
-      hdr = make_int4(0, 0, 0, 0);
-      if (td.y > 0 && lane < td.y) hdr = __ldg(reinterpret_cast<const int4*>(ws.pool + td.x + lane));
+      if (q.x < 0) break;
+      if (q.z > 0) {  // < 0: inline tile, nothing to stream
+        produce(q.x, q.y, q.z, stage0, hdr);
+        stage0 += q.z;
+      }
+      // rotate: producer 0's next descriptor has been in flight since the top
+      q = q_next;
+      hdr = w == 0 ? load_hdr(q.y, q.z, 0) : hdr_next;
     }
     return;
   }
@@ -1874,7 +1930,12 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
   }
   if (!(stages & 4)) return cudaSuccess;
   const int per_sm = (dtype == 0 && nv == 1) ? 3 : 2;
-  const int ring = (per_sm == 3 ? 64 : 96) * 1024;
+  // two producer warps (each owning half of a slightly larger ring) when the largest
+  // possible stage fits one half
+  static const int np_env = [] { const char* ev = getenv("ARFE_PULL_NP"); return ev ? atoi(ev) : 0; }();
+  const int max_stage = (p.PH < kMaxPh ? p.PH : kMaxPh) * (p.PW < kJ ? p.PW : kJ) * 32 * V * nv * (dtype == 0 ? 4 : 2);
+  const int np = (nv == 2 && max_stage <= 52 * 1024 && np_env != 1) ? 2 : 1;
+  const int ring = per_sm == 3 ? 64 * 1024 : (np == 2 ? 104 * 1024 : 96 * 1024);
   const int smem = kPullCtl + kNSlot * kDescBytes + ring;
   const int nb4 = ntiles[0] * tm[0].groups, nb8 = ntiles[1] * tm[1].groups;
   static const int sms = [] {
@@ -1884,13 +1945,16 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
     return n;
   }();
   const int pgrid = nb4 + nb8 < per_sm * sms ? nb4 + nb8 : per_sm * sms;
-#define ARFE_PULL(TT, NVV)                                                                          \
+#define ARFE_PULL(TT, NVV, NPP)                                                                     \
   do {                                                                                              \
-    if ((e = set_smem(roi_bwd_pull_tma<TT, NVV>, smem)) != cudaSuccess) return e;                   \
-    roi_bwd_pull_tma<TT, NVV><<<pgrid, kPullThreads, smem, stream>>>(p, ws, tm[0], tm[1], nb4, nb8, ring); \
+    if ((e = set_smem(roi_bwd_pull_tma<TT, NVV, NPP>, smem)) != cudaSuccess) return e;              \
+    roi_bwd_pull_tma<TT, NVV, NPP><<<pgrid, (kTileH + NPP) * 32, smem, stream>>>(p, ws, tm[0], tm[1], nb4, nb8, ring); \
   } while (0)
-  if (dtype == 0) { if (nv == 2) ARFE_PULL(float, 2); else ARFE_PULL(float, 1); }
-  else ARFE_PULL(__nv_bfloat16, 1);
+  if (dtype == 0) {
+    if (nv == 2 && np == 2) ARFE_PULL(float, 2, 2);
+    else if (nv == 2) ARFE_PULL(float, 2, 1);
+    else ARFE_PULL(float, 1, 1);
+  } else ARFE_PULL(__nv_bfloat16, 1, 1);
 #undef ARFE_PULL
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   const int igrid = ntiles[0] + ntiles[1] < 592 ? ntiles[0] + ntiles[1] : 592;

@@ -11,7 +11,7 @@ relu(conv) of the context regions, incoming gradients) are synthetic inputs.
 Step (channels-last: 14 launches of our kernels):
   fwd: gather -> apply -> roi_fuse (3 regions: plan, ring kernel, left-out regions) -> gate
   bwd: gate_bwd -> roi_fuse_bwd (bin, pull, inline tiles, flagged regions; reuses the
-       forward's plan) -> apply_bwd (2 launches) -> gather_bwd
+       forward's plan) -> apply_bwd -> gather_bwd (2 launches)
 """
 import math
 
@@ -319,9 +319,10 @@ class TrainStep:
         """Kernels of libarfe_b200.so per step: gather 1, apply 1, roi fwd (plan +
         ring + left-out regions = 3 | 1), gate 2, roi bwd (bin + pull + inline tiles +
         flagged-region fallback = 4, the plan is the forward's | atomic 1),
-        apply bwd 2, gather bwd 2 (vector kernel + small levels) | 1.  (Channels-last:
+        apply bwd 1 | 2, gather bwd 2 (pooled levels + small levels; one merged launch was
+        measured slower: 49 us vs 34 + 11 us, a third wave of CTAs) | 2.  (Channels-last:
         plan and bin run on the second stream of plan_async; same count.)"""
-        return (1 + 1 + 3 + 2 + 4 + 2 + 1) if self.cl else (1 + 1 + 1 + 2 + 1 + 2 + 2)
+        return (1 + 1 + 3 + 2 + 4 + 1 + 2) if self.cl else (1 + 1 + 1 + 2 + 1 + 2 + 2)
 
     # -- algorithmic bytes per launch (DESIGN.md section 5) ------------------
     def algorithmic_bytes(self):
