@@ -220,13 +220,34 @@ gather_bwd_up_cl(const FpnParams p, const UpLevels ul) {
 #pragma unroll
   for (int u = 0; u < V; ++u) g[u] = 0.f;
   const T* __restrict__ d = static_cast<const T*>(p.gathered);
-  for (int Y = Ya; Y < Yb; ++Y)
-    for (int X = Xa; X < Xb; ++X) {
-      float t[V];
-      ldv<T>(d + (((size_t)b * Hr + Y) * Wr + X) * C + c, t);
+  if (Yb - Ya <= 4 && Xb - Xa <= 4) {
+    // the usual case (ratios up to 4): a whole window row of loads in flight instead of
+    // one DRAM latency per refine pixel; same summation order as the loop below
+    const T* __restrict__ w0 = d + (((size_t)b * Hr + Ya) * Wr + Xa) * C + c;
+    const int ny = Yb - Ya, nx = Xb - Xa;
 #pragma unroll
-      for (int u = 0; u < V; ++u) g[u] += t[u];
+    for (int dy = 0; dy < 4; ++dy) {
+      if (dy >= ny) break;
+      float t[4][V];
+#pragma unroll
+      for (int dx = 0; dx < 4; ++dx)
+        if (dx < nx) ldv<T>(w0 + ((size_t)dy * Wr + dx) * C, t[dx]);
+#pragma unroll
+      for (int dx = 0; dx < 4; ++dx)
+        if (dx < nx) {
+#pragma unroll
+          for (int u = 0; u < V; ++u) g[u] += t[dx][u];
+        }
     }
+  } else {
+    for (int Y = Ya; Y < Yb; ++Y)
+      for (int X = Xa; X < Xb; ++X) {
+        float t[V];
+        ldv<T>(d + (((size_t)b * Hr + Y) * Wr + X) * C + c, t);
+#pragma unroll
+        for (int u = 0; u < V; ++u) g[u] += t[u];
+      }
+  }
 #pragma unroll
   for (int u = 0; u < V; ++u) g[u] = __fdiv_rn(g[u], (float)p.L);
   stv<T>(static_cast<T*>(p.outs[l]) + (i - ul.start[j]) * V, g);
