@@ -196,9 +196,11 @@ class TrainStep:
         forward (latency-bound table walking next to bandwidth-bound streaming)."""
         if getattr(self, "side", None) is None:
             self.side = torch.cuda.Stream(self.dev)
-            self.ev_free, self.ev_plan, self.ev_bin = (torch.cuda.Event() for _ in range(3))
-            self.ev_free.record(torch.cuda.current_stream(self.dev))
-        self.side.wait_event(self.ev_free)  # the previous step's backward still reads the workspace
+            self.ev_fork, self.ev_plan, self.ev_bin = (torch.cuda.Event() for _ in range(3))
+        # fork: everything before this step (the previous step's backward still reads the
+        # workspace) precedes the rebuild; the joins are the waits on ev_plan / ev_bin
+        self.ev_fork.record(torch.cuda.current_stream(self.dev))
+        self.side.wait_event(self.ev_fork)
         geo = (self.H, self.W, self.scales, self.nlev, self.B, self.C, self.rois.data_ptr(), self.K,
                self.R, 1.0, self.P, self.P, 0, 56.0, self.dt)
         tail = (self.ws_ptr, self.ws_bytes, self.side.cuda_stream)
@@ -296,7 +298,11 @@ class TrainStep:
                 a.copy_(b)
 
     def step(self, timer=None):
-        """One training step. `timer(name, fn)` wraps each of our launches."""
+        """One training step. `timer(name, fn)` wraps each of our launches; without a
+        timer a captured step (capture()) is replayed as one CUDA graph."""
+        if timer is None and getattr(self, "graph", None) is not None:
+            self.graph.replay()
+            return
         run = timer or (lambda name, fn: L.check(fn(), name))
         if self.cl and self.overlap_plan:
             self.plan_async()
@@ -310,10 +316,21 @@ class TrainStep:
         self.glue_before_apply_bwd()
         run("fpn_apply_bwd", self.fpn_apply_bwd)
         run("fpn_gather_bwd", self.fpn_gather_bwd)
-        if getattr(self, "side", None) is not None:
-            # the next step's plan may be rebuilt (second stream) once this step is over, i.e.
-            # under the next step's AR-FPN forward kernels, not under this step's tail
-            self.ev_free.record(torch.cuda.current_stream(self.dev))
+
+    def capture(self):
+        """Capture the step (the same launches, second stream included) into a CUDA graph:
+        the 14 kernels are 35-170 us each, so launch gaps are a visible share of the step."""
+        for _ in range(3):
+            self.step()  # kernel attributes set, second stream and events created
+        torch.cuda.synchronize(self.dev)
+        graph, cap, saved = torch.cuda.CUDAGraph(), torch.cuda.Stream(self.dev), self.stream
+        try:
+            with torch.cuda.graph(graph, stream=cap):
+                self.stream = cap.cuda_stream
+                self.step()
+        finally:
+            self.stream = saved
+        self.graph = graph
 
     def launches_per_step(self):
         """Kernels of libarfe_b200.so per step: gather 1, apply 1, roi fwd (plan +
