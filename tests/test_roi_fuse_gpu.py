@@ -523,3 +523,24 @@ def test_ring_kernel_variants_by_channel_count(oracle, cuda, dtype, C):
             assert float(d) <= 3e-5 * float(r.abs().max()) + 1e-5, (l, float(d))
         else:
             assert_close_bf16(fg[l].grad, r, f"backward level {l} C={C}")
+
+
+def test_mask_pool_14x14_full_channel_groups(oracle, cuda):
+    """14x14 at C = 256 fp32: a stage may hold 8 x 8 bins of 1 KB (64 KB), more than half the
+    ring, so the pull kernel runs its one-producer, two-vector instantiation; the forward
+    takes the 14-row ring kernel with 14 consumer warps."""
+    import arfe_b200 as A
+    feats = small_pyramid(oracle, batch=1, channels=256, img_h=96, img_w=128)
+    rois = mixed_rois(oracle, 10, 128, 96, 1, seed=5)
+    fo = [f.clone().requires_grad_(True) for f in feats]
+    ref = oracle.arrff_bbox_feats(fo, rois, list(STRIDES), out_size=14)
+    g = torch.randn(ref.shape, generator=torch.Generator().manual_seed(21))
+    ref.backward(g)
+    fg = [_cl(f.to(cuda)).requires_grad_(True) for f in feats]
+    got = A.roi_fuse(fg, rois.to(cuda), 14, _scales(), regions=3, out_channels_last=True)
+    assert_close_fp32(got, ref, "forward 14x14 C=256")
+    got.backward(_cl(g.to(cuda)))
+    for l in range(5):
+        r = fo[l].grad if fo[l].grad is not None else torch.zeros_like(feats[l])
+        d = (fg[l].grad.cpu() - r).abs().max()
+        assert float(d) <= 3e-5 * float(r.abs().max()) + 1e-5, (l, float(d))

@@ -29,3 +29,34 @@ def test_step_graph_replay_matches_plain_launches(cuda):
     for a, b in zip(ref, _outputs(st)):
         assert torch.equal(a, b)
     assert st.launches_per_step() == 14
+
+
+_HASH_SNIPPET = r"""
+import hashlib, sys, torch
+sys.path.insert(0, %r)
+from arfe_b200 import workload as wl, _lib as L
+host = wl.host_inputs(batch=2, rois_per_img=96, channels=256, img_h=256, img_w=320, channels_last=True)
+st = wl.TrainStep(host, torch.device("cuda:0"))
+st.step(); st.step(); torch.cuda.synchronize()
+h = hashlib.sha256()
+for t in st.dy:
+    h.update(t.cpu().numpy().tobytes())
+print("HASH", h.hexdigest())
+"""
+
+
+def test_pull_one_and_two_producer_warps_agree_bitwise(cuda):
+    """The pull backward writes every gradient element once in a fixed order, so the
+    one-producer (ARFE_PULL_NP=1) and two-producer instantiations must agree to the bit."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = []
+    for np_ in ("1", "0"):
+        env = dict(os.environ, ARFE_PULL_NP=np_)
+        r = subprocess.run([sys.executable, "-c", _HASH_SNIPPET % root], env=env, capture_output=True,
+                           text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out.append([l for l in r.stdout.splitlines() if l.startswith("HASH")][0])
+    assert out[0] == out[1]
