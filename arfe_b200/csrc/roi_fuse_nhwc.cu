@@ -1938,7 +1938,7 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
   // possible stage fits one half
   static const int np_env = [] { const char* ev = getenv("ARFE_PULL_NP"); return ev ? atoi(ev) : 0; }();
   const int max_stage = (p.PH < kMaxPh ? p.PH : kMaxPh) * (p.PW < kJ ? p.PW : kJ) * 32 * V * nv * (dtype == 0 ? 4 : 2);
-  const int np = (nv == 2 && max_stage <= 52 * 1024 && np_env != 1) ? 2 : 1;
+  const int np = (per_sm == 2 && max_stage <= 52 * 1024 && np_env != 1) ? 2 : 1;
   const int ring = per_sm == 3 ? 64 * 1024 : (np == 2 ? 104 * 1024 : 96 * 1024);
   const int smem = kPullCtl + kNSlot * kDescBytes + ring;
   const int nb4 = ntiles[0] * tm[0].groups, nb8 = ntiles[1] * tm[1].groups;
@@ -1958,7 +1958,8 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
     if (nv == 2 && np == 2) ARFE_PULL(float, 2, 2);
     else if (nv == 2) ARFE_PULL(float, 2, 1);
     else ARFE_PULL(float, 1, 1);
-  } else ARFE_PULL(__nv_bfloat16, 1, 1);
+  } else if (np == 2) ARFE_PULL(__nv_bfloat16, 1, 2);
+  else ARFE_PULL(__nv_bfloat16, 1, 1);
 #undef ARFE_PULL
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   const int igrid = ntiles[0] + ntiles[1] < 592 ? ntiles[0] + ntiles[1] : 592;
