@@ -770,6 +770,77 @@ __device__ __forceinline__ void fwd_consume_rows(const FwdPipe& pp, int stage0, 
   float wx[NC > 0 ? NC : 1];
 #pragma unroll
   for (int j = 0; j < NC; ++j) wx[j] = wxp[j];
+  if (PH == 7 && nblk == 1) {
+    // Bins at least one pixel high: a window row is sampled by at most the two adjacent bin
+    // rows p0, p0 + 1 and p0 never decreases down the window, so two live accumulators per
+    // chunk suffice.  A bin row is written out as soon as the window has moved past it
+    // (same additions in the same order as the general path below: identical bits) -- no
+    // run-time index into register accumulators, hence no jump table.
+    uint64_t lo[NCH][V2], hi[NCH][V2];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int u = 0; u < V2; ++u) lo[ch][u] = hi[ch][u] = 0ull;
+    int cur = 0;  // bin row held in lo; hi holds cur + 1
+    auto flush = [&]() {
+      if (o) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          float f[V];
+#pragma unroll
+          for (int u = 0; u < V2; ++u) unpack2(lo[ch][u], f[2 * u], f[2 * u + 1]);
+          st_vec<T>(o + (size_t)cur * ostep + ch * (32 * V), f);
+        }
+      }
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+        for (int u = 0; u < V2; ++u) { lo[ch][u] = hi[ch][u]; hi[ch][u] = 0ull; }
+      ++cur;
+    };
+    for (int rr = 0; rr < nrows; ++rr) {
+      const int stage = stage0 + rr;
+      const int slot = stage % kFwdSlots;
+      const int4 rec = *reinterpret_cast<const int4*>(rowtab + rr);
+      mbar_wait(pp.full + slot, (stage / kFwdSlots) & 1);
+      if (NC > 0 && rec.y > 0) {
+        while (cur < rec.x) flush();  // warp-uniform
+        const uint64_t w0p = pack2(__int_as_float(rec.z), __int_as_float(rec.z));
+        const uint64_t w1p = pack2(__int_as_float(rec.w), __int_as_float(rec.w));
+        const unsigned char* __restrict__ s0 = pp.ring + pp.stage_off[slot] + tap0;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const unsigned char* __restrict__ sc = s0 + ch * kChunkBytes;
+          uint64_t v[NC > 0 ? NC : 1][V2];
+#pragma unroll
+          for (int j = 0; j < NC; ++j) lds_pairs<T>(sc + j * tap_step, v[j]);
+          uint64_t t[V2];
+#pragma unroll
+          for (int u = 0; u < V2; ++u) t[u] = mul2(v[0][u], pack2(wx[0], wx[0]));
+#pragma unroll
+          for (int j = 1; j < NC; ++j)
+#pragma unroll
+            for (int u = 0; u < V2; ++u) t[u] = fma2(v[j][u], pack2(wx[j], wx[j]), t[u]);
+          for (int j = NC; j < nc_dyn; ++j) {
+            uint64_t vv[V2];
+            lds_pairs<T>(sc + j * tap_step, vv);
+            const float w = wxp[j];
+#pragma unroll
+            for (int u = 0; u < V2; ++u) t[u] = fma2(vv[u], pack2(w, w), t[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < V2; ++u) {
+            lo[ch][u] = fma2(t[u], w0p, lo[ch][u]);
+            hi[ch][u] = fma2(t[u], w1p, hi[ch][u]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pp.empty + slot);
+    }
+    while (cur < PH) flush();
+    return;
+  }
   uint64_t acc[NCH][PH][V2];
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch)
