@@ -770,7 +770,7 @@ __device__ __forceinline__ void fwd_consume_rows(const FwdPipe& pp, int stage0, 
   float wx[NC > 0 ? NC : 1];
 #pragma unroll
   for (int j = 0; j < NC; ++j) wx[j] = wxp[j];
-  if (PH == 7 && nblk == 1) {
+  if (nblk == 1) {
     // Bins at least one pixel high: a window row is sampled by at most the two adjacent bin
     // rows p0, p0 + 1 and p0 never decreases down the window, so two live accumulators per
     // chunk suffice.  A bin row is written out as soon as the window has moved past it
