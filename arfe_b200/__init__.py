@@ -4,7 +4,8 @@ path: AR-FPN aggregation (WFPNDualSpatial) and AR-RFF RoI fusion
 reference's module/operator surface.  Compute lives in libarfe_b200.so
 (C ABI: include/arfe_b200.h); there is no CPU fallback.
 """
-from ._compat import ConvModule, register_into_mmdet  # noqa: F401
+from ._compat import (ConvModule, accelerate_class, optimize_detector,  # noqa: F401
+                      register_into_mmdet)
 from .bbox_head import MultiBBoxHead, MultiRoIsBBoxHead  # noqa: F401
 from .functional import (fpn_apply, fpn_gather, rff_gate, roi_fuse,  # noqa: F401
                          roi_fuse_debug, roi_fuse_split, split3)

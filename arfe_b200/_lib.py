@@ -11,7 +11,9 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libarfe_b200.so")
+# ARFE_B200_LIB: load another build of the same ABI (scripts/ point it at the
+# -DARFE_PROFILE library libarfe_b200_prof.so); the package default has no knobs.
+LIB_PATH = os.environ.get("ARFE_B200_LIB") or os.path.join(_PKG, "libarfe_b200.so")
 
 ARFE_F32, ARFE_BF16 = 0, 1
 ARFE_NCHW, ARFE_NHWC = 0, 1
@@ -64,6 +66,8 @@ _SIGNATURES = {
                                  c_void_p, c_void_p], c_int),
     "arfe_fpn_gather_backward": ([c_void_p, c_void_p, _ip, _ip, c_int, c_int, c_int, c_int, c_int,
                                   c_int, _pp, c_void_p], c_int),
+    "arfe_fpn_gather_backward_acc": ([c_void_p, c_void_p, _ip, _ip, c_int, c_int, c_int, c_int, c_int,
+                                      c_int, _pp, _pp, c_void_p], c_int),
     "arfe_fpn_apply_forward": ([_pp, c_void_p, _pp, _pp, _ip, _ip, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_int, _pp, c_void_p], c_int),
     "arfe_fpn_apply_backward": ([_pp, c_void_p, _pp, _pp, _ip, _ip, c_int, c_int, c_int, c_int,

@@ -31,6 +31,25 @@ int cuda_result(cudaError_t e, const char* what) {
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 size_t esize(int dtype) { return dtype == ARFE_F32 ? 4 : 2; }
 
+// Launches go to the device that owns the tensors, not to whatever device happens to be
+// current in the calling thread (the stream handle must belong to the same device).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const void* ptr) {
+    cudaPointerAttributes a;
+    if (ptr && cudaPointerGetAttributes(&a, ptr) == cudaSuccess && a.type == cudaMemoryTypeDevice) {
+      if (cudaGetDevice(&prev) == cudaSuccess && a.device != prev)
+        switched = cudaSetDevice(a.device) == cudaSuccess;
+    } else {
+      cudaGetLastError();  // not a device pointer: leave the error state clean, validation reports it
+    }
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 #define REQUIRE(cond, code, ...) \
   do { if (!(cond)) return fail(code, __VA_ARGS__); } while (0)
 
@@ -126,10 +145,8 @@ int arfe_roi_fuse_forward(const void* const* feats, const int32_t* H, const int3
     REQUIRE(aligned(out, 16), ARFE_E_ALIGN, "%s: out must be 16-byte aligned", fn);
   }
   p.out = out; p.lvl_out = lvl_out; p.boxes_out = boxes_out; p.out_cl = out_layout == ARFE_NHWC;
-  {
-    const char* ev = getenv("ARFE_FWD_SKIP");  // profiling aid, default off
-    p.debug_skip = ev ? atoi(ev) : 0;
-  }
+  DeviceGuard guard(out);
+  p.debug_skip = ARFE_KNOB_ENV("ARFE_FWD_SKIP", 0);
   return cuda_result(arfe::launch_roi_fuse_forward(p, dtype, layout, (cudaStream_t)stream), fn);
 }
 
@@ -145,6 +162,7 @@ static int forward_plan_impl(const char* fn, const void* const* feats, const int
   if (rc) return rc;
   if (K == 0) return ARFE_OK;
   REQUIRE(workspace, ARFE_E_NULL, "%s: workspace is NULL", fn);
+  DeviceGuard guard(workspace);
   if (stages == 1) {  // plan only: no tensors involved
     REQUIRE(B >= 1 && aligned(rois, 4) && aligned(workspace, 256), ARFE_E_ALIGN, "%s: rois / workspace misaligned", fn);
     REQUIRE(workspace_bytes >= arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W), ARFE_E_SHAPE,
@@ -171,10 +189,7 @@ static int forward_plan_impl(const char* fn, const void* const* feats, const int
   REQUIRE(workspace_bytes >= arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W), ARFE_E_SHAPE,
           "%s: workspace too small (%zu < %zu)", fn, workspace_bytes, arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W));
   p.out = out; p.lvl_out = lvl_out; p.boxes_out = boxes_out; p.out_cl = 1;
-  {
-    const char* ev = getenv("ARFE_FWD_SKIP");  // profiling aid, default off
-    p.debug_skip = ev ? atoi(ev) : 0;
-  }
+  p.debug_skip = ARFE_KNOB_ENV("ARFE_FWD_SKIP", 0);
   return cuda_result(arfe::launch_roi_fuse_forward_plan(p, dtype, workspace, workspace_bytes, stages, (cudaStream_t)stream), fn);
 }
 
@@ -230,6 +245,7 @@ int arfe_roi_fuse_backward(const void* dout, int dout_layout, const int32_t* H, 
   }
   REQUIRE(dout_layout == ARFE_NCHW || dout_layout == ARFE_NHWC, ARFE_E_ENUM, "%s: unknown dout_layout %d", fn, dout_layout);
   p.dout = dout; p.dout_cl = dout_layout == ARFE_NHWC;
+  DeviceGuard guard(dout);
   return cuda_result(arfe::launch_roi_fuse_backward(p, dtype, layout, (cudaStream_t)stream), fn);
 }
 
@@ -264,6 +280,7 @@ static int backward_pull_impl(const char* fn, const void* dout, const void* cons
   REQUIRE(C % (dtype == ARFE_F32 ? 4 : 8) == 0, ARFE_E_UNSUPPORTED, "%s: C must be a multiple of %d",
           fn, dtype == ARFE_F32 ? 4 : 8);
   if (plan_ready == kBinOnly && K == 0) return ARFE_OK;
+  DeviceGuard guard(workspace ? workspace : (dfeats ? static_cast<const void*>(dfeats[0]) : nullptr));
   for (int l = 0; l < L && dfeats; ++l) {
     REQUIRE(dfeats[l], ARFE_E_NULL, "%s: dfeats[%d] is NULL", fn, l);
     REQUIRE(aligned(dfeats[l], 16), ARFE_E_ALIGN, "%s: dfeats[%d] must be 16-byte aligned", fn, l);
@@ -294,10 +311,7 @@ static int backward_pull_impl(const char* fn, const void* dout, const void* cons
   REQUIRE(workspace_bytes >= arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W), ARFE_E_SHAPE,
           "%s: workspace too small (%zu < %zu)", fn, workspace_bytes, arfe::roi_pull_workspace_bytes(K, regions, L, B, H, W));
   p.dout = dout; p.dout_cl = 1;
-  {
-    const char* ev = getenv("ARFE_BWD_SKIP");  // profiling aid, default off
-    p.debug_skip = ev ? atoi(ev) : 0;
-  }
+  p.debug_skip = ARFE_KNOB_ENV("ARFE_BWD_SKIP", 0);
   rc = cuda_result(arfe::launch_roi_fuse_backward_pull(p, dtype, workspace, workspace_bytes, stages, (cudaStream_t)stream), fn);
   if (rc) return rc;
   // regions whose tap tables did not fit the workspace records: atomic kernel, adds on top
@@ -378,6 +392,7 @@ int arfe_roi_fuse_taps(const int32_t* H, const int32_t* W, const float* spatial_
   if (rc) return rc;
   if (K == 0) return ARFE_OK;
   REQUIRE(max_grid >= 1, ARFE_E_SHAPE, "%s: max_grid=%d", fn, max_grid);
+  DeviceGuard guard(rois);
   REQUIRE((ylo == nullptr) == (yhi == nullptr) && (ylo == nullptr) == (ywl == nullptr) &&
               (ylo == nullptr) == (ywh == nullptr) && (xlo == nullptr) == (xhi == nullptr) &&
               (xlo == nullptr) == (xwl == nullptr) && (xlo == nullptr) == (xwh == nullptr),
@@ -395,6 +410,7 @@ int arfe_rff_gate_forward(const void* ori, int64_t ori_roi_stride, const void* a
   if (K == 0) return ARFE_OK;
   REQUIRE(ori && a && b && out, ARFE_E_NULL, "%s: NULL tensor", fn);
   REQUIRE(n_per_roi < (1ll << 31), ARFE_E_SHAPE, "%s: n_per_roi too large", fn);
+  DeviceGuard guard(out);
   return cuda_result(arfe::launch_rff_gate_forward(ori, ori_roi_stride, a, b, out, K, n_per_roi,
                                                    dtype, (cudaStream_t)stream), fn);
 }
@@ -410,6 +426,7 @@ int arfe_rff_gate_backward(const void* g, const void* ori, int64_t ori_roi_strid
   REQUIRE(g && ori && a && b && d_ori && d_ab, ARFE_E_NULL, "%s: NULL tensor", fn);
   REQUIRE(n_per_roi < (1ll << 31), ARFE_E_SHAPE, "%s: n_per_roi too large", fn);
   REQUIRE(d_ori_roi_stride >= n_per_roi, ARFE_E_SHAPE, "%s: d_ori stride < n_per_roi", fn);
+  DeviceGuard guard(d_ab);
   return cuda_result(arfe::launch_rff_gate_backward(g, ori, ori_roi_stride, a, b, d_ori, d_ori_roi_stride, d_ab, K,
                                                     n_per_roi, dtype, (cudaStream_t)stream), fn);
 }
@@ -445,12 +462,14 @@ int arfe_fpn_gather_forward(const void* const* feats, const int32_t* H, const in
     }
   }
   p.gathered = out; p.argmax = argmax;
+  DeviceGuard guard(out);
   return cuda_result(arfe::launch_fpn_gather_forward(p, dtype, layout, (cudaStream_t)stream), fn);
 }
 
-int arfe_fpn_gather_backward(const void* dout, const uint8_t* argmax, const int32_t* H,
-                             const int32_t* W, int L, int B, int C, int refine_level, int dtype,
-                             int layout, void* const* dfeats, void* stream) {
+int arfe_fpn_gather_backward_acc(const void* dout, const uint8_t* argmax, const int32_t* H,
+                                 const int32_t* W, int L, int B, int C, int refine_level, int dtype,
+                                 int layout, const float* const* addend, void* const* dfeats,
+                                 void* stream) {
   const char* fn = "arfe_fpn_gather_backward";
   arfe::FpnParams p;
   int rc = fill_fpn(fn, p, H, W, L, B, C, dtype, layout);
@@ -463,9 +482,21 @@ int arfe_fpn_gather_backward(const void* dout, const uint8_t* argmax, const int3
   for (int l = 0; l < L; ++l) {
     REQUIRE(dfeats[l], ARFE_E_NULL, "%s: dfeats[%d] is NULL", fn, l);
     p.outs[l] = dfeats[l];
+    if (addend && addend[l]) {
+      REQUIRE(aligned(addend[l], 16), ARFE_E_ALIGN, "%s: addend[%d] must be 16-byte aligned", fn, l);
+      p.addend[l] = addend[l];
+    }
   }
   p.gathered = const_cast<void*>(dout); p.argmax = const_cast<uint8_t*>(argmax);
+  DeviceGuard guard(dout);
   return cuda_result(arfe::launch_fpn_gather_backward(p, dtype, layout, (cudaStream_t)stream), fn);
+}
+
+int arfe_fpn_gather_backward(const void* dout, const uint8_t* argmax, const int32_t* H,
+                             const int32_t* W, int L, int B, int C, int refine_level, int dtype,
+                             int layout, void* const* dfeats, void* stream) {
+  return arfe_fpn_gather_backward_acc(dout, argmax, H, W, L, B, C, refine_level, dtype, layout, nullptr,
+                                      dfeats, stream);
 }
 
 int arfe_fpn_apply_forward(const void* const* feats, const void* bsf, const void* const* g1,
@@ -484,6 +515,7 @@ int arfe_fpn_apply_forward(const void* const* feats, const void* bsf, const void
     p.feats[l] = feats[l]; p.g1[l] = g1[l]; p.g2[l] = g2[l]; p.outs[l] = outs[l];
   }
   p.bsf = bsf; p.Hr = Hr; p.Wr = Wr;
+  DeviceGuard guard(bsf);
   return cuda_result(arfe::launch_fpn_apply_forward(p, dtype, layout, (cudaStream_t)stream), fn);
 }
 
@@ -503,6 +535,7 @@ int arfe_fpn_apply_backward(const void* const* douts, const void* bsf, const voi
     p.feats[l] = douts[l]; p.g1[l] = g1[l]; p.g2[l] = g2[l]; p.dg1[l] = dg1[l]; p.dg2[l] = dg2[l];
   }
   p.bsf = bsf; p.Hr = Hr; p.Wr = Wr; p.dbsf = dbsf;
+  DeviceGuard guard(dbsf);
   return cuda_result(arfe::launch_fpn_apply_backward(p, dtype, layout, (cudaStream_t)stream), fn);
 }
 

@@ -151,7 +151,9 @@ gather_bwd(const FpnParams p, const LevelOffsets lo) {
         if (nearest_src(X, W, Wr) == x) g += ldf(d + at<kNHWC>(b, c, Y, X, C, Hr, Wr));
     }
   }
-  stf(static_cast<T*>(p.outs[l]) + (i - lo.start[j]), __fdiv_rn(g, (float)p.L));
+  g = __fdiv_rn(g, (float)p.L);
+  if (p.addend[l]) g += __ldg(p.addend[l] + (i - lo.start[j]));
+  stf(static_cast<T*>(p.outs[l]) + (i - lo.start[j]), g);
 }
 
 // Fast (NCHW fp32, exact integer ratios): one thread per refine element routes
@@ -171,23 +173,34 @@ gather_bwd_fast(const FpnParams p, const VecFlags vf) {
     if (s == 0) continue;
     const int W = p.W[l], H = p.H[l];
     const int arg = p.argmax[(((size_t)l * p.B + b) * C + c) * Hr * Wr + (size_t)Y * Wr + X];
-    float* __restrict__ o = static_cast<float*>(p.outs[l]) + (((size_t)b * C + c) * H + (size_t)s * Y) * W + (size_t)s * X;
+    const size_t at0 = (((size_t)b * C + c) * H + (size_t)s * Y) * W + (size_t)s * X;
+    float* __restrict__ o = static_cast<float*>(p.outs[l]) + at0;
+    const float* __restrict__ add = p.addend[l] ? p.addend[l] + at0 : nullptr;
     if (s == 4) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int k = arg - 4 * r;
-        *reinterpret_cast<float4*>(o + (size_t)r * W) =
-            make_float4(k == 0 ? g : 0.f, k == 1 ? g : 0.f, k == 2 ? g : 0.f, k == 3 ? g : 0.f);
+        float4 v = make_float4(k == 0 ? g : 0.f, k == 1 ? g : 0.f, k == 2 ? g : 0.f, k == 3 ? g : 0.f);
+        if (add) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(add + (size_t)r * W));
+          v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        *reinterpret_cast<float4*>(o + (size_t)r * W) = v;
       }
     } else {
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int k = arg - 2 * r;
-        *reinterpret_cast<float2*>(o + (size_t)r * W) = make_float2(k == 0 ? g : 0.f, k == 1 ? g : 0.f);
+        float2 v = make_float2(k == 0 ? g : 0.f, k == 1 ? g : 0.f);
+        if (add) {
+          const float2 t = __ldg(reinterpret_cast<const float2*>(add + (size_t)r * W));
+          v.x += t.x; v.y += t.y;
+        }
+        *reinterpret_cast<float2*>(o + (size_t)r * W) = v;
       }
     }
   }
-  static_cast<float*>(p.outs[p.refine_level])[i] = g;
+  static_cast<float*>(p.outs[p.refine_level])[i] = p.addend[p.refine_level] ? g + __ldg(p.addend[p.refine_level] + i) : g;
 }
 
 // ----------------------------------------------------------------- apply fwd

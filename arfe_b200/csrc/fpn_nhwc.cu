@@ -55,6 +55,16 @@ __device__ __forceinline__ void stv(T* __restrict__ p, const float (&f)[Vec<T>::
   }
 }
 
+// f[] += V consecutive fp32 values at a (a != NULL)
+template <int V>
+__device__ __forceinline__ void add_f32(const float* __restrict__ a, float (&f)[V]) {
+#pragma unroll
+  for (int u = 0; u < V; u += 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(a + u));
+    f[u] += t.x; f[u + 1] += t.y; f[u + 2] += t.z; f[u + 3] += t.w;
+  }
+}
+
 struct Exact { int s[kMaxLevels]; };  // pooling ratio of level l (< refine) if exact, else 0
 
 // ---------------------------------------------------------------- gather fwd
@@ -173,15 +183,19 @@ gather_bwd_cl(const FpnParams p, const Exact ex) {
       arg[u] = q.x; arg[u + 1] = q.y; arg[u + 2] = q.z; arg[u + 3] = q.w;
     }
     T* __restrict__ o = static_cast<T*>(p.outs[l]);
+    const float* __restrict__ add = p.addend[l];
     for (int dy = 0; dy < s; ++dy)
       for (int dx = 0; dx < s; ++dx) {
         const int pos = dy * s + dx;
+        const size_t at = (((size_t)b * H + (size_t)s * Y + dy) * W + (size_t)s * X + dx) * C + c;
         float v[V];
 #pragma unroll
         for (int u = 0; u < V; ++u) v[u] = (arg[u] == pos) ? g[u] : 0.f;
-        stv<T>(o + (((size_t)b * H + (size_t)s * Y + dy) * W + (size_t)s * X + dx) * C + c, v);
+        if (add) add_f32<V>(add + at, v);
+        stv<T>(o + at, v);
       }
   }
+  if (p.addend[p.refine_level]) add_f32<V>(p.addend[p.refine_level] + i * V, g);
   stv<T>(static_cast<T*>(p.outs[p.refine_level]) + i * V, g);
 }
 
@@ -250,6 +264,7 @@ gather_bwd_up_cl(const FpnParams p, const UpLevels ul) {
   }
 #pragma unroll
   for (int u = 0; u < V; ++u) g[u] = __fdiv_rn(g[u], (float)p.L);
+  if (p.addend[l]) add_f32<V>(p.addend[l] + (i - ul.start[j]) * V, g);
   stv<T>(static_cast<T*>(p.outs[l]) + (i - ul.start[j]) * V, g);
 }
 
@@ -436,6 +451,8 @@ cudaError_t launch_fpn_gather_backward_cl(const FpnParams& p, int dtype, unsigne
                                           cudaStream_t stream) {
   const int V = dtype == 0 ? 4 : 8;
   const Exact ex = exact_ratios(p);
+  for (int l = 0; l < p.L; ++l)
+    if (p.addend[l] && !a16(p.addend[l])) return cudaErrorInvalidValue;
   unsigned m = (1u << p.L) - 1u;
   for (int l = 0; l < p.refine_level; ++l)
     if (ex.s[l]) m &= ~(1u << l);
@@ -478,7 +495,7 @@ static cudaError_t launch_apply_cl(const FpnParams& p, int dtype, cudaStream_t s
   if (nv > 4) return cudaErrorInvalidValue;
   // resident CTAs per SM the compiler must allow: the backward is latency-bound, its
   // speed follows occupancy (80 registers: 76 us, 64: 62 us); forward 4 / 2
-  static const int occ_env = [] { const char* ev = getenv("ARFE_APPLY_OCC"); return ev ? atoi(ev) : 0; }();
+  static const int occ_env = ARFE_KNOB_ENV("ARFE_APPLY_OCC", 0);
   const int occ = kBackward ? (occ_env ? occ_env : 4) : 0;
 #define ARFE_APPLY(TT, NV)                                                                         \
   do {                                                                                             \

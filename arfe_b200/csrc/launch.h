@@ -3,11 +3,39 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#ifdef ARFE_PROFILE
+#include <stdlib.h>
+#endif
+
+// Profiling knobs (phase skipping, environment switches) exist only in the
+// -DARFE_PROFILE build (libarfe_b200_prof.so, used by scripts/*knobs*.py).  The
+// shipped library contains neither the skip branches nor a getenv: both macros
+// fold to constants.
+#ifdef ARFE_PROFILE
+#define ARFE_SKIP(p, bits) (((p).debug_skip & (bits)) != 0)
+#define ARFE_KNOB_ENV(name, dflt) ([] { const char* ev_ = getenv(name); return ev_ ? atoi(ev_) : (dflt); }())
+#else
+#define ARFE_SKIP(p, bits) false
+#define ARFE_KNOB_ENV(name, dflt) (dflt)
+#endif
 
 namespace arfe {
 
 constexpr int kMaxLevels = 8;  // == ARFE_MAX_LEVELS
 constexpr int kMaxPool = 32;   // == ARFE_MAX_POOL
+
+// SM count of the CURRENT device (persistent grids are sized from it); cached per device.
+inline int sm_count() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
 
 struct RoiFuseParams {
   const void* feats[kMaxLevels];  // forward: pyramid
@@ -28,7 +56,7 @@ struct RoiFuseParams {
   const int* flag_count;  // ... and how many (device memory)
   long long reg_off[3];  // channels-last out / dout: element offset of region r's block from the base pointer ...
   int bin_stride;        // ... and elements between consecutive bins (concatenated: r * C, R * C)
-  int debug_skip;    // profiling aid (ARFE_FWD_SKIP): 1 compute, 2 staging, 4 write-out, 8 all but setup
+  int debug_skip;    // ARFE_PROFILE builds only (ARFE_FWD_SKIP / ARFE_BWD_SKIP): 1 compute, 2 staging, 4 write-out, 8 all but setup
 };
 
 cudaError_t launch_roi_fuse_forward(const RoiFuseParams& p, int dtype, int layout,
@@ -73,6 +101,7 @@ struct FpnParams {
   void* gathered;         // gather fwd out / gather bwd dout
   uint8_t* argmax;        // gather
   float* dbsf;            // apply bwd
+  const float* addend[kMaxLevels];  // gather bwd: fp32 tensor added to level l's gradient (NULL: none)
 };
 
 bool fpn_cl_ok(const FpnParams& p, int dtype, bool need_feats, bool need_outs);

@@ -144,7 +144,7 @@ roi_fuse_fwd_nchw(const RoiFuseParams p, int opitch) {
     forward_generic<T, false>(p, hd, out_blk);
     return;
   }
-  if (p.debug_skip & 8) return;  // setup only
+  if (ARFE_SKIP(p, 8)) return;  // setup only
   const int H = hd.H, W = hd.W;
   const size_t HW = (size_t)H * W;
   const float inv_count = 1.0f / hd.g.count;
@@ -201,11 +201,11 @@ roi_fuse_fwd_nchw(const RoiFuseParams p, int opitch) {
       for (int c = warp; c < cc; c += nw) {
         const T* __restrict__ plane = fimg + (size_t)(c0 + c) * HW;
         float* __restrict__ dst = win + lane * kPitch + c;
-        if (!(p.debug_skip & 2)) stage_plane_n<T>(niter, plane, dst, goff);
+        if (!ARFE_SKIP(p, 2)) stage_plane_n<T>(niter, plane, dst, goff);
       }
       __syncthreads();
       // ---- compute: one warp per bin column, lane == channel ----
-      if (lane < cc && !(p.debug_skip & 1)) {
+      if (lane < cc && !ARFE_SKIP(p, 1)) {
         float* __restrict__ outs_lane = opitch > 0 ? outs + lane * opitch : nullptr;
         for (int pw = warp; pw < PW; pw += nw) {
           const int4 d = bd.pw[pw];
@@ -238,7 +238,7 @@ roi_fuse_fwd_nchw(const RoiFuseParams p, int opitch) {
         }
       }
       __syncthreads();
-      if (opitch > 0 && !(p.debug_skip & 4)) {
+      if (opitch > 0 && !ARFE_SKIP(p, 4)) {
         // ---- coalesced write: per channel a run of `run` floats at bin ph0*PW ----
         T* __restrict__ dst = out_blk + (size_t)c0 * PHW + ph0 * PW;
         for (int c = warp; c < cc; c += nw)

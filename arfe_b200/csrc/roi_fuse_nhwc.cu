@@ -1007,7 +1007,7 @@ roi_fuse_fwd_ring(const RoiFuseParams p, const PullWs ws, int ncons, int ring_by
           const uint32_t off = head + (uint32_t)lane * bytes;
           const unsigned char* __restrict__ rsrc = src + (size_t)(rr + lane) * src_step;
           stage_off[slot] = off;
-          if (p.debug_skip & 2) {  // profiling aid: no copies
+          if (ARFE_SKIP(p, 2)) {  // profiling aid: no copies
             mbar_arrive(full + slot);
           } else {
             mbar_arrive_expect_tx(full + slot, bytes);
@@ -1050,7 +1050,7 @@ roi_fuse_fwd_ring(const RoiFuseParams p, const PullWs ws, int ncons, int ring_by
       FwdPipe pipe{full, empty, stage_off, ring};
 #define ARFE_CONSUME(NCC) \
   fwd_consume_rows<T, PH, NCC, NCH>(pipe, stage, nrows, nblk, tb.rowtab, wxp, tap0, C, o, (size_t)PW * BS)
-      switch ((p.debug_skip & 1) ? 0 : nc) {  // profiling aid: 0 taps == no math
+      switch (ARFE_SKIP(p, 1) ? 0 : nc) {  // profiling aid: 0 taps == no math
         case 0: ARFE_CONSUME(0); break;
         case 1: ARFE_CONSUME(1); break;
         case 2: ARFE_CONSUME(2); break;
@@ -1461,7 +1461,7 @@ __device__ __forceinline__ void pull_consume_tile(const RoiFuseParams& p, const 
     mbar_wait(ctl.full + slot, (stage / kNSlot) & 1);
     const StageDesc& d = desc[slot];
     const int4 rd = d.rows[warp];
-    if (act && rd.x >= 0 && !(p.debug_skip & 1)) {  // (profiling aid: no math)
+    if (act && rd.x >= 0 && !ARFE_SKIP(p, 1)) {  // (profiling aid: no math)
       const int npw = d.npw;
       const float a0 = __int_as_float(rd.z), a1 = __int_as_float(rd.w);
       const uint64_t a0p = pack2(a0, a0), a1p = pack2(a1, a1);
@@ -1612,10 +1612,10 @@ roi_bwd_pull_tma(const RoiFuseParams p, const PullWs ws, const TileMap tm4, cons
         unsigned char* const dst = sub + off;
         if (lane == 0) {
           ctl.stage_off[slot] = (uint32_t)(dst - ring);
-          mbar_arrive_expect_tx(ctl.full + slot, ((p.debug_skip & 2) ? 0u : bytes) + kDescBytes);
+          mbar_arrive_expect_tx(ctl.full + slot, (ARFE_SKIP(p, 2) ? 0u : bytes) + kDescBytes);
           bulk_g2s(desc + slot, gdesc + i, kDescBytes, ctl.full + slot);
         }
-        if (p.debug_skip & 2) {
+        if (ARFE_SKIP(p, 2)) {
           // profiling aid: no bin copies
         } else if ((uint32_t)BS * sizeof(T) == bin_bytes) {
           // split layout, all channels in this group: the npw bins of a bin row are
@@ -1856,7 +1856,7 @@ cudaError_t launch_roi_fuse_forward_cl(const RoiFuseParams& p, int dtype, int ou
     if (bpp > PHW) bpp = PHW;
     smem += bpp * opitch * 4;
   }
-  static const int occ = [] { const char* e = getenv("ARFE_FWD_OCC"); return e ? atoi(e) : 3; }();
+  static const int occ = ARFE_KNOB_ENV("ARFE_FWD_OCC", 3);
 #define ARFE_FWD_CL1(TT, OC, OCC)                                                       \
   do {                                                                                  \
     if ((e = set_smem(roi_fuse_fwd_cl<TT, OC, OCC>, smem)) != cudaSuccess) return e;    \
@@ -1898,7 +1898,7 @@ cudaError_t launch_roi_fuse_forward_plan(const RoiFuseParams& p0, int dtype, voi
   if (need > workspace_bytes) return cudaErrorInvalidValue;
   const int V = dtype == 0 ? 4 : 8, elt = dtype == 0 ? 4 : 2;
   // consumer warp == (output column, channel chunk pair | chunk)
-  static const int nch_env = [] { const char* ev = getenv("ARFE_FWD_NCH"); return ev ? atoi(ev) : 0; }();
+  static const int nch_env = ARFE_KNOB_ENV("ARFE_FWD_NCH", 0);
   const int nch = (p.C % (64 * V) == 0 && p.PH * V * 2 <= 64 && nch_env != 1) ? 2 : 1;
   const int ncons = p.PW * ((p.C + 32 * V * nch - 1) / (32 * V * nch));
   const bool ring_ok = (p.PH == 7 || p.PH == 14) && p.PH * V <= 64 && ncons <= (nch == 2 ? 7 : 14);
@@ -1913,12 +1913,10 @@ cudaError_t launch_roi_fuse_forward_plan(const RoiFuseParams& p0, int dtype, voi
   if ((stages & 1) && (e = launch_prep(p, ws, stream)) != cudaSuccess) return e;
   if (!(stages & 2)) return cudaSuccess;
   if (!ring_ok) return launch_roi_fuse_forward_cl(p, dtype, 1, stream);
-  static const int sms = [] {
-    int dev = 0, n = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n;
-  }();
+  // plan built earlier (plan_ready): the ring kernel's work counter is the only state a forward
+  // consumes, so the same plan serves any number of forward calls
+  if (!(stages & 1) && (e = cudaMemsetAsync(ws.counters + 5, 0, 4, stream)) != cudaSuccess) return e;
+  const int sms = sm_count();
   const int pgrid = N < per_sm * sms ? N : per_sm * sms;
   const int smem = fixed + ring;
 #define ARFE_FWD_RING(TT, PHH, NCHH, NTT)                                                             \
@@ -1972,7 +1970,7 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
   const int V = dtype == 0 ? 4 : 8;
   // fp32: a CTA takes 2 x 128 channels when C allows (1 KB bin pieces: half the bulk
   // copies and stages of the 128-channel variant)
-  static const int nv_env = [] { const char* ev = getenv("ARFE_PULL_NV"); return ev ? atoi(ev) : 0; }();
+  static const int nv_env = ARFE_KNOB_ENV("ARFE_PULL_NV", 0);
   const int nv = (dtype == 0 && p.C % (64 * V) == 0 && nv_env != 1) ? 2 : 1;
   TileMap tm[2];
   int ntiles[2];
@@ -2007,18 +2005,13 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
   const int per_sm = (dtype == 0 && nv == 1) ? 3 : 2;
   // two producer warps (each owning half of a slightly larger ring) when the largest
   // possible stage fits one half
-  static const int np_env = [] { const char* ev = getenv("ARFE_PULL_NP"); return ev ? atoi(ev) : 0; }();
+  static const int np_env = ARFE_KNOB_ENV("ARFE_PULL_NP", 0);
   const int max_stage = (p.PH < kMaxPh ? p.PH : kMaxPh) * (p.PW < kJ ? p.PW : kJ) * 32 * V * nv * (dtype == 0 ? 4 : 2);
   const int np = (per_sm == 2 && max_stage <= 52 * 1024 && np_env != 1) ? 2 : 1;
   const int ring = per_sm == 3 ? 64 * 1024 : (np == 2 ? 104 * 1024 : 96 * 1024);
   const int smem = kPullCtl + kNSlot * kDescBytes + ring;
   const int nb4 = ntiles[0] * tm[0].groups, nb8 = ntiles[1] * tm[1].groups;
-  static const int sms = [] {
-    int dev = 0, n = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n;
-  }();
+  const int sms = sm_count();
   const int pgrid = nb4 + nb8 < per_sm * sms ? nb4 + nb8 : per_sm * sms;
 #define ARFE_PULL(TT, NVV, NPP)                                                                     \
   do {                                                                                              \

@@ -34,6 +34,70 @@ def _vec_ok(C, dtype):
     return C % (4 if dtype == torch.float32 else 8) == 0
 
 
+_GEO = {}
+
+
+def _geo(Hs, Ws, scales):
+    """ctypes copies of the level sizes / scales, built once per pyramid geometry."""
+    key = (tuple(Hs), tuple(Ws), tuple(float(s) for s in scales))
+    g = _GEO.get(key)
+    if g is None:
+        if len(_GEO) > 64:
+            _GEO.clear()
+        g = _GEO[key] = (L.int_array(Hs), L.int_array(Ws), L.float_array(scales))
+    return g
+
+
+_SIDE = {}
+
+
+def _side_stream(device):
+    s = _SIDE.get(device.index)
+    if s is None:
+        s = _SIDE[device.index] = torch.cuda.Stream(device)
+    return s
+
+
+class _Plan:
+    """RoI plan of one forward (region tables in a device workspace) and, when a
+    backward will follow, the pull kernel's tile bins -- built on a side stream
+    while the forward kernels run on the caller's stream; the backward joins on
+    `ev_bin` (plan_ready = 2)."""
+
+    def __init__(self, geo_args, K, regions, nlev, B, Hs_c, Ws_c, device, need_bins, split):
+        lib = L.lib()
+        self.nbytes = lib.arfe_roi_plan_bytes(K, regions, nlev, B, Hs_c, Ws_c)
+        self.ws = torch.empty(self.nbytes + 256, dtype=torch.uint8, device=device)
+        self.ptr = (self.ws.data_ptr() + 255) // 256 * 256
+        self.ev_bin = None
+        main = torch.cuda.current_stream(device)
+        L.check(lib.arfe_roi_plan_build(*geo_args, self.ptr, self.nbytes, c_stream(main)),
+                "arfe_roi_plan_build")
+        if need_bins and not torch.cuda.is_current_stream_capturing():
+            side = _side_stream(device)
+            ev_plan = torch.cuda.Event()
+            ev_plan.record(main)
+            side.wait_event(ev_plan)
+            self.ws.record_stream(side)
+            L.check(lib.arfe_roi_pull_bin(*geo_args, int(split), self.ptr, self.nbytes, c_stream(side)),
+                    "arfe_roi_pull_bin")
+            self.ev_bin = torch.cuda.Event()
+            self.ev_bin.record(side)
+
+    def ready_for_backward(self, device):
+        """plan_ready code for the backward: 2 = plan and bins are there (after joining the
+        side stream), 1 = plan only."""
+        if self.ev_bin is None:
+            return 1
+        torch.cuda.current_stream(device).wait_event(self.ev_bin)
+        return 2
+
+
+def c_stream(stream):
+    import ctypes
+    return ctypes.c_void_p(stream.cuda_stream)
+
+
 class _RoIFuseFunction(Function):
     """Fused region generation + level map + multi-level RoIAlign (+ cat).
 
@@ -62,25 +126,25 @@ class _RoIFuseFunction(Function):
                     finest_scale, layout, dt, B, C, Hs, Ws, feats[0].dtype, fast)
         ctx.save_for_backward(rois)
         ctx.plan = None
+        Hs_c, Ws_c, sc_c = _geo(Hs, Ws, spatial_scales)
         if K > 0 and out_cl:
             # channels-last in and out: plan + ring kernel; the plan (region tables in
-            # a device workspace) is kept for the backward
-            nbytes = L.lib().arfe_roi_plan_bytes(K, regions, len(feats), B, L.int_array(Hs),
-                                                 L.int_array(Ws))
-            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=out.device)
-            ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+            # a device workspace) is kept for the backward, whose tile bins are built on
+            # a side stream while the forward runs
+            need_bwd = any(f.requires_grad for f in feats)
+            geo_args = (Hs_c, Ws_c, sc_c, len(feats), B, C, rois.data_ptr(), K, regions, float(facs),
+                        oh, ow, int(sample_num), float(finest_scale), dt)
+            plan = _Plan(geo_args, K, regions, len(feats), B, Hs_c, Ws_c, out.device, need_bwd, False)
             rc = L.lib().arfe_roi_fuse_forward_plan(
-                L.ptr_array(feats), L.int_array(Hs), L.int_array(Ws),
-                L.float_array(spatial_scales), len(feats), B, C, rois.data_ptr(),
+                L.ptr_array(feats), Hs_c, Ws_c, sc_c, len(feats), B, C, rois.data_ptr(),
                 K, regions, float(facs), oh, ow, int(sample_num), float(finest_scale), dt,
-                out.data_ptr(), None, None, ws_ptr, nbytes, 0, L.stream_ptr(out.device))
+                out.data_ptr(), None, None, plan.ptr, plan.nbytes, 1, L.stream_ptr(out.device))
             L.check(rc, "arfe_roi_fuse_forward_plan")
-            if any(f.requires_grad for f in feats):
-                ctx.plan = (ws, ws_ptr, nbytes)
+            if need_bwd:
+                ctx.plan = plan
         elif K > 0:
             rc = L.lib().arfe_roi_fuse_forward(
-                L.ptr_array(feats), L.int_array(Hs), L.int_array(Ws),
-                L.float_array(spatial_scales), len(feats), B, C, rois.data_ptr(),
+                L.ptr_array(feats), Hs_c, Ws_c, sc_c, len(feats), B, C, rois.data_ptr(),
                 K, regions, float(facs), oh, ow, int(sample_num),
                 float(finest_scale), dt, layout, L.ARFE_NHWC if out_cl else L.ARFE_NCHW,
                 out.data_ptr(), None, None, L.stream_ptr(out.device))
@@ -104,18 +168,19 @@ class _RoIFuseFunction(Function):
         if fast and K > 0:
             # pull kernel: channels-last dout, every gradient element written once
             g = g.contiguous(memory_format=torch.channels_last)
+            Hs_c, Ws_c, sc_c = _geo(Hs, Ws, scales)
             if ctx.plan is not None:
-                ws, ws_ptr, nbytes = ctx.plan
-                ready = 1
+                ws, ws_ptr, nbytes = ctx.plan.ws, ctx.plan.ptr, ctx.plan.nbytes
+                ready = ctx.plan.ready_for_backward(dev)
             else:
-                nbytes = lib.arfe_roi_plan_bytes(K, regions, nlev, B, L.int_array(Hs), L.int_array(Ws))
+                nbytes = lib.arfe_roi_plan_bytes(K, regions, nlev, B, Hs_c, Ws_c)
                 ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
                 ws_ptr = (ws.data_ptr() + 255) // 256 * 256
                 ready = 0
             dfeats = [torch.empty((B, C, Hs[l], Ws[l]), dtype=torch.float32, device=dev,
                                   memory_format=torch.channels_last) for l in range(nlev)]
             rc = lib.arfe_roi_fuse_backward_pull(
-                g.data_ptr(), L.int_array(Hs), L.int_array(Ws), L.float_array(scales), nlev, B,
+                g.data_ptr(), Hs_c, Ws_c, sc_c, nlev, B,
                 C, rois.data_ptr(), K, regions, float(facs), oh, ow, int(sample_num),
                 float(finest_scale), dt, L.ptr_array(dfeats), ws_ptr, nbytes, ready,
                 L.stream_ptr(dev))
@@ -176,16 +241,18 @@ class _RoIFuseSplitFunction(Function):
         ctx.plan = None
         if K > 0:
             lib = L.lib()
-            nbytes = lib.arfe_roi_plan_bytes(K, regions, len(feats), B, L.int_array(Hs), L.int_array(Ws))
-            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
-            ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+            Hs_c, Ws_c, sc_c = _geo(Hs, Ws, spatial_scales)
+            need_bwd = any(f.requires_grad for f in feats)
+            geo_args = (Hs_c, Ws_c, sc_c, len(feats), B, C, rois.data_ptr(), K, regions, float(facs),
+                        oh, ow, int(sample_num), float(finest_scale), dt)
+            plan = _Plan(geo_args, K, regions, len(feats), B, Hs_c, Ws_c, dev, need_bwd, True)
             rc = lib.arfe_roi_fuse_forward_plan_split(
-                L.ptr_array(feats), L.int_array(Hs), L.int_array(Ws), L.float_array(spatial_scales),
-                len(feats), B, C, rois.data_ptr(), K, regions, float(facs), oh, ow, int(sample_num),
-                float(finest_scale), dt, L.ptr_array(outs), ws_ptr, nbytes, 0, L.stream_ptr(dev))
+                L.ptr_array(feats), Hs_c, Ws_c, sc_c, len(feats), B, C, rois.data_ptr(), K, regions,
+                float(facs), oh, ow, int(sample_num), float(finest_scale), dt, L.ptr_array(outs),
+                plan.ptr, plan.nbytes, 1, L.stream_ptr(dev))
             L.check(rc, "arfe_roi_fuse_forward_plan_split")
-            if any(f.requires_grad for f in feats):
-                ctx.plan = (ws, ws_ptr, nbytes)
+            if need_bwd:
+                ctx.plan = plan
         return tuple(outs)
 
     @staticmethod
@@ -209,16 +276,17 @@ class _RoIFuseSplitFunction(Function):
         dfeats = [torch.empty((B, C, Hs[l], Ws[l]), dtype=torch.float32, device=dev,
                               memory_format=torch.channels_last) for l in range(nlev)]
         if K > 0:
+            Hs_c, Ws_c, sc_c = _geo(Hs, Ws, scales)
             if ctx.plan is not None:
-                ws, ws_ptr, nbytes = ctx.plan
-                ready = 1
+                ws, ws_ptr, nbytes = ctx.plan.ws, ctx.plan.ptr, ctx.plan.nbytes
+                ready = ctx.plan.ready_for_backward(dev)
             else:
-                nbytes = lib.arfe_roi_plan_bytes(K, regions, nlev, B, L.int_array(Hs), L.int_array(Ws))
+                nbytes = lib.arfe_roi_plan_bytes(K, regions, nlev, B, Hs_c, Ws_c)
                 ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
                 ws_ptr = (ws.data_ptr() + 255) // 256 * 256
                 ready = 0
             rc = lib.arfe_roi_fuse_backward_pull_split(
-                L.ptr_array(gs), L.int_array(Hs), L.int_array(Ws), L.float_array(scales), nlev, B, C,
+                L.ptr_array(gs), Hs_c, Ws_c, sc_c, nlev, B, C,
                 rois.data_ptr(), K, regions, float(facs), oh, ow, int(sample_num), float(finest_scale),
                 dt, L.ptr_array(dfeats), ws_ptr, nbytes, ready, L.stream_ptr(dev))
             L.check(rc, "arfe_roi_fuse_backward_pull_split")
@@ -350,52 +418,74 @@ def split3(x, c):
     return _Split3.apply(x, c)
 
 
+def _gate_rows(t):
+    """How the gate kernel can walk a [K, C, H, W] tensor in place:
+    ("nchw", rows=K, n=C*H*W, row stride) when every RoI's block is NCHW-dense
+    (a channel slice of the NCHW cat tensor qualifies), ("nhwc", rows=K*H*W,
+    n=C, bin stride) when it is channels-last with a uniform bin stride (a
+    region tensor of roi_fuse_split, or a channel slice of the channels-last
+    cat tensor), else None.  Holds for K == 1 too (stride(0) is then free)."""
+    if t.dim() != 4:
+        return None
+    K, C, H, W = t.shape
+    s0, s1, s2, s3 = t.stride()
+    inner_nchw = (C == 1 or s1 == H * W) and (H == 1 or s2 == W) and (W == 1 or s3 == 1)
+    if inner_nchw and (K == 1 or s0 >= C * H * W):
+        return "nchw", K, C * H * W, (s0 if K > 1 else C * H * W)
+    cs = s3 if W > 1 else (s2 if H > 1 else (s0 if K > 1 else C))  # elements between consecutive bins
+    inner_nhwc = (C == 1 or s1 == 1) and (W == 1 or s3 == cs) and (H == 1 or s2 == W * cs) and cs >= C
+    if inner_nhwc and (K == 1 or s0 == H * W * cs):
+        return "nhwc", K * H * W, C, cs
+    return None
+
+
 class _RFFGateFunction(Function):
-    """out = ori + ori*(a+b), multirois_bbox_head.py:175,182."""
+    """out = ori + ori*(a+b), multirois_bbox_head.py:175,182.  ori is read in
+    place from wherever it lives (a slice of the cat tensor or a region tensor
+    of its own); a, b, out and the gradients follow its memory layout."""
 
     @staticmethod
     def forward(ctx, ori, a, b):
         L.require_cuda(ori, a, b)
         dt = L.dtype_code(ori)
-        K = ori.size(0)
-        n = 1
-        for d in ori.shape[1:]:
-            n *= int(d)
-        # ori may be a channel slice of the concatenated tensor: rows strided
-        if K > 1 and not ori[0].is_contiguous():
+        view = _gate_rows(ori)
+        if view is None:
             ori = ori.contiguous()
-        stride = ori.stride(0) if K > 1 else n
-        if stride < n:
-            ori = ori.contiguous()
-            stride = n
-        a = a.contiguous()
-        b = b.contiguous()
-        out = torch.empty(ori.shape, dtype=ori.dtype, device=ori.device)
-        if K > 0:
+            view = _gate_rows(ori) or ("nchw", ori.size(0), ori[0].numel() if ori.size(0) else 1,
+                                       ori[0].numel() if ori.size(0) else 1)
+        kind, rows, n, stride = view
+        mf = torch.channels_last if kind == "nhwc" else torch.contiguous_format
+        dense = (lambda t: t.to(ori.dtype).contiguous(memory_format=mf)) if ori.dim() == 4 else \
+            (lambda t: t.to(ori.dtype).contiguous())
+        a_in, b_in = a, b
+        a, b = dense(a), dense(b)
+        out = torch.empty(ori.shape, dtype=ori.dtype, device=ori.device,
+                          **({"memory_format": mf} if ori.dim() == 4 else {}))
+        if rows > 0:
             rc = L.lib().arfe_rff_gate_forward(
                 ori.data_ptr(), stride, a.data_ptr(), b.data_ptr(),
-                out.data_ptr(), K, n, dt, L.stream_ptr(ori.device))
+                out.data_ptr(), rows, n, dt, L.stream_ptr(ori.device))
             L.check(rc, "arfe_rff_gate_forward")
         ctx.save_for_backward(ori, a, b)
-        ctx.meta = (stride, n, dt)
+        ctx.meta = (rows, n, stride, dt, mf, a_in.dtype, b_in.dtype)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
         ori, a, b = ctx.saved_tensors
-        stride, n, dt = ctx.meta
-        K = ori.size(0)
-        g = g.contiguous()
-        d_ori = torch.empty(ori.shape, dtype=ori.dtype, device=ori.device)
-        d_ab = torch.empty(ori.shape, dtype=ori.dtype, device=ori.device)
-        if K > 0:
+        rows, n, stride, dt, mf, a_dtype, b_dtype = ctx.meta
+        kw = {"memory_format": mf} if ori.dim() == 4 else {}
+        g = g.to(ori.dtype).contiguous(**kw)
+        d_ori = torch.empty(ori.shape, dtype=ori.dtype, device=ori.device, **kw)
+        d_ab = torch.empty(ori.shape, dtype=ori.dtype, device=ori.device, **kw)
+        if rows > 0:
             rc = L.lib().arfe_rff_gate_backward(
                 g.data_ptr(), ori.data_ptr(), stride, a.data_ptr(), b.data_ptr(),
-                d_ori.data_ptr(), n, d_ab.data_ptr(), K, n, dt,
+                d_ori.data_ptr(), n, d_ab.data_ptr(), rows, n, dt,
                 L.stream_ptr(g.device))
             L.check(rc, "arfe_rff_gate_backward")
-        return d_ori, d_ab, d_ab
+        return d_ori, d_ab.to(a_dtype), d_ab.to(b_dtype)
 
 
 def rff_gate(ori, a, b):

@@ -19,17 +19,17 @@ class RoIAlign(nn.Module):
         self.spatial_scale = float(spatial_scale)
         self.aligned = aligned
         self.sample_num = int(sample_num)
+        # kept as an attribute for config / repr compatibility (roi_align.py:110-124 of the
+        # reference); there is one implementation here, so asking for another one is an error
         self.use_torchvision = use_torchvision
-        assert not (use_torchvision and aligned), \
-            'Torchvision does not support aligned RoIAlgin'
+        if use_torchvision:
+            raise NotImplementedError(
+                'use_torchvision=True selects torchvision.ops.roi_align in the reference; '
+                'arfe_b200 has a single implementation (libarfe_b200.so) and no library fallback')
 
     def forward(self, features, rois):
         """features: NCHW (or channels_last) map; rois: [K,5] (idx,x1,y1,x2,y2)."""
         assert rois.dim() == 2 and rois.size(1) == 5
-        if self.use_torchvision:
-            from torchvision.ops import roi_align as tv_roi_align
-            return tv_roi_align(features, rois, self.out_size,
-                                self.spatial_scale, self.sample_num)
         return roi_align(features, rois, self.out_size, self.spatial_scale,
                          self.sample_num, self.aligned)
 

@@ -79,23 +79,25 @@ class SingleRoIExtractor(nn.Module):
         out_size, sample_num, scales = self._layer_args()
         feats, half = self._cast_in(feats)
         num_levels = len(feats)
-        if roi_scale_factor is not None:
-            rois = self.roi_rescale(rois, roi_scale_factor)
-        if lvl is None and replace_rois is None:
+        if roi_scale_factor is None and lvl is None and replace_rois is None:
             out = roi_fuse(feats, rois, out_size, scales[:num_levels], sample_num,
                            regions=1, finest_scale=self.finest_scale,
                            out_channels_last=self.roi_feats_channels_last)
         else:
-            # hook path (unused by ARFE's configs): levels from torch ops, one
-            # single-level launch of the same kernel per level
+            # hook path (unused by ARFE's configs): the reference's order of operations,
+            # single_level.py:118-152 -- levels from the ORIGINAL rois (or replace_rois),
+            # shifted by lvl, and only then the rescale of the boxes that are sampled;
+            # one single-level launch of the same kernel per level
             out = feats[0].new_zeros(rois.size(0), self.out_channels, *out_size)
-            if num_levels == 1:
+            if num_levels == 1:  # :121-124 returns before the rescale
                 out = self.roi_layers[0](feats[0], rois) if len(rois) else out
             else:
                 src = replace_rois if replace_rois is not None else rois
                 target = self.map_roi_levels(src, num_levels)
                 if lvl is not None:
                     target = (target + lvl).clamp(min=0, max=num_levels - 1).long()
+                if roi_scale_factor is not None:
+                    rois = self.roi_rescale(rois, roi_scale_factor)
                 for i in range(num_levels):
                     inds = target == i
                     if inds.any():

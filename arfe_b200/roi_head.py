@@ -40,8 +40,10 @@ class StandardRoIHead(nn.Module):
     def _bbox_forward(self, x, rois):
         ext = self.bbox_roi_extractor
         bbox_feats = ext.forward_regions(x[:ext.num_inputs], rois, regions=3,
-                                         facs=self.facs)
-        cls_score, bbox_pred = self.bbox_head(bbox_feats)
+                                         facs=getattr(self, 'facs', 1))
+        if getattr(self, 'with_shared_head', False):
+            bbox_feats = self.shared_head(bbox_feats)
+        cls_score, bbox_pred = self.bbox_head(bbox_feats)[:2]
         return dict(cls_score=cls_score, bbox_pred=bbox_pred, bbox_feats=bbox_feats)
 
 
@@ -64,6 +66,6 @@ class CascadeRoIHead(nn.Module):
     def _bbox_forward(self, stage, x, rois):
         ext, head = self.bbox_roi_extractor[stage], self.bbox_head[stage]
         bbox_feats = ext.forward_regions(x[:ext.num_inputs], rois, regions=3,
-                                         facs=self.facs)
-        cls_score, bbox_pred = head(bbox_feats)
+                                         facs=getattr(self, 'facs', 1))
+        cls_score, bbox_pred = head(bbox_feats)[:2]
         return dict(cls_score=cls_score, bbox_pred=bbox_pred, bbox_feats=bbox_feats)

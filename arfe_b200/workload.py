@@ -33,10 +33,14 @@ def pyramid_shapes(img_h=800, img_w=1344, strides=STRIDES):
     return shapes
 
 
-def synthetic_rois(K, img_w=1344, img_h=800, batch=1, seed=0, smin=16.0, smax=600.0):
+def synthetic_rois(K, img_w=1344, img_h=800, batch=1, seed=0, smin=16.0, smax=600.0,
+                   order="image_major"):
     """centre uniform, sqrt(area) log-uniform in
-    [16,600] px, aspect log-uniform in [0.5,2], clipped; RoI i belongs to
-    image i % batch (same generator as oracle.synthetic_rois)."""
+    [16,600] px, aspect log-uniform in [0.5,2], clipped (same generator as
+    oracle.synthetic_rois).  order="image_major": per-image blocks, the order
+    bbox2roi builds (mmdet/core/bbox/transforms.py:51-59: one block of
+    (img_id, x1, y1, x2, y2) rows per image, torch.cat); "interleaved": RoI i
+    belongs to image i % batch (kept as a correctness case)."""
     g = torch.Generator().manual_seed(seed)
     u = torch.rand(K, 4, generator=g)
     cx, cy = u[:, 0] * img_w, u[:, 1] * img_h
@@ -47,30 +51,44 @@ def synthetic_rois(K, img_w=1344, img_h=800, batch=1, seed=0, smin=16.0, smax=60
     y1 = (cy - h / 2).clamp(0, img_h - 1)
     x2 = torch.max((cx + w / 2).clamp(0, img_w - 1), x1 + 1.0)
     y2 = torch.max((cy + h / 2).clamp(0, img_h - 1), y1 + 1.0)
-    b = (torch.arange(K) % batch).float()
+    if order == "image_major":
+        b = ((torch.arange(K) * batch) // max(K, 1)).float()
+    elif order == "interleaved":
+        b = (torch.arange(K) % batch).float()
+    else:
+        raise ValueError(f"unknown RoI order {order!r}")
     return torch.stack([b, x1, y1, x2, y2], dim=1).float().contiguous()
 
 
 def host_inputs(batch=2, rois_per_img=512, channels=256, img_h=800, img_w=1344,
                 dtype=torch.float32, seed=0, pin=False, channels_last=False, strides=STRIDES,
-                out_size=7):
+                out_size=7, roi_order="image_major", smin=16.0, smax=600.0, device=None):
     """Synthetic inputs of one step on the HOST (optionally pinned; optionally
-    stored in torch.channels_last memory format -- same logical tensors)."""
+    stored in torch.channels_last memory format -- same logical tensors).
+    device: generate the dense tensors there instead (large sweeps: no host copy
+    to make; the RoIs always come from the seeded host generator)."""
     shapes = pyramid_shapes(img_h, img_w, strides)
-    g = torch.Generator().manual_seed(seed)
+    g = torch.Generator(device=device).manual_seed(seed) if device is not None else \
+        torch.Generator().manual_seed(seed)
     K = batch * rois_per_img
     hr, wr = shapes[2]
+
+    def randn(*shape):
+        return torch.randn(*shape, generator=g, device=device)
     t = {}
-    t["x"] = [torch.randn(batch, channels, h, w, generator=g).to(dtype) for h, w in shapes]
-    t["bsf"] = torch.randn(batch, channels, hr, wr, generator=g).to(dtype)
-    t["g1"] = [torch.randn(batch, 1, h, w, generator=g).to(dtype) for h, w in shapes]
-    t["g2"] = [torch.randn(batch, 1, h, w, generator=g).to(dtype) for h, w in shapes]
-    t["rois"] = synthetic_rois(K, img_w, img_h, batch, seed)
+    t["x"] = [randn(batch, channels, h, w).to(dtype) for h, w in shapes]
+    t["bsf"] = randn(batch, channels, hr, wr).to(dtype)
+    t["g1"] = [randn(batch, 1, h, w).to(dtype) for h, w in shapes]
+    t["g2"] = [randn(batch, 1, h, w).to(dtype) for h, w in shapes]
+    t["rois"] = synthetic_rois(K, img_w, img_h, batch, seed, smin=smin, smax=smax, order=roi_order)
     P = out_size
-    t["a"] = torch.randn(K, channels, P, P, generator=g).relu().to(dtype)
-    t["b"] = torch.randn(K, channels, P, P, generator=g).relu().to(dtype)
-    t["gz"] = torch.randn(K, channels, P, P, generator=g).to(dtype)      # dL/d(gate out)
-    t["gbsf"] = torch.randn(batch, channels, hr, wr, generator=g).to(dtype)  # dL/d(gathered)
+    t["a"] = randn(K, channels, P, P).relu().to(dtype)
+    t["b"] = randn(K, channels, P, P).relu().to(dtype)
+    t["gz"] = randn(K, channels, P, P).to(dtype)      # dL/d(gate out)
+    # dL/d(lw), dL/d(lh): what the backward of the two context-branch convs (PyTorch) hands back
+    t["glw"] = randn(K, channels, P, P).to(dtype)
+    t["glh"] = randn(K, channels, P, P).to(dtype)
+    t["gbsf"] = randn(batch, channels, hr, wr).to(dtype)  # dL/d(gathered)
     if channels_last:
         def cl(v):
             if isinstance(v, list):
@@ -95,11 +113,15 @@ class TrainStep:
     memory layout through the compatibility kernels.
     """
 
-    def __init__(self, host, device, regions=3, channels_last=True, split=None):
+    def __init__(self, host, device, regions=3, channels_last=True, split=None, roi_levels=4):
         """split (channels-last only, default on): the region features and their
         gradients are separate tensors (ori | lw | lh) instead of one concatenated
         tensor -- what the head's convolutions produce / consume -- so the step
-        needs no torch copies between our kernels."""
+        needs no torch copies between our kernels.
+        roi_levels: pyramid levels the RoI extractor reads -- the reference's
+        bbox_roi_extractor has featmap_strides=[4, 8, 16, 32]
+        (configs/_base_/models/faster_rcnn_r50_fpn.py:44) and is handed
+        x[:num_inputs] (standard_roi_head.py:140); the 5th level only feeds the RPN."""
         self.dev = device
         self.lib = L.lib()
         x = host["x"]
@@ -113,6 +135,7 @@ class TrainStep:
         self.B, self.C = x[0].shape[:2]
         self.shapes = host["shapes"]
         self.nlev = len(x)
+        self.rlev = min(int(roi_levels), self.nlev)
         self.K = host["rois"].shape[0]
         self.R = regions
         self.P = host.get("out_size", 7)
@@ -126,6 +149,7 @@ class TrainStep:
             return v.contiguous(memory_format=mf) if v.dim() == 4 else v
         self.x, self.bsf, self.g1, self.g2 = d(host["x"]), d(host["bsf"]), d(host["g1"]), d(host["g2"])
         self.rois, self.a, self.b, self.gz, self.gbsf = (d(host[k]) for k in ("rois", "a", "b", "gz", "gbsf"))
+        self.glw, self.glh = d(host["glw"]), d(host["glh"])
         B, C, K, R = self.B, self.C, self.K, self.R
         hr, wr = self.shapes[2]
 
@@ -145,16 +169,19 @@ class TrainStep:
         if self.split:
             self.Fr = [e(K, C, P, P) for _ in range(R)]
             self.p_Fr = L.ptr_array(self.Fr)
-            # stand-ins for the conv backward of the two context branches: d_ab for both
-            self.p_dFr = L.ptr_array([self.d_ori] + [self.d_ab] * (R - 1))
+            # d_ori from the gate backward; d_lw / d_lh stand in for the backward of the two
+            # context-branch convs (PyTorch, out of the path): tensors of their own
+            self.p_dFr = L.ptr_array([self.d_ori, self.glw, self.glh][:R])
         self.dy = [e(B, C, h, w, dtype=torch.float32) for h, w in self.shapes]
+        for t in self.dy[self.rlev:]:
+            t.zero_()  # levels the RoI head does not read: no gradient from this path, never rewritten
         self.dy_in = self.dy if self.dtype == torch.float32 else [e(B, C, h, w) for h, w in self.shapes]
         self.dbsf = e(B, C, hr, wr, dtype=torch.float32)
         self.dg1 = [e(B, 1, h, w, dtype=torch.float32) for h, w in self.shapes]
         self.dg2 = [e(B, 1, h, w, dtype=torch.float32) for h, w in self.shapes]
         self.dx = [e(B, C, h, w) for h, w in self.shapes]
         self.ws_bytes = self.lib.arfe_roi_plan_bytes(
-            K, R, self.nlev, B, L.int_array([s[0] for s in self.shapes]),
+            K, R, self.rlev, B, L.int_array([s[0] for s in self.shapes]),
             L.int_array([s[1] for s in self.shapes]))
         self.ws = torch.empty(self.ws_bytes + 256, dtype=torch.uint8, device=device)
         self.ws_ptr = (self.ws.data_ptr() + 255) // 256 * 256
@@ -190,7 +217,7 @@ class TrainStep:
             self.p_x, self.bsf.data_ptr(), self.p_g1, self.p_g2, self.H, self.W, self.nlev,
             self.B, self.C, hr, wr, self.dt, self.layout, self.p_y, self.stream)
 
-    def plan_async(self):
+    def plan_async(self, bins=True):
         """The RoI plan depends only on the RoIs, the backward's tile bins only on
         the plan: build both on a second stream, under the AR-FPN kernels of the
         forward (latency-bound table walking next to bandwidth-bound streaming)."""
@@ -201,14 +228,16 @@ class TrainStep:
         # workspace) precedes the rebuild; the joins are the waits on ev_plan / ev_bin
         self.ev_fork.record(torch.cuda.current_stream(self.dev))
         self.side.wait_event(self.ev_fork)
-        geo = (self.H, self.W, self.scales, self.nlev, self.B, self.C, self.rois.data_ptr(), self.K,
+        geo = (self.H, self.W, self.scales, self.rlev, self.B, self.C, self.rois.data_ptr(), self.K,
                self.R, 1.0, self.P, self.P, 0, 56.0, self.dt)
         tail = (self.ws_ptr, self.ws_bytes, self.side.cuda_stream)
         L.check(self.lib.arfe_roi_plan_build(*geo, *tail), "arfe_roi_plan_build")
         self.ev_plan.record(self.side)
-        L.check(self.lib.arfe_roi_pull_bin(*geo, int(self.split), *tail), "arfe_roi_pull_bin")
-        self.ev_bin.record(self.side)
-        self.async_plan, self.async_bins = 1, 1
+        self.async_plan, self.async_bins = 1, 0
+        if bins:
+            L.check(self.lib.arfe_roi_pull_bin(*geo, int(self.split), *tail), "arfe_roi_pull_bin")
+            self.ev_bin.record(self.side)
+            self.async_bins = 1
 
     def roi_fuse_fwd(self):
         ready = 0
@@ -218,18 +247,18 @@ class TrainStep:
         if self.split:
             self.planned = 1
             return self.lib.arfe_roi_fuse_forward_plan_split(
-                self.p_y, self.H, self.W, self.scales, self.nlev, self.B, self.C,
+                self.p_y, self.H, self.W, self.scales, self.rlev, self.B, self.C,
                 self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt,
                 self.p_Fr, self.ws_ptr, self.ws_bytes, ready, self.stream)
         if self.cl:
             # channels-last: plan + ring kernel; the plan stays in the workspace for the backward
             self.planned = 1
             return self.lib.arfe_roi_fuse_forward_plan(
-                self.p_y, self.H, self.W, self.scales, self.nlev, self.B, self.C,
+                self.p_y, self.H, self.W, self.scales, self.rlev, self.B, self.C,
                 self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt,
                 self.F.data_ptr(), None, None, self.ws_ptr, self.ws_bytes, ready, self.stream)
         return self.lib.arfe_roi_fuse_forward(
-            self.p_y, self.H, self.W, self.scales, self.nlev, self.B, self.C,
+            self.p_y, self.H, self.W, self.scales, self.rlev, self.B, self.C,
             self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt, self.layout,
             self.layout, self.F.data_ptr(), None, None, self.stream)
 
@@ -251,18 +280,18 @@ class TrainStep:
             ready, self.async_bins = 2, 0
         if self.split:
             rc = self.lib.arfe_roi_fuse_backward_pull_split(
-                self.p_dFr, self.H, self.W, self.scales, self.nlev, self.B, self.C,
+                self.p_dFr, self.H, self.W, self.scales, self.rlev, self.B, self.C,
                 self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt,
                 self.p_dy, self.ws_ptr, self.ws_bytes, ready, self.stream)
         elif self.cl:
             rc = self.lib.arfe_roi_fuse_backward_pull(
-                self.dF.data_ptr(), self.H, self.W, self.scales, self.nlev, self.B, self.C,
+                self.dF.data_ptr(), self.H, self.W, self.scales, self.rlev, self.B, self.C,
                 self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt,
                 self.p_dy, self.ws_ptr, self.ws_bytes, ready, self.stream)
         if self.cl:
             return rc
         return self.lib.arfe_roi_fuse_backward(
-            self.dF.data_ptr(), L.ARFE_NCHW, self.H, self.W, self.scales, self.nlev, self.B,
+            self.dF.data_ptr(), L.ARFE_NCHW, self.H, self.W, self.scales, self.rlev, self.B,
             self.C, self.rois.data_ptr(), self.K, self.R, 1.0, self.P, self.P, 0, 56.0, self.dt,
             self.layout, self.p_dy, self.stream)
 
@@ -274,9 +303,11 @@ class TrainStep:
             self.p_dg2, self.stream)
 
     def fpn_gather_bwd(self):
-        return self.lib.arfe_fpn_gather_backward(
+        # d x_l = d out_l (the residual's identity, = dy_l written by roi_fuse_bwd) + the gather's
+        # routed gradient, in the one write of dx_l (wfpn_dual_spatial.py:113,135 under autograd)
+        return self.lib.arfe_fpn_gather_backward_acc(
             self.gbsf.data_ptr(), self.argmax.data_ptr(), self.H, self.W, self.nlev, self.B,
-            self.C, 2, self.dt, self.layout, self.p_dx, self.stream)
+            self.C, 2, self.dt, self.layout, self.p_dy, self.p_dx, self.stream)
 
     def glue_before_roi_bwd(self):
         """torch plumbing between our kernels: assemble dF (stand-in for the
@@ -286,10 +317,10 @@ class TrainStep:
         if self.split:
             return  # the pull kernel reads d_ori / d_ab where they are
         C = self.C  # d_ori was written in place into dF[:, :C] by the gate backward
-        for r in range(1, self.R):
-            self.dF[:, r * C:(r + 1) * C].copy_(self.d_ab)
+        for r, t in zip(range(1, self.R), (self.glw, self.glh)):
+            self.dF[:, r * C:(r + 1) * C].copy_(t)
         if not self.cl:
-            for t in self.dy:
+            for t in self.dy[:self.rlev]:
                 t.zero_()
 
     def glue_before_apply_bwd(self):
@@ -297,25 +328,27 @@ class TrainStep:
             for a, b in zip(self.dy_in, self.dy):
                 a.copy_(b)
 
+    _GLUE = {"roi_fuse_bwd": "glue_before_roi_bwd", "fpn_apply_bwd": "glue_before_apply_bwd"}
+
+    def run_ops(self, names, timer=None):
+        """The named ops in order (with the torch glue that belongs in front of them);
+        `timer(name, fn)` wraps each of our launches."""
+        run = timer or (lambda name, fn: L.check(fn(), name))
+        if self.cl and self.overlap_plan and "roi_fuse_fwd" in names:
+            self.plan_async(bins="roi_fuse_bwd" in names or getattr(self, "want_bins", False))
+        for n in names:
+            glue = self._GLUE.get(n)
+            if glue:
+                getattr(self, glue)()
+            run(n, getattr(self, n))
+
     def step(self, timer=None):
         """One training step. `timer(name, fn)` wraps each of our launches; without a
         timer a captured step (capture()) is replayed as one CUDA graph."""
         if timer is None and getattr(self, "graph", None) is not None:
             self.graph.replay()
             return
-        run = timer or (lambda name, fn: L.check(fn(), name))
-        if self.cl and self.overlap_plan:
-            self.plan_async()
-        run("fpn_gather_fwd", self.fpn_gather_fwd)
-        run("fpn_apply_fwd", self.fpn_apply_fwd)
-        run("roi_fuse_fwd", self.roi_fuse_fwd)
-        run("rff_gate_fwd", self.rff_gate_fwd)
-        run("rff_gate_bwd", self.rff_gate_bwd)
-        self.glue_before_roi_bwd()
-        run("roi_fuse_bwd", self.roi_fuse_bwd)
-        self.glue_before_apply_bwd()
-        run("fpn_apply_bwd", self.fpn_apply_bwd)
-        run("fpn_gather_bwd", self.fpn_gather_bwd)
+        self.run_ops(KERNELS, timer)
 
     def capture(self):
         """Capture the step (the same launches, second stream included) into a CUDA graph:
@@ -346,6 +379,7 @@ class TrainStep:
         e = 4 if self.dtype == torch.float32 else 2
         B, C, K, R = self.B, self.C, self.K, self.R
         P = sum(h * w for h, w in self.shapes)
+        Pr = sum(h * w for h, w in self.shapes[:self.rlev])  # levels the RoI extractor reads
         hr, wr = self.shapes[2]
         pyr = B * C * P * e
         ref = B * C * hr * wr
@@ -354,10 +388,104 @@ class TrainStep:
         return {
             "fpn_gather_fwd": pyr + ref * e + 2 * ref,                       # + uint8 argmax (2 levels)
             "fpn_apply_fwd": 2 * pyr + ref * e + 2 * B * P * e,
-            "roi_fuse_fwd": out_roi + pyr + 20 * K,
+            "roi_fuse_fwd": out_roi + B * C * Pr * e + 20 * K,
             "rff_gate_fwd": 4 * n_gate,
             "rff_gate_bwd": 6 * n_gate,
-            "roi_fuse_bwd": out_roi + B * C * P * 4 + 20 * K,                # fp32 accumulators
+            "roi_fuse_bwd": out_roi + B * C * Pr * 4 + 20 * K,               # fp32 accumulators
             "fpn_apply_bwd": pyr + ref * e + 2 * B * P * e + ref * 4 + 2 * B * P * 4,
-            "fpn_gather_bwd": ref * e + 2 * ref + pyr,
+            "fpn_gather_bwd": ref * e + 2 * ref + pyr + B * C * P * 4,          # + the fp32 addend (dy)
         }
+
+
+# ---------------------------------------------------------------------------
+# The other BASELINE.json configurations, as schedules over TrainStep states
+# ---------------------------------------------------------------------------
+FWD_OPS = ("fpn_gather_fwd", "fpn_apply_fwd", "roi_fuse_fwd", "rff_gate_fwd")
+ROI_FWD = ("roi_fuse_fwd", "rff_gate_fwd")
+ROI_BWD = ("rff_gate_bwd", "roi_fuse_bwd")
+FPN_BWD = ("fpn_apply_bwd", "fpn_gather_bwd")
+RETINA_STRIDES = (8, 16, 32, 64, 128)
+
+
+class Case:
+    """An ordered schedule [(prefix, TrainStep, op names)] = one step of a configuration."""
+
+    def __init__(self, workload, images, parts, dtype):
+        self.workload, self.images, self.parts, self.dtype = workload, images, parts, dtype
+
+    def step(self, timer=None):
+        for prefix, st, names in self.parts:
+            t = None if timer is None else (lambda n, fn, p=prefix: timer(p + n, fn))
+            st.run_ops(names, t)
+
+    def op_names(self):
+        return [p + n for p, _, names in self.parts for n in names]
+
+    def algorithmic_bytes(self):
+        out = {}
+        for prefix, st, names in self.parts:
+            alg = st.algorithmic_bytes()
+            for n in names:
+                out[prefix + n] = alg[n]
+        return out
+
+    def launches_per_step(self):
+        cl = {"fpn_gather_fwd": 1, "fpn_apply_fwd": 1, "roi_fuse_fwd": 3, "rff_gate_fwd": 1,
+              "rff_gate_bwd": 1, "roi_fuse_bwd": 4, "fpn_apply_bwd": 1, "fpn_gather_bwd": 2}
+        nchw = dict(cl, roi_fuse_fwd=1, roi_fuse_bwd=1, fpn_apply_bwd=2)
+        return sum((cl if st.cl else nchw)[n] for _, st, names in self.parts for n in names)
+
+
+def _share_pyramid(st, src):
+    """st's RoI ops read src's aggregated pyramid (one neck, several RoI consumers)."""
+    st.y, st.p_y = src.y, src.p_y
+    return st
+
+
+def make_case(config, dev, seed=0, rois_per_img=None):
+    """BASELINE.json configs[config] on one GPU (channels-last fast path, dense inputs
+    generated on the device)."""
+    f32, bf16 = torch.float32, torch.bfloat16
+    if config == 0:
+        K = rois_per_img or 1000
+        st = TrainStep(host_inputs(1, K, 256, seed=seed, channels_last=True, device=dev), dev)
+        return Case(f"configs[0]: Faster R-CNN R50 + AR-FPN + AR-RFF inference (forward of the fused path), "
+                    f"1 image 800x1344, {K} RoIs, C=256, fp32", 1, [("", st, FWD_OPS)], "f32")
+    if config == 1:
+        K = rois_per_img or 512
+        st = TrainStep(host_inputs(2, K, 256, seed=seed, channels_last=True, device=dev), dev)
+        return Case(f"configs[1]: training step, 2 img x {K} RoIs", 2, [("", st, KERNELS)], "f32")
+    if config == 2:
+        st = TrainStep(host_inputs(8, 8, 256, seed=seed, channels_last=True, strides=RETINA_STRIDES,
+                                   device=dev), dev)
+        return Case("configs[2]: RetinaNet R50 + AR-FPN neck-only aggregation (gather + gated residual, "
+                    "forward), batch 8, 800x1344, strides 8-128, C=256, fp32", 8,
+                    [("", st, FWD_OPS[:2])], "f32")
+    if config == 3:
+        K = rois_per_img or 512
+        st = TrainStep(host_inputs(2, K, 256, dtype=bf16, seed=seed, channels_last=True, device=dev), dev)
+        km = max(K // 4, 1)  # mask head: the positive quarter of the sampled RoIs
+        mask = TrainStep(host_inputs(2, km, 256, dtype=bf16, seed=seed + 1, channels_last=True,
+                                     out_size=14, device=dev), dev, regions=1)
+        mask.d_ori.normal_()  # incoming gradient of the 14x14 mask features
+        _share_pyramid(mask, st)
+        st.want_bins = mask.want_bins = True  # the backward follows in a later part of the schedule
+        return Case(f"configs[3]: Mask R-CNN R50 + AR-FPN + AR-RFF training step, bf16 I/O, 2 img x {K} RoIs "
+                    f"(bbox 7x7 x 3 regions) + 2 x {km} RoIs (mask 14x14 x 1 region)", 2,
+                    [("", st, KERNELS[:4]), ("mask.", mask, ("roi_fuse_fwd",)),
+                     ("mask.", mask, ("roi_fuse_bwd",)), ("", st, KERNELS[4:])], "bf16")
+    if config == 4:
+        K = rois_per_img or 512
+        stages = [TrainStep(host_inputs(1, K, 256, seed=seed + i, channels_last=True, device=dev), dev)
+                  for i in range(3)]
+        for st in stages:
+            st.want_bins = True
+        for st in stages[1:]:
+            _share_pyramid(st, stages[0])
+        parts = [("", stages[0], FWD_OPS[:2])]
+        parts += [(f"s{i}.", st, ROI_FWD) for i, st in enumerate(stages)]
+        parts += [(f"s{i}.", st, ROI_BWD) for i, st in reversed(list(enumerate(stages)))]
+        parts += [("", stages[0], FPN_BWD)]
+        return Case(f"configs[4]: Cascade R-CNN + AR-RFF, three-stage RoI fusion training step, 1 image x {K} "
+                    f"RoIs per stage, C=256, fp32", 1, parts, "f32")
+    raise ValueError(f"unknown config {config}")

@@ -2,18 +2,26 @@
 """bench.py -- headline benchmark of the region-aware feature path.
 
 Workload (BASELINE.json configs[1], per GPU): one TRAINING step (fwd + bwd) of
-fused AR-FPN + AR-RFF for 2 synthetic 800x1344 images x 512 RoIs, C=256, fp32,
-FPN strides 4..64.  metric = images/s (whole job, all GPUs); us_per_img is
-also printed.  See arfe_b200/workload.py for the exact step.
+fused AR-FPN + AR-RFF for 2 synthetic 800x1344 images x 512 RoIs (image-major,
+as bbox2roi builds them), C=256, fp32, pyramid strides 4..64, RoI extractor on
+strides 4..32.  metric = images/s (whole job, all GPUs); us_per_img is also
+printed.  See arfe_b200/workload.py for the exact step.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]        our CUDA path
+  python bench.py [--gpus N] [--steps K] [--warmup W]        our CUDA path, configs[1]
+  python bench.py --config {0,2,3,4} [--rois-per-img K]       the other BASELINE configs
   python bench.py --impl reference ...                        reference CPU path
 
 value : inputs resident in HBM, direct C-ABI calls, CUDA-event timed.
-e2e   : same step, inputs start in PINNED HOST memory every step (H2D inside
-        the timed region) and a result scalar is read back (D2H).
+e2e   : same step through the C ABI, inputs start in PINNED HOST memory every
+        step (H2D inside the timed region) and a result scalar is read back.
+e2e_modules : the same step through the public modules / autograd Functions
+        (what a swapped-in config runs), host buffers in, scalar out.
 roofline : dominant kernel, algorithmic bytes / CUDA-event time vs the measured
         HBM copy peak (MEASURED_PEAKS.json).
+verified : after the timed loop the buffers the timed steps wrote are compared
+        with the oracle (the reference's arithmetic on the host): AR-FPN on all
+        channels, the RoI part on all RoIs for a subset of channels (RoIAlign
+        and the gate are independent per channel).
 cpu_baseline : the oracle's CPU path (test infrastructure, used here only as
         the thing measured against) on a bounded sample, rank 0, N=1.
 """
@@ -35,16 +43,20 @@ BATCH, ROIS_PER_IMG, CHANNELS = 2, 512, 256
 WORKLOAD = ("configs[1]: Faster R-CNN R50 + AR-FPN + AR-RFF training step "
             "(fwd+bwd of the fused path), 2 img/GPU x 512 RoIs, 800x1344, C=256, "
             "strides 4-64, 3 regions, 7x7")
+TRAFFIC_FILE = os.path.join("profiles", "r2_traffic.json")
+VERIFY_CHANNELS = (0, 37, 101, 127, 128, 200, 254, 255)
 
 
 def measured_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture
-    (profiles/r1_traffic.json); None when no capture exists for it."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        return float(t[kernel]["bytes"])
-    except Exception:
-        return None
+    """DRAM bytes per launch of `kernel` from the committed ncu capture; None when no
+    capture exists for it."""
+    for f in (TRAFFIC_FILE, os.path.join("profiles", "r1_traffic.json")):
+        try:
+            t = json.load(open(os.path.join(ROOT, f)))
+            return float(t[kernel]["bytes"]), f
+        except Exception:
+            continue
+    return None, None
 
 
 def peaks():
@@ -102,34 +114,27 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_rank_to_cores(local_rank, world):
+    """Give each rank its own slice of the host cores the GPU is local to (NVML's ideal
+    affinity), before any pinned buffer is allocated: staging memory is then first
+    touched, and the copy threads run, next to the GPU's root port."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = [i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0))) or sorted(os.sched_getaffinity(0))
+        per = max(len(allowed) // max(world, 1), 1)
+        mine = allowed[(local_rank * per) % len(allowed):][:per] or allowed
+        os.sched_setaffinity(0, mine)
+        return {"gpu_ideal_cores": f"{cores[0]}-{cores[-1]}" if cores else None, "bound_to": f"{mine[0]}-{mine[-1]}"}
+    except Exception as ex:  # pragma: no cover
+        return {"error": str(ex)[:80]}
+
+
 # ----------------------------------------------------------------- CPU arms
-def cpu_step(oracle, host, backend):
-    """The same step on the host through the oracle (reference arithmetic).
-    Returns (seconds in the AR-FPN part, seconds in the AR-RFF part)."""
-    C = host["a"].shape[1]
-    t0 = time.perf_counter()
-    x = [t.clone().requires_grad_(True) for t in host["x"]]
-    bsf = host["bsf"].clone().requires_grad_(True)
-    g1 = [t.clone().requires_grad_(True) for t in host["g1"]]
-    g2 = [t.clone().requires_grad_(True) for t in host["g2"]]
-    gathered = oracle.wfpn_gather(x, 2)
-    y = oracle.wfpn_apply(x, bsf, g1, g2)
-    t1 = time.perf_counter()
-    yd = [t.detach().requires_grad_(True) for t in y]
-    F = oracle.arrff_bbox_feats(yd, host["rois"], [4, 8, 16, 32, 64], backend=backend)
-    a = host["a"].clone().requires_grad_(True)
-    b = host["b"].clone().requires_grad_(True)
-    z = oracle.rff_gate(F[:, :C], a, b)
-    # gradients reaching the two context-region blocks: synthetic stand-in for
-    # the conv backward that stays on PyTorch (same role as TrainStep's glue)
-    torch.autograd.backward([z, F[:, C:2 * C], F[:, 2 * C:]], [host["gz"], host["gz"], host["gz"]])
-    t2 = time.perf_counter()
-    dy = [t.grad if t.grad is not None else torch.zeros_like(t) for t in yd]
-    torch.autograd.backward(list(y) + [gathered], dy + [host["gbsf"]])
-    t3 = time.perf_counter()
-    return (t1 - t0) + (t3 - t2), (t2 - t1)
-
-
 def cpu_sample_inputs(rois_per_img):
     from arfe_b200 import workload as wl
     return wl.host_inputs(batch=1, rois_per_img=rois_per_img, channels=CHANNELS, seed=0)
@@ -150,13 +155,13 @@ def run_reference(args, rank, world):
     rpi = 64  # bounded sample: 1 image, 64 of its 512 RoIs (RoI part is linear in K)
     host = cpu_sample_inputs(rpi)
     for _ in range(args.warmup):
-        cpu_step(O, host, backend)
+        O.reference_step(host, backend)
     t_fpn = t_roi = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        f, r = cpu_step(O, host, backend)
-        t_fpn += f
-        t_roi += r
+        r = O.reference_step(host, backend)
+        t_fpn += r["t_fpn"]
+        t_roi += r["t_roi"]
     dt = (time.perf_counter() - t0) / args.steps
     t_img = t_fpn / args.steps + t_roi / args.steps * (ROIS_PER_IMG / rpi)
     value = 1.0 / t_img
@@ -189,12 +194,12 @@ def cpu_baseline_leg():
     backend, kind = "c", "port"
     rpi = 128
     host = cpu_sample_inputs(rpi)
-    cpu_step(O, host, backend)  # warm
+    O.reference_step(host, backend)  # warm
     t0 = time.perf_counter()
     n, t_fpn, t_roi = 0, 0.0, 0.0
     while n < 2 or time.perf_counter() - t0 < 10.0:
-        f, r = cpu_step(O, host, backend)
-        t_fpn, t_roi, n = t_fpn + f, t_roi + r, n + 1
+        r = O.reference_step(host, backend)
+        t_fpn, t_roi, n = t_fpn + r["t_fpn"], t_roi + r["t_roi"], n + 1
     t_img = t_fpn / n + t_roi / n * (ROIS_PER_IMG / rpi)
     cores = os.cpu_count() or 1
     return {"value": 1.0 / t_img, "unit": UNIT, "cores": cores, "kind": kind,
@@ -203,7 +208,142 @@ def cpu_baseline_leg():
                        f"cores, serial backward) + torch CPU ops on {torch.get_num_threads()} threads")}
 
 
+# ------------------------------------------------------------- verification
+def verify_step(step, host):
+    """Compare what the timed steps left in the device buffers with the oracle
+    (test infrastructure used as the checker).  Returns {"verified": bool, ...}."""
+    from oracle import arfe_oracle as O
+    from oracle import build_oracle
+    build_oracle.build_c_oracle()
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    S = [c for c in VERIFY_CHANNELS if c < step.C]
+    cpu = lambda t: t.detach().float().cpu().contiguous()
+    nchw = lambda v: [nchw(t) for t in v] if isinstance(v, list) and torch.is_tensor(v[0]) else \
+        (v.contiguous() if torch.is_tensor(v) else v)
+    dy_dev = [cpu(t) for t in step.dy]
+    ref = O.reference_step({k: nchw(v) for k, v in host.items()}, backend="c", channels=S,
+                           dy_full=dy_dev, roi_levels=step.rlev)
+    worst, failed = {}, []
+
+    def check(name, got, want, rel, scale):
+        got, want = cpu(got), want.detach().float()
+        err = (got - want).abs()
+        tol = rel * want.abs() + scale * float(want.abs().max()) + 1e-6
+        ratio = float((err / tol).max()) if err.numel() else 0.0
+        worst[name] = max(worst.get(name, 0.0), round(ratio, 3))
+        if ratio > 1.0 or not bool(torch.isfinite(got).all()):
+            failed.append(name)
+
+    exact = bool(torch.equal(cpu(step.gathered), ref["gathered"]))
+    if not exact:
+        failed.append("gathered (bit-exact)")
+    F = [cpu(t) for t in step.Fr] if step.split else \
+        [cpu(step.F[:, r * step.C:(r + 1) * step.C]) for r in range(step.R)]
+    c = len(S)
+    d_ori = step.d_ori if step.split else step.dF[:, :step.C]
+    for l in range(step.nlev):
+        check("y", step.y[l], ref["y"][l], 1e-5, 0.0)
+        check("dy", dy_dev[l][:, S], ref["dy"][l], 1e-5, 2e-5)
+        check("dx", cpu(step.dx[l]), ref["dx"][l], 1e-5, 2e-5)
+        check("dg1", step.dg1[l], ref["dg1"][l], 1e-5, 2e-5)
+        check("dg2", step.dg2[l], ref["dg2"][l], 1e-5, 2e-5)
+    for r in range(step.R):
+        check("F", F[r][:, S], ref["F"][:, r * c:(r + 1) * c], 1e-5, 0.0)
+    check("z", cpu(step.z)[:, S], ref["z"], 1e-5, 0.0)
+    check("d_ori", cpu(d_ori)[:, S], ref["d_ori"], 1e-5, 0.0)
+    check("d_ab", cpu(step.d_ab)[:, S], ref["d_ab"], 1e-5, 0.0)
+    check("dbsf", step.dbsf, ref["dbsf"], 1e-5, 2e-5)
+    return {"verified": not failed, "failed": failed, "gather_bit_exact": exact,
+            "max_err_over_tol": worst, "channels_checked_roi_part": S,
+            "tolerance": "|err| <= 1e-5 |ref| + 1e-6 (forward); + 2e-5 max|ref| for gradients summed in another order",
+            "against": "oracle.reference_step (C port of roi_align_v2.cpp + torch CPU ops) on the same host inputs, "
+                       "all RoIs, all pixels; d x / d bsf / d gate maps from the device d y",
+            "seconds": round(time.perf_counter() - t0, 1)}
+
+
 # ------------------------------------------------------------------ GPU arm
+def make_timer(names, only=None):
+    from arfe_b200 import _lib as L
+    ev = {n: [] for n in names}
+
+    def timed(name, fn):
+        if only is not None and name != only:
+            L.check(fn(), name)
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        L.check(fn(), name)
+        b.record()
+        ev[name].append((a, b))
+    return ev, timed
+
+
+def mean_ms(ev):
+    return {n: sum(a.elapsed_time(b) for a, b in v) / len(v) for n, v in ev.items() if v}
+
+
+def time_case(case, steps, warmup, barrier=None):
+    """Device-timed steps of a schedule: (ms per step, per-op ms, dominant op, its ms inside the run)."""
+    names = case.op_names()
+    for _ in range(max(warmup - 2, 1)):
+        case.step()
+    ev_w, timed_w = make_timer(names)
+    for _ in range(2):
+        case.step(timed_w)
+    if barrier:
+        barrier()
+    torch.cuda.synchronize()
+    top = max(mean_ms(ev_w).items(), key=lambda kv: kv[1])[0]
+    ev_top, timed_top = make_timer(names, only=top)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        case.step(timed_top)
+    b.record()
+    if barrier:
+        barrier()
+    torch.cuda.synchronize()
+    ms_total = a.elapsed_time(b)
+    top_ms = mean_ms(ev_top)[top]
+    ev_all, timed_all = make_timer(names)
+    for _ in range(steps):
+        case.step(timed_all)
+    torch.cuda.synchronize()
+    return ms_total, mean_ms(ev_all), top, top_ms
+
+
+def kernel_table(alg, per_ms, peak):
+    return {n: {"ms": round(per_ms[n], 4), "alg_MB": round(alg[n] / 1e6, 1),
+                "GBps": round(alg[n] / (per_ms[n] * 1e-3) / 1e9, 1),
+                "frac": round(alg[n] / (per_ms[n] * 1e-3) / 1e9 / peak, 3)} for n in per_ms}
+
+
+def other_configs_block(dev, peak):
+    """Compact device-timed numbers of the other BASELINE configs (the full lines come
+    from --config N): tracked by the driver round over round."""
+    from arfe_b200 import workload as wl
+    out = {}
+    for tag, cfg, kpi in (("config0_infer_K1000", 0, None), ("config2_retina_neck_B8", 2, None),
+                          ("config3_mask_bf16", 3, None), ("config4_cascade_K512", 4, 512),
+                          ("config4_cascade_K8192", 4, 8192)):
+        try:
+            case = wl.make_case(cfg, dev, rois_per_img=kpi)
+            ms_total, per_ms, top, _ = time_case(case, 10, 3)
+            alg = case.algorithmic_bytes()
+            ms = ms_total / 10
+            out[tag] = {"us_per_img": round(ms * 1e3 / case.images, 1),
+                        "images_per_s": round(case.images / (ms * 1e-3), 1), "dtype": case.dtype,
+                        "step_frac_of_hbm_peak": round(sum(alg.values()) / (ms * 1e-3) / 1e9 / peak, 3),
+                        "slowest_op": top, "slowest_op_ms": round(per_ms[top], 4),
+                        "slowest_op_frac": round(alg[top] / (per_ms[top] * 1e-3) / 1e9 / peak, 3)}
+            del case
+            torch.cuda.empty_cache()
+        except Exception as ex:  # pragma: no cover
+            out[tag] = {"error": str(ex)[:200]}
+    return out
+
+
 def run_ours(args, rank, local_rank, world):
     import torch.distributed as dist
     from arfe_b200 import _lib as L
@@ -213,115 +353,117 @@ def run_ours(args, rank, local_rank, world):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    affinity = bind_rank_to_cores(local_rank, world)
     L.lib()  # fail loudly if the extension is missing
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    cl = not args.nchw
-    host = wl.host_inputs(BATCH, ROIS_PER_IMG, CHANNELS, seed=rank, pin=True, channels_last=cl)
-    step = wl.TrainStep(host, dev, channels_last=cl)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- device-resident steps; CUDA events around the dominant kernel inside the timed
-    # region.  Events around all eight ops cost 38 us per step (scripts/step_modes.py:
-    # 629 us plain, 667 us instrumented), so the per-op table is a separate pass.
-    names = wl.KERNELS
+    peak, peak_src = peaks()
+    cl = not args.nchw
+    main_cfg = args.config == 1
+    if main_cfg:
+        host = wl.host_inputs(BATCH, args.rois_per_img or ROIS_PER_IMG, CHANNELS, seed=rank, pin=True,
+                              channels_last=cl)
+        step = wl.TrainStep(host, dev, channels_last=cl)
+        case = wl.Case(WORKLOAD, BATCH, [("", step, wl.KERNELS)], "f32")
+    else:
+        case = wl.make_case(args.config, dev, seed=rank, rois_per_img=args.rois_per_img)
+        step = case.parts[0][1]
+    images = case.images
 
-    def make_timer(only=None):
-        ev = {n: [] for n in names}
-
-        def timed(name, fn):
-            if only is not None and name != only:
-                L.check(fn(), name)
-                return
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            L.check(fn(), name)
-            b.record()
-            ev[name].append((a, b))
-        return ev, timed
-
-    def mean_ms(ev):
-        return {n: sum(a.elapsed_time(b) for a, b in v) / len(v) for n, v in ev.items() if v}
-
-    for _ in range(max(args.warmup - 2, 1)):
-        step.step()
-    ev_w, timed_w = make_timer()      # last warm-up steps: which op is the dominant one
-    for _ in range(2):
-        step.step(timed_w)
-    barrier()
-    top = max(mean_ms(ev_w).items(), key=lambda kv: kv[1])[0]
-    ev_top, timed_top = make_timer(only=top)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    for _ in range(args.steps):
-        step.step(timed_top)
-    t_end.record()
-    barrier()
+    ms_total, per_kernel_ms, top, top_ms = time_case(case, args.steps, args.warmup, barrier)
     clocks = sampler.stop() if rank == 0 else None
-    ms_total = t_start.elapsed_time(t_end)
-    top_ms = mean_ms(ev_top)[top]
-    # per-op table: the same K steps again with events around every op (outside the timed region)
-    ev_all, timed_all = make_timer()
-    for _ in range(args.steps):
-        step.step(timed_all)
-    barrier()
-    per_kernel_ms = mean_ms(ev_all)
 
-    # ---- e2e: host buffers in, scalar out, public module-level API --------
-    e2e_ms, h2d, d2h = run_e2e(args, host, dev, barrier, cl)
+    verification = None
+    if main_cfg and rank == 0 and not args.no_verify:
+        # the buffers still hold what the last timed step wrote
+        verification = verify_step(step, host)
 
-    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
+    e2e = e2e_mod = None
+    if main_cfg:
+        e2e_ms, h2d, d2h, h2d_gbps = run_e2e(args, host, dev, barrier, cl)
+        mod_ms = run_e2e_modules(args, host, dev, barrier) if cl else None
+        t = torch.tensor([ms_total, e2e_ms, mod_ms or 0.0, -h2d_gbps[0], -h2d_gbps[1]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_ms, mod_ms = float(t[0]), float(t[1]), (float(t[2]) if mod_ms else None)
+        e2e = {"value": world * images / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+               "h2d_GBps_per_gpu": {"one_rank_at_a_time": round(-float(t[3]), 1),
+                                    "all_ranks_concurrently": round(-float(t[4]), 1),
+                                    "note": "slowest rank; pinned host -> device copy of one step's inputs, outside the timed region"},
+               "host_affinity": affinity,
+               "note": "pinned-host pyramid + RoIs + conv stand-ins copied H2D every step (double-buffered: the copies of step "
+                       "k+1 overlap step k), loss scalar read back every step; bound by the H2D copy"}
+        if mod_ms:
+            e2e_mod = {"value": world * images / (mod_ms / args.steps * 1e-3), "unit": UNIT,
+                       "ms_per_step": mod_ms / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "path": "arfe_b200.fpn_gather / fpn_apply / roi_fuse_split / rff_gate autograd Functions "
+                               "(what WFPNDualSpatial.forward and StandardRoIHead._bbox_forward call; the convs "
+                               "between them are stand-in inputs as in `value`), torch.autograd.backward, "
+                               "per-call allocation, tile bins on a side stream"}
+    else:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t[0])
 
     if rank == 0:
         ms_step = ms_total / args.steps
-        value = world * BATCH / (ms_step * 1e-3)
-        e2e_value = world * BATCH / (e2e_ms / args.steps * 1e-3)
-        alg = step.algorithmic_bytes()
-        peak, peak_src = peaks()
+        value = world * images / (ms_step * 1e-3)
+        alg = case.algorithmic_bytes()
         achieved = alg[top] / (top_ms * 1e-3) / 1e9
-        kern = {n: {"ms": round(per_kernel_ms[n], 4), "alg_MB": round(alg[n] / 1e6, 1),
-                    "GBps": round(alg[n] / (per_kernel_ms[n] * 1e-3) / 1e9, 1),
-                    "frac": round(alg[n] / (per_kernel_ms[n] * 1e-3) / 1e9 / peak, 3)} for n in names}
+        traffic, traffic_src = measured_traffic(top) if (cl and main_cfg) else (None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "us_per_img": 1e6 / value * world,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": case.dtype,
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "rois_per_gpu": BATCH * ROIS_PER_IMG,
+            "config": {"workload": case.workload, "baseline_config": args.config,
+                       "global_batch": world * images, "rois_per_gpu": step.K,
+                       "roi_order": "image-major (per-image blocks, bbox2roi)",
+                       "roi_levels": f"extractor on the first {step.rlev} of {step.nlev} pyramid levels (featmap_strides 4-32)",
                        "parallelism": f"dp{world} (images sharded, no data-path collective)",
                        "memory_format": "torch.channels_last (fast path)" if cl else "NCHW (reference layout, compatibility kernels)",
                        "roi_tensors": ("regions as separate tensors (ori | lw | lh), read/written in place: no cat / slice copies in the step"
                                        if step.split else "concatenated [K, 3C, 7, 7]; torch slice copies between the kernels are inside the step"),
-                       "streams": ("RoI plan and tile binning (2 kernels, ~40 us) run on a second stream under the AR-FPN forward kernels; "
+                       "backward": "d x_l = d out_l + gather gradient in one write (arfe_fpn_gather_backward_acc); "
+                                   "d lw / d lh are separate input tensors",
+                       "streams": ("RoI plan and tile binning (2 kernels) run on a second stream under the AR-FPN forward kernels; "
                                    "the per-op times of roi_fuse_fwd / roi_fuse_bwd exclude them, the step time includes them"
                                    if getattr(step, "overlap_plan", False) else "one stream"),
-                       "l2": "inputs+outputs per step (~1.5 GB) exceed the 126 MB L2; no explicit flush",
+                       "l2": "inputs+outputs per step (~1.8 GB) exceed the 126 MB L2; no explicit flush",
                        "timing": "CUDA events on the launch stream, max over ranks",
                        "instrumentation": "the timed region carries events around the dominant kernel only (roofline.achieved); "
-                                          "`kernels` is a second pass of the same K steps with events around every op (+38 us per step)"},
+                                          "`kernels` is a second pass of the same K steps with events around every op"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps,
-                    "note": "pinned-host pyramid+RoIs+conv stand-ins copied H2D every step (double-buffered: the copies of step k+1 overlap step k), loss scalar read back every step; PCIe-bound"},
-            "gpu_launches": step.launches_per_step() * args.steps,
+            "gpu_launches": case.launches_per_step() * args.steps,
             "roofline": {"bound": "hbm", "kernel": top, "kernel_ms": top_ms, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic(top) if cl else None,
-                         "algorithmic_bytes": alg[top], "peak_source": peak_src,
-                         "traffic_source": "ncu --set full capture, profiles/r1_traffic.json"},
-            "kernels": kern,
+                         "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": alg[top],
+                         "peak_source": peak_src,
+                         "traffic_source": f"ncu --set full capture, {traffic_src}" if traffic_src else None,
+                         "step_algorithmic_bytes": sum(alg.values()),
+                         "step_frac": sum(alg.values()) / (ms_step * 1e-3) / 1e9 / peak},
+            "kernels": kernel_table(alg, per_kernel_ms, peak),
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if e2e:
+            line["e2e"] = e2e
+        if e2e_mod:
+            line["e2e_modules"] = e2e_mod
+        if verification is not None:
+            line["verified"] = verification["verified"]
+            line["verification"] = verification
+        if main_cfg and world == 1 and not args.no_other_configs:
+            line["other_configs"] = other_configs_block(dev, peak)
+        if main_cfg and world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -329,20 +471,24 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+E2E_KEYS_LIST = ("x", "g1", "g2")
+E2E_KEYS = ("bsf", "rois", "a", "b", "gz", "glw", "glh", "gbsf")
+
+
 def run_e2e(args, host, dev, barrier, cl):
     """Same step, but every step starts from pinned host memory (H2D inside the
     timed region, every step) and ends with a device->host read of the result
     scalar.  The copies of step k+1 run on a second stream into the other of two
     input buffer sets while step k computes (what any input pipeline does); the
-    region is PCIe-bound either way (356 MB per step)."""
+    region is bound by the copy either way."""
     from arfe_b200 import workload as wl
     steps = [wl.TrainStep(host, dev, channels_last=cl) for _ in range(2)]
 
     def pairs_of(step):
         pairs = []
-        for key in ("x", "g1", "g2"):
+        for key in E2E_KEYS_LIST:
             pairs += list(zip(getattr(step, key), host[key]))
-        for key in ("bsf", "rois", "a", "b", "gz", "gbsf"):
+        for key in E2E_KEYS:
             pairs.append((getattr(step, key), host[key]))
         return pairs
     pairs = [pairs_of(s) for s in steps]
@@ -376,6 +522,26 @@ def run_e2e(args, host, dev, barrier, cl):
             used[i] = True
             main.synchronize()   # the result scalar is on the host
 
+    # what the copy alone achieves: this rank by itself, then all ranks at once
+    def h2d_rate(n=3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            for d, s in pairs[0]:
+                d.copy_(s, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize(dev)
+        return n * h2d / (a.elapsed_time(b) * 1e-3) / 1e9
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    h2d_rate(1)
+    alone = 0.0
+    for r in range(world):
+        barrier()
+        if r == rank:
+            alone = h2d_rate()
+    barrier()
+    together = h2d_rate()
+
     run(min(args.warmup, 3))
     torch.cuda.synchronize(dev)
     barrier()
@@ -384,7 +550,74 @@ def run_e2e(args, host, dev, barrier, cl):
     run(args.steps)
     b.record()
     barrier()
-    return a.elapsed_time(b), h2d, 4
+    return a.elapsed_time(b), h2d, 4, (alone, together)
+
+
+def run_e2e_modules(args, host, dev, barrier):
+    """The step through the public autograd Functions (the calls the modules make), host
+    buffers in, scalar out, every step: per-call allocation, autograd bookkeeping, the
+    gradient accumulation of x (residual + gather paths) done by autograd."""
+    import arfe_b200 as A
+    strides = host["strides"]
+    scales = [1.0 / s for s in strides[:4]]
+    cl = lambda t: t.contiguous(memory_format=torch.channels_last) if t.dim() == 4 else t
+    keys = E2E_KEYS_LIST + E2E_KEYS
+    bufs = [{k: ([torch.empty_like(cl(t), device=dev) for t in host[k]] if isinstance(host[k], list)
+                 else torch.empty_like(cl(host[k]), device=dev)) for k in keys} for _ in range(2)]
+    main = torch.cuda.current_stream(dev)
+    copier = torch.cuda.Stream(dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+    used = [False, False]
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def issue_copy(k):
+        i = k % 2
+        with torch.cuda.stream(copier):
+            if used[i]:
+                copier.wait_event(done[i])
+            for key in keys:
+                if isinstance(host[key], list):
+                    for d, s in zip(bufs[i][key], host[key]):
+                        d.copy_(s, non_blocking=True)
+                else:
+                    bufs[i][key].copy_(host[key], non_blocking=True)
+            ready[i].record(copier)
+
+    def one(b):
+        x = [t.detach().requires_grad_(True) for t in b["x"]]
+        bsf = b["bsf"].detach().requires_grad_(True)
+        g1 = [t.detach().requires_grad_(True) for t in b["g1"]]
+        g2 = [t.detach().requires_grad_(True) for t in b["g2"]]
+        a_, b_ = b["a"].detach().requires_grad_(True), b["b"].detach().requires_grad_(True)
+        gathered = A.fpn_gather(x, 2)
+        y = A.fpn_apply(x, bsf, g1, g2)
+        ori, lw, lh = A.roi_fuse_split(list(y[:4]), b["rois"], 7, scales, regions=3)
+        z = A.rff_gate(ori, a_, b_)
+        torch.autograd.backward([z, lw, lh, gathered], [b["gz"], b["glw"], b["glh"], b["gbsf"]])
+        return z.detach().sum() + x[4].grad.sum()
+
+    def run(n):
+        issue_copy(0)
+        for k in range(n):
+            i = k % 2
+            if k + 1 < n:
+                issue_copy(k + 1)
+            main.wait_event(ready[i])
+            loss_host.copy_(one(bufs[i]), non_blocking=True)
+            done[i].record(main)
+            used[i] = True
+            main.synchronize()
+
+    run(min(args.warmup, 3))
+    torch.cuda.synchronize(dev)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    run(args.steps)
+    b.record()
+    barrier()
+    return a.elapsed_time(b)
 
 
 def main():
@@ -393,7 +626,12 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=1, choices=[0, 1, 2, 3, 4],
+                    help="index into BASELINE.json configs (default 1: the headline training step)")
+    ap.add_argument("--rois-per-img", type=int, default=None, help="RoIs per image (config 4 sweep: 512 ... 8192)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--nchw", action="store_true", help="reference memory layout through the compatibility kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

@@ -247,6 +247,18 @@ int arfe_fpn_gather_backward(const void* dout, const uint8_t* argmax,
                              const int32_t* H, const int32_t* W, int L, int B,
                              int C, int refine_level, int dtype, int layout,
                              void* const* dfeats, void* stream);
+/* Same, with the other gradient paths of x_l folded into the one write of
+ * dfeats[l]: dfeats[l] = addend[l] + (the gather's routed gradient).  x_l feeds
+ * both the gather (wfpn_dual_spatial.py:102-113) and the gated residual whose
+ * d x_l is d out_l itself (:135), so autograd would otherwise spend one more
+ * pass over the pyramid adding the two.  addend: NULL, or L device pointers
+ * (NULL entries allowed) to fp32 tensors [B,C,H[l],W[l]] in `layout`, 16-byte
+ * aligned -- e.g. the gradient pyramid arfe_roi_fuse_backward_pull wrote. */
+int arfe_fpn_gather_backward_acc(const void* dout, const uint8_t* argmax,
+                                 const int32_t* H, const int32_t* W, int L,
+                                 int B, int C, int refine_level, int dtype,
+                                 int layout, const float* const* addend,
+                                 void* const* dfeats, void* stream);
 
 /* ------------------------------------------------------------------------
  * AR-FPN gated residual:

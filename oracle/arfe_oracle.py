@@ -401,9 +401,11 @@ class WFPNDualSpatial(nn.Module):
 # Synthetic inputs of SURVEY.md section 8(d)
 # --------------------------------------------------------------------------
 def synthetic_rois(K, img_w=1344, img_h=800, batch=1, seed=0,
-                   smin=16.0, smax=600.0):
+                   smin=16.0, smax=600.0, order="interleaved"):
     """Centre uniform in the canvas, sqrt(area) log-uniform in [smin, smax],
-    aspect log-uniform in [0.5, 2], clipped to the image, seeded."""
+    aspect log-uniform in [0.5, 2], clipped to the image, seeded.
+    order: "interleaved" (RoI i -> image i % batch) or "image_major" (per-image
+    blocks, what bbox2roi builds: core/bbox/transforms.py:51-59)."""
     g = torch.Generator().manual_seed(seed)
     u = torch.rand(K, 4, generator=g)
     cx = u[:, 0] * img_w
@@ -418,7 +420,10 @@ def synthetic_rois(K, img_w=1344, img_h=800, batch=1, seed=0,
     y2 = (cy + h / 2).clamp(0, img_h - 1)
     x2 = torch.max(x2, x1 + 1.0)
     y2 = torch.max(y2, y1 + 1.0)
-    b = (torch.arange(K) % batch).float()
+    if order == "image_major":
+        b = ((torch.arange(K) * batch) // max(K, 1)).float()
+    else:
+        b = (torch.arange(K) % batch).float()
     return torch.stack([b, x1, y1, x2, y2], dim=1).float().contiguous()
 
 
@@ -442,3 +447,68 @@ def synthetic_pyramid(batch=1, channels=256, shapes=None, seed=0,
     shapes = shapes or pyramid_shapes()
     return [torch.randn(batch, channels, h, w, generator=g).to(dtype)
             for (h, w) in shapes]
+
+
+# --------------------------------------------------------------------------
+# The bench workload's training step, composed from the restated reference ops
+# --------------------------------------------------------------------------
+def reference_step(host, backend="c", channels=None, dy_full=None, refine_level=2, roi_levels=4):
+    """One training step of the region-aware feature path on the inputs of
+    arfe_b200.workload.host_inputs (plain dict of CPU tensors), in the
+    reference's arithmetic -- what arfe_b200.workload.TrainStep.step computes:
+
+      gathered = wfpn_gather(x)                       wfpn_dual_spatial.py:102-113
+      y        = wfpn_apply(x, bsf, g1, g2)           :118-135
+      F        = cat(ori, lw, lh) RoI features of y   standard_roi_head.py:138-155
+      z        = ori + ori * (a + b)                  multirois_bbox_head.py:175,182
+      backward from (z, lw, lh, gathered) with the incoming gradients
+      (gz, glw, glh, gbsf); d x_l = d y_l + the gather's routed gradient.
+
+    roi_levels: the extractor reads x[:num_inputs] with featmap_strides
+    [4, 8, 16, 32] (configs/_base_/models/faster_rcnn_r50_fpn.py:44,
+    standard_roi_head.py:140).
+    channels: RoIAlign and the gate are independent per channel, so a checker
+    may run the RoI part on a channel subset (all K RoIs, exact per element);
+    the AR-FPN backward then needs d y over ALL channels (its gate gradients
+    are channel sums): pass the tensor under test as dy_full, or leave it None
+    to skip that part.  Returns a dict of tensors plus wall-clock seconds
+    t_fpn / t_roi (the two CPU arms of bench.py)."""
+    import time
+    strides = list(host.get("strides", (4, 8, 16, 32, 64)))
+    P = host.get("out_size", 7)
+    f32 = lambda t: t.detach().float().contiguous()
+    C = host["a"].shape[1]
+    S = list(range(C)) if channels is None else list(channels)
+    c = len(S)
+    out = {}
+    t0 = time.perf_counter()
+    x = [f32(t).requires_grad_(True) for t in host["x"]]
+    bsf = f32(host["bsf"]).requires_grad_(True)
+    g1 = [f32(t).requires_grad_(True) for t in host["g1"]]
+    g2 = [f32(t).requires_grad_(True) for t in host["g2"]]
+    gathered = wfpn_gather(x, refine_level)
+    y = wfpn_apply(x, bsf, g1, g2)
+    t1 = time.perf_counter()
+    yd = [t.detach()[:, S].contiguous().requires_grad_(True) for t in y]
+    F_ = arrff_bbox_feats(yd, f32(host["rois"]), strides[:roi_levels], out_size=P, backend=backend)
+    a = f32(host["a"])[:, S].contiguous().requires_grad_(True)
+    b = f32(host["b"])[:, S].contiguous().requires_grad_(True)
+    ori = F_[:, :c]
+    ori.retain_grad()
+    z = rff_gate(ori, a, b)
+    sub = lambda k: f32(host[k])[:, S].contiguous()
+    torch.autograd.backward([z, F_[:, c:2 * c], F_[:, 2 * c:]], [sub("gz"), sub("glw"), sub("glh")])
+    dy = [t.grad if t.grad is not None else torch.zeros_like(t) for t in yd]
+    t2 = time.perf_counter()
+    out.update(gathered=gathered.detach(), y=[t.detach() for t in y], F=F_.detach(), z=z.detach(),
+               d_ori=ori.grad.detach(), d_ab=a.grad.detach(), dy=dy, channels=S)
+    t3 = t2
+    if channels is None or dy_full is not None:
+        dyf = dy if dy_full is None else [f32(t) for t in dy_full]
+        torch.autograd.backward(list(y) + [gathered], list(dyf) + [f32(host["gbsf"])])
+        t3 = time.perf_counter()
+        out.update(dbsf=bsf.grad, dg1=[t.grad for t in g1], dg2=[t.grad for t in g2],
+                   dx=[t.grad for t in x])
+    out["t_fpn"] = (t1 - t0) + (t3 - t2)
+    out["t_roi"] = t2 - t1
+    return out

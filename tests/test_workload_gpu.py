@@ -47,16 +47,30 @@ print("HASH", h.hexdigest())
 
 def test_pull_one_and_two_producer_warps_agree_bitwise(cuda):
     """The pull backward writes every gradient element once in a fixed order, so the
-    one-producer (ARFE_PULL_NP=1) and two-producer instantiations must agree to the bit."""
+    one-producer instantiation (ARFE_PULL_NP=1, a knob that exists only in the -DARFE_PROFILE
+    build libarfe_b200_prof.so) and the shipped library's two-producer one must agree to the bit."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prof = os.path.join(root, "arfe_b200", "libarfe_b200_prof.so")
+    if not os.path.exists(prof):
+        pytest.skip("profile build of the library not present (python -m arfe_b200.build --profile)")
     out = []
-    for np_ in ("1", "0"):
-        env = dict(os.environ, ARFE_PULL_NP=np_)
+    for env in (dict(os.environ, ARFE_B200_LIB=prof, ARFE_PULL_NP="1"),
+                {k: v for k, v in os.environ.items() if not k.startswith("ARFE_")}):
         r = subprocess.run([sys.executable, "-c", _HASH_SNIPPET % root], env=env, capture_output=True,
                            text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
         out.append([l for l in r.stdout.splitlines() if l.startswith("HASH")][0])
     assert out[0] == out[1]
+
+
+def test_shipped_library_has_no_profiling_knobs():
+    """the default build must contain neither a getenv-selected code path nor
+    the phase-skip switches: no ARFE_* string survives in libarfe_b200.so."""
+    from arfe_b200 import _lib
+    data = open(_lib.LIB_PATH, "rb").read()
+    for knob in (b"ARFE_FWD_SKIP", b"ARFE_BWD_SKIP", b"ARFE_PULL_NP", b"ARFE_PULL_NV", b"ARFE_FWD_NCH",
+                 b"ARFE_FWD_OCC", b"ARFE_APPLY_OCC"):
+        assert knob not in data, knob
