@@ -390,11 +390,13 @@ def run_ours(args, rank, local_rank, world):
     e2e = e2e_mod = None
     if main_cfg:
         e2e_ms, h2d, d2h, h2d_gbps = run_e2e(args, host, dev, barrier, cl)
-        mod_ms = run_e2e_modules(args, host, dev, barrier) if cl else None
-        t = torch.tensor([ms_total, e2e_ms, mod_ms or 0.0, -h2d_gbps[0], -h2d_gbps[1]], dtype=torch.float64, device=dev)
+        mod_ms, mod_dev_ms = run_e2e_modules(args, host, dev, barrier) if cl else (None, None)
+        t = torch.tensor([ms_total, e2e_ms, mod_ms or 0.0, -h2d_gbps[0], -h2d_gbps[1], mod_dev_ms or 0.0],
+                         dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, e2e_ms, mod_ms = float(t[0]), float(t[1]), (float(t[2]) if mod_ms else None)
+        mod_dev_ms = float(t[5]) if mod_dev_ms else None
         e2e = {"value": world * images / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
                "h2d_GBps_per_gpu": {"one_rank_at_a_time": round(-float(t[3]), 1),
@@ -406,6 +408,10 @@ def run_ours(args, rank, local_rank, world):
         if mod_ms:
             e2e_mod = {"value": world * images / (mod_ms / args.steps * 1e-3), "unit": UNIT,
                        "ms_per_step": mod_ms / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "device_resident": {"value": world * images / (mod_dev_ms / args.steps * 1e-3), "unit": UNIT,
+                                           "ms_per_step": mod_dev_ms / args.steps,
+                                           "note": "same calls, inputs already in HBM, no read-back: compare with `value` "
+                                                   "(pre-planned, pre-allocated C-ABI calls) for the cost of the module path"},
                        "path": "arfe_b200.fpn_gather / fpn_apply / roi_fuse_split / rff_gate autograd Functions "
                                "(what WFPNDualSpatial.forward and StandardRoIHead._bbox_forward call; the convs "
                                "between them are stand-in inputs as in `value`), torch.autograd.backward, "
@@ -617,7 +623,17 @@ def run_e2e_modules(args, host, dev, barrier):
     run(args.steps)
     b.record()
     barrier()
-    return a.elapsed_time(b)
+    e2e_ms = a.elapsed_time(b)
+    # the same calls with the inputs already resident in HBM (no copies, no read-back)
+    for _ in range(3):
+        one(bufs[0])
+    barrier()
+    a.record()
+    for _ in range(args.steps):
+        one(bufs[0])
+    b.record()
+    barrier()
+    return e2e_ms, a.elapsed_time(b)
 
 
 def main():

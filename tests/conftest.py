@@ -25,4 +25,9 @@ def cuda():
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+    # The module tests compare cuDNN / cuBLAS convolutions and FCs (PyTorch, outside the
+    # path) with the fp32 CPU oracle: keep them in true fp32 (cuDNN's TF32 default gives
+    # ~1e-3 relative error, e.g. once channels-last inputs select its tensor-core kernels)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     return torch.device("cuda:0")
