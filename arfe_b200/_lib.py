@@ -72,6 +72,8 @@ _SIGNATURES = {
                                 c_int, c_int, c_int, _pp, c_void_p], c_int),
     "arfe_fpn_apply_backward": ([_pp, c_void_p, _pp, _pp, _ip, _ip, c_int, c_int, c_int, c_int,
                                  c_int, c_int, c_int, c_void_p, _pp, _pp, c_void_p], c_int),
+    "arfe_fpn_backward_fused": ([_pp, c_int, c_void_p, _pp, _pp, c_void_p, c_void_p, _ip, _ip, c_int, c_int,
+                                 c_int, c_int, c_int, c_int, c_void_p, _pp, _pp, _pp, c_void_p], c_int),
 }
 
 EXPORTS = tuple(_SIGNATURES)

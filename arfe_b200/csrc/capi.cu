@@ -539,4 +539,36 @@ int arfe_fpn_apply_backward(const void* const* douts, const void* bsf, const voi
   return cuda_result(arfe::launch_fpn_apply_backward(p, dtype, layout, (cudaStream_t)stream), fn);
 }
 
+int arfe_fpn_backward_fused(const void* const* douts, int douts_f32, const void* bsf, const void* const* g1,
+                            const void* const* g2, const void* dgathered, const uint8_t* argmax,
+                            const int32_t* H, const int32_t* W, int L, int B, int C, int refine_level,
+                            int dtype, int layout, float* dbsf, float* const* dg1, float* const* dg2,
+                            void* const* dx, void* stream) {
+  const char* fn = "arfe_fpn_backward_fused";
+  arfe::FpnParams p;
+  int rc = fill_fpn(fn, p, H, W, L, B, C, dtype, layout);
+  if (rc) return rc;
+  REQUIRE(refine_level >= 0 && refine_level < L, ARFE_E_SHAPE, "%s: refine_level=%d", fn, refine_level);
+  REQUIRE(layout == ARFE_NHWC, ARFE_E_UNSUPPORTED,
+          "%s: channels-last tensors only (use arfe_fpn_apply_backward + arfe_fpn_gather_backward_acc)", fn);
+  if (B == 0) return ARFE_OK;
+  REQUIRE(douts && bsf && g1 && g2 && dgathered && dbsf && dg1 && dg2 && dx, ARFE_E_NULL, "%s: NULL argument", fn);
+  REQUIRE(refine_level == 0 || argmax, ARFE_E_NULL, "%s: argmax is NULL", fn);
+  for (int l = 0; l < L; ++l) {
+    REQUIRE(douts[l] && g1[l] && g2[l] && dg1[l] && dg2[l] && dx[l], ARFE_E_NULL, "%s: NULL tensor at level %d", fn, l);
+    p.feats[l] = douts[l]; p.g1[l] = g1[l]; p.g2[l] = g2[l]; p.dg1[l] = dg1[l]; p.dg2[l] = dg2[l];
+    p.outs[l] = dx[l];
+  }
+  p.refine_level = refine_level; p.Hr = H[refine_level]; p.Wr = W[refine_level];
+  p.bsf = bsf; p.dbsf = dbsf; p.gathered = const_cast<void*>(dgathered); p.argmax = const_cast<uint8_t*>(argmax);
+  DeviceGuard guard(dbsf);
+  const cudaError_t e = arfe::launch_fpn_backward_fused_cl(p, dtype, douts_f32 ? 1 : 0, (cudaStream_t)stream);
+  if (e == cudaErrorNotSupported)
+    return fail(ARFE_E_UNSUPPORTED,
+                "%s: needs C %% %d == 0, C <= %d, 16-byte aligned tensors and integer pooling ratios below the "
+                "refine level (use arfe_fpn_apply_backward + arfe_fpn_gather_backward_acc)",
+                fn, dtype == ARFE_F32 ? 4 : 8, dtype == ARFE_F32 ? 256 : 512);
+  return cuda_result(e, fn);
+}
+
 }  // extern "C"

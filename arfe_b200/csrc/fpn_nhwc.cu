@@ -410,6 +410,157 @@ apply_cl(const FpnParams p) {
   }
 }
 
+// ------------------------------------------------- fused AR-FPN backward
+// apply backward + gather backward in ONE pass over the incoming gradient pyramid.
+// x_l feeds the gather (wfpn_dual_spatial.py:102-113) and the gated residual (:135), so
+//   d x_l = d out_l + (gather's routed gradient),
+// and d out_l is also what the gate / bsf gradients are made of.  The warp of refine pixel
+// (b, Y, X) walks the level pixels that read it -- for the pooled levels (exact ratio s)
+// that is exactly its s x s pooling window, for the refine level the pixel itself, for the
+// upsampled levels the level pixel whose nearest destination it is -- so every d out
+// element is read once and every d x element written once: the separate kernels read the
+// pyramid twice.  Arithmetic and summation order are those of apply_cl<kBackward> and
+// gather_bwd_cl / gather_bwd_up_cl (the results are bit-identical to the two-call path).
+// TD = element type of d out (fp32 straight from the RoI backward, or T).
+template <typename TD, int V>
+__device__ __forceinline__ void ldv_as_f32(const TD* __restrict__ p, float (&f)[V]) {
+  if constexpr (sizeof(TD) == 4) {
+#pragma unroll
+    for (int u = 0; u < V; u += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p + u));
+      f[u] = v.x; f[u + 1] = v.y; f[u + 2] = v.z; f[u + 3] = v.w;
+    }
+  } else {
+    static_assert(V == 8, "bf16 vectors are 8 wide");
+    ldv<TD>(p, f);
+  }
+}
+
+template <typename T, typename TD, int NV>
+__global__ void __launch_bounds__(kThreads, (Vec<T>::n * NV > 8 ? 3 : 4))
+fpn_bwd_fused_cl(const FpnParams p, const Exact ex) {
+  constexpr int V = Vec<T>::n;
+  const int Hr = p.Hr, Wr = p.Wr, C = p.C;
+  const int lane = threadIdx.x & 31;
+  const size_t wid = (size_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (wid >= (size_t)p.B * Hr * Wr) return;
+  const int X = (int)(wid % Wr);
+  const int Y = (int)((wid / Wr) % Hr);
+  const int b = (int)(wid / ((size_t)Wr * Hr));
+  const float Lf = (float)p.L;
+  float bs[NV][V], db[NV][V], gg[NV][V];
+  bool on[NV];
+  const size_t rpix = ((size_t)b * Hr + Y) * Wr + X;
+  const T* __restrict__ dga = static_cast<const T*>(p.gathered);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = (v * 32 + lane) * V;
+    on[v] = c < C;
+#pragma unroll
+    for (int u = 0; u < V; ++u) { bs[v][u] = 0.f; db[v][u] = 0.f; gg[v][u] = 0.f; }
+    if (on[v]) {
+      ldv<T>(static_cast<const T*>(p.bsf) + rpix * C + c, bs[v]);
+      ldv<T>(dga + rpix * C + c, gg[v]);
+#pragma unroll
+      for (int u = 0; u < V; ++u) gg[v][u] = __fdiv_rn(gg[v][u], Lf);
+    }
+  }
+  // One level pixel: gate / bsf gradients from d out, then d x = routed + d out
+  // (the order of arfe_fpn_gather_backward_acc).  routed(v, u) = the gather's gradient.
+  auto pixel = [&](int l, size_t pix, auto routed) {
+    const TD* __restrict__ din = static_cast<const TD*>(p.feats[l]);
+    T* __restrict__ dx = static_cast<T*>(p.outs[l]);
+    const float a1 = ldf(static_cast<const T*>(p.g1[l]) + pix), a2 = ldf(static_cast<const T*>(p.g2[l]) + pix);
+    const float t1 = tanhf(fmaxf(a1, 0.f)), t2 = tanhf(fmaxf(a2, 0.f));
+    const float gate = t1 + t2;
+    float sum = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      if (!on[v]) continue;
+      float f[V];
+      ldv_as_f32<TD, V>(din + pix * C + (v * 32 + lane) * V, f);
+#pragma unroll
+      for (int u = 0; u < V; ++u) {
+        sum = fmaf(f[u], bs[v][u], sum);
+        db[v][u] = fmaf(f[u], gate, db[v][u]);
+        f[u] = routed(v, u) + f[u];
+      }
+      stv<T>(dx + pix * C + (v * 32 + lane) * V, f);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if (lane == 0) {
+      p.dg1[l][pix] = a1 > 0.f ? sum * (1.f - t1 * t1) : 0.f;
+      p.dg2[l][pix] = a2 > 0.f ? sum * (1.f - t2 * t2) : 0.f;
+    }
+  };
+  // ---- pooled levels: the s x s window of this refine pixel, argmax cell gets g / L ----
+  for (int l = 0; l < p.refine_level; ++l) {
+    const int H = p.H[l], W = p.W[l], s = ex.s[l];
+    unsigned arg[NV][V / 4];
+    const uint8_t* a = p.argmax + ((((size_t)l * p.B + b) * Hr + Y) * Wr + X) * C;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int u = 0; u < V / 4; ++u)
+        arg[v][u] = on[v] ? __ldg(reinterpret_cast<const unsigned*>(a + (v * 32 + lane) * V) + u) : 0u;
+    for (int dy = 0; dy < s; ++dy)
+      for (int dxx = 0; dxx < s; ++dxx) {
+        const unsigned pos = (unsigned)(dy * s + dxx);
+        pixel(l, ((size_t)b * H + (size_t)s * Y + dy) * W + (size_t)s * X + dxx, [&](int v, int u) {
+          return (((arg[v][u >> 2] >> (8 * (u & 3))) & 255u) == pos) ? gg[v][u] : 0.f;
+        });
+      }
+  }
+  // ---- the refine level itself ----
+  pixel(p.refine_level, rpix, [&](int v, int u) { return gg[v][u]; });
+  // ---- upsampled levels: the level pixel (at most one) whose nearest destination this is;
+  // its gather gradient = sum of d(gathered) over the refine pixels that read it, / L ----
+  for (int l = p.refine_level + 1; l < p.L; ++l) {
+    const int H = p.H[l], W = p.W[l];
+    int ya, yb, xa, xb;
+    dst_range(Y, Hr, H, ya, yb);
+    dst_range(X, Wr, W, xa, xb);
+    for (int y = ya; y < yb; ++y)
+      for (int x = xa; x < xb; ++x) {
+        const float sy = (float)Hr / (float)H, sx = (float)Wr / (float)W;
+        int Ya = (int)floorf((float)y * sy) - 1; if (Ya < 0) Ya = 0;
+        int Yb = (int)ceilf((float)(y + 1) * sy) + 1; if (Yb > Hr) Yb = Hr;
+        int Xa = (int)floorf((float)x * sx) - 1; if (Xa < 0) Xa = 0;
+        int Xb = (int)ceilf((float)(x + 1) * sx) + 1; if (Xb > Wr) Xb = Wr;
+        while (Ya < Yb && nearest_src(Ya, H, Hr) != y) ++Ya;
+        while (Yb > Ya && nearest_src(Yb - 1, H, Hr) != y) --Yb;
+        while (Xa < Xb && nearest_src(Xa, W, Wr) != x) ++Xa;
+        while (Xb > Xa && nearest_src(Xb - 1, W, Wr) != x) --Xb;
+        float r[NV][V];
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+#pragma unroll
+          for (int u = 0; u < V; ++u) r[v][u] = 0.f;
+        for (int Y2 = Ya; Y2 < Yb; ++Y2)
+          for (int X2 = Xa; X2 < Xb; ++X2)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              if (!on[v]) continue;
+              float t[V];
+              ldv<T>(dga + (((size_t)b * Hr + Y2) * Wr + X2) * C + (v * 32 + lane) * V, t);
+#pragma unroll
+              for (int u = 0; u < V; ++u) r[v][u] += t[u];
+            }
+        pixel(l, ((size_t)b * H + y) * W + x, [&](int v, int u) { return __fdiv_rn(r[v][u], Lf); });
+      }
+  }
+  float* __restrict__ o = p.dbsf + rpix * C;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    if (!on[v]) continue;
+    const int c = (v * 32 + lane) * V;
+#pragma unroll
+    for (int u = 0; u < V; u += 4)
+      *reinterpret_cast<float4*>(o + c + u) = make_float4(db[v][u], db[v][u + 1], db[v][u + 2], db[v][u + 3]);
+  }
+}
+
 // Pooling ratio of each level below the refine level when it is an exact integer.
 inline Exact exact_ratios(const FpnParams& p) {
   Exact ex;
@@ -520,6 +671,34 @@ cudaError_t launch_fpn_apply_forward_cl(const FpnParams& p, int dtype, cudaStrea
 }
 cudaError_t launch_fpn_apply_backward_cl(const FpnParams& p, int dtype, cudaStream_t stream) {
   return launch_apply_cl<true>(p, dtype, stream);
+}
+
+// dout_f32: the incoming gradients are fp32 whatever the feature dtype is.
+// cudaErrorNotSupported: not a case of the fused kernel (the caller uses the two calls).
+cudaError_t launch_fpn_backward_fused_cl(const FpnParams& p, int dtype, int dout_f32, cudaStream_t stream) {
+  const int V = dtype == 0 ? 4 : 8;
+  const size_t warps = (size_t)p.B * p.Hr * p.Wr;
+  if (warps == 0) return cudaSuccess;
+  const int nv = (p.C + 32 * V - 1) / (32 * V);
+  if (p.C % V || nv > 2) return cudaErrorNotSupported;
+  const Exact ex = exact_ratios(p);
+  for (int l = 0; l < p.L; ++l) {
+    if (l < p.refine_level && (ex.s[l] == 0 || ex.s[l] > 15)) return cudaErrorNotSupported;
+    if (!a16(p.feats[l]) || !a16(p.outs[l])) return cudaErrorNotSupported;
+  }
+  if (!a16(p.bsf) || !a16(p.gathered) || !a16(p.dbsf) || (reinterpret_cast<uintptr_t>(p.argmax) & 3u))
+    return cudaErrorNotSupported;
+  const unsigned grid = blocks_for(warps, kThreads / 32);
+#define ARFE_FUSED(TT, TD, NV) fpn_bwd_fused_cl<TT, TD, NV><<<grid, kThreads, 0, stream>>>(p, ex)
+  if (dtype == 0) {
+    if (nv == 1) ARFE_FUSED(float, float, 1); else ARFE_FUSED(float, float, 2);
+  } else if (dout_f32) {
+    if (nv == 1) ARFE_FUSED(__nv_bfloat16, float, 1); else ARFE_FUSED(__nv_bfloat16, float, 2);
+  } else {
+    if (nv == 1) ARFE_FUSED(__nv_bfloat16, __nv_bfloat16, 1); else ARFE_FUSED(__nv_bfloat16, __nv_bfloat16, 2);
+  }
+#undef ARFE_FUSED
+  return cudaGetLastError();
 }
 
 }  // namespace arfe

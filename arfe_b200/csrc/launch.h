@@ -110,6 +110,7 @@ cudaError_t launch_fpn_gather_backward_cl(const FpnParams& p, int dtype, unsigne
                                           cudaStream_t stream);
 cudaError_t launch_fpn_apply_forward_cl(const FpnParams& p, int dtype, cudaStream_t stream);
 cudaError_t launch_fpn_apply_backward_cl(const FpnParams& p, int dtype, cudaStream_t stream);
+cudaError_t launch_fpn_backward_fused_cl(const FpnParams& p, int dtype, int dout_f32, cudaStream_t stream);
 
 cudaError_t launch_fpn_gather_forward(const FpnParams& p, int dtype, int layout,
                                       cudaStream_t stream);

@@ -20,8 +20,10 @@ import torch
 from . import _lib as L
 
 STRIDES = (4, 8, 16, 32, 64)
-KERNELS = ("fpn_gather_fwd", "fpn_apply_fwd", "roi_fuse_fwd", "rff_gate_fwd",
-           "rff_gate_bwd", "roi_fuse_bwd", "fpn_apply_bwd", "fpn_gather_bwd")
+KERNELS_NCHW = ("fpn_gather_fwd", "fpn_apply_fwd", "roi_fuse_fwd", "rff_gate_fwd",
+                "rff_gate_bwd", "roi_fuse_bwd", "fpn_apply_bwd", "fpn_gather_bwd")
+# channels-last: the AR-FPN backward is one fused pass over the gradient pyramid
+KERNELS = KERNELS_NCHW[:6] + ("fpn_bwd",)
 
 
 def pyramid_shapes(img_h=800, img_w=1344, strides=STRIDES):
@@ -204,6 +206,7 @@ class TrainStep:
         else:         # memory [K][R*C*49]: a row is one RoI
             self.gate_rows, self.gate_n, self.gate_stride = K, C * self.PP, R * C * self.PP
         self.stream = L.stream_ptr(device)
+        self.kernels = KERNELS if self.cl else KERNELS_NCHW
 
     # -- the eight ops; each returns the C return code ----------------------
     def fpn_gather_fwd(self):
@@ -309,6 +312,15 @@ class TrainStep:
             self.gbsf.data_ptr(), self.argmax.data_ptr(), self.H, self.W, self.nlev, self.B,
             self.C, 2, self.dt, self.layout, self.p_dy, self.p_dx, self.stream)
 
+    def fpn_bwd(self):
+        """apply backward + gather backward fused (channels-last): dbsf, dg1, dg2 and
+        d x_l = d out_l + the gather's routed gradient, d out (fp32, straight from the RoI
+        backward) read once."""
+        return self.lib.arfe_fpn_backward_fused(
+            self.p_dy, 1, self.bsf.data_ptr(), self.p_g1, self.p_g2, self.gbsf.data_ptr(),
+            self.argmax.data_ptr(), self.H, self.W, self.nlev, self.B, self.C, 2, self.dt, self.layout,
+            self.dbsf.data_ptr(), self.p_dg1, self.p_dg2, self.p_dx, self.stream)
+
     def glue_before_roi_bwd(self):
         """torch plumbing between our kernels: assemble dF (stand-in for the
         conv backward of the two context branches, which stays on PyTorch) and,
@@ -348,7 +360,7 @@ class TrainStep:
         if timer is None and getattr(self, "graph", None) is not None:
             self.graph.replay()
             return
-        self.run_ops(KERNELS, timer)
+        self.run_ops(self.kernels, timer)
 
     def capture(self):
         """Capture the step (the same launches, second stream included) into a CUDA graph:
@@ -372,7 +384,7 @@ class TrainStep:
         apply bwd 1 | 2, gather bwd 2 (pooled levels + small levels; one merged launch was
         measured slower: 49 us vs 34 + 11 us, a third wave of CTAs) | 2.  (Channels-last:
         plan and bin run on the second stream of plan_async; same count.)"""
-        return (1 + 1 + 3 + 2 + 4 + 1 + 2) if self.cl else (1 + 1 + 1 + 2 + 1 + 2 + 2)
+        return (1 + 1 + 3 + 2 + 4 + 1) if self.cl else (1 + 1 + 1 + 2 + 1 + 2 + 2)
 
     # -- algorithmic bytes per launch (DESIGN.md section 5) ------------------
     def algorithmic_bytes(self):
@@ -394,6 +406,8 @@ class TrainStep:
             "roi_fuse_bwd": out_roi + B * C * Pr * 4 + 20 * K,               # fp32 accumulators
             "fpn_apply_bwd": pyr + ref * e + 2 * B * P * e + ref * 4 + 2 * B * P * 4,
             "fpn_gather_bwd": ref * e + 2 * ref + pyr + B * C * P * 4,          # + the fp32 addend (dy)
+            # fused: d out (fp32) once, d x once, bsf + d gathered + argmax + dbsf, gate maps in and out
+            "fpn_bwd": B * C * P * 4 + pyr + 2 * ref * e + 2 * ref + ref * 4 + 2 * B * P * e + 2 * B * P * 4,
         }
 
 
@@ -403,7 +417,7 @@ class TrainStep:
 FWD_OPS = ("fpn_gather_fwd", "fpn_apply_fwd", "roi_fuse_fwd", "rff_gate_fwd")
 ROI_FWD = ("roi_fuse_fwd", "rff_gate_fwd")
 ROI_BWD = ("rff_gate_bwd", "roi_fuse_bwd")
-FPN_BWD = ("fpn_apply_bwd", "fpn_gather_bwd")
+FPN_BWD = ("fpn_bwd",)
 RETINA_STRIDES = (8, 16, 32, 64, 128)
 
 
@@ -431,7 +445,7 @@ class Case:
 
     def launches_per_step(self):
         cl = {"fpn_gather_fwd": 1, "fpn_apply_fwd": 1, "roi_fuse_fwd": 3, "rff_gate_fwd": 1,
-              "rff_gate_bwd": 1, "roi_fuse_bwd": 4, "fpn_apply_bwd": 1, "fpn_gather_bwd": 2}
+              "rff_gate_bwd": 1, "roi_fuse_bwd": 4, "fpn_apply_bwd": 1, "fpn_gather_bwd": 2, "fpn_bwd": 1}
         nchw = dict(cl, roi_fuse_fwd=1, roi_fuse_bwd=1, fpn_apply_bwd=2)
         return sum((cl if st.cl else nchw)[n] for _, st, names in self.parts for n in names)
 

@@ -370,7 +370,7 @@ def run_ours(args, rank, local_rank, world):
         host = wl.host_inputs(BATCH, args.rois_per_img or ROIS_PER_IMG, CHANNELS, seed=rank, pin=True,
                               channels_last=cl)
         step = wl.TrainStep(host, dev, channels_last=cl)
-        case = wl.Case(WORKLOAD, BATCH, [("", step, wl.KERNELS)], "f32")
+        case = wl.Case(WORKLOAD, BATCH, [("", step, step.kernels)], "f32")
     else:
         case = wl.make_case(args.config, dev, seed=rank, rois_per_img=args.rois_per_img)
         step = case.parts[0][1]
@@ -441,7 +441,9 @@ def run_ours(args, rank, local_rank, world):
                        "memory_format": "torch.channels_last (fast path)" if cl else "NCHW (reference layout, compatibility kernels)",
                        "roi_tensors": ("regions as separate tensors (ori | lw | lh), read/written in place: no cat / slice copies in the step"
                                        if step.split else "concatenated [K, 3C, 7, 7]; torch slice copies between the kernels are inside the step"),
-                       "backward": "d x_l = d out_l + gather gradient in one write (arfe_fpn_gather_backward_acc); "
+                       "backward": ("AR-FPN backward fused (arfe_fpn_backward_fused: dbsf, d gate maps and d x_l = d out_l + gather "
+                                    "gradient, d out read once); " if cl else
+                                    "d x_l = d out_l + gather gradient in one write (arfe_fpn_gather_backward_acc); ") +
                                    "d lw / d lh are separate input tensors",
                        "streams": ("RoI plan and tile binning (2 kernels) run on a second stream under the AR-FPN forward kernels; "
                                    "the per-op times of roi_fuse_fwd / roi_fuse_bwd exclude them, the step time includes them"

@@ -284,6 +284,27 @@ int arfe_fpn_apply_backward(const void* const* douts, const void* bsf,
                             float* dbsf, float* const* dg1, float* const* dg2,
                             void* stream);
 
+/* The whole AR-FPN backward in one pass over the incoming gradient pyramid
+ * (channels-last only): what arfe_fpn_apply_backward followed by
+ * arfe_fpn_gather_backward_acc(addend = douts) compute, bit for bit, reading
+ * every d out element once:
+ *   dbsf, dg1[l], dg2[l]  as arfe_fpn_apply_backward        (wfpn_dual_spatial.py:118-135)
+ *   dx[l] = douts[l] + gradient of the gather w.r.t. x_l     (:102-113, :135)
+ * douts[l]: [B,C,H[l],W[l]] in `dtype`, or fp32 when douts_f32 != 0 (the
+ * accumulators arfe_roi_fuse_backward_pull wrote); dgathered: [B,C,Hr,Wr]
+ * `dtype` = d(gather output); argmax from arfe_fpn_gather_forward; dx[l]:
+ * `dtype`, fully written.  ARFE_E_UNSUPPORTED (nothing launched) when the case
+ * is outside the fused kernel: NCHW, C % (4|8) != 0, C > 256 (fp32) / 512
+ * (bf16), or a non-integer pooling ratio below the refine level. */
+int arfe_fpn_backward_fused(const void* const* douts, int douts_f32,
+                            const void* bsf, const void* const* g1,
+                            const void* const* g2, const void* dgathered,
+                            const uint8_t* argmax, const int32_t* H,
+                            const int32_t* W, int L, int B, int C,
+                            int refine_level, int dtype, int layout,
+                            float* dbsf, float* const* dg1, float* const* dg2,
+                            void* const* dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,13 @@ K = int(os.environ.get("PROBE_K", "512"))
 B = int(os.environ.get("PROBE_B", "2"))
 dt = torch.bfloat16 if os.environ.get("PROBE_BF16") else torch.float32
 host = wl.host_inputs(B, K, 256, channels_last=True, device=dev, dtype=dt)
+if os.environ.get("PROBE_SORT"):
+    # RoIs ordered by (image, level of the original box, top edge): a locality probe
+    r = host["rois"]
+    s_ = torch.sqrt((r[:, 3] - r[:, 1]) * (r[:, 4] - r[:, 2]))
+    lv = torch.floor(torch.log2(s_ / 56 + 1e-6)).clamp(0, 3)
+    key = r[:, 0] * 1e6 + (3 - lv) * 1e5 + r[:, 2] * (1.0 / torch.pow(2.0, lv)) 
+    host["rois"] = r[torch.argsort(key)].contiguous()
 st = wl.TrainStep(host, dev)
 st.step()
 torch.cuda.synchronize()

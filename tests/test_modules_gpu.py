@@ -88,7 +88,10 @@ def test_extractor_fp16_contract(oracle, cuda):
     ext.roi_feats_split = True
     parts = ext.forward_regions([_cl(f) for f in fg], rois.to(cuda), regions=3, facs=1)
     assert all(p.dtype == torch.float16 for p in parts)
-    assert torch.equal(torch.cat(parts, 1), got3)
+    # another kernel (channels-last ring) than got3's: fp32 results agree to ~1e-7, so the
+    # fp16 roundings may differ by one ulp
+    err = (torch.cat(parts, 1).float() - got3.float()).abs()
+    assert bool((err <= 2.0 ** -10 * got3.float().abs() + 1e-6).all()), float(err.max())
 
 
 def test_extractor_hooks_follow_reference_order(oracle, cuda):

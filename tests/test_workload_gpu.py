@@ -28,7 +28,7 @@ def test_step_graph_replay_matches_plain_launches(cuda):
     torch.cuda.synchronize()
     for a, b in zip(ref, _outputs(st)):
         assert torch.equal(a, b)
-    assert st.launches_per_step() == 14
+    assert st.launches_per_step() == 13
 
 
 _HASH_SNIPPET = r"""
