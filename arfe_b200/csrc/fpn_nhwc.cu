@@ -18,6 +18,7 @@
 #include <type_traits>
 
 #include "fpn_common.cuh"
+#include "tma.cuh"
 
 namespace arfe {
 using namespace fpn;
@@ -34,6 +35,22 @@ __device__ __forceinline__ void ldv(const T* __restrict__ p, float (&f)[Vec<T>::
     f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
   } else {
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    }
+  }
+}
+// V consecutive channels from shared memory
+template <typename T>
+__device__ __forceinline__ void lds_vec(const unsigned char* p, float (&f)[Vec<T>::n]) {
+  if constexpr (sizeof(T) == 4) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  } else {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -561,6 +578,210 @@ fpn_bwd_fused_cl(const FpnParams p, const Exact ex) {
   }
 }
 
+// ---------------------------------------- fused AR-FPN backward, TMA-staged
+// Same arithmetic as fpn_bwd_fused_cl, other data movement.  The register kernel keeps
+// one level pixel (1 KB) in flight per warp and pays a DRAM latency per pixel: it runs at
+// half the copy bandwidth however it is tuned.  In NHWC
+// everything a refine pixel needs is a handful of CONTIGUOUS pieces -- the s rows of its
+// s x s window on every pooled level (s px x C channels each), its own pixel, the one
+// pixel of each upsampled level, its bsf / d(gathered) pixels and its argmax bytes -- so
+// the warp fetches the whole footprint (~25 KB at C = 256 fp32) with one bulk async copy
+// (TMA) per piece into its own shared-memory buffer, signalled by one mbarrier, and
+// computes from shared memory: ~25 KB in flight per warp instead of 1 KB, no
+// registers held by loads.  Lane i owns level pixel i of the footprint for the scalar
+// work (gate maps in, tanh, d gate out), so those loads and stores are parallel too.
+// d x of the levels above the refine level (a sum over the refine pixels reading one
+// level pixel) is finished by gather_bwd_up_cl with d out as the addend (2 % of the pyramid).
+constexpr int kFusedWarps = 8;
+constexpr int kFusedMaxJobs = 32;   // bulk copies per footprint (one per lane)
+constexpr int kFusedMaxPix = 32;    // level pixels per footprint (one per lane)
+
+struct FusedGeom {
+  int s[kMaxLevels];        // pooled levels: window side; 0 above the refine level
+  int buf_bytes;            // footprint bytes, rounded up to 128
+  int items;                // B * Hr * Wr
+};
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(kFusedWarps * 32, 1)
+fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
+  constexpr int V = Vec<T>::n;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  unsigned char* buf = smem_raw + 128 + (size_t)warp * geo.buf_bytes;
+  uint64_t* bar = bars + warp;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int Hr = p.Hr, Wr = p.Wr, C = p.C, R = p.refine_level;
+  const uint32_t pixB = (uint32_t)C * 4u;            // d out is fp32
+  const uint32_t featB = (uint32_t)C * sizeof(T);    // bsf / d(gathered) pixel
+  const float Lf = (float)p.L;
+  uint32_t phase = 0;
+  for (int item = blockIdx.x * kFusedWarps + warp; item < geo.items; item += gridDim.x * kFusedWarps) {
+    const int X = item % Wr;
+    const int Y = (item / Wr) % Hr;
+    const int b = item / (Wr * Hr);
+    const size_t rpix = ((size_t)b * Hr + Y) * Wr + X;
+    // ---- footprint: copy jobs (lane j issues job j) and level pixels (lane i owns pixel i)
+    const void* src = nullptr;
+    uint32_t dst = 0, bytes = 0, off = 0, total = 0;
+    int job = 0, npix = 0;
+    int my_l = -1;
+    size_t my_pix = 0;
+    uint32_t loff[kMaxLevels];  // buffer offset of level l's pixels
+    int lw[kMaxLevels];         // pixels per row of level l's piece (0: none)
+#pragma unroll
+    for (int l = 0; l < kMaxLevels; ++l) {
+      loff[l] = off;
+      lw[l] = 0;
+      if (l >= p.L) continue;
+      const int H = p.H[l], W = p.W[l];
+      int ya, yb, xa, xb;
+      if (l < R) { ya = geo.s[l] * Y; yb = ya + geo.s[l]; xa = geo.s[l] * X; xb = xa + geo.s[l]; }
+      else if (l == R) { ya = Y; yb = Y + 1; xa = X; xb = X + 1; }
+      else { dst_range(Y, Hr, H, ya, yb); dst_range(X, Wr, W, xa, xb); }
+      const int ny = yb - ya, nx = xb - xa;
+      if (ny <= 0 || nx <= 0) continue;
+      lw[l] = nx;
+      const uint32_t rowB = (uint32_t)nx * pixB;
+      if (lane >= job && lane < job + ny) {
+        const int r = lane - job;
+        src = static_cast<const float*>(p.feats[l]) + (((size_t)b * H + ya + r) * W + xa) * C;
+        dst = off + (uint32_t)r * rowB;
+        bytes = rowB;
+      }
+      if (lane >= npix && lane < npix + ny * nx) {
+        const int q = lane - npix;
+        my_l = l;
+        my_pix = ((size_t)b * H + ya + q / nx) * W + xa + q % nx;
+      }
+      job += ny;
+      npix += ny * nx;
+      off += (uint32_t)ny * rowB;
+    }
+    const uint32_t o_bsf = off, o_dga = off + featB, o_arg = off + 2 * featB;
+    if (lane == job) { src = static_cast<const T*>(p.bsf) + rpix * C; dst = o_bsf; bytes = featB; }
+    if (lane == job + 1) { src = static_cast<const T*>(p.gathered) + rpix * C; dst = o_dga; bytes = featB; }
+    if (lane >= job + 2 && lane < job + 2 + R) {
+      const int l = lane - job - 2;
+      src = p.argmax + (((size_t)l * p.B + b) * Hr * Wr + (size_t)Y * Wr + X) * C;
+      dst = o_arg + (uint32_t)l * C;
+      bytes = (uint32_t)C;
+    }
+    total = o_arg + (uint32_t)R * C;
+    // ---- issue: the previous item's reads of the buffer are done (end-of-loop __syncwarp)
+    if (lane == 0) mbar_arrive_expect_tx(bar, total);
+    __syncwarp();
+    if (bytes) bulk_g2s(buf + dst, src, bytes, bar);
+    // ---- the scalar work of this lane's level pixel, while the copies fly
+    float a1 = 0.f, a2 = 0.f, t1 = 0.f, t2 = 0.f, mysum = 0.f;
+    if (my_l >= 0) {
+      a1 = ldf(static_cast<const T*>(p.g1[my_l]) + my_pix);
+      a2 = ldf(static_cast<const T*>(p.g2[my_l]) + my_pix);
+      t1 = tanhf(fmaxf(a1, 0.f));
+      t2 = tanhf(fmaxf(a2, 0.f));
+    }
+    const float mygate = t1 + t2;
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    // ---- compute from shared memory
+    float bs[NV][V], db[NV][V], gg[NV][V];
+    bool on[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = (v * 32 + lane) * V;
+      on[v] = c < C;
+#pragma unroll
+      for (int u = 0; u < V; ++u) { bs[v][u] = 0.f; db[v][u] = 0.f; gg[v][u] = 0.f; }
+      if (on[v]) {
+        lds_vec<T>(buf + o_bsf + (uint32_t)c * sizeof(T), bs[v]);
+        lds_vec<T>(buf + o_dga + (uint32_t)c * sizeof(T), gg[v]);
+#pragma unroll
+        for (int u = 0; u < V; ++u) gg[v][u] = __fdiv_rn(gg[v][u], Lf);
+      }
+    }
+    int q = 0;  // running level-pixel index == owning lane
+    auto pixel = [&](int l, uint32_t boff, size_t pix, bool write_dx, auto routed) {
+      T* __restrict__ dx = static_cast<T*>(p.outs[l]);
+      const float gate = __shfl_sync(0xffffffffu, mygate, q);
+      float sum = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if (!on[v]) continue;
+        float f[V];
+        const float* sp = reinterpret_cast<const float*>(buf + boff) + (v * 32 + lane) * V;
+#pragma unroll
+        for (int u = 0; u < V; u += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(sp + u);
+          f[u] = t.x; f[u + 1] = t.y; f[u + 2] = t.z; f[u + 3] = t.w;
+        }
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+          sum = fmaf(f[u], bs[v][u], sum);
+          db[v][u] = fmaf(f[u], gate, db[v][u]);
+          f[u] = routed(v, u) + f[u];
+        }
+        if (write_dx) stv<T>(dx + pix * C + (v * 32 + lane) * V, f);
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+      if (lane == q) mysum = sum;
+      ++q;
+    };
+#pragma unroll
+    for (int l = 0; l < kMaxLevels; ++l) {
+      if (l >= p.L || lw[l] == 0) continue;
+      const int H = p.H[l], W = p.W[l];
+      if (l < R) {
+        const int s = geo.s[l];
+        unsigned arg[NV][V / 4];
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+#pragma unroll
+          for (int u = 0; u < V / 4; ++u)
+            arg[v][u] = on[v] ? *reinterpret_cast<const unsigned*>(buf + o_arg + (uint32_t)l * C + (v * 32 + lane) * V + 4 * u) : 0u;
+        for (int dy = 0; dy < s; ++dy)
+          for (int dxx = 0; dxx < s; ++dxx) {
+            const unsigned pos = (unsigned)(dy * s + dxx);
+            pixel(l, loff[l] + (uint32_t)(dy * s + dxx) * pixB,
+                  ((size_t)b * H + (size_t)s * Y + dy) * W + (size_t)s * X + dxx, true, [&](int v, int u) {
+                    return (((arg[v][u >> 2] >> (8 * (u & 3))) & 255u) == pos) ? gg[v][u] : 0.f;
+                  });
+          }
+      } else if (l == R) {
+        pixel(l, loff[l], rpix, true, [&](int v, int u) { return gg[v][u]; });
+      } else {
+        // upsampled level: at most one pixel; its d x is written by gather_bwd_up_cl
+        int ya, yb, xa, xb;
+        dst_range(Y, Hr, H, ya, yb);
+        dst_range(X, Wr, W, xa, xb);
+        for (int y = ya; y < yb; ++y)
+          for (int x = xa; x < xb; ++x)
+            pixel(l, loff[l] + (uint32_t)((y - ya) * (xb - xa) + (x - xa)) * pixB, 0, false,
+                  [&](int, int) { return 0.f; });
+      }
+    }
+    if (my_l >= 0) {
+      p.dg1[my_l][my_pix] = a1 > 0.f ? mysum * (1.f - t1 * t1) : 0.f;
+      p.dg2[my_l][my_pix] = a2 > 0.f ? mysum * (1.f - t2 * t2) : 0.f;
+    }
+    float* __restrict__ o = p.dbsf + rpix * C;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      if (!on[v]) continue;
+      const int c = (v * 32 + lane) * V;
+#pragma unroll
+      for (int u = 0; u < V; u += 4)
+        *reinterpret_cast<float4*>(o + c + u) = make_float4(db[v][u], db[v][u + 1], db[v][u + 2], db[v][u + 3]);
+    }
+    __syncwarp();  // every lane is done with the buffer before the next item's copies land in it
+  }
+}
+
 // Pooling ratio of each level below the refine level when it is an exact integer.
 inline Exact exact_ratios(const FpnParams& p) {
   Exact ex;
@@ -688,6 +909,65 @@ cudaError_t launch_fpn_backward_fused_cl(const FpnParams& p, int dtype, int dout
   }
   if (!a16(p.bsf) || !a16(p.gathered) || !a16(p.dbsf) || (reinterpret_cast<uintptr_t>(p.argmax) & 3u))
     return cudaErrorNotSupported;
+  // ---- TMA-staged kernel: fp32 d out, footprint of a refine pixel within one lane-set ----
+  if ((dtype == 0 || dout_f32) && p.C % 16 == 0) {
+    FusedGeom geo;
+    int jobs = 2 + p.refine_level, pix = 1;
+    size_t bytes = 0;
+    for (int l = 0; l < kMaxLevels; ++l) geo.s[l] = 0;
+    for (int l = 0; l < p.L; ++l) {
+      if (l < p.refine_level) { geo.s[l] = ex.s[l]; jobs += ex.s[l]; pix += ex.s[l] * ex.s[l]; bytes += (size_t)ex.s[l] * ex.s[l]; }
+      else if (l > p.refine_level) {
+        // upsampled level (smaller map): at most ceil(H / Hr) + 1 == 2 rows / columns can map to one refine pixel
+        const int my = (p.H[l] + p.Hr - 1) / p.Hr + 1, mx = (p.W[l] + p.Wr - 1) / p.Wr + 1;
+        if (p.H[l] > p.Hr || p.W[l] > p.Wr) { jobs = 1 << 20; break; }
+        jobs += my; pix += my * mx; bytes += (size_t)my * mx;
+      } else { jobs += 1; bytes += 1; }
+    }
+    bytes = bytes * p.C * 4 + 2 * (size_t)p.C * (dtype == 0 ? 4 : 2) + (size_t)p.refine_level * p.C;
+    bytes = (bytes + 127) / 128 * 128;
+    const size_t smem = 128 + bytes * kFusedWarps;
+    if (jobs <= kFusedMaxJobs && pix <= kFusedMaxPix && smem <= 220 * 1024 && warps < (1u << 30)) {
+      geo.buf_bytes = (int)bytes;
+      geo.items = (int)warps;
+      const int sms = sm_count();
+      const int per_sm = (int)((220 * 1024) / smem) < 1 ? 1 : (int)((220 * 1024) / smem);
+      int grid = sms * (per_sm > 2 ? 2 : per_sm);
+      const int need = (int)((warps + kFusedWarps - 1) / kFusedWarps);
+      if (grid > need) grid = need;
+      cudaError_t e;
+#define ARFE_FUSED_TMA(TT, NV)                                                                        \
+  do {                                                                                                \
+    if ((e = cudaFuncSetAttribute(fpn_bwd_fused_tma<TT, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e; \
+    fpn_bwd_fused_tma<TT, NV><<<grid, kFusedWarps * 32, smem, stream>>>(p, geo);                      \
+  } while (0)
+      if (dtype == 0) { if (nv == 1) ARFE_FUSED_TMA(float, 1); else ARFE_FUSED_TMA(float, 2); }
+      else { if (nv == 1) ARFE_FUSED_TMA(__nv_bfloat16, 1); else ARFE_FUSED_TMA(__nv_bfloat16, 2); }
+#undef ARFE_FUSED_TMA
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      // d x of the levels above the refine level: gather gradient + d out
+      FpnParams q = p;
+      UpLevels ul;
+      size_t st = 0;
+      int n = 0;
+      for (int l = 0; l < kMaxLevels; ++l) q.addend[l] = nullptr;
+      for (int l = p.refine_level + 1; l < p.L; ++l) {
+        ul.start[n] = st;
+        ul.level[n] = l;
+        st += (size_t)p.B * p.H[l] * p.W[l] * (p.C / V);
+        q.addend[l] = static_cast<const float*>(p.feats[l]);
+        ++n;
+      }
+      ul.n = n;
+      for (int j = n; j <= kMaxLevels; ++j) ul.start[j] = st;
+      for (int j = n; j < kMaxLevels; ++j) ul.level[j] = 0;
+      if (st) {
+        if (dtype == 0) gather_bwd_up_cl<float><<<blocks_for(st, kThreads), kThreads, 0, stream>>>(q, ul);
+        else gather_bwd_up_cl<__nv_bfloat16><<<blocks_for(st, kThreads), kThreads, 0, stream>>>(q, ul);
+      }
+      return cudaGetLastError();
+    }
+  }
   const unsigned grid = blocks_for(warps, kThreads / 32);
 #define ARFE_FUSED(TT, TD, NV) fpn_bwd_fused_cl<TT, TD, NV><<<grid, kThreads, 0, stream>>>(p, ex)
   if (dtype == 0) {

@@ -384,7 +384,7 @@ class TrainStep:
         apply bwd 1 | 2, gather bwd 2 (pooled levels + small levels; one merged launch was
         measured slower: 49 us vs 34 + 11 us, a third wave of CTAs) | 2.  (Channels-last:
         plan and bin run on the second stream of plan_async; same count.)"""
-        return (1 + 1 + 3 + 2 + 4 + 1) if self.cl else (1 + 1 + 1 + 2 + 1 + 2 + 2)
+        return (1 + 1 + 3 + 2 + 4 + 2) if self.cl else (1 + 1 + 1 + 2 + 1 + 2 + 2)
 
     # -- algorithmic bytes per launch (DESIGN.md section 5) ------------------
     def algorithmic_bytes(self):
@@ -445,7 +445,7 @@ class Case:
 
     def launches_per_step(self):
         cl = {"fpn_gather_fwd": 1, "fpn_apply_fwd": 1, "roi_fuse_fwd": 3, "rff_gate_fwd": 1,
-              "rff_gate_bwd": 1, "roi_fuse_bwd": 4, "fpn_apply_bwd": 1, "fpn_gather_bwd": 2, "fpn_bwd": 1}
+              "rff_gate_bwd": 1, "roi_fuse_bwd": 4, "fpn_apply_bwd": 1, "fpn_gather_bwd": 2, "fpn_bwd": 2}
         nchw = dict(cl, roi_fuse_fwd=1, roi_fuse_bwd=1, fpn_apply_bwd=2)
         return sum((cl if st.cl else nchw)[n] for _, st, names in self.parts for n in names)
 
