@@ -582,43 +582,66 @@ fpn_bwd_fused_cl(const FpnParams p, const Exact ex) {
 // Same arithmetic as fpn_bwd_fused_cl, other data movement.  The register kernel keeps
 // one level pixel (1 KB) in flight per warp and pays a DRAM latency per pixel: it runs at
 // half the copy bandwidth however it is tuned.  In NHWC
-// everything a refine pixel needs is a handful of CONTIGUOUS pieces -- the s rows of its
-// s x s window on every pooled level (s px x C channels each), its own pixel, the one
-// pixel of each upsampled level, its bsf / d(gathered) pixels and its argmax bytes -- so
-// the warp fetches the whole footprint (~25 KB at C = 256 fp32) with one bulk async copy
-// (TMA) per piece into its own shared-memory buffer, signalled by one mbarrier, and
-// computes from shared memory: ~25 KB in flight per warp instead of 1 KB, no
-// registers held by loads.  Lane i owns level pixel i of the footprint for the scalar
-// work (gate maps in, tanh, d gate out), so those loads and stores are parallel too.
-// d x of the levels above the refine level (a sum over the refine pixels reading one
-// level pixel) is finished by gather_bwd_up_cl with d out as the addend (2 % of the pyramid).
+// everything a refine pixel needs from d out is a handful of CONTIGUOUS pieces -- the s
+// rows of its s x s window on every pooled level (s px x C channels each), its own pixel,
+// the one pixel of each upsampled level that reads it -- so the warp fetches the whole
+// footprint (23 KB at C = 256) with one bulk async copy (TMA) per piece into its own
+// shared-memory buffer, signalled by one mbarrier, and computes from shared memory:
+// 23 KB in flight per warp instead of 1 KB, no registers held by loads.
+//   * lane i owns level pixel i of the footprint for the scalar work (gate maps in, tanh,
+//     d gate out); the channel sum of a pixel is taken once per footprint from a
+//     [pixel][lane] table of partial dot products, not by five shuffles per pixel;
+//   * fp32: d x = d out + gather gradient is formed IN the buffer -- the gather routes
+//     g / L to one cell per channel and pooled level, i.e. one read-modify-write per
+//     channel instead of a compare + select + add per channel and pixel -- and the rows
+//     leave by bulk stores (TMA) as they came; bf16 d x is converted and stored from registers;
+//   * d x of the levels above the refine level (a sum over the refine pixels reading one
+//     level pixel) is finished by gather_bwd_up_cl with d out as the addend (2 % of the pyramid).
 constexpr int kFusedWarps = 8;
 constexpr int kFusedMaxJobs = 32;   // bulk copies per footprint (one per lane)
 constexpr int kFusedMaxPix = 32;    // level pixels per footprint (one per lane)
+constexpr int kFusedMaxPooled = 3;  // levels below the refine level
+constexpr int kFusedPartBytes = kFusedMaxPix * 33 * 4 + 128 - (kFusedMaxPix * 33 * 4) % 128;
 
 struct FusedGeom {
   int s[kMaxLevels];        // pooled levels: window side; 0 above the refine level
   int buf_bytes;            // footprint bytes, rounded up to 128
+  int tab_bytes;            // upsampled-level lookup tables, rounded up to 128
   int items;                // B * Hr * Wr
 };
+
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
 
 template <typename T, int NV>
 __global__ void __launch_bounds__(kFusedWarps * 32, 1)
 fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
   constexpr int V = Vec<T>::n;
+  constexpr bool kStoreTma = sizeof(T) == 4;  // d x has the staged element type
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Hr = p.Hr, Wr = p.Wr, C = p.C, R = p.refine_level;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  unsigned char* buf = smem_raw + 128 + (size_t)warp * geo.buf_bytes;
+  short* tab = reinterpret_cast<short*>(smem_raw + 128);  // level R+1+j: [Hr] rows then [Wr] columns
+  unsigned char* buf = smem_raw + 128 + geo.tab_bytes + (size_t)warp * (geo.buf_bytes + kFusedPartBytes);
+  float* part = reinterpret_cast<float*>(buf + geo.buf_bytes);  // [level pixel][33]: per-lane partial dot products
   uint64_t* bar = bars + warp;
   if (lane == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncwarp();
-  const int Hr = p.Hr, Wr = p.Wr, C = p.C, R = p.refine_level;
-  const uint32_t pixB = (uint32_t)C * 4u;            // d out is fp32
-  const uint32_t featB = (uint32_t)C * sizeof(T);    // bsf / d(gathered) pixel
+  // which row / column of an upsampled level reads refine row Y / column X (-1: none)
+  for (int e = threadIdx.x; e < (p.L - 1 - R) * (Hr + Wr); e += blockDim.x) {
+    const int l = R + 1 + e / (Hr + Wr), i = e % (Hr + Wr);
+    int a, bnd;
+    if (i < Hr) dst_range(i, Hr, p.H[l], a, bnd);
+    else dst_range(i - Hr, Wr, p.W[l], a, bnd);
+    tab[e] = (short)(bnd > a ? a : -1);
+  }
+  __syncthreads();
+  const uint32_t pixB = (uint32_t)C * 4u;  // d out is fp32
   const float Lf = (float)p.L;
   uint32_t phase = 0;
   for (int item = blockIdx.x * kFusedWarps + warp; item < geo.items; item += gridDim.x * kFusedWarps) {
@@ -626,70 +649,64 @@ fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
     const int Y = (item / Wr) % Hr;
     const int b = item / (Wr * Hr);
     const size_t rpix = ((size_t)b * Hr + Y) * Wr + X;
-    // ---- footprint: copy jobs (lane j issues job j) and level pixels (lane i owns pixel i)
-    const void* src = nullptr;
-    uint32_t dst = 0, bytes = 0, off = 0, total = 0;
+    // ---- footprint: copy jobs (lane j moves job j, in and out) and level pixels (lane i owns pixel i)
+    const float* src = nullptr;
+    float* gdst = nullptr;      // where this lane's piece goes as d x (fp32, levels <= R)
+    uint32_t dst = 0, bytes = 0, off = 0, off_r = 0;
     int job = 0, npix = 0;
     int my_l = -1;
     size_t my_pix = 0;
     uint32_t loff[kMaxLevels];  // buffer offset of level l's pixels
-    int lw[kMaxLevels];         // pixels per row of level l's piece (0: none)
+    bool have[kMaxLevels];
+    size_t lpix[kMaxLevels];    // global pixel index of the piece's first pixel
 #pragma unroll
     for (int l = 0; l < kMaxLevels; ++l) {
       loff[l] = off;
-      lw[l] = 0;
+      have[l] = false;
+      lpix[l] = 0;
       if (l >= p.L) continue;
       const int H = p.H[l], W = p.W[l];
-      int ya, yb, xa, xb;
-      if (l < R) { ya = geo.s[l] * Y; yb = ya + geo.s[l]; xa = geo.s[l] * X; xb = xa + geo.s[l]; }
-      else if (l == R) { ya = Y; yb = Y + 1; xa = X; xb = X + 1; }
-      else { dst_range(Y, Hr, H, ya, yb); dst_range(X, Wr, W, xa, xb); }
-      const int ny = yb - ya, nx = xb - xa;
-      if (ny <= 0 || nx <= 0) continue;
-      lw[l] = nx;
-      const uint32_t rowB = (uint32_t)nx * pixB;
-      if (lane >= job && lane < job + ny) {
+      int ya, xa, n;  // piece = n rows x n pixels from (ya, xa)
+      if (l < R) { n = geo.s[l]; ya = n * Y; xa = n * X; }
+      else if (l == R) { n = 1; ya = Y; xa = X; }
+      else {
+        const short* t = tab + (l - R - 1) * (Hr + Wr);
+        ya = t[Y]; xa = t[Hr + X]; n = (ya >= 0 && xa >= 0) ? 1 : 0;
+      }
+      if (n == 0) continue;
+      have[l] = true;
+      if (l == R) off_r = off;
+      lpix[l] = ((size_t)b * H + ya) * W + xa;
+      const uint32_t rowB = (uint32_t)n * pixB;
+      if (lane >= job && lane < job + n) {
         const int r = lane - job;
-        src = static_cast<const float*>(p.feats[l]) + (((size_t)b * H + ya + r) * W + xa) * C;
+        src = static_cast<const float*>(p.feats[l]) + (lpix[l] + (size_t)r * W) * C;
+        if (kStoreTma && l <= R) gdst = static_cast<float*>(p.outs[l]) + (lpix[l] + (size_t)r * W) * C;
         dst = off + (uint32_t)r * rowB;
         bytes = rowB;
       }
-      if (lane >= npix && lane < npix + ny * nx) {
+      if (lane >= npix && lane < npix + n * n) {
         const int q = lane - npix;
         my_l = l;
-        my_pix = ((size_t)b * H + ya + q / nx) * W + xa + q % nx;
+        my_pix = lpix[l] + (size_t)(q / n) * W + q % n;
       }
-      job += ny;
-      npix += ny * nx;
-      off += (uint32_t)ny * rowB;
+      job += n;
+      npix += n * n;
+      off += (uint32_t)n * rowB;
     }
-    const uint32_t o_bsf = off, o_dga = off + featB, o_arg = off + 2 * featB;
-    if (lane == job) { src = static_cast<const T*>(p.bsf) + rpix * C; dst = o_bsf; bytes = featB; }
-    if (lane == job + 1) { src = static_cast<const T*>(p.gathered) + rpix * C; dst = o_dga; bytes = featB; }
-    if (lane >= job + 2 && lane < job + 2 + R) {
-      const int l = lane - job - 2;
-      src = p.argmax + (((size_t)l * p.B + b) * Hr * Wr + (size_t)Y * Wr + X) * C;
-      dst = o_arg + (uint32_t)l * C;
-      bytes = (uint32_t)C;
-    }
-    total = o_arg + (uint32_t)R * C;
-    // ---- issue: the previous item's reads of the buffer are done (end-of-loop __syncwarp)
-    if (lane == 0) mbar_arrive_expect_tx(bar, total);
+    // ---- issue the loads (the bulk stores of the previous item have finished reading the buffer)
+    if (lane == 0) mbar_arrive_expect_tx(bar, off);
     __syncwarp();
     if (bytes) bulk_g2s(buf + dst, src, bytes, bar);
     // ---- the scalar work of this lane's level pixel, while the copies fly
-    float a1 = 0.f, a2 = 0.f, t1 = 0.f, t2 = 0.f, mysum = 0.f;
+    float a1 = 0.f, a2 = 0.f, t1 = 0.f, t2 = 0.f;
     if (my_l >= 0) {
       a1 = ldf(static_cast<const T*>(p.g1[my_l]) + my_pix);
       a2 = ldf(static_cast<const T*>(p.g2[my_l]) + my_pix);
-      t1 = tanhf(fmaxf(a1, 0.f));
-      t2 = tanhf(fmaxf(a2, 0.f));
     }
-    const float mygate = t1 + t2;
-    mbar_wait(bar, phase);
-    phase ^= 1u;
-    // ---- compute from shared memory
+    // bsf, d(gathered) and the argmax bytes of this refine pixel: plain loads, in flight with the copies
     float bs[NV][V], db[NV][V], gg[NV][V];
+    unsigned arg[kFusedMaxPooled][NV][V / 4];
     bool on[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
@@ -697,18 +714,38 @@ fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
       on[v] = c < C;
 #pragma unroll
       for (int u = 0; u < V; ++u) { bs[v][u] = 0.f; db[v][u] = 0.f; gg[v][u] = 0.f; }
-      if (on[v]) {
-        lds_vec<T>(buf + o_bsf + (uint32_t)c * sizeof(T), bs[v]);
-        lds_vec<T>(buf + o_dga + (uint32_t)c * sizeof(T), gg[v]);
 #pragma unroll
-        for (int u = 0; u < V; ++u) gg[v][u] = __fdiv_rn(gg[v][u], Lf);
+      for (int l = 0; l < kFusedMaxPooled; ++l)
+#pragma unroll
+        for (int u = 0; u < V / 4; ++u) arg[l][v][u] = 0u;
+      if (on[v]) {
+        ldv<T>(static_cast<const T*>(p.bsf) + rpix * C + c, bs[v]);
+        ldv<T>(static_cast<const T*>(p.gathered) + rpix * C + c, gg[v]);
+#pragma unroll
+        for (int l = 0; l < kFusedMaxPooled; ++l)
+          if (l < R) {
+            const uint8_t* a = p.argmax + (((size_t)l * p.B + b) * Hr * Wr + (size_t)Y * Wr + X) * C + c;
+#pragma unroll
+            for (int u = 0; u < V / 4; ++u) arg[l][v][u] = __ldg(reinterpret_cast<const unsigned*>(a) + u);
+          }
       }
     }
+    if (my_l >= 0) {
+      t1 = tanhf(fmaxf(a1, 0.f));
+      t2 = tanhf(fmaxf(a2, 0.f));
+    }
+    const float mygate = t1 + t2;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int u = 0; u < V; ++u) gg[v][u] = __fdiv_rn(gg[v][u], Lf);
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    // ---- compute from shared memory
     int q = 0;  // running level-pixel index == owning lane
     auto pixel = [&](int l, uint32_t boff, size_t pix, bool write_dx, auto routed) {
-      T* __restrict__ dx = static_cast<T*>(p.outs[l]);
       const float gate = __shfl_sync(0xffffffffu, mygate, q);
-      float sum = 0.f;
+      float sum[4] = {0.f, 0.f, 0.f, 0.f};  // four chains: the dot product is not one dependent FMA string
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         if (!on[v]) continue;
@@ -721,51 +758,74 @@ fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
         }
 #pragma unroll
         for (int u = 0; u < V; ++u) {
-          sum = fmaf(f[u], bs[v][u], sum);
+          sum[u & 3] = fmaf(f[u], bs[v][u], sum[u & 3]);
           db[v][u] = fmaf(f[u], gate, db[v][u]);
-          f[u] = routed(v, u) + f[u];
         }
-        if (write_dx) stv<T>(dx + pix * C + (v * 32 + lane) * V, f);
-      }
+        if constexpr (!kStoreTma) {
+          if (write_dx) {
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-      if (lane == q) mysum = sum;
+            for (int u = 0; u < V; ++u) f[u] = routed(v, u) + f[u];
+            stv<T>(static_cast<T*>(p.outs[l]) + pix * C + (v * 32 + lane) * V, f);
+          }
+        }
+      }
+      part[q * 33 + lane] = (sum[0] + sum[1]) + (sum[2] + sum[3]);
       ++q;
     };
 #pragma unroll
     for (int l = 0; l < kMaxLevels; ++l) {
-      if (l >= p.L || lw[l] == 0) continue;
-      const int H = p.H[l], W = p.W[l];
+      if (l >= p.L || !have[l]) continue;
+      const int W = p.W[l];
       if (l < R) {
         const int s = geo.s[l];
-        unsigned arg[NV][V / 4];
-#pragma unroll
-        for (int v = 0; v < NV; ++v)
-#pragma unroll
-          for (int u = 0; u < V / 4; ++u)
-            arg[v][u] = on[v] ? *reinterpret_cast<const unsigned*>(buf + o_arg + (uint32_t)l * C + (v * 32 + lane) * V + 4 * u) : 0u;
         for (int dy = 0; dy < s; ++dy)
           for (int dxx = 0; dxx < s; ++dxx) {
             const unsigned pos = (unsigned)(dy * s + dxx);
-            pixel(l, loff[l] + (uint32_t)(dy * s + dxx) * pixB,
-                  ((size_t)b * H + (size_t)s * Y + dy) * W + (size_t)s * X + dxx, true, [&](int v, int u) {
-                    return (((arg[v][u >> 2] >> (8 * (u & 3))) & 255u) == pos) ? gg[v][u] : 0.f;
-                  });
+            pixel(l, loff[l] + pos * pixB, lpix[l] + (size_t)dy * W + dxx, true, [&](int v, int u) {
+              return (((arg[l < kFusedMaxPooled ? l : 0][v][u >> 2] >> (8 * (u & 3))) & 255u) == pos) ? gg[v][u] : 0.f;
+            });
           }
       } else if (l == R) {
         pixel(l, loff[l], rpix, true, [&](int v, int u) { return gg[v][u]; });
       } else {
-        // upsampled level: at most one pixel; its d x is written by gather_bwd_up_cl
-        int ya, yb, xa, xb;
-        dst_range(Y, Hr, H, ya, yb);
-        dst_range(X, Wr, W, xa, xb);
-        for (int y = ya; y < yb; ++y)
-          for (int x = xa; x < xb; ++x)
-            pixel(l, loff[l] + (uint32_t)((y - ya) * (xb - xa) + (x - xa)) * pixB, 0, false,
-                  [&](int, int) { return 0.f; });
+        pixel(l, loff[l], 0, false, [&](int, int) { return 0.f; });  // d x: gather_bwd_up_cl
+      }
+    }
+    __syncwarp();  // the partial sums are complete; nobody reads d out from the buffer any more
+    if constexpr (kStoreTma) {
+      // d x in place: the gather's gradient goes to the argmax cell of every pooled window
+      // (one read-modify-write per channel and level) and to the refine pixel itself
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if (!on[v]) continue;
+        const uint32_t coff = (uint32_t)((v * 32 + lane) * V) * 4u;
+#pragma unroll
+        for (int l = 0; l < kFusedMaxPooled; ++l)
+          if (l < R) {
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+              const unsigned pos = (arg[l][v][u >> 2] >> (8 * (u & 3))) & 255u;
+              float* cell = reinterpret_cast<float*>(buf + loff[l] + pos * pixB + coff) + u;
+              *cell = gg[v][u] + *cell;
+            }
+          }
+        float* cell = reinterpret_cast<float*>(buf + off_r + coff);
+#pragma unroll
+        for (int u = 0; u < V; ++u) cell[u] = gg[v][u] + cell[u];
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (gdst) {
+        bulk_s2g(gdst, buf + dst, bytes);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
     if (my_l >= 0) {
+      // lane i owns level pixel i: sum of the 32 lanes' partial dot products, fixed order
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc[k & 3] += part[lane * 33 + k];
+      const float mysum = (acc[0] + acc[1]) + (acc[2] + acc[3]);
       p.dg1[my_l][my_pix] = a1 > 0.f ? mysum * (1.f - t1 * t1) : 0.f;
       p.dg2[my_l][my_pix] = a2 > 0.f ? mysum * (1.f - t2 * t2) : 0.f;
     }
@@ -778,8 +838,12 @@ fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
       for (int u = 0; u < V; u += 4)
         *reinterpret_cast<float4*>(o + c + u) = make_float4(db[v][u], db[v][u + 1], db[v][u + 2], db[v][u + 3]);
     }
+    if constexpr (kStoreTma) {
+      if (gdst) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stores have read the buffer
+    }
     __syncwarp();  // every lane is done with the buffer before the next item's copies land in it
   }
+  if constexpr (kStoreTma) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // Pooling ratio of each level below the refine level when it is an exact integer.
@@ -912,23 +976,27 @@ cudaError_t launch_fpn_backward_fused_cl(const FpnParams& p, int dtype, int dout
   // ---- TMA-staged kernel: fp32 d out, footprint of a refine pixel within one lane-set ----
   if ((dtype == 0 || dout_f32) && p.C % 16 == 0) {
     FusedGeom geo;
-    int jobs = 2 + p.refine_level, pix = 1;
+    int jobs = 0, pix = 0;
     size_t bytes = 0;
     for (int l = 0; l < kMaxLevels; ++l) geo.s[l] = 0;
     for (int l = 0; l < p.L; ++l) {
       if (l < p.refine_level) { geo.s[l] = ex.s[l]; jobs += ex.s[l]; pix += ex.s[l] * ex.s[l]; bytes += (size_t)ex.s[l] * ex.s[l]; }
       else if (l > p.refine_level) {
-        // upsampled level (smaller map): at most ceil(H / Hr) + 1 == 2 rows / columns can map to one refine pixel
-        const int my = (p.H[l] + p.Hr - 1) / p.Hr + 1, mx = (p.W[l] + p.Wr - 1) / p.Wr + 1;
+        // upsampled level (a map no larger than the refine map): nearest_src(y: Hr <- H) is strictly
+        // increasing in y, so at most one level pixel reads a given refine pixel
         if (p.H[l] > p.Hr || p.W[l] > p.Wr) { jobs = 1 << 20; break; }
-        jobs += my; pix += my * mx; bytes += (size_t)my * mx;
-      } else { jobs += 1; bytes += 1; }
+        jobs += 1; pix += 1; bytes += 1;
+      } else { jobs += 1; pix += 1; bytes += 1; }
     }
-    bytes = bytes * p.C * 4 + 2 * (size_t)p.C * (dtype == 0 ? 4 : 2) + (size_t)p.refine_level * p.C;
+    if (p.refine_level > kFusedMaxPooled) jobs = 1 << 20;
+    bytes = bytes * p.C * 4;
     bytes = (bytes + 127) / 128 * 128;
-    const size_t smem = 128 + bytes * kFusedWarps;
+    size_t tab = (size_t)(p.L - 1 - p.refine_level) * (p.Hr + p.Wr) * 2;
+    tab = (tab + 127) / 128 * 128;
+    const size_t smem = 128 + tab + (bytes + kFusedPartBytes) * kFusedWarps;
     if (jobs <= kFusedMaxJobs && pix <= kFusedMaxPix && smem <= 220 * 1024 && warps < (1u << 30)) {
       geo.buf_bytes = (int)bytes;
+      geo.tab_bytes = (int)tab;
       geo.items = (int)warps;
       const int sms = sm_count();
       const int per_sm = (int)((220 * 1024) / smem) < 1 ? 1 : (int)((220 * 1024) / smem);

@@ -225,9 +225,16 @@ def test_fused_fpn_backward_equals_the_two_call_path(cuda, dtype):
     L.check(st.fpn_gather_bwd(), "gather bwd acc")
     torch.cuda.synchronize()
     two = st.dx + st.dg1 + st.dg2 + [st.dbsf]
+    n = len(st.dx)
     for i, (a, b) in enumerate(zip(fused, two)):
-        if dtype == torch.bfloat16 and i >= len(st.dx):
-            # the two-call path reads d out rounded to bf16 (glue copy), the fused one reads fp32
-            assert torch.allclose(a.float(), b.float(), rtol=2e-2, atol=2e-2 * float(b.abs().max())), i
+        if i < n or i == len(fused) - 1:
+            # d x and d bsf: same additions in the same order (for bf16 the two-call path reads d out
+            # rounded to bf16 by the glue copy, the fused one reads the fp32 accumulators: d bsf differs)
+            if dtype == torch.bfloat16 and i >= n:
+                assert torch.allclose(a.float(), b.float(), rtol=2e-2, atol=2e-2 * float(b.abs().max())), i
+            else:
+                assert torch.equal(a, b), (i, float((a.float() - b.float()).abs().max()))
         else:
-            assert torch.equal(a, b), (i, float((a.float() - b.float()).abs().max()))
+            # d gate maps: channel sums taken in another order (per-footprint reduction vs shuffle tree)
+            tol = 2e-2 if dtype == torch.bfloat16 else 2e-5
+            assert float((a - b).abs().max()) <= tol * float(b.abs().max()) + 1e-6, i
