@@ -584,24 +584,26 @@ fpn_bwd_fused_cl(const FpnParams p, const Exact ex) {
 // half the copy bandwidth however it is tuned.  In NHWC
 // everything a refine pixel needs from d out is a handful of CONTIGUOUS pieces -- the s
 // rows of its s x s window on every pooled level (s px x C channels each), its own pixel,
-// the one pixel of each upsampled level that reads it -- so the warp fetches the whole
-// footprint (23 KB at C = 256) with one bulk async copy (TMA) per piece into its own
-// shared-memory buffer, signalled by one mbarrier, and computes from shared memory:
-// 23 KB in flight per warp instead of 1 KB, no registers held by loads.
-//   * lane i owns level pixel i of the footprint for the scalar work (gate maps in, tanh,
-//     d gate out); the channel sum of a pixel is taken once per footprint from a
-//     [pixel][lane] table of partial dot products, not by five shuffles per pixel;
+// the one pixel of each upsampled level that reads it -- so the whole footprint (23 KB at
+// C = 256) is fetched with one bulk async copy (TMA) per piece into a shared-memory
+// buffer, signalled by one mbarrier, and consumed from shared memory: 23 KB in flight per
+// buffer instead of 1 KB per warp, no registers held by loads.
+//   * a PAIR of warps shares a buffer, each warp taking half of the channels: sixteen
+//     warps per SM hide each other's shared-memory and arithmetic latencies (eight
+//     single warps with a buffer each issued one instruction every ~8 cycles);
+//   * lane i of the pair's first warp owns level pixel i of the footprint for the scalar
+//     work (gate maps in, d gate out): those loads and stores are parallel, not per pixel;
 //   * fp32: d x = d out + gather gradient is formed IN the buffer -- the gather routes
 //     g / L to one cell per channel and pooled level, i.e. one read-modify-write per
 //     channel instead of a compare + select + add per channel and pixel -- and the rows
 //     leave by bulk stores (TMA) as they came; bf16 d x is converted and stored from registers;
 //   * d x of the levels above the refine level (a sum over the refine pixels reading one
 //     level pixel) is finished by gather_bwd_up_cl with d out as the addend (2 % of the pyramid).
-constexpr int kFusedWarps = 8;
+constexpr int kFusedPairs = 8;
+constexpr int kFusedWarps = 2 * kFusedPairs;
 constexpr int kFusedMaxJobs = 32;   // bulk copies per footprint (one per lane)
 constexpr int kFusedMaxPix = 32;    // level pixels per footprint (one per lane)
 constexpr int kFusedMaxPooled = 3;  // levels below the refine level
-constexpr int kFusedPartBytes = kFusedMaxPix * 33 * 4 + 128 - (kFusedMaxPix * 33 * 4) % 128;
 
 struct FusedGeom {
   int s[kMaxLevels];        // pooled levels: window side; 0 above the refine level
@@ -614,7 +616,12 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void pair_sync(int pair) {
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+}
 
+// NV = 128-bit (fp32: 4 channels) / 8-channel (bf16) vectors per lane of ONE warp; the pair
+// covers 2 * NV * 32 * V channels.
 template <typename T, int NV>
 __global__ void __launch_bounds__(kFusedWarps * 32, 1)
 fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
@@ -622,13 +629,13 @@ fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
   constexpr bool kStoreTma = sizeof(T) == 4;  // d x has the staged element type
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = warp >> 1, half = warp & 1;
   const int Hr = p.Hr, Wr = p.Wr, C = p.C, R = p.refine_level;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  short* tab = reinterpret_cast<short*>(smem_raw + 128);  // level R+1+j: [Hr] rows then [Wr] columns
-  unsigned char* buf = smem_raw + 128 + geo.tab_bytes + (size_t)warp * (geo.buf_bytes + kFusedPartBytes);
-  float* part = reinterpret_cast<float*>(buf + geo.buf_bytes);  // [level pixel][33]: per-lane partial dot products
-  uint64_t* bar = bars + warp;
-  if (lane == 0) {
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw) + pair;
+  float* psum = reinterpret_cast<float*>(smem_raw + 128) + pair * 32;   // second warp's channel sums
+  short* tab = reinterpret_cast<short*>(smem_raw + 128 + kFusedPairs * 128);  // level R+1+j: [Hr] rows, [Wr] columns
+  unsigned char* buf = smem_raw + 128 + kFusedPairs * 128 + geo.tab_bytes + (size_t)pair * geo.buf_bytes;
+  if (half == 0 && lane == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -643,13 +650,21 @@ fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
   __syncthreads();
   const uint32_t pixB = (uint32_t)C * 4u;  // d out is fp32
   const float Lf = (float)p.L;
+  bool on[NV];
+  int ch[NV];  // first channel of this lane's v-th vector
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    ch[v] = ((half * NV + v) * 32 + lane) * V;
+    on[v] = ch[v] < C;
+  }
   uint32_t phase = 0;
-  for (int item = blockIdx.x * kFusedWarps + warp; item < geo.items; item += gridDim.x * kFusedWarps) {
+  for (int item = blockIdx.x * kFusedPairs + pair; item < geo.items; item += gridDim.x * kFusedPairs) {
     const int X = item % Wr;
     const int Y = (item / Wr) % Hr;
     const int b = item / (Wr * Hr);
     const size_t rpix = ((size_t)b * Hr + Y) * Wr + X;
-    // ---- footprint: copy jobs (lane j moves job j, in and out) and level pixels (lane i owns pixel i)
+    // ---- footprint: copy jobs (lane j of the first warp moves job j, in and out) and level
+    // pixels (lane i owns pixel i); both warps compute it, it is a few dozen instructions
     const float* src = nullptr;
     float* gdst = nullptr;      // where this lane's piece goes as d x (fp32, levels <= R)
     uint32_t dst = 0, bytes = 0, off = 0, off_r = 0;
@@ -694,24 +709,28 @@ fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
       npix += n * n;
       off += (uint32_t)n * rowB;
     }
-    // ---- issue the loads (the bulk stores of the previous item have finished reading the buffer)
-    if (lane == 0) mbar_arrive_expect_tx(bar, off);
-    __syncwarp();
-    if (bytes) bulk_g2s(buf + dst, src, bytes, bar);
-    // ---- the scalar work of this lane's level pixel, while the copies fly
-    float a1 = 0.f, a2 = 0.f, t1 = 0.f, t2 = 0.f;
+    // ---- first warp: issue the loads once its bulk stores of the previous item have read the buffer
+    // (the second warp's last access to the buffer precedes the pair barrier of the previous item)
+    if (half == 0) {
+      if constexpr (kStoreTma) {
+        if (gdst) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(bar, off);
+      __syncwarp();
+      if (bytes) bulk_g2s(buf + dst, src, bytes, bar);
+    }
+    // ---- plain loads, in flight with the copies: gate values of this lane's level pixel,
+    // bsf / d(gathered) / argmax bytes of this lane's channels
+    float a1 = 0.f, a2 = 0.f;
     if (my_l >= 0) {
       a1 = ldf(static_cast<const T*>(p.g1[my_l]) + my_pix);
       a2 = ldf(static_cast<const T*>(p.g2[my_l]) + my_pix);
     }
-    // bsf, d(gathered) and the argmax bytes of this refine pixel: plain loads, in flight with the copies
     float bs[NV][V], db[NV][V], gg[NV][V];
     unsigned arg[kFusedMaxPooled][NV][V / 4];
-    bool on[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      const int c = (v * 32 + lane) * V;
-      on[v] = c < C;
 #pragma unroll
       for (int u = 0; u < V; ++u) { bs[v][u] = 0.f; db[v][u] = 0.f; gg[v][u] = 0.f; }
 #pragma unroll
@@ -719,17 +738,18 @@ fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
 #pragma unroll
         for (int u = 0; u < V / 4; ++u) arg[l][v][u] = 0u;
       if (on[v]) {
-        ldv<T>(static_cast<const T*>(p.bsf) + rpix * C + c, bs[v]);
-        ldv<T>(static_cast<const T*>(p.gathered) + rpix * C + c, gg[v]);
+        ldv<T>(static_cast<const T*>(p.bsf) + rpix * C + ch[v], bs[v]);
+        ldv<T>(static_cast<const T*>(p.gathered) + rpix * C + ch[v], gg[v]);
 #pragma unroll
         for (int l = 0; l < kFusedMaxPooled; ++l)
           if (l < R) {
-            const uint8_t* a = p.argmax + (((size_t)l * p.B + b) * Hr * Wr + (size_t)Y * Wr + X) * C + c;
+            const uint8_t* a = p.argmax + (((size_t)l * p.B + b) * Hr * Wr + (size_t)Y * Wr + X) * C + ch[v];
 #pragma unroll
             for (int u = 0; u < V / 4; ++u) arg[l][v][u] = __ldg(reinterpret_cast<const unsigned*>(a) + u);
           }
       }
     }
+    float t1 = 0.f, t2 = 0.f;
     if (my_l >= 0) {
       t1 = tanhf(fmaxf(a1, 0.f));
       t2 = tanhf(fmaxf(a2, 0.f));
@@ -741,8 +761,9 @@ fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
       for (int u = 0; u < V; ++u) gg[v][u] = __fdiv_rn(gg[v][u], Lf);
     mbar_wait(bar, phase);
     phase ^= 1u;
-    // ---- compute from shared memory
-    int q = 0;  // running level-pixel index == owning lane
+    // ---- the level pixels, from shared memory
+    int q = 0;            // running level-pixel index == owning lane
+    float mysum = 0.f;    // this warp's channel sum of the pixel this lane owns
     auto pixel = [&](int l, uint32_t boff, size_t pix, bool write_dx, auto routed) {
       const float gate = __shfl_sync(0xffffffffu, mygate, q);
       float sum[4] = {0.f, 0.f, 0.f, 0.f};  // four chains: the dot product is not one dependent FMA string
@@ -750,7 +771,7 @@ fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
       for (int v = 0; v < NV; ++v) {
         if (!on[v]) continue;
         float f[V];
-        const float* sp = reinterpret_cast<const float*>(buf + boff) + (v * 32 + lane) * V;
+        const float* sp = reinterpret_cast<const float*>(buf + boff) + ch[v];
 #pragma unroll
         for (int u = 0; u < V; u += 4) {
           const float4 t = *reinterpret_cast<const float4*>(sp + u);
@@ -765,40 +786,62 @@ fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
           if (write_dx) {
 #pragma unroll
             for (int u = 0; u < V; ++u) f[u] = routed(v, u) + f[u];
-            stv<T>(static_cast<T*>(p.outs[l]) + pix * C + (v * 32 + lane) * V, f);
+            stv<T>(static_cast<T*>(p.outs[l]) + pix * C + ch[v], f);
           }
         }
       }
-      part[q * 33 + lane] = (sum[0] + sum[1]) + (sum[2] + sum[3]);
+      float s = (sum[0] + sum[1]) + (sum[2] + sum[3]);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+      if (lane == q) mysum = s;
       ++q;
+    };
+    auto window = [&](auto s_tag, int l) {  // pooled level, window side known at compile time
+      constexpr int S = decltype(s_tag)::value;
+      const int W = p.W[l];
+#pragma unroll
+      for (int dy = 0; dy < S; ++dy)
+#pragma unroll
+        for (int dxx = 0; dxx < S; ++dxx) {
+          const unsigned pos = (unsigned)(dy * S + dxx);
+          pixel(l, loff[l] + pos * pixB, lpix[l] + (size_t)dy * W + dxx, true, [&](int v, int u) {
+            return (((arg[l < kFusedMaxPooled ? l : 0][v][u >> 2] >> (8 * (u & 3))) & 255u) == pos) ? gg[v][u] : 0.f;
+          });
+        }
     };
 #pragma unroll
     for (int l = 0; l < kMaxLevels; ++l) {
       if (l >= p.L || !have[l]) continue;
-      const int W = p.W[l];
       if (l < R) {
         const int s = geo.s[l];
-        for (int dy = 0; dy < s; ++dy)
-          for (int dxx = 0; dxx < s; ++dxx) {
-            const unsigned pos = (unsigned)(dy * s + dxx);
-            pixel(l, loff[l] + pos * pixB, lpix[l] + (size_t)dy * W + dxx, true, [&](int v, int u) {
-              return (((arg[l < kFusedMaxPooled ? l : 0][v][u >> 2] >> (8 * (u & 3))) & 255u) == pos) ? gg[v][u] : 0.f;
-            });
-          }
+        if (s == 4) window(std::integral_constant<int, 4>{}, l);
+        else if (s == 2) window(std::integral_constant<int, 2>{}, l);
+        else if (s == 1) window(std::integral_constant<int, 1>{}, l);
+        else {
+          const int W = p.W[l];
+          for (int dy = 0; dy < s; ++dy)
+            for (int dxx = 0; dxx < s; ++dxx) {
+              const unsigned pos = (unsigned)(dy * s + dxx);
+              pixel(l, loff[l] + pos * pixB, lpix[l] + (size_t)dy * W + dxx, true, [&](int v, int u) {
+                return (((arg[l < kFusedMaxPooled ? l : 0][v][u >> 2] >> (8 * (u & 3))) & 255u) == pos) ? gg[v][u] : 0.f;
+              });
+            }
+        }
       } else if (l == R) {
         pixel(l, loff[l], rpix, true, [&](int v, int u) { return gg[v][u]; });
       } else {
         pixel(l, loff[l], 0, false, [&](int, int) { return 0.f; });  // d x: gather_bwd_up_cl
       }
     }
-    __syncwarp();  // the partial sums are complete; nobody reads d out from the buffer any more
+    if (half == 1) psum[lane] = mysum;
     if constexpr (kStoreTma) {
       // d x in place: the gather's gradient goes to the argmax cell of every pooled window
-      // (one read-modify-write per channel and level) and to the refine pixel itself
+      // (one read-modify-write per channel and level) and to the refine pixel itself.
+      // Each lane touches only its own channels, which no other lane of the pair reads.
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         if (!on[v]) continue;
-        const uint32_t coff = (uint32_t)((v * 32 + lane) * V) * 4u;
+        const uint32_t coff = (uint32_t)ch[v] * 4u;
 #pragma unroll
         for (int l = 0; l < kFusedMaxPooled; ++l)
           if (l < R) {
@@ -814,34 +857,30 @@ fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
         for (int u = 0; u < V; ++u) cell[u] = gg[v][u] + cell[u];
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (gdst) {
-        bulk_s2g(gdst, buf + dst, bytes);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
     }
-    if (my_l >= 0) {
-      // lane i owns level pixel i: sum of the 32 lanes' partial dot products, fixed order
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int k = 0; k < 32; ++k) acc[k & 3] += part[lane * 33 + k];
-      const float mysum = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-      p.dg1[my_l][my_pix] = a1 > 0.f ? mysum * (1.f - t1 * t1) : 0.f;
-      p.dg2[my_l][my_pix] = a2 > 0.f ? mysum * (1.f - t2 * t2) : 0.f;
+    pair_sync(pair);  // both halves of every pixel are final; the second warp's sums are visible
+    if (half == 0) {
+      if constexpr (kStoreTma) {
+        if (gdst) {
+          bulk_s2g(gdst, buf + dst, bytes);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      if (my_l >= 0) {
+        const float tot = mysum + psum[lane];
+        p.dg1[my_l][my_pix] = a1 > 0.f ? tot * (1.f - t1 * t1) : 0.f;
+        p.dg2[my_l][my_pix] = a2 > 0.f ? tot * (1.f - t2 * t2) : 0.f;
+      }
     }
     float* __restrict__ o = p.dbsf + rpix * C;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       if (!on[v]) continue;
-      const int c = (v * 32 + lane) * V;
 #pragma unroll
       for (int u = 0; u < V; u += 4)
-        *reinterpret_cast<float4*>(o + c + u) = make_float4(db[v][u], db[v][u + 1], db[v][u + 2], db[v][u + 3]);
+        *reinterpret_cast<float4*>(o + ch[v] + u) = make_float4(db[v][u], db[v][u + 1], db[v][u + 2], db[v][u + 3]);
     }
-    if constexpr (kStoreTma) {
-      if (gdst) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stores have read the buffer
-    }
-    __syncwarp();  // every lane is done with the buffer before the next item's copies land in it
+    __syncwarp();
   }
   if constexpr (kStoreTma) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -993,24 +1032,23 @@ cudaError_t launch_fpn_backward_fused_cl(const FpnParams& p, int dtype, int dout
     bytes = (bytes + 127) / 128 * 128;
     size_t tab = (size_t)(p.L - 1 - p.refine_level) * (p.Hr + p.Wr) * 2;
     tab = (tab + 127) / 128 * 128;
-    const size_t smem = 128 + tab + (bytes + kFusedPartBytes) * kFusedWarps;
-    if (jobs <= kFusedMaxJobs && pix <= kFusedMaxPix && smem <= 220 * 1024 && warps < (1u << 30)) {
+    const size_t smem = 128 + kFusedPairs * 128 + tab + bytes * kFusedPairs;
+    const int nvw = (nv + 1) / 2;  // vectors per lane of one warp of a pair
+    if (jobs <= kFusedMaxJobs && pix <= kFusedMaxPix && smem <= 220 * 1024 && warps < (1u << 30) && nvw == 1) {
       geo.buf_bytes = (int)bytes;
       geo.tab_bytes = (int)tab;
       geo.items = (int)warps;
-      const int sms = sm_count();
-      const int per_sm = (int)((220 * 1024) / smem) < 1 ? 1 : (int)((220 * 1024) / smem);
-      int grid = sms * (per_sm > 2 ? 2 : per_sm);
-      const int need = (int)((warps + kFusedWarps - 1) / kFusedWarps);
+      int grid = sm_count();
+      const int need = (int)((warps + kFusedPairs - 1) / kFusedPairs);
       if (grid > need) grid = need;
       cudaError_t e;
-#define ARFE_FUSED_TMA(TT, NV)                                                                        \
+#define ARFE_FUSED_TMA(TT)                                                                            \
   do {                                                                                                \
-    if ((e = cudaFuncSetAttribute(fpn_bwd_fused_tma<TT, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e; \
-    fpn_bwd_fused_tma<TT, NV><<<grid, kFusedWarps * 32, smem, stream>>>(p, geo);                      \
+    if ((e = cudaFuncSetAttribute(fpn_bwd_fused_tma<TT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e; \
+    fpn_bwd_fused_tma<TT, 1><<<grid, kFusedWarps * 32, smem, stream>>>(p, geo);                       \
   } while (0)
-      if (dtype == 0) { if (nv == 1) ARFE_FUSED_TMA(float, 1); else ARFE_FUSED_TMA(float, 2); }
-      else { if (nv == 1) ARFE_FUSED_TMA(__nv_bfloat16, 1); else ARFE_FUSED_TMA(__nv_bfloat16, 2); }
+      if (dtype == 0) ARFE_FUSED_TMA(float);
+      else ARFE_FUSED_TMA(__nv_bfloat16);
 #undef ARFE_FUSED_TMA
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
       // d x of the levels above the refine level: gather gradient + d out
