@@ -693,7 +693,7 @@ fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
       if (l == R) off_r = off;
       lpix[l] = ((size_t)b * H + ya) * W + xa;
       const uint32_t rowB = (uint32_t)n * pixB;
-      if (lane >= job && lane < job + n) {
+      if (half == 0 && lane >= job && lane < job + n) {
         const int r = lane - job;
         src = static_cast<const float*>(p.feats[l]) + (lpix[l] + (size_t)r * W) * C;
         if (kStoreTma && l <= R) gdst = static_cast<float*>(p.outs[l]) + (lpix[l] + (size_t)r * W) * C;
@@ -702,12 +702,19 @@ fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
       }
       if (lane >= npix && lane < npix + n * n) {
         const int q = lane - npix;
+        const int sh = 31 - __clz(n);
+        const int qr = (n & (n - 1)) == 0 ? q >> sh : q / n;  // window sides are 1, 2, 4 in practice
         my_l = l;
-        my_pix = lpix[l] + (size_t)(q / n) * W + q % n;
+        my_pix = lpix[l] + (size_t)qr * W + (q - qr * n);
       }
       job += n;
       npix += n * n;
       off += (uint32_t)n * rowB;
+    }
+    float a1 = 0.f, a2 = 0.f;  // gate values of this lane's level pixel: in flight first
+    if (my_l >= 0) {
+      a1 = ldf(static_cast<const T*>(p.g1[my_l]) + my_pix);
+      a2 = ldf(static_cast<const T*>(p.g2[my_l]) + my_pix);
     }
     // ---- first warp: issue the loads once its bulk stores of the previous item have read the buffer
     // (the second warp's last access to the buffer precedes the pair barrier of the previous item)
@@ -722,11 +729,6 @@ fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
     }
     // ---- plain loads, in flight with the copies: gate values of this lane's level pixel,
     // bsf / d(gathered) / argmax bytes of this lane's channels
-    float a1 = 0.f, a2 = 0.f;
-    if (my_l >= 0) {
-      a1 = ldf(static_cast<const T*>(p.g1[my_l]) + my_pix);
-      a2 = ldf(static_cast<const T*>(p.g2[my_l]) + my_pix);
-    }
     float bs[NV][V], db[NV][V], gg[NV][V];
     unsigned arg[kFusedMaxPooled][NV][V / 4];
 #pragma unroll
@@ -764,8 +766,9 @@ fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
     // ---- the level pixels, from shared memory
     int q = 0;            // running level-pixel index == owning lane
     float mysum = 0.f;    // this warp's channel sum of the pixel this lane owns
-    auto pixel = [&](int l, uint32_t boff, size_t pix, bool write_dx, auto routed) {
-      const float gate = __shfl_sync(0xffffffffu, mygate, q);
+    // lane-local part of one level pixel: returns this lane's share of sum_c d out * bsf
+    auto pixel = [&](int l, uint32_t boff, size_t pix, int qq, bool write_dx, auto routed) -> float {
+      const float gate = __shfl_sync(0xffffffffu, mygate, qq);
       float sum[4] = {0.f, 0.f, 0.f, 0.f};  // four chains: the dot product is not one dependent FMA string
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
@@ -790,24 +793,55 @@ fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
           }
         }
       }
-      float s = (sum[0] + sum[1]) + (sum[2] + sum[3]);
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-      if (lane == q) mysum = s;
-      ++q;
+      return (sum[0] + sum[1]) + (sum[2] + sum[3]);
+    };
+    // warp totals of N per-lane values at once (N = 4: 7 shuffles instead of 20): after the
+    // exchange steps lane L holds the total of value (L >> 3) & (N - 1); pixel q0 + i goes to lane q0 + i
+    auto reduce_to_owners = [&](auto n_tag, const float (&val)[decltype(n_tag)::value], int q0) {
+      constexpr int N = decltype(n_tag)::value;
+      float x;
+      if constexpr (N == 4) {
+        const bool hi = (lane & 16) != 0, mid = (lane & 8) != 0;
+        float k0 = hi ? val[2] : val[0], k1 = hi ? val[3] : val[1];
+        k0 += __shfl_xor_sync(0xffffffffu, hi ? val[0] : val[2], 16);
+        k1 += __shfl_xor_sync(0xffffffffu, hi ? val[1] : val[3], 16);
+        x = (mid ? k1 : k0) + __shfl_xor_sync(0xffffffffu, mid ? k0 : k1, 8);
+      } else if constexpr (N == 2) {
+        const bool mid = (lane & 8) != 0;
+        x = (mid ? val[1] : val[0]) + __shfl_xor_sync(0xffffffffu, mid ? val[0] : val[1], 8);
+        x += __shfl_xor_sync(0xffffffffu, x, 16);
+      } else {
+        x = val[0] + __shfl_xor_sync(0xffffffffu, val[0], 16);
+        x += __shfl_xor_sync(0xffffffffu, x, 8);
+      }
+      x += __shfl_xor_sync(0xffffffffu, x, 4);
+      x += __shfl_xor_sync(0xffffffffu, x, 2);
+      x += __shfl_xor_sync(0xffffffffu, x, 1);
+      const int i = lane - q0;
+      const float got = __shfl_sync(0xffffffffu, x, (i & (N - 1)) << 3);
+      if (i >= 0 && i < N) mysum = got;
     };
     auto window = [&](auto s_tag, int l) {  // pooled level, window side known at compile time
       constexpr int S = decltype(s_tag)::value;
       const int W = p.W[l];
 #pragma unroll
-      for (int dy = 0; dy < S; ++dy)
+      for (int dy = 0; dy < S; ++dy) {
+        float val[S];
 #pragma unroll
         for (int dxx = 0; dxx < S; ++dxx) {
           const unsigned pos = (unsigned)(dy * S + dxx);
-          pixel(l, loff[l] + pos * pixB, lpix[l] + (size_t)dy * W + dxx, true, [&](int v, int u) {
+          val[dxx] = pixel(l, loff[l] + pos * pixB, lpix[l] + (size_t)dy * W + dxx, q + dxx, true, [&](int v, int u) {
             return (((arg[l < kFusedMaxPooled ? l : 0][v][u >> 2] >> (8 * (u & 3))) & 255u) == pos) ? gg[v][u] : 0.f;
           });
         }
+        reduce_to_owners(std::integral_constant<int, S>{}, val, q);
+        q += S;
+      }
+    };
+    auto single = [&](int l, uint32_t boff, size_t pix, bool write_dx, auto routed) {
+      float val[1] = {pixel(l, boff, pix, q, write_dx, routed)};
+      reduce_to_owners(std::integral_constant<int, 1>{}, val, q);
+      ++q;
     };
 #pragma unroll
     for (int l = 0; l < kMaxLevels; ++l) {
@@ -816,21 +850,20 @@ fpn_bwd_fused_tma(const FpnParams p, const FusedGeom geo) {
         const int s = geo.s[l];
         if (s == 4) window(std::integral_constant<int, 4>{}, l);
         else if (s == 2) window(std::integral_constant<int, 2>{}, l);
-        else if (s == 1) window(std::integral_constant<int, 1>{}, l);
         else {
           const int W = p.W[l];
           for (int dy = 0; dy < s; ++dy)
             for (int dxx = 0; dxx < s; ++dxx) {
               const unsigned pos = (unsigned)(dy * s + dxx);
-              pixel(l, loff[l] + pos * pixB, lpix[l] + (size_t)dy * W + dxx, true, [&](int v, int u) {
+              single(l, loff[l] + pos * pixB, lpix[l] + (size_t)dy * W + dxx, true, [&](int v, int u) {
                 return (((arg[l < kFusedMaxPooled ? l : 0][v][u >> 2] >> (8 * (u & 3))) & 255u) == pos) ? gg[v][u] : 0.f;
               });
             }
         }
       } else if (l == R) {
-        pixel(l, loff[l], rpix, true, [&](int v, int u) { return gg[v][u]; });
+        single(l, loff[l], rpix, true, [&](int v, int u) { return gg[v][u]; });
       } else {
-        pixel(l, loff[l], 0, false, [&](int, int) { return 0.f; });  // d x: gather_bwd_up_cl
+        single(l, loff[l], 0, false, [&](int, int) { return 0.f; });  // d x: gather_bwd_up_cl
       }
     }
     if (half == 1) psum[lane] = mysum;
