@@ -430,7 +430,13 @@ struct PullWs {
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Tiles of the two pull passes (4- and 8-pixel-wide tiles, 8 rows).
-inline bool pull_heavy(int H, int W) { return (long long)H * W <= 64 * 96; }
+inline bool pull_heavy(int H, int W) {
+  // Narrow (8 x 4) tiles at every level: smaller stages keep more of them in flight in the ring,
+  // which is what the pull kernel's speed follows (8 x 8 tiles on the two large levels: 166 us,
+  // narrow everywhere: 141 us on the bench workload; profiles/r2_pull_tiles.txt).
+  static const long long cut = ARFE_KNOB_ENV("ARFE_PULL_HEAVY_PX", 1 << 30);
+  return (long long)H * W <= cut;
+}
 inline int pull_tiles(int L, int B, const int* H, const int* W) {
   int n = 0;
   for (int l = 0; l < L; ++l) {
@@ -1113,8 +1119,10 @@ __device__ int init_candidates(ListSmem& sm, const PullWs& ws, int key) {
 // Ordered compaction of the regions intersecting the tile into sm.list, from
 // candidate `pos` on, until the candidates or the list capacity run out.
 // Returns the new cursor.  CTA-wide (uniform control flow).
+// jcap: output columns per list entry (narrow tiles: 4, so that a stage stays small enough for
+// two producer rings at three CTAs per SM; wide tiles: kJ).
 __device__ int build_list(ListSmem& sm, const RoiFuseParams& p, const PullWs& ws, const Tile& T,
-                          int pos, int total_cand) {
+                          int pos, int total_cand, int jcap) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int PW = p.PW;
   __syncthreads();
@@ -1147,7 +1155,7 @@ __device__ int build_list(ListSmem& sm, const RoiFuseParams& p, const PullWs& ws
         }
         if (phi >= 0) {
           nbr = (h.flags >> 8) & 15;
-          ncb = (phi - plo + kJ) / kJ;
+          ncb = (phi - plo + jcap) / jcap;
           mine = nbr * ncb;
         }
       }
@@ -1175,8 +1183,8 @@ __device__ int build_list(ListSmem& sm, const RoiFuseParams& p, const PullWs& ws
       for (int rb = 0; rb < nbr; ++rb)
         for (int cb = 0; cb < ncb; ++cb) {
           e.id = id | (rb << 24);
-          e.pw0 = (short)(plo + cb * kJ);
-          e.npw = (short)min(kJ, phi - (plo + cb * kJ) + 1);
+          e.pw0 = (short)(plo + cb * jcap);
+          e.npw = (short)min(jcap, phi - (plo + cb * jcap) + 1);
           sm.list[o++] = e;
         }
       atomicMax(&sm.list_n, end);
@@ -1270,11 +1278,12 @@ __device__ void bin_tile(ListSmem& sm, const RoiFuseParams& p, const PullWs& ws,
   // How many list entries in all?  Usually one pass of the list builder holds
   // them; long lists (upper levels, thousands of RoIs) are counted pass by pass
   // first, so that the tile still gets ONE contiguous run of the pool.
-  int pos = build_list(sm, p, ws, T, 0, total_cand);
+  constexpr int jcap = TW == 4 ? 4 : kJ;
+  int pos = build_list(sm, p, ws, T, 0, total_cand, jcap);
   int n = sm.list_n;
   const bool single = pos >= total_cand;
   while (pos < total_cand) {
-    pos = build_list(sm, p, ws, T, pos, total_cand);
+    pos = build_list(sm, p, ws, T, pos, total_cand, jcap);
     n += sm.list_n;
   }
   if (tid == 0) {
@@ -1293,7 +1302,7 @@ __device__ void bin_tile(ListSmem& sm, const RoiFuseParams& p, const PullWs& ws,
     int done = 0;  // entries written so far
     pos = 0;
     do {
-      if (!single) pos = build_list(sm, p, ws, T, pos, total_cand);  // else: the list is still in place
+      if (!single) pos = build_list(sm, p, ws, T, pos, total_cand, jcap);  // else: the list is still in place
       const int m = sm.list_n;
       for (int c0 = 0; c0 < m; c0 += chunk) {
         const int nc = min(chunk, m - c0);
@@ -1358,7 +1367,9 @@ roi_bin_kernel(const RoiFuseParams p, const PullWs ws, const TileMap tm4, const 
 // TW pixels with that column's weights (zero where it does not reach): FFMA2
 // arithmetic on shared-memory operands, accumulators in registers, every
 // gradient element written once -- no atomics, no zero-fill, deterministic.
-constexpr int kNSlot = 16;
+constexpr int kNSlot = 16;      // stages (groups of list entries) in flight
+constexpr int kDescSlots = 32;  // list-entry descriptors in flight
+constexpr int kMaxGroup = 8;    // list entries per stage
 constexpr int kDescBytes = (int)sizeof(StageDesc);
 constexpr int kTileQ = 4;      // tiles announced ahead of the consumers
 constexpr int kPullCtl = 1024; // barriers, stage offsets, tile queue
@@ -1372,17 +1383,19 @@ constexpr int kPullCtl = 1024; // barriers, stage offsets, tile queue
 struct PullCtl {
   uint64_t full[kNSlot], empty[kNSlot];
   uint64_t tq_full[kTileQ], tq_empty[kTileQ];
-  uint32_t stage_off[kNSlot];
-  int4 tq[kTileQ];  // {work item g (< 0: no more work), pool offset, stages, 0}
+  int4 sinfo[kNSlot];  // per stage: {first descriptor slot, list entries, ring offset of its bins, 0}
+  int4 tq[kTileQ];  // {work item g (< 0: no more work), pool offset, list entries, 0}
 };
 static_assert(sizeof(PullCtl) <= kPullCtl, "control block");
 
-// Consumer side of one tile: stages [stage0, stage0 + n).
+// Consumer side of one tile: its n list entries arrive in stages of 1 .. kMaxGroup entries
+// (as many as the producer could fit when it issued them) from stage `stage` on; one wait
+// and one release per stage, not per entry.
 template <typename T, int TW, int NV>
 __device__ __forceinline__ void pull_consume_tile(const RoiFuseParams& p, const PullWs& ws,
                                                   const TileMap& tm, PullCtl& ctl,
                                                   const StageDesc* desc, const unsigned char* ring,
-                                                  int block, int n, int stage0) {
+                                                  int block, int n, int& stage) {
   constexpr int V = VecOf<T>::n;
   constexpr int V2 = V / 2;
   constexpr int CG = 32 * V * NV;  // channels per group; NV > 1 requires C % CG == 0 (launcher)
@@ -1404,54 +1417,59 @@ __device__ __forceinline__ void pull_consume_tile(const RoiFuseParams& p, const 
 #pragma unroll
       for (int u = 0; u < V2; ++u) acc[x][v][u] = 0ull;
 
-  for (int i = 0; i < n; ++i) {
-    const int stage = stage0 + i;
+  for (int done = 0; done < n; ++stage) {
     const int slot = stage % kNSlot;
     mbar_wait(ctl.full + slot, (stage / kNSlot) & 1);
-    const StageDesc& d = desc[slot];
-    const int4 rd = d.rows[warp];
-    if (act && rd.x >= 0 && !ARFE_SKIP(p, 1)) {  // (profiling aid: no math)
+    const int4 info = ctl.sinfo[slot];
+    uint32_t soff = (uint32_t)info.z;
+    for (int ge = 0; ge < info.y; ++ge) {
+      const StageDesc& d = desc[(info.x + ge) % kDescSlots];
+      const int4 rd = d.rows[warp];
       const int npw = d.npw;
-      const float a0 = __int_as_float(rd.z), a1 = __int_as_float(rd.w);
-      const uint64_t a0p = pack2(a0, a0), a1p = pack2(a1, a1);
-      const unsigned char* __restrict__ s0 =
-          ring + ctl.stage_off[slot] + (uint32_t)(rd.x * npw) * bin_bytes + (uint32_t)(lane * V) * sizeof(T);
-      const uint32_t two_step = rd.y ? (uint32_t)npw * bin_bytes : 0u;
+      if (act && rd.x >= 0 && !ARFE_SKIP(p, 1)) {  // (profiling aid: no math)
+        const float a0 = __int_as_float(rd.z), a1 = __int_as_float(rd.w);
+        const uint64_t a0p = pack2(a0, a0), a1p = pack2(a1, a1);
+        const unsigned char* __restrict__ s0 =
+            ring + soff + (uint32_t)(rd.x * npw) * bin_bytes + (uint32_t)(lane * V) * sizeof(T);
+        const uint32_t two_step = rd.y ? (uint32_t)npw * bin_bytes : 0u;
 #pragma unroll 2
-      for (int jj = 0; jj < npw; ++jj) {
-        uint64_t e[NV][V2];
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          lds_pairs<T>(s0 + v * kVecBytes, e[v]);
-#pragma unroll
-          for (int u = 0; u < V2; ++u) e[v][u] = mul2(e[v][u], a0p);
-        }
-        if (rd.y) {
+        for (int jj = 0; jj < npw; ++jj) {
+          uint64_t e[NV][V2];
 #pragma unroll
           for (int v = 0; v < NV; ++v) {
-            uint64_t e1[V2];
-            lds_pairs<T>(s0 + two_step + v * kVecBytes, e1);
+            lds_pairs<T>(s0 + v * kVecBytes, e[v]);
 #pragma unroll
-            for (int u = 0; u < V2; ++u) e[v][u] = fma2(e1[u], a1p, e[v][u]);
+            for (int u = 0; u < V2; ++u) e[v][u] = mul2(e[v][u], a0p);
           }
+          if (rd.y) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              uint64_t e1[V2];
+              lds_pairs<T>(s0 + two_step + v * kVecBytes, e1);
+#pragma unroll
+              for (int u = 0; u < V2; ++u) e[v][u] = fma2(e1[u], a1p, e[v][u]);
+            }
+          }
+          float w[TW];
+#pragma unroll
+          for (int x = 0; x < TW; x += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(d.cw[jj] + x);
+            w[x] = t4.x; w[x + 1] = t4.y; w[x + 2] = t4.z; w[x + 3] = t4.w;
+          }
+#pragma unroll
+          for (int x = 0; x < TW; ++x) {
+            const uint64_t wp = pack2(w[x], w[x]);
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+#pragma unroll
+              for (int u = 0; u < V2; ++u) acc[x][v][u] = fma2(e[v][u], wp, acc[x][v][u]);
+          }
+          s0 += bin_bytes;
         }
-        float w[TW];
-#pragma unroll
-        for (int x = 0; x < TW; x += 4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(d.cw[jj] + x);
-          w[x] = t4.x; w[x + 1] = t4.y; w[x + 2] = t4.z; w[x + 3] = t4.w;
-        }
-#pragma unroll
-        for (int x = 0; x < TW; ++x) {
-          const uint64_t wp = pack2(w[x], w[x]);
-#pragma unroll
-          for (int v = 0; v < NV; ++v)
-#pragma unroll
-            for (int u = 0; u < V2; ++u) acc[x][v][u] = fma2(e[v][u], wp, acc[x][v][u]);
-        }
-        s0 += bin_bytes;
       }
+      soff += (uint32_t)(d.nph * npw) * bin_bytes;
     }
+    done += info.y;
     __syncwarp();
     if (lane == 0) mbar_arrive(ctl.empty + slot);
   }
@@ -1474,180 +1492,170 @@ __device__ __forceinline__ void pull_consume_tile(const RoiFuseParams& p, const 
 // Work item g in [0, nb4 + nb8): (tile, channel group) of the narrow-tile pass,
 // then of the wide-tile pass.
 //
-// NP producer warps.  One thread needs ~250 ns per (barrier wait, expect_tx, bulk
-// copy) sequence however small the copy (scripts/micro/l2_tma_bw.cu), and that, not
-// bandwidth, bounds a stream of 10-50 KB stages; the rate scales with the number of
-// issuing warps.  Producer w owns the stages s with s % NP == w (s counts the CTA's
-// stages), the slots s % kNSlot of those stages and the w-th part of the byte ring.
-// Producer 0 also claims the work items and announces them in the tile queue;
-// the others follow the queue like the consumers do.
-template <typename T, int NV, int NP>
-__global__ void __launch_bounds__((kTileH + NP) * 32, (VecOf<T>::n * NV == 4 ? 3 : 2))
+// ONE producer warp, vectorised: a pass of its loop takes the next list entries of the
+// tile -- lane t does the bookkeeping and issues the bulk copies of the t-th of them (its
+// 400-byte descriptor, its bin rows) -- and hands as many as fit the ring (up to kMaxGroup)
+// to the consumers as ONE stage behind one mbarrier.  A single lane walking one entry at a
+// time (~100 dependent instructions, ~0.5 us) used to be what the consumers waited for;
+// one barrier round trip per entry was the next cost (profiles/r2_pull_stages.txt).
+template <typename T, int NV, bool kNarrow>
+__global__ void __launch_bounds__((kTileH + 1) * 32, (VecOf<T>::n * NV == 4 ? 3 : 2))
 roi_bwd_pull_tma(const RoiFuseParams p, const PullWs ws, const TileMap tm4, const TileMap tm8,
-                 int nb4, int nb8, int ring_bytes) {
+                 int nb4, int nb8, int ring_bytes, int gmax) {
   constexpr int V = VecOf<T>::n;
   constexpr int CG = 32 * V * NV;
-  constexpr int kOwnSlots = kNSlot / NP;
-  static_assert(kNSlot % NP == 0, "slots are dealt round-robin to the producers");
   extern __shared__ __align__(16) unsigned char smem[];
   PullCtl& ctl = *reinterpret_cast<PullCtl*>(smem);
   StageDesc* desc = reinterpret_cast<StageDesc*>(smem + kPullCtl);
-  unsigned char* ring = smem + kPullCtl + kNSlot * kDescBytes;
+  unsigned char* ring = smem + kPullCtl + kDescSlots * kDescBytes;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int total = nb4 + nb8;
 
   if (tid == 0) {
     for (int i = 0; i < kNSlot; ++i) { mbar_init(ctl.full + i, 1); mbar_init(ctl.empty + i, kTileH); }
-    for (int i = 0; i < kTileQ; ++i) { mbar_init(ctl.tq_full + i, 1); mbar_init(ctl.tq_empty + i, kTileH + NP - 1); }
+    for (int i = 0; i < kTileQ; ++i) { mbar_init(ctl.tq_full + i, 1); mbar_init(ctl.tq_empty + i, kTileH); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   if (warp >= kTileH) {
-    // ------------------------------------------------------------ producers
-    const int w = warp - kTileH;
-    const uint32_t sub_bytes = ((uint32_t)ring_bytes / NP) & ~127u;
-    unsigned char* const sub = ring + (uint32_t)w * sub_bytes;
-    uint32_t head = 0, tail = 0;  // live bytes of this producer's ring part: [tail, head) modulo wrap
-    uint32_t my_off = 0;          // lane j: offset of the stage in this producer's j-th slot
-    int issued = 0, released = 0; // own stages issued / known to be consumed
+    // ------------------------------------------------------------ producer
+    const uint32_t ring_cap = (uint32_t)ring_bytes & ~127u;
+    uint32_t head = 0, tail = 0;  // live bytes of the ring: [tail, head) modulo wrap
+    uint32_t my_off = 0;          // lane s: ring offset of the stage in slot s
+    int my_m = 0;                 // lane s: list entries of the stage in slot s
+    int issued = 0, released = 0; // stages issued / known to be consumed
+    int dissued = 0, dreleased = 0;  // descriptor slots handed out / free again
     const int C = p.C, BS = p.bin_stride;
-    // slot and barrier phase of this producer's o-th stage
-    auto slot_of = [&](int o) -> int { return (o * NP + w) % kNSlot; };
-    auto phase_of = [&](int o) -> uint32_t { return (uint32_t)((o * NP + w) / kNSlot) & 1u; };
     auto load_hdr = [&](int pool_off, int n, int first) -> int4 {
       return (n > 0 && first + lane < n) ? __ldg(reinterpret_cast<const int4*>(ws.pool + pool_off + first + lane))
                                          : make_int4(0, 0, 0, 0);
     };
-    // stages [0, n) of work item g (pool entries from pool_off) whose CTA-wide index
-    // stage0 + i belongs to this producer; hdr = headers of the first 32 entries
-    auto produce = [&](int g, int pool_off, int n, int stage0, int4 hdr) {
+    auto retire = [&]() {  // stage `released` was consumed: its ring space and descriptor slots are free
+      dreleased += __shfl_sync(0xffffffffu, my_m, released % kNSlot);
+      ++released;
+      const uint32_t nxt = __shfl_sync(0xffffffffu, my_off, released % kNSlot);
+      tail = released < issued ? nxt : head;
+    };
+    // the n list entries of work item g (pool entries from pool_off); hdr = headers of the first 32
+    auto produce = [&](int g, int pool_off, int n, int4 hdr) {
       const bool narrow = g < nb4;
       const int grp = narrow ? g % tm4.groups : (g - nb4) % tm8.groups;
       const int c0 = grp * CG;
       const uint32_t bin_bytes = (uint32_t)min(CG, C - c0) * sizeof(T);
       const T* __restrict__ dsrc = static_cast<const T*>(p.dout) + c0;
       const StageDesc* __restrict__ gdesc = ws.pool + pool_off;
-      for (int i = 0; i < n; ++i) {
-        if ((i & 31) == 0 && i > 0) hdr = load_hdr(pool_off, n, i);
-        if (NP > 1 && (stage0 + i) % NP != w) continue;
-        const int src_off = __shfl_sync(0xffffffffu, hdr.x, i & 31);
-        const int nn = __shfl_sync(0xffffffffu, hdr.y, i & 31);
-        const int rg = __shfl_sync(0xffffffffu, hdr.z, i & 31);
+      int chunk0 = 0;  // hdr holds entries [chunk0, chunk0 + 32)
+      int i = 0;       // next entry
+      while (i < n) {
+        if (i >= chunk0 + 32) {
+          chunk0 = (i / 32) * 32;
+          hdr = load_hdr(pool_off, n, chunk0);
+        }
+        const int it = i + lane;  // this lane's entry
+        const bool valid = it < min(n, chunk0 + 32) && lane < gmax;
+        const int hl = valid ? (it & 31) : 0;
+        const int src_off = __shfl_sync(0xffffffffu, hdr.x, hl);
+        const int nn = __shfl_sync(0xffffffffu, hdr.y, hl);
+        const int rg = __shfl_sync(0xffffffffu, hdr.z, hl);
         const int nph = nn & 0xffff, npw = (nn >> 16) & 0xffff;
         const int nbins = nph * npw;
-        const uint32_t bytes = (uint32_t)nbins * bin_bytes;
-        const int slot = slot_of(issued);
-        // the slot's previous stage and enough ring space must have been released
-        // (a producer's stages are released in order)
-        auto release_one = [&]() {
-          mbar_wait(ctl.empty + slot_of(released), phase_of(released));
-          ++released;
-          const uint32_t nxt = __shfl_sync(0xffffffffu, my_off, released % kOwnSlots);
-          tail = released < issued ? nxt : head;
-        };
-        while (released < issued - kOwnSlots + 1) release_one();
-        uint32_t off;
+        const uint32_t bytes = valid ? (uint32_t)nbins * bin_bytes : 0u;
+        uint32_t incl = bytes;  // inclusive prefix over the lanes
+#pragma unroll
+        for (int d = 1; d < kMaxGroup; d <<= 1) {
+          const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += v;
+        }
+        const uint32_t bytes0 = __shfl_sync(0xffffffffu, bytes, 0);
+        int m = 0;
         while (true) {
-          if (released == issued) { head = tail = 0; off = 0; break; }           // ring empty
-          if (head >= tail) {
-            if (head + bytes <= sub_bytes) { off = head; break; }
-            if (bytes < tail) { off = 0; break; }                                  // wrap
-          } else if (head + bytes < tail) { off = head; break; }
-          release_one();
+          while (released < issued && mbar_test(ctl.empty + released % kNSlot, (released / kNSlot) & 1)) retire();
+          if (released == issued) head = tail = 0;  // ring empty
+          const uint32_t room = head >= tail ? ring_cap - head : tail - head - 1u;
+          // the entries of a tile are consecutive in the pool: their descriptors travel as ONE
+          // copy, so a stage does not run across the end of the descriptor ring
+          const int free_desc = min(kDescSlots - (dissued - dreleased), kDescSlots - dissued % kDescSlots);
+          if (issued - released < kNSlot)
+            m = __popc(__ballot_sync(0xffffffffu, valid && incl <= room && lane < free_desc));
+          if (m > 0) break;
+          if (issued - released < kNSlot && free_desc > 0 && head >= tail && released != issued && bytes0 < tail) {
+            head = 0;  // wrap
+            continue;
+          }
+          mbar_wait(ctl.empty + released % kNSlot, (released / kNSlot) & 1);  // wait for the oldest stage
+          retire();
         }
-        head = off + bytes;
-        if (lane == issued % kOwnSlots) my_off = off;
-        unsigned char* const dst = sub + off;
+        const int slot = issued % kNSlot;
+        const uint32_t sbytes = __shfl_sync(0xffffffffu, incl, m - 1);
+        if (lane == slot) { my_off = head; my_m = m; }
         if (lane == 0) {
-          ctl.stage_off[slot] = (uint32_t)(dst - ring);
-          mbar_arrive_expect_tx(ctl.full + slot, (ARFE_SKIP(p, 2) ? 0u : bytes) + kDescBytes);
-          bulk_g2s(desc + slot, gdesc + i, kDescBytes, ctl.full + slot);
+          ctl.sinfo[slot] = make_int4(dissued % kDescSlots, m, (int)head, 0);
+          mbar_arrive_expect_tx(ctl.full + slot, (ARFE_SKIP(p, 2) ? 0u : sbytes) + (uint32_t)m * kDescBytes);
         }
-        if (ARFE_SKIP(p, 2)) {
-          // profiling aid: no bin copies
-        } else if ((uint32_t)BS * sizeof(T) == bin_bytes) {
-          // split layout, all channels in this group: the npw bins of a bin row are
-          // contiguous -> one bulk copy per bin row
-          for (int ih = lane; ih < nph; ih += 32)
-            bulk_g2s(dst + (uint32_t)(ih * npw) * bin_bytes,
-                     dsrc + p.reg_off[rg] + (size_t)src_off + (size_t)(ih * p.PW) * BS,
-                     (uint32_t)npw * bin_bytes, ctl.full + slot);
-        } else {
-          for (int bi = lane; bi < nbins; bi += 32) {
-            const int ih = bi / npw, iw = bi - ih * npw;
-            bulk_g2s(dst + (uint32_t)bi * bin_bytes,
-                     dsrc + p.reg_off[rg] + (size_t)src_off + (size_t)(ih * p.PW + iw) * BS, bin_bytes, ctl.full + slot);
+        __syncwarp();
+        if (lane == 0) bulk_g2s(desc + dissued % kDescSlots, gdesc + i, (uint32_t)m * kDescBytes, ctl.full + slot);
+        if (lane < m) {
+          unsigned char* const dst = ring + head + incl - bytes;
+          if (ARFE_SKIP(p, 2)) {
+            // profiling aid: no bin copies
+          } else if ((uint32_t)BS * sizeof(T) == bin_bytes) {
+            // split layout, all channels in this group: the npw bins of a bin row are
+            // contiguous -> one bulk copy per bin row
+            for (int ih = 0; ih < nph; ++ih)
+              bulk_g2s(dst + (uint32_t)(ih * npw) * bin_bytes,
+                       dsrc + p.reg_off[rg] + (size_t)src_off + (size_t)(ih * p.PW) * BS,
+                       (uint32_t)npw * bin_bytes, ctl.full + slot);
+          } else {
+            for (int bi = 0; bi < nbins; ++bi) {
+              const int ih = bi / npw, iw = bi - ih * npw;
+              bulk_g2s(dst + (uint32_t)bi * bin_bytes,
+                       dsrc + p.reg_off[rg] + (size_t)src_off + (size_t)(ih * p.PW + iw) * BS, bin_bytes, ctl.full + slot);
+            }
           }
         }
+        __syncwarp();
+        head += sbytes;
         ++issued;
+        dissued += m;
+        i += m;
       }
     };
-    int stage0 = 0;
     auto claim = [&]() -> int { return lane == 0 ? atomicAdd(ws.counters + 2, 1) : 0; };
     auto tile_desc_of = [&](int g) -> int2 {
       if (g >= total) return make_int2(0, -1);
       return g < nb4 ? ws.tile_desc[tm4.tile_base + g / tm4.groups]
                      : ws.tile_desc[tm8.tile_base + (g - nb4) / tm8.groups];
     };
-    // current item {g (< 0: no more work), pool offset, stages} and its first 32 headers
-    int4 q = make_int4(0, 0, 0, 0), hdr = make_int4(0, 0, 0, 0);
-    // producer 0: software pipeline -- claim two items ahead, tile descriptor and the
-    // first 32 stage headers one item ahead
-    int c_next = 0;
-    // followers: the next item, when it had been announced already
-    bool have = false;
-    if (w == 0) {
-      const int g = __shfl_sync(0xffffffffu, claim(), 0);
-      c_next = claim();
+    // software pipeline over the work items: the claim (an atomic), the tile descriptor (a load that
+    // needs the claim) and the first 32 entry headers (a load that needs the descriptor) of item
+    // k + 3 / k + 2 / k + 1 are in flight while item k is produced -- none of the three latencies
+    // is on the path of a tile any more (tiles of the big levels hold only a few entries each)
+    auto item_of = [&](int g) -> int4 {
       const int2 td = tile_desc_of(g);
-      q = make_int4(g < total ? g : -1, td.x, td.y, 0);
-      hdr = load_hdr(q.y, q.z, 0);
-    }
+      // (profiling aid 4: every tile as if no region reached it -- the cost of the tile loop and the write-out)
+      return make_int4(g < total ? g : -1, td.x, ARFE_SKIP(p, 4) ? min(td.y, 0) : td.y, 0);
+    };
+    int4 q = item_of(__shfl_sync(0xffffffffu, claim(), 0));
+    int4 q1 = item_of(__shfl_sync(0xffffffffu, claim(), 0));
+    int c2 = claim();
+    int4 hdr = load_hdr(q.y, q.z, 0);
+    int4 hdr1 = load_hdr(q1.y, q1.z, 0);
     for (int it = 0;; ++it) {
-      int4 q_next = make_int4(0, 0, 0, 0), hdr_next = make_int4(0, 0, 0, 0);
-      if (w == 0) {
-        const int g_next = __shfl_sync(0xffffffffu, c_next, 0);
-        c_next = claim();
-        const int2 td_next = tile_desc_of(g_next);
-        q_next = make_int4(g_next < total ? g_next : -1, td_next.x, td_next.y, 0);
-        // announce the current item
-        const int qs = it % kTileQ;
-        if (it >= kTileQ) mbar_wait(ctl.tq_empty + qs, ((it / kTileQ) - 1) & 1);
-        if (lane == 0) {
-          ctl.tq[qs] = q;
-          mbar_arrive(ctl.tq_full + qs);
-        }
-      } else {
-        if (!have) {
-          const int qs = it % kTileQ;
-          mbar_wait(ctl.tq_full + qs, (it / kTileQ) & 1);
-          q = ctl.tq[qs];
-          __syncwarp();
-          if (lane == 0) mbar_arrive(ctl.tq_empty + qs);
-          hdr = load_hdr(q.y, q.z, 0);
-        }
-        have = false;
-        if (q.x >= 0) {
-          const int qn = (it + 1) % kTileQ;
-          const int ready = __shfl_sync(0xffffffffu, (int)mbar_test(ctl.tq_full + qn, ((it + 1) / kTileQ) & 1), 0);
-          if (ready) {
-            q_next = ctl.tq[qn];
-            __syncwarp();
-            if (lane == 0) mbar_arrive(ctl.tq_empty + qn);
-            hdr_next = load_hdr(q_next.y, q_next.z, 0);
-            have = true;
-          }
-        }
+      const int4 q2 = item_of(__shfl_sync(0xffffffffu, c2, 0));
+      c2 = claim();
+      // announce the current item
+      const int qs = it % kTileQ;
+      if (it >= kTileQ) mbar_wait(ctl.tq_empty + qs, ((it / kTileQ) - 1) & 1);
+      if (lane == 0) {
+        ctl.tq[qs] = q;
+        mbar_arrive(ctl.tq_full + qs);
       }
       if (q.x < 0) break;
-      if (q.z > 0) {  // < 0: inline tile, nothing to stream
-        produce(q.x, q.y, q.z, stage0, hdr);
-        stage0 += q.z;
-      }
-      // rotate: producer 0's next descriptor has been in flight since the top
-      q = q_next;
-      hdr = w == 0 ? load_hdr(q.y, q.z, 0) : hdr_next;
+      const int4 hdr2 = load_hdr(q2.y, q2.z, 0);
+      if (q.z > 0) produce(q.x, q.y, q.z, hdr);  // < 0: inline tile, nothing to stream
+      q = q1; q1 = q2;
+      hdr = hdr1; hdr1 = hdr2;
     }
     return;
   }
@@ -1663,9 +1671,8 @@ roi_bwd_pull_tma(const RoiFuseParams p, const PullWs ws, const TileMap tm4, cons
     if (q.x < 0) break;
     const int n = q.z;
     if (n < 0) continue;  // served by roi_bwd_pull_inline
-    if (q.x < nb4) pull_consume_tile<T, 4, NV>(p, ws, tm4, ctl, desc, ring, q.x, n, stage);
+    if (kNarrow || q.x < nb4) pull_consume_tile<T, 4, NV>(p, ws, tm4, ctl, desc, ring, q.x, n, stage);
     else pull_consume_tile<T, 8, NV>(p, ws, tm8, ctl, desc, ring, q.x - nb4, n, stage);
-    stage += n;
   }
 }
 
@@ -1694,7 +1701,7 @@ __device__ void pull_tile_inline(const RoiFuseParams& p, const PullWs& ws, const
     const int total_cand = init_candidates(sm, ws, tl.key);
     int pos = 0;
     while (pos < total_cand) {
-      pos = build_list(sm, p, ws, tl, pos, total_cand);
+      pos = build_list(sm, p, ws, tl, pos, total_cand, TW == 4 ? 4 : kJ);
       const int n = sm.list_n;
       for (int q0 = 0; q0 < n; q0 += kChunkR) {
         const int nc = min(kChunkR, n - q0);
@@ -1951,28 +1958,30 @@ cudaError_t launch_roi_fuse_backward_pull(const RoiFuseParams& p, int dtype, voi
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   if (!(stages & 4)) return cudaSuccess;
-  const int per_sm = (dtype == 0 && nv == 1) ? 3 : 2;
-  // two producer warps (each owning half of a slightly larger ring) when the largest
-  // possible stage fits one half
-  static const int np_env = ARFE_KNOB_ENV("ARFE_PULL_NP", 0);
-  const int max_stage = (p.PH < kMaxPh ? p.PH : kMaxPh) * (p.PW < kJ ? p.PW : kJ) * 32 * V * nv * (dtype == 0 ? 4 : 2);
-  const int np = (per_sm == 2 && max_stage <= 52 * 1024 && np_env != 1) ? 2 : 1;
-  const int ring = per_sm == 3 ? 64 * 1024 : (np == 2 ? 104 * 1024 : 96 * 1024);
-  const int smem = kPullCtl + kNSlot * kDescBytes + ring;
+  const bool narrow = ntiles[1] == 0;  // every tile is 4 pixels wide
+  static const int persm_env = ARFE_KNOB_ENV("ARFE_PULL_PERSM", 0);
+  const int per_sm = persm_env ? persm_env : ((dtype == 0 && nv == 1) ? 3 : 2);
+  static const int gmax_env = ARFE_KNOB_ENV("ARFE_PULL_G", kMaxGroup);
+  const int gmax = gmax_env < 1 ? 1 : (gmax_env > kMaxGroup ? kMaxGroup : gmax_env);
+  const int ring = (((per_sm == 3 ? 75 : 113) * 1024 - kPullCtl - kDescSlots * kDescBytes) / 1024) * 1024;
+  const int jmax = narrow ? 4 : kJ;
+  const int max_entry = (p.PH < kMaxPh ? p.PH : kMaxPh) * (p.PW < jmax ? p.PW : jmax) * 32 * V * nv * (dtype == 0 ? 4 : 2);
+  if (max_entry > ring) return cudaErrorInvalidValue;  // (C <= 512 per group by construction: cannot happen)
+  const int smem = kPullCtl + kDescSlots * kDescBytes + ring;
   const int nb4 = ntiles[0] * tm[0].groups, nb8 = ntiles[1] * tm[1].groups;
   const int sms = sm_count();
   const int pgrid = nb4 + nb8 < per_sm * sms ? nb4 + nb8 : per_sm * sms;
-#define ARFE_PULL(TT, NVV, NPP)                                                                     \
+#define ARFE_PULL(TT, NVV, NAR)                                                                     \
   do {                                                                                              \
-    if ((e = set_smem(roi_bwd_pull_tma<TT, NVV, NPP>, smem)) != cudaSuccess) return e;              \
-    roi_bwd_pull_tma<TT, NVV, NPP><<<pgrid, (kTileH + NPP) * 32, smem, stream>>>(p, ws, tm[0], tm[1], nb4, nb8, ring); \
+    if ((e = set_smem(roi_bwd_pull_tma<TT, NVV, NAR>, smem)) != cudaSuccess) return e;              \
+    roi_bwd_pull_tma<TT, NVV, NAR><<<pgrid, (kTileH + 1) * 32, smem, stream>>>(p, ws, tm[0], tm[1], nb4, nb8, ring, gmax); \
   } while (0)
+#define ARFE_PULL_N(TT, NVV) do { if (narrow) ARFE_PULL(TT, NVV, true); else ARFE_PULL(TT, NVV, false); } while (0)
   if (dtype == 0) {
-    if (nv == 2 && np == 2) ARFE_PULL(float, 2, 2);
-    else if (nv == 2) ARFE_PULL(float, 2, 1);
-    else ARFE_PULL(float, 1, 1);
-  } else if (np == 2) ARFE_PULL(__nv_bfloat16, 1, 2);
-  else ARFE_PULL(__nv_bfloat16, 1, 1);
+    if (nv == 2) ARFE_PULL_N(float, 2);
+    else ARFE_PULL_N(float, 1);
+  } else ARFE_PULL_N(__nv_bfloat16, 1);
+#undef ARFE_PULL_N
 #undef ARFE_PULL
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   const int igrid = ntiles[0] + ntiles[1] < 592 ? ntiles[0] + ntiles[1] : 592;

@@ -45,10 +45,11 @@ print("HASH", h.hexdigest())
 """
 
 
-def test_pull_one_and_two_producer_warps_agree_bitwise(cuda):
-    """The pull backward writes every gradient element once in a fixed order, so the
-    one-producer instantiation (ARFE_PULL_NP=1, a knob that exists only in the -DARFE_PROFILE
-    build libarfe_b200_prof.so) and the shipped library's two-producer one must agree to the bit."""
+def test_pull_stage_grouping_does_not_change_the_bits(cuda):
+    """The pull backward writes every gradient element once, adding the list entries of a tile in
+    list order; how many entries travel per stage (as many as fit the ring when the producer
+    issues them -- timing dependent) must not matter: one entry per stage (ARFE_PULL_G=1, a knob of
+    the -DARFE_PROFILE build libarfe_b200_prof.so) and the shipped library agree to the bit."""
     import os
     import subprocess
     import sys
@@ -57,13 +58,14 @@ def test_pull_one_and_two_producer_warps_agree_bitwise(cuda):
     if not os.path.exists(prof):
         pytest.skip("profile build of the library not present (python -m arfe_b200.build --profile)")
     out = []
-    for env in (dict(os.environ, ARFE_B200_LIB=prof, ARFE_PULL_NP="1"),
+    for env in (dict(os.environ, ARFE_B200_LIB=prof, ARFE_PULL_G="1"),
+                dict(os.environ, ARFE_B200_LIB=prof, ARFE_PULL_G="3"),
                 {k: v for k, v in os.environ.items() if not k.startswith("ARFE_")}):
         r = subprocess.run([sys.executable, "-c", _HASH_SNIPPET % root], env=env, capture_output=True,
                            text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
         out.append([l for l in r.stdout.splitlines() if l.startswith("HASH")][0])
-    assert out[0] == out[1]
+    assert out[0] == out[1] == out[2]
 
 
 def test_shipped_library_has_no_profiling_knobs():
@@ -71,6 +73,6 @@ def test_shipped_library_has_no_profiling_knobs():
     the phase-skip switches: no ARFE_* string survives in libarfe_b200.so."""
     from arfe_b200 import _lib
     data = open(_lib.LIB_PATH, "rb").read()
-    for knob in (b"ARFE_FWD_SKIP", b"ARFE_BWD_SKIP", b"ARFE_PULL_NP", b"ARFE_PULL_NV", b"ARFE_FWD_NCH",
-                 b"ARFE_FWD_OCC", b"ARFE_APPLY_OCC"):
+    for knob in (b"ARFE_FWD_SKIP", b"ARFE_BWD_SKIP", b"ARFE_PULL_G", b"ARFE_PULL_NV", b"ARFE_FWD_NCH",
+                 b"ARFE_FWD_OCC", b"ARFE_APPLY_OCC", b"ARFE_PULL_HEAVY_PX", b"ARFE_PULL_PERSM"):
         assert knob not in data, knob
