@@ -8,8 +8,9 @@ from ._compat import (ConvModule, accelerate_class, optimize_detector,  # noqa: 
                       register_into_mmdet)
 from .bbox_head import MultiBBoxHead, MultiRoIsBBoxHead  # noqa: F401
 from .functional import (fpn_apply, fpn_gather, rff_gate, roi_fuse,  # noqa: F401
-                         roi_fuse_debug, roi_fuse_split, split3)
+                         roi_fuse_debug, roi_fuse_split, rff_softmax_fuse, split3)
 from .neck import NonLocal2D, WFPNDualSpatial  # noqa: F401
+from .proposals import batched_nms, bbox2roi, nms  # noqa: F401
 from .regions import get_adaptive_scale_rois  # noqa: F401
 from .roi_align import RoIAlign, RoIAlignFunction, roi_align  # noqa: F401
 from .roi_extractor import SingleRoIExtractor  # noqa: F401

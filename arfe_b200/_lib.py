@@ -62,6 +62,14 @@ _SIGNATURES = {
                                c_void_p], c_int),
     "arfe_rff_gate_backward": ([c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64,
                                 c_void_p, c_i64, c_i64, c_int, c_void_p], c_int),
+    "arfe_rff_softmax_fuse_forward": ([_pp, ctypes.POINTER(c_i64), c_void_p, ctypes.POINTER(c_i64), c_void_p,
+                                       ctypes.POINTER(c_i64), c_i64, c_int, c_int, c_int, c_void_p], c_int),
+    "arfe_rff_softmax_fuse_backward": ([c_void_p, _pp, ctypes.POINTER(c_i64), c_void_p, ctypes.POINTER(c_i64),
+                                        ctypes.POINTER(c_i64), _pp, c_void_p, c_i64, c_int, c_int, c_int,
+                                        c_void_p], c_int),
+    "arfe_nms_workspace_bytes": ([c_int], ctypes.c_size_t),
+    "arfe_nms": ([c_void_p, c_int, c_float, c_void_p, ctypes.c_size_t, c_void_p, c_void_p, c_void_p], c_int),
+    "arfe_bbox2roi": ([_pp, _ip, _ip, c_int, c_void_p, c_void_p], c_int),
     "arfe_fpn_gather_forward": ([_pp, _ip, _ip, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                  c_void_p, c_void_p], c_int),
     "arfe_fpn_gather_backward": ([c_void_p, c_void_p, _ip, _ip, c_int, c_int, c_int, c_int, c_int,
@@ -114,6 +122,10 @@ def ptr_array(tensors):
 
 def int_array(vals):
     return (ctypes.c_int32 * len(vals))(*[int(v) for v in vals])
+
+
+def i64_array(vals):
+    return (c_i64 * len(vals))(*[int(v) for v in vals])
 
 
 def float_array(vals):

@@ -431,6 +431,78 @@ int arfe_rff_gate_backward(const void* g, const void* ori, int64_t ori_roi_strid
                                                     n_per_roi, dtype, (cudaStream_t)stream), fn);
 }
 
+static int softmax_fuse_impl(const char* fn, int backward, const void* const* regions, const int64_t* region_strides,
+                             const void* logits, const int64_t* logit_strides, void* out, const void* dout,
+                             const int64_t* out_strides, void* const* d_regions, void* d_logits, int64_t K, int PP,
+                             int C, int dtype, void* stream) {
+  REQUIRE(dtype == ARFE_F32 || dtype == ARFE_BF16, ARFE_E_ENUM, "%s: unknown dtype %d", fn, dtype);
+  REQUIRE(K >= 0 && PP >= 1 && C >= 1, ARFE_E_SHAPE, "%s: bad K=%lld PP=%d C=%d", fn, (long long)K, PP, C);
+  if (K == 0) return ARFE_OK;
+  REQUIRE(regions && region_strides && logits && logit_strides && out_strides, ARFE_E_NULL, "%s: NULL argument", fn);
+  REQUIRE(regions[0] && regions[1] && regions[2], ARFE_E_NULL, "%s: NULL region tensor", fn);
+  if (backward) {
+    REQUIRE(dout && d_regions && d_logits && d_regions[0] && d_regions[1] && d_regions[2], ARFE_E_NULL, "%s: NULL gradient tensor", fn);
+  } else {
+    REQUIRE(out, ARFE_E_NULL, "%s: out is NULL", fn);
+  }
+  for (int i = 0; i < 3; ++i)
+    REQUIRE(region_strides[i] >= 1 && out_strides[i] >= 1 && logit_strides[i] >= 1, ARFE_E_SHAPE, "%s: strides must be >= 1", fn);
+  DeviceGuard guard(logits);
+  return cuda_result(arfe::launch_rff_softmax_fuse(backward, regions, region_strides, logits, logit_strides, out, dout,
+                                                   out_strides, d_regions, d_logits, K, PP, C, dtype, (cudaStream_t)stream), fn);
+}
+
+int arfe_rff_softmax_fuse_forward(const void* const* regions, const int64_t* region_strides, const void* logits,
+                                  const int64_t* logit_strides, void* out, const int64_t* out_strides, int64_t K,
+                                  int PP, int C, int dtype, void* stream) {
+  return softmax_fuse_impl("arfe_rff_softmax_fuse_forward", 0, regions, region_strides, logits, logit_strides, out,
+                           nullptr, out_strides, nullptr, nullptr, K, PP, C, dtype, stream);
+}
+
+int arfe_rff_softmax_fuse_backward(const void* dout, const void* const* regions, const int64_t* region_strides,
+                                   const void* logits, const int64_t* logit_strides, const int64_t* out_strides,
+                                   void* const* d_regions, void* d_logits, int64_t K, int PP, int C, int dtype,
+                                   void* stream) {
+  return softmax_fuse_impl("arfe_rff_softmax_fuse_backward", 1, regions, region_strides, logits, logit_strides, nullptr,
+                           dout, out_strides, d_regions, d_logits, K, PP, C, dtype, stream);
+}
+
+size_t arfe_nms_workspace_bytes(int n) { return n > 0 ? arfe::nms_workspace_bytes(n) : 0; }
+
+int arfe_nms(const float* dets_sorted, int n, float iou_threshold, void* workspace, size_t workspace_bytes,
+             int64_t* keep, int32_t* num_keep, void* stream) {
+  const char* fn = "arfe_nms";
+  REQUIRE(n >= 0, ARFE_E_SHAPE, "%s: n=%d", fn, n);
+  REQUIRE(num_keep, ARFE_E_NULL, "%s: num_keep is NULL", fn);
+  if (n > 0) {
+    REQUIRE(dets_sorted && keep && workspace, ARFE_E_NULL, "%s: NULL argument", fn);
+    REQUIRE(aligned(workspace, 8) && aligned(dets_sorted, 4), ARFE_E_ALIGN, "%s: workspace (8) / dets (4) misaligned", fn);
+    REQUIRE(workspace_bytes >= arfe::nms_workspace_bytes(n), ARFE_E_SHAPE, "%s: workspace too small (%zu < %zu)", fn,
+            workspace_bytes, arfe::nms_workspace_bytes(n));
+  }
+  DeviceGuard guard(num_keep);
+  return cuda_result(arfe::launch_nms(dets_sorted, n, iou_threshold, workspace, keep, num_keep, (cudaStream_t)stream), fn);
+}
+
+int arfe_bbox2roi(const float* const* boxes, const int32_t* counts, const int32_t* cols, int B, float* rois,
+                  void* stream) {
+  const char* fn = "arfe_bbox2roi";
+  REQUIRE(B >= 0, ARFE_E_SHAPE, "%s: B=%d", fn, B);
+  if (B == 0) return ARFE_OK;
+  REQUIRE(boxes && counts && cols, ARFE_E_NULL, "%s: NULL argument", fn);
+  long long total = 0;
+  for (int i = 0; i < B; ++i) {
+    REQUIRE(counts[i] >= 0 && cols[i] >= 4, ARFE_E_SHAPE, "%s: list %d has %d rows of %d floats", fn, i, counts[i], cols[i]);
+    REQUIRE(counts[i] == 0 || boxes[i], ARFE_E_NULL, "%s: boxes[%d] is NULL", fn, i);
+    total += counts[i];
+  }
+  if (total == 0) return ARFE_OK;
+  REQUIRE(rois, ARFE_E_NULL, "%s: rois is NULL", fn);
+  REQUIRE(total < (1ll << 31), ARFE_E_SHAPE, "%s: too many boxes", fn);
+  DeviceGuard guard(rois);
+  return cuda_result(arfe::launch_bbox2roi(boxes, counts, cols, B, rois, (cudaStream_t)stream), fn);
+}
+
 static int fill_fpn(const char* fn, arfe::FpnParams& p, const int32_t* H, const int32_t* W, int L,
                     int B, int C, int dtype, int layout) {
   int rc = check_common(fn, L, B, C, H, W, dtype, layout);

@@ -88,6 +88,19 @@ cudaError_t launch_rff_gate_backward(const void* g, const void* ori,
                                      void* d_ab, int64_t K, int64_t n, int dtype,
                                      cudaStream_t stream);
 
+// softmax-over-regions fusion (rff_gate.cu); strides in elements: regions / out (k, bin, channel), logits (k, region, bin)
+cudaError_t launch_rff_softmax_fuse(int backward, const void* const* reg, const int64_t* rstr, const void* logits,
+                                    const int64_t* lstr, void* out, const void* dout, const int64_t* ostr,
+                                    void* const* dreg, void* dlogits, int64_t K, int PP, int C, int dtype,
+                                    cudaStream_t stream);
+
+// proposal side (proposals.cu)
+size_t nms_workspace_bytes(int n);
+cudaError_t launch_nms(const float* dets_sorted, int n, float thr, void* workspace, int64_t* keep, int* num_keep,
+                       cudaStream_t stream);
+cudaError_t launch_bbox2roi(const float* const* boxes, const int* counts, const int* cols, int B, float* rois,
+                            cudaStream_t stream);
+
 struct FpnParams {
   const void* feats[kMaxLevels];  // x_l (gather fwd / apply fwd) or dout_l (apply bwd)
   void* outs[kMaxLevels];         // out_l (apply fwd) or dx_l (gather bwd)

@@ -140,3 +140,166 @@ cudaError_t launch_rff_gate_backward(const void* g, const void* ori, int64_t ori
 }
 
 }  // namespace arfe
+
+// ---------------------------------------------------------------------------
+// AR-RFF, softmax-over-regions variant (the fusion of the paper's figure; in the
+// reference it is the commented block multirois_bbox_head.py:187-197):
+//   ws  = softmax(logits, dim = 1)            logits [K, 3, PH, PW]
+//   out = r0 * ws[:, 0] + r1 * ws[:, 1] + r2 * ws[:, 2]      r_j [K, C, PH, PW]
+// backward: d r_j = d out * ws_j;  d logit_j = ws_j * (s_j - sum_i ws_i s_i) with
+// s_j = sum_c d out * r_j  (a reduction over the C channels of one bin).
+// Element (k, bin, c) of a region / out tensor sits at k * ks + bin * bs + c * cs:
+// channels-last tensors (cs == 1; also channel slices of the concatenated tensor) take
+// the warp-per-bin kernels (lanes over channels, 128-bit accesses, warp-shuffle
+// reduction), NCHW tensors (bs == 1) the thread-per-bin kernels (lanes over bins).
+namespace arfe {
+namespace {
+
+struct FuseAddr { int64_t ks, bs, cs; };
+
+__device__ __forceinline__ void softmax3(float l0, float l1, float l2, float (&w)[3]) {
+  const float m = fmaxf(l0, fmaxf(l1, l2));
+  const float e0 = expf(l0 - m), e1 = expf(l1 - m), e2 = expf(l2 - m);
+  const float s = e0 + e1 + e2;
+  w[0] = e0 / s; w[1] = e1 / s; w[2] = e2 / s;
+}
+template <typename T> __device__ __forceinline__ float ldsc(const T* p) {
+  if constexpr (sizeof(T) == 4) return *p; else return __bfloat162float(*p);
+}
+template <typename T> __device__ __forceinline__ void stsc(T* p, float v) {
+  if constexpr (sizeof(T) == 4) *p = v; else *p = __float2bfloat16_rn(v);
+}
+
+// warp == one (RoI, bin) row; V channels per lane step (channels-last: cs == 1)
+template <typename T, int V, bool kBackward>
+__global__ void __launch_bounds__(kThreads)
+softmax_fuse_cl(const T* __restrict__ r0, const T* __restrict__ r1, const T* __restrict__ r2, FuseAddr ra,
+                const T* __restrict__ logits, int64_t lks, int64_t lrs, int64_t lbs,
+                T* __restrict__ out, const T* __restrict__ dout, FuseAddr oa,
+                T* __restrict__ d0, T* __restrict__ d1, T* __restrict__ d2, T* __restrict__ dlogits,
+                int64_t rows, int PP, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int64_t k = row / PP;
+  const int bin = (int)(row - k * PP);
+  const T* lg = logits + k * lks + (int64_t)bin * lbs;
+  float w[3];
+  softmax3(ldsc(lg), ldsc(lg + lrs), ldsc(lg + 2 * lrs), w);
+  const int64_t ro = k * ra.ks + (int64_t)bin * ra.bs, oo = k * oa.ks + (int64_t)bin * oa.bs;
+  float s[3] = {0.f, 0.f, 0.f};
+  for (int c = lane * V; c < C; c += 32 * V) {
+    float a[V], b[V], d[V];
+    load_vec<T, V>(r0 + ro + c, a);
+    load_vec<T, V>(r1 + ro + c, b);
+    load_vec<T, V>(r2 + ro + c, d);
+    if constexpr (!kBackward) {
+      float o[V];
+#pragma unroll
+      for (int q = 0; q < V; ++q) o[q] = fmaf(d[q], w[2], fmaf(b[q], w[1], a[q] * w[0]));
+      store_vec<T, V>(out + oo + c, o);
+    } else {
+      float g[V], x0[V], x1[V], x2[V];
+      load_vec<T, V>(dout + oo + c, g);
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        s[0] = fmaf(g[q], a[q], s[0]); s[1] = fmaf(g[q], b[q], s[1]); s[2] = fmaf(g[q], d[q], s[2]);
+        x0[q] = g[q] * w[0]; x1[q] = g[q] * w[1]; x2[q] = g[q] * w[2];
+      }
+      store_vec<T, V>(d0 + oo + c, x0);
+      store_vec<T, V>(d1 + oo + c, x1);
+      store_vec<T, V>(d2 + oo + c, x2);
+    }
+  }
+  if constexpr (kBackward) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int dd = 16; dd > 0; dd >>= 1) s[j] += __shfl_xor_sync(0xffffffffu, s[j], dd);
+    if (lane < 3) {
+      const float mean = w[0] * s[0] + w[1] * s[1] + w[2] * s[2];
+      const float sj = lane == 0 ? s[0] : (lane == 1 ? s[1] : s[2]);
+      const float wj = lane == 0 ? w[0] : (lane == 1 ? w[1] : w[2]);
+      stsc(dlogits + k * lks + (int64_t)bin * lbs + lane * lrs, wj * (sj - mean));
+    }
+  }
+}
+
+// thread == one (RoI, bin); loops over the channels (NCHW: consecutive threads, consecutive bins)
+template <typename T, bool kBackward>
+__global__ void __launch_bounds__(kThreads)
+softmax_fuse_any(const T* __restrict__ r0, const T* __restrict__ r1, const T* __restrict__ r2, FuseAddr ra,
+                 const T* __restrict__ logits, int64_t lks, int64_t lrs, int64_t lbs,
+                 T* __restrict__ out, const T* __restrict__ dout, FuseAddr oa,
+                 T* __restrict__ d0, T* __restrict__ d1, T* __restrict__ d2, T* __restrict__ dlogits,
+                 int64_t rows, int PP, int C) {
+  const int64_t row = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (row >= rows) return;
+  const int64_t k = row / PP;
+  const int bin = (int)(row - k * PP);
+  const T* lg = logits + k * lks + (int64_t)bin * lbs;
+  float w[3];
+  softmax3(ldsc(lg), ldsc(lg + lrs), ldsc(lg + 2 * lrs), w);
+  const int64_t ro = k * ra.ks + (int64_t)bin * ra.bs, oo = k * oa.ks + (int64_t)bin * oa.bs;
+  float s[3] = {0.f, 0.f, 0.f};
+  for (int c = 0; c < C; ++c) {
+    const float a = ldsc(r0 + ro + c * ra.cs), b = ldsc(r1 + ro + c * ra.cs), d = ldsc(r2 + ro + c * ra.cs);
+    if constexpr (!kBackward) {
+      stsc(out + oo + c * oa.cs, fmaf(d, w[2], fmaf(b, w[1], a * w[0])));
+    } else {
+      const float g = ldsc(dout + oo + c * oa.cs);
+      s[0] = fmaf(g, a, s[0]); s[1] = fmaf(g, b, s[1]); s[2] = fmaf(g, d, s[2]);
+      stsc(d0 + oo + c * oa.cs, g * w[0]);
+      stsc(d1 + oo + c * oa.cs, g * w[1]);
+      stsc(d2 + oo + c * oa.cs, g * w[2]);
+    }
+  }
+  if constexpr (kBackward) {
+    const float mean = w[0] * s[0] + w[1] * s[1] + w[2] * s[2];
+    T* dl = dlogits + k * lks + (int64_t)bin * lbs;
+    stsc(dl, w[0] * (s[0] - mean));
+    stsc(dl + lrs, w[1] * (s[1] - mean));
+    stsc(dl + 2 * lrs, w[2] * (s[2] - mean));
+  }
+}
+
+template <typename T, bool kBackward>
+cudaError_t launch_softmax_fuse_t(const void* const* reg, const int64_t* rstr, const void* logits,
+                                  const int64_t* lstr, void* out, const void* dout, const int64_t* ostr,
+                                  void* const* dreg, void* dlogits, int64_t K, int PP, int C,
+                                  cudaStream_t stream) {
+  const int64_t rows = K * PP;
+  if (rows == 0) return cudaSuccess;
+  constexpr int V = sizeof(T) == 4 ? 4 : 8;
+  const FuseAddr ra{rstr[0], rstr[1], rstr[2]}, oa{ostr[0], ostr[1], ostr[2]};
+  auto r0 = (const T*)reg[0]; auto r1 = (const T*)reg[1]; auto r2 = (const T*)reg[2];
+  T* d0 = kBackward ? (T*)dreg[0] : nullptr; T* d1 = kBackward ? (T*)dreg[1] : nullptr; T* d2 = kBackward ? (T*)dreg[2] : nullptr;
+  const bool cl = ra.cs == 1 && oa.cs == 1;
+  if (cl) {
+    bool vec = C % V == 0 && ra.ks % V == 0 && ra.bs % V == 0 && oa.ks % V == 0 && oa.bs % V == 0 &&
+               aligned16(r0) && aligned16(r1) && aligned16(r2) && aligned16(kBackward ? dout : out);
+    if (kBackward) vec = vec && aligned16(d0) && aligned16(d1) && aligned16(d2);
+    const unsigned grid = (unsigned)((rows + kThreads / 32 - 1) / (kThreads / 32));
+    if (vec) softmax_fuse_cl<T, V, kBackward><<<grid, kThreads, 0, stream>>>(r0, r1, r2, ra, (const T*)logits, lstr[0], lstr[1], lstr[2], (T*)out, (const T*)dout, oa, d0, d1, d2, (T*)dlogits, rows, PP, C);
+    else softmax_fuse_cl<T, 1, kBackward><<<grid, kThreads, 0, stream>>>(r0, r1, r2, ra, (const T*)logits, lstr[0], lstr[1], lstr[2], (T*)out, (const T*)dout, oa, d0, d1, d2, (T*)dlogits, rows, PP, C);
+  } else {
+    const unsigned grid = (unsigned)((rows + kThreads - 1) / kThreads);
+    softmax_fuse_any<T, kBackward><<<grid, kThreads, 0, stream>>>(r0, r1, r2, ra, (const T*)logits, lstr[0], lstr[1], lstr[2], (T*)out, (const T*)dout, oa, d0, d1, d2, (T*)dlogits, rows, PP, C);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_rff_softmax_fuse(int backward, const void* const* reg, const int64_t* rstr, const void* logits,
+                                    const int64_t* lstr, void* out, const void* dout, const int64_t* ostr,
+                                    void* const* dreg, void* dlogits, int64_t K, int PP, int C, int dtype,
+                                    cudaStream_t stream) {
+  if (dtype == 0)
+    return backward ? launch_softmax_fuse_t<float, true>(reg, rstr, logits, lstr, out, dout, ostr, dreg, dlogits, K, PP, C, stream)
+                    : launch_softmax_fuse_t<float, false>(reg, rstr, logits, lstr, out, dout, ostr, dreg, dlogits, K, PP, C, stream);
+  return backward ? launch_softmax_fuse_t<__nv_bfloat16, true>(reg, rstr, logits, lstr, out, dout, ostr, dreg, dlogits, K, PP, C, stream)
+                  : launch_softmax_fuse_t<__nv_bfloat16, false>(reg, rstr, logits, lstr, out, dout, ostr, dreg, dlogits, K, PP, C, stream);
+}
+
+}  // namespace arfe

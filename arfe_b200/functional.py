@@ -492,6 +492,73 @@ def rff_gate(ori, a, b):
     return _RFFGateFunction.apply(ori, a, b)
 
 
+def _kbc_strides(t):
+    """(k, bin, channel) element strides of a [K, C, H, W] tensor whose bins are evenly spaced
+    (NCHW-dense or channels-last, possibly a channel slice), else None."""
+    K, C, H, W = t.shape
+    s0, s1, s2, s3 = t.stride()
+    bs = s3 if W > 1 else (s2 if H > 1 else 1)
+    if H > 1 and W > 1 and s2 != W * s3:
+        return None
+    return (s0 if K > 1 else C * H * W * max(bs, 1), bs, s1 if C > 1 else 1)
+
+
+class _RFFSoftmaxFuseFunction(Function):
+    """Softmax-over-regions fusion (multirois_bbox_head.py:187-197, the commented variant
+    of the paper's figure): out = sum_j r_j * softmax(logits, 1)[:, j]."""
+
+    @staticmethod
+    def forward(ctx, logits, r0, r1, r2):
+        L.require_cuda(logits, r0, r1, r2)
+        K, C, H, W = r0.shape
+        dt = L.dtype_code(r0)
+        regs = [r0, r1, r2]
+        st = _kbc_strides(r0)
+        if st is None or any(r.dtype != r0.dtype or _kbc_strides(r) != st for r in regs):
+            mf = torch.channels_last if L.layout_of(r0) == L.ARFE_NHWC else torch.contiguous_format
+            regs = [r.to(r0.dtype).contiguous(memory_format=mf) for r in regs]
+            st = _kbc_strides(regs[0])
+        mf = torch.channels_last if st[2] == 1 and C > 1 else torch.contiguous_format
+        logits_c = logits.to(r0.dtype).contiguous()            # [K, 3, H, W]: strides (3 PP, PP, 1)
+        out = torch.empty((K, C, H, W), dtype=r0.dtype, device=r0.device, memory_format=mf)
+        PP = H * W
+        lst = (3 * PP, PP, 1)
+        if K > 0:
+            rc = L.lib().arfe_rff_softmax_fuse_forward(
+                L.ptr_array(regs), L.i64_array(st), logits_c.data_ptr(), L.i64_array(lst), out.data_ptr(),
+                L.i64_array(_kbc_strides(out)), K, PP, C, dt, L.stream_ptr(out.device))
+            L.check(rc, "arfe_rff_softmax_fuse_forward")
+        ctx.save_for_backward(logits_c, *regs)
+        ctx.meta = (st, lst, mf, dt, logits.dtype)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        logits_c, r0, r1, r2 = ctx.saved_tensors
+        st, lst, mf, dt, ldtype = ctx.meta
+        K, C, H, W = r0.shape
+        g = g.to(r0.dtype).contiguous(memory_format=mf)
+        dregs = [torch.empty((K, C, H, W), dtype=r0.dtype, device=g.device, memory_format=mf) for _ in range(3)]
+        dlog = torch.empty_like(logits_c)
+        if K > 0:
+            rc = L.lib().arfe_rff_softmax_fuse_backward(
+                g.data_ptr(), L.ptr_array([r0, r1, r2]), L.i64_array(st), logits_c.data_ptr(), L.i64_array(lst),
+                L.i64_array(_kbc_strides(g)), L.ptr_array(dregs), dlog.data_ptr(), K, H * W, C, dt,
+                L.stream_ptr(g.device))
+            L.check(rc, "arfe_rff_softmax_fuse_backward")
+        return (dlog.to(ldtype),) + tuple(dregs)
+
+
+def rff_softmax_fuse(regions, logits):
+    """regions: the three region tensors (r0, r1, r2), each [K, C, h, w] (e.g. from roi_fuse_split), or
+    the concatenated [K, 3C, h, w] tensor; logits: [K, 3, h, w].  Returns [K, C, h, w]."""
+    if torch.is_tensor(regions):
+        c = regions.shape[1] // 3
+        regions = (regions[:, :c], regions[:, c:2 * c], regions[:, 2 * c:])
+    return _RFFSoftmaxFuseFunction.apply(logits, *regions)
+
+
 class _FPNGatherFunction(Function):
     """wfpn_dual_spatial.py:102-113."""
 

@@ -228,6 +228,37 @@ int arfe_rff_gate_backward(const void* g, const void* ori,
                            int64_t K, int64_t n_per_roi, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------
+ * AR-RFF, softmax-over-regions fusion -- the fusion of the paper's figure; in the
+ * reference it is the commented block
+ * mmdet/models/roi_heads/bbox_heads/multirois_bbox_head.py:187-197:
+ *   ws  = softmax(logits, dim=1)                      logits [K, 3, PH, PW]
+ *   out = r0 * ws[:,0] + r1 * ws[:,1] + r2 * ws[:,2]  r_j, out [K, C, PH, PW]
+ * regions[3]: device pointers; element (k, bin, c) of every region tensor sits
+ * at k*region_strides[0] + bin*region_strides[1] + c*region_strides[2] (elements)
+ * -- one triple for the three, which covers NCHW tensors, channels-last tensors
+ * and the channel slices of the concatenated [K, 3C, PH, PW] tensor alike; out /
+ * dout / d_regions use out_strides the same way; logits / d_logits element
+ * (k, j, bin) sits at k*logit_strides[0] + j*logit_strides[1] + bin*logit_strides[2].
+ * PP = PH*PW.  Channels-last tensors (channel stride 1) take a warp-per-bin
+ * kernel with 128-bit accesses; anything else a thread-per-bin kernel.
+ * backward: d_regions[j] = dout * ws_j (written), d_logits_j = ws_j * (s_j -
+ * sum_i ws_i s_i), s_j = sum_c dout * r_j (written). */
+int arfe_rff_softmax_fuse_forward(const void* const* regions,
+                                  const int64_t* region_strides,
+                                  const void* logits,
+                                  const int64_t* logit_strides, void* out,
+                                  const int64_t* out_strides, int64_t K, int PP,
+                                  int C, int dtype, void* stream);
+int arfe_rff_softmax_fuse_backward(const void* dout, const void* const* regions,
+                                   const int64_t* region_strides,
+                                   const void* logits,
+                                   const int64_t* logit_strides,
+                                   const int64_t* out_strides,
+                                   void* const* d_regions, void* d_logits,
+                                   int64_t K, int PP, int C, int dtype,
+                                   void* stream);
+
+/* ------------------------------------------------------------------------
  * AR-FPN gather: every level resized to the refine level and averaged.
  *   WFPNDualSpatial.forward, mmdet/models/necks/wfpn_dual_spatial.py:102-113
  *   levels < refine_level: F.adaptive_max_pool2d; others: nearest interpolate;
@@ -283,6 +314,31 @@ int arfe_fpn_apply_backward(const void* const* douts, const void* bsf,
                             int C, int Hr, int Wr, int dtype, int layout,
                             float* dbsf, float* const* dg1, float* const* dg2,
                             void* stream);
+
+/* ------------------------------------------------------------------------
+ * Proposal side: the two steps immediately before the extractor.
+ *
+ * arfe_nms -- greedy NMS, twin of nms_ext.nms
+ * (mmdet/ops/nms/src/cuda/nms_kernel.cu:24-131, cpu/nms_cpu.cpp:8-69):
+ * dets_sorted: device [n, 5] fp32 rows (x1, y1, x2, y2, score) ALREADY sorted by
+ * score, descending (the reference sorts with ATen first, :79-81).  keep:
+ * device int64 [n], receives the kept positions (indices into dets_sorted) in
+ * order; num_keep: device int32.  Suppression rule: IoU > iou_threshold with
+ * areas (x2-x1)*(y2-y1), every product and sum rounded separately as on the
+ * reference's CPU path.  The bitmask is swept on the device: nothing but the
+ * caller's read of num_keep crosses PCIe (the reference copies the n x n/64
+ * mask to the host and sweeps it there).  workspace: arfe_nms_workspace_bytes(n)
+ * bytes, 8-byte aligned.
+ *
+ * arfe_bbox2roi -- mmdet/core/bbox/transforms.py:41-60: rois row r of image i's
+ * block = (i, x1, y1, x2, y2) of boxes[i] row r; blocks in image order.  boxes:
+ * HOST array of B device pointers, counts[i] rows of cols[i] >= 4 floats each. */
+size_t arfe_nms_workspace_bytes(int n);
+int arfe_nms(const float* dets_sorted, int n, float iou_threshold,
+             void* workspace, size_t workspace_bytes, int64_t* keep,
+             int32_t* num_keep, void* stream);
+int arfe_bbox2roi(const float* const* boxes, const int32_t* counts,
+                  const int32_t* cols, int B, float* rois, void* stream);
 
 /* The whole AR-FPN backward in one pass over the incoming gradient pyramid
  * (channels-last only): what arfe_fpn_apply_backward followed by

@@ -79,6 +79,70 @@ def ref_ext():
     return _ref_ext
 
 
+_ref_nms = None
+
+
+def ref_nms_ext():
+    """The reference's nms_ext (CPU build) compiled unmodified, or None."""
+    global _ref_nms
+    if _ref_nms is None:
+        from . import build_oracle
+        path = build_oracle.ref_nms_ext_path()
+        if path is None:
+            return None
+        spec = importlib.util.spec_from_file_location("nms_ext", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _ref_nms = mod
+    return _ref_nms
+
+
+def nms(dets, iou_thr, backend="py"):
+    """ops/nms/src/cpu/nms_cpu.cpp:8-69 (greedy NMS in descending-score order, IoU with
+    areas (x2-x1)*(y2-y1), suppressed when ovr > threshold): kept indices into dets, in
+    score order.  backend "ref" runs the reference's own compiled code; "py" restates it
+    with numpy float32 scalars (each product / sum rounded separately, as the C++ does)."""
+    dets = dets.detach().float().cpu().contiguous()
+    if backend == "ref":
+        return ref_nms_ext().nms(dets, float(iou_thr))
+    d = dets.numpy().astype(np.float32)
+    if d.shape[0] == 0:
+        return torch.zeros(0, dtype=torch.long)
+    x1, y1, x2, y2, sc = (d[:, i] for i in range(5))
+    areas = (x2 - x1) * (y2 - y1)
+    order = torch.from_numpy(sc).sort(0, descending=True)[1].numpy()
+    suppressed = np.zeros(d.shape[0], dtype=bool)
+    keep = []
+    thr = np.float32(iou_thr)
+    for _i in range(d.shape[0]):
+        i = order[_i]
+        if suppressed[i]:
+            continue
+        keep.append(int(i))
+        rest = order[_i + 1:]
+        xx1, yy1 = np.maximum(x1[i], x1[rest]), np.maximum(y1[i], y1[rest])
+        xx2, yy2 = np.minimum(x2[i], x2[rest]), np.minimum(y2[i], y2[rest])
+        w, h = np.maximum(np.float32(0), xx2 - xx1), np.maximum(np.float32(0), yy2 - yy1)
+        inter = w * h
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ovr = inter / (areas[i] + areas[rest] - inter)
+        suppressed[rest[ovr > thr]] = True
+    return torch.tensor(keep, dtype=torch.long)
+
+
+def bbox2roi(bbox_list):
+    """core/bbox/transforms.py:41-60."""
+    rois_list = []
+    for img_id, bboxes in enumerate(bbox_list):
+        if bboxes.size(0) > 0:
+            img_inds = bboxes.new_full((bboxes.size(0), 1), img_id)
+            rois = torch.cat([img_inds, bboxes[:, :4]], dim=-1)
+        else:
+            rois = bboxes.new_zeros((0, 5))
+        rois_list.append(rois)
+    return torch.cat(rois_list, 0)
+
+
 def _fptr(t):
     return ctypes.cast(t.data_ptr(), ctypes.POINTER(ctypes.c_float))
 
@@ -260,6 +324,17 @@ def rff_gate(ori, a, b):
     """bbox_heads/multirois_bbox_head.py:175,182: ori + ori*(a+b), where a, b
     are already relu(conv(.)) (:172-173)."""
     return ori + ori * (a + b)
+
+
+def rff_softmax_fuse(regions, logits):
+    """bbox_heads/multirois_bbox_head.py:187-197 (commented in the shipped tree; the
+    fusion drawn in the paper's figure): ws = softmax(logits, dim=1);
+    out = r0 * ws[:, 0:1] + r1 * ws[:, 1:2] + r2 * ws[:, 2:3]."""
+    ws = F.softmax(logits, dim=1)
+    r0, r1, r2 = regions
+    k, _, h, w = ws.shape
+    return r0 * ws[:, 0, :, :].view(-1, 1, h, w) + r1 * ws[:, 1, :, :].view(-1, 1, h, w) + \
+        r2 * ws[:, 2, :, :].view(-1, 1, h, w)
 
 
 class ConvModule(nn.Module):

@@ -95,11 +95,37 @@ def build_reference_cuda_ext(force=False):
     return ref_cuda_ext_path()
 
 
+REF_NMS_SRCS = ["mmdet/ops/nms/src/nms_ext.cpp", "mmdet/ops/nms/src/cpu/nms_cpu.cpp"]
+REF_NMS_DIR = os.path.join(REF_DIR, "nms")
+
+
+def ref_nms_ext_path():
+    hits = sorted(glob.glob(os.path.join(REF_NMS_DIR, "nms_ext*.so")))
+    return hits[0] if hits else None
+
+
+def build_reference_nms_ext(force=False):
+    """The reference's own NMS (nms_ext.cpp + cpu/nms_cpu.cpp, CPU-only: WITH_CUDA is not
+    defined), compiled unmodified and in place: the checker of arfe_nms."""
+    srcs = [os.path.join(REF_ROOT, s) for s in REF_NMS_SRCS]
+    if not all(os.path.exists(s) for s in srcs):
+        return ref_nms_ext_path()
+    have = ref_nms_ext_path()
+    if have and not force and _newer(have, srcs):
+        return have
+    os.makedirs(REF_NMS_DIR, exist_ok=True)
+    from torch.utils.cpp_extension import load
+    load(name="nms_ext", sources=srcs, build_directory=REF_NMS_DIR, extra_cflags=["-O2"], verbose=False,
+         is_python_module=True)
+    return ref_nms_ext_path()
+
+
 def main():
     force = "--force" in sys.argv
     print("C oracle      :", build_c_oracle(force))
     print("reference ext :", build_reference_ext(force) or
           "unavailable (no /root/reference and no prebuilt oracle/_ref)")
+    print("reference NMS :", build_reference_nms_ext(force) or "unavailable")
     if "--cuda" in sys.argv:
         print("reference CUDA:", build_reference_cuda_ext(force) or "unavailable")
 

@@ -95,6 +95,18 @@ def main():
         **{f"g1_{l}": g1[l].numpy() for l in range(5)},
         **{f"g2_{l}": g2[l].numpy() for l in range(5)},
         **{f"out{l}": outs[l].numpy() for l in range(5)})
+    # 5. NMS through the reference's own nms_ext (CPU build, compiled unmodified)
+    assert build_oracle.build_reference_nms_ext() is not None, "needs /root/reference"
+    gen = torch.Generator().manual_seed(26)
+    n = 600
+    ctr = torch.rand(n, 2, generator=gen) * 300
+    wh = torch.rand(n, 2, generator=gen) * 80 + 2
+    dets = torch.cat([ctr - wh / 2, ctr + wh / 2, torch.rand(n, 1, generator=gen)], 1).contiguous()
+    res = {"dets": dets.numpy()}
+    for thr in (0.3, 0.5, 0.7):
+        res[f"keep_{int(thr * 10)}"] = O.nms(dets, thr, "ref").numpy()
+    np.savez_compressed(os.path.join(HERE, "nms_small.npz"), **res)
+
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

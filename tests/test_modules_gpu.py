@@ -213,3 +213,83 @@ def test_use_torchvision_is_refused():
     import arfe_b200 as A
     with pytest.raises(NotImplementedError):
         A.RoIAlign(7, 0.25, use_torchvision=True, aligned=False)
+
+
+@pytest.mark.parametrize("layout", ["nchw_cat", "cl_cat", "cl_split"])
+@pytest.mark.parametrize("K,C", [(0, 8), (1, 16), (37, 20), (64, 256)])
+def test_rff_softmax_fusion_variant(oracle, cuda, layout, K, C):
+    """the softmax-over-regions fusion (multirois_bbox_head.py:187-197,
+    commented in the shipped tree) -- forward and all four gradients against the oracle's
+    restatement, for the concatenated NCHW / channels-last tensor and for split region tensors."""
+    import arfe_b200 as A
+    gen = torch.Generator().manual_seed(K * 7 + C)
+    x = torch.randn(K, 3 * C, 7, 7, generator=gen)
+    logits = torch.randn(K, 3, 7, 7, generator=gen) * 2
+    g = torch.randn(K, C, 7, 7, generator=gen)
+    xo, lo = x.clone().requires_grad_(True), logits.clone().requires_grad_(True)
+    ref = oracle.rff_softmax_fuse((xo[:, :C], xo[:, C:2 * C], xo[:, 2 * C:]), lo)
+    if layout == "cl_split":
+        parts = [_cl(x[:, j * C:(j + 1) * C].contiguous().to(cuda)).requires_grad_(True) for j in range(3)]
+        regions = tuple(parts)
+    else:
+        xg = (_cl(x.to(cuda)) if layout == "cl_cat" else x.to(cuda)).requires_grad_(True)
+        regions = xg
+    lg = logits.to(cuda).requires_grad_(True)
+    got = A.rff_softmax_fuse(regions, lg)
+    assert_close_fp32(got, ref, f"softmax fusion fwd {layout}")
+    if K == 0:
+        return
+    ref.backward(g)
+    got.backward(g.to(cuda))
+    dx = torch.cat([p.grad for p in parts], 1) if layout == "cl_split" else xg.grad
+    assert_close_fp32(dx, xo.grad, "softmax fusion d regions")
+    err = (lg.grad.cpu() - lo.grad).abs().max()
+    assert float(err) <= 1e-5 * float(lo.grad.abs().max()) + 1e-5, float(err)   # a 3*C-term sum per bin
+    # bf16 I/O
+    gb = A.rff_softmax_fuse(x.bfloat16().to(cuda), logits.bfloat16().to(cuda))
+    xb = x.bfloat16().float()
+    refb = oracle.rff_softmax_fuse((xb[:, :C], xb[:, C:2 * C], xb[:, 2 * C:]), logits.bfloat16().float())
+    err = (gb.float().cpu() - refb).abs()
+    assert bool((err <= 1e-2 * refb.abs() + 1e-2 * float(refb.abs().mean())).all())
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 700, 5000])
+def test_nms_matches_reference(oracle, cuda, n):
+    """arfe_nms (device-side sweep) keeps exactly the boxes the reference's
+    NMS keeps (its own nms_ext when oracle/_ref/nms travelled, else the pinned restatement),
+    clustered boxes, several thresholds."""
+    import arfe_b200 as A
+    gen = torch.Generator().manual_seed(n)
+    ncl = max(n // 12, 1)
+    centres = torch.rand(ncl, 2, generator=gen) * torch.tensor([1300.0, 780.0])
+    ctr = centres[torch.randint(0, ncl, (n,), generator=gen)] + torch.randn(n, 2, generator=gen) * 12
+    wh = torch.exp(torch.randn(n, 2, generator=gen) * 0.4) * 60
+    dets = torch.cat([ctr - wh / 2, ctr + wh / 2, torch.rand(n, 1, generator=gen)], 1).contiguous()
+    backend = "ref" if oracle.ref_nms_ext() is not None else "py"
+    for thr in (0.3, 0.5, 0.7):
+        want = oracle.nms(dets, thr, backend)
+        got_dets, got = A.nms(dets.to(cuda), thr)
+        assert torch.equal(got.cpu(), want), (n, thr, len(want), len(got))
+        assert torch.equal(got_dets.cpu(), dets[want])
+
+
+def test_batched_nms_and_bbox2roi(oracle, cuda):
+    import arfe_b200 as A
+    gen = torch.Generator().manual_seed(5)
+    n = 900
+    ctr = torch.rand(n, 2, generator=gen) * 400
+    wh = torch.rand(n, 2, generator=gen) * 90 + 4
+    boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+    scores = torch.rand(n, generator=gen)
+    lvl = torch.randint(0, 5, (n,), generator=gen)
+    dets, keep = A.batched_nms(boxes.to(cuda), scores.to(cuda), lvl.to(cuda), dict(type='nms', iou_thr=0.7))
+    # reference composition (nms_wrapper.py:143-157) on the oracle
+    off = lvl.float() * (boxes.max() + 1)
+    want = oracle.nms(torch.cat([boxes + off[:, None], scores[:, None]], 1), 0.7, "py")
+    assert torch.equal(keep.cpu(), want)
+    assert torch.equal(dets.cpu(), torch.cat([boxes[want], scores[want, None]], 1))
+    # proposals -> RoIs, image-major
+    lists = [dets[:300, :5], dets[:0], dets[300:450, :4].contiguous(), dets[450:]]
+    rois = A.bbox2roi(lists)
+    assert torch.equal(rois.cpu(), oracle.bbox2roi([t.cpu() for t in lists]))
+    assert A.bbox2roi([dets[:0], dets[:0]]).shape == (0, 5)

@@ -135,3 +135,24 @@ def test_level_thresholds_golden(oracle):
     scale = np.sqrt((w * h).astype(np.float32)).astype(np.float32)
     v = (scale / np.float32(56.0)).astype(np.float32) + np.float32(1e-6)
     assert np.array_equal(_device_level(v.astype(np.float32), 5), d["lvls"])
+
+
+def test_oracle_nms_matches_reference_and_golden(oracle):
+    """The numpy restatement of nms_cpu.cpp == the reference's own nms_ext compiled unmodified
+    (when oracle/_ref/nms travelled) == the committed fixture minted from it."""
+    d = np.load(os.path.join(GOLD, "nms_small.npz"))
+    dets = torch.from_numpy(d["dets"])
+    for thr in (0.3, 0.5, 0.7):
+        keep = oracle.nms(dets, thr, "py")
+        assert np.array_equal(keep.numpy(), d[f"keep_{int(thr * 10)}"]), thr
+    if oracle.ref_nms_ext() is not None:
+        gen = torch.Generator().manual_seed(3)
+        for n in (1, 2, 65, 257):
+            ctr = torch.rand(n, 2, generator=gen) * 100
+            wh = torch.rand(n, 2, generator=gen) * 50 + 1
+            x = torch.cat([ctr - wh / 2, ctr + wh / 2, torch.rand(n, 1, generator=gen)], 1)
+            for thr in (0.1, 0.5, 0.9):
+                assert torch.equal(oracle.nms(x, thr, "py"), oracle.nms(x, thr, "ref")), (n, thr)
+    lists = [torch.rand(3, 5), torch.zeros(0, 5), torch.rand(2, 4)]
+    r = oracle.bbox2roi(lists)
+    assert r.shape == (5, 5) and r[:, 0].tolist() == [0, 0, 0, 2, 2]
