@@ -7,7 +7,7 @@
 
 Plain nvcc, no torch headers: the library's ABI is include/arfe_b200.h.  Every
 translation unit is compiled to an object in parallel, then linked.
-Run:  python -m arfe_b200.build [--force] [--verbose] [--profile]
+Run:  python -m arfe_b200.build [--force] [--verbose] [--release | --profile]   (default: both)
 """
 import glob
 import os
@@ -75,5 +75,12 @@ def build(force=False, verbose=False, profile=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv,
-                profile="--profile" in sys.argv))
+    # both libraries by default (the profile build must never be staler than the product:
+    # tests compare the two); --release / --profile build one
+    kinds = [False, True]
+    if "--release" in sys.argv:
+        kinds = [False]
+    if "--profile" in sys.argv:
+        kinds = [True]
+    for prof in kinds:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, profile=prof))
