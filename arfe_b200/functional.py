@@ -73,16 +73,24 @@ class _Plan:
         main = torch.cuda.current_stream(device)
         L.check(lib.arfe_roi_plan_build(*geo_args, self.ptr, self.nbytes, c_stream(main)),
                 "arfe_roi_plan_build")
-        if need_bins and not torch.cuda.is_current_stream_capturing():
-            side = _side_stream(device)
-            ev_plan = torch.cuda.Event()
-            ev_plan.record(main)
-            side.wait_event(ev_plan)
-            self.ws.record_stream(side)
-            L.check(lib.arfe_roi_pull_bin(*geo_args, int(split), self.ptr, self.nbytes, c_stream(side)),
-                    "arfe_roi_pull_bin")
-            self.ev_bin = torch.cuda.Event()
-            self.ev_bin.record(side)
+        self._bins = (geo_args, int(split)) if need_bins else None
+
+    def fork_bins(self, device):
+        """Called right after the forward's launch: the tile bins are built on the side stream
+        next to whatever follows the extraction (the head's convolutions), not next to the ring
+        forward, which a second latency-bound kernel slows down."""
+        if self._bins is None or torch.cuda.is_current_stream_capturing():
+            return
+        geo_args, split = self._bins
+        main, side = torch.cuda.current_stream(device), _side_stream(device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        self.ws.record_stream(side)
+        L.check(L.lib().arfe_roi_pull_bin(*geo_args, split, self.ptr, self.nbytes, c_stream(side)),
+                "arfe_roi_pull_bin")
+        self.ev_bin = torch.cuda.Event()
+        self.ev_bin.record(side)
 
     def ready_for_backward(self, device):
         """plan_ready code for the backward: 2 = plan and bins are there (after joining the
@@ -141,6 +149,7 @@ class _RoIFuseFunction(Function):
                 out.data_ptr(), None, None, plan.ptr, plan.nbytes, 1, L.stream_ptr(out.device))
             L.check(rc, "arfe_roi_fuse_forward_plan")
             if need_bwd:
+                plan.fork_bins(out.device)
                 ctx.plan = plan
         elif K > 0:
             rc = L.lib().arfe_roi_fuse_forward(
@@ -252,6 +261,7 @@ class _RoIFuseSplitFunction(Function):
                 plan.ptr, plan.nbytes, 1, L.stream_ptr(dev))
             L.check(rc, "arfe_roi_fuse_forward_plan_split")
             if need_bwd:
+                plan.fork_bins(dev)
                 ctx.plan = plan
         return tuple(outs)
 

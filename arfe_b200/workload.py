@@ -220,27 +220,41 @@ class TrainStep:
             self.p_x, self.bsf.data_ptr(), self.p_g1, self.p_g2, self.H, self.W, self.nlev,
             self.B, self.C, hr, wr, self.dt, self.layout, self.p_y, self.stream)
 
-    def plan_async(self, bins=True):
-        """The RoI plan depends only on the RoIs, the backward's tile bins only on
-        the plan: build both on a second stream, under the AR-FPN kernels of the
-        forward (latency-bound table walking next to bandwidth-bound streaming)."""
+    def _geo(self):
+        return (self.H, self.W, self.scales, self.rlev, self.B, self.C, self.rois.data_ptr(), self.K,
+                self.R, 1.0, self.P, self.P, 0, 56.0, self.dt)
+
+    def _side(self):
         if getattr(self, "side", None) is None:
             self.side = torch.cuda.Stream(self.dev)
             self.ev_fork, self.ev_plan, self.ev_bin = (torch.cuda.Event() for _ in range(3))
+        return self.side
+
+    def plan_async(self, bins=True):
+        """The RoI plan depends only on the RoIs: build it on a second stream, under the AR-FPN
+        forward kernels (latency-bound table walking next to bandwidth-bound streaming).
+        bins: the backward's tile bins follow -- bins_async(), issued after the forward."""
+        side = self._side()
         # fork: everything before this step (the previous step's backward still reads the
-        # workspace) precedes the rebuild; the joins are the waits on ev_plan / ev_bin
+        # workspace) precedes the rebuild; the join is the wait on ev_plan
         self.ev_fork.record(torch.cuda.current_stream(self.dev))
-        self.side.wait_event(self.ev_fork)
-        geo = (self.H, self.W, self.scales, self.rlev, self.B, self.C, self.rois.data_ptr(), self.K,
-               self.R, 1.0, self.P, self.P, 0, 56.0, self.dt)
-        tail = (self.ws_ptr, self.ws_bytes, self.side.cuda_stream)
-        L.check(self.lib.arfe_roi_plan_build(*geo, *tail), "arfe_roi_plan_build")
-        self.ev_plan.record(self.side)
-        self.async_plan, self.async_bins = 1, 0
-        if bins:
-            L.check(self.lib.arfe_roi_pull_bin(*geo, int(self.split), *tail), "arfe_roi_pull_bin")
-            self.ev_bin.record(self.side)
-            self.async_bins = 1
+        side.wait_event(self.ev_fork)
+        L.check(self.lib.arfe_roi_plan_build(*self._geo(), self.ws_ptr, self.ws_bytes, side.cuda_stream),
+                "arfe_roi_plan_build")
+        self.ev_plan.record(side)
+        self.async_plan, self.async_bins, self.want_bins_now = 1, 0, bool(bins)
+
+    def bins_async(self):
+        """The pull backward's tile bins depend only on the plan.  They are forked AFTER the
+        forward's launch: next to the ring forward (another latency-bound kernel) the binning
+        kernel cost it ~20 us; next to the streaming gate kernels that follow it is free."""
+        side = self._side()
+        self.ev_fork.record(torch.cuda.current_stream(self.dev))
+        side.wait_event(self.ev_fork)
+        L.check(self.lib.arfe_roi_pull_bin(*self._geo(), int(self.split), self.ws_ptr, self.ws_bytes,
+                                           side.cuda_stream), "arfe_roi_pull_bin")
+        self.ev_bin.record(side)
+        self.async_bins, self.want_bins_now = 1, False
 
     def roi_fuse_fwd(self):
         ready = 0
@@ -353,6 +367,8 @@ class TrainStep:
             if glue:
                 getattr(self, glue)()
             run(n, getattr(self, n))
+            if n == "roi_fuse_fwd" and getattr(self, "want_bins_now", False):
+                self.bins_async()
 
     def step(self, timer=None):
         """One training step. `timer(name, fn)` wraps each of our launches; without a

@@ -41,6 +41,7 @@ def bwd(ready):
     st.planned = 1
     if ready:
         st.plan_async(bins=True)
+        st.bins_async()
         st.async_plan = 0
     L.check(st.roi_fuse_bwd(), "bwd")
 
@@ -65,6 +66,7 @@ def timeit(fn, ready, n=30):
                 fn_b.record()
             else:
                 st.plan_async(bins=True)
+                st.bins_async()
                 torch.cuda.current_stream().wait_event(st.ev_bin)
                 st.async_plan = st.async_bins = 0
                 fn_a.record()
