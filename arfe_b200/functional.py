@@ -569,11 +569,24 @@ def rff_softmax_fuse(regions, logits):
     return _RFFSoftmaxFuseFunction.apply(logits, *regions)
 
 
+class FPNLink:
+    """Couples the gather and the gated residual of ONE neck forward (WFPNDualSpatial.forward):
+    x_l feeds both, so autograd would add their two gradients with one more pass over the
+    pyramid.  With a link the residual's backward hands its d out_l (= its d x_l) to the
+    gather's backward, which runs later (bsf = refine(gather(x)) sits between them) and
+    writes d x_l = d out_l + routed gradient once (arfe_fpn_gather_backward_acc).  Only for
+    a composition in which the residual's bsf is computed from the gather's output."""
+
+    def __init__(self):
+        self.gather_pending = False
+        self.douts = None
+
+
 class _FPNGatherFunction(Function):
     """wfpn_dual_spatial.py:102-113."""
 
     @staticmethod
-    def forward(ctx, refine_level, *feats):
+    def forward(ctx, refine_level, link, *feats):
         feats, layout, dt = _prep_feats(feats)
         B, C = feats[0].shape[:2]
         Hs = [f.shape[2] for f in feats]
@@ -595,6 +608,9 @@ class _FPNGatherFunction(Function):
                 L.stream_ptr(out.device))
             L.check(rc, "arfe_fpn_gather_forward")
         ctx.meta = (refine_level, layout, dt, B, C, Hs, Ws, feats[0].dtype)
+        ctx.link = link
+        if link is not None:
+            link.gather_pending = need_grad and feats[0].dtype == torch.float32 and B > 0
         if argmax is not None:
             ctx.save_for_backward(argmax)
         return out
@@ -608,24 +624,30 @@ class _FPNGatherFunction(Function):
         g = L.as_layout(g.to(fdtype), layout)
         dfeats = [torch.empty((B, C, Hs[l], Ws[l]), dtype=fdtype, device=g.device,
                               memory_format=mf) for l in range(len(Hs))]
+        link, addend = ctx.link, None
+        if link is not None:
+            link.gather_pending = False
+            if link.douts is not None:  # the residual's d out_l: folded into the one write of d x_l
+                addend, link.douts = L.ptr_array(link.douts), None
         if B > 0:
-            rc = L.lib().arfe_fpn_gather_backward(
+            rc = L.lib().arfe_fpn_gather_backward_acc(
                 g.data_ptr(), argmax.data_ptr() if argmax is not None else None,
                 L.int_array(Hs), L.int_array(Ws), len(Hs), B, C, refine_level, dt,
-                layout, L.ptr_array(dfeats), L.stream_ptr(g.device))
+                layout, addend, L.ptr_array(dfeats), L.stream_ptr(g.device))
             L.check(rc, "arfe_fpn_gather_backward")
-        return (None,) + tuple(dfeats)
+        return (None, None) + tuple(dfeats)
 
 
-def fpn_gather(feats, refine_level=2):
-    return _FPNGatherFunction.apply(refine_level, *feats)
+def fpn_gather(feats, refine_level=2, link=None):
+    return _FPNGatherFunction.apply(refine_level, link, *feats)
 
 
 class _FPNApplyFunction(Function):
     """wfpn_dual_spatial.py:118-135; args: bsf, then L feats, L g1, L g2."""
 
     @staticmethod
-    def forward(ctx, nlev, bsf, *tensors):
+    def forward(ctx, nlev, link, bsf, *tensors):
+        ctx.link = link
         feats, g1, g2 = tensors[:nlev], tensors[nlev:2 * nlev], tensors[2 * nlev:]
         feats, layout, dt = _prep_feats(feats)
         L.require_cuda(bsf, *g1, *g2)
@@ -675,10 +697,16 @@ class _FPNApplyFunction(Function):
             L.check(rc, "arfe_fpn_apply_backward")
         cast = (lambda t: t) if fdtype == torch.float32 else (lambda t: t.to(fdtype))
         # d x_l = d out_l: the residual path is the identity, no copy is made
-        return (None, cast(dbsf)) + tuple(d) + tuple(cast(t) for t in dg1) + \
+        dx = tuple(d)
+        link = ctx.link
+        if link is not None and link.gather_pending and fdtype == torch.float32 and \
+                all(ctx.needs_input_grad[3:3 + nlev]):
+            # the gather's backward (still to run: bsf came from it) adds them in its own write
+            link.douts, dx = list(d), (None,) * nlev
+        return (None, None, cast(dbsf)) + dx + tuple(cast(t) for t in dg1) + \
             tuple(cast(t) for t in dg2)
 
 
-def fpn_apply(feats, bsf, g1, g2):
+def fpn_apply(feats, bsf, g1, g2, link=None):
     n = len(feats)
-    return _FPNApplyFunction.apply(n, bsf, *feats, *g1, *g2)
+    return _FPNApplyFunction.apply(n, link, bsf, *feats, *g1, *g2)

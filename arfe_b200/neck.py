@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from ._compat import ConvModule, xavier_init
-from .functional import fpn_apply, fpn_gather
+from .functional import FPNLink, fpn_apply, fpn_gather
 
 
 class NonLocal2D(nn.Module):
@@ -85,10 +85,12 @@ class WFPNDualSpatial(nn.Module):
 
     def forward(self, inputs):
         assert len(inputs) == self.num_levels
-        ori_fe = fpn_gather(inputs, self.refine_level)
+        # bsf is computed from the gather's output, so the two ops can share one write of d x_l
+        link = FPNLink() if torch.is_grad_enabled() else None
+        ori_fe = fpn_gather(inputs, self.refine_level, link)
         bsf = self.refine(ori_fe)
         # pre-activation gate maps; relu (ConvModule's default act) + tanh + sum
         # are fused into the apply kernel
         g1 = [self.reduce_convs[i](inputs[i], activate=False) for i in range(self.num_levels)]
         g2 = [self.reduce_convs2[i](inputs[i], activate=False) for i in range(self.num_levels)]
-        return tuple(fpn_apply(list(inputs), bsf, g1, g2))
+        return tuple(fpn_apply(list(inputs), bsf, g1, g2, link))

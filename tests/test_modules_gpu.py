@@ -293,3 +293,37 @@ def test_batched_nms_and_bbox2roi(oracle, cuda):
     rois = A.bbox2roi(lists)
     assert torch.equal(rois.cpu(), oracle.bbox2roi([t.cpu() for t in lists]))
     assert A.bbox2roi([dets[:0], dets[:0]]).shape == (0, 5)
+
+
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_neck_module_backward_with_linked_gradients(oracle, cuda, nhwc):
+    """WFPNDualSpatial forward + backward through the module (gather and gated residual coupled
+    by an FPNLink: d x_l = d out_l + gather gradient written once) against the oracle module with
+    the same weights: input gradients and every parameter gradient."""
+    import arfe_b200 as A
+    torch.manual_seed(0)
+    shapes = [(48, 80), (24, 40), (12, 20), (6, 10), (3, 5)]
+    ref_m = oracle.WFPNDualSpatial(16, 5)
+    ref_m.init_weights()
+    torch.nn.init.normal_(ref_m.refine.conv_out.conv.weight, 0, 0.05)
+    m = A.WFPNDualSpatial(16, 5)
+    m.load_state_dict(ref_m.state_dict())
+    m = m.to(cuda)
+    if nhwc:
+        m = m.to(memory_format=torch.channels_last)
+    xs = oracle.synthetic_pyramid(2, 16, shapes, seed=4)
+    gs = [torch.randn(x.shape, generator=torch.Generator().manual_seed(30 + i)) for i, x in enumerate(xs)]
+    xo = [x.clone().requires_grad_(True) for x in xs]
+    torch.autograd.backward(list(ref_m(xo)), gs)
+    xg = [(_cl(x.to(cuda)) if nhwc else x.to(cuda)).requires_grad_(True) for x in xs]
+    out = m(xg)
+    torch.autograd.backward(list(out), [g.to(cuda) for g in gs])
+    for l in range(5):
+        err = (xg[l].grad.cpu() - xo[l].grad).abs().max()
+        assert float(err) <= 1e-3 * float(xo[l].grad.abs().max()) + 1e-6, (l, float(err))
+    ref_p = dict(ref_m.named_parameters())
+    for name, prm in m.named_parameters():
+        r = ref_p[name].grad
+        assert prm.grad is not None, name
+        err = (prm.grad.cpu() - r).abs().max()
+        assert float(err) <= 2e-3 * float(r.abs().max()) + 1e-6, (name, float(err))
