@@ -65,23 +65,6 @@ __device__ __forceinline__ void st_vec(T* __restrict__ p, const float (&f)[VecOf
   }
 }
 
-// Streaming (evict-first) stores for tensors that are written once and not read by the
-// kernel: the RoI tensor of the forward (154 MB) and the gradient pyramid of the backward
-// (183 MB) would otherwise push the data the kernel re-reads from L2 -- the pyramid windows,
-// the dout bins -- out of the 126 MB L2.
-template <typename T>
-__device__ __forceinline__ void st_vec_cs(T* __restrict__ p, const float (&f)[VecOf<T>::n]) {
-  if constexpr (sizeof(T) == 4) {
-    __stcs(reinterpret_cast<float4*>(p), make_float4(f[0], f[1], f[2], f[3]));
-  } else {
-    uint4 v;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-    __stcs(reinterpret_cast<uint4*>(p), v);
-  }
-}
-
 // Packed fp32 pairs (FFMA2 / FMUL2: two IEEE fp32 operations per instruction).
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
   uint64_t r;
@@ -761,7 +744,7 @@ __device__ __forceinline__ void fwd_consume_rows(const FwdPipe& pp, int stage0, 
           float f[V];
 #pragma unroll
           for (int u = 0; u < V2; ++u) unpack2(lo[ch][u], f[2 * u], f[2 * u + 1]);
-          st_vec_cs<T>(o + (size_t)cur * ostep + ch * (32 * V), f);
+          st_vec<T>(o + (size_t)cur * ostep + ch * (32 * V), f);
         }
       }
 #pragma unroll
@@ -865,7 +848,7 @@ __device__ __forceinline__ void fwd_consume_rows(const FwdPipe& pp, int stage0, 
         float f[V];
 #pragma unroll
         for (int u = 0; u < V2; ++u) unpack2(acc[ch][ph][u], f[2 * u], f[2 * u + 1]);
-        st_vec_cs<T>(o + (size_t)ph * ostep + ch * (32 * V), f);
+        st_vec<T>(o + (size_t)ph * ostep + ch * (32 * V), f);
       }
   }
 }
@@ -1501,7 +1484,7 @@ __device__ __forceinline__ void pull_consume_tile(const RoiFuseParams& p, const 
       for (int v = 0; v < NV; ++v)
 #pragma unroll
         for (int u = 0; u < V2; u += 2)
-          __stcs(reinterpret_cast<ulonglong2*>(o + v * 32 * V + 2 * u), make_ulonglong2(acc[x][v][u], acc[x][v][u + 1]));
+          *reinterpret_cast<ulonglong2*>(o + v * 32 * V + 2 * u) = make_ulonglong2(acc[x][v][u], acc[x][v][u + 1]);
     }
   }
 }

@@ -326,4 +326,6 @@ def test_neck_module_backward_with_linked_gradients(oracle, cuda, nhwc):
         r = ref_p[name].grad
         assert prm.grad is not None, name
         err = (prm.grad.cpu() - r).abs().max()
-        assert float(err) <= 2e-3 * float(r.abs().max()) + 1e-6, (name, float(err))
+        # (refine.phi's bias shifts every logit of a softmax row alike: its gradient is exactly 0
+        # in exact arithmetic, ~1e-6 of rounding noise on both sides -- hence the absolute floor)
+        assert float(err) <= 2e-3 * float(r.abs().max()) + 1e-5, (name, float(err))
