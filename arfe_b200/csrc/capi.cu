@@ -503,6 +503,36 @@ int arfe_bbox2roi(const float* const* boxes, const int32_t* counts, const int32_
   return cuda_result(arfe::launch_bbox2roi(boxes, counts, cols, B, rois, (cudaStream_t)stream), fn);
 }
 
+size_t arfe_fpn_gate_conv_workspace_bytes(int L, int B, const int32_t* H, const int32_t* W) {
+  if (L < 1 || L > ARFE_MAX_LEVELS || B < 0 || !H || !W) return 0;
+  return arfe::fpn_gate_conv_workspace_bytes(L, B, H, W);
+}
+
+int arfe_fpn_gate_conv_forward(const void* const* feats, const float* const* w1, const float* const* b1,
+                               const float* const* w2, const float* const* b2, const int32_t* H, const int32_t* W,
+                               int L, int B, int C, int dtype, int layout, void* workspace, size_t workspace_bytes,
+                               void* const* g1, void* const* g2, void* stream) {
+  const char* fn = "arfe_fpn_gate_conv_forward";
+  int rc = check_common(fn, L, B, C, H, W, dtype, layout);
+  if (rc) return rc;
+  REQUIRE(layout == ARFE_NHWC, ARFE_E_UNSUPPORTED, "%s: channels-last feature maps only", fn);
+  if (B == 0) return ARFE_OK;
+  REQUIRE(feats && w1 && b1 && w2 && b2 && g1 && g2 && workspace, ARFE_E_NULL, "%s: NULL argument", fn);
+  for (int l = 0; l < L; ++l) {
+    REQUIRE(feats[l] && w1[l] && b1[l] && w2[l] && b2[l] && g1[l] && g2[l], ARFE_E_NULL, "%s: NULL tensor at level %d", fn, l);
+    REQUIRE(aligned(feats[l], 16), ARFE_E_ALIGN, "%s: feats[%d] must be 16-byte aligned", fn, l);
+  }
+  REQUIRE(aligned(workspace, 16), ARFE_E_ALIGN, "%s: workspace must be 16-byte aligned", fn);
+  REQUIRE(workspace_bytes >= arfe::fpn_gate_conv_workspace_bytes(L, B, H, W), ARFE_E_SHAPE, "%s: workspace too small", fn);
+  DeviceGuard guard(workspace);
+  const cudaError_t e = arfe::launch_fpn_gate_conv_forward(feats, w1, b1, w2, b2, H, W, L, B, C, dtype, workspace, g1,
+                                                           g2, (cudaStream_t)stream);
+  if (e == cudaErrorNotSupported)
+    return fail(ARFE_E_UNSUPPORTED, "%s: needs C %% %d == 0 and C <= %d", fn, dtype == ARFE_F32 ? 4 : 8,
+                dtype == ARFE_F32 ? 256 : 512);
+  return cuda_result(e, fn);
+}
+
 static int fill_fpn(const char* fn, arfe::FpnParams& p, const int32_t* H, const int32_t* W, int L,
                     int B, int C, int dtype, int layout) {
   int rc = check_common(fn, L, B, C, H, W, dtype, layout);

@@ -94,6 +94,13 @@ cudaError_t launch_rff_softmax_fuse(int backward, const void* const* reg, const 
                                     void* const* dreg, void* dlogits, int64_t K, int PP, int C, int dtype,
                                     cudaStream_t stream);
 
+// AR-FPN gate convolutions, both 3x3 C -> 1 filters of every level in one pass over x (fpn_gate_conv.cu)
+size_t fpn_gate_conv_workspace_bytes(int L, int B, const int* H, const int* W);
+cudaError_t launch_fpn_gate_conv_forward(const void* const* feats, const float* const* w1, const float* const* b1,
+                                         const float* const* w2, const float* const* b2, const int* H, const int* W,
+                                         int L, int B, int C, int dtype, void* workspace, void* const* g1,
+                                         void* const* g2, cudaStream_t stream);
+
 // proposal side (proposals.cu)
 size_t nms_workspace_bytes(int n);
 cudaError_t launch_nms(const float* dets_sorted, int n, float thr, void* workspace, int64_t* keep, int* num_keep,

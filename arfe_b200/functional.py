@@ -569,6 +569,76 @@ def rff_softmax_fuse(regions, logits):
     return _RFFSoftmaxFuseFunction.apply(logits, *regions)
 
 
+class _FPNGateConvFunction(Function):
+    """g1_l, g2_l = the two C -> 1 3x3 convolutions of every level (wfpn_dual_spatial.py:120-121),
+    x read once for both (arfe_fpn_gate_conv_forward).  The backward of a convolution is the
+    library's (torch.nn.grad): a dense op outside the path."""
+
+    @staticmethod
+    def forward(ctx, nlev, *tensors):
+        feats = tensors[:nlev]
+        w1, b1 = tensors[nlev:2 * nlev], tensors[2 * nlev:3 * nlev]
+        w2, b2 = tensors[3 * nlev:4 * nlev], tensors[4 * nlev:5 * nlev]
+        feats, layout, dt = _prep_feats(feats)
+        if layout != L.ARFE_NHWC:
+            raise RuntimeError("fpn_gate_conv needs channels-last feature maps")
+        B, C = feats[0].shape[:2]
+        Hs = [f.shape[2] for f in feats]
+        Ws = [f.shape[3] for f in feats]
+        dev = feats[0].device
+        f32 = lambda ts: [t.detach().float().contiguous() for t in ts]
+        w1f, b1f, w2f, b2f = f32(w1), f32(b1), f32(w2), f32(b2)
+        g1 = [torch.empty((B, 1, h, w), dtype=feats[0].dtype, device=dev) for h, w in zip(Hs, Ws)]
+        g2 = [torch.empty_like(t) for t in g1]
+        if B > 0:
+            lib = L.lib()
+            nbytes = lib.arfe_fpn_gate_conv_workspace_bytes(nlev, B, L.int_array(Hs), L.int_array(Ws))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            rc = lib.arfe_fpn_gate_conv_forward(
+                L.ptr_array(feats), L.ptr_array(w1f), L.ptr_array(b1f), L.ptr_array(w2f), L.ptr_array(b2f),
+                L.int_array(Hs), L.int_array(Ws), nlev, B, C, dt, layout, ws.data_ptr(), nbytes,
+                L.ptr_array(g1), L.ptr_array(g2), L.stream_ptr(dev))
+            L.check(rc, "arfe_fpn_gate_conv_forward")
+        ctx.nlev = nlev
+        ctx.save_for_backward(*feats, *w1, *w2)
+        return tuple(g1) + tuple(g2)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *grads):
+        from torch.nn.grad import conv2d_input, conv2d_weight
+        n = ctx.nlev
+        saved = ctx.saved_tensors
+        feats, w1, w2 = saved[:n], saved[n:2 * n], saved[2 * n:3 * n]
+        dg1, dg2 = grads[:n], grads[n:]
+        need = ctx.needs_input_grad
+        dx, dw1, db1, dw2, db2 = [], [], [], [], []
+        for l in range(n):
+            x = feats[l]
+            gx = None
+            for w, g, dw, db, wi, bi in ((w1[l], dg1[l], dw1, db1, 1 + n + l, 1 + 2 * n + l),
+                                         (w2[l], dg2[l], dw2, db2, 1 + 3 * n + l, 1 + 4 * n + l)):
+                if g is None:
+                    dw.append(None); db.append(None)
+                    continue
+                g = g.to(x.dtype)
+                if need[1 + l]:
+                    t = conv2d_input(x.shape, w.to(x.dtype), g, padding=1)
+                    gx = t if gx is None else gx + t
+                dw.append(conv2d_weight(x, w.shape, g, padding=1).to(w.dtype) if need[wi] else None)
+                db.append(g.sum().reshape(1).to(w.dtype) if need[bi] else None)
+            dx.append(gx)
+        return (None,) + tuple(dx) + tuple(dw1) + tuple(db1) + tuple(dw2) + tuple(db2)
+
+
+def fpn_gate_conv(feats, w1, b1, w2, b2):
+    """(g1 list, g2 list): raw outputs (bias included, no activation) of the two C -> 1 3x3 gate
+    convolutions of every level; feats channels-last; w*: [1, C, 3, 3], b*: [1] per level."""
+    n = len(feats)
+    out = _FPNGateConvFunction.apply(n, *feats, *w1, *b1, *w2, *b2)
+    return list(out[:n]), list(out[n:])
+
+
 class FPNLink:
     """Couples the gather and the gated residual of ONE neck forward (WFPNDualSpatial.forward):
     x_l feeds both, so autograd would add their two gradients with one more pass over the

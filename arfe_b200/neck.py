@@ -11,7 +11,8 @@ import torch
 import torch.nn as nn
 
 from ._compat import ConvModule, xavier_init
-from .functional import FPNLink, fpn_apply, fpn_gather
+from . import _lib as L
+from .functional import FPNLink, fpn_apply, fpn_gate_conv, fpn_gather
 
 
 class NonLocal2D(nn.Module):
@@ -77,11 +78,23 @@ class WFPNDualSpatial(nn.Module):
                                         norm_cfg=norm_cfg, inplace=False))
         self.refine = NonLocal2D(in_channels, reduction=1, use_scale=False,
                                  conv_cfg=conv_cfg, norm_cfg=norm_cfg)
+        # channels-last inputs: the 2 x num_levels gate convolutions as one fused pass (forward);
+        # set False to run them through cuDNN like the reference
+        self.fuse_gate_convs = True
 
     def init_weights(self):
         for m in self.modules():
             if isinstance(m, nn.Conv2d):
                 xavier_init(m, distribution='uniform')
+
+    def _gate_convs_fusable(self, inputs):
+        x = inputs[0]
+        v = 4 if x.dtype == torch.float32 else 8
+        return x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and x.dim() == 4 and \
+            x.shape[1] % v == 0 and x.shape[1] <= 64 * v and \
+            all(L.layout_of(t) == L.ARFE_NHWC for t in inputs) and \
+            all(tuple(m.conv.weight.shape[2:]) == (3, 3) and m.conv.bias is not None
+                for m in list(self.reduce_convs) + list(self.reduce_convs2))
 
     def forward(self, inputs):
         assert len(inputs) == self.num_levels
@@ -91,6 +104,13 @@ class WFPNDualSpatial(nn.Module):
         bsf = self.refine(ori_fe)
         # pre-activation gate maps; relu (ConvModule's default act) + tanh + sum
         # are fused into the apply kernel
-        g1 = [self.reduce_convs[i](inputs[i], activate=False) for i in range(self.num_levels)]
-        g2 = [self.reduce_convs2[i](inputs[i], activate=False) for i in range(self.num_levels)]
+        if self.fuse_gate_convs and self._gate_convs_fusable(inputs):
+            # both C -> 1 convolutions of every level in one pass over the pyramid
+            c1 = [m.conv for m in self.reduce_convs]
+            c2 = [m.conv for m in self.reduce_convs2]
+            g1, g2 = fpn_gate_conv(list(inputs), [c.weight for c in c1], [c.bias for c in c1],
+                                   [c.weight for c in c2], [c.bias for c in c2])
+        else:
+            g1 = [self.reduce_convs[i](inputs[i], activate=False) for i in range(self.num_levels)]
+            g2 = [self.reduce_convs2[i](inputs[i], activate=False) for i in range(self.num_levels)]
         return tuple(fpn_apply(list(inputs), bsf, g1, g2, link))

@@ -340,6 +340,29 @@ int arfe_nms(const float* dets_sorted, int n, float iou_threshold,
 int arfe_bbox2roi(const float* const* boxes, const int32_t* counts,
                   const int32_t* cols, int B, float* rois, void* stream);
 
+/* ------------------------------------------------------------------------
+ * AR-FPN gate convolutions: g1_l = reduce_convs[l].conv(x_l), g2_l =
+ * reduce_convs2[l].conv(x_l) -- the two C -> 1 3x3 convolutions (padding 1, bias
+ * included, no activation) of mmdet/models/necks/wfpn_dual_spatial.py:38-55,
+ * :120-121, for all levels, reading every x_l ONCE (a C -> 1 convolution is a
+ * channel reduction bound by reading x; through two library convolutions the
+ * pyramid is read twice).  Forward only: the backward of a convolution stays
+ * with the library.
+ * feats[l]: [B,C,H[l],W[l]] `dtype`, channels-last (layout must be ARFE_NHWC);
+ * w1[l], w2[l]: fp32 [1,C,3,3] (the Conv2d weight as stored); b1[l], b2[l]: fp32
+ * [1]; g1[l], g2[l]: [B,1,H[l],W[l]] `dtype`, written.  workspace:
+ * arfe_fpn_gate_conv_workspace_bytes(L, B, H, W) bytes (18 floats per pixel),
+ * 16-byte aligned. */
+size_t arfe_fpn_gate_conv_workspace_bytes(int L, int B, const int32_t* H,
+                                          const int32_t* W);
+int arfe_fpn_gate_conv_forward(const void* const* feats,
+                               const float* const* w1, const float* const* b1,
+                               const float* const* w2, const float* const* b2,
+                               const int32_t* H, const int32_t* W, int L, int B,
+                               int C, int dtype, int layout, void* workspace,
+                               size_t workspace_bytes, void* const* g1,
+                               void* const* g2, void* stream);
+
 /* The whole AR-FPN backward in one pass over the incoming gradient pyramid
  * (channels-last only): what arfe_fpn_apply_backward followed by
  * arfe_fpn_gather_backward_acc(addend = douts) compute, bit for bit, reading

@@ -1,0 +1,48 @@
+"""The fused gate convolutions (arfe_fpn_gate_conv_forward) against cuDNN's 2 x 5 Conv2d(C, 1, 3) on the
+bench pyramid, channels-last, fp32 true precision (TF32 off) and TF32."""
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.getcwd())
+import arfe_b200 as A  # noqa: E402
+from arfe_b200 import workload as wl  # noqa: E402
+
+dev = torch.device("cuda:0")
+shapes = wl.pyramid_shapes(800, 1344)
+B, C = 2, 256
+xs = [torch.randn(B, C, h, w, device=dev).contiguous(memory_format=torch.channels_last) for h, w in shapes]
+w1 = [torch.randn(1, C, 3, 3, device=dev) * 0.05 for _ in shapes]
+w2 = [torch.randn(1, C, 3, 3, device=dev) * 0.05 for _ in shapes]
+b1 = [torch.randn(1, device=dev) for _ in shapes]
+b2 = [torch.randn(1, device=dev) for _ in shapes]
+
+
+def timeit(fn, n=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n * 1e3
+
+
+def cudnn():
+    return [F.conv2d(x, w, b, padding=1) for x, w, b in zip(xs, w1, b1)] + \
+           [F.conv2d(x, w, b, padding=1) for x, w, b in zip(xs, w2, b2)]
+
+
+with torch.no_grad():
+    t_ours = timeit(lambda: A.fpn_gate_conv(xs, w1, b1, w2, b2))
+    torch.backends.cudnn.allow_tf32 = False
+    t_fp32 = timeit(cudnn)
+    torch.backends.cudnn.allow_tf32 = True
+    t_tf32 = timeit(cudnn)
+pyr = sum(B * C * h * w * 4 for h, w in shapes)
+print(f"fused gate convs {t_ours:7.1f} us ({pyr / t_ours / 1e3:6.0f} GB/s of pyramid) | cuDNN 10 convs fp32 {t_fp32:7.1f} us, tf32 {t_tf32:7.1f} us")

@@ -238,3 +238,35 @@ def test_fused_fpn_backward_equals_the_two_call_path(cuda, dtype):
             # d gate maps: channel sums taken in another order (per-footprint reduction vs shuffle tree)
             tol = 2e-2 if dtype == torch.bfloat16 else 2e-5
             assert float((a - b).abs().max()) <= tol * float(b.abs().max()) + 1e-6, i
+
+
+@pytest.mark.parametrize("case", ["small_f32", "bench_f32", "bench_bf16"])
+def test_fused_gate_convs_match_conv2d(cuda, case):
+    """arfe_fpn_gate_conv_forward (both C -> 1 3x3 gate convolutions of every
+    level, one pass over x) against torch CPU conv2d -- the op the reference's ConvModule runs."""
+    import torch.nn.functional as F
+    import arfe_b200 as A
+    from arfe_b200 import workload as wl
+    bf16 = case.endswith("bf16")
+    if case.startswith("small"):
+        B, C, shapes = 2, 24, [(9, 13), (5, 7), (3, 4), (2, 2), (1, 1)]
+    else:
+        B, C, shapes = 2, 256, wl.pyramid_shapes(800, 1344)
+    gen = torch.Generator().manual_seed(8)
+    xs = [torch.randn(B, C, h, w, generator=gen) for h, w in shapes]
+    w1 = [torch.randn(1, C, 3, 3, generator=gen) * 0.05 for _ in shapes]
+    w2 = [torch.randn(1, C, 3, 3, generator=gen) * 0.05 for _ in shapes]
+    b1 = [torch.randn(1, generator=gen) for _ in shapes]
+    b2 = [torch.randn(1, generator=gen) for _ in shapes]
+    if bf16:
+        xs = [x.bfloat16().float() for x in xs]
+    dt = torch.bfloat16 if bf16 else torch.float32
+    g1, g2 = A.fpn_gate_conv([_cl(x.to(cuda, dt)) for x in xs], [t.to(cuda) for t in w1], [t.to(cuda) for t in b1],
+                             [t.to(cuda) for t in w2], [t.to(cuda) for t in b2])
+    for l in range(5):
+        for got, w, b in ((g1[l], w1[l], b1[l]), (g2[l], w2[l], b2[l])):
+            ref = F.conv2d(xs[l], w, b, padding=1)
+            assert got.shape == ref.shape and got.dtype == dt
+            err = (got.float().cpu() - ref).abs().max()
+            tol = (1e-2 if bf16 else 1e-5) * float(ref.abs().max()) + 1e-6   # 9 C-term sums in another order
+            assert float(err) <= tol, (case, l, float(err), float(ref.abs().max()))
