@@ -445,8 +445,9 @@ def run_ours(args, rank, local_rank, world):
                                     "gradient, d out read once); " if cl else
                                     "d x_l = d out_l + gather gradient in one write (arfe_fpn_gather_backward_acc); ") +
                                    "d lw / d lh are separate input tensors",
-                       "streams": ("RoI plan and tile binning (2 kernels) run on a second stream under the AR-FPN forward kernels; "
-                                   "the per-op times of roi_fuse_fwd / roi_fuse_bwd exclude them, the step time includes them"
+                       "streams": ("the RoI plan (under the AR-FPN forward kernels) and the backward's tile binning (forked after the "
+                                   "RoI forward, under the gate kernels) run on a second stream; the per-op times of roi_fuse_fwd / "
+                                   "roi_fuse_bwd exclude them, the ops they overlap and the step time include them"
                                    if getattr(step, "overlap_plan", False) else "one stream"),
                        "l2": "inputs+outputs per step (~1.8 GB) exceed the 126 MB L2; no explicit flush",
                        "timing": "CUDA events on the launch stream, max over ranks",

@@ -6,5 +6,7 @@ for text in texts:
     for line in text.strip().splitlines():
         if not line.startswith('{'): continue
         d = json.loads(line)
-        print("ms/step %.3f  img/s %.1f  e2e %.1f" % (d["ms_per_step"], d["value"], d["e2e"]["value"]))
+        e2e = d.get("e2e", {}).get("value")
+        print("ms/step %.3f  img/s %.1f  e2e %s  %s" % (d["ms_per_step"], d["value"], "%.1f" % e2e if e2e else "-",
+                                                      d.get("config", {}).get("workload", "")[:60]))
         for k, v in d["kernels"].items(): print("   %-16s %7.4f ms  %6.0f GB/s  frac %.3f" % (k, v["ms"], v["GBps"], v["frac"]))
