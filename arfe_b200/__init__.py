@@ -7,8 +7,8 @@ reference's module/operator surface.  Compute lives in libarfe_b200.so
 from ._compat import (ConvModule, accelerate_class, optimize_detector,  # noqa: F401
                       register_into_mmdet)
 from .bbox_head import MultiBBoxHead, MultiRoIsBBoxHead  # noqa: F401
-from .functional import (fpn_apply, fpn_gate_conv, fpn_gather, rff_gate, roi_fuse,  # noqa: F401
-                         roi_fuse_debug, roi_fuse_split, rff_softmax_fuse, split3)
+from .functional import (fpn_apply, fpn_gate_conv, fpn_gather, nonlocal_attention, rff_gate,  # noqa: F401
+                         roi_fuse, roi_fuse_debug, roi_fuse_split, rff_softmax_fuse, split3)
 from .neck import NonLocal2D, WFPNDualSpatial  # noqa: F401
 from .proposals import batched_nms, bbox2roi, nms  # noqa: F401
 from .regions import get_adaptive_scale_rois  # noqa: F401

@@ -533,6 +533,32 @@ int arfe_fpn_gate_conv_forward(const void* const* feats, const float* const* w1,
   return cuda_result(e, fn);
 }
 
+int arfe_nonlocal_default_split(int B, int HW) { return arfe::nonlocal_default_split(B, HW); }
+
+size_t arfe_nonlocal_workspace_bytes(int B, int HW, int D, int nsplit) {
+  if (B < 0 || HW < 1 || nsplit < 1 || nsplit > 8 || (D != 64 && D != 128 && D != 256)) return 0;
+  return arfe::nonlocal_workspace_bytes(B, HW, D, nsplit);
+}
+
+int arfe_nonlocal_attention_forward(const void* theta, const void* phi, const void* g, void* y, int B, int HW, int D,
+                                    int dtype, int layout, float scale, int nsplit, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  const char* fn = "arfe_nonlocal_attention_forward";
+  REQUIRE(dtype == ARFE_F32 || dtype == ARFE_BF16, ARFE_E_UNSUPPORTED, "%s: dtype=%d", fn, dtype);
+  REQUIRE(layout == ARFE_NCHW || layout == ARFE_NHWC, ARFE_E_UNSUPPORTED, "%s: layout=%d", fn, layout);
+  REQUIRE(D == 64 || D == 128 || D == 256, ARFE_E_UNSUPPORTED, "%s: inter_channels must be 64, 128 or 256 (got %d)", fn, D);
+  REQUIRE(B >= 0 && HW >= 1, ARFE_E_SHAPE, "%s: B=%d HW=%d", fn, B, HW);
+  if (B == 0) return ARFE_OK;
+  REQUIRE(B <= 21845, ARFE_E_SHAPE, "%s: B=%d exceeds the grid limit", fn, B);
+  REQUIRE(nsplit >= 1 && nsplit <= 8 && nsplit <= (HW + 63) / 64, ARFE_E_SHAPE, "%s: nsplit=%d", fn, nsplit);
+  REQUIRE(theta && phi && g && y && workspace, ARFE_E_NULL, "%s: NULL argument", fn);
+  REQUIRE(aligned(workspace, 1024), ARFE_E_ALIGN, "%s: workspace must be 1024-byte aligned", fn);
+  REQUIRE(workspace_bytes >= arfe::nonlocal_workspace_bytes(B, HW, D, nsplit), ARFE_E_SHAPE, "%s: workspace too small", fn);
+  DeviceGuard guard(workspace);
+  return cuda_result(arfe::launch_nonlocal_attention(theta, phi, g, y, B, HW, D, dtype, layout == ARFE_NHWC, scale,
+                                                     workspace, nsplit, (cudaStream_t)stream), fn);
+}
+
 static int fill_fpn(const char* fn, arfe::FpnParams& p, const int32_t* H, const int32_t* W, int L,
                     int B, int C, int dtype, int layout) {
   int rc = check_common(fn, L, B, C, H, W, dtype, layout);

@@ -108,6 +108,13 @@ cudaError_t launch_nms(const float* dets_sorted, int n, float thr, void* workspa
 cudaError_t launch_bbox2roi(const float* const* boxes, const int* counts, const int* cols, int B, float* rois,
                             cudaStream_t stream);
 
+// NonLocal2D refine as a fused tensor-core attention (nonlocal_attn.cu)
+int nonlocal_default_split(int B, int HW);
+size_t nonlocal_workspace_bytes(int B, int HW, int D, int nsplit);
+cudaError_t launch_nonlocal_attention(const void* theta, const void* phi, const void* g, void* y, int B, int HW, int D,
+                                      int dtype, int in_cl, float scale, void* workspace, int nsplit,
+                                      cudaStream_t stream);
+
 struct FpnParams {
   const void* feats[kMaxLevels];  // x_l (gather fwd / apply fwd) or dout_l (apply bwd)
   void* outs[kMaxLevels];         // out_l (apply fwd) or dx_l (gather bwd)

@@ -1,0 +1,566 @@
+// NonLocal2D refine of the AR-FPN neck as ONE fused attention on the 5th-generation tensor
+// cores.
+//
+// Reference: mmdet/ops/non_local.py:65-69 (embedded_gaussian: softmax(theta_x . phi_x [/ sqrt(Ci)]))
+// and :78-101 (y = pairwise_weight . g_x), called from necks/wfpn_dual_spatial.py:115 with
+// reduction = 1, use_scale = False: per image a 4200 x 4200 x 256 attention whose weight matrix the
+// reference materialises in fp32 (70.6 MB per image, written and re-read three times).
+//
+// What runs here (the 1x1 convolutions theta / phi / g / conv_out stay plain library GEMMs):
+//
+//  nl_pack_kernel      theta, phi, g (fp32 or bf16, NCHW or channels-last) -> bf16 operand tiles that
+//                      are already the shared-memory image the tensor core wants: K-major, 128-byte
+//                      swizzle (16-byte chunk c of row r stored at chunk c ^ (r & 7)), one contiguous
+//                      blob per tile, so the attention kernel fetches a tile with a single bulk copy
+//                      (cp.async.bulk, no tensor map) straight into place.
+//                        Qp [B][nqb][D/64 slabs][128 rows][128 B]     theta, rows = positions
+//                        Kp [B][nkb][D/64 slabs][ 64 rows][128 B]     phi,   rows = positions
+//                        Vp [B][nkb][D rows][128 B]                   g transposed: rows = channels, 64 positions
+//  nl_attn_kernel      one CTA = 128 query positions of one image (x one slice of the keys when the
+//                      key range is split to fill the SMs).  Warp roles:
+//                        warps 0-3  softmax: S (TMEM) -> registers, running max / sum, P (bf16) -> smem,
+//                                   rescale of O in TMEM only when a row maximum grew by more than 2^8
+//                                   (exact: the reference maximum used for the exponent is arbitrary),
+//                                   epilogue O / l -> y
+//                        warp 4     one lane issues tcgen05.mma: S = Q K^T (M128 N64 K16 x D/16) and
+//                                   O += P V (M128 N=D K16 x 4), accumulators in tensor memory;
+//                                   tcgen05.commit -> mbarriers
+//                        warp 5     one lane issues the bulk copies of Q and the K / V tile rings
+//                      S is double buffered in TMEM and P in shared memory, so Q K^T of step j+1 runs
+//                      under the softmax of step j.
+//  nl_combine_kernel   (key range split only) merges the partial (O, max, sum) triples.
+//
+// Arithmetic: operands rounded to bf16 (round to nearest even), products exact, fp32 accumulation in
+// the tensor core, fp32 softmax with exp2; tolerance against the fp32 reference is the bf16 one of
+// north_star (1e-2), written in tests/test_nonlocal_gpu.py.
+#include <cuda_bf16.h>
+
+#include "launch.h"
+#include "tma.cuh"
+
+namespace arfe {
+namespace {
+
+constexpr int NL_BM = 128;  // queries per CTA = UMMA M
+constexpr int NL_BN = 64;   // keys per step = one 128-byte swizzle row of bf16
+constexpr float NL_RESCALE = 8.f;  // log2 units a row maximum may grow before O is rescaled
+
+template <int D>
+struct NlCfg {
+  static constexpr int SLABS = D / 64;
+  static constexpr int Q_BYTES = NL_BM * D * 2;
+  static constexpr int K_BYTES = NL_BN * D * 2;
+  static constexpr int V_BYTES = D * NL_BN * 2;
+  static constexpr int P_BYTES = NL_BM * NL_BN * 2;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + Q_BYTES;
+  static constexpr int OFF_V = OFF_K + 2 * K_BYTES;
+  static constexpr int OFF_P = OFF_V + 2 * V_BYTES;
+  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+  static constexpr int SMEM = OFF_BAR + 256 + 1024;  // barriers + TMEM slot, slack for 1024-byte alignment
+  static constexpr int TMEM_USED = D + 2 * NL_BN;    // O | S0 | S1
+  static constexpr int TMEM_COLS = TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512);
+};
+
+// ---- tcgen05 / TMEM primitives (inline PTX) ---------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {  // arrives when all MMAs issued so far have completed
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, bf16 operands, fp32 accumulate
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart
+// (cute::UMMA::SmemDescriptor: start >> 4 | SBO >> 4 at bit 32 | version 1 at bit 46 | SWIZZLE_128B = 2 at bit 61)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulator, bf16 A and B, both K-major
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+#define NL_R32(r)                                                                                                  \
+  r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10], r[11], r[12], r[13], r[14], r[15], r[16],    \
+      r[17], r[18], r[19], r[20], r[21], r[22], r[23], r[24], r[25], r[26], r[27], r[28], r[29], r[30], r[31]
+// 32 consecutive fp32 columns of this thread's TMEM lane (warp w reads lanes 32 (w % 4) ...)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+// A wait that cannot hang the device: a protocol error traps (the launch fails with an error the
+// C ABI reports) instead of spinning for ever.
+__device__ __forceinline__ void nl_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0;
+  unsigned long long t0 = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (!done && (spin & 1023u) == 1023u) {  // 2 s without progress: a protocol error, not a slow step
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 2000000000ull) __trap();
+    }
+  }
+}
+
+// barrier indices
+enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 3, B_VFULL = 5, B_VEMPTY = 7, B_SFULL = 9, B_PFULL = 11, B_PVDONE = 13, B_COUNT = 15 };
+
+template <typename OutT>
+__device__ __forceinline__ void nl_store1(OutT* p, float v);
+template <>
+__device__ __forceinline__ void nl_store1<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void nl_store1<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+// ------------------------------------------------------------------------------------------------
+template <int D, typename OutT>
+__global__ void __launch_bounds__(192, 1)
+nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, const uint8_t* __restrict__ Vp,
+               OutT* __restrict__ y, float* __restrict__ part_o, float* __restrict__ part_ml, int HW, int nqb,
+               int nkb, int nsplit, float sl2, int out_cl) {
+  using C = NlCfg<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qb = blockIdx.x, b = blockIdx.y, z = blockIdx.z, B = gridDim.y;
+  const int kb_lo = (int)((long long)nkb * z / nsplit), kb_hi = (int)((long long)nkb * (z + 1) / nsplit);
+  const int n_it = kb_hi - kb_lo;
+
+  if (tid == 0) {
+    for (int i = 0; i < B_COUNT; ++i) mbar_init(&bars[i], (i == B_PFULL || i == B_PFULL + 1) ? 128 : 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {  // tensor memory: O | S0 | S1
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t tmem_o = tmem, tmem_s = tmem + D;
+
+  if (warp == 5) {
+    // ===== loader =====
+    if (lane == 0) {
+      const uint8_t* q_src = Qp + ((size_t)b * nqb + qb) * C::Q_BYTES;
+      mbar_arrive_expect_tx(&bars[B_QFULL], C::Q_BYTES);
+      for (int s = 0; s < C::SLABS; ++s)
+        bulk_g2s(smem + C::OFF_Q + s * (NL_BM * 128), q_src + s * (NL_BM * 128), NL_BM * 128, &bars[B_QFULL]);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+        const size_t blk = (size_t)b * nkb + (kb_lo + it);
+        nl_wait(&bars[B_KEMPTY + s], ph ^ 1u);
+        mbar_arrive_expect_tx(&bars[B_KFULL + s], C::K_BYTES);
+        bulk_g2s(smem + C::OFF_K + s * C::K_BYTES, Kp + blk * C::K_BYTES, C::K_BYTES, &bars[B_KFULL + s]);
+        nl_wait(&bars[B_VEMPTY + s], ph ^ 1u);
+        mbar_arrive_expect_tx(&bars[B_VFULL + s], C::V_BYTES);
+        bulk_g2s(smem + C::OFF_V + s * C::V_BYTES, Vp + blk * C::V_BYTES, C::V_BYTES, &bars[B_VFULL + s]);
+      }
+    }
+  } else if (warp == 4) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = idesc_bf16(NL_BM, NL_BN);
+      constexpr uint32_t idesc_pv = idesc_bf16(NL_BM, D);
+      const uint32_t q_addr = smem_u32(smem + C::OFF_Q);
+      nl_wait(&bars[B_QFULL], 0);
+      for (int it = 0; it <= n_it; ++it) {
+        if (it < n_it) {  // S[it & 1] = Q K_it^T
+          const int s = it & 1;
+          nl_wait(&bars[B_KFULL + s], (uint32_t)(it >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(smem + C::OFF_K + s * C::K_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint64_t ad = smem_desc_sw128(q_addr + (kk >> 2) * (NL_BM * 128) + (kk & 3) * 32);
+            const uint64_t bd = smem_desc_sw128(k_addr + (kk >> 2) * (NL_BN * 128) + (kk & 3) * 32);
+            tc_mma(tmem_s + (uint32_t)(it & 1) * NL_BN, ad, bd, idesc_qk, kk > 0);
+          }
+          tc_commit(&bars[B_SFULL + (it & 1)]);
+          tc_commit(&bars[B_KEMPTY + s]);
+        }
+        if (it >= 1) {  // O += P_jt V_jt
+          const int jt = it - 1, s = jt & 1;
+          const uint32_t ph = (uint32_t)(jt >> 1) & 1u;
+          nl_wait(&bars[B_VFULL + s], ph);
+          nl_wait(&bars[B_PFULL + s], ph);
+          tc_fence_after();
+          const uint32_t p_addr = smem_u32(smem + C::OFF_P + s * C::P_BYTES);
+          const uint32_t v_addr = smem_u32(smem + C::OFF_V + s * C::V_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < NL_BN / 16; ++kk)
+            tc_mma(tmem_o, smem_desc_sw128(p_addr + kk * 32), smem_desc_sw128(v_addr + kk * 32), idesc_pv,
+                   (jt > 0 || kk > 0) ? 1u : 0u);
+          tc_commit(&bars[B_PVDONE + s]);
+          tc_commit(&bars[B_VEMPTY + s]);
+        }
+      }
+    }
+  } else {
+    // ===== softmax / correction / epilogue: thread = query row, warp = TMEM lane quadrant =====
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int row = tid;  // 0..127
+    float m_ref = 0.f, l = 0.f;
+    for (int it = 0; it < n_it; ++it) {
+      const int buf = it & 1;
+      nl_wait(&bars[B_SFULL + buf], (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      uint32_t s0[32], s1[32];
+      tmem_ld32(tmem_s + lane_base + buf * NL_BN, s0);
+      tmem_ld32(tmem_s + lane_base + buf * NL_BN + 32, s1);
+      tmem_wait_ld();
+      const int nvalid = HW - (kb_lo + it) * NL_BN;  // keys of this step that exist (>= 64: all)
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float v0 = __uint_as_float(s0[c]) * sl2, v1 = __uint_as_float(s1[c]) * sl2;
+        if (c >= nvalid) v0 = -INFINITY;
+        if (c + 32 >= nvalid) v1 = -INFINITY;
+        s0[c] = __float_as_uint(v0);
+        s1[c] = __float_as_uint(v1);
+        mx = fmaxf(mx, fmaxf(v0, v1));
+      }
+      if (it == 0) {
+        m_ref = mx;
+      } else {
+        const bool grow = mx > m_ref + NL_RESCALE;
+        if (__any_sync(0xffffffffu, grow)) {
+          // O must be quiescent: P V of the previous step done (it was issued after this step's Q K^T)
+          nl_wait(&bars[B_PVDONE + ((it - 1) & 1)], (uint32_t)((it - 1) >> 1) & 1u);
+          tc_fence_after();
+          const float m_new = grow ? mx : m_ref;
+          const float alpha = fast_exp2(m_ref - m_new);
+          l *= alpha;
+          m_ref = m_new;
+#pragma unroll 1
+          for (int ch = 0; ch < D / 32; ++ch) {
+            uint32_t o[32];
+            tmem_ld32(tmem_o + lane_base + ch * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+            tmem_st32(tmem_o + lane_base + ch * 32, o);
+          }
+          tmem_wait_st();
+        }
+      }
+      // P = exp2(s - m_ref) as bf16 into the swizzled A tile; l sums what the tensor core will see
+      uint8_t* p_row = smem + C::OFF_P + buf * C::P_BYTES + row * 128;
+      float lsum = 0.f;
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = c8 * 8 + e * 2;
+          const float x0 = __uint_as_float(c < 32 ? s0[c & 31] : s1[c & 31]);
+          const float x1 = __uint_as_float(c + 1 < 32 ? s0[(c + 1) & 31] : s1[(c + 1) & 31]);
+          w[e] = pack_bf16(fast_exp2(x0 - m_ref), fast_exp2(x1 - m_ref));
+          lsum += bf16_lo(w[e]) + bf16_hi(w[e]);
+        }
+        *reinterpret_cast<uint4*>(p_row + ((c8 ^ (row & 7)) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      l += lsum;
+      fence_async_smem();  // generic-proxy writes of P -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(&bars[B_PFULL + buf]);
+    }
+    // epilogue
+    nl_wait(&bars[B_PVDONE + ((n_it - 1) & 1)], (uint32_t)((n_it - 1) >> 1) & 1u);
+    tc_fence_after();
+    const int p = qb * NL_BM + row;
+    const float inv = nsplit == 1 ? 1.f / l : 1.f;
+    if (nsplit > 1) {
+      const size_t prow = ((size_t)z * B + b) * ((size_t)nqb * NL_BM) + p;
+      part_ml[prow * 2 + 0] = m_ref;
+      part_ml[prow * 2 + 1] = l;
+    }
+#pragma unroll 1
+    for (int ch = 0; ch < D / 32; ++ch) {
+      uint32_t o[32];
+      tmem_ld32(tmem_o + lane_base + ch * 32, o);
+      tmem_wait_ld();
+      if (nsplit > 1) {
+        float4* dst = reinterpret_cast<float4*>(part_o + (((size_t)z * B + b) * ((size_t)nqb * NL_BM) + p) * D + ch * 32);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          dst[c] = make_float4(__uint_as_float(o[4 * c]), __uint_as_float(o[4 * c + 1]), __uint_as_float(o[4 * c + 2]),
+                               __uint_as_float(o[4 * c + 3]));
+      } else if (p < HW) {
+        if (out_cl) {
+          OutT* dst = y + ((size_t)b * HW + p) * D + ch * 32;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) nl_store1(dst + c, __uint_as_float(o[c]) * inv);
+        } else {
+          OutT* dst = y + ((size_t)b * D + ch * 32) * HW + p;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) nl_store1(dst + (size_t)c * HW, __uint_as_float(o[c]) * inv);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Merge of the key-range partials: y = sum_z O_z 2^(m_z - M) / sum_z l_z 2^(m_z - M)
+template <typename OutT>
+__global__ void nl_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml,
+                                  OutT* __restrict__ y, int B, int HW, int D, int rows_pad, int nsplit, int out_cl) {
+  const int d4 = D / 4;
+  const long long n = (long long)B * HW * d4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    // NCHW output: consecutive threads = consecutive positions; channels-last: consecutive channels
+    int b, p, c4;
+    if (out_cl) {
+      c4 = (int)(i % d4);
+      p = (int)((i / d4) % HW);
+      b = (int)(i / ((long long)d4 * HW));
+    } else {
+      p = (int)(i % HW);
+      c4 = (int)((i / HW) % d4);
+      b = (int)(i / ((long long)d4 * HW));
+    }
+    float M = -INFINITY;
+    for (int zz = 0; zz < nsplit; ++zz) M = fmaxf(M, part_ml[(((size_t)zz * B + b) * rows_pad + p) * 2]);
+    float den = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int zz = 0; zz < nsplit; ++zz) {
+      const size_t r = ((size_t)zz * B + b) * rows_pad + p;
+      const float w = exp2f(part_ml[r * 2] - M);
+      den += part_ml[r * 2 + 1] * w;
+      const float4 o = *reinterpret_cast<const float4*>(part_o + r * D + c4 * 4);
+      acc.x += o.x * w; acc.y += o.y * w; acc.z += o.z * w; acc.w += o.w * w;
+    }
+    const float inv = 1.f / den;
+    if (out_cl) {
+      OutT* dst = y + ((size_t)b * HW + p) * D + c4 * 4;
+      nl_store1(dst, acc.x * inv); nl_store1(dst + 1, acc.y * inv); nl_store1(dst + 2, acc.z * inv); nl_store1(dst + 3, acc.w * inv);
+    } else {
+      OutT* dst = y + ((size_t)b * D + c4 * 4) * HW + p;
+      nl_store1(dst, acc.x * inv); nl_store1(dst + HW, acc.y * inv); nl_store1(dst + 2 * (size_t)HW, acc.z * inv);
+      nl_store1(dst + 3 * (size_t)HW, acc.w * inv);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Operand packing: a 64-position x 64-channel tile through shared memory, out as 16-byte chunks of
+// 8 bf16 along the contraction axis (channels for theta / phi, positions for g), swizzled.
+template <typename T>
+__device__ __forceinline__ float nl_to_float(T v);
+template <>
+__device__ __forceinline__ float nl_to_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float nl_to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+nl_pack_kernel(const T* __restrict__ theta, const T* __restrict__ phi, const T* __restrict__ g,
+               uint8_t* __restrict__ Qp, uint8_t* __restrict__ Kp, uint8_t* __restrict__ Vp, int HW, int D, int in_cl,
+               int nqb, int nkb) {
+  __shared__ float tile[64][65];  // [position][channel]
+  const int which = blockIdx.z % 3, b = blockIdx.z / 3;
+  const int pb = blockIdx.x, slab = blockIdx.y;
+  if (which == 0 ? pb >= nqb * 2 : pb >= nkb) return;
+  const T* src = which == 0 ? theta : (which == 1 ? phi : g);
+  const int p0 = pb * 64, c0 = slab * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  if (in_cl) {  // [B][HW][D]: channels contiguous
+    for (int pl = ty; pl < 64; pl += 4) {
+      const int p = p0 + pl;
+      tile[pl][tx] = p < HW ? nl_to_float(src[((size_t)b * HW + p) * D + c0 + tx]) : 0.f;
+    }
+  } else {  // [B][D][HW]: positions contiguous
+    for (int cl = ty; cl < 64; cl += 4) {
+      const int p = p0 + tx;
+      tile[tx][cl] = p < HW ? nl_to_float(src[((size_t)b * D + c0 + cl) * HW + p]) : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < 512; q += 256) {
+    const int r = q >> 3, c = q & 7;
+    uint32_t w[4];
+    uint8_t* dst;
+    if (which < 2) {  // row = position, chunk = 8 channels
+#pragma unroll
+      for (int e = 0; e < 4; ++e) w[e] = pack_bf16(tile[r][c * 8 + 2 * e], tile[r][c * 8 + 2 * e + 1]);
+      const int prow = p0 + r;
+      if (which == 0) {
+        const int rr = prow & (NL_BM - 1);
+        dst = Qp + ((size_t)b * nqb + (prow >> 7)) * ((size_t)NL_BM * D * 2) + (size_t)slab * (NL_BM * 128) + rr * 128 +
+              ((c ^ (rr & 7)) * 16);
+      } else {
+        dst = Kp + ((size_t)b * nkb + pb) * ((size_t)NL_BN * D * 2) + (size_t)slab * (NL_BN * 128) + r * 128 +
+              ((c ^ (r & 7)) * 16);
+      }
+    } else {  // row = channel, chunk = 8 positions
+#pragma unroll
+      for (int e = 0; e < 4; ++e) w[e] = pack_bf16(tile[c * 8 + 2 * e][r], tile[c * 8 + 2 * e + 1][r]);
+      const int d = c0 + r;
+      dst = Vp + ((size_t)b * nkb + pb) * ((size_t)D * NL_BN * 2) + (size_t)d * 128 + ((c ^ (d & 7)) * 16);
+    }
+    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+struct NlLayout {
+  int nqb, nkb, rows_pad;
+  size_t q_bytes, k_bytes, v_bytes, part_o_bytes, part_ml_bytes;
+  size_t off_k, off_v, off_po, off_pml, total;
+};
+NlLayout nl_layout(int B, int HW, int D, int nsplit) {
+  NlLayout a;
+  a.nqb = (HW + NL_BM - 1) / NL_BM;
+  a.nkb = (HW + NL_BN - 1) / NL_BN;
+  a.rows_pad = a.nqb * NL_BM;
+  a.q_bytes = (size_t)B * a.nqb * NL_BM * D * 2;
+  a.k_bytes = (size_t)B * a.nkb * NL_BN * D * 2;
+  a.v_bytes = a.k_bytes;
+  a.part_o_bytes = nsplit > 1 ? (size_t)nsplit * B * a.rows_pad * D * 4 : 0;
+  a.part_ml_bytes = nsplit > 1 ? (size_t)nsplit * B * a.rows_pad * 2 * 4 : 0;
+  a.off_k = a.q_bytes;
+  a.off_v = a.off_k + a.k_bytes;
+  a.off_po = a.off_v + a.v_bytes;
+  a.off_pml = a.off_po + a.part_o_bytes;
+  a.total = a.off_pml + a.part_ml_bytes;
+  return a;
+}
+
+template <int D, typename OutT>
+cudaError_t nl_launch_attn(const NlLayout& a, uint8_t* ws, OutT* y, int B, int HW, int nsplit, float sl2, int out_cl,
+                           cudaStream_t stream) {
+  using C = NlCfg<D>;
+  cudaError_t e = cudaFuncSetAttribute(nl_attn_kernel<D, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+  if (e != cudaSuccess) return e;
+  nl_attn_kernel<D, OutT><<<dim3(a.nqb, B, nsplit), 192, C::SMEM, stream>>>(
+      ws, ws + a.off_k, ws + a.off_v, y, reinterpret_cast<float*>(ws + a.off_po),
+      reinterpret_cast<float*>(ws + a.off_pml), HW, a.nqb, a.nkb, nsplit, sl2, out_cl);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t nl_run(const void* theta, const void* phi, const void* g, void* y, int B, int HW, int D, int in_cl,
+                   float scale, void* workspace, int nsplit, cudaStream_t stream) {
+  const NlLayout a = nl_layout(B, HW, D, nsplit);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const int pbs = a.nqb * 2 > a.nkb ? a.nqb * 2 : a.nkb;
+  nl_pack_kernel<T><<<dim3(pbs, D / 64, 3 * B), 256, 0, stream>>>(
+      static_cast<const T*>(theta), static_cast<const T*>(phi), static_cast<const T*>(g), ws, ws + a.off_k,
+      ws + a.off_v, HW, D, in_cl, a.nqb, a.nkb);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const float sl2 = scale * 1.4426950408889634f;
+  T* yo = static_cast<T*>(y);
+  switch (D) {
+    case 64: e = nl_launch_attn<64, T>(a, ws, yo, B, HW, nsplit, sl2, in_cl, stream); break;
+    case 128: e = nl_launch_attn<128, T>(a, ws, yo, B, HW, nsplit, sl2, in_cl, stream); break;
+    case 256: e = nl_launch_attn<256, T>(a, ws, yo, B, HW, nsplit, sl2, in_cl, stream); break;
+    default: return cudaErrorNotSupported;
+  }
+  if (e != cudaSuccess) return e;
+  if (nsplit > 1) {
+    const long long n = (long long)B * HW * (D / 4);
+    const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    nl_combine_kernel<T><<<blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(ws + a.off_po),
+                                                      reinterpret_cast<const float*>(ws + a.off_pml), yo, B, HW, D,
+                                                      a.rows_pad, nsplit, in_cl);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+}  // namespace
+
+int nonlocal_default_split(int B, int HW) {
+  if (B < 1 || HW < 1) return 1;
+  const int nqb = (HW + NL_BM - 1) / NL_BM, nkb = (HW + NL_BN - 1) / NL_BN;
+  int s = sm_count() / (nqb * B);
+  if (s < 1) s = 1;
+  if (s > 4) s = 4;
+  if (s > nkb) s = nkb;
+  return s;
+}
+
+size_t nonlocal_workspace_bytes(int B, int HW, int D, int nsplit) { return nl_layout(B, HW, D, nsplit).total; }
+
+cudaError_t launch_nonlocal_attention(const void* theta, const void* phi, const void* g, void* y, int B, int HW, int D,
+                                      int dtype, int in_cl, float scale, void* workspace, int nsplit,
+                                      cudaStream_t stream) {
+  if (D != 64 && D != 128 && D != 256) return cudaErrorNotSupported;
+  return dtype == 0 ? nl_run<float>(theta, phi, g, y, B, HW, D, in_cl, scale, workspace, nsplit, stream)
+                    : nl_run<__nv_bfloat16>(theta, phi, g, y, B, HW, D, in_cl, scale, workspace, nsplit, stream);
+}
+
+}  // namespace arfe

@@ -780,3 +780,69 @@ class _FPNApplyFunction(Function):
 def fpn_apply(feats, bsf, g1, g2, link=None):
     n = len(feats)
     return _FPNApplyFunction.apply(n, link, bsf, *feats, *g1, *g2)
+
+
+class _NonLocalAttentionFunction(Function):
+    """mmdet/ops/non_local.py:65-69 + :98-101: y = softmax(scale * theta_x . phi_x) . g_x as one
+    fused tensor-core attention (arfe_nonlocal_attention_forward); the HW x HW weight matrix is
+    not materialised.  Backward: recomputed from the saved operands with library matmuls (the
+    flash-style backward kernel is not built)."""
+
+    @staticmethod
+    def forward(ctx, theta, phi, g, scale, nsplit):
+        L.require_cuda(theta, phi, g)
+        layout = L.layout_of(theta)
+        theta, phi, g = (L.as_layout(t, layout) for t in (theta, phi, g))
+        dt = L.dtype_code(theta)
+        if not (theta.dtype == phi.dtype == g.dtype) or not (theta.shape == phi.shape == g.shape):
+            raise ValueError("nonlocal_attention: theta, phi, g must share dtype and shape")
+        B, D, H, W = theta.shape
+        HW = H * W
+        y = torch.empty_like(theta)
+        if B > 0 and HW > 0:
+            lib = L.lib()
+            with torch.cuda.device(theta.device):
+                if nsplit is None:
+                    nsplit = lib.arfe_nonlocal_default_split(B, HW)
+                nbytes = lib.arfe_nonlocal_workspace_bytes(B, HW, D, nsplit)
+            if nbytes == 0:
+                raise RuntimeError(f"nonlocal_attention: inter_channels must be 64, 128 or 256 (got {D})")
+            ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=theta.device)
+            base = (ws.data_ptr() + 1023) // 1024 * 1024
+            rc = lib.arfe_nonlocal_attention_forward(
+                theta.data_ptr(), phi.data_ptr(), g.data_ptr(), y.data_ptr(), B, HW, D, dt, layout,
+                float(scale), nsplit, base, nbytes, L.stream_ptr(theta.device))
+            L.check(rc, "arfe_nonlocal_attention_forward")
+        ctx.scale = float(scale)
+        ctx.save_for_backward(theta, phi, g)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        theta, phi, g = ctx.saved_tensors
+        B, D, H, W = theta.shape
+        f = torch.float32
+        th = theta.reshape(B, D, -1).permute(0, 2, 1).to(f)      # [B, HW, D]
+        ph = phi.reshape(B, D, -1).to(f)                         # [B, D, HW]
+        gx = g.reshape(B, D, -1).permute(0, 2, 1).to(f)          # [B, HW, D]
+        dyx = dy.reshape(B, D, -1).permute(0, 2, 1).to(f)        # [B, HW, D]
+        p = torch.matmul(th, ph).mul_(ctx.scale).softmax(dim=-1)
+        dg = torch.matmul(p.transpose(1, 2), dyx)
+        dp = torch.matmul(dyx, gx.transpose(1, 2))
+        ds = p * (dp - (dp * p).sum(dim=-1, keepdim=True))
+        ds.mul_(ctx.scale)
+        dth = torch.matmul(ds, ph.transpose(1, 2))
+        dph = torch.matmul(th.transpose(1, 2), ds)               # [B, D, HW]
+
+        def back(t, transposed):
+            t = t.permute(0, 2, 1) if transposed else t
+            return t.reshape(B, D, H, W).to(theta.dtype)
+        return back(dth, True), back(dph, False), back(dg, True), None, None
+
+
+def nonlocal_attention(theta, phi, g, scale=1.0, nsplit=None):
+    """theta, phi, g: [B, D, H, W] (the outputs of NonLocal2D's 1x1 convolutions, NCHW or
+    channels-last); returns y [B, D, H, W] = what the reference reshapes its
+    ``matmul(pairwise_weight, g_x)`` into (non_local.py:98-101)."""
+    return _NonLocalAttentionFunction.apply(theta, phi, g, scale, nsplit)

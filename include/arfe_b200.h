@@ -384,6 +384,32 @@ int arfe_fpn_backward_fused(const void* const* douts, int douts_f32,
                             float* dbsf, float* const* dg1, float* const* dg2,
                             void* const* dx, void* stream);
 
+/* ------------------------------------------------------------------------
+ * NonLocal2D refine as one fused attention on the tensor cores (tcgen05, TMEM):
+ *   y[b, p, :] = sum_q softmax_q(scale * <theta[b, p, :], phi[b, q, :]>) g[b, q, :]
+ * = mmdet/ops/non_local.py:65-69 (embedded_gaussian; scale = 1, or
+ * 1/sqrt(inter_channels) when use_scale) followed by :98-101 (pairwise_weight .
+ * g_x), the call of mmdet/models/necks/wfpn_dual_spatial.py:115.  The HW x HW
+ * weight matrix (70.6 MB per image at 50 x 84) is never materialised.  The 1x1
+ * convolutions g / theta / phi / conv_out and the residual stay with the caller.
+ * theta, phi, g, y: [B, D, H, W] `dtype` with HW = H * W, all ARFE_NCHW or all
+ * ARFE_NHWC (y has the layout of the inputs and is what the reference's
+ * `y.permute(0, 2, 1).contiguous().reshape(n, D, h, w)` holds); D = inter_channels
+ * in {64, 128, 256}.  Operands are rounded to bf16, accumulation and softmax are
+ * fp32: results agree with the fp32 reference to bf16 accuracy (1e-2).
+ * nsplit >= 1 slices the key range over several CTAs per 128-query block
+ * (arfe_nonlocal_default_split: enough to fill the SMs of the current device);
+ * workspace: arfe_nonlocal_workspace_bytes(B, HW, D, nsplit) bytes, 1024-byte
+ * aligned (bf16 operand tiles + the partial results when nsplit > 1).  Forward
+ * only. */
+int arfe_nonlocal_default_split(int B, int HW);
+size_t arfe_nonlocal_workspace_bytes(int B, int HW, int D, int nsplit);
+int arfe_nonlocal_attention_forward(const void* theta, const void* phi,
+                                    const void* g, void* y, int B, int HW, int D,
+                                    int dtype, int layout, float scale,
+                                    int nsplit, void* workspace,
+                                    size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
