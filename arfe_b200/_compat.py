@@ -104,18 +104,24 @@ def register_into_mmdet(force=True):
     return True
 
 
-def optimize_detector(model):
+def optimize_detector(model, fused_attention='auto'):
     """Put a built detector on the fast path: parameters and activations in
     torch.channels_last (cuDNN's preferred layout for the convs around the path, and
     the layout in which our kernels need no transposes and no atomics) and the RoI
     extractors in split mode (regions handed to the head as separate tensors).
     Without it an unchanged NCHW config runs through the compatibility kernels --
-    correct, ~3.8x slower on the RoI part."""
+    correct, ~3.8x slower on the RoI part.
+    fused_attention: NonLocal2D.fused_attention of every refine block ('auto': the tensor-core
+    attention for bfloat16 activations only; True: also for float32 ones, whose operands are
+    then rounded to bf16)."""
     import torch
+    from .neck import NonLocal2D
     from .roi_extractor import SingleRoIExtractor
     model = model.to(memory_format=torch.channels_last)
     for m in model.modules():
         if isinstance(m, SingleRoIExtractor):
             m.roi_feats_split = True
             m.roi_feats_channels_last = True
+        elif isinstance(m, NonLocal2D):
+            m.fused_attention = fused_attention
     return model

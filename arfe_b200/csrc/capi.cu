@@ -548,6 +548,7 @@ int arfe_nonlocal_attention_forward(const void* theta, const void* phi, const vo
   REQUIRE(layout == ARFE_NCHW || layout == ARFE_NHWC, ARFE_E_UNSUPPORTED, "%s: layout=%d", fn, layout);
   REQUIRE(D == 64 || D == 128 || D == 256, ARFE_E_UNSUPPORTED, "%s: inter_channels must be 64, 128 or 256 (got %d)", fn, D);
   REQUIRE(B >= 0 && HW >= 1, ARFE_E_SHAPE, "%s: B=%d HW=%d", fn, B, HW);
+  REQUIRE(scale > 0.f, ARFE_E_SHAPE, "%s: scale must be positive", fn);
   if (B == 0) return ARFE_OK;
   REQUIRE(B <= 21845, ARFE_E_SHAPE, "%s: B=%d exceeds the grid limit", fn, B);
   REQUIRE(nsplit >= 1 && nsplit <= 8 && nsplit <= (HW + 63) / 64, ARFE_E_SHAPE, "%s: nsplit=%d", fn, nsplit);

@@ -18,16 +18,16 @@
 //                        Vp [B][nkb][D rows][128 B]                   g transposed: rows = channels, 64 positions
 //  nl_attn_kernel      one CTA = 128 query positions of one image (x one slice of the keys when the
 //                      key range is split to fill the SMs).  Warp roles:
-//                        warps 0-3  softmax: S (TMEM) -> registers, running max / sum, P (bf16) -> smem,
-//                                   rescale of O in TMEM only when a row maximum grew by more than 2^8
-//                                   (exact: the reference maximum used for the exponent is arbitrary),
-//                                   epilogue O / l -> y
-//                        warp 4     one lane issues tcgen05.mma: S = Q K^T (M128 N64 K16 x D/16) and
+//                        warps 0-7  softmax, thread = (query row, half of the 64 key columns): S (TMEM) ->
+//                                   registers, running max / sum, P (bf16) -> smem; rescale of O in TMEM
+//                                   only when a row maximum grew by more than 2^8 (exact: the maximum
+//                                   used as the exponent's reference is arbitrary); epilogue O / l -> y
+//                        warp 8     one lane issues tcgen05.mma: S = Q K^T (M128 N64 K16 x D/16) and
 //                                   O += P V (M128 N=D K16 x 4), accumulators in tensor memory;
 //                                   tcgen05.commit -> mbarriers
-//                        warp 5     one lane issues the bulk copies of Q and the K / V tile rings
-//                      S is double buffered in TMEM and P in shared memory, so Q K^T of step j+1 runs
-//                      under the softmax of step j.
+//                        warps 9,10 one lane each issues the bulk copies of Q + the K ring / the V ring
+//                      Four S tiles live in TMEM (Q K^T runs three steps ahead of P V) and P is double
+//                      buffered in shared memory, so the tensor pipe never waits for a softmax hand-off.
 //  nl_combine_kernel   (key range split only) merges the partial (O, max, sum) triples.
 //
 // Arithmetic: operands rounded to bf16 (round to nearest even), products exact, fp32 accumulation in
@@ -44,6 +44,7 @@ namespace {
 constexpr int NL_BM = 128;  // queries per CTA = UMMA M
 constexpr int NL_BN = 64;   // keys per step = one 128-byte swizzle row of bf16
 constexpr float NL_RESCALE = 8.f;  // log2 units a row maximum may grow before O is rescaled
+constexpr int NL_SBUF = 4;         // S tiles in tensor memory: Q K^T runs NL_SBUF - 1 steps ahead of P V
 
 template <int D>
 struct NlCfg {
@@ -57,8 +58,9 @@ struct NlCfg {
   static constexpr int OFF_V = OFF_K + 2 * K_BYTES;
   static constexpr int OFF_P = OFF_V + 2 * V_BYTES;
   static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
-  static constexpr int SMEM = OFF_BAR + 256 + 1024;  // barriers + TMEM slot, slack for 1024-byte alignment
-  static constexpr int TMEM_USED = D + 2 * NL_BN;    // O | S0 | S1
+  static constexpr int OFF_XCH = OFF_BAR + 256;      // row max / sum exchange between the two column halves
+  static constexpr int SMEM = OFF_XCH + 2 * 2 * NL_BM * 4;  // the kernel has no static shared memory: base 1024-aligned
+  static constexpr int TMEM_USED = D + NL_SBUF * NL_BN;  // O | S0 .. S3
   static constexpr int TMEM_COLS = TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512);
 };
 
@@ -161,7 +163,7 @@ __device__ __forceinline__ void nl_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // barrier indices
-enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 3, B_VFULL = 5, B_VEMPTY = 7, B_SFULL = 9, B_PFULL = 11, B_PVDONE = 13, B_COUNT = 15 };
+enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 3, B_VFULL = 5, B_VEMPTY = 7, B_SFULL = 9, B_PFULL = 13, B_PVDONE = 15, B_COUNT = 17 };
 
 template <typename OutT>
 __device__ __forceinline__ void nl_store1(OutT* p, float v);
@@ -171,16 +173,20 @@ template <>
 __device__ __forceinline__ void nl_store1<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
 
 // ------------------------------------------------------------------------------------------------
+constexpr int NL_SOFTMAX_WARPS = 8;  // two per TMEM lane quadrant: each takes half of the 64 key columns
+constexpr int NL_THREADS = (NL_SOFTMAX_WARPS + 3) * 32;  // + MMA issuer, K loader, V loader
+
 template <int D, typename OutT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(NL_THREADS, 1)
 nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, const uint8_t* __restrict__ Vp,
                OutT* __restrict__ y, float* __restrict__ part_o, float* __restrict__ part_ml, int HW, int nqb,
                int nkb, int nsplit, float sl2, int out_cl) {
   using C = NlCfg<D>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128-byte swizzle atoms need a 1024-byte aligned base
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  float* xch = reinterpret_cast<float*>(smem + C::OFF_XCH);  // [2 parities][2 halves][128 rows]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qb = blockIdx.x, b = blockIdx.y, z = blockIdx.z, B = gridDim.y;
@@ -188,10 +194,11 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
   const int n_it = kb_hi - kb_lo;
 
   if (tid == 0) {
-    for (int i = 0; i < B_COUNT; ++i) mbar_init(&bars[i], (i == B_PFULL || i == B_PFULL + 1) ? 128 : 1);
+    for (int i = 0; i < B_COUNT; ++i)
+      mbar_init(&bars[i], (i == B_PFULL || i == B_PFULL + 1) ? NL_SOFTMAX_WARPS * 32 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {  // tensor memory: O | S0 | S1
+  if (warp == NL_SOFTMAX_WARPS) {  // tensor memory: O | S0 | S1
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)C::TMEM_COLS)
                  : "memory");
@@ -203,8 +210,8 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   const uint32_t tmem_o = tmem, tmem_s = tmem + D;
 
-  if (warp == 5) {
-    // ===== loader =====
+  if (warp == NL_SOFTMAX_WARPS + 1) {
+    // ===== loader of Q and the K ring (a slot is free once the Q K^T that read it has completed) =====
     if (lane == 0) {
       const uint8_t* q_src = Qp + ((size_t)b * nqb + qb) * C::Q_BYTES;
       mbar_arrive_expect_tx(&bars[B_QFULL], C::Q_BYTES);
@@ -212,152 +219,173 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
         bulk_g2s(smem + C::OFF_Q + s * (NL_BM * 128), q_src + s * (NL_BM * 128), NL_BM * 128, &bars[B_QFULL]);
       for (int it = 0; it < n_it; ++it) {
         const int s = it & 1;
-        const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-        const size_t blk = (size_t)b * nkb + (kb_lo + it);
-        nl_wait(&bars[B_KEMPTY + s], ph ^ 1u);
+        nl_wait(&bars[B_KEMPTY + s], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         mbar_arrive_expect_tx(&bars[B_KFULL + s], C::K_BYTES);
-        bulk_g2s(smem + C::OFF_K + s * C::K_BYTES, Kp + blk * C::K_BYTES, C::K_BYTES, &bars[B_KFULL + s]);
-        nl_wait(&bars[B_VEMPTY + s], ph ^ 1u);
-        mbar_arrive_expect_tx(&bars[B_VFULL + s], C::V_BYTES);
-        bulk_g2s(smem + C::OFF_V + s * C::V_BYTES, Vp + blk * C::V_BYTES, C::V_BYTES, &bars[B_VFULL + s]);
+        bulk_g2s(smem + C::OFF_K + s * C::K_BYTES, Kp + ((size_t)b * nkb + (kb_lo + it)) * C::K_BYTES, C::K_BYTES,
+                 &bars[B_KFULL + s]);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == NL_SOFTMAX_WARPS + 2) {
+    // ===== loader of the V ring (free once the P V that read it has completed) =====
+    if (lane == 0) {
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1;
+        nl_wait(&bars[B_VEMPTY + s], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&bars[B_VFULL + s], C::V_BYTES);
+        bulk_g2s(smem + C::OFF_V + s * C::V_BYTES, Vp + ((size_t)b * nkb + (kb_lo + it)) * C::V_BYTES, C::V_BYTES,
+                 &bars[B_VFULL + s]);
+      }
+    }
+  } else if (warp == NL_SOFTMAX_WARPS) {
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc_qk = idesc_bf16(NL_BM, NL_BN);
       constexpr uint32_t idesc_pv = idesc_bf16(NL_BM, D);
       const uint32_t q_addr = smem_u32(smem + C::OFF_Q);
       nl_wait(&bars[B_QFULL], 0);
-      for (int it = 0; it <= n_it; ++it) {
-        if (it < n_it) {  // S[it & 1] = Q K_it^T
-          const int s = it & 1;
-          nl_wait(&bars[B_KFULL + s], (uint32_t)(it >> 1) & 1u);
-          tc_fence_after();
-          const uint32_t k_addr = smem_u32(smem + C::OFF_K + s * C::K_BYTES);
+      // S[it % NL_SBUF] = Q K_it^T
+      auto issue_qk = [&](int it) {
+        const int s = it & 1;
+        nl_wait(&bars[B_KFULL + s], (uint32_t)(it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(smem + C::OFF_K + s * C::K_BYTES);
+        const uint32_t d_tmem = tmem_s + (uint32_t)(it % NL_SBUF) * NL_BN;
 #pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk) {
-            const uint64_t ad = smem_desc_sw128(q_addr + (kk >> 2) * (NL_BM * 128) + (kk & 3) * 32);
-            const uint64_t bd = smem_desc_sw128(k_addr + (kk >> 2) * (NL_BN * 128) + (kk & 3) * 32);
-            tc_mma(tmem_s + (uint32_t)(it & 1) * NL_BN, ad, bd, idesc_qk, kk > 0);
-          }
-          tc_commit(&bars[B_SFULL + (it & 1)]);
-          tc_commit(&bars[B_KEMPTY + s]);
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint64_t ad = smem_desc_sw128(q_addr + (kk >> 2) * (NL_BM * 128) + (kk & 3) * 32);
+          const uint64_t bd = smem_desc_sw128(k_addr + (kk >> 2) * (NL_BN * 128) + (kk & 3) * 32);
+          tc_mma(d_tmem, ad, bd, idesc_qk, kk > 0);
         }
-        if (it >= 1) {  // O += P_jt V_jt
-          const int jt = it - 1, s = jt & 1;
-          const uint32_t ph = (uint32_t)(jt >> 1) & 1u;
-          nl_wait(&bars[B_VFULL + s], ph);
-          nl_wait(&bars[B_PFULL + s], ph);
-          tc_fence_after();
-          const uint32_t p_addr = smem_u32(smem + C::OFF_P + s * C::P_BYTES);
-          const uint32_t v_addr = smem_u32(smem + C::OFF_V + s * C::V_BYTES);
+        tc_commit(&bars[B_SFULL + (it % NL_SBUF)]);
+        tc_commit(&bars[B_KEMPTY + s]);
+      };
+      for (int it = 0; it < NL_SBUF - 1 && it < n_it; ++it) issue_qk(it);
+      for (int jt = 0; jt < n_it; ++jt) {  // O += P_jt V_jt, then the Q K^T NL_SBUF - 1 steps ahead
+        const int s = jt & 1;
+        const uint32_t ph = (uint32_t)(jt >> 1) & 1u;
+        nl_wait(&bars[B_VFULL + s], ph);
+        nl_wait(&bars[B_PFULL + s], ph);
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(smem + C::OFF_P + s * C::P_BYTES);
+        const uint32_t v_addr = smem_u32(smem + C::OFF_V + s * C::V_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < NL_BN / 16; ++kk)
-            tc_mma(tmem_o, smem_desc_sw128(p_addr + kk * 32), smem_desc_sw128(v_addr + kk * 32), idesc_pv,
-                   (jt > 0 || kk > 0) ? 1u : 0u);
-          tc_commit(&bars[B_PVDONE + s]);
-          tc_commit(&bars[B_VEMPTY + s]);
-        }
+        for (int kk = 0; kk < NL_BN / 16; ++kk)
+          tc_mma(tmem_o, smem_desc_sw128(p_addr + kk * 32), smem_desc_sw128(v_addr + kk * 32), idesc_pv,
+                 (jt > 0 || kk > 0) ? 1u : 0u);
+        tc_commit(&bars[B_PVDONE + s]);
+        tc_commit(&bars[B_VEMPTY + s]);
+        if (jt + NL_SBUF - 1 < n_it) issue_qk(jt + NL_SBUF - 1);
       }
     }
   } else {
-    // ===== softmax / correction / epilogue: thread = query row, warp = TMEM lane quadrant =====
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const int row = tid;  // 0..127
-    float m_ref = 0.f, l = 0.f;
+    // ===== softmax / correction / epilogue =====
+    // thread = (query row, half of the key columns); warps w and w + 4 share TMEM lane quadrant w & 3
+    const int quad = warp & 3, half = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const int row = quad * 32 + lane;  // 0..127
+    const uint32_t pair_bar = 1 + quad;  // named barrier of the two warps of a quadrant
+    float m_ref = 0.f, l = 0.f;          // m_ref in units of the raw logits
     for (int it = 0; it < n_it; ++it) {
-      const int buf = it & 1;
-      nl_wait(&bars[B_SFULL + buf], (uint32_t)(it >> 1) & 1u);
+      const int buf = it & 1, sbuf = it % NL_SBUF;
+      nl_wait(&bars[B_SFULL + sbuf], (uint32_t)(it / NL_SBUF) & 1u);
       tc_fence_after();
-      uint32_t s0[32], s1[32];
-      tmem_ld32(tmem_s + lane_base + buf * NL_BN, s0);
-      tmem_ld32(tmem_s + lane_base + buf * NL_BN + 32, s1);
+      uint32_t sr[32];
+      tmem_ld32(tmem_s + lane_base + sbuf * NL_BN + half * 32, sr);
       tmem_wait_ld();
-      const int nvalid = HW - (kb_lo + it) * NL_BN;  // keys of this step that exist (>= 64: all)
-      float mx = -INFINITY;
+      const int nvalid = HW - (kb_lo + it) * NL_BN - half * 32;  // columns of this thread that are real keys
+      if (nvalid < 32) {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        float v0 = __uint_as_float(s0[c]) * sl2, v1 = __uint_as_float(s1[c]) * sl2;
-        if (c >= nvalid) v0 = -INFINITY;
-        if (c + 32 >= nvalid) v1 = -INFINITY;
-        s0[c] = __float_as_uint(v0);
-        s1[c] = __float_as_uint(v1);
-        mx = fmaxf(mx, fmaxf(v0, v1));
+        for (int c = 0; c < 32; ++c)
+          if (c >= nvalid) sr[c] = __float_as_uint(-INFINITY);
       }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 32; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], __uint_as_float(sr[c]));
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      // row maximum over both halves (double-buffered exchange: one pair barrier per step)
+      xch[(buf * 2 + half) * NL_BM + row] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      mx = fmaxf(mx, xch[(buf * 2 + (half ^ 1)) * NL_BM + row]);
       if (it == 0) {
         m_ref = mx;
       } else {
-        const bool grow = mx > m_ref + NL_RESCALE;
+        const bool grow = (mx - m_ref) * sl2 > NL_RESCALE;
         if (__any_sync(0xffffffffu, grow)) {
           // O must be quiescent: P V of the previous step done (it was issued after this step's Q K^T)
           nl_wait(&bars[B_PVDONE + ((it - 1) & 1)], (uint32_t)((it - 1) >> 1) & 1u);
           tc_fence_after();
           const float m_new = grow ? mx : m_ref;
-          const float alpha = fast_exp2(m_ref - m_new);
+          const float alpha = fast_exp2((m_ref - m_new) * sl2);
           l *= alpha;
           m_ref = m_new;
 #pragma unroll 1
-          for (int ch = 0; ch < D / 32; ++ch) {
+          for (int ch = 0; ch < D / 64; ++ch) {  // this warp's half of the channels
             uint32_t o[32];
-            tmem_ld32(tmem_o + lane_base + ch * 32, o);
+            const uint32_t addr = tmem_o + lane_base + half * (D / 2) + ch * 32;
+            tmem_ld32(addr, o);
             tmem_wait_ld();
 #pragma unroll
             for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-            tmem_st32(tmem_o + lane_base + ch * 32, o);
+            tmem_st32(addr, o);
           }
           tmem_wait_st();
         }
       }
-      // P = exp2(s - m_ref) as bf16 into the swizzled A tile; l sums what the tensor core will see
+      // P = exp2((s - m_ref) * sl2) as bf16 into the swizzled A tile (free once P V of step it - 2 is done)
+      const float neg_m = -m_ref * sl2;
+      if (it >= 2) nl_wait(&bars[B_PVDONE + buf], (uint32_t)((it - 2) >> 1) & 1u);
       uint8_t* p_row = smem + C::OFF_P + buf * C::P_BYTES + row * 128;
-      float lsum = 0.f;
+      float ls4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
+      for (int c8 = 0; c8 < 4; ++c8) {
         uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int c = c8 * 8 + e * 2;
-          const float x0 = __uint_as_float(c < 32 ? s0[c & 31] : s1[c & 31]);
-          const float x1 = __uint_as_float(c + 1 < 32 ? s0[(c + 1) & 31] : s1[(c + 1) & 31]);
-          w[e] = pack_bf16(fast_exp2(x0 - m_ref), fast_exp2(x1 - m_ref));
-          lsum += bf16_lo(w[e]) + bf16_hi(w[e]);
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c]), sl2, neg_m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c + 1]), sl2, neg_m));
+          ls4[e] += p0 + p1;
+          w[e] = pack_bf16(p0, p1);
         }
-        *reinterpret_cast<uint4*>(p_row + ((c8 ^ (row & 7)) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(p_row + (((half * 4 + c8) ^ (row & 7)) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      l += lsum;
+      l += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
       fence_async_smem();  // generic-proxy writes of P -> visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(&bars[B_PFULL + buf]);
     }
-    // epilogue
+    // epilogue: total row sum, then this warp's half of the channels
+    xch[((n_it & 1) * 2 + half) * NL_BM + row] = l;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    l += xch[((n_it & 1) * 2 + (half ^ 1)) * NL_BM + row];
     nl_wait(&bars[B_PVDONE + ((n_it - 1) & 1)], (uint32_t)((n_it - 1) >> 1) & 1u);
     tc_fence_after();
     const int p = qb * NL_BM + row;
     const float inv = nsplit == 1 ? 1.f / l : 1.f;
-    if (nsplit > 1) {
-      const size_t prow = ((size_t)z * B + b) * ((size_t)nqb * NL_BM) + p;
-      part_ml[prow * 2 + 0] = m_ref;
+    const size_t prow = ((size_t)z * B + b) * ((size_t)nqb * NL_BM) + p;
+    if (nsplit > 1 && half == 0) {
+      part_ml[prow * 2 + 0] = m_ref * sl2;  // log2 units
       part_ml[prow * 2 + 1] = l;
     }
 #pragma unroll 1
-    for (int ch = 0; ch < D / 32; ++ch) {
+    for (int ch = 0; ch < D / 64; ++ch) {
       uint32_t o[32];
-      tmem_ld32(tmem_o + lane_base + ch * 32, o);
+      const int d0 = half * (D / 2) + ch * 32;
+      tmem_ld32(tmem_o + lane_base + d0, o);
       tmem_wait_ld();
       if (nsplit > 1) {
-        float4* dst = reinterpret_cast<float4*>(part_o + (((size_t)z * B + b) * ((size_t)nqb * NL_BM) + p) * D + ch * 32);
+        float4* dst = reinterpret_cast<float4*>(part_o + prow * D + d0);
 #pragma unroll
         for (int c = 0; c < 8; ++c)
           dst[c] = make_float4(__uint_as_float(o[4 * c]), __uint_as_float(o[4 * c + 1]), __uint_as_float(o[4 * c + 2]),
                                __uint_as_float(o[4 * c + 3]));
       } else if (p < HW) {
         if (out_cl) {
-          OutT* dst = y + ((size_t)b * HW + p) * D + ch * 32;
+          OutT* dst = y + ((size_t)b * HW + p) * D + d0;
 #pragma unroll
           for (int c = 0; c < 32; ++c) nl_store1(dst + c, __uint_as_float(o[c]) * inv);
         } else {
-          OutT* dst = y + ((size_t)b * D + ch * 32) * HW + p;
+          OutT* dst = y + ((size_t)b * D + d0) * HW + p;
 #pragma unroll
           for (int c = 0; c < 32; ++c) nl_store1(dst + (size_t)c * HW, __uint_as_float(o[c]) * inv);
         }
@@ -366,7 +394,7 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == NL_SOFTMAX_WARPS) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TMEM_COLS)
                  : "memory");
@@ -504,7 +532,7 @@ cudaError_t nl_launch_attn(const NlLayout& a, uint8_t* ws, OutT* y, int B, int H
   using C = NlCfg<D>;
   cudaError_t e = cudaFuncSetAttribute(nl_attn_kernel<D, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
   if (e != cudaSuccess) return e;
-  nl_attn_kernel<D, OutT><<<dim3(a.nqb, B, nsplit), 192, C::SMEM, stream>>>(
+  nl_attn_kernel<D, OutT><<<dim3(a.nqb, B, nsplit), NL_THREADS, C::SMEM, stream>>>(
       ws, ws + a.off_k, ws + a.off_v, y, reinterpret_cast<float*>(ws + a.off_po),
       reinterpret_cast<float*>(ws + a.off_pml), HW, a.nqb, a.nkb, nsplit, sl2, out_cl);
   return cudaGetLastError();

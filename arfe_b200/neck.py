@@ -4,20 +4,30 @@ reduce_convs2.{i}.conv, refine.{g,theta,phi,conv_out}.conv.
 
 The gather (all levels -> refine level, mean) and the gated residual
 ``x + up(bsf) * (tanh(relu(c1)) + tanh(relu(c2)))`` run in libarfe_b200.so;
-the 256->1 3x3 gate convolutions and the NonLocal2D refine are dense
-contractions that stay on cuDNN/cuBLAS.
+the NonLocal2D refine's attention is one tensor-core kernel (tcgen05) when its operands may be
+bf16, and both C -> 1 gate convolutions of every level one pass over the pyramid (forward); the
+other convolutions are library calls.
 """
 import torch
 import torch.nn as nn
 
 from ._compat import ConvModule, xavier_init
 from . import _lib as L
-from .functional import FPNLink, fpn_apply, fpn_gate_conv, fpn_gather
+from .functional import FPNLink, fpn_apply, fpn_gate_conv, fpn_gather, nonlocal_attention
 
 
 class NonLocal2D(nn.Module):
-    """mmdet/ops/non_local.py:6-105 (embedded gaussian / dot product).  Plain
-    PyTorch: out of the kernel scope of this tier ("next" row 1)."""
+    """mmdet/ops/non_local.py:6-105 (embedded gaussian / dot product), same constructor and
+    parameter names (g / theta / phi / conv_out).
+
+    ``fused_attention`` selects how softmax(theta_x . phi_x) . g_x (:65-69, :98-101) runs:
+      True    one tensor-core attention kernel (arfe_nonlocal_attention_forward): operands rounded
+              to bf16, fp32 accumulation and softmax; the HW x HW weight matrix is never materialised;
+      False   the reference's two matmuls and softmax through the library;
+      'auto'  (default) fused for bfloat16 activations, library for float32 -- an fp32 module keeps
+              the reference's fp32 arithmetic unless the caller opts into bf16 operands
+              (``arfe_b200.optimize_detector(model, fused_attention=True)``).
+    The 1x1 convolutions stay library GEMMs either way."""
 
     def __init__(self, in_channels, reduction=2, use_scale=True, conv_cfg=None,
                  norm_cfg=None, mode='embedded_gaussian'):
@@ -31,7 +41,20 @@ class NonLocal2D(nn.Module):
         self.phi = ConvModule(in_channels, self.inter_channels, kernel_size=1, act_cfg=None)
         self.conv_out = ConvModule(self.inter_channels, in_channels, kernel_size=1,
                                    conv_cfg=conv_cfg, norm_cfg=norm_cfg, act_cfg=None)
+        self.fused_attention = 'auto'
         self.init_weights()
+
+    def _use_fused(self, x):
+        if self.fused_attention is False or self.mode != 'embedded_gaussian':
+            return False
+        ok = x.is_cuda and self.inter_channels in (64, 128, 256) and \
+            x.dtype in (torch.float32, torch.bfloat16)
+        if self.fused_attention is True:
+            if not ok:
+                raise RuntimeError("NonLocal2D(fused_attention=True) needs CUDA float32/bfloat16 "
+                                   "activations and inter_channels in (64, 128, 256)")
+            return True
+        return ok and x.dtype == torch.bfloat16
 
     def init_weights(self, std=0.01, zeros_init=True):
         for m in [self.g, self.theta, self.phi]:
@@ -45,6 +68,10 @@ class NonLocal2D(nn.Module):
 
     def forward(self, x):
         n, _, h, w = x.shape
+        if self._use_fused(x):
+            scale = 1.0 / self.inter_channels ** 0.5 if self.use_scale else 1.0
+            y = nonlocal_attention(self.theta(x), self.phi(x), self.g(x), scale)
+            return x + self.conv_out(y)
         g_x = self.g(x).reshape(n, self.inter_channels, -1).permute(0, 2, 1)
         theta_x = self.theta(x).reshape(n, self.inter_channels, -1).permute(0, 2, 1)
         phi_x = self.phi(x).reshape(n, self.inter_channels, -1)

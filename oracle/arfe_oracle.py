@@ -415,6 +415,27 @@ def wfpn_apply(inputs, bsf, gate1, gate2):
     return tuple(outs)
 
 
+def nonlocal_attention(theta, phi, g, use_scale=False, round_operands=None):
+    """ops/non_local.py:78-101 between the 1x1 convolutions and conv_out: theta, phi, g are the
+    [N, C, H, W] outputs of self.theta / self.phi / self.g; returns y [N, C, H, W] (:101).
+    embedded_gaussian (:65-69) with the optional 1/sqrt(C) scale.  round_operands (a torch dtype)
+    rounds the three operands first -- the arithmetic a reduced-precision tensor-core kernel is
+    entitled to -- and computes everything else in fp32 like the reference."""
+    n, c, h, w = theta.shape
+    f = torch.float32
+    if round_operands is not None:
+        theta, phi, g = (t.to(round_operands) for t in (theta, phi, g))
+    g_x = g.to(f).reshape(n, c, -1).permute(0, 2, 1)              # :83-84
+    theta_x = theta.to(f).reshape(n, c, -1).permute(0, 2, 1)      # :87-89
+    phi_x = phi.to(f).reshape(n, c, -1)                           # :92
+    pw = torch.matmul(theta_x, phi_x)                             # :67
+    if use_scale:
+        pw = pw / theta_x.shape[-1] ** 0.5                        # :68-70
+    pw = pw.softmax(dim=-1)                                       # :71
+    y = torch.matmul(pw, g_x)                                     # :99
+    return y.permute(0, 2, 1).contiguous().reshape(n, c, h, w)    # :101
+
+
 class NonLocal2D(nn.Module):
     """ops/non_local.py:22-105 as configured by the neck
     (wfpn_dual_spatial.py:78-83): reduction=1, use_scale=False,
@@ -434,12 +455,7 @@ class NonLocal2D(nn.Module):
 
     def forward(self, x):
         n, c, h, w = x.shape
-        g_x = self.g(x).view(n, c, -1).permute(0, 2, 1)
-        theta_x = self.theta(x).view(n, c, -1).permute(0, 2, 1)
-        phi_x = self.phi(x).view(n, c, -1)
-        pw = torch.matmul(theta_x, phi_x).softmax(dim=-1)
-        y = torch.matmul(pw, g_x).permute(0, 2, 1).contiguous().reshape(
-            n, c, h, w)
+        y = nonlocal_attention(self.theta(x), self.phi(x), self.g(x))
         return x + self.conv_out(y)
 
 

@@ -1,0 +1,18 @@
+"""A few calls of the fused NonLocal2D attention at the bench shape (for ncu)."""
+import os
+import sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch
+import arfe_b200 as A
+
+B, D, H, W = 2, 256, 50, 84
+layout = sys.argv[1] if len(sys.argv) > 1 else "nhwc"
+nsplit = int(sys.argv[2]) if len(sys.argv) > 2 else None
+g = torch.Generator(device="cuda").manual_seed(0)
+ts = [torch.randn(B, D, H, W, generator=g, device="cuda") * (0.25 if i < 2 else 1.0) for i in range(3)]
+if layout == "nhwc":
+    ts = [t.contiguous(memory_format=torch.channels_last) for t in ts]
+for _ in range(4):
+    y = A.nonlocal_attention(*ts, 1.0, nsplit)
+torch.cuda.synchronize()
+print(float(y.float().abs().mean()))

@@ -107,6 +107,15 @@ def main():
         res[f"keep_{int(thr * 10)}"] = O.nms(dets, thr, "ref").numpy()
     np.savez_compressed(os.path.join(HERE, "nms_small.npz"), **res)
 
+    # 6. NonLocal2D attention (restated non_local.py:65-101; torch CPU executes the arithmetic)
+    gen = torch.Generator().manual_seed(27)
+    th = torch.randn(2, 64, 9, 11, generator=gen) * 0.4
+    ph = torch.randn(2, 64, 9, 11, generator=gen) * 0.4
+    gx = torch.randn(2, 64, 9, 11, generator=gen)
+    np.savez_compressed(os.path.join(HERE, "nonlocal_small.npz"), theta=th.numpy(), phi=ph.numpy(), g=gx.numpy(),
+                        y=O.nonlocal_attention(th, ph, gx).numpy(),
+                        y_scaled=O.nonlocal_attention(th, ph, gx, use_scale=True).numpy())
+
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

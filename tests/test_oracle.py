@@ -156,3 +156,25 @@ def test_oracle_nms_matches_reference_and_golden(oracle):
     lists = [torch.rand(3, 5), torch.zeros(0, 5), torch.rand(2, 4)]
     r = oracle.bbox2roi(lists)
     assert r.shape == (5, 5) and r[:, 0].tolist() == [0, 0, 0, 2, 2]
+
+
+def test_nonlocal_attention_golden_and_module(oracle):
+    """The restated NonLocal2D attention (non_local.py:65-101) reproduces its committed fixture,
+    equals a literal transcription of the reference's forward, and rounding the operands to bf16
+    moves it by no more than the bound the tensor-core kernel is tested against."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nonlocal_small.npz"))
+    th, ph, gx = (torch.from_numpy(z[k]) for k in ("theta", "phi", "g"))
+    assert torch.equal(oracle.nonlocal_attention(th, ph, gx), torch.from_numpy(z["y"]))
+    assert torch.equal(oracle.nonlocal_attention(th, ph, gx, use_scale=True), torch.from_numpy(z["y_scaled"]))
+    n, c, h, w = th.shape
+    g_x = gx.view(n, c, -1).permute(0, 2, 1)
+    theta_x = th.view(n, c, -1).permute(0, 2, 1)
+    phi_x = ph.view(n, c, -1)
+    pw = torch.matmul(theta_x, phi_x)
+    pw /= theta_x.shape[-1] ** 0.5
+    pw = pw.softmax(dim=-1)
+    y = torch.matmul(pw, g_x).permute(0, 2, 1).contiguous().reshape(n, c, h, w)
+    assert torch.equal(y, torch.from_numpy(z["y_scaled"]))
+    yb = oracle.nonlocal_attention(th, ph, gx, round_operands=torch.bfloat16)
+    assert (yb - torch.from_numpy(z["y"])).abs().max() <= 1e-2 * torch.from_numpy(z["y"]).abs().max()
