@@ -19,15 +19,15 @@
 //  nl_attn_kernel      one CTA = 128 query positions of one image (x one slice of the keys when the
 //                      key range is split to fill the SMs).  Warp roles:
 //                        warps 0-7  softmax, thread = (query row, half of the 64 key columns): S (TMEM) ->
-//                                   registers, running max / sum, P (bf16) -> smem; rescale of O in TMEM
+//                                   registers, running max / sum, P (bf16) -> TMEM over S; rescale of O in TMEM
 //                                   only when a row maximum grew by more than 2^8 (exact: the maximum
 //                                   used as the exponent's reference is arbitrary); epilogue O / l -> y
 //                        warp 8     one lane issues tcgen05.mma: S = Q K^T (M128 N64 K16 x D/16) and
-//                                   O += P V (M128 N=D K16 x 4), accumulators in tensor memory;
+//                                   O += P V (M128 N=D K16 x 4, A = P from TMEM), accumulators in TMEM;
 //                                   tcgen05.commit -> mbarriers
 //                        warps 9,10 one lane each issues the bulk copies of Q + the K ring / the V ring
-//                      Four S tiles live in TMEM (Q K^T runs three steps ahead of P V) and P is double
-//                      buffered in shared memory, so the tensor pipe never waits for a softmax hand-off.
+//                      Four S tiles live in TMEM (Q K^T runs three steps ahead of P V); P overwrites
+//                      its own S tile, so the softmax weights never touch shared memory.
 //  nl_combine_kernel   (key range split only) merges the partial (O, max, sum) triples.
 //
 // Arithmetic: operands rounded to bf16 (round to nearest even), products exact, fp32 accumulation in
@@ -52,12 +52,10 @@ struct NlCfg {
   static constexpr int Q_BYTES = NL_BM * D * 2;
   static constexpr int K_BYTES = NL_BN * D * 2;
   static constexpr int V_BYTES = D * NL_BN * 2;
-  static constexpr int P_BYTES = NL_BM * NL_BN * 2;
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + Q_BYTES;
   static constexpr int OFF_V = OFF_K + 2 * K_BYTES;
-  static constexpr int OFF_P = OFF_V + 2 * V_BYTES;
-  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+  static constexpr int OFF_BAR = OFF_V + 2 * V_BYTES;
   static constexpr int OFF_XCH = OFF_BAR + 256;      // row max / sum exchange between the two column halves
   static constexpr int SMEM = OFF_XCH + 2 * 2 * NL_BM * 4;  // the kernel has no static shared memory: base 1024-aligned
   static constexpr int TMEM_USED = D + NL_SBUF * NL_BN;  // O | S0 .. S3
@@ -83,6 +81,19 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the same with A read from tensor memory (row m in lane m, elements 2 c and 2 c + 1 of the row in
+// the low and high half of 32-bit column c): D[tmem] (+)= A[tmem] . B[smem]^T
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart
@@ -120,6 +131,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
       "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -162,6 +181,14 @@ __device__ __forceinline__ void nl_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Phase-skip knob of the -DARFE_PROFILE build (scripts/nonlocal_knobs.py): 1 no K / V copies after the
+// first two steps, 2 no softmax arithmetic, 4 no MMAs.  Folds to false in the shipped library.
+#ifdef ARFE_PROFILE
+#define NL_DBG(bit) ((dbg & (bit)) != 0)
+#else
+#define NL_DBG(bit) false
+#endif
+
 // barrier indices
 enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 3, B_VFULL = 5, B_VEMPTY = 7, B_SFULL = 9, B_PFULL = 13, B_PVDONE = 15, B_COUNT = 17 };
 
@@ -180,7 +207,7 @@ template <int D, typename OutT>
 __global__ void __launch_bounds__(NL_THREADS, 1)
 nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, const uint8_t* __restrict__ Vp,
                OutT* __restrict__ y, float* __restrict__ part_o, float* __restrict__ part_ml, int HW, int nqb,
-               int nkb, int nsplit, float sl2, int out_cl) {
+               int nkb, int nsplit, float sl2, int out_cl, int dbg) {
   using C = NlCfg<D>;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128-byte swizzle atoms need a 1024-byte aligned base
@@ -195,7 +222,7 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
 
   if (tid == 0) {
     for (int i = 0; i < B_COUNT; ++i)
-      mbar_init(&bars[i], (i == B_PFULL || i == B_PFULL + 1) ? NL_SOFTMAX_WARPS * 32 : 1);
+      mbar_init(&bars[i], (i == B_PFULL || i == B_PFULL + 1) ? NL_SOFTMAX_WARPS : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == NL_SOFTMAX_WARPS) {  // tensor memory: O | S0 | S1
@@ -220,6 +247,7 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
       for (int it = 0; it < n_it; ++it) {
         const int s = it & 1;
         nl_wait(&bars[B_KEMPTY + s], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        if (NL_DBG(1) && it >= 2) { mbar_arrive(&bars[B_KFULL + s]); continue; }
         mbar_arrive_expect_tx(&bars[B_KFULL + s], C::K_BYTES);
         bulk_g2s(smem + C::OFF_K + s * C::K_BYTES, Kp + ((size_t)b * nkb + (kb_lo + it)) * C::K_BYTES, C::K_BYTES,
                  &bars[B_KFULL + s]);
@@ -231,6 +259,7 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
       for (int it = 0; it < n_it; ++it) {
         const int s = it & 1;
         nl_wait(&bars[B_VEMPTY + s], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        if (NL_DBG(1) && it >= 2) { mbar_arrive(&bars[B_VFULL + s]); continue; }
         mbar_arrive_expect_tx(&bars[B_VFULL + s], C::V_BYTES);
         bulk_g2s(smem + C::OFF_V + s * C::V_BYTES, Vp + ((size_t)b * nkb + (kb_lo + it)) * C::V_BYTES, C::V_BYTES,
                  &bars[B_VFULL + s]);
@@ -254,7 +283,7 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint64_t ad = smem_desc_sw128(q_addr + (kk >> 2) * (NL_BM * 128) + (kk & 3) * 32);
           const uint64_t bd = smem_desc_sw128(k_addr + (kk >> 2) * (NL_BN * 128) + (kk & 3) * 32);
-          tc_mma(d_tmem, ad, bd, idesc_qk, kk > 0);
+          if (!NL_DBG(4)) tc_mma(d_tmem, ad, bd, idesc_qk, kk > 0);
         }
         tc_commit(&bars[B_SFULL + (it % NL_SBUF)]);
         tc_commit(&bars[B_KEMPTY + s]);
@@ -266,12 +295,13 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
         nl_wait(&bars[B_VFULL + s], ph);
         nl_wait(&bars[B_PFULL + s], ph);
         tc_fence_after();
-        const uint32_t p_addr = smem_u32(smem + C::OFF_P + s * C::P_BYTES);
+        const uint32_t p_tmem = tmem_s + (uint32_t)(jt % NL_SBUF) * NL_BN;  // P_jt lies over S_jt
         const uint32_t v_addr = smem_u32(smem + C::OFF_V + s * C::V_BYTES);
 #pragma unroll
         for (int kk = 0; kk < NL_BN / 16; ++kk)
-          tc_mma(tmem_o, smem_desc_sw128(p_addr + kk * 32), smem_desc_sw128(v_addr + kk * 32), idesc_pv,
-                 (jt > 0 || kk > 0) ? 1u : 0u);
+          if (!NL_DBG(4))
+            tc_mma_ts(tmem_o, p_tmem + kk * 8, smem_desc_sw128(v_addr + kk * 32), idesc_pv,
+                      (jt > 0 || kk > 0) ? 1u : 0u);
         tc_commit(&bars[B_PVDONE + s]);
         tc_commit(&bars[B_VEMPTY + s]);
         if (jt + NL_SBUF - 1 < n_it) issue_qk(jt + NL_SBUF - 1);
@@ -289,6 +319,12 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
       const int buf = it & 1, sbuf = it % NL_SBUF;
       nl_wait(&bars[B_SFULL + sbuf], (uint32_t)(it / NL_SBUF) & 1u);
       tc_fence_after();
+      if (NL_DBG(2)) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_PFULL + buf]);
+        continue;
+      }
       uint32_t sr[32];
       tmem_ld32(tmem_s + lane_base + sbuf * NL_BN + half * 32, sr);
       tmem_wait_ld();
@@ -331,28 +367,24 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
           tmem_wait_st();
         }
       }
-      // P = exp2((s - m_ref) * sl2) as bf16 into the swizzled A tile (free once P V of step it - 2 is done)
+      // P = exp2((s - m_ref) * sl2) as bf16 pairs over this row's S columns in tensor memory (both
+      // halves have their S values in registers since the pair barrier): the A operand of P V
       const float neg_m = -m_ref * sl2;
-      if (it >= 2) nl_wait(&bars[B_PVDONE + buf], (uint32_t)((it - 2) >> 1) & 1u);
-      uint8_t* p_row = smem + C::OFF_P + buf * C::P_BYTES + row * 128;
       float ls4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pw[16];
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        uint32_t w[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = c8 * 8 + e * 2;
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c]), sl2, neg_m));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c + 1]), sl2, neg_m));
-          ls4[e] += p0 + p1;
-          w[e] = pack_bf16(p0, p1);
-        }
-        *reinterpret_cast<uint4*>(p_row + (((half * 4 + c8) ^ (row & 7)) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
+      for (int e = 0; e < 16; ++e) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(sr[2 * e]), sl2, neg_m));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(sr[2 * e + 1]), sl2, neg_m));
+        ls4[e & 3] += p0 + p1;
+        pw[e] = pack_bf16(p0, p1);
       }
+      tmem_st16(tmem_s + lane_base + sbuf * NL_BN + half * 16, pw);
       l += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
-      fence_async_smem();  // generic-proxy writes of P -> visible to the tensor core (async proxy)
+      tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&bars[B_PFULL + buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_PFULL + buf]);
     }
     // epilogue: total row sum, then this warp's half of the channels
     xch[((n_it & 1) * 2 + half) * NL_BM + row] = l;
@@ -534,7 +566,8 @@ cudaError_t nl_launch_attn(const NlLayout& a, uint8_t* ws, OutT* y, int B, int H
   if (e != cudaSuccess) return e;
   nl_attn_kernel<D, OutT><<<dim3(a.nqb, B, nsplit), NL_THREADS, C::SMEM, stream>>>(
       ws, ws + a.off_k, ws + a.off_v, y, reinterpret_cast<float*>(ws + a.off_po),
-      reinterpret_cast<float*>(ws + a.off_pml), HW, a.nqb, a.nkb, nsplit, sl2, out_cl);
+      reinterpret_cast<float*>(ws + a.off_pml), HW, a.nqb, a.nkb, nsplit, sl2, out_cl,
+      ARFE_KNOB_ENV("ARFE_NL_DBG", 0));
   return cudaGetLastError();
 }
 

@@ -319,6 +319,62 @@ def kernel_table(alg, per_ms, peak):
                 "frac": round(alg[n] / (per_ms[n] * 1e-3) / 1e9 / peak, 3)} for n in per_ms}
 
 
+def tensor_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["bf16_tflops"]), "measured burst cuBLAS bf16 (MEASURED_PEAKS.json)"
+    except Exception:
+        return 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def nonlocal_refine_block(dev, verify=True):
+    """SURVEY 8(f) row 1, next to the path: the NonLocal2D attention of the refine level of configs[1]
+    (2 images, 256 channels, 50 x 84 positions) -- fused tensor-core kernel (pack + attention + merge,
+    the whole arfe_nonlocal_attention_forward call) against the reference's two matmuls + softmax through
+    the library in fp32, both device-timed on resident inputs; checked against the oracle."""
+    import arfe_b200 as A
+    B, D, H, W = 2, 256, 50, 84
+    g = torch.Generator().manual_seed(5)
+    host = [torch.randn(B, D, H, W, generator=g) * s for s in (0.25, 0.25, 1.0)]
+    ts = [t.to(dev).contiguous(memory_format=torch.channels_last) for t in host]
+
+    def lib_ref():
+        th = ts[0].reshape(B, D, -1).permute(0, 2, 1)
+        pw = torch.matmul(th, ts[1].reshape(B, D, -1)).softmax(dim=-1)
+        return torch.matmul(pw, ts[2].reshape(B, D, -1).permute(0, 2, 1))
+
+    def timeit(fn, n=20):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    t_f = timeit(lambda: A.nonlocal_attention(*ts))
+    t_l = timeit(lib_ref, 5)
+    flops = 4.0 * B * (H * W) ** 2 * D
+    peak, src = tensor_peak()
+    out = {"shape": f"B={B} C={D} {H}x{W} ({H * W} positions), fp32 in/out, operands bf16, channels-last",
+           "fused_us": round(t_f * 1e3, 1), "library_fp32_us": round(t_l * 1e3, 1),
+           "tflops": round(flops / (t_f * 1e-3) / 1e12, 1), "peak_tflops": peak, "peak_source": src,
+           "frac": round(flops / (t_f * 1e-3) / 1e12 / peak, 3), "gpu_launches_per_call": 3}
+    if verify:
+        from oracle import arfe_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        want = O.nonlocal_attention(*host)
+        got = A.nonlocal_attention(*ts).float().cpu()
+        err = float((got - want).abs().max() / want.abs().max())
+        out["verified"] = bool(err <= 1e-2 and torch.isfinite(got).all())
+        out["max_err_over_max_ref"] = round(err, 5)
+        out["tolerance"] = "|err| <= 1e-2 max|ref| (bf16 operands, north_star's bf16 bound) against oracle.nonlocal_attention"
+    return out
+
+
 def other_configs_block(dev, peak):
     """Compact device-timed numbers of the other BASELINE configs (the full lines come
     from --config N): tracked by the driver round over round."""
@@ -472,6 +528,10 @@ def run_ours(args, rank, local_rank, world):
             line["verification"] = verification
         if main_cfg and world == 1 and not args.no_other_configs:
             line["other_configs"] = other_configs_block(dev, peak)
+            try:
+                line["next_rows"] = {"nonlocal_refine": nonlocal_refine_block(dev, verify=not args.no_verify)}
+            except Exception as ex:  # pragma: no cover
+                line["next_rows"] = {"nonlocal_refine": {"error": str(ex)[:200]}}
         if main_cfg and world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(line), flush=True)

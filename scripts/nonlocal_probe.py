@@ -120,6 +120,23 @@ def run_time():
         e1.record()
         torch.cuda.synchronize()
         t = e0.elapsed_time(e1) / n
+        # the same call replayed as a CUDA graph: device time without the Python / ctypes launch path
+        gr = torch.cuda.CUDAGraph()
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            A.nonlocal_attention(theta, phi, gx, 1.0, nsplit)
+            with torch.cuda.graph(gr, stream=st):
+                A.nonlocal_attention(theta, phi, gx, 1.0, nsplit)
+        torch.cuda.current_stream().wait_stream(st)
+        gr.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            gr.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        tg = e0.elapsed_time(e1) / n
         e0.record()
         for _ in range(n):
             reference(theta, phi, gx, False)
@@ -128,7 +145,8 @@ def run_time():
         tr = e0.elapsed_time(e1) / n
         B, D, H, W = theta.shape
         flops = 4.0 * B * (H * W) ** 2 * D
-        print(f"{case}: fused {t * 1e3:.1f} us ({flops / t / 1e9:.1f} TFLOP/s)   torch eager {tr * 1e3:.1f} us", flush=True)
+        print(f"{case}: fused {t * 1e3:.1f} us, as a graph {tg * 1e3:.1f} us ({flops / tg / 1e9:.1f} TFLOP/s)   "
+              f"torch eager {tr * 1e3:.1f} us", flush=True)
 
 
 if __name__ == "__main__":
