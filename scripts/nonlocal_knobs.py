@@ -1,5 +1,6 @@
 """Phase-skip decomposition of the fused NonLocal2D attention (profile build only):
-ARFE_NL_DBG bits: 1 no K / V copies, 2 no softmax arithmetic, 4 no MMAs.  Results are garbage."""
+ARFE_NL_DBG bits: 1 no K / V copies, 2 no softmax arithmetic, 4 no MMAs, 16 no row-max exchange between the
+column halves, 32 no ex2, 64 no P store, 128 no S load.  Results are garbage."""
 import os
 import subprocess
 import sys
@@ -20,7 +21,7 @@ for ns in (1, 2):
     e1.record(); torch.cuda.synchronize()
     print("nsplit", ns, "call %%.1f us" %% (e0.elapsed_time(e1) / 20 * 1e3))
 '''
-for dbg in (0, 1, 2, 4, 3, 5, 6, 7):
+for dbg in [int(a) for a in sys.argv[1:]] or (0, 1, 4, 5):
     env = dict(os.environ, ARFE_B200_LIB=os.path.join(ROOT, "arfe_b200", "libarfe_b200_prof.so"), ARFE_NL_DBG=str(dbg))
     r = subprocess.run([sys.executable, "-c", SNIP % ROOT], env=env, capture_output=True, text=True, timeout=300)
     print("ARFE_NL_DBG", dbg, "|", " | ".join(r.stdout.strip().splitlines()), r.stderr.strip()[-300:] if r.returncode else "", flush=True)
