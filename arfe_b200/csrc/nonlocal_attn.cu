@@ -31,7 +31,9 @@
 //                      the tensor pipe ran at half speed.  Two S tiles live in TMEM (Q K^T of step j + 1
 //                      runs under the softmax of step j); P overwrites its own S tile, so the softmax
 //                      weights never touch shared memory; K and V rings are three tiles deep.
-//  nl_combine_kernel   (key range split only) merges the partial (O, max, sum) triples.
+//                      Key range split: each CTA leaves (O, max, sum) in the workspace and the CTA of a
+//                      query block that arrives last (an atomic counter; nobody waits) merges them and
+//                      writes y -- no second kernel.
 //
 // Arithmetic: operands rounded to bf16 (round to nearest even), products exact, fp32 accumulation in
 // the tensor core, fp32 softmax with exp2; tolerance against the fp32 reference is the bf16 one of
@@ -227,8 +229,8 @@ constexpr int NL_THREADS = (NL_SOFTMAX_WARPS + 3) * 32;  // + MMA issuer, K load
 template <int D, typename OutT>
 __global__ void __launch_bounds__(NL_THREADS, 1)
 nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, const uint8_t* __restrict__ Vp,
-               OutT* __restrict__ y, float* __restrict__ part_o, float* __restrict__ part_ml, int HW, int nqb,
-               int nkb, int nsplit, float sl2, int out_cl, int dbg) {
+               OutT* __restrict__ y, float* __restrict__ part_o, float* __restrict__ part_ml,
+               int* __restrict__ counters, int HW, int nqb, int nkb, int nsplit, float sl2, int out_cl, int dbg) {
   using C = NlCfg<D>;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128-byte swizzle atoms need a 1024-byte aligned base
@@ -465,34 +467,100 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
     nl_wait(&bars[B_PVDONE + ((n_it - 1) & 1)], (uint32_t)((n_it - 1) >> 1) & 1u);
     tc_fence_after();
     const int p = qb * NL_BM + row;
-    const float inv = nsplit == 1 ? 1.f / l : 1.f;
-    const size_t prow = ((size_t)z * B + b) * ((size_t)nqb * NL_BM) + p;
-    if (nsplit > 1 && half == 0) {
-      part_ml[prow * 2 + 0] = m_ref * sl2;  // log2 units
-      part_ml[prow * 2 + 1] = l;
-    }
-#pragma unroll 1
-    for (int ch = 0; ch < D / 64; ++ch) {
-      uint32_t o[32];
-      const int d0 = half * (D / 2) + ch * 32;
-      tmem_ld32(tmem_o + lane_base + d0, o);
-      tmem_wait_ld();
-      if (nsplit > 1) {
-        float4* dst = reinterpret_cast<float4*>(part_o + prow * D + d0);
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          dst[c] = make_float4(__uint_as_float(o[4 * c]), __uint_as_float(o[4 * c + 1]), __uint_as_float(o[4 * c + 2]),
-                               __uint_as_float(o[4 * c + 3]));
-      } else if (p < HW) {
-        if (out_cl) {
-          OutT* dst = y + ((size_t)b * HW + p) * D + d0;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) nl_store1(dst + c, __uint_as_float(o[c]) * inv);
-        } else {
+    const int NB = B * nqb, blk = b * nqb + qb;
+    // all MMAs and with them all tile copies are complete: the K ring is free; per warp a 32 x 33 float
+    // staging tile turns "lane = row" into "lane = channel" for channels-last output
+    float* stage = reinterpret_cast<float*>(smem + C::OFF_K) + warp * (32 * 33);
+    // 32 channels d0.. of this thread's row, scaled: lanes are consecutive positions
+    auto write_final = [&](const float (&v)[32], int d0) {
+      if (!out_cl) {  // [B][D][HW]: 128 contiguous bytes per channel and warp
+        if (p < HW) {
           OutT* dst = y + ((size_t)b * D + d0) * HW + p;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) nl_store1(dst + (size_t)c * HW, __uint_as_float(o[c]) * inv);
+          for (int c = 0; c < 32; ++c) nl_store1(dst + (size_t)c * HW, v[c]);
         }
+      } else {  // [B][HW][D]: transpose the 32 x 32 tile through shared memory
+#pragma unroll
+        for (int c = 0; c < 32; ++c) stage[lane * 33 + c] = v[c];
+        __syncwarp();
+        const int p0 = qb * NL_BM + quad * 32;
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r)
+          if (p0 + r < HW) nl_store1(y + ((size_t)b * HW + p0 + r) * D + d0 + lane, stage[r * 33 + lane]);
+        __syncwarp();
+      }
+    };
+    if (nsplit == 1) {
+      const float inv = 1.f / l;
+#pragma unroll 1
+      for (int ch = 0; ch < D / 64; ++ch) {
+        uint32_t o[32];
+        float v[32];
+        const int d0 = half * (D / 2) + ch * 32;
+        tmem_ld32(tmem_o + lane_base + d0, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(o[c]) * inv;
+        write_final(v, d0);
+      }
+    } else {
+      // Key range split: every CTA leaves its (O, max, sum) in the workspace -- O column-major inside the
+      // query block, so that lanes = rows store contiguously -- and the CTA of a query block that
+      // arrives LAST (a counter, nobody waits) merges:  y = sum_z O_z 2^(m_z - M) / sum_z l_z 2^(m_z - M)
+      const float m_own = m_ref * sl2;  // log2 units
+      if (half == 0) {
+        part_ml[(((size_t)z * NB + blk) * NL_BM + row) * 2 + 0] = m_own;
+        part_ml[(((size_t)z * NB + blk) * NL_BM + row) * 2 + 1] = l;
+      }
+#pragma unroll 1
+      for (int ch = 0; ch < D / 64; ++ch) {
+        uint32_t o[32];
+        const int d0 = half * (D / 2) + ch * 32;
+        tmem_ld32(tmem_o + lane_base + d0, o);
+        tmem_wait_ld();
+        float* dst = part_o + (((size_t)z * NB + blk) * D + d0) * NL_BM + row;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) dst[(size_t)c * NL_BM] = __uint_as_float(o[c]);
+      }
+      __threadfence();
+      int* flag = reinterpret_cast<int*>(xch);
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+      if (tid == 0) flag[0] = atomicAdd(&counters[blk], 1);
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+      if (flag[0] == nsplit - 1) {
+        __threadfence();
+        float M = m_own;
+        for (int zz = 0; zz < nsplit; ++zz)
+          if (zz != z) M = fmaxf(M, __ldcg(&part_ml[(((size_t)zz * NB + blk) * NL_BM + row) * 2]));
+        const float w_own = exp2f(m_own - M);
+        float den = l * w_own;
+        for (int zz = 0; zz < nsplit; ++zz)
+          if (zz != z) {
+            const float* ml = &part_ml[(((size_t)zz * NB + blk) * NL_BM + row) * 2];
+            den += __ldcg(ml + 1) * exp2f(__ldcg(ml) - M);
+          }
+        const float inv = 1.f / den;
+#pragma unroll 1
+        for (int ch = 0; ch < D / 64; ++ch) {
+          uint32_t o[32];
+          float v[32];
+          const int d0 = half * (D / 2) + ch * 32;
+          tmem_ld32(tmem_o + lane_base + d0, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(o[c]) * w_own;
+          for (int zz = 0; zz < nsplit; ++zz)
+            if (zz != z) {
+              const float wz = exp2f(__ldcg(&part_ml[(((size_t)zz * NB + blk) * NL_BM + row) * 2]) - M);
+              const float* src = part_o + (((size_t)zz * NB + blk) * D + d0) * NL_BM + row;
+#pragma unroll
+              for (int c = 0; c < 32; ++c) v[c] = fmaf(__ldcg(src + (size_t)c * NL_BM), wz, v[c]);
+            }
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] *= inv;
+          write_final(v, d0);
+        }
+        if (tid == 0) counters[blk] = 0;  // ready for the next call on this workspace
       }
     }
     tc_fence_before();
@@ -502,48 +570,6 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TMEM_COLS)
                  : "memory");
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Merge of the key-range partials: y = sum_z O_z 2^(m_z - M) / sum_z l_z 2^(m_z - M)
-template <typename OutT>
-__global__ void nl_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml,
-                                  OutT* __restrict__ y, int B, int HW, int D, int rows_pad, int nsplit, int out_cl) {
-  const int d4 = D / 4;
-  const long long n = (long long)B * HW * d4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    // NCHW output: consecutive threads = consecutive positions; channels-last: consecutive channels
-    int b, p, c4;
-    if (out_cl) {
-      c4 = (int)(i % d4);
-      p = (int)((i / d4) % HW);
-      b = (int)(i / ((long long)d4 * HW));
-    } else {
-      p = (int)(i % HW);
-      c4 = (int)((i / HW) % d4);
-      b = (int)(i / ((long long)d4 * HW));
-    }
-    float M = -INFINITY;
-    for (int zz = 0; zz < nsplit; ++zz) M = fmaxf(M, part_ml[(((size_t)zz * B + b) * rows_pad + p) * 2]);
-    float den = 0.f;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int zz = 0; zz < nsplit; ++zz) {
-      const size_t r = ((size_t)zz * B + b) * rows_pad + p;
-      const float w = exp2f(part_ml[r * 2] - M);
-      den += part_ml[r * 2 + 1] * w;
-      const float4 o = *reinterpret_cast<const float4*>(part_o + r * D + c4 * 4);
-      acc.x += o.x * w; acc.y += o.y * w; acc.z += o.z * w; acc.w += o.w * w;
-    }
-    const float inv = 1.f / den;
-    if (out_cl) {
-      OutT* dst = y + ((size_t)b * HW + p) * D + c4 * 4;
-      nl_store1(dst, acc.x * inv); nl_store1(dst + 1, acc.y * inv); nl_store1(dst + 2, acc.z * inv); nl_store1(dst + 3, acc.w * inv);
-    } else {
-      OutT* dst = y + ((size_t)b * D + c4 * 4) * HW + p;
-      nl_store1(dst, acc.x * inv); nl_store1(dst + HW, acc.y * inv); nl_store1(dst + 2 * (size_t)HW, acc.z * inv);
-      nl_store1(dst + 3 * (size_t)HW, acc.w * inv);
-    }
   }
 }
 
@@ -561,8 +587,10 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 nl_pack_kernel(const T* __restrict__ theta, const T* __restrict__ phi, const T* __restrict__ g,
                uint8_t* __restrict__ Qp, uint8_t* __restrict__ Kp, uint8_t* __restrict__ Vp, int HW, int D, int in_cl,
-               int nqb, int nkb) {
+               int nqb, int nkb, int* __restrict__ counters, int ncounters) {
   __shared__ float tile[64][65];  // [position][channel]
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)  // arrival counters of the key-range merge
+    for (int i = threadIdx.x; i < ncounters; i += blockDim.x) counters[i] = 0;
   const int which = blockIdx.z % 3, b = blockIdx.z / 3;
   const int pb = blockIdx.x, slab = blockIdx.y;
   if (which == 0 ? pb >= nqb * 2 : pb >= nkb) return;
@@ -608,7 +636,7 @@ nl_pack_kernel(const T* __restrict__ theta, const T* __restrict__ phi, const T* 
 struct NlLayout {
   int nqb, nkb, rows_pad;
   size_t q_bytes, k_bytes, v_bytes, part_o_bytes, part_ml_bytes;
-  size_t off_k, off_v, off_po, off_pml, total;
+  size_t off_k, off_v, off_po, off_pml, off_cnt, total;
 };
 NlLayout nl_layout(int B, int HW, int D, int nsplit) {
   NlLayout a;
@@ -624,7 +652,8 @@ NlLayout nl_layout(int B, int HW, int D, int nsplit) {
   a.off_v = a.off_k + a.k_bytes;
   a.off_po = a.off_v + a.v_bytes;
   a.off_pml = a.off_po + a.part_o_bytes;
-  a.total = a.off_pml + a.part_ml_bytes;
+  a.off_cnt = a.off_pml + a.part_ml_bytes;  // one arrival counter per query block (zeroed by the pack kernel)
+  a.total = a.off_cnt + (((size_t)B * a.nqb * 4 + 255) & ~(size_t)255);
   return a;
 }
 
@@ -636,8 +665,8 @@ cudaError_t nl_launch_attn(const NlLayout& a, uint8_t* ws, OutT* y, int B, int H
   if (e != cudaSuccess) return e;
   nl_attn_kernel<D, OutT><<<dim3(a.nqb, B, nsplit), NL_THREADS, C::SMEM, stream>>>(
       ws, ws + a.off_k, ws + a.off_v, y, reinterpret_cast<float*>(ws + a.off_po),
-      reinterpret_cast<float*>(ws + a.off_pml), HW, a.nqb, a.nkb, nsplit, sl2, out_cl,
-      ARFE_KNOB_ENV("ARFE_NL_DBG", 0));
+      reinterpret_cast<float*>(ws + a.off_pml), reinterpret_cast<int*>(ws + a.off_cnt), HW, a.nqb, a.nkb, nsplit, sl2,
+      out_cl, ARFE_KNOB_ENV("ARFE_NL_DBG", 0));
   return cudaGetLastError();
 }
 
@@ -649,7 +678,7 @@ cudaError_t nl_run(const void* theta, const void* phi, const void* g, void* y, i
   const int pbs = a.nqb * 2 > a.nkb ? a.nqb * 2 : a.nkb;
   nl_pack_kernel<T><<<dim3(pbs, D / 64, 3 * B), 256, 0, stream>>>(
       static_cast<const T*>(theta), static_cast<const T*>(phi), static_cast<const T*>(g), ws, ws + a.off_k,
-      ws + a.off_v, HW, D, in_cl, a.nqb, a.nkb);
+      ws + a.off_v, HW, D, in_cl, a.nqb, a.nkb, reinterpret_cast<int*>(ws + a.off_cnt), B * a.nqb);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const float sl2 = scale * 1.4426950408889634f;
@@ -659,15 +688,6 @@ cudaError_t nl_run(const void* theta, const void* phi, const void* g, void* y, i
     case 128: e = nl_launch_attn<128, T>(a, ws, yo, B, HW, nsplit, sl2, in_cl, stream); break;
     case 256: e = nl_launch_attn<256, T>(a, ws, yo, B, HW, nsplit, sl2, in_cl, stream); break;
     default: return cudaErrorNotSupported;
-  }
-  if (e != cudaSuccess) return e;
-  if (nsplit > 1) {
-    const long long n = (long long)B * HW * (D / 4);
-    const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-    nl_combine_kernel<T><<<blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(ws + a.off_po),
-                                                      reinterpret_cast<const float*>(ws + a.off_pml), yo, B, HW, D,
-                                                      a.rows_pad, nsplit, in_cl);
-    e = cudaGetLastError();
   }
   return e;
 }
