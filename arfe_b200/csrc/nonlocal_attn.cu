@@ -241,7 +241,7 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qb = blockIdx.x, b = blockIdx.y, z = blockIdx.z, B = gridDim.y;
   const int kb_lo = (int)((long long)nkb * z / nsplit), kb_hi = (int)((long long)nkb * (z + 1) / nsplit);
-  const int n_it = kb_hi - kb_lo;
+  const int n_it = (NL_DBG(1024) && kb_hi - kb_lo > 2) ? 2 : kb_hi - kb_lo;  // 1024: fixed cost only
 
   if (tid == 0) {
     for (int i = 0; i < B_COUNT; ++i)
@@ -596,6 +596,47 @@ nl_pack_kernel(const T* __restrict__ theta, const T* __restrict__ phi, const T* 
   if (which == 0 ? pb >= nqb * 2 : pb >= nkb) return;
   const T* src = which == 0 ? theta : (which == 1 ? phi : g);
   const int p0 = pb * 64, c0 = slab * 64;
+  if ((which < 2) == (in_cl != 0)) {
+    // the 8 elements of a chunk are contiguous in the source (theta / phi channels-last, g NCHW):
+    // straight from global memory, two chunks per thread, no staging
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int q = threadIdx.x + 256 * i, r = q >> 3, c = q & 7;
+      float v[8];
+      uint8_t* dst;
+      if (which < 2) {
+        const int prow = p0 + r;
+        if (prow < HW) {
+          const T* sp = src + ((size_t)b * HW + prow) * D + c0 + c * 8;
+          if constexpr (sizeof(T) == 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(sp)), bb = __ldg(reinterpret_cast<const float4*>(sp) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bb.x; v[5] = bb.y; v[6] = bb.z; v[7] = bb.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = nl_to_float(sp[e]);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        }
+        dst = which == 0 ? Qp + (((size_t)b * nqb * NL_BM + prow) * D + c0 + c * 8) * 2
+                         : Kp + ((size_t)b * nkb + pb) * ((size_t)NL_BN * D * 2) + (size_t)slab * (NL_BN * 128) + r * 128 +
+                               ((c ^ (r & 7)) * 16);
+      } else {
+        const int d = c0 + r;
+        const T* sp = src + ((size_t)b * D + d) * HW;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int pp = p0 + c * 8 + e;
+          v[e] = pp < HW ? nl_to_float(__ldg(sp + pp)) : 0.f;
+        }
+        dst = Vp + ((size_t)b * nkb + pb) * ((size_t)D * NL_BN * 2) + (size_t)d * 128 + ((c ^ (d & 7)) * 16);
+      }
+      *reinterpret_cast<uint4*>(dst) =
+          make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+    return;
+  }
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   if (in_cl) {  // [B][HW][D]: channels contiguous
     for (int pl = ty; pl < 64; pl += 4) {

@@ -15,11 +15,17 @@ ts = [torch.randn(B, D, H, W, device="cuda").contiguous(memory_format=torch.chan
 for ns in (1, 2):
     for _ in range(3): A.nonlocal_attention(*ts, 1.0, ns)
     torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph(); st = torch.cuda.Stream(); st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        with torch.cuda.graph(gr, stream=st):
+            A.nonlocal_attention(*ts, 1.0, ns)
+    torch.cuda.current_stream().wait_stream(st)
+    gr.replay(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(20): A.nonlocal_attention(*ts, 1.0, ns)
+    for _ in range(20): gr.replay()
     e1.record(); torch.cuda.synchronize()
-    print("nsplit", ns, "call %%.1f us" %% (e0.elapsed_time(e1) / 20 * 1e3))
+    print("nsplit", ns, "graph %%.1f us" %% (e0.elapsed_time(e1) / 20 * 1e3))
 '''
 for dbg in [int(a) for a in sys.argv[1:]] or (0, 1, 4, 5):
     env = dict(os.environ, ARFE_B200_LIB=os.path.join(ROOT, "arfe_b200", "libarfe_b200_prof.so"), ARFE_NL_DBG=str(dbg))
