@@ -362,7 +362,7 @@ def nonlocal_refine_block(dev, verify=True):
     out = {"shape": f"B={B} C={D} {H}x{W} ({H * W} positions), fp32 in/out, operands bf16, channels-last",
            "fused_us": round(t_f * 1e3, 1), "library_fp32_us": round(t_l * 1e3, 1),
            "tflops": round(flops / (t_f * 1e-3) / 1e12, 1), "peak_tflops": peak, "peak_source": src,
-           "frac": round(flops / (t_f * 1e-3) / 1e12 / peak, 3), "gpu_launches_per_call": 3}
+           "frac": round(flops / (t_f * 1e-3) / 1e12 / peak, 3), "gpu_launches_per_call": 2}
     if verify:
         from oracle import arfe_oracle as O
         torch.set_num_threads(os.cpu_count() or 1)

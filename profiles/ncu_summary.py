@@ -9,7 +9,9 @@ KEEP = ('gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__throughput.avg.pct', 'launch__grid_size', 'launch__block_size',
         'launch__shared_mem_per_block_dynamic', 'l1tex__t_sector_hit_rate.pct',
         'lts__t_sectors_op_red.sum', 'lts__t_sectors_op_atom.sum', 'l1tex__throughput.avg.pct',
-        'lts__throughput.avg.pct', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active')
+        'lts__throughput.avg.pct', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+        'sm__cycles_active.avg', 'sm__cycles_elapsed.max', 'launch__shared_mem_per_block')
 out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
