@@ -195,11 +195,11 @@ __device__ __forceinline__ void nl_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(a), "r"(parity)
         : "memory");
-    if (!done && (spin & 1023u) == 1023u) {  // 2 s without progress: a protocol error, not a slow step
+    if (!done && (spin & 1023u) == 1023u) {  // 20 s without progress: a protocol error, not a slow step
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       if (t0 == 0) t0 = t;
-      else if (t - t0 > 2000000000ull) __trap();
+      else if (t - t0 > 20000000000ull) __trap();
     }
   }
 }

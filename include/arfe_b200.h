@@ -400,8 +400,10 @@ int arfe_fpn_backward_fused(const void* const* douts, int douts_f32,
  * nsplit >= 1 slices the key range over several CTAs per 128-query block
  * (arfe_nonlocal_default_split: enough to fill the SMs of the current device);
  * workspace: arfe_nonlocal_workspace_bytes(B, HW, D, nsplit) bytes, 1024-byte
- * aligned (bf16 operand tiles + the partial results when nsplit > 1).  Forward
- * only. */
+ * aligned (bf16 operand tiles + the partial results and arrival counters when
+ * nsplit > 1); it holds all device-side state of a call: concurrent calls on
+ * different streams need different workspaces.  scale must be positive.
+ * Forward only. */
 int arfe_nonlocal_default_split(int B, int HW);
 size_t arfe_nonlocal_workspace_bytes(int B, int HW, int D, int nsplit);
 int arfe_nonlocal_attention_forward(const void* theta, const void* phi,

@@ -71,6 +71,18 @@ def test_argument_errors_need_no_gpu():
     assert rc == -5
     rc = lib.arfe_rff_gate_forward(None, 10, None, None, None, 1, 20, 0, None)
     assert rc == -2  # stride < n_per_roi
+    # NonLocal2D attention: channel counts outside the tensor-core tiles, bad splits, NULLs
+    assert lib.arfe_nonlocal_workspace_bytes(2, 4200, 256, 2) > 2 * 4200 * 256 * 2 * 3
+    assert lib.arfe_nonlocal_workspace_bytes(2, 4200, 96, 2) == 0
+    rc = lib.arfe_nonlocal_attention_forward(None, None, None, None, 1, 64, 96, 0, 0, 1.0, 1, None, 0, None)
+    assert rc == -5 and b"inter_channels" in lib.arfe_last_error()
+    rc = lib.arfe_nonlocal_attention_forward(None, None, None, None, 1, 64, 64, 0, 0, 1.0, 2, None, 0, None)
+    assert rc == -2  # more key slices than key tiles
+    rc = lib.arfe_nonlocal_attention_forward(None, None, None, None, 1, 64, 64, 0, 0, -1.0, 1, None, 0, None)
+    assert rc == -2  # scale must be positive
+    rc = lib.arfe_nonlocal_attention_forward(None, None, None, None, 1, 64, 64, 0, 0, 1.0, 1, None, 0, None)
+    assert rc == -1  # NULL tensors
+    assert lib.arfe_nonlocal_attention_forward(None, None, None, None, 0, 64, 64, 0, 0, 1.0, 1, None, 0, None) == 0
 
 
 def test_python_surface_refuses_cpu_tensors():

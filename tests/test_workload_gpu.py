@@ -74,5 +74,5 @@ def test_shipped_library_has_no_profiling_knobs():
     from arfe_b200 import _lib
     data = open(_lib.LIB_PATH, "rb").read()
     for knob in (b"ARFE_FWD_SKIP", b"ARFE_BWD_SKIP", b"ARFE_PULL_G", b"ARFE_PULL_NV", b"ARFE_FWD_NCH",
-                 b"ARFE_FWD_OCC", b"ARFE_APPLY_OCC", b"ARFE_PULL_HEAVY_PX", b"ARFE_PULL_PERSM"):
+                 b"ARFE_FWD_OCC", b"ARFE_APPLY_OCC", b"ARFE_PULL_HEAVY_PX", b"ARFE_PULL_PERSM", b"ARFE_NL_DBG"):
         assert knob not in data, knob
