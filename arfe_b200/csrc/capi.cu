@@ -560,6 +560,28 @@ int arfe_nonlocal_attention_forward(const void* theta, const void* phi, const vo
                                                      workspace, nsplit, (cudaStream_t)stream), fn);
 }
 
+int arfe_fpn_gate_conv_backward(const void* const* feats, const float* const* w1, const float* const* w2,
+                                const void* const* dg1, const void* const* dg2, const int32_t* H, const int32_t* W,
+                                int L, int B, int C, int dtype, int layout, void* const* dx, float* const* dw1,
+                                float* const* db1, float* const* dw2, float* const* db2, void* stream) {
+  const char* fn = "arfe_fpn_gate_conv_backward";
+  int rc = check_common(fn, L, B, C, H, W, dtype, layout);
+  if (rc) return rc;
+  REQUIRE(layout == ARFE_NHWC, ARFE_E_UNSUPPORTED, "%s: channels-last feature maps only", fn);
+  if (B == 0) return ARFE_OK;
+  REQUIRE(feats && w1 && w2 && dg1 && dg2 && dw1 && db1 && dw2 && db2, ARFE_E_NULL, "%s: NULL argument", fn);
+  for (int l = 0; l < L; ++l) {
+    REQUIRE(feats[l] && w1[l] && w2[l] && dg1[l] && dg2[l] && dw1[l] && db1[l] && dw2[l] && db2[l] && (!dx || dx[l]),
+            ARFE_E_NULL, "%s: NULL tensor at level %d", fn, l);
+    REQUIRE(aligned(feats[l], 16) && (!dx || aligned(dx[l], 16)), ARFE_E_ALIGN, "%s: feats / dx[%d] must be 16-byte aligned", fn, l);
+  }
+  DeviceGuard guard(feats[0]);
+  const cudaError_t e = arfe::launch_fpn_gate_conv_backward(feats, w1, w2, dg1, dg2, H, W, L, B, C, dtype, dx, dw1, db1,
+                                                            dw2, db2, (cudaStream_t)stream);
+  if (e == cudaErrorNotSupported) return fail(ARFE_E_UNSUPPORTED, "%s: needs C %% 4 == 0 and C <= 512", fn);
+  return cuda_result(e, fn);
+}
+
 static int fill_fpn(const char* fn, arfe::FpnParams& p, const int32_t* H, const int32_t* W, int L,
                     int B, int C, int dtype, int layout) {
   int rc = check_common(fn, L, B, C, H, W, dtype, layout);

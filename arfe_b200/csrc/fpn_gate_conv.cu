@@ -174,6 +174,149 @@ gate_conv_sum(const ConvLevels lv, const float* __restrict__ dots) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Backward of both gate convolutions of every level in ONE pass over x (r2):
+//   g_f[q'] = b_f + sum_{tap, c} w_f[c][tap] x[q' + off(tap)][c]
+//   => pixel q of x meets, for filter f and tap t, the output gradient s_{f,t} = dg_f[q - off(t)]
+//      (zero outside the map):   dx[q][c]       = sum_{f,t} s_{f,t} w_f[c][t]
+//                                dw_f[c][t]    += sum_q     s_{f,t} x[q][c]        db_f += sum_q dg_f[q]
+// The 18 scalars of a pixel serve both sums: x is read once, dx written once (through two library
+// calls per convolution x is read twice and dx written and summed twice).  Warp == (pixel, group of
+// 128 channels), lane == 4 channels: 72 weight-gradient accumulators per lane, reduced over the
+// CTA in shared memory and added to dw with one atomic per element and CTA (the order of these
+// additions is not fixed: weight gradients are reproducible to rounding, like the library's).
+constexpr int kBwdPixPerCta = 512;
+
+struct ConvBwdLevels {
+  const void* x[kMaxLevels];
+  const float* w1[kMaxLevels];
+  const float* w2[kMaxLevels];
+  const void* dg1[kMaxLevels];
+  const void* dg2[kMaxLevels];
+  void* dx[kMaxLevels];
+  float* dw1[kMaxLevels];
+  float* dw2[kMaxLevels];
+  float* db1[kMaxLevels];
+  float* db2[kMaxLevels];
+  int H[kMaxLevels], W[kMaxLevels];
+  int cta0[kMaxLevels + 1];
+  int L, B, C, need_dx;
+};
+
+template <typename T>
+__device__ __forceinline__ float ld_scalar(const T* p) {
+  if constexpr (sizeof(T) == 4) return __ldg(p);
+  else return __bfloat162float(*p);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+gate_conv_bwd(const ConvBwdLevels lv) {
+  extern __shared__ float bsm[];  // [18][C] weights | [18][C] weight-gradient partials | [2] bias partials
+  int l = 0;
+  while (l + 1 < lv.L && (int)blockIdx.x >= lv.cta0[l + 1]) ++l;
+  const int C = lv.C, H = lv.H[l], W = lv.W[l];
+  float* wsm = bsm;
+  float* dsm = bsm + kDots * C;
+  float* bsum = dsm + kDots * C;
+  for (int e = threadIdx.x; e < 9 * C; e += kThreads) {  // linear reads of [C][9], transposed in shared memory
+    const int cc = e / 9, t = e - cc * 9;
+    wsm[t * C + cc] = __ldg(lv.w1[l] + e);
+    wsm[(9 + t) * C + cc] = __ldg(lv.w2[l] + e);
+  }
+  for (int e = threadIdx.x; e < kDots * C; e += kThreads) dsm[e] = 0.f;
+  if (threadIdx.x < 2) bsum[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ngroups = (C + 127) / 128;            // 1, 2 or 4 channel groups of 128
+  const int group = warp % ngroups, slot = warp / ngroups, nslots = (kThreads / 32) / ngroups;
+  const int c = group * 128 + lane * 4;
+  const bool cact = c < C;
+  const long long npix = (long long)lv.B * H * W;
+  const long long p0 = (long long)((int)blockIdx.x - lv.cta0[l]) * kBwdPixPerCta;
+  const long long p1 = min(p0 + kBwdPixPerCta, npix);
+  const T* __restrict__ x = static_cast<const T*>(lv.x[l]);
+  const T* __restrict__ g1 = static_cast<const T*>(lv.dg1[l]);
+  const T* __restrict__ g2 = static_cast<const T*>(lv.dg2[l]);
+  T* __restrict__ dx = static_cast<T*>(lv.dx[l]);
+  float acc[kDots][4];
+#pragma unroll
+  for (int d = 0; d < kDots; ++d)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[d][u] = 0.f;
+  float bacc = 0.f;  // lanes 4 and 13 of group 0: the centre taps are dg_f[q] itself
+  // one pixel's operands: lane d < 18 fetches s_d = dg_f[q - off(tap)], every lane its 4 channels of x[q]
+  auto fetch = [&](long long pp, float& sv, float (&xv)[4]) {
+    sv = 0.f;
+    xv[0] = xv[1] = xv[2] = xv[3] = 0.f;
+    const unsigned pi = (unsigned)pp;  // B * H * W < 2^31 (checked by the launcher): 32-bit divisions
+    const int xq = (int)(pi % (unsigned)W), yq = (int)((pi / (unsigned)W) % (unsigned)H);
+    if (lane < kDots) {
+      const int t = lane < 9 ? lane : lane - 9;
+      const int yy = yq - (t / 3 - 1), xx = xq - (t % 3 - 1);
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+        sv = ld_scalar<T>((lane < 9 ? g1 : g2) + pp + (long long)(yy - yq) * W + (xx - xq));
+    }
+    if (cact) {
+      if constexpr (sizeof(T) == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + pp * C + c));
+        xv[0] = v.x; xv[1] = v.y; xv[2] = v.z; xv[3] = v.w;
+      } else {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(x + pp * C + c));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+        const float2 a = __bfloat1622float2(h[0]), b2 = __bfloat1622float2(h[1]);
+        xv[0] = a.x; xv[1] = a.y; xv[2] = b2.x; xv[3] = b2.y;
+      }
+    }
+  };
+  // (Keeping the operands of the next two pixels in flight was measured slower, 500 vs 392 us: the
+  // kernel is bound by its ~300 instructions per pixel and warp at 16 resident warps, not by the loads.)
+  for (long long pp = p0 + slot; pp < p1; pp += nslots) {
+    float sv, xv[4];
+    fetch(pp, sv, xv);
+    if (group == 0 && (lane == 4 || lane == 13)) bacc += sv;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+    for (int d = 0; d < kDots; ++d) {
+      const float s = __shfl_sync(0xffffffffu, sv, d);
+      if (cact) {
+        const float4 w = *reinterpret_cast<const float4*>(wsm + d * C + c);
+        d0 = fmaf(s, w.x, d0); d1 = fmaf(s, w.y, d1); d2 = fmaf(s, w.z, d2); d3 = fmaf(s, w.w, d3);
+      }
+      acc[d][0] = fmaf(s, xv[0], acc[d][0]); acc[d][1] = fmaf(s, xv[1], acc[d][1]);
+      acc[d][2] = fmaf(s, xv[2], acc[d][2]); acc[d][3] = fmaf(s, xv[3], acc[d][3]);
+    }
+    if (lv.need_dx && cact) {
+      if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(dx + pp * C + c) = make_float4(d0, d1, d2, d3);
+      } else {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(d0, d1), hi = __floats2bfloat162_rn(d2, d3);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&lo);
+        o.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(dx + pp * C + c) = o;
+      }
+    }
+  }
+  // CTA-level reduction of the weight gradients, then one atomic per element
+  if (cact) {
+#pragma unroll
+    for (int d = 0; d < kDots; ++d)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) atomicAdd(dsm + d * C + c + u, acc[d][u]);
+  }
+  if (group == 0 && (lane == 4 || lane == 13)) atomicAdd(bsum + (lane == 13), bacc);
+  __syncthreads();
+  for (int e = threadIdx.x; e < kDots * C; e += kThreads) {
+    const int d = e / C, cc = e - d * C;
+    float* dw = d < 9 ? lv.dw1[l] : lv.dw2[l];
+    atomicAdd(dw + cc * 9 + (d < 9 ? d : d - 9), dsm[e]);
+  }
+  if (threadIdx.x == 0) atomicAdd(lv.db1[l], bsum[0]);
+  if (threadIdx.x == 1) atomicAdd(lv.db2[l], bsum[1]);
+}
+
 }  // namespace
 
 size_t fpn_gate_conv_workspace_bytes(int L, int B, const int* H, const int* W) {
@@ -225,6 +368,44 @@ cudaError_t launch_fpn_gate_conv_forward(const void* const* feats, const float* 
   const unsigned grid = (unsigned)((pix + kThreads - 1) / kThreads);
   if (dtype == 0) gate_conv_sum<float><<<grid, kThreads, 0, stream>>>(lv, dots);
   else gate_conv_sum<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(lv, dots);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fpn_gate_conv_backward(const void* const* feats, const float* const* w1, const float* const* w2,
+                                          const void* const* dg1, const void* const* dg2, const int* H, const int* W,
+                                          int L, int B, int C, int dtype, void* const* dx, float* const* dw1,
+                                          float* const* db1, float* const* dw2, float* const* db2,
+                                          cudaStream_t stream) {
+  const size_t smem = ((size_t)2 * kDots * C + 2) * sizeof(float);
+  if (C % 4 || C > 512 || smem > 200 * 1024) return cudaErrorNotSupported;
+  ConvBwdLevels lv;
+  int cta = 0;
+  for (int l = 0; l < kMaxLevels; ++l) {
+    lv.cta0[l] = cta;
+    if (l < L) {
+      lv.x[l] = feats[l]; lv.w1[l] = w1[l]; lv.w2[l] = w2[l]; lv.dg1[l] = dg1[l]; lv.dg2[l] = dg2[l];
+      lv.dx[l] = dx ? dx[l] : nullptr; lv.dw1[l] = dw1[l]; lv.dw2[l] = dw2[l]; lv.db1[l] = db1[l]; lv.db2[l] = db2[l];
+      lv.H[l] = H[l]; lv.W[l] = W[l];
+      const long long n = (long long)B * H[l] * W[l];
+      cta += (int)((n + kBwdPixPerCta - 1) / kBwdPixPerCta);
+    } else {
+      lv.x[l] = lv.dg1[l] = lv.dg2[l] = nullptr; lv.w1[l] = lv.w2[l] = nullptr; lv.dx[l] = nullptr;
+      lv.dw1[l] = lv.dw2[l] = lv.db1[l] = lv.db2[l] = nullptr; lv.H[l] = lv.W[l] = 1;
+    }
+  }
+  for (int l = L; l <= kMaxLevels; ++l) lv.cta0[l] = cta;
+  lv.L = L; lv.B = B; lv.C = C; lv.need_dx = dx != nullptr;
+  if (cta == 0) return cudaSuccess;
+  for (int l = 0; l < L; ++l)
+    if ((long long)B * H[l] * W[l] >= (1ll << 31)) return cudaErrorNotSupported;
+  cudaError_t e;
+  if (dtype == 0) {
+    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(gate_conv_bwd<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    gate_conv_bwd<float><<<cta, kThreads, smem, stream>>>(lv);
+  } else {
+    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(gate_conv_bwd<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    gate_conv_bwd<__nv_bfloat16><<<cta, kThreads, smem, stream>>>(lv);
+  }
   return cudaGetLastError();
 }
 

@@ -101,6 +101,12 @@ cudaError_t launch_fpn_gate_conv_forward(const void* const* feats, const float* 
                                          int L, int B, int C, int dtype, void* workspace, void* const* g1,
                                          void* const* g2, cudaStream_t stream);
 
+cudaError_t launch_fpn_gate_conv_backward(const void* const* feats, const float* const* w1, const float* const* w2,
+                                          const void* const* dg1, const void* const* dg2, const int* H, const int* W,
+                                          int L, int B, int C, int dtype, void* const* dx, float* const* dw1,
+                                          float* const* db1, float* const* dw2, float* const* db2,
+                                          cudaStream_t stream);
+
 // proposal side (proposals.cu)
 size_t nms_workspace_bytes(int n);
 cudaError_t launch_nms(const float* dets_sorted, int n, float thr, void* workspace, int64_t* keep, int* num_keep,

@@ -571,8 +571,8 @@ def rff_softmax_fuse(regions, logits):
 
 class _FPNGateConvFunction(Function):
     """g1_l, g2_l = the two C -> 1 3x3 convolutions of every level (wfpn_dual_spatial.py:120-121),
-    x read once for both (arfe_fpn_gate_conv_forward).  The backward of a convolution is the
-    library's (torch.nn.grad): a dense op outside the path."""
+    x read once for both (arfe_fpn_gate_conv_forward); the backward of all of them -- d x, d weights,
+    d biases -- is again one pass over x (arfe_fpn_gate_conv_backward)."""
 
     @staticmethod
     def forward(ctx, nlev, *tensors):
@@ -606,29 +606,41 @@ class _FPNGateConvFunction(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, *grads):
-        from torch.nn.grad import conv2d_input, conv2d_weight
         n = ctx.nlev
         saved = ctx.saved_tensors
-        feats, w1, w2 = saved[:n], saved[n:2 * n], saved[2 * n:3 * n]
-        dg1, dg2 = grads[:n], grads[n:]
+        feats, w1, w2 = list(saved[:n]), saved[n:2 * n], saved[2 * n:3 * n]
         need = ctx.needs_input_grad
-        dx, dw1, db1, dw2, db2 = [], [], [], [], []
-        for l in range(n):
-            x = feats[l]
-            gx = None
-            for w, g, dw, db, wi, bi in ((w1[l], dg1[l], dw1, db1, 1 + n + l, 1 + 2 * n + l),
-                                         (w2[l], dg2[l], dw2, db2, 1 + 3 * n + l, 1 + 4 * n + l)):
-                if g is None:
-                    dw.append(None); db.append(None)
-                    continue
-                g = g.to(x.dtype)
-                if need[1 + l]:
-                    t = conv2d_input(x.shape, w.to(x.dtype), g, padding=1)
-                    gx = t if gx is None else gx + t
-                dw.append(conv2d_weight(x, w.shape, g, padding=1).to(w.dtype) if need[wi] else None)
-                db.append(g.sum().reshape(1).to(w.dtype) if need[bi] else None)
-            dx.append(gx)
-        return (None,) + tuple(dx) + tuple(dw1) + tuple(db1) + tuple(dw2) + tuple(db2)
+        B, C = feats[0].shape[:2]
+        Hs = [f.shape[2] for f in feats]
+        Ws = [f.shape[3] for f in feats]
+        dev, fdt = feats[0].device, feats[0].dtype
+        # both filters of every level in one pass over x (arfe_fpn_gate_conv_backward); a missing output
+        # gradient is a zero map
+        dg = [[(g.to(fdt).contiguous() if g is not None else torch.zeros((B, 1, h, w), dtype=fdt, device=dev))
+               for g, h, w in zip(gs, Hs, Ws)] for gs in (grads[:n], grads[n:])]
+        need_dx = any(need[1:1 + n])
+        mf = torch.channels_last
+        dx = [torch.empty(f.shape, dtype=fdt, device=dev, memory_format=mf) for f in feats] if need_dx else None
+        f32 = lambda ts: [t.detach().float().contiguous() for t in ts]
+        w1f, w2f = f32(w1), f32(w2)
+        dw1 = [torch.zeros_like(t) for t in w1f]
+        dw2 = [torch.zeros_like(t) for t in w2f]
+        db1 = [torch.zeros(1, dtype=torch.float32, device=dev) for _ in range(n)]
+        db2 = [torch.zeros(1, dtype=torch.float32, device=dev) for _ in range(n)]
+        if B > 0:
+            rc = L.lib().arfe_fpn_gate_conv_backward(
+                L.ptr_array(feats), L.ptr_array(w1f), L.ptr_array(w2f), L.ptr_array(dg[0]), L.ptr_array(dg[1]),
+                L.int_array(Hs), L.int_array(Ws), n, B, C, L.dtype_code(feats[0]), L.ARFE_NHWC,
+                L.ptr_array(dx) if need_dx else None, L.ptr_array(dw1), L.ptr_array(db1), L.ptr_array(dw2),
+                L.ptr_array(db2), L.stream_ptr(dev))
+            L.check(rc, "arfe_fpn_gate_conv_backward")
+        elif need_dx:
+            dx = [t.zero_() for t in dx]
+        pick = lambda ts, off, ref: tuple((t.to(r.dtype) if need[off + i] else None)
+                                          for i, (t, r) in enumerate(zip(ts, ref)))
+        gx = tuple((dx[l] if need[1 + l] else None) for l in range(n)) if need_dx else (None,) * n
+        return (None,) + gx + pick(dw1, 1 + n, w1) + pick(db1, 1 + 2 * n, w1) + pick(dw2, 1 + 3 * n, w2) + \
+            pick(db2, 1 + 4 * n, w2)
 
 
 def fpn_gate_conv(feats, w1, b1, w2, b2):

@@ -363,6 +363,22 @@ int arfe_fpn_gate_conv_forward(const void* const* feats,
                                size_t workspace_bytes, void* const* g1,
                                void* const* g2, void* stream);
 
+/* Backward of the same two convolutions for all levels in one pass over x:
+ *   dx[l]  = sum over both filters and the 9 taps of w_f[c][tap] * dg_f[q - off(tap)]   (written;
+ *            NULL dx: the inputs need no gradient)
+ *   dw1[l], dw2[l] (fp32 [1,C,3,3]) and db1[l], db2[l] (fp32 [1]) are ACCUMULATED into (+=; the
+ *   caller zeroes them or passes the running .grad); their summation order is not fixed.
+ * feats[l], dx[l]: [B,C,H[l],W[l]] `dtype`, channels-last; dg1[l], dg2[l]: [B,1,H[l],W[l]] `dtype`
+ * (gradients of the raw convolution outputs).  C a multiple of 4, at most 512. */
+int arfe_fpn_gate_conv_backward(const void* const* feats,
+                                const float* const* w1, const float* const* w2,
+                                const void* const* dg1, const void* const* dg2,
+                                const int32_t* H, const int32_t* W, int L, int B,
+                                int C, int dtype, int layout, void* const* dx,
+                                float* const* dw1, float* const* db1,
+                                float* const* dw2, float* const* db2,
+                                void* stream);
+
 /* The whole AR-FPN backward in one pass over the incoming gradient pyramid
  * (channels-last only): what arfe_fpn_apply_backward followed by
  * arfe_fpn_gather_backward_acc(addend = douts) compute, bit for bit, reading

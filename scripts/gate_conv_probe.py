@@ -44,5 +44,29 @@ with torch.no_grad():
     t_fp32 = timeit(cudnn)
     torch.backends.cudnn.allow_tf32 = True
     t_tf32 = timeit(cudnn)
+
+# backward: d x, d weights, d biases of all ten convolutions
+xg = [x.clone().requires_grad_(True) for x in xs]
+pw = [t.clone().requires_grad_(True) for t in w1 + w2 + b1 + b2]
+n = len(shapes)
+
+
+def bwd_ours():
+    g1, g2 = A.fpn_gate_conv(xg, pw[:n], pw[2 * n:3 * n], pw[n:2 * n], pw[3 * n:])
+    torch.autograd.backward(list(g1) + list(g2), [torch.ones_like(t) for t in list(g1) + list(g2)])
+
+
+def bwd_cudnn():
+    outs = [F.conv2d(x, w, b, padding=1) for x, w, b in zip(xg, pw[:n], pw[2 * n:3 * n])] + \
+           [F.conv2d(x, w, b, padding=1) for x, w, b in zip(xg, pw[n:2 * n], pw[3 * n:])]
+    torch.autograd.backward(outs, [torch.ones_like(t) for t in outs])
+
+
+tb_ours = timeit(bwd_ours, 10)
+torch.backends.cudnn.allow_tf32 = False
+tb_fp32 = timeit(bwd_cudnn, 5)
+torch.backends.cudnn.allow_tf32 = True
+tb_tf32 = timeit(bwd_cudnn, 5)
+print(f"forward + backward: fused {tb_ours:7.1f} us | cuDNN fp32 {tb_fp32:7.1f} us, tf32 {tb_tf32:7.1f} us")
 pyr = sum(B * C * h * w * 4 for h, w in shapes)
 print(f"fused gate convs {t_ours:7.1f} us ({pyr / t_ours / 1e3:6.0f} GB/s of pyramid) | cuDNN 10 convs fp32 {t_fp32:7.1f} us, tf32 {t_tf32:7.1f} us")

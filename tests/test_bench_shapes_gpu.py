@@ -270,3 +270,62 @@ def test_fused_gate_convs_match_conv2d(cuda, case):
             err = (got.float().cpu() - ref).abs().max()
             tol = (1e-2 if bf16 else 1e-5) * float(ref.abs().max()) + 1e-6   # 9 C-term sums in another order
             assert float(err) <= tol, (case, l, float(err), float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("case", ["small_f32", "odd_f32", "bench_f32", "bench_bf16"])
+def test_fused_gate_convs_backward_matches_conv2d(cuda, case):
+    """SURVEY 8(f) row 2, backward: arfe_fpn_gate_conv_backward (d x, d weights, d biases of both
+    C -> 1 3x3 gate convolutions of every level in one pass over x) against torch CPU autograd of
+    conv2d.  Sums over pixels (weights) and over 18 taps (d x) in another order than the
+    library's: 2e-5 of the tensor's scale in fp32; bf16 I/O 1e-2."""
+    import torch.nn.functional as F
+    import arfe_b200 as A
+    from arfe_b200 import workload as wl
+    bf16 = case.endswith("bf16")
+    if case.startswith("small"):
+        B, C, shapes = 2, 24, [(9, 13), (5, 7), (3, 4), (2, 2), (1, 1)]
+    elif case.startswith("odd"):
+        B, C, shapes = 3, 132, [(7, 5), (4, 3), (1, 2)]          # C not a multiple of 128: ragged channel group
+    else:
+        B, C, shapes = 2, 256, wl.pyramid_shapes(800, 1344)
+    n = len(shapes)
+    gen = torch.Generator().manual_seed(9)
+    xs = [torch.randn(B, C, h, w, generator=gen) for h, w in shapes]
+    w1 = [torch.randn(1, C, 3, 3, generator=gen) * 0.05 for _ in shapes]
+    w2 = [torch.randn(1, C, 3, 3, generator=gen) * 0.05 for _ in shapes]
+    b1 = [torch.randn(1, generator=gen) for _ in shapes]
+    b2 = [torch.randn(1, generator=gen) for _ in shapes]
+    u1 = [torch.randn(B, 1, h, w, generator=gen) for h, w in shapes]
+    u2 = [torch.randn(B, 1, h, w, generator=gen) for h, w in shapes]
+    if bf16:
+        xs = [x.bfloat16().float() for x in xs]
+        u1 = [t.bfloat16().float() for t in u1]
+        u2 = [t.bfloat16().float() for t in u2]
+    dt = torch.bfloat16 if bf16 else torch.float32
+    leaf = lambda ts: [t.clone().requires_grad_(True) for t in ts]
+    xr, w1r, w2r, b1r, b2r = leaf(xs), leaf(w1), leaf(w2), leaf(b1), leaf(b2)
+    loss = sum((F.conv2d(xr[l], w1r[l], b1r[l], padding=1) * u1[l]).sum() +
+               (F.conv2d(xr[l], w2r[l], b2r[l], padding=1) * u2[l]).sum() for l in range(n))
+    loss.backward()
+    xg = [_cl(x.to(cuda, dt)).requires_grad_(True) for x in xs]
+    par = lambda ts: [t.to(cuda).requires_grad_(True) for t in ts]
+    w1g, w2g, b1g, b2g = par(w1), par(w2), par(b1), par(b2)
+    g1, g2 = A.fpn_gate_conv(xg, w1g, b1g, w2g, b2g)
+    loss = sum((g1[l].float() * u1[l].to(cuda)).sum() + (g2[l].float() * u2[l].to(cuda)).sum() for l in range(n))
+    loss.backward()
+    tol = 1e-2 if bf16 else 2e-5
+    for l in range(n):
+        for name, got, want in (("dx", xg[l].grad, xr[l].grad), ("dw1", w1g[l].grad, w1r[l].grad),
+                                ("dw2", w2g[l].grad, w2r[l].grad), ("db1", b1g[l].grad, b1r[l].grad),
+                                ("db2", b2g[l].grad, b2r[l].grad)):
+            assert got is not None and got.shape == want.shape, (name, l)
+            err = float((got.float().cpu() - want).abs().max())
+            assert err <= tol * float(want.abs().max()) + 1e-5, (case, name, l, err, float(want.abs().max()))
+    # inputs that need no gradient: parameters only
+    xn = [_cl(x.to(cuda, dt)) for x in xs]
+    w1n = par(w1)
+    g1, g2 = A.fpn_gate_conv(xn, w1n, b1g, w2g, b2g)
+    sum((g1[l].float() * u1[l].to(cuda)).sum() for l in range(n)).backward()
+    for l in range(n):
+        err = float((w1n[l].grad.cpu() - w1r[l].grad).abs().max())
+        assert err <= tol * float(w1r[l].grad.abs().max()) + 1e-5, (case, l, err)
