@@ -797,8 +797,8 @@ def fpn_apply(feats, bsf, g1, g2, link=None):
 class _NonLocalAttentionFunction(Function):
     """mmdet/ops/non_local.py:65-69 + :98-101: y = softmax(scale * theta_x . phi_x) . g_x as one
     fused tensor-core attention (arfe_nonlocal_attention_forward); the HW x HW weight matrix is
-    not materialised.  Backward: recomputed from the saved operands with library matmuls (the
-    flash-style backward kernel is not built)."""
+    not materialised.  Backward: recomputed from the saved operands with library GEMMs on bf16
+    operands (the forward's arithmetic; a flash-style backward kernel is not built)."""
 
     @staticmethod
     def forward(ctx, theta, phi, g, scale, nsplit):
@@ -832,24 +832,30 @@ class _NonLocalAttentionFunction(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
+        # Recomputed from the saved operands with library GEMMs in the forward kernel's arithmetic:
+        # bf16 operands (theta, phi, g, the weights P, d y, d S), fp32 accumulation and fp32 softmax.
         theta, phi, g = ctx.saved_tensors
         B, D, H, W = theta.shape
-        f = torch.float32
-        th = theta.reshape(B, D, -1).permute(0, 2, 1).to(f)      # [B, HW, D]
-        ph = phi.reshape(B, D, -1).to(f)                         # [B, D, HW]
-        gx = g.reshape(B, D, -1).permute(0, 2, 1).to(f)          # [B, HW, D]
-        dyx = dy.reshape(B, D, -1).permute(0, 2, 1).to(f)        # [B, HW, D]
-        p = torch.matmul(th, ph).mul_(ctx.scale).softmax(dim=-1)
-        dg = torch.matmul(p.transpose(1, 2), dyx)
-        dp = torch.matmul(dyx, gx.transpose(1, 2))
-        ds = p * (dp - (dp * p).sum(dim=-1, keepdim=True))
-        ds.mul_(ctx.scale)
-        dth = torch.matmul(ds, ph.transpose(1, 2))
-        dph = torch.matmul(th.transpose(1, 2), ds)               # [B, D, HW]
+        f, h = torch.float32, torch.bfloat16
+        flat = lambda t: t.reshape(B, D, -1) if t.is_contiguous() else t.permute(0, 2, 3, 1).reshape(B, -1, D).transpose(1, 2)
+        th = flat(theta).transpose(1, 2).to(h)                   # [B, HW, D]
+        ph = flat(phi).to(h)                                     # [B, D, HW]
+        gx = flat(g).transpose(1, 2).to(h)                       # [B, HW, D]
+        dyx = flat(dy).transpose(1, 2).to(h)                     # [B, HW, D]
+        p = torch.bmm(th, ph, out_dtype=f).mul_(ctx.scale).softmax(dim=-1)
+        pb = p.to(h)
+        dg = torch.bmm(pb.transpose(1, 2), dyx, out_dtype=f)     # [B, HW, D]
+        dp = torch.bmm(dyx, gx.transpose(1, 2), out_dtype=f)     # [B, HW, HW]
+        delta = (dp * p).sum(dim=-1, keepdim=True)
+        ds = dp.sub_(delta).mul_(p).mul_(ctx.scale).to(h)
+        del p, dp
+        dth = torch.bmm(ds, ph.transpose(1, 2), out_dtype=f)     # [B, HW, D]
+        dph = torch.bmm(th.transpose(1, 2), ds, out_dtype=f)     # [B, D, HW]
 
-        def back(t, transposed):
-            t = t.permute(0, 2, 1) if transposed else t
-            return t.reshape(B, D, H, W).to(theta.dtype)
+        def back(t, positions_first):
+            t = t.transpose(1, 2) if positions_first else t       # -> [B, D, HW]
+            t = t.reshape(B, D, H, W).to(theta.dtype)
+            return t.contiguous(memory_format=torch.channels_last) if not theta.is_contiguous() else t.contiguous()
         return back(dth, True), back(dph, False), back(dg, True), None, None
 
 

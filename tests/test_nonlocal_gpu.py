@@ -182,8 +182,9 @@ def test_nonlocal_module_forward_backward(oracle, cuda, layout):
     assert (out.detach().cpu() - out_ref.detach()).abs().max() <= 1e-2 * s
     assert (xg.grad.cpu() - xr.grad).abs().max() <= 2e-2 * xr.grad.abs().max()
     # the gradient of phi's bias is zero in exact arithmetic (a per-row constant shift of the logits
-    # leaves the softmax unchanged): rounding noise on both sides, hence the absolute floor
-    floor = 1e-5 * max(float(q.grad.abs().max()) for q in ref.parameters())
+    # leaves the softmax unchanged): what comes out is the rounding noise of d S, which the backward
+    # holds in bf16 like the forward holds the weights -- hence the floor relative to the largest gradient
+    floor = 2e-3 * max(float(q.grad.abs().max()) for q in ref.parameters())
     for (n, p), (_, q) in zip(mod.named_parameters(), ref.named_parameters()):
         assert (p.grad.cpu() - q.grad).abs().max() <= 2e-2 * q.grad.abs().max() + floor, n
 
@@ -202,3 +203,45 @@ def test_nonlocal_module_policy(cuda):
     m2.fused_attention = True
     with pytest.raises(RuntimeError):
         m2(torch.randn(1, 96, 4, 4, device=cuda))              # ... running the fused path is refused
+
+
+def test_neck_bf16_uses_fused_attention_and_gate_convs(oracle, cuda):
+    """WFPNDualSpatial on bf16 channels-last maps takes every fused kernel of the neck -- gather,
+    tensor-core attention ('auto' policy), one-pass gate convolutions, gated residual -- and stays
+    within the bf16 bound of the fp32 oracle module with the same weights, forward and input gradients."""
+    import arfe_b200 as A
+    torch.manual_seed(1)
+    C, shapes = 64, [(48, 80), (24, 40), (12, 20), (6, 10), (3, 5)]
+    ref_m = oracle.WFPNDualSpatial(C, 5)
+    ref_m.init_weights()
+    for p in ref_m.refine.parameters():
+        torch.nn.init.normal_(p, 0, 0.05)
+    m = A.WFPNDualSpatial(C, 5)
+    m.load_state_dict(ref_m.state_dict())
+    m = m.to(cuda).to(torch.bfloat16).to(memory_format=torch.channels_last)
+    xs = [x.bfloat16().float() for x in oracle.synthetic_pyramid(2, C, shapes, seed=6)]
+    calls = []
+    real = A.neck.nonlocal_attention
+    A.neck.nonlocal_attention = lambda *a, **k: (calls.append(1), real(*a, **k))[1]
+    try:
+        xg = [x.to(cuda, torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True) for x in xs]
+        out = m(xg)
+        gs = [torch.randn(x.shape, generator=torch.Generator().manual_seed(40 + i)) for i, x in enumerate(xs)]
+        torch.autograd.backward(list(out), [g.to(cuda, torch.bfloat16) for g in gs])
+    finally:
+        A.neck.nonlocal_attention = real
+    assert calls, "the bf16 neck did not take the fused attention"
+    xo = [x.clone().requires_grad_(True) for x in xs]
+    ref = ref_m(xo)
+    torch.autograd.backward(list(ref), [g.bfloat16().float() for g in gs])
+    for l in range(5):
+        assert out[l].dtype == torch.bfloat16
+        err = (out[l].float().cpu() - ref[l].detach()).abs().max()
+        assert float(err) <= 2e-2 * float(ref[l].abs().max()), (l, float(err))
+        # gradients: the gates are tanh(relu(conv)); where a pre-activation sits within bf16 rounding of
+        # zero the relu's derivative flips and that pixel's gradient legitimately differs by O(1), so the
+        # bound is on the relative L2 error and on all but 0.5 % of the elements, not on the maximum
+        d = (xg[l].grad.float().cpu() - xo[l].grad).abs()
+        scale = float(xo[l].grad.abs().max())
+        assert float(d.norm() / xo[l].grad.norm()) <= 3e-2, (l, float(d.norm() / xo[l].grad.norm()))
+        assert float((d > 3e-2 * scale).float().mean()) <= 5e-3, (l, float((d > 3e-2 * scale).float().mean()))
