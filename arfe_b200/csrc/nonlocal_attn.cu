@@ -15,7 +15,7 @@
 //                      copy (cp.async.bulk, no tensor map) straight into place.
 //                        Qp [B][nqb * 128 rows][D]                    theta as plain bf16 rows (goes to TMEM)
 //                        Kp [B][nkb][D/64 slabs][ 64 rows][128 B]     phi,   rows = positions
-//                        Vp [B][nkb][D rows][128 B]                   g transposed: rows = channels, 64 positions
+//                        Vp [B][nkb][D/64 slabs][ 64 rows][128 B]     g, same layout: P V takes it MN-major
 //  nl_attn_kernel      one CTA = 128 query positions of one image (x one slice of the keys when the
 //                      key range is split to fill the SMs).  Warp roles:
 //                        warps 0-7  softmax, thread = (query row, half of the 64 key columns): S (TMEM) ->
@@ -51,6 +51,9 @@ constexpr int NL_BN = 64;   // keys per step = one 128-byte swizzle row of bf16
 constexpr float NL_RESCALE = 8.f;  // log2 units a row maximum may grow before O is rescaled
 constexpr int NL_SBUF = 2;         // S tiles in tensor memory: Q K^T runs NL_SBUF - 1 steps ahead of P V
 constexpr int NL_STAGES = 3;       // K and V tile rings in shared memory
+// g (V) tiles are kept like phi (K) tiles -- rows = positions, 128-byte rows of 64 channels per slab -- and
+// handed to P V as an MN-major B operand (N = channels contiguous): no transposition of g anywhere.
+constexpr bool NL_V_MN = true;
 
 template <int D>
 struct NlCfg {
@@ -124,9 +127,17 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulator, bf16 A and B, both K-major
-__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// the same for an MN-major operand (the N / M index contiguous): 8 k-rows of 128 bytes form a swizzle
+// atom of 64 MN-elements; LBO = bytes between atoms along MN, SBO = bytes between 8-row groups along K
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulator, bf16 A and B; A K-major,
+// B K-major or MN-major (bit 16)
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool b_mn = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 
 #define NL_R32(r)                                                                                                  \
@@ -295,7 +306,7 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
   } else if (warp == NL_SOFTMAX_WARPS) {
     // ===== MMA issuer: the whole warp walks the schedule (warp-uniform), one elected lane issues =====
     constexpr uint32_t idesc_qk = idesc_bf16(NL_BM, NL_BN);
-    constexpr uint32_t idesc_pv = idesc_bf16(NL_BM, D);
+    constexpr uint32_t idesc_pv = idesc_bf16(NL_BM, D, NL_V_MN);
     nl_wait(&bars[B_QFULL], 0);  // Q sits in tensor memory (written by the softmax warps)
     tc_fence_after();
     // S[it % NL_SBUF] = Q K_it^T: A = Q from tensor memory (no shared-memory operand traffic for the
@@ -333,8 +344,10 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
 #pragma unroll
         for (int kk = 0; kk < NL_BN / 16; ++kk)
           if (!NL_DBG(4))
-            tc_mma_ts(tmem_o, p_tmem + kk * 8, smem_desc_sw128(v_addr + kk * 32), idesc_pv,
-                      (jt > 0 || kk > 0) ? 1u : 0u);
+            tc_mma_ts(tmem_o, p_tmem + kk * 8,
+                      NL_V_MN ? smem_desc_sw128_mn(v_addr + kk * (16 * 128), NL_BN * 128, 1024)  // 16 key rows on
+                              : smem_desc_sw128(v_addr + kk * 32),
+                      idesc_pv, (jt > 0 || kk > 0) ? 1u : 0u);
         tc_commit(&bars[B_PVDONE + (jt & 1)]);
         tc_commit(&bars[B_VEMPTY + s]);
       }
@@ -596,7 +609,9 @@ nl_pack_kernel(const T* __restrict__ theta, const T* __restrict__ phi, const T* 
   if (which == 0 ? pb >= nqb * 2 : pb >= nkb) return;
   const T* src = which == 0 ? theta : (which == 1 ? phi : g);
   const int p0 = pb * 64, c0 = slab * 64;
-  if ((which < 2) == (in_cl != 0)) {
+  const bool rows_pos = which < 2 || NL_V_MN;  // tile rows = positions, chunks = 8 channels
+  uint8_t* KVp = which == 1 ? Kp : Vp;
+  if (rows_pos == (in_cl != 0)) {
     // the 8 elements of a chunk are contiguous in the source (theta / phi channels-last, g NCHW):
     // straight from global memory, two chunks per thread, no staging
 #pragma unroll
@@ -604,7 +619,7 @@ nl_pack_kernel(const T* __restrict__ theta, const T* __restrict__ phi, const T* 
       const int q = threadIdx.x + 256 * i, r = q >> 3, c = q & 7;
       float v[8];
       uint8_t* dst;
-      if (which < 2) {
+      if (rows_pos) {
         const int prow = p0 + r;
         if (prow < HW) {
           const T* sp = src + ((size_t)b * HW + prow) * D + c0 + c * 8;
@@ -620,7 +635,7 @@ nl_pack_kernel(const T* __restrict__ theta, const T* __restrict__ phi, const T* 
           for (int e = 0; e < 8; ++e) v[e] = 0.f;
         }
         dst = which == 0 ? Qp + (((size_t)b * nqb * NL_BM + prow) * D + c0 + c * 8) * 2
-                         : Kp + ((size_t)b * nkb + pb) * ((size_t)NL_BN * D * 2) + (size_t)slab * (NL_BN * 128) + r * 128 +
+                         : KVp + ((size_t)b * nkb + pb) * ((size_t)NL_BN * D * 2) + (size_t)slab * (NL_BN * 128) + r * 128 +
                                ((c ^ (r & 7)) * 16);
       } else {
         const int d = c0 + r;
@@ -654,14 +669,14 @@ nl_pack_kernel(const T* __restrict__ theta, const T* __restrict__ phi, const T* 
     const int r = q >> 3, c = q & 7;
     uint32_t w[4];
     uint8_t* dst;
-    if (which < 2) {  // row = position, chunk = 8 channels
+    if (rows_pos) {  // row = position, chunk = 8 channels
 #pragma unroll
       for (int e = 0; e < 4; ++e) w[e] = pack_bf16(tile[r][c * 8 + 2 * e], tile[r][c * 8 + 2 * e + 1]);
       const int prow = p0 + r;
       if (which == 0) {  // plain rows of D bf16: the attention kernel moves them to tensor memory itself
         dst = Qp + (((size_t)b * nqb * NL_BM + prow) * D + c0 + c * 8) * 2;
       } else {
-        dst = Kp + ((size_t)b * nkb + pb) * ((size_t)NL_BN * D * 2) + (size_t)slab * (NL_BN * 128) + r * 128 +
+        dst = KVp + ((size_t)b * nkb + pb) * ((size_t)NL_BN * D * 2) + (size_t)slab * (NL_BN * 128) + r * 128 +
               ((c ^ (r & 7)) * 16);
       }
     } else {  // row = channel, chunk = 8 positions
