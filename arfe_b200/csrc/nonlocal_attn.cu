@@ -38,6 +38,8 @@
 // Arithmetic: operands rounded to bf16 (round to nearest even), products exact, fp32 accumulation in
 // the tensor core, fp32 softmax with exp2; tolerance against the fp32 reference is the bf16 one of
 // north_star (1e-2), written in tests/test_nonlocal_gpu.py.
+#include <cuda.h>
+#include <string.h>
 #include <cuda_bf16.h>
 
 #include "launch.h"
@@ -215,6 +217,16 @@ __device__ __forceinline__ void nl_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// 3-D tensor-map copy (TMA proper): box (64 channels, 64 positions, 1 image) of a [B][HW][D] bf16 tensor,
+// written with the 128-byte swizzle the MMA descriptors expect; positions beyond HW are zero-filled.
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // Phase-skip knob of the -DARFE_PROFILE build (scripts/nonlocal_knobs.py): 1 no K / V copies after the
 // first two steps, 2 no softmax arithmetic, 4 no MMAs.  Folds to false in the shipped library.
 #ifdef ARFE_PROFILE
@@ -237,9 +249,14 @@ __device__ __forceinline__ void nl_store1<__nv_bfloat16>(__nv_bfloat16* p, float
 constexpr int NL_SOFTMAX_WARPS = 8;  // two per TMEM lane quadrant: each takes half of the 64 key columns
 constexpr int NL_THREADS = (NL_SOFTMAX_WARPS + 3) * 32;  // + MMA issuer, K loader, V loader
 
-template <int D, typename OutT>
+// TM = false: Qp / Kp / Vp are the packed operands of nl_pack_kernel (tiles by 1-D bulk copies).
+// TM = true : the inputs are bf16 channels-last already ([B][HW][D] rows): Qp is theta itself, and the K / V
+//             tiles come straight from phi / g through tensor maps (cp.async.bulk.tensor, hardware swizzle,
+//             zero fill past HW) -- no packing pass at all.
+template <int D, typename OutT, bool TM>
 __global__ void __launch_bounds__(NL_THREADS, 1)
 nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, const uint8_t* __restrict__ Vp,
+               const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                OutT* __restrict__ y, float* __restrict__ part_o, float* __restrict__ part_ml,
                int* __restrict__ counters, int HW, int nqb, int nkb, int nsplit, float sl2, int out_cl, int dbg) {
   using C = NlCfg<D>;
@@ -281,8 +298,15 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
           mbar_arrive(&bars[B_KFULL + s]);
         } else {
           mbar_arrive_expect_tx(&bars[B_KFULL + s], C::K_BYTES);
-          bulk_g2s(smem + C::OFF_K + s * C::K_BYTES, Kp + ((size_t)b * nkb + (kb_lo + it)) * C::K_BYTES, C::K_BYTES,
-                   &bars[B_KFULL + s]);
+          if constexpr (TM) {
+#pragma unroll
+            for (int sl = 0; sl < C::SLABS; ++sl)
+              tma_load_3d(smem + C::OFF_K + s * C::K_BYTES + sl * (NL_BN * 128), &tm_k, sl * 64, (kb_lo + it) * NL_BN, b,
+                          &bars[B_KFULL + s]);
+          } else {
+            bulk_g2s(smem + C::OFF_K + s * C::K_BYTES, Kp + ((size_t)b * nkb + (kb_lo + it)) * C::K_BYTES, C::K_BYTES,
+                     &bars[B_KFULL + s]);
+          }
         }
       }
       __syncwarp();
@@ -297,8 +321,15 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
           mbar_arrive(&bars[B_VFULL + s]);
         } else {
           mbar_arrive_expect_tx(&bars[B_VFULL + s], C::V_BYTES);
-          bulk_g2s(smem + C::OFF_V + s * C::V_BYTES, Vp + ((size_t)b * nkb + (kb_lo + it)) * C::V_BYTES, C::V_BYTES,
-                   &bars[B_VFULL + s]);
+          if constexpr (TM) {
+#pragma unroll
+            for (int sl = 0; sl < C::SLABS; ++sl)
+              tma_load_3d(smem + C::OFF_V + s * C::V_BYTES + sl * (NL_BN * 128), &tm_v, sl * 64, (kb_lo + it) * NL_BN, b,
+                          &bars[B_VFULL + s]);
+          } else {
+            bulk_g2s(smem + C::OFF_V + s * C::V_BYTES, Vp + ((size_t)b * nkb + (kb_lo + it)) * C::V_BYTES, C::V_BYTES,
+                     &bars[B_VFULL + s]);
+          }
         }
       }
       __syncwarp();
@@ -362,14 +393,17 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
     const uint32_t pair_bar = 1 + quad;  // named barrier of the two warps of a quadrant
     float m_ref = 0.f, l = 0.f;          // m_ref in units of the raw logits
     {  // this row's half of theta (bf16 pairs) into tensor memory: the A operand of every Q K^T
-      const uint4* q_src = reinterpret_cast<const uint4*>(Qp + (((size_t)b * nqb + qb) * NL_BM + row) * (D * 2) +
-                                                          half * D);
+      // packed: rows padded with zeros to whole query blocks; TM: theta itself, rows past HW read as zero
+      const int qrow = qb * NL_BM + row;
+      const bool qok = !TM || qrow < HW;
+      const uint4* q_src = reinterpret_cast<const uint4*>(
+          Qp + (TM ? ((size_t)b * HW + (qok ? qrow : 0)) : (((size_t)b * nqb + qb) * NL_BM + row)) * (D * 2) + half * D);
 #pragma unroll
       for (int ch = 0; ch < D / 128; ++ch) {
         uint32_t qv[32];
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
-          const uint4 t = __ldg(q_src + ch * 8 + v);
+          const uint4 t = qok ? __ldg(q_src + ch * 8 + v) : make_uint4(0u, 0u, 0u, 0u);
           qv[4 * v] = t.x; qv[4 * v + 1] = t.y; qv[4 * v + 2] = t.z; qv[4 * v + 3] = t.w;
         }
         tmem_st32(tmem_q + lane_base + half * (D / 4) + ch * 32, qv);
@@ -378,7 +412,7 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
         uint32_t qv[16];
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-          const uint4 t = __ldg(q_src + v);
+          const uint4 t = qok ? __ldg(q_src + v) : make_uint4(0u, 0u, 0u, 0u);
           qv[4 * v] = t.x; qv[4 * v + 1] = t.y; qv[4 * v + 2] = t.z; qv[4 * v + 3] = t.w;
         }
         tmem_st16(tmem_q + lane_base + half * 16, qv);
@@ -713,16 +747,44 @@ NlLayout nl_layout(int B, int HW, int D, int nsplit) {
   return a;
 }
 
-template <int D, typename OutT>
-cudaError_t nl_launch_attn(const NlLayout& a, uint8_t* ws, OutT* y, int B, int HW, int nsplit, float sl2, int out_cl,
-                           cudaStream_t stream) {
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// [B][HW][D] bf16 rows -> boxes of 64 channels x 64 positions, 128-byte swizzle, zero fill out of bounds
+bool make_tile_map(CUtensorMap* tm, const void* base, int B, int HW, int D) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)HW, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)HW * D * 2};
+  const cuuint32_t box[3] = {64, (cuuint32_t)NL_BN, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int D, typename OutT, bool TM>
+cudaError_t nl_launch_attn(const NlLayout& a, const uint8_t* q, const uint8_t* k, const uint8_t* v, const CUtensorMap& tk,
+                           const CUtensorMap& tv, uint8_t* ws, OutT* y, int B, int HW, int nsplit, float sl2,
+                           int out_cl, cudaStream_t stream) {
   using C = NlCfg<D>;
-  cudaError_t e = cudaFuncSetAttribute(nl_attn_kernel<D, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+  cudaError_t e = cudaFuncSetAttribute(nl_attn_kernel<D, OutT, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
   if (e != cudaSuccess) return e;
-  nl_attn_kernel<D, OutT><<<dim3(a.nqb, B, nsplit), NL_THREADS, C::SMEM, stream>>>(
-      ws, ws + a.off_k, ws + a.off_v, y, reinterpret_cast<float*>(ws + a.off_po),
-      reinterpret_cast<float*>(ws + a.off_pml), reinterpret_cast<int*>(ws + a.off_cnt), HW, a.nqb, a.nkb, nsplit, sl2,
-      out_cl, ARFE_KNOB_ENV("ARFE_NL_DBG", 0));
+  nl_attn_kernel<D, OutT, TM><<<dim3(a.nqb, B, nsplit), NL_THREADS, C::SMEM, stream>>>(
+      q, k, v, tk, tv, y, reinterpret_cast<float*>(ws + a.off_po), reinterpret_cast<float*>(ws + a.off_pml),
+      reinterpret_cast<int*>(ws + a.off_cnt), HW, a.nqb, a.nkb, nsplit, sl2, out_cl, ARFE_KNOB_ENV("ARFE_NL_DBG", 0));
   return cudaGetLastError();
 }
 
@@ -731,21 +793,36 @@ cudaError_t nl_run(const void* theta, const void* phi, const void* g, void* y, i
                    float scale, void* workspace, int nsplit, cudaStream_t stream) {
   const NlLayout a = nl_layout(B, HW, D, nsplit);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const float sl2 = scale * 1.4426950408889634f;
+  T* yo = static_cast<T*>(y);
+  cudaError_t e;
+  CUtensorMap tk, tv;
+  memset(&tk, 0, sizeof(tk));
+  memset(&tv, 0, sizeof(tv));
+  // bf16 channels-last inputs are already what the kernel reads: theta rows directly, phi / g tiles through
+  // tensor maps; only the arrival counters of the key-range merge need a reset
+  if (sizeof(T) == 2 && in_cl && (reinterpret_cast<uintptr_t>(phi) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(theta) & 15) == 0 && make_tile_map(&tk, phi, B, HW, D) && make_tile_map(&tv, g, B, HW, D)) {
+    if (nsplit > 1 && (e = cudaMemsetAsync(ws + a.off_cnt, 0, (size_t)B * a.nqb * 4, stream)) != cudaSuccess) return e;
+    const uint8_t* q = static_cast<const uint8_t*>(theta);
+    switch (D) {
+      case 64: return nl_launch_attn<64, T, true>(a, q, nullptr, nullptr, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
+      case 128: return nl_launch_attn<128, T, true>(a, q, nullptr, nullptr, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
+      case 256: return nl_launch_attn<256, T, true>(a, q, nullptr, nullptr, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
+      default: return cudaErrorNotSupported;
+    }
+  }
   const int pbs = a.nqb * 2 > a.nkb ? a.nqb * 2 : a.nkb;
   nl_pack_kernel<T><<<dim3(pbs, D / 64, 3 * B), 256, 0, stream>>>(
       static_cast<const T*>(theta), static_cast<const T*>(phi), static_cast<const T*>(g), ws, ws + a.off_k,
       ws + a.off_v, HW, D, in_cl, a.nqb, a.nkb, reinterpret_cast<int*>(ws + a.off_cnt), B * a.nqb);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  const float sl2 = scale * 1.4426950408889634f;
-  T* yo = static_cast<T*>(y);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
   switch (D) {
-    case 64: e = nl_launch_attn<64, T>(a, ws, yo, B, HW, nsplit, sl2, in_cl, stream); break;
-    case 128: e = nl_launch_attn<128, T>(a, ws, yo, B, HW, nsplit, sl2, in_cl, stream); break;
-    case 256: e = nl_launch_attn<256, T>(a, ws, yo, B, HW, nsplit, sl2, in_cl, stream); break;
+    case 64: return nl_launch_attn<64, T, false>(a, ws, ws + a.off_k, ws + a.off_v, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
+    case 128: return nl_launch_attn<128, T, false>(a, ws, ws + a.off_k, ws + a.off_v, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
+    case 256: return nl_launch_attn<256, T, false>(a, ws, ws + a.off_k, ws + a.off_v, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
     default: return cudaErrorNotSupported;
   }
-  return e;
 }
 
 }  // namespace

@@ -412,7 +412,9 @@ int arfe_fpn_backward_fused(const void* const* douts, int douts_f32,
  * ARFE_NHWC (y has the layout of the inputs and is what the reference's
  * `y.permute(0, 2, 1).contiguous().reshape(n, D, h, w)` holds); D = inter_channels
  * in {64, 128, 256}.  Operands are rounded to bf16, accumulation and softmax are
- * fp32: results agree with the fp32 reference to bf16 accuracy (1e-2).
+ * fp32: results agree with the fp32 reference to bf16 accuracy (1e-2).  bf16
+ * ARFE_NHWC inputs (16-byte aligned) are read in place through tensor maps; any
+ * other combination is converted into bf16 tiles in the workspace first.
  * nsplit >= 1 slices the key range over several CTAs per 128-query block
  * (arfe_nonlocal_default_split: enough to fill the SMs of the current device);
  * workspace: arfe_nonlocal_workspace_bytes(B, HW, D, nsplit) bytes, 1024-byte
