@@ -356,13 +356,17 @@ def nonlocal_refine_block(dev, verify=True):
         return e0.elapsed_time(e1) / n
 
     t_f = timeit(lambda: A.nonlocal_attention(*ts))
+    tb = [t.bfloat16() for t in ts]          # bf16 channels-last: read in place through tensor maps, no packing pass
+    t_b = timeit(lambda: A.nonlocal_attention(*tb))
     t_l = timeit(lib_ref, 5)
     flops = 4.0 * B * (H * W) ** 2 * D
     peak, src = tensor_peak()
     out = {"shape": f"B={B} C={D} {H}x{W} ({H * W} positions), fp32 in/out, operands bf16, channels-last",
-           "fused_us": round(t_f * 1e3, 1), "library_fp32_us": round(t_l * 1e3, 1),
+           "fused_us": round(t_f * 1e3, 1), "fused_bf16_io_us": round(t_b * 1e3, 1), "library_fp32_us": round(t_l * 1e3, 1),
            "tflops": round(flops / (t_f * 1e-3) / 1e12, 1), "peak_tflops": peak, "peak_source": src,
-           "frac": round(flops / (t_f * 1e-3) / 1e12 / peak, 3), "gpu_launches_per_call": 2}
+           "frac": round(flops / (t_f * 1e-3) / 1e12 / peak, 3),
+           "frac_bf16_io": round(flops / (t_b * 1e-3) / 1e12 / peak, 3), "gpu_launches_per_call": 2,
+           "timing": "CUDA events around 20 calls through the Python wrapper (the call replayed as a CUDA graph is 3-4 us shorter)"}
     if verify:
         from oracle import arfe_oracle as O
         torch.set_num_threads(os.cpu_count() or 1)
