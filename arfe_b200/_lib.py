@@ -72,6 +72,7 @@ _SIGNATURES = {
                                     ctypes.c_size_t, _pp, _pp, c_void_p], c_int),
     "arfe_fpn_gate_conv_backward": ([_pp, _pp, _pp, _pp, _pp, _ip, _ip, c_int, c_int, c_int, c_int, c_int, _pp, _pp,
                                      _pp, _pp, _pp, c_void_p], c_int),
+    "arfe_nonlocal_backward_rows": ([c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_float, c_void_p], c_int),
     "arfe_nonlocal_default_split": ([c_int, c_int], c_int),
     "arfe_nonlocal_workspace_bytes": ([c_int, c_int, c_int, c_int], ctypes.c_size_t),
     "arfe_nonlocal_attention_forward": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

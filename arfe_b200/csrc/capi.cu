@@ -582,6 +582,16 @@ int arfe_fpn_gate_conv_backward(const void* const* feats, const float* const* w1
   return cuda_result(e, fn);
 }
 
+int arfe_nonlocal_backward_rows(const float* S, const float* dP, void* P_bf16, void* dS_bf16, int64_t rows, int n,
+                                float scale, void* stream) {
+  const char* fn = "arfe_nonlocal_backward_rows";
+  REQUIRE(rows >= 0 && n >= 1 && n <= 50 * 1024, ARFE_E_SHAPE, "%s: rows=%lld n=%d (n <= 51200)", fn, (long long)rows, n);
+  if (rows == 0) return ARFE_OK;
+  REQUIRE(S && dP && P_bf16 && dS_bf16, ARFE_E_NULL, "%s: NULL argument", fn);
+  DeviceGuard guard(S);
+  return cuda_result(arfe::launch_nonlocal_backward_rows(S, dP, P_bf16, dS_bf16, rows, n, scale, (cudaStream_t)stream), fn);
+}
+
 static int fill_fpn(const char* fn, arfe::FpnParams& p, const int32_t* H, const int32_t* W, int L,
                     int B, int C, int dtype, int layout) {
   int rc = check_common(fn, L, B, C, H, W, dtype, layout);

@@ -121,6 +121,9 @@ cudaError_t launch_nonlocal_attention(const void* theta, const void* phi, const 
                                       int dtype, int in_cl, float scale, void* workspace, int nsplit,
                                       cudaStream_t stream);
 
+cudaError_t launch_nonlocal_backward_rows(const float* S, const float* dP, void* Pb, void* dSb, long long rows, int n,
+                                          float scale, cudaStream_t stream);
+
 struct FpnParams {
   const void* feats[kMaxLevels];  // x_l (gather fwd / apply fwd) or dout_l (apply bwd)
   void* outs[kMaxLevels];         // out_l (apply fwd) or dx_l (gather bwd)

@@ -723,6 +723,58 @@ nl_pack_kernel(const T* __restrict__ theta, const T* __restrict__ phi, const T* 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Row pass of the attention BACKWARD (the GEMMs around it stay library calls): from the logits S and
+// dP = dY . g^T of one query row,
+//   P = softmax(scale * S),  delta = sum_q P dP,  dS = scale * P * (dP - delta)
+// P and dS leave as bf16 (the operands of the three GEMMs that follow); S and dP are read once.
+__global__ void __launch_bounds__(256)
+nl_bwd_rows_kernel(const float* __restrict__ S, const float* __restrict__ dP, __nv_bfloat16* __restrict__ Pb,
+                   __nv_bfloat16* __restrict__ dSb, int n, float scale) {
+  extern __shared__ float prow[];  // the row's exponentials
+  __shared__ float red[8];
+  const size_t base = (size_t)blockIdx.x * n;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float sl2 = scale * 1.4426950408889634f;
+  auto block_reduce = [&](float v, bool is_max) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float t = __shfl_xor_sync(0xffffffffu, v, o);
+      v = is_max ? fmaxf(v, t) : v + t;
+    }
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float r = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+    return r;
+  };
+  float mx = -INFINITY;
+  for (int i = tid; i < n; i += 256) {
+    const float v = __ldg(S + base + i);
+    prow[i] = v;
+    mx = fmaxf(mx, v);
+  }
+  mx = block_reduce(mx, true);
+  float sum = 0.f, dot = 0.f;
+  for (int i = tid; i < n; i += 256) {
+    const float e = exp2f((prow[i] - mx) * sl2);
+    prow[i] = e;
+    sum += e;
+    dot = fmaf(e, __ldg(dP + base + i), dot);
+  }
+  sum = block_reduce(sum, false);
+  dot = block_reduce(dot, false);
+  const float inv = 1.f / sum, delta = dot * inv;
+  for (int i = tid; i < n; i += 256) {
+    const float pv = prow[i] * inv;
+    Pb[base + i] = __float2bfloat16(pv);
+    dSb[base + i] = __float2bfloat16(scale * pv * (__ldg(dP + base + i) - delta));
+  }
+}
+
 struct NlLayout {
   int nqb, nkb, rows_pad;
   size_t q_bytes, k_bytes, v_bytes, part_o_bytes, part_ml_bytes;
@@ -826,6 +878,20 @@ cudaError_t nl_run(const void* theta, const void* phi, const void* g, void* y, i
 }
 
 }  // namespace
+
+cudaError_t launch_nonlocal_backward_rows(const float* S, const float* dP, void* Pb, void* dSb, long long rows, int n,
+                                          float scale, cudaStream_t stream) {
+  if (rows <= 0 || n <= 0) return cudaSuccess;
+  const size_t smem = (size_t)n * sizeof(float);
+  if (smem > 200 * 1024 || rows > 0x7fffffffll) return cudaErrorNotSupported;
+  cudaError_t e;
+  if (smem > 48 * 1024 &&
+      (e = cudaFuncSetAttribute(nl_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+    return e;
+  nl_bwd_rows_kernel<<<(unsigned)rows, 256, smem, stream>>>(S, dP, static_cast<__nv_bfloat16*>(Pb),
+                                                           static_cast<__nv_bfloat16*>(dSb), n, scale);
+  return cudaGetLastError();
+}
 
 int nonlocal_default_split(int B, int HW) {
   if (B < 1 || HW < 1) return 1;

@@ -842,13 +842,17 @@ class _NonLocalAttentionFunction(Function):
         ph = flat(phi).to(h)                                     # [B, D, HW]
         gx = flat(g).transpose(1, 2).to(h)                       # [B, HW, D]
         dyx = flat(dy).transpose(1, 2).to(h)                     # [B, HW, D]
-        p = torch.bmm(th, ph, out_dtype=f).mul_(ctx.scale).softmax(dim=-1)
-        pb = p.to(h)
-        dg = torch.bmm(pb.transpose(1, 2), dyx, out_dtype=f)     # [B, HW, D]
+        HW = H * W
+        s = torch.bmm(th, ph, out_dtype=f)                       # [B, HW, HW] logits
         dp = torch.bmm(dyx, gx.transpose(1, 2), out_dtype=f)     # [B, HW, HW]
-        delta = (dp * p).sum(dim=-1, keepdim=True)
-        ds = dp.sub_(delta).mul_(p).mul_(ctx.scale).to(h)
-        del p, dp
+        pb = torch.empty((B, HW, HW), dtype=h, device=s.device)
+        ds = torch.empty_like(pb)
+        # softmax, its Jacobian and the two bf16 casts in one pass over S and dP
+        rc = L.lib().arfe_nonlocal_backward_rows(s.data_ptr(), dp.data_ptr(), pb.data_ptr(), ds.data_ptr(),
+                                                 B * HW, HW, ctx.scale, L.stream_ptr(s.device))
+        L.check(rc, "arfe_nonlocal_backward_rows")
+        del s, dp
+        dg = torch.bmm(pb.transpose(1, 2), dyx, out_dtype=f)     # [B, HW, D]
         dth = torch.bmm(ds, ph.transpose(1, 2), out_dtype=f)     # [B, HW, D]
         dph = torch.bmm(th.transpose(1, 2), ds, out_dtype=f)     # [B, D, HW]
 

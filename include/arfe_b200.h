@@ -422,6 +422,13 @@ int arfe_fpn_backward_fused(const void* const* douts, int douts_f32,
  * nsplit > 1); it holds all device-side state of a call: concurrent calls on
  * different streams need different workspaces.  scale must be positive.
  * Forward only. */
+/* Row pass of the attention backward (the five GEMMs around it are library calls on bf16 operands): for
+ * every query row, from the logits S = theta_x . phi_x and dP = dY . g_x^T (fp32 [rows][n], read once),
+ *   P = softmax(scale * S),  dS = scale * P * (dP - sum_q P dP)     (non_local.py:65-69 differentiated)
+ * written as bf16 [rows][n].  n <= 51200. */
+int arfe_nonlocal_backward_rows(const float* S, const float* dP, void* P_bf16,
+                                void* dS_bf16, int64_t rows, int n, float scale,
+                                void* stream);
 int arfe_nonlocal_default_split(int B, int HW);
 size_t arfe_nonlocal_workspace_bytes(int B, int HW, int D, int nsplit);
 int arfe_nonlocal_attention_forward(const void* theta, const void* phi,

@@ -247,3 +247,20 @@ def test_neck_bf16_uses_fused_attention_and_gate_convs(oracle, cuda):
         scale = float(xo[l].grad.abs().max())
         assert float(d.norm() / xo[l].grad.norm()) <= 3e-2, (l, float(d.norm() / xo[l].grad.norm()))
         assert float((d > 3e-2 * scale).float().mean()) <= 5e-3, (l, float((d > 3e-2 * scale).float().mean()))
+
+
+def test_backward_row_pass(cuda):
+    """arfe_nonlocal_backward_rows: P = softmax(scale S) and dS = scale P (dP - sum P dP) per row, as bf16."""
+    from arfe_b200 import _lib as L
+    g = torch.Generator().manual_seed(13)
+    rows, n, scale = 37, 4200, 0.7
+    S = (torch.randn(rows, n, generator=g) * 3).to(cuda)
+    dP = torch.randn(rows, n, generator=g).to(cuda)
+    Pb = torch.empty(rows, n, dtype=torch.bfloat16, device=cuda)
+    dSb = torch.empty_like(Pb)
+    L.check(L.lib().arfe_nonlocal_backward_rows(S.data_ptr(), dP.data_ptr(), Pb.data_ptr(), dSb.data_ptr(), rows, n,
+                                                scale, L.stream_ptr(cuda)), "rows")
+    P = (S.double() * scale).softmax(-1)
+    dS = scale * P * (dP.double() - (P * dP.double()).sum(-1, keepdim=True))
+    assert float((Pb.double() - P).abs().max()) <= 4e-3 * float(P.max())
+    assert float((dSb.double() - dS).abs().max()) <= 4e-3 * float(dS.abs().max()) + 1e-9
