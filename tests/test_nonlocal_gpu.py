@@ -48,6 +48,8 @@ def _check(y, ts, oracle, use_scale=False, tol32=1e-2, tolb=3e-3):
     (2, 256, 25, 42, "nhwc", torch.bfloat16, 3),
     (1, 256, 16, 8, "nhwc", torch.float32, 2),     # exactly one 128-row query block, two key steps
     (3, 64, 20, 13, "nchw", torch.bfloat16, 4),
+    (1, 64, 3, 5, "nchw", torch.float32, 1),       # 15 positions (the coarsest level): half a key step is empty
+    (2, 64, 3, 5, "nhwc", torch.bfloat16, 1),      # the same through the tensor maps (box larger than the tensor)
     (1, 64, 7, 11, "nhwc", torch.bfloat16, 1),     # tensor-map path: one ragged tile (zero fill past HW)
     (2, 128, 9, 15, "nhwc", torch.bfloat16, 2),    # tensor-map path: 135 positions, key range split
 ])
