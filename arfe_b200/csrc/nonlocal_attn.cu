@@ -227,8 +227,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
       : "memory");
 }
 
-// Phase-skip knob of the -DARFE_PROFILE build (scripts/nonlocal_knobs.py): 1 no K / V copies after the
-// first two steps, 2 no softmax arithmetic, 4 no MMAs.  Folds to false in the shipped library.
+// Phase-skip knob of the -DARFE_PROFILE build (scripts/nonlocal_knobs.py), bits: 1 no K / V copies after
+// the ring's first fill, 2 no softmax work at all, 4 no MMAs, 16 no row-max exchange between the column
+// halves, 32 no ex2, 64 no P store, 128 no S load, 1024 two key steps only (fixed cost of a CTA).
+// Results are garbage (without MMAs S is stale: data-dependent paths like the O rescale then run at
+// random, so those timings say little).  Folds to false in the shipped library.
 #ifdef ARFE_PROFILE
 #define NL_DBG(bit) ((dbg & (bit)) != 0)
 #else

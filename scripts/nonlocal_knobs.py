@@ -1,6 +1,8 @@
 """Phase-skip decomposition of the fused NonLocal2D attention (profile build only):
 ARFE_NL_DBG bits: 1 no K / V copies, 2 no softmax arithmetic, 4 no MMAs, 16 no row-max exchange between the
-column halves, 32 no ex2, 64 no P store, 128 no S load.  Results are garbage."""
+column halves, 32 no ex2, 64 no P store, 128 no S load, 1024 two key steps only (the fixed cost of a CTA).
+Results are garbage.  The call is timed as a CUDA graph replay (the Python wrapper costs ~40 us of host time).
+usage: python scripts/nonlocal_knobs.py [bits ...]"""
 import os
 import subprocess
 import sys
