@@ -239,7 +239,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
 #endif
 
 // barrier indices
-enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 4, B_VFULL = 7, B_VEMPTY = 10, B_SFULL = 13, B_PFULL = 15, B_PVDONE = 17, B_COUNT = 19 };
+// One tcgen05.commit per MMA group (a commit costs the issuing warp several hundred cycles: four per step
+// paced the whole kernel): "Q K^T of step it done" (B_QKDONE) tells the softmax that S is ready AND the K
+// loader that the tile's slot is free; "P V of step it done" (B_PVDONE) frees the V slot and O.  Both are
+// rings of NL_EVT = 6 barriers (a multiple of the 2 S tiles and the 3 ring slots): completion it + 6 on a
+// barrier needs tile it + 6, which its loader fetches only after it has seen completion it + 3 > it -- no
+// waiter can be lapped, so the parity waits stay exact.
+constexpr int NL_EVT = 6;
+enum { B_QFULL = 0, B_KFULL = 1, B_VFULL = 4, B_PFULL = 7, B_QKDONE = 9, B_PVDONE = 15, B_COUNT = 21 };
 
 template <typename OutT>
 __device__ __forceinline__ void nl_store1(OutT* p, float v);
@@ -295,7 +302,8 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
     // ===== loader of the K ring (a slot is free once the Q K^T that read it has completed) =====
     for (int it = 0; it < n_it; ++it) {
       const int s = it % NL_STAGES;
-      nl_wait(&bars[B_KEMPTY + s], ((uint32_t)(it / NL_STAGES) & 1u) ^ 1u);
+      if (it >= NL_STAGES)  // the slot's previous tile: Q K^T of step it - NL_STAGES done
+        nl_wait(&bars[B_QKDONE + (it - NL_STAGES) % NL_EVT], (uint32_t)((it - NL_STAGES) / NL_EVT) & 1u);
       if (elect_one()) {
         if (NL_DBG(1) && it >= NL_STAGES) {
           mbar_arrive(&bars[B_KFULL + s]);
@@ -318,7 +326,8 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
     // ===== loader of the V ring (free once the P V that read it has completed) =====
     for (int it = 0; it < n_it; ++it) {
       const int s = it % NL_STAGES;
-      nl_wait(&bars[B_VEMPTY + s], ((uint32_t)(it / NL_STAGES) & 1u) ^ 1u);
+      if (it >= NL_STAGES)  // P V of step it - NL_STAGES done
+        nl_wait(&bars[B_PVDONE + (it - NL_STAGES) % NL_EVT], (uint32_t)((it - NL_STAGES) / NL_EVT) & 1u);
       if (elect_one()) {
         if (NL_DBG(1) && it >= NL_STAGES) {
           mbar_arrive(&bars[B_VFULL + s]);
@@ -357,8 +366,7 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
           const uint64_t bd = smem_desc_sw128(k_addr + (kk >> 2) * (NL_BN * 128) + (kk & 3) * 32);
           if (!NL_DBG(4)) tc_mma_ts(d_tmem, tmem_q + kk * 8, bd, idesc_qk, kk > 0);
         }
-        tc_commit(&bars[B_SFULL + (it % NL_SBUF)]);
-        tc_commit(&bars[B_KEMPTY + s]);
+        tc_commit(&bars[B_QKDONE + it % NL_EVT]);
       }
       __syncwarp();
     };
@@ -382,8 +390,7 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
                       NL_V_MN ? smem_desc_sw128_mn(v_addr + kk * (16 * 128), NL_BN * 128, 1024)  // 16 key rows on
                               : smem_desc_sw128(v_addr + kk * 32),
                       idesc_pv, (jt > 0 || kk > 0) ? 1u : 0u);
-        tc_commit(&bars[B_PVDONE + (jt & 1)]);
-        tc_commit(&bars[B_VEMPTY + s]);
+        tc_commit(&bars[B_PVDONE + jt % NL_EVT]);
       }
       __syncwarp();
     }
@@ -427,7 +434,7 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
     }
     for (int it = 0; it < n_it; ++it) {
       const int buf = it & 1, sbuf = it % NL_SBUF;
-      nl_wait(&bars[B_SFULL + sbuf], (uint32_t)(it / NL_SBUF) & 1u);
+      nl_wait(&bars[B_QKDONE + it % NL_EVT], (uint32_t)(it / NL_EVT) & 1u);
       tc_fence_after();
       if (NL_DBG(2)) {
         tc_fence_before();
@@ -465,7 +472,7 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
         const bool grow = (mx - m_ref) * sl2 > NL_RESCALE;
         if (__any_sync(0xffffffffu, grow)) {
           // O must be quiescent: P V of the previous step done (it was issued after this step's Q K^T)
-          nl_wait(&bars[B_PVDONE + ((it - 1) & 1)], (uint32_t)((it - 1) >> 1) & 1u);
+          nl_wait(&bars[B_PVDONE + (it - 1) % NL_EVT], (uint32_t)((it - 1) / NL_EVT) & 1u);
           tc_fence_after();
           const float m_new = grow ? mx : m_ref;
           const float alpha = fast_exp2((m_ref - m_new) * sl2);
@@ -514,7 +521,7 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
     xch[((n_it & 1) * 2 + half) * NL_BM + row] = l;
     asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
     l += xch[((n_it & 1) * 2 + (half ^ 1)) * NL_BM + row];
-    nl_wait(&bars[B_PVDONE + ((n_it - 1) & 1)], (uint32_t)((n_it - 1) >> 1) & 1u);
+    nl_wait(&bars[B_PVDONE + (n_it - 1) % NL_EVT], (uint32_t)((n_it - 1) / NL_EVT) & 1u);
     tc_fence_after();
     const int p = qb * NL_BM + row;
     const int NB = B * nqb, blk = b * nqb + qb;
