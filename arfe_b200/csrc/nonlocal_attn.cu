@@ -51,7 +51,7 @@ namespace {
 constexpr int NL_BM = 128;  // queries per CTA = UMMA M
 constexpr int NL_BN = 64;   // keys per step = one 128-byte swizzle row of bf16
 constexpr float NL_RESCALE = 8.f;  // log2 units a row maximum may grow before O is rescaled
-constexpr int NL_SBUF = 2;         // S tiles in tensor memory: Q K^T runs NL_SBUF - 1 steps ahead of P V
+constexpr int NL_SBUF_MAX = 4;     // S tiles in tensor memory (as many as fit): Q K^T runs SBUF - 1 steps ahead of P V
 constexpr int NL_STAGES = 3;       // K and V tile rings in shared memory
 // g (V) tiles are kept like phi (K) tiles -- rows = positions, 128-byte rows of 64 channels per slab -- and
 // handed to P V as an MN-major B operand (N = channels contiguous): no transposition of g anywhere.
@@ -69,7 +69,8 @@ struct NlCfg {
   static constexpr int SMEM = OFF_XCH + 2 * 2 * NL_BM * 4;  // the kernel has no static shared memory: base 1024-aligned
   // tensor memory columns: O (D, fp32) | Q (D / 2: bf16 pairs) | S0 .. (64 each; P_j is written over S_j)
   static constexpr int TM_Q = D, TM_S = D + D / 2;
-  static constexpr int TMEM_USED = TM_S + NL_SBUF * NL_BN;
+  static constexpr int SBUF = (512 - TM_S) / NL_BN < NL_SBUF_MAX ? (512 - TM_S) / NL_BN : NL_SBUF_MAX;  // 2 at D = 256
+  static constexpr int TMEM_USED = TM_S + SBUF * NL_BN;
   static constexpr int TMEM_COLS = TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512);
 };
 
@@ -246,7 +247,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
 // barrier needs tile it + 6, which its loader fetches only after it has seen completion it + 3 > it -- no
 // waiter can be lapped, so the parity waits stay exact.
 constexpr int NL_EVT = 6;
-enum { B_QFULL = 0, B_KFULL = 1, B_VFULL = 4, B_PFULL = 7, B_QKDONE = 9, B_PVDONE = 15, B_COUNT = 21 };
+enum { B_QFULL = 0, B_KFULL = 1, B_VFULL = 4, B_PFULL = 7, B_QKDONE = 11, B_PVDONE = 17, B_COUNT = 23 };
 
 template <typename OutT>
 __device__ __forceinline__ void nl_store1(OutT* p, float v);
@@ -283,7 +284,7 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
 
   if (tid == 0) {
     for (int i = 0; i < B_COUNT; ++i)
-      mbar_init(&bars[i], (i == B_PFULL || i == B_PFULL + 1 || i == B_QFULL) ? NL_SOFTMAX_WARPS : 1);
+      mbar_init(&bars[i], ((i >= B_PFULL && i < B_PFULL + NL_SBUF_MAX) || i == B_QFULL) ? NL_SOFTMAX_WARPS : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == NL_SOFTMAX_WARPS) {  // tensor memory: O | Q | S0 | S1
@@ -359,7 +360,7 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
       nl_wait(&bars[B_KFULL + s], (uint32_t)(it / NL_STAGES) & 1u);
       tc_fence_after();
       const uint32_t k_addr = smem_u32(smem + C::OFF_K + s * C::K_BYTES);
-      const uint32_t d_tmem = tmem_s + (uint32_t)(it % NL_SBUF) * NL_BN;
+      const uint32_t d_tmem = tmem_s + (uint32_t)(it % C::SBUF) * NL_BN;
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
@@ -370,17 +371,17 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
       }
       __syncwarp();
     };
-    for (int it = 0; it < NL_SBUF - 1 && it < n_it; ++it) issue_qk(it);
+    for (int it = 0; it < C::SBUF - 1 && it < n_it; ++it) issue_qk(it);
     for (int jt = 0; jt < n_it; ++jt) {
-      // the Q K^T NL_SBUF - 1 steps ahead goes first: its S tile held P_{jt-1}, which the P V issued
+      // the Q K^T SBUF - 1 steps ahead goes first: its S tile held P_{jt-1}, which the P V issued
       // in the previous round has consumed (the tensor pipe executes in issue order)
-      if (jt + NL_SBUF - 1 < n_it) issue_qk(jt + NL_SBUF - 1);
+      if (jt + C::SBUF - 1 < n_it) issue_qk(jt + C::SBUF - 1);
       // O += P_jt V_jt
       const int s = jt % NL_STAGES;
       nl_wait(&bars[B_VFULL + s], (uint32_t)(jt / NL_STAGES) & 1u);
-      nl_wait(&bars[B_PFULL + (jt & 1)], (uint32_t)(jt >> 1) & 1u);
+      nl_wait(&bars[B_PFULL + jt % C::SBUF], (uint32_t)(jt / C::SBUF) & 1u);
       tc_fence_after();
-      const uint32_t p_tmem = tmem_s + (uint32_t)(jt % NL_SBUF) * NL_BN;  // P_jt lies over S_jt
+      const uint32_t p_tmem = tmem_s + (uint32_t)(jt % C::SBUF) * NL_BN;  // P_jt lies over S_jt
       const uint32_t v_addr = smem_u32(smem + C::OFF_V + s * C::V_BYTES);
       if (elect_one()) {
 #pragma unroll
@@ -433,13 +434,13 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
       if (lane == 0) mbar_arrive(&bars[B_QFULL]);
     }
     for (int it = 0; it < n_it; ++it) {
-      const int buf = it & 1, sbuf = it % NL_SBUF;
+      const int buf = it & 1, sbuf = it % C::SBUF;
       nl_wait(&bars[B_QKDONE + it % NL_EVT], (uint32_t)(it / NL_EVT) & 1u);
       tc_fence_after();
       if (NL_DBG(2)) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[B_PFULL + buf]);
+        if (lane == 0) mbar_arrive(&bars[B_PFULL + sbuf]);
         continue;
       }
       uint32_t sr[32];
@@ -515,7 +516,7 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[B_PFULL + buf]);
+      if (lane == 0) mbar_arrive(&bars[B_PFULL + sbuf]);
     }
     // epilogue: total row sum, then this warp's half of the channels
     xch[((n_it & 1) * 2 + half) * NL_BM + row] = l;

@@ -107,7 +107,8 @@ def run_time():
     torch.backends.cuda.matmul.allow_tf32 = False
     for case in [(2, 256, 50, 84, "nchw", "f32", 1, "random", 1.0), (2, 256, 50, 84, "nchw", "f32", 2, "random", 1.0),
                  (2, 256, 50, 84, "nhwc", "f32", 2, "random", 1.0), (2, 256, 50, 84, "nhwc", "bf16", 2, "random", 1.0),
-                 (8, 256, 25, 42, "nchw", "f32", 2, "random", 1.0)]:
+                 (8, 256, 25, 42, "nchw", "f32", 2, "random", 1.0),
+                 (2, 128, 50, 84, "nhwc", "bf16", 2, "random", 1.0), (2, 128, 50, 84, "nhwc", "bf16", 1, "random", 1.0)]:
         (theta, phi, gx), nsplit = make(case)
         for _ in range(3):
             A.nonlocal_attention(theta, phi, gx, 1.0, nsplit)
