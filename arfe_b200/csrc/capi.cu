@@ -554,6 +554,8 @@ int arfe_nonlocal_attention_forward(const void* theta, const void* phi, const vo
   REQUIRE(nsplit >= 1 && nsplit <= 8 && nsplit <= (HW + 63) / 64, ARFE_E_SHAPE, "%s: nsplit=%d", fn, nsplit);
   REQUIRE(theta && phi && g && y && workspace, ARFE_E_NULL, "%s: NULL argument", fn);
   REQUIRE(aligned(workspace, 1024), ARFE_E_ALIGN, "%s: workspace must be 1024-byte aligned", fn);
+  REQUIRE(aligned(theta, 16) && aligned(phi, 16) && aligned(g, 16) && aligned(y, 16), ARFE_E_ALIGN,
+          "%s: theta, phi, g, y must be 16-byte aligned", fn);
   REQUIRE(workspace_bytes >= arfe::nonlocal_workspace_bytes(B, HW, D, nsplit), ARFE_E_SHAPE, "%s: workspace too small", fn);
   DeviceGuard guard(workspace);
   return cuda_result(arfe::launch_nonlocal_attention(theta, phi, g, y, B, HW, D, dtype, layout == ARFE_NHWC, scale,

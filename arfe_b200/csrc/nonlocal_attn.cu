@@ -13,7 +13,8 @@
 //                      swizzle (16-byte chunk c of row r stored at chunk c ^ (r & 7)), one contiguous
 //                      blob per tile, so the attention kernel fetches a K or V tile with a single bulk
 //                      copy (cp.async.bulk, no tensor map) straight into place.
-//                        Qp [B][nqb * 128 rows][D]                    theta as plain bf16 rows (goes to TMEM)
+//                        theta is not packed: the attention kernel reads it in place (any layout / type),
+//                        converts and writes it to tensor memory
 //                        Kp [B][nkb][D/64 slabs][ 64 rows][128 B]     phi,   rows = positions
 //                        Vp [B][nkb][D/64 slabs][ 64 rows][128 B]     g, same layout: P V takes it MN-major
 //  nl_attn_kernel      one CTA = 128 query positions of one image (x one slice of the keys when the
@@ -256,6 +257,13 @@ __device__ __forceinline__ void nl_store1<float>(float* p, float v) { *p = v; }
 template <>
 __device__ __forceinline__ void nl_store1<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
 
+template <typename T>
+__device__ __forceinline__ float nl_to_float(T v);
+template <>
+__device__ __forceinline__ float nl_to_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float nl_to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
 // ------------------------------------------------------------------------------------------------
 constexpr int NL_SOFTMAX_WARPS = 8;  // two per TMEM lane quadrant: each takes half of the 64 key columns
 constexpr int NL_THREADS = (NL_SOFTMAX_WARPS + 3) * 32;  // + MMA issuer, K loader, V loader
@@ -403,30 +411,42 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
     const int row = quad * 32 + lane;  // 0..127
     const uint32_t pair_bar = 1 + quad;  // named barrier of the two warps of a quadrant
     float m_ref = 0.f, l = 0.f;          // m_ref in units of the raw logits
-    {  // this row's half of theta (bf16 pairs) into tensor memory: the A operand of every Q K^T
-      // packed: rows padded with zeros to whole query blocks; TM: theta itself, rows past HW read as zero
+    {  // this row's half of theta as bf16 pairs into tensor memory: the A operand of every Q K^T.  theta is
+      // read in place (Qp = theta, `OutT` elements in the layout `out_cl` says): thread = (query row, half
+      // of the channels); rows past HW are zero
       const int qrow = qb * NL_BM + row;
-      const bool qok = !TM || qrow < HW;
-      const uint4* q_src = reinterpret_cast<const uint4*>(
-          Qp + (TM ? ((size_t)b * HW + (qok ? qrow : 0)) : (((size_t)b * nqb + qb) * NL_BM + row)) * (D * 2) + half * D);
+      const bool qok = qrow < HW;
+      constexpr int QC = D / 4;  // 32-bit columns (bf16 pairs) per thread
+      const OutT* th = reinterpret_cast<const OutT*>(Qp);
 #pragma unroll
-      for (int ch = 0; ch < D / 128; ++ch) {
-        uint32_t qv[32];
-#pragma unroll
-        for (int v = 0; v < 8; ++v) {
-          const uint4 t = qok ? __ldg(q_src + ch * 8 + v) : make_uint4(0u, 0u, 0u, 0u);
-          qv[4 * v] = t.x; qv[4 * v + 1] = t.y; qv[4 * v + 2] = t.z; qv[4 * v + 3] = t.w;
-        }
-        tmem_st32(tmem_q + lane_base + half * (D / 4) + ch * 32, qv);
-      }
-      if (D == 64) {  // 16 columns per half
+      for (int c0 = 0; c0 < QC; c0 += 16) {
         uint32_t qv[16];
+        if (!qok) {
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const uint4 t = qok ? __ldg(q_src + v) : make_uint4(0u, 0u, 0u, 0u);
-          qv[4 * v] = t.x; qv[4 * v + 1] = t.y; qv[4 * v + 2] = t.z; qv[4 * v + 3] = t.w;
+          for (int v = 0; v < 16; ++v) qv[v] = 0u;
+        } else if (out_cl) {  // [B][HW][D]: this thread's 32 channels are contiguous
+          const OutT* src = th + ((size_t)b * HW + qrow) * D + half * (D / 2) + c0 * 2;
+          if constexpr (sizeof(OutT) == 2) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const uint4 t = __ldg(reinterpret_cast<const uint4*>(src) + v);
+              qv[4 * v] = t.x; qv[4 * v + 1] = t.y; qv[4 * v + 2] = t.z; qv[4 * v + 3] = t.w;
+            }
+          } else {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(src) + v);
+              qv[2 * v] = pack_bf16(t.x, t.y);
+              qv[2 * v + 1] = pack_bf16(t.z, t.w);
+            }
+          }
+        } else {  // [B][D][HW]: lanes = consecutive positions, channels HW apart
+          const OutT* src = th + ((size_t)b * D + half * (D / 2) + c0 * 2) * HW + qrow;
+#pragma unroll
+          for (int v = 0; v < 16; ++v)
+            qv[v] = pack_bf16(nl_to_float(__ldg(src + (size_t)(2 * v) * HW)), nl_to_float(__ldg(src + (size_t)(2 * v + 1) * HW)));
         }
-        tmem_st16(tmem_q + lane_base + half * 16, qv);
+        tmem_st16(tmem_q + lane_base + half * QC + c0, qv);
       }
       tmem_wait_st();
       tc_fence_before();
@@ -635,13 +655,6 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
 // Operand packing: a 64-position x 64-channel tile through shared memory, out as 16-byte chunks of
 // 8 bf16 along the contraction axis (channels for theta / phi, positions for g), swizzled.
 template <typename T>
-__device__ __forceinline__ float nl_to_float(T v);
-template <>
-__device__ __forceinline__ float nl_to_float<float>(float v) { return v; }
-template <>
-__device__ __forceinline__ float nl_to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
-
-template <typename T>
 __global__ void __launch_bounds__(256)
 nl_pack_kernel(const T* __restrict__ theta, const T* __restrict__ phi, const T* __restrict__ g,
                uint8_t* __restrict__ Qp, uint8_t* __restrict__ Kp, uint8_t* __restrict__ Vp, int HW, int D, int in_cl,
@@ -649,9 +662,9 @@ nl_pack_kernel(const T* __restrict__ theta, const T* __restrict__ phi, const T* 
   __shared__ float tile[64][65];  // [position][channel]
   if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)  // arrival counters of the key-range merge
     for (int i = threadIdx.x; i < ncounters; i += blockDim.x) counters[i] = 0;
-  const int which = blockIdx.z % 3, b = blockIdx.z / 3;
+  const int which = 1 + blockIdx.z % 2, b = blockIdx.z / 2;  // 1: phi, 2: g (theta is read in place by the attention kernel)
   const int pb = blockIdx.x, slab = blockIdx.y;
-  if (which == 0 ? pb >= nqb * 2 : pb >= nkb) return;
+  if (pb >= nkb) return;
   const T* src = which == 0 ? theta : (which == 1 ? phi : g);
   const int p0 = pb * 64, c0 = slab * 64;
   const bool rows_pos = which < 2 || NL_V_MN;  // tile rows = positions, chunks = 8 channels
@@ -796,7 +809,7 @@ NlLayout nl_layout(int B, int HW, int D, int nsplit) {
   a.nqb = (HW + NL_BM - 1) / NL_BM;
   a.nkb = (HW + NL_BN - 1) / NL_BN;
   a.rows_pad = a.nqb * NL_BM;
-  a.q_bytes = (size_t)B * a.nqb * NL_BM * D * 2;
+  a.q_bytes = 0;  // theta is read in place
   a.k_bytes = (size_t)B * a.nkb * NL_BN * D * 2;
   a.v_bytes = a.k_bytes;
   a.part_o_bytes = nsplit > 1 ? (size_t)nsplit * B * a.rows_pad * D * 4 : 0;
@@ -875,15 +888,15 @@ cudaError_t nl_run(const void* theta, const void* phi, const void* g, void* y, i
       default: return cudaErrorNotSupported;
     }
   }
-  const int pbs = a.nqb * 2 > a.nkb ? a.nqb * 2 : a.nkb;
-  nl_pack_kernel<T><<<dim3(pbs, D / 64, 3 * B), 256, 0, stream>>>(
+  nl_pack_kernel<T><<<dim3(a.nkb, D / 64, 2 * B), 256, 0, stream>>>(
       static_cast<const T*>(theta), static_cast<const T*>(phi), static_cast<const T*>(g), ws, ws + a.off_k,
       ws + a.off_v, HW, D, in_cl, a.nqb, a.nkb, reinterpret_cast<int*>(ws + a.off_cnt), B * a.nqb);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  const uint8_t* qsrc = static_cast<const uint8_t*>(theta);
   switch (D) {
-    case 64: return nl_launch_attn<64, T, false>(a, ws, ws + a.off_k, ws + a.off_v, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
-    case 128: return nl_launch_attn<128, T, false>(a, ws, ws + a.off_k, ws + a.off_v, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
-    case 256: return nl_launch_attn<256, T, false>(a, ws, ws + a.off_k, ws + a.off_v, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
+    case 64: return nl_launch_attn<64, T, false>(a, qsrc, ws + a.off_k, ws + a.off_v, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
+    case 128: return nl_launch_attn<128, T, false>(a, qsrc, ws + a.off_k, ws + a.off_v, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
+    case 256: return nl_launch_attn<256, T, false>(a, qsrc, ws + a.off_k, ws + a.off_v, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
     default: return cudaErrorNotSupported;
   }
 }
