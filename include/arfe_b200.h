@@ -412,9 +412,10 @@ int arfe_fpn_backward_fused(const void* const* douts, int douts_f32,
  * ARFE_NHWC (y has the layout of the inputs and is what the reference's
  * `y.permute(0, 2, 1).contiguous().reshape(n, D, h, w)` holds); D = inter_channels
  * in {64, 128, 256}.  Operands are rounded to bf16, accumulation and softmax are
- * fp32: results agree with the fp32 reference to bf16 accuracy (1e-2).  bf16
- * ARFE_NHWC inputs (16-byte aligned) are read in place through tensor maps; any
- * other combination is converted into bf16 tiles in the workspace first.
+ * fp32: results agree with the fp32 reference to bf16 accuracy (1e-2).  All
+ * four tensors 16-byte aligned.  theta is always read in place; bf16 ARFE_NHWC
+ * phi / g are read in place too (tensor maps), any other combination of phi / g
+ * is first converted into bf16 tiles in the workspace.
  * nsplit >= 1 slices the key range over several CTAs per 128-query block
  * (arfe_nonlocal_default_split: enough to fill the SMs of the current device);
  * workspace: arfe_nonlocal_workspace_bytes(B, HW, D, nsplit) bytes, 1024-byte
@@ -422,13 +423,6 @@ int arfe_fpn_backward_fused(const void* const* douts, int douts_f32,
  * nsplit > 1); it holds all device-side state of a call: concurrent calls on
  * different streams need different workspaces.  scale must be positive.
  * Forward only. */
-/* Row pass of the attention backward (the five GEMMs around it are library calls on bf16 operands): for
- * every query row, from the logits S = theta_x . phi_x and dP = dY . g_x^T (fp32 [rows][n], read once),
- *   P = softmax(scale * S),  dS = scale * P * (dP - sum_q P dP)     (non_local.py:65-69 differentiated)
- * written as bf16 [rows][n].  n <= 51200. */
-int arfe_nonlocal_backward_rows(const float* S, const float* dP, void* P_bf16,
-                                void* dS_bf16, int64_t rows, int n, float scale,
-                                void* stream);
 int arfe_nonlocal_default_split(int B, int HW);
 size_t arfe_nonlocal_workspace_bytes(int B, int HW, int D, int nsplit);
 int arfe_nonlocal_attention_forward(const void* theta, const void* phi,
@@ -436,6 +430,14 @@ int arfe_nonlocal_attention_forward(const void* theta, const void* phi,
                                     int dtype, int layout, float scale,
                                     int nsplit, void* workspace,
                                     size_t workspace_bytes, void* stream);
+
+/* Row pass of the attention backward (the five GEMMs around it are library calls on bf16 operands): for
+ * every query row, from the logits S = theta_x . phi_x and dP = dY . g_x^T (fp32 [rows][n], read once),
+ *   P = softmax(scale * S),  dS = scale * P * (dP - sum_q P dP)     (non_local.py:65-69 differentiated)
+ * written as bf16 [rows][n].  n <= 51200. */
+int arfe_nonlocal_backward_rows(const float* S, const float* dP, void* P_bf16,
+                                void* dS_bf16, int64_t rows, int n, float scale,
+                                void* stream);
 
 #ifdef __cplusplus
 }
