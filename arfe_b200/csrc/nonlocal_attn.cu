@@ -8,15 +8,15 @@
 //
 // What runs here (the 1x1 convolutions theta / phi / g / conv_out stay plain library GEMMs):
 //
-//  nl_pack_kernel      theta, phi, g (fp32 or bf16, NCHW or channels-last) -> bf16 operand tiles that
+//  nl_pack_kernel      phi, g (fp32 or bf16, NCHW or channels-last) -> bf16 operand tiles that
 //                      are already the shared-memory image the tensor core wants: K-major, 128-byte
 //                      swizzle (16-byte chunk c of row r stored at chunk c ^ (r & 7)), one contiguous
 //                      blob per tile, so the attention kernel fetches a K or V tile with a single bulk
 //                      copy (cp.async.bulk, no tensor map) straight into place.
 //                        theta is not packed: the attention kernel reads it in place (any layout / type),
 //                        converts and writes it to tensor memory
-//                        Kp [B][nkb][D/64 slabs][ 64 rows][128 B]     phi,   rows = positions
-//                        Vp [B][nkb][D/64 slabs][ 64 rows][128 B]     g, same layout: P V takes it MN-major
+//                        Kp, Vp [B][nkb][D/64 slabs][64 position rows][128 B]   channels-last inputs
+//                        Kp, Vp [B][nkb][D channel rows][128 B = 64 positions]   NCHW inputs
 //  nl_attn_kernel      one CTA = 128 query positions of one image (x one slice of the keys when the
 //                      key range is split to fill the SMs).  Warp roles:
 //                        warps 0-7  softmax, thread = (query row, half of the 64 key columns): S (TMEM) ->
@@ -54,9 +54,9 @@ constexpr int NL_BN = 64;   // keys per step = one 128-byte swizzle row of bf16
 constexpr float NL_RESCALE = 8.f;  // log2 units a row maximum may grow before O is rescaled
 constexpr int NL_SBUF_MAX = 4;     // S tiles in tensor memory (as many as fit): Q K^T runs SBUF - 1 steps ahead of P V
 constexpr int NL_STAGES = 3;       // K and V tile rings in shared memory
-// g (V) tiles are kept like phi (K) tiles -- rows = positions, 128-byte rows of 64 channels per slab -- and
-// handed to P V as an MN-major B operand (N = channels contiguous): no transposition of g anywhere.
-constexpr bool NL_V_MN = true;
+// phi (K) and g (V) tiles share one layout per input layout (rows = positions for channels-last inputs,
+// rows = channels for NCHW ones); the MMA takes one of them as a K-major and the other as an MN-major B
+// operand, so nothing is ever transposed.
 
 template <int D>
 struct NlCfg {
@@ -272,7 +272,7 @@ constexpr int NL_THREADS = (NL_SOFTMAX_WARPS + 3) * 32;  // + MMA issuer, K load
 // TM = true : the inputs are bf16 channels-last already ([B][HW][D] rows): Qp is theta itself, and the K / V
 //             tiles come straight from phi / g through tensor maps (cp.async.bulk.tensor, hardware swizzle,
 //             zero fill past HW) -- no packing pass at all.
-template <int D, typename OutT, bool TM>
+template <int D, typename OutT, bool TM, bool POS>
 __global__ void __launch_bounds__(NL_THREADS, 1)
 nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, const uint8_t* __restrict__ Vp,
                const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
@@ -357,8 +357,11 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
     }
   } else if (warp == NL_SOFTMAX_WARPS) {
     // ===== MMA issuer: the whole warp walks the schedule (warp-uniform), one elected lane issues =====
-    constexpr uint32_t idesc_qk = idesc_bf16(NL_BM, NL_BN);
-    constexpr uint32_t idesc_pv = idesc_bf16(NL_BM, D, NL_V_MN);
+    // tiles with position rows (channels-last inputs): K is the K-major, V the MN-major B operand;
+    // tiles with channel rows (NCHW inputs): the other way round
+    constexpr bool pos_rows = POS;  // == (out_cl != 0): the layout of the inputs
+    constexpr uint32_t idesc_qk = idesc_bf16(NL_BM, NL_BN, !pos_rows);
+    constexpr uint32_t idesc_pv = idesc_bf16(NL_BM, D, pos_rows);
     nl_wait(&bars[B_QFULL], 0);  // Q sits in tensor memory (written by the softmax warps)
     tc_fence_after();
     // S[it % NL_SBUF] = Q K_it^T: A = Q from tensor memory (no shared-memory operand traffic for the
@@ -372,7 +375,8 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint64_t bd = smem_desc_sw128(k_addr + (kk >> 2) * (NL_BN * 128) + (kk & 3) * 32);
+          const uint64_t bd = pos_rows ? smem_desc_sw128(k_addr + (kk >> 2) * (NL_BN * 128) + (kk & 3) * 32)
+                                       : smem_desc_sw128_mn(k_addr + kk * (16 * 128), 1024, 1024);  // 16 channel rows on
           if (!NL_DBG(4)) tc_mma_ts(d_tmem, tmem_q + kk * 8, bd, idesc_qk, kk > 0);
         }
         tc_commit(&bars[B_QKDONE + it % NL_EVT]);
@@ -396,8 +400,8 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
         for (int kk = 0; kk < NL_BN / 16; ++kk)
           if (!NL_DBG(4))
             tc_mma_ts(tmem_o, p_tmem + kk * 8,
-                      NL_V_MN ? smem_desc_sw128_mn(v_addr + kk * (16 * 128), NL_BN * 128, 1024)  // 16 key rows on
-                              : smem_desc_sw128(v_addr + kk * 32),
+                      pos_rows ? smem_desc_sw128_mn(v_addr + kk * (16 * 128), NL_BN * 128, 1024)  // 16 key rows on
+                               : smem_desc_sw128(v_addr + kk * 32),
                       idesc_pv, (jt > 0 || kk > 0) ? 1u : 0u);
         tc_commit(&bars[B_PVDONE + jt % NL_EVT]);
       }
@@ -652,101 +656,62 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// Operand packing: a 64-position x 64-channel tile through shared memory, out as 16-byte chunks of
-// 8 bf16 along the contraction axis (channels for theta / phi, positions for g), swizzled.
+// Operand packing of phi and g (theta is read in place): fp32 / bf16 -> bf16 tiles of 64 positions in
+// the swizzled shared-memory image, straight from global memory (two 16-byte chunks per thread, no
+// staging, no transposition -- the MMA descriptors take either orientation):
+//   channels-last [B][HW][D]: tile = [D/64 slabs][64 position rows][128 B = 64 channels]
+//                             (phi: K-major operand of Q K^T; g: MN-major operand of P V)
+//   NCHW          [B][D][HW]: tile = [D channel rows][128 B = 64 positions]
+//                             (phi: MN-major operand of Q K^T; g: K-major operand of P V)
 template <typename T>
 __global__ void __launch_bounds__(256)
-nl_pack_kernel(const T* __restrict__ theta, const T* __restrict__ phi, const T* __restrict__ g,
-               uint8_t* __restrict__ Qp, uint8_t* __restrict__ Kp, uint8_t* __restrict__ Vp, int HW, int D, int in_cl,
-               int nqb, int nkb, int* __restrict__ counters, int ncounters) {
-  __shared__ float tile[64][65];  // [position][channel]
+nl_pack_kernel(const T* __restrict__ phi, const T* __restrict__ g, uint8_t* __restrict__ Kp, uint8_t* __restrict__ Vp,
+               int HW, int D, int in_cl, int nkb, int* __restrict__ counters, int ncounters) {
   if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)  // arrival counters of the key-range merge
     for (int i = threadIdx.x; i < ncounters; i += blockDim.x) counters[i] = 0;
-  const int which = 1 + blockIdx.z % 2, b = blockIdx.z / 2;  // 1: phi, 2: g (theta is read in place by the attention kernel)
+  const int which = blockIdx.z & 1, b = blockIdx.z >> 1;  // 0: phi, 1: g
   const int pb = blockIdx.x, slab = blockIdx.y;
-  if (pb >= nkb) return;
-  const T* src = which == 0 ? theta : (which == 1 ? phi : g);
+  const T* src = which == 0 ? phi : g;
+  uint8_t* tile = (which == 0 ? Kp : Vp) + ((size_t)b * nkb + pb) * ((size_t)NL_BN * D * 2);
   const int p0 = pb * 64, c0 = slab * 64;
-  const bool rows_pos = which < 2 || NL_V_MN;  // tile rows = positions, chunks = 8 channels
-  uint8_t* KVp = which == 1 ? Kp : Vp;
-  if (rows_pos == (in_cl != 0)) {
-    // the 8 elements of a chunk are contiguous in the source (theta / phi channels-last, g NCHW):
-    // straight from global memory, two chunks per thread, no staging
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int q = threadIdx.x + 256 * i, r = q >> 3, c = q & 7;
-      float v[8];
-      uint8_t* dst;
-      if (rows_pos) {
-        const int prow = p0 + r;
-        if (prow < HW) {
-          const T* sp = src + ((size_t)b * HW + prow) * D + c0 + c * 8;
-          if constexpr (sizeof(T) == 4) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(sp)), bb = __ldg(reinterpret_cast<const float4*>(sp) + 1);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bb.x; v[5] = bb.y; v[6] = bb.z; v[7] = bb.w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = nl_to_float(sp[e]);
-          }
+  for (int i = 0; i < 2; ++i) {
+    const int q = threadIdx.x + 256 * i, r = q >> 3, c = q & 7;
+    float v[8];
+    uint8_t* dst;
+    if (in_cl) {  // row r = position, chunk c = 8 channels
+      const int prow = p0 + r;
+      if (prow < HW) {
+        const T* sp = src + ((size_t)b * HW + prow) * D + c0 + c * 8;
+        if constexpr (sizeof(T) == 4) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(sp)), bb = __ldg(reinterpret_cast<const float4*>(sp) + 1);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bb.x; v[5] = bb.y; v[6] = bb.z; v[7] = bb.w;
         } else {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+          for (int e = 0; e < 8; ++e) v[e] = nl_to_float(sp[e]);
         }
-        dst = which == 0 ? Qp + (((size_t)b * nqb * NL_BM + prow) * D + c0 + c * 8) * 2
-                         : KVp + ((size_t)b * nkb + pb) * ((size_t)NL_BN * D * 2) + (size_t)slab * (NL_BN * 128) + r * 128 +
-                               ((c ^ (r & 7)) * 16);
       } else {
-        const int d = c0 + r;
-        const T* sp = src + ((size_t)b * D + d) * HW;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int pp = p0 + c * 8 + e;
-          v[e] = pp < HW ? nl_to_float(__ldg(sp + pp)) : 0.f;
-        }
-        dst = Vp + ((size_t)b * nkb + pb) * ((size_t)D * NL_BN * 2) + (size_t)d * 128 + ((c ^ (d & 7)) * 16);
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
       }
-      *reinterpret_cast<uint4*>(dst) =
-          make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-    }
-    return;
-  }
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-  if (in_cl) {  // [B][HW][D]: channels contiguous
-    for (int pl = ty; pl < 64; pl += 4) {
-      const int p = p0 + pl;
-      tile[pl][tx] = p < HW ? nl_to_float(src[((size_t)b * HW + p) * D + c0 + tx]) : 0.f;
-    }
-  } else {  // [B][D][HW]: positions contiguous
-    for (int cl = ty; cl < 64; cl += 4) {
-      const int p = p0 + tx;
-      tile[tx][cl] = p < HW ? nl_to_float(src[((size_t)b * D + c0 + cl) * HW + p]) : 0.f;
-    }
-  }
-  __syncthreads();
-  for (int q = threadIdx.x; q < 512; q += 256) {
-    const int r = q >> 3, c = q & 7;
-    uint32_t w[4];
-    uint8_t* dst;
-    if (rows_pos) {  // row = position, chunk = 8 channels
-#pragma unroll
-      for (int e = 0; e < 4; ++e) w[e] = pack_bf16(tile[r][c * 8 + 2 * e], tile[r][c * 8 + 2 * e + 1]);
-      const int prow = p0 + r;
-      if (which == 0) {  // plain rows of D bf16: the attention kernel moves them to tensor memory itself
-        dst = Qp + (((size_t)b * nqb * NL_BM + prow) * D + c0 + c * 8) * 2;
-      } else {
-        dst = KVp + ((size_t)b * nkb + pb) * ((size_t)NL_BN * D * 2) + (size_t)slab * (NL_BN * 128) + r * 128 +
-              ((c ^ (r & 7)) * 16);
-      }
-    } else {  // row = channel, chunk = 8 positions
-#pragma unroll
-      for (int e = 0; e < 4; ++e) w[e] = pack_bf16(tile[c * 8 + 2 * e][r], tile[c * 8 + 2 * e + 1][r]);
+      dst = tile + (size_t)slab * (NL_BN * 128) + r * 128 + ((c ^ (r & 7)) * 16);
+    } else {  // row d = channel, chunk c = 8 positions
       const int d = c0 + r;
-      dst = Vp + ((size_t)b * nkb + pb) * ((size_t)D * NL_BN * 2) + (size_t)d * 128 + ((c ^ (d & 7)) * 16);
+      const T* sp = src + ((size_t)b * D + d) * HW;
+      const int pp0 = p0 + c * 8;
+      if (sizeof(T) == 4 && (HW & 3) == 0 && pp0 + 8 <= HW) {  // rows 16-byte aligned: two vector loads
+        const float4 a = __ldg(reinterpret_cast<const float4*>(sp + pp0)), bb = __ldg(reinterpret_cast<const float4*>(sp + pp0) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bb.x; v[5] = bb.y; v[6] = bb.z; v[7] = bb.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = pp0 + e < HW ? nl_to_float(__ldg(sp + pp0 + e)) : 0.f;
+      }
+      dst = tile + (size_t)d * 128 + ((c ^ (d & 7)) * 16);
     }
-    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(dst) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
   }
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // Row pass of the attention BACKWARD (the GEMMs around it stay library calls): from the logits S and
@@ -851,14 +816,14 @@ bool make_tile_map(CUtensorMap* tm, const void* base, int B, int HW, int D) {
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int D, typename OutT, bool TM>
+template <int D, typename OutT, bool TM, bool POS>
 cudaError_t nl_launch_attn(const NlLayout& a, const uint8_t* q, const uint8_t* k, const uint8_t* v, const CUtensorMap& tk,
                            const CUtensorMap& tv, uint8_t* ws, OutT* y, int B, int HW, int nsplit, float sl2,
                            int out_cl, cudaStream_t stream) {
   using C = NlCfg<D>;
-  cudaError_t e = cudaFuncSetAttribute(nl_attn_kernel<D, OutT, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+  cudaError_t e = cudaFuncSetAttribute(nl_attn_kernel<D, OutT, TM, POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
   if (e != cudaSuccess) return e;
-  nl_attn_kernel<D, OutT, TM><<<dim3(a.nqb, B, nsplit), NL_THREADS, C::SMEM, stream>>>(
+  nl_attn_kernel<D, OutT, TM, POS><<<dim3(a.nqb, B, nsplit), NL_THREADS, C::SMEM, stream>>>(
       q, k, v, tk, tv, y, reinterpret_cast<float*>(ws + a.off_po), reinterpret_cast<float*>(ws + a.off_pml),
       reinterpret_cast<int*>(ws + a.off_cnt), HW, a.nqb, a.nkb, nsplit, sl2, out_cl, ARFE_KNOB_ENV("ARFE_NL_DBG", 0));
   return cudaGetLastError();
@@ -882,21 +847,24 @@ cudaError_t nl_run(const void* theta, const void* phi, const void* g, void* y, i
     if (nsplit > 1 && (e = cudaMemsetAsync(ws + a.off_cnt, 0, (size_t)B * a.nqb * 4, stream)) != cudaSuccess) return e;
     const uint8_t* q = static_cast<const uint8_t*>(theta);
     switch (D) {
-      case 64: return nl_launch_attn<64, T, true>(a, q, nullptr, nullptr, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
-      case 128: return nl_launch_attn<128, T, true>(a, q, nullptr, nullptr, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
-      case 256: return nl_launch_attn<256, T, true>(a, q, nullptr, nullptr, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
+      case 64: return nl_launch_attn<64, T, true, true>(a, q, nullptr, nullptr, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
+      case 128: return nl_launch_attn<128, T, true, true>(a, q, nullptr, nullptr, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
+      case 256: return nl_launch_attn<256, T, true, true>(a, q, nullptr, nullptr, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
       default: return cudaErrorNotSupported;
     }
   }
   nl_pack_kernel<T><<<dim3(a.nkb, D / 64, 2 * B), 256, 0, stream>>>(
-      static_cast<const T*>(theta), static_cast<const T*>(phi), static_cast<const T*>(g), ws, ws + a.off_k,
-      ws + a.off_v, HW, D, in_cl, a.nqb, a.nkb, reinterpret_cast<int*>(ws + a.off_cnt), B * a.nqb);
+      static_cast<const T*>(phi), static_cast<const T*>(g), ws + a.off_k, ws + a.off_v, HW, D, in_cl, a.nkb,
+      reinterpret_cast<int*>(ws + a.off_cnt), B * a.nqb);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   const uint8_t* qsrc = static_cast<const uint8_t*>(theta);
   switch (D) {
-    case 64: return nl_launch_attn<64, T, false>(a, qsrc, ws + a.off_k, ws + a.off_v, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
-    case 128: return nl_launch_attn<128, T, false>(a, qsrc, ws + a.off_k, ws + a.off_v, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
-    case 256: return nl_launch_attn<256, T, false>(a, qsrc, ws + a.off_k, ws + a.off_v, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
+    case 64: return in_cl ? nl_launch_attn<64, T, false, true>(a, qsrc, ws + a.off_k, ws + a.off_v, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream)
+                         : nl_launch_attn<64, T, false, false>(a, qsrc, ws + a.off_k, ws + a.off_v, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
+    case 128: return in_cl ? nl_launch_attn<128, T, false, true>(a, qsrc, ws + a.off_k, ws + a.off_v, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream)
+                         : nl_launch_attn<128, T, false, false>(a, qsrc, ws + a.off_k, ws + a.off_v, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
+    case 256: return in_cl ? nl_launch_attn<256, T, false, true>(a, qsrc, ws + a.off_k, ws + a.off_v, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream)
+                         : nl_launch_attn<256, T, false, false>(a, qsrc, ws + a.off_k, ws + a.off_v, tk, tv, ws, yo, B, HW, nsplit, sl2, in_cl, stream);
     default: return cudaErrorNotSupported;
   }
 }
