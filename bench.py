@@ -379,6 +379,49 @@ def nonlocal_refine_block(dev, verify=True):
     return out
 
 
+def neck_module_block(dev):
+    """Module level: WFPNDualSpatial (the reference's neck class) on the configs[1] pyramid, channels-last fp32,
+    forward and forward + backward, with the refine block's attention through the library and through the
+    fused tensor-core kernel -- what swapping the module into a detector buys, device-timed, inputs resident."""
+    import arfe_b200 as A
+    from arfe_b200 import workload as wl
+    shapes = wl.pyramid_shapes(800, 1344)
+    B, C = 2, 256
+    out = {"shape": f"B={B} C={C} 5 levels of 800x1344, fp32 channels-last; gather / gate convolutions / gated residual fused in both arms"}
+
+    def timeit(fn, n):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    g = torch.Generator().manual_seed(6)
+    xs = [torch.randn(B, C, h, w, generator=g).to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+          for h, w in shapes]
+    gs = [torch.randn_like(x) for x in xs]
+    m = A.WFPNDualSpatial(C, 5).to(dev).to(memory_format=torch.channels_last)
+    m.init_weights()
+    torch.nn.init.normal_(m.refine.conv_out.conv.weight, 0, 0.02)
+    for tag, fused in (("library_attention", False), ("fused_attention", True)):
+        m.refine.fused_attention = fused
+
+        def fwd():
+            with torch.no_grad():
+                return m(xs)
+
+        def fwdbwd():
+            torch.autograd.backward(list(m(xs)), gs)
+
+        out[tag] = {"forward_ms": round(timeit(fwd, 10), 3), "forward_backward_ms": round(timeit(fwdbwd, 5), 3)}
+    return out
+
+
 def other_configs_block(dev, peak):
     """Compact device-timed numbers of the other BASELINE configs (the full lines come
     from --config N): tracked by the driver round over round."""
@@ -533,7 +576,8 @@ def run_ours(args, rank, local_rank, world):
         if main_cfg and world == 1 and not args.no_other_configs:
             line["other_configs"] = other_configs_block(dev, peak)
             try:
-                line["next_rows"] = {"nonlocal_refine": nonlocal_refine_block(dev, verify=not args.no_verify)}
+                line["next_rows"] = {"nonlocal_refine": nonlocal_refine_block(dev, verify=not args.no_verify),
+                                     "neck_module": neck_module_block(dev)}
             except Exception as ex:  # pragma: no cover
                 line["next_rows"] = {"nonlocal_refine": {"error": str(ex)[:200]}}
         if main_cfg and world == 1 and not args.no_cpu_baseline:
