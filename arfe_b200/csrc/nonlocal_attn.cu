@@ -8,15 +8,20 @@
 //
 // What runs here (the 1x1 convolutions theta / phi / g / conv_out stay plain library GEMMs):
 //
-//  nl_pack_kernel      phi, g (fp32 or bf16, NCHW or channels-last) -> bf16 operand tiles that
-//                      are already the shared-memory image the tensor core wants: K-major, 128-byte
-//                      swizzle (16-byte chunk c of row r stored at chunk c ^ (r & 7)), one contiguous
-//                      blob per tile, so the attention kernel fetches a K or V tile with a single bulk
-//                      copy (cp.async.bulk, no tensor map) straight into place.
-//                        theta is not packed: the attention kernel reads it in place (any layout / type),
-//                        converts and writes it to tensor memory
-//                        Kp, Vp [B][nkb][D/64 slabs][64 position rows][128 B]   channels-last inputs
-//                        Kp, Vp [B][nkb][D channel rows][128 B = 64 positions]   NCHW inputs
+//  nl_pack_kernel      phi, g (fp32 or bf16, NCHW or channels-last) -> bf16 tiles of 64 positions that are
+//                      already the shared-memory image the tensor core wants (128-byte swizzle: 16-byte
+//                      chunk c of row r stored at chunk c ^ (r & 7)), one contiguous blob per tile, so the
+//                      attention kernel fetches a K or V tile with a single bulk copy (cp.async.bulk)
+//                      straight into place.  Tiles keep the orientation of the input -- the MMA takes a
+//                      B operand K-major or MN-major -- so nothing is transposed:
+//                        channels-last: [B][nkb][D/64 slabs][64 position rows][128 B = 64 channels]
+//                                       (phi: K-major operand of Q K^T, g: MN-major operand of P V)
+//                        NCHW:          [B][nkb][D channel rows][128 B = 64 positions]
+//                                       (phi: MN-major operand of Q K^T, g: K-major operand of P V)
+//                      bf16 channels-last inputs skip this pass: their tiles are read in place through
+//                      tensor maps (cp.async.bulk.tensor, hardware swizzle, zero fill past HW).
+//                      theta is never packed: the attention kernel reads it in place (any layout / type),
+//                      converts and writes it to tensor memory.
 //  nl_attn_kernel      one CTA = 128 query positions of one image (x one slice of the keys when the
 //                      key range is split to fill the SMs).  Warp roles:
 //                        warps 0-7  softmax, thread = (query row, half of the 64 key columns): S (TMEM) ->
@@ -31,7 +36,10 @@
 //                      memory every M128 N64 K16 instruction fetched 4 KB of Q for 32 cycles of math and
 //                      the tensor pipe ran at half speed.  Two S tiles live in TMEM (Q K^T of step j + 1
 //                      runs under the softmax of step j); P overwrites its own S tile, so the softmax
-//                      weights never touch shared memory; K and V rings are three tiles deep.
+//                      weights never touch shared memory (four S tiles, Q K^T three steps ahead, where
+//                      tensor memory has room: D <= 128); K and V rings are three tiles deep.  One
+//                      tcgen05.commit per MMA group: completion barriers in rings of six, shared by
+//                      the softmax warps and the tile loaders.
 //                      Key range split: each CTA leaves (O, max, sum) in the workspace and the CTA of a
 //                      query block that arrives last (an atomic counter; nobody waits) merges them and
 //                      writes y -- no second kernel.
