@@ -26,7 +26,9 @@ class NonLocal2D(nn.Module):
       False   the reference's two matmuls and softmax through the library;
       'auto'  (default) fused for bfloat16 activations, library for float32 -- an fp32 module keeps
               the reference's fp32 arithmetic unless the caller opts into bf16 operands
-              (``arfe_b200.optimize_detector(model, fused_attention=True)``).
+              (``arfe_b200.optimize_detector(model, fused_attention=True)``), or has already told
+              PyTorch that bf16 is acceptable inside float32 matmuls
+              (``torch.set_float32_matmul_precision('medium')``).
     The 1x1 convolutions stay library GEMMs either way."""
 
     def __init__(self, in_channels, reduction=2, use_scale=True, conv_cfg=None,
@@ -54,7 +56,7 @@ class NonLocal2D(nn.Module):
                 raise RuntimeError("NonLocal2D(fused_attention=True) needs CUDA float32/bfloat16 "
                                    "activations and inter_channels in (64, 128, 256)")
             return True
-        return ok and x.dtype == torch.bfloat16
+        return ok and (x.dtype == torch.bfloat16 or torch.get_float32_matmul_precision() == 'medium')
 
     def init_weights(self, std=0.01, zeros_init=True):
         for m in [self.g, self.theta, self.phi]:

@@ -200,6 +200,13 @@ def test_nonlocal_module_policy(cuda):
     mod = A.NonLocal2D(64, reduction=1, use_scale=False).to(cuda)
     x = torch.randn(1, 64, 6, 6, device=cuda)
     assert mod.fused_attention == 'auto' and not mod._use_fused(x) and mod._use_fused(x.bfloat16())
+    prec = torch.get_float32_matmul_precision()
+    try:  # PyTorch's own switch for "bf16 is fine inside float32 matmuls"
+        torch.set_float32_matmul_precision('medium')
+        assert mod._use_fused(x)
+    finally:
+        torch.set_float32_matmul_precision(prec)
+    assert not mod._use_fused(x)
     neck = A.WFPNDualSpatial(64, 5)
     A.optimize_detector(neck, fused_attention=True)
     assert neck.refine.fused_attention is True and neck.refine._use_fused(x)
