@@ -48,6 +48,7 @@
 // the tensor core, fp32 softmax with exp2; tolerance against the fp32 reference is the bf16 one of
 // north_star (1e-2), written in tests/test_nonlocal_gpu.py.
 #include <cuda.h>
+#include <cstdio>
 #include <string.h>
 #include <cuda_bf16.h>
 
@@ -246,6 +247,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
 #define NL_DBG(bit) ((dbg & (bit)) != 0)
 #else
 #define NL_DBG(bit) false
+#endif
+
+// Per-phase clock accounting of the softmax loop (profile build, ARFE_NL_DBG bit 65536): block (0,0,0),
+// warp 0, lane 0 prints the average cycles per step of each phase.
+#ifdef ARFE_PROFILE
+#define NL_T(i) do { if (NL_DBG(65536)) { const long long t_ = clock64(); tacc[i] += t_ - tlast; tlast = t_; } } while (0)
+#else
+#define NL_T(i) do { } while (0)
 #endif
 
 // barrier indices
@@ -465,10 +474,14 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_QFULL]);
     }
+#ifdef ARFE_PROFILE
+    long long tacc[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
+#endif
     for (int it = 0; it < n_it; ++it) {
       const int buf = it & 1, sbuf = it % C::SBUF;
       nl_wait(&bars[B_QKDONE + it % NL_EVT], (uint32_t)(it / NL_EVT) & 1u);
       tc_fence_after();
+      NL_T(0);
       if (NL_DBG(2)) {
         tc_fence_before();
         __syncwarp();
@@ -483,6 +496,7 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
 #pragma unroll
         for (int c = 0; c < 32; ++c) sr[c] = __float_as_uint((float)(c + it + lane) * 0.01f);
       }
+      NL_T(1);
       const int nvalid = HW - (kb_lo + it) * NL_BN - half * 32;  // columns of this thread that are real keys
       if (nvalid < 32) {
 #pragma unroll
@@ -499,6 +513,7 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
         mx = fmaxf(mx, xch[(buf * 2 + (half ^ 1)) * NL_BM + row]);
       }
+      NL_T(2);
       if (it == 0) {
         m_ref = mx;
       } else {
@@ -540,16 +555,24 @@ nl_attn_kernel(const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, c
         pw[e] = pack_bf16(p0, p1);
       }
       l += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
+      NL_T(3);
       if (!NL_DBG(64)) {
         tmem_st16(tmem_s + lane_base + sbuf * NL_BN + half * 16, pw);
         tmem_wait_st();
       } else if (pw[3] == 0x12345678u) {
         l += 1.f;
       }
+      NL_T(4);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_PFULL + sbuf]);
+      NL_T(5);
     }
+#ifdef ARFE_PROFILE
+    if (NL_DBG(65536) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0)
+      printf("softmax warp 0, cycles per step over %d steps: wait S %lld | ld S %lld | max + exchange %lld | rescale check + exp + pack %lld | st P %lld | fence + arrive %lld\n",
+             n_it, tacc[0] / n_it, tacc[1] / n_it, tacc[2] / n_it, tacc[3] / n_it, tacc[4] / n_it, tacc[5] / n_it);
+#endif
     // epilogue: total row sum, then this warp's half of the channels
     xch[((n_it & 1) * 2 + half) * NL_BM + row] = l;
     asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
